@@ -1,0 +1,159 @@
+"""Oracle (test infrastructure): generate tests/golden/* by running the REAL reference.
+
+Run in the authoring container only (needs /root/reference):
+
+    python -m oracle.make_golden [--only model|roi|post]
+
+Everything stored is an *output of reference code* (with the smp.Unet stub of
+oracle/refload.py standing in for the absent third-party UNet) on seeded inputs and the
+procedural weights of oracle/paramfill.py.  The tests regenerate the same inputs and
+weights and compare.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+from dataclasses import replace
+
+import numpy as np
+import torch
+
+from . import headport, paramfill, refload
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+# ----------------------------------------------------------------------------- seeded inputs (shared with tests)
+def synth_images(seed: int, b: int, h: int, w: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(b, 3, h, w, generator=g)
+
+
+def synth_rois(seed: int, n_images: int, per_image: int) -> torch.Tensor:
+    """SURVEY §8d box law: x1,y1~U[0,.5), w,h~U[.2,.5), x2=min(x1+w,1), y2=min(y1+h,1)."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    n = n_images * per_image
+    xy = torch.rand(n, 2, generator=g) * 0.5
+    wh = torch.rand(n, 2, generator=g) * 0.3 + 0.2
+    b = torch.arange(n_images, dtype=torch.float32).repeat_interleave(per_image)[:, None]
+    return torch.cat([b, xy, (xy + wh).clamp(max=1.0)], 1)
+
+
+def edge_rois(n_images: int) -> torch.Tensor:
+    """Edge cases of SURVEY §8d: x2=1/y2=1, zero-area ROI, ROI outside [0,1], reversed box."""
+    r = [[0, 0.0, 0.0, 1.0, 1.0], [n_images - 1, 0.25, 0.5, 0.25, 0.5], [0, -0.2, -0.1, 0.4, 0.6],
+         [n_images - 1, 0.6, 0.7, 1.3, 1.2], [0, 0.7, 0.6, 0.3, 0.2], [0, 0.1, 0.2, 0.9, 0.95]]
+    return torch.tensor(r, dtype=torch.float32)
+
+
+SMALL_CASES = {
+    # name: (cfg, image hw, rois)
+    "small_b0_bn_relu": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24)), (96, 128)),
+    "small_b0_bn_relu_exportscale": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24),
+                                             spatial_scale=(96.0, 128.0)), (96, 128)),
+    "small_b1_bc72": (replace(headport.PRESETS["b1_enhanced"], roi_size=(20, 16), mask_size=(40, 32)), (64, 96)),
+    "small_b7_bc96_d4": (replace(headport.PRESETS["b7_ultra"], roi_size=(32, 16), mask_size=(64, 32)), (64, 64)),
+    "small_b0_ln_silu_noatt": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24),
+                                       normalization_type="layernorm2d", activation_function="silu",
+                                       use_attention_module=False), (96, 128)),
+    "small_b0_bn_swish_beta": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24),
+                                       activation_function="swish", activation_beta=1.5), (96, 128)),
+    "small_b0_resize": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28)), (96, 128)),
+}
+
+_FULL_KEYS = ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_mask",
+              "distance_map", "roi_features", "roi_patches")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _run_reference(cfg: headport.PathConfig, images, rois, seed=0):
+    model = refload.build_reference_model(**cfg.factory_kwargs())
+    sd = paramfill.fill_state_dict(model.state_dict(), seed=seed)
+    model.load_state_dict(sd)
+    for ra in (model.roi_align_mask, model.roi_align_rgb):      # export_onnx_advanced.py:80-98 mutates these
+        ra.spatial_scale = cfg.spatial_scale
+        ra.spatial_scale_h, ra.spatial_scale_w = cfg.spatial_scale
+    with torch.no_grad():
+        logits, aux = model(images, rois)
+    return model, sd, logits, aux
+
+
+def make_model_goldens():
+    keys_json = {}
+    for name, (cfg, (h, w)) in SMALL_CASES.items():
+        images = synth_images(11, 2, h, w)
+        rois = torch.cat([synth_rois(11, 2, 2), edge_rois(2)], 0)
+        model, sd, logits, aux = _run_reference(cfg, images, rois)
+        out = {"logits": _np(logits), "full_image_logits_ch0": _np(aux["full_image_logits"][:, 0]),
+               "shared_features_sub": _np(aux["shared_features"][:, ::8]),
+               "fg_attention_sub": _np(aux["fg_attention"][:, ::8])}
+        for k in _FULL_KEYS:
+            if k in aux:
+                out[k] = _np(aux[k])
+        Dil = refload.ref_class_from_script("export_hierarchical_instance_peopleseg_onnx.py", "MaskDilationModule")
+        out["dilated1"] = _np(Dil(1)(logits))
+        out["dilated2"] = _np(Dil(2)(logits))
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **{k: v.astype(np.float32) for k, v in out.items()})
+        if "ln_" in name:
+            keys_json[name] = {k: list(v.shape) for k, v in sd.items()}
+        print(name, "logits", tuple(logits.shape), "absmax", float(logits.abs().max()),
+              "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
+
+    # state-dict key/shape contract of the three presets (+ the small cases above)
+    for pname, cfg in headport.PRESETS.items():
+        model = refload.build_reference_model(**cfg.factory_kwargs())
+        keys_json["preset_" + pname] = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLDEN, "state_dict_keys.json"), "w") as f:
+        json.dump(keys_json, f)
+
+    # BASELINE config 1: B0 std, 2x480x640, 8 ROIs (seeds: weights 0 / data 1)
+    cfg = headport.PRESETS["b0"]
+    images = synth_images(1, 2, 480, 640)
+    rois = synth_rois(1, 2, 4)
+    model, sd, logits, aux = _run_reference(cfg, images, rois)
+    out = {"logits": _np(logits), "full_image_logits_ch0_s2": _np(aux["full_image_logits"][:, 0, ::2, ::2]),
+           "shared_features_sub": _np(aux["shared_features"][:, ::8, ::4, ::4]),
+           "fg_attention_sub": _np(aux["fg_attention"][:, ::8, ::4, ::4])}
+    for k in ("bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_map", "roi_features"):
+        out[k] = _np(aux[k])
+    np.savez_compressed(os.path.join(GOLDEN, "cfg1_b0.npz"), **{k: v.astype(np.float32) for k, v in out.items()})
+    print("cfg1_b0 logits absmax", float(logits.abs().max()),
+          "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
+
+
+def make_roi_goldens():
+    """DynamicRoIAlign itself (hed/dynamic_roi_align.py) on random feature maps, all conventions."""
+    mod = refload.ref_import("dynamic_roi_align")
+    g = torch.Generator().manual_seed(21)
+    feat = torch.randn(3, 5, 37, 53, generator=g)
+    rois = torch.cat([synth_rois(21, 3, 3), edge_rois(3)], 0)
+    out = {"feat": _np(feat), "rois": _np(rois)}
+    for tag, scale, aligned, (oh, ow) in [("a640", 640.0, True, (16, 12)), ("ahw", (37.0, 53.0), True, (16, 12)),
+                                          ("u_hw", (37.0, 53.0), False, (7, 9)), ("a64", 64.0, True, (5, 3))]:
+        ra = mod.DynamicRoIAlign(spatial_scale=scale, sampling_ratio=2, aligned=aligned)
+        out[tag] = _np(ra(feat, rois, oh, ow))
+    np.savez_compressed(os.path.join(GOLDEN, "roi_align.npz"), **out)
+    print("roi_align goldens:", {k: v.shape for k, v in out.items()})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="all")
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if args.only in ("all", "roi"):
+        make_roi_goldens()
+    if args.only in ("all", "model"):
+        make_model_goldens()
+    if args.only in ("all", "post"):
+        from . import make_golden_post
+        make_golden_post.make_post_goldens(GOLDEN)
+
+
+if __name__ == "__main__":
+    main()

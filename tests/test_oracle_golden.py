@@ -1,0 +1,50 @@
+"""CPU: the oracle port (oracle/headport.py + oracle/effunet.py) against the golden vectors that
+oracle/make_golden.py produced by running the REAL reference modules (the pin of SURVEY §8c)."""
+import pytest
+import torch
+
+from oracle import headport
+from tests import common
+
+def _state(name):
+    cfg = common.SMALL_CASES[name][0] if name in common.SMALL_CASES else headport.PRESETS["b0"]
+    return common.procedural_state(common.shapes_for_case(name), weights_path=cfg.pretrained_weights_path)
+
+
+@pytest.mark.parametrize("name", list(common.SMALL_CASES))
+def test_port_matches_reference_small(name):
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    logits, aux = headport.forward(_state(name), images, rois, cfg)
+    assert common.rel_err(logits, g["logits"]) < 2e-5
+    assert common.rel_err(aux["full_image_logits"][:, 0], g["full_image_logits_ch0"]) < 2e-5
+    assert common.rel_err(aux["shared_features"][:, ::8], g["shared_features_sub"]) < 2e-5
+    assert common.rel_err(aux["fg_attention"][:, ::8], g["fg_attention_sub"]) < 2e-5
+    for k in ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_mask",
+              "distance_map", "roi_features", "roi_patches"):
+        assert common.rel_err(aux[k], g[k]) < 5e-5, k
+    for d in (1, 2):   # MaskDilationModule applied to the *golden* logits -> thresholds see identical inputs
+        out = headport.mask_dilation(g["logits"], d)
+        assert torch.equal(out, g[f"dilated{d}"])
+
+
+def test_port_matches_reference_cfg1():
+    cfg, images, rois = common.cfg1_inputs()
+    g = common.golden("cfg1_b0")
+    logits, aux = headport.forward(_state("preset_b0"), images, rois, cfg)
+    assert common.rel_err(logits, g["logits"]) < 2e-5
+    assert common.argmax_agreement(logits, g["logits"]) > 0.9999
+    assert common.rel_err(aux["full_image_logits"][:, 0, ::2, ::2], g["full_image_logits_ch0_s2"]) < 2e-5
+    for k in ("bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_map", "roi_features"):
+        assert common.rel_err(aux[k], g[k]) < 5e-5, k
+
+
+def test_roi_align_port_matches_reference():
+    g = common.golden("roi_align")
+    feat, rois = g["feat"], g["rois"]
+    for tag, (sh, sw), aligned, (oh, ow) in [("a640", (640.0, 640.0), True, (16, 12)), ("ahw", (37.0, 53.0), True, (16, 12)),
+                                             ("u_hw", (37.0, 53.0), False, (7, 9)), ("a64", (64.0, 64.0), True, (5, 3))]:
+        out = headport.roi_align(feat, rois, oh, ow, sh, sw, aligned)
+        assert (out - g[tag]).abs().max() < 2e-5, tag
+    # N = 0
+    assert headport.roi_align(feat, rois[:0], 4, 4, 37.0, 53.0).shape == (0, 5, 4, 4)
