@@ -1,0 +1,42 @@
+// Shared device/host helpers for the sm_100a kernels of the RGB hierarchical
+// instance-segmentation path.  Activations live in HBM as NHWC fp16 ("channel-last
+// rows"), optionally as a channel slice [c_off, c_off+C) of a wider buffer whose
+// per-pixel stride is Cs elements (Cs % 8 == 0 so that TMA strides are 16-byte
+// multiples).  Tails with <= 2 channels (logits) are kept in fp32.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HIS_OK 0
+#define HIS_ERR_INVALID_ARG (-1)
+#define HIS_ERR_UNSUPPORTED (-2)
+#define HIS_ERR_LAUNCH (-3)
+#define HIS_ERR_DRIVER (-4)
+#define HIS_ERR_NO_DEVICE (-5)
+
+enum HisAct { HIS_ACT_NONE = 0, HIS_ACT_RELU = 1, HIS_ACT_SILU = 2, HIS_ACT_SIGMOID = 3, HIS_ACT_SWISH = 4, HIS_ACT_GELU = 5 };
+enum HisResMode { HIS_RES_NONE = 0, HIS_RES_ADD = 1 /* before act */, HIS_RES_MUL = 2 /* after act */ };
+
+#define HIS_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return his_set_error(HIS_ERR_LAUNCH, cudaGetErrorString(e__)); \
+  } while (0)
+
+int his_set_error(int code, const char* msg);
+
+__device__ __forceinline__ float his_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float his_act(float v, int act, float beta) {
+  switch (act) {
+    case HIS_ACT_RELU: return fmaxf(v, 0.0f);
+    case HIS_ACT_SILU: return v * his_sigmoid(v);
+    case HIS_ACT_SIGMOID: return his_sigmoid(v);
+    case HIS_ACT_SWISH: return v * his_sigmoid(beta * v);
+    case HIS_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    default: return v;
+  }
+}
+
+static inline int his_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -1,0 +1,498 @@
+// Implicit-GEMM convolution on the Blackwell tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces the dense conv2d / conv_transpose2d(k2,s2) ATen calls of the reference head
+// (hed/advanced/hierarchical_segmentation_rgb.py:657-673, ..._refinement.py:37-39,479-523,
+// ..._unet.py:44-47,313-372) and of the EfficientNet-UNet 1x1 / decoder 3x3 convs.
+//
+// GEMM view: D[M=128 pixels, N=Cout tile] += A[M, K] * B[N, K]^T, K = taps * Cin.
+//  * A is never materialised: the M tile is a (bh x bw) rectangle of output pixels of one image
+//    (bh*bw == 128) and, for filter tap (dy,dx), the operand tile is the SAME rectangle of the
+//    NHWC fp16 input shifted by (dy-1,dx-1).  One 4-D TMA box load {64ch, bw, bh, 1} per
+//    (tap, 64-channel block) lands it in shared memory as 128 rows x 128 B in the canonical
+//    K-major SWIZZLE_128B UMMA layout; out-of-image coordinates are zero-filled by the TMA
+//    unit, which *is* the conv zero padding (and the channel tail padding).
+//  * B (weights) is pre-packed fp16 [group][tap][Cout_slab][Cin_pad], K-major, 2-D TMA tiles.
+//  * D accumulates in TMEM (fp32), double buffered (2 x block_n columns) so that the epilogue
+//    of tile i overlaps the MMAs of tile i+1.
+//  * Epilogue: tcgen05.ld -> y = act(acc*scale[c] + shift[c] (+res)) (*res) -> fp16 ->
+//    swizzled smem staging -> TMA store (clips partial tiles / channel tails).  The residual /
+//    multiplicand tile arrives through TMA into the same staging buffer.
+//  * conv_transpose k2s2 = 4 independent 1x1 GEMMs ("groups"), each scattered through its own
+//    strided output tensor map (pixel (2y+dy, 2x+dx)).
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over work items):
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // fp16 elements = 128 B = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kBBytesMax = 256 * kBlockK * 2;     // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax; // 48 KB
+constexpr int kStagingBytes = kBlockM * 64 * 2;   // 16 KB : 128 rows x 64 channels fp16
+constexpr int kNumStaging = 2;
+constexpr int kTmemCols = 512;
+constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct ConvGemmParams {
+  int n_img, H, W;
+  int bh, bw, tiles_x, tiles_y;
+  int ksize;            // 1 or 3
+  int kblocks_per_tap;  // ceil(Cin / 64)
+  int n_tiles, block_n; // N tiling of one (group, tap) slab
+  int groups;           // 1, or 4 for conv-transpose k2s2
+  int cout_slab;        // n_tiles * block_n  (rows of one slab in B, scale/shift length per group)
+  int num_work;
+  int act;
+  float act_beta;
+  int res_mode;
+  const float* scale;   // [cout_slab]
+  const float* shift;   // [cout_slab]
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for one swizzle atom along K) | [32,46) SBO>>4 (8 rows * 128 B)
+//   [46,48) version=1 | [61,64) layout: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n.
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 0u << 7;                       // a_format = F16
+  d |= 0u << 10;                      // b_format = F16
+  d |= (uint32_t)(n >> 3) << 17;      // n_dim
+  d |= (uint32_t)(kBlockM >> 4) << 24;  // m_dim
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct WorkItem { int img, y0, x0, n_tile, group; };
+
+__device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) {
+  WorkItem it;
+  it.n_tile = w % p.n_tiles; w /= p.n_tiles;
+  it.group = w % p.groups;   w /= p.groups;
+  int tx = w % p.tiles_x;    w /= p.tiles_x;
+  int ty = w % p.tiles_y;    w /= p.tiles_y;
+  it.img = w; it.y0 = ty * p.bh; it.x0 = tx * p.bw;
+  return it;
+}
+
+// ------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(256, 1)
+conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                       const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
+                       const __grid_constant__ CUtensorMap tmR, const ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base;
+  const uint32_t staging_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = staging_base + kNumStaging * kStagingBytes;
+  // barrier slots (8 B each): full[4] empty[4] tmem_full[2] tmem_empty[2] res_full[2]; then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 4 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to the aligned base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.ksize * p.ksize;
+  const int kiters = taps * p.kblocks_per_tap;
+  const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO0);
+    if (p.res_mode) prefetch_tmap(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); mbar_init(res_bar(a), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+      const WorkItem it = decode_work(p, w);
+      const int pad = p.ksize >> 1;
+      for (int k = 0; k < kiters; ++k) {
+        const int tap = k / p.kblocks_per_tap, cb = k - tap * p.kblocks_per_tap;
+        const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = stage_base + stage * kStageBytes, sb = sa + kABytes;
+        mbar_expect_tx(full_bar(stage), kABytes + b_bytes);
+        tma_load_4d(sa, &tmA, full_bar(stage), cb * kBlockK, it.x0 + dx, it.y0 + dy, it.img);
+        tma_load_2d(sb, &tmB, full_bar(stage), cb * kBlockK, (it.group * taps + tap) * p.cout_slab + it.n_tile * p.block_n);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = make_idesc_f16(p.block_n);
+    int stage = 0; uint32_t phase = 0; int iter = 0;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
+      const int acc = iter & 1; const uint32_t acc_phase = (iter >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int k = 0; k < kiters; ++k) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = stage_base + stage * kStageBytes, sb = sa + kABytes;
+        const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
+#pragma unroll
+        for (int kk = 0; kk < kBlockK / 16; ++kk)
+          umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+        umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+        if (k == kiters - 1) umma_commit(tfull_bar(acc));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int te = threadIdx.x - 128;           // 0..127 == output row of the tile == TMEM lane
+    const int q = warp & 3;                     // TMEM lane quarter this warp may touch
+    const int nchunks = (p.block_n + 63) >> 6;
+    int iter = 0; uint32_t cc = 0;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
+      const WorkItem it = decode_work(p, w);
+      const int acc = iter & 1; const uint32_t acc_phase = (iter >> 1) & 1;
+      const CUtensorMap* tmO = it.group == 0 ? &tmO0 : it.group == 1 ? &tmO1 : it.group == 2 ? &tmO2 : &tmO3;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int j = 0; j < nchunks; ++j, ++cc) {
+        const int b = cc & 1;
+        const uint32_t stg = staging_base + b * kStagingBytes;
+        const int ch0 = it.n_tile * p.block_n + j * 64;   // first output channel of this chunk
+        if (te == 0) {
+          tma_wait_read<1>();                    // the store that last read staging[b] has drained
+          if (p.res_mode) {
+            mbar_expect_tx(res_bar(b), kStagingBytes);
+            tma_load_4d(stg, &tmR, res_bar(b), ch0, it.x0, it.y0, it.img);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * 64);
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        if (j == nchunks - 1) {                  // accumulator fully read -> hand TMEM back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (p.res_mode) mbar_wait(res_bar(b), (cc >> 1) & 1);
+        uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = ch0 + i * 8;
+          uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ (te & 7)) << 4));
+          float r[8];
+          if (p.res_mode) {
+            const uint4 rv = *cell;
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
+          }
+          __half2 o[4];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float y0 = 0.f, y1 = 0.f;
+            if (c + e < p.cout_slab) {           // cout_slab is a multiple of 16 -> pairs never straddle
+              y0 = __uint_as_float(v[i * 8 + e]) * __ldg(p.scale + c + e) + __ldg(p.shift + c + e);
+              y1 = __uint_as_float(v[i * 8 + e + 1]) * __ldg(p.scale + c + e + 1) + __ldg(p.shift + c + e + 1);
+            }
+            if (p.res_mode == HIS_RES_ADD) { y0 += r[e]; y1 += r[e + 1]; }
+            y0 = his_act(y0, p.act, p.act_beta); y1 = his_act(y1, p.act, p.act_beta);
+            if (p.res_mode == HIS_RES_MUL) { y0 *= r[e]; y1 *= r[e + 1]; }
+            o[e >> 1] = __floats2half2_rn(y0, y1);
+          }
+          *cell = *reinterpret_cast<uint4*>(o);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (te == 0) {
+          tma_store_4d(tmO, stg, ch0, it.x0, it.y0, it.img);
+          tma_commit();
+        }
+      }
+    }
+    if (te == 0) tma_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)ptr;
+  }
+  return fn;
+}
+
+// NHWC fp16 activation slice -> 4-D map {C, W, H, N}; strides in elements of the *buffer*.
+int encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN,
+                   int box_c, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return his_set_error(HIS_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+    return his_set_error(HIS_ERR_INVALID_ARG, "activation slice is not 16-byte aligned (channel offset/stride must be multiples of 8)");
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128]; snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
+    return his_set_error(HIS_ERR_DRIVER, buf);
+  }
+  return HIS_OK;
+}
+
+int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return his_set_error(HIS_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  if (((uintptr_t)base & 15) || (strides[0] & 15)) return his_set_error(HIS_ERR_INVALID_ARG, "packed weights must be 16-byte aligned, K % 8 == 0");
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[128]; snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return his_set_error(HIS_ERR_DRIVER, buf);
+  }
+  return HIS_OK;
+}
+
+struct ConvGemmPlan {
+  CUtensorMap tmA, tmB, tmO[4], tmR;
+  ConvGemmParams p;
+  int grid;
+};
+
+int g_num_sms = 0;
+
+}  // namespace
+
+extern "C" {
+
+// See include/his_b200.h for the contract.
+int his_conv_gemm_tile_n(int cout, int* n_tiles, int* block_n) {
+  if (cout <= 0) return HIS_ERR_INVALID_ARG;
+  int c16 = (cout + 15) / 16 * 16;
+  if (c16 <= 256) { *n_tiles = 1; *block_n = c16; return HIS_OK; }
+  int nt = (c16 + 255) / 256;
+  int bn = ((c16 + nt - 1) / nt + 63) / 64 * 64;   // multi-tile: block_n % 64 == 0 so 64-wide store chunks never overlap
+  *n_tiles = (c16 + bn - 1) / bn; *block_n = bn;
+  return HIS_OK;
+}
+
+int his_conv_gemm_create(void** out_plan,
+                         const void* in, int n_img, int H, int W, int cin, int in_cs,
+                         const void* w_packed, int cin_pad,
+                         void* out, int cout, int out_cs,
+                         const void* res, int res_cs,
+                         const float* scale, const float* shift,
+                         int ksize, int transposed, int act, float act_beta, int res_mode) {
+  if (!out_plan || !in || !w_packed || !out || !scale || !shift) return his_set_error(HIS_ERR_INVALID_ARG, "null pointer");
+  if (!(ksize == 1 || ksize == 3) || (transposed && ksize != 1)) return his_set_error(HIS_ERR_UNSUPPORTED, "ksize must be 1 or 3 (transposed: k2s2 packed as 4 1x1 groups)");
+  if (res_mode != HIS_RES_NONE && !res) return his_set_error(HIS_ERR_INVALID_ARG, "res_mode set without residual tensor");
+  if (res_mode != HIS_RES_NONE && transposed) return his_set_error(HIS_ERR_UNSUPPORTED, "residual with transposed conv");
+  if ((in_cs % 8) || (out_cs % 8) || (cin_pad % 8) || cin_pad < cin) return his_set_error(HIS_ERR_INVALID_ARG, "channel strides must be multiples of 8");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return his_set_error(HIS_ERR_NO_DEVICE, "no CUDA device");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return his_set_error(HIS_ERR_NO_DEVICE, "no CUDA device");
+    if (prop.major != 10) return his_set_error(HIS_ERR_UNSUPPORTED, "conv_gemm_sm100 needs a compute-capability 10.x device (B200)");
+    g_num_sms = prop.multiProcessorCount;
+    if (cudaFuncSetAttribute(conv_gemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+      return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
+  }
+  ConvGemmPlan* pl = new ConvGemmPlan();
+  memset(pl, 0, sizeof(*pl));
+  ConvGemmParams& p = pl->p;
+  p.n_img = n_img; p.H = H; p.W = W; p.ksize = ksize;
+  // pick the 128-pixel rectangle with the least padded area
+  long long best = -1;
+  for (int bw = 1; bw <= 128; bw <<= 1) {
+    int bh = 128 / bw;
+    long long area = (long long)his_div_up(W, bw) * bw * his_div_up(H, bh) * bh;
+    if (best < 0 || area < best || (area == best && bw >= 8 && bw <= 32)) { best = area; p.bw = bw; p.bh = bh; }
+  }
+  p.tiles_x = his_div_up(W, p.bw); p.tiles_y = his_div_up(H, p.bh);
+  p.kblocks_per_tap = his_div_up(cin, kBlockK);
+  his_conv_gemm_tile_n(cout, &p.n_tiles, &p.block_n);
+  p.groups = transposed ? 4 : 1;
+  p.cout_slab = p.n_tiles * p.block_n;
+  p.num_work = n_img * p.tiles_y * p.tiles_x * p.n_tiles * p.groups;
+  p.act = act; p.act_beta = act_beta; p.res_mode = res_mode; p.scale = scale; p.shift = shift;
+  int taps = ksize * ksize;
+  int rc;
+  if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, kBlockK, p.bw, p.bh))) { delete pl; return rc; }
+  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, p.block_n))) { delete pl; return rc; }
+  if (!transposed) {
+    if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
+    pl->tmO[1] = pl->tmO[2] = pl->tmO[3] = pl->tmO[0];
+  } else {
+    for (int g = 0; g < 4; ++g) {
+      int dy = g >> 1, dx = g & 1;
+      const __half* base = (const __half*)out + ((long long)dy * 2 * W + dx) * out_cs;
+      if ((rc = encode_act_map(&pl->tmO[g], base, cout, W, H, n_img, 2LL * out_cs, 4LL * W * out_cs, 4LL * H * W * out_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
+    }
+  }
+  if (res_mode != HIS_RES_NONE) {
+    if ((rc = encode_act_map(&pl->tmR, res, cout, W, H, n_img, res_cs, (long long)W * res_cs, (long long)H * W * res_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
+  } else {
+    pl->tmR = pl->tmO[0];
+  }
+  pl->grid = p.num_work < g_num_sms ? p.num_work : g_num_sms;
+  *out_plan = pl;
+  return HIS_OK;
+}
+
+int his_conv_gemm_run(void* plan, void* stream) {
+  if (!plan) return his_set_error(HIS_ERR_INVALID_ARG, "null plan");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  if (pl->p.num_work == 0) return HIS_OK;
+  conv_gemm_sm100_kernel<<<pl->grid, 256, kSmemBytes, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2],
+                                                                            pl->tmO[3], pl->tmR, pl->p);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_conv_gemm_destroy(void* plan) {
+  delete (ConvGemmPlan*)plan;
+  return HIS_OK;
+}
+
+// Algorithmic FLOPs of one run (2*MAC over true channel counts are computed by the caller); this
+// returns the padded MMA work actually issued, for roofline bookkeeping.
+long long his_conv_gemm_issued_macs(void* plan) {
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  const ConvGemmParams& p = pl->p;
+  return (long long)p.num_work * kBlockM * p.block_n * (long long)(p.ksize * p.ksize * p.kblocks_per_tap * kBlockK);
+}
+
+}  // extern "C"

@@ -1,0 +1,733 @@
+// CUDA-core kernels of the path: Dynamic RoI Align gather, direct convolutions for the odd
+// shapes (Cin = 2/3, Cout <= 2 tails, stem, segmentation head), depthwise conv + BN + SiLU,
+// squeeze-excite / channel attention, spatial attention, pooling, resizes and the hierarchical
+// combine.  All are HBM-bound: coalesced channel-last accesses, 16-byte vectors where the channel
+// count allows, one pass per tensor.  Dense convolutions live in conv_gemm_sm100.cu.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+thread_local char g_err[256] = "";
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long long work, int per_block = kThreads) {
+  long long g = (work + per_block - 1) / per_block;
+  if (g > 148LL * 64) g = 148LL * 64;   // grid-stride loops; multiple of the SM count
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// block size that is a multiple of the number of 8-channel groups, so a thread keeps one group
+inline int threads_multiple_of(int cgs) {
+  if (cgs <= 0 || cgs > 1024) return 0;
+  return cgs <= kThreads ? cgs * (kThreads / cgs) : cgs;
+}
+
+// ------------------------------------------------------------------------------------ RoI Align
+// reference hed/dynamic_roi_align.py:56-171 (see oracle/headport.py:roi_align for the derivation).
+__device__ __forceinline__ float linspace01(int i, int n) {
+  if (n <= 1) return 0.0f;
+  const float step = __fdiv_rn(1.0f, (float)(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+__device__ __forceinline__ float roi_px(float lo, float hi, float g, int size, int aligned) {
+  const float f = __fadd_rn(lo, __fmul_rn(g, __fsub_rn(hi, lo)));
+  if (aligned) {
+    const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(f, (float)(size - 1)), 2.0f), 1.0f);
+    return __fmul_rn(__fdiv_rn(__fadd_rn(nrm, 1.0f), 2.0f), (float)(size - 1));
+  }
+  const float nrm = __fsub_rn(__fmul_rn(__fdiv_rn(f, (float)size), 2.0f), 1.0f);
+  return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nrm, 1.0f), (float)size), 1.0f), 2.0f);
+}
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(__ldg(p)); }
+
+// One thread per (roi, oy, ox); channels looped (C is 2 or 3 on the hot path).  Consecutive threads
+// walk ox, so the four taps of a warp fall on at most a few image rows (coalesced when the ROI is
+// sampled near unit stride).
+template <typename T>
+__global__ void roi_align_kernel(const T* __restrict__ feat, long long sN, long long sC, long long sH, long long sW, int B, int C,
+                                 int H, int W, const float* __restrict__ rois, int n_rois, int oh, int ow, float scale_h,
+                                 float scale_w, int aligned, __half* __restrict__ out_h, int out_cs, float* __restrict__ out_f) {
+  const long long total = (long long)n_rois * oh * ow;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % ow);
+    const int oy = (int)((idx / ow) % oh);
+    const int k = (int)(idx / ((long long)ow * oh));
+    const float* r = rois + 5 * k;
+    const int b = (int)r[0];
+    const float x1 = __fmul_rn(r[1], scale_w), y1 = __fmul_rn(r[2], scale_h);
+    const float x2 = __fmul_rn(r[3], scale_w), y2 = __fmul_rn(r[4], scale_h);
+    const float px = roi_px(x1, x2, linspace01(ox, ow), W, aligned);
+    const float py = roi_px(y1, y2, linspace01(oy, oh), H, aligned);
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const int ix = (int)fx0, iy = (int)fy0;
+    const float wx1 = px - fx0, wx0 = (fx0 + 1.0f) - px;
+    const float wy1 = py - fy0, wy0 = (fy0 + 1.0f) - py;
+    const bool okb = (b >= 0 && b < B) && isfinite(px) && isfinite(py);
+    const bool x0ok = okb && ix >= 0 && ix < W, x1ok = okb && ix + 1 >= 0 && ix + 1 < W;
+    const bool y0ok = iy >= 0 && iy < H, y1ok = iy + 1 >= 0 && iy + 1 < H;
+    for (int c = 0; c < C; ++c) {
+      const T* base = feat + (long long)(okb ? b : 0) * sN + (long long)c * sC;
+      float v = 0.0f;
+      if (x0ok && y0ok) v += ld_as_float(base + iy * sH + ix * sW) * (wx0 * wy0);
+      if (x1ok && y0ok) v += ld_as_float(base + iy * sH + (ix + 1) * sW) * (wx1 * wy0);
+      if (x0ok && y1ok) v += ld_as_float(base + (iy + 1) * sH + ix * sW) * (wx0 * wy1);
+      if (x1ok && y1ok) v += ld_as_float(base + (iy + 1) * sH + (ix + 1) * sW) * (wx1 * wy1);
+      if (out_h) out_h[idx * out_cs + c] = __float2half_rn(v);
+      if (out_f) out_f[(((long long)k * C + c) * oh + oy) * ow + ox] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ direct conv
+struct DirectConvParams {
+  const void* in; int in_fmt;          // 0: NHWC fp16 (stride in_cs), 1: NCHW fp32
+  const float* in_affine;              // optional [2*Cin]: x*a[c]+b[c] on in-bounds samples (input normalisation)
+  int N, H, W, Cin, in_cs;
+  const __half* w;                     // [kh][kw][Cin][Cout]
+  const float* scale; const float* shift;
+  int Cout, kh, kw, stride, pad, Ho, Wo;
+  int act; float act_beta; int res_mode;
+  const __half* res; int res_cs;
+  __half* out_h; int out_cs;           // NHWC fp16 slice (may be null)
+  float* out_f;                        // NCHW fp32 (may be null)
+};
+
+template <int COT>
+__global__ void direct_conv_kernel(const DirectConvParams p) {
+  const int groups = p.Cout / COT;
+  const long long total = (long long)p.N * p.Ho * p.Wo * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % groups);
+    long long pix = idx / groups;
+    const int ox = (int)(pix % p.Wo), oy = (int)((pix / p.Wo) % p.Ho), n = (int)(pix / ((long long)p.Wo * p.Ho));
+    const int co = cg * COT;
+    float acc[COT];
+#pragma unroll
+    for (int t = 0; t < COT; ++t) acc[t] = 0.0f;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int iy = oy * p.stride - p.pad + ky;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int ix = ox * p.stride - p.pad + kx;
+        if (ix < 0 || ix >= p.W) continue;
+        const __half* wrow = p.w + ((long long)(ky * p.kw + kx) * p.Cin) * p.Cout + co;
+        if (p.in_fmt == 0) {
+          const __half* ip = (const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs;
+          for (int ci = 0; ci < p.Cin; ++ci) {
+            const float x = __half2float(__ldg(ip + ci));
+            const __half* wp = wrow + (long long)ci * p.Cout;
+#pragma unroll
+            for (int t = 0; t < COT; ++t) acc[t] = fmaf(x, __half2float(__ldg(wp + t)), acc[t]);
+          }
+        } else {
+          const float* ip = (const float*)p.in + (long long)n * p.Cin * p.H * p.W + (long long)iy * p.W + ix;
+          for (int ci = 0; ci < p.Cin; ++ci) {
+            float x = __ldg(ip + (long long)ci * p.H * p.W);
+            if (p.in_affine) x = fmaf(x, __ldg(p.in_affine + ci), __ldg(p.in_affine + p.Cin + ci));
+            const __half* wp = wrow + (long long)ci * p.Cout;
+#pragma unroll
+            for (int t = 0; t < COT; ++t) acc[t] = fmaf(x, __half2float(__ldg(wp + t)), acc[t]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < COT; ++t) {
+      float y = acc[t] * __ldg(p.scale + co + t) + __ldg(p.shift + co + t);
+      float r = 0.0f;
+      if (p.res_mode) r = __half2float(p.res[pix * p.res_cs + co + t]);
+      if (p.res_mode == HIS_RES_ADD) y += r;
+      y = his_act(y, p.act, p.act_beta);
+      if (p.res_mode == HIS_RES_MUL) y *= r;
+      acc[t] = y;
+    }
+    if (p.out_h) {
+      __half* op = p.out_h + pix * p.out_cs + co;
+#pragma unroll
+      for (int t = 0; t < COT; ++t) op[t] = __float2half_rn(acc[t]);
+    }
+    if (p.out_f) {
+#pragma unroll
+      for (int t = 0; t < COT; ++t) p.out_f[(((long long)n * p.Cout + co + t) * p.Ho + oy) * p.Wo + ox] = acc[t];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ depthwise conv
+// NHWC fp16, 8 channels (16 B) per thread, fused BN scale/shift + activation, optional per-(n,c)
+// sums for the squeeze-excite pooling that follows (fp32 atomics, one per thread per channel after
+// a warp-level merge of threads that share the channel group is not possible in general -> the
+// block first reduces into shared memory).
+struct DwParams {
+  const __half* in; int N, H, W, C, in_cs;
+  const __half* w;            // [k*k][C]
+  const float* scale; const float* shift;
+  int k, stride, pad, Ho, Wo, act;
+  __half* out; int out_cs;
+  float* pool;                // [N][C] sums of the activated output (may be null)
+};
+
+__global__ void depthwise_kernel(const DwParams p) {
+  extern __shared__ float s_pool[];     // [C] partial sums of this block (one image per block-row)
+  const int cgs = p.C / 8;
+  const int n = blockIdx.y;
+  if (p.pool) { for (int c = threadIdx.x; c < p.C; c += blockDim.x) s_pool[c] = 0.0f; __syncthreads(); }
+  const long long per_img = (long long)p.Ho * p.Wo * cgs;
+  float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const int ox = (int)(pix % p.Wo), oy = (int)(pix / p.Wo);
+    const int c0 = cg * 8;
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
+    for (int ky = 0; ky < p.k; ++ky) {
+      const int iy = oy * p.stride - p.pad + ky;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kx = 0; kx < p.k; ++kx) {
+        const int ix = ox * p.stride - p.pad + kx;
+        if (ix < 0 || ix >= p.W) continue;
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs + c0));
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)(ky * p.k + kx) * p.C + c0));
+        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
+          acc[2 * e] = fmaf(xf.x, wf.x, acc[2 * e]);
+          acc[2 * e + 1] = fmaf(xf.y, wf.y, acc[2 * e + 1]);
+        }
+      }
+    }
+    __half2 o[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      float y0 = his_act(acc[e] * __ldg(p.scale + c0 + e) + __ldg(p.shift + c0 + e), p.act, 1.0f);
+      float y1 = his_act(acc[e + 1] * __ldg(p.scale + c0 + e + 1) + __ldg(p.shift + c0 + e + 1), p.act, 1.0f);
+      o[e >> 1] = __floats2half2_rn(y0, y1);
+      // pool what the next layer will actually read (the fp16-rounded value)
+      const float2 rf = __half22float2(o[e >> 1]);
+      psum[e] += rf.x; psum[e + 1] += rf.y;
+    }
+    *reinterpret_cast<uint4*>(p.out + ((long long)n * p.Ho * p.Wo + pix) * p.out_cs + c0) = *reinterpret_cast<uint4*>(o);
+  }
+  if (p.pool) {
+    // blockDim.x is a multiple of C/8 (host guarantees), so this thread always saw channel group threadIdx.x % cgs
+    const int c0 = (threadIdx.x % cgs) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_pool[c0 + e], psum[e]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) atomicAdd(p.pool + (long long)n * p.C + c, s_pool[c]);
+  }
+}
+
+// per-(n,c) sums of an NHWC fp16 tensor (ChannelAttentionModule's adaptive_avg_pool2d)
+__global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, int cs, float* __restrict__ pool) {
+  extern __shared__ float s_pool[];
+  const int n = blockIdx.y, cgs = C / 8;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_pool[c] = 0.0f;
+  __syncthreads();
+  const long long per_img = (long long)HW * cgs;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int my_cg = -1;
+  const bool fixed_cg = true;   // host launches blockDim.x as a multiple of C/8
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
+    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+    if (fixed_cg) {
+      my_cg = cg;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); atomicAdd(&s_pool[cg * 8 + 2 * e], f.x); atomicAdd(&s_pool[cg * 8 + 2 * e + 1], f.y); }
+    }
+  }
+  if (fixed_cg && my_cg >= 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_pool[my_cg * 8 + e], acc[e]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(pool + (long long)n * C + c, s_pool[c]);
+}
+
+// gate[n][c] = sigmoid(W2 * act(W1 * (pool[n]/HW) + b1) + b2): one block per image.
+__global__ void se_gate_kernel(const float* __restrict__ pool, float inv_hw, int C, int R, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int act,
+                               float act_beta, float* __restrict__ gate) {
+  extern __shared__ float sm[];      // [C] means, [R] hidden
+  float* mean = sm; float* hid = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(long long)n * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[(long long)r * C + c], mean[c], s);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[r] = his_act(s + (b1 ? b1[r] : 0.0f), act, act_beta);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = b2 ? b2[c] : 0.0f;
+    for (int r = 0; r < R; ++r) s = fmaf(w2[(long long)c * R + r], hid[r], s);
+    gate[(long long)n * C + c] = his_sigmoid(s);
+  }
+}
+
+// x[n,p,c] *= gate[n,c]  (in place or to another slice)
+__global__ void scale_channels_kernel(const __half* __restrict__ in, int in_cs, const float* __restrict__ gate, long long HW, int C,
+                                      long long total, __half* __restrict__ out, int out_cs) {
+  const int cgs = C / 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const long long n = pix / HW;
+    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * in_cs + cg * 8));
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    const float* g = gate + n * C + cg * 8;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(xh[e]);
+      xh[e] = __floats2half2_rn(f.x * __ldg(g + 2 * e), f.y * __ldg(g + 2 * e + 1));
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+  }
+}
+
+// ------------------------------------------------------------------------------------ pooling / resize
+__global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, __half* __restrict__ out, int out_cs) {
+  const int Ho = H / 2, Wo = W / 2, cgs = C / 8;
+  const long long total = (long long)N * Ho * Wo * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    const __half* base = in + ((long long)(n * H + 2 * oy) * W + 2 * ox) * in_cs + cg * 8;
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(base)), b = __ldg(reinterpret_cast<const uint4*>(base + in_cs));
+    uint4 c = __ldg(reinterpret_cast<const uint4*>(base + (long long)W * in_cs)), d = __ldg(reinterpret_cast<const uint4*>(base + (long long)(W + 1) * in_cs));
+    __half2* ah = reinterpret_cast<__half2*>(&a); const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    const __half2* ch = reinterpret_cast<const __half2*>(&c); const __half2* dh = reinterpret_cast<const __half2*>(&d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ah[e] = __hmax2(__hmax2(ah[e], bh[e]), __hmax2(ch[e], dh[e]));
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = a;
+  }
+}
+
+// nearest resize of an NHWC fp16 tensor into a channel slice (smp UnetDecoderBlock F.interpolate(mode="nearest"))
+__global__ void resize_nearest_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, int Ho, int Wo,
+                                      __half* __restrict__ out, int out_cs) {
+  const int cgs = C / 8;
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const long long total = (long long)N * Ho * Wo * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    const int iy = min((int)floorf(oy * sy), H - 1), ix = min((int)floorf(ox * sx), W - 1);
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) =
+        __ldg(reinterpret_cast<const uint4*>(in + ((long long)(n * H + iy) * W + ix) * in_cs + cg * 8));
+  }
+}
+
+// bilinear resize (align_corners=False, PyTorch upsample_bilinear2d source-index rule) of NCHW fp32
+__global__ void resize_bilinear_f32_kernel(const float* __restrict__ in, int NC, int H, int W, int Ho, int Wo, float* __restrict__ out) {
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const long long total = (long long)NC * Ho * Wo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
+    const long long nc = idx / ((long long)Wo * Ho);
+    const float fy = fmaxf(((float)oy + 0.5f) * sy - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sx - 0.5f, 0.0f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* b = in + nc * H * W;
+    out[idx] = (1.0f - ly) * ((1.0f - lx) * b[y0 * W + x0] + lx * b[y0 * W + x1]) + ly * ((1.0f - lx) * b[y1 * W + x0] + lx * b[y1 * W + x1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ attention glue
+// SpatialAttentionModule (attention_modules.py:67-113): per-pixel channel mean & max -> [N,H,W,2] fp32
+__global__ void channel_stats_kernel(const __half* __restrict__ in, long long pixels, int C, int cs, float* __restrict__ stats) {
+  // one warp per pixel: lanes stride the channel vector in 16-byte pieces
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long pix = warp_global; pix < pixels; pix += nwarps) {
+    float s = 0.0f, m = -INFINITY;
+    for (int c = lane * 8; c < C; c += 256) {
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * cs + c));
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); s += f.x + f.y; m = fmaxf(m, fmaxf(f.x, f.y)); }
+    }
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+    if (lane == 0) { stats[pix * 2] = s / (float)C; stats[pix * 2 + 1] = m; }
+  }
+}
+
+// x * sigmoid(conv_kxk([mean,max])) ; w is [2][k][k] fp32 (PyTorch [1,2,k,k])
+__global__ void spatial_attention_apply_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs,
+                                               const float* __restrict__ stats, const float* __restrict__ w, int k,
+                                               __half* __restrict__ out, int out_cs) {
+  const int lane = threadIdx.x & 31;
+  const long long pixels = (long long)N * H * W;
+  const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int pad = k / 2;
+  for (long long pix = warp_global; pix < pixels; pix += nwarps) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const long long img0 = pix - ((long long)y * W + x);
+    float s = 0.0f;
+    for (int t = lane; t < k * k; t += 32) {
+      const int ky = t / k, kx = t % k, iy = y + ky - pad, ix = x + kx - pad;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(stats + (img0 + (long long)iy * W + ix) * 2));
+        s = fmaf(st.x, __ldg(w + t), s); s = fmaf(st.y, __ldg(w + k * k + t), s);
+      }
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float g = his_sigmoid(s);
+    for (int c = lane * 8; c < C; c += 256) {
+      uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * in_cs + c));
+      __half2* xh = reinterpret_cast<__half2*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); xh[e] = __floats2half2_rn(f.x * g, f.y * g); }
+      *reinterpret_cast<uint4*>(out + pix * out_cs + c) = xv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ head tails
+// upsample_bg_fg (..._refinement.py:501-506): ConvT(2->32,k2,s2) + norm(BN folded) + act + 1x1(32->2), NCHW fp32 in/out.
+//   wt: [2][32][2][2] (PyTorch ConvTranspose2d weight), s/t: folded scale/shift [32] (bias folded in), w1: [2][32], b1: [2]
+__global__ void upsample_bgfg_kernel(const float* __restrict__ low, int N, int h, int w, const float* __restrict__ wt,
+                                     const float* __restrict__ s, const float* __restrict__ t, const float* __restrict__ w1,
+                                     const float* __restrict__ b1, int act, float act_beta, float* __restrict__ out) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)N * Ho * Wo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho), n = (int)(idx / ((long long)Wo * Ho));
+    const int iy = oy >> 1, ix = ox >> 1, ky = oy & 1, kx = ox & 1;
+    const float a0 = low[((long long)(n * 2 + 0) * h + iy) * w + ix], a1 = low[((long long)(n * 2 + 1) * h + iy) * w + ix];
+    float o0 = b1[0], o1 = b1[1];
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      float v = a0 * __ldg(wt + ((0 * 32 + c) * 2 + ky) * 2 + kx) + a1 * __ldg(wt + ((1 * 32 + c) * 2 + ky) * 2 + kx);
+      v = his_act(v * __ldg(s + c) + __ldg(t + c), act, act_beta);
+      o0 = fmaf(v, __ldg(w1 + c), o0); o1 = fmaf(v, __ldg(w1 + 32 + c), o1);
+    }
+    out[((long long)(n * 2 + 0) * Ho + oy) * Wo + ox] = o0;
+    out[((long long)(n * 2 + 1) * Ho + oy) * Wo + ox] = o1;
+  }
+}
+
+// ..._refinement.py:588-596: L0 = bgfg0, L1 = bgfg1 + tn0*softmax(bgfg)1, L2 = bgfg1 + tn1*softmax(bgfg)1  (NCHW fp32)
+__global__ void head_combine_kernel(const float* __restrict__ bgfg, const float* __restrict__ tn, int N, long long HW, float* __restrict__ logits) {
+  const long long total = (long long)N * HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / HW, p = idx % HW;
+    const float b0 = bgfg[(n * 2) * HW + p], b1 = bgfg[(n * 2 + 1) * HW + p];
+    const float t0 = tn[(n * 2) * HW + p], t1 = tn[(n * 2 + 1) * HW + p];
+    const float m = fmaxf(b0, b1);
+    const float e0 = expf(b0 - m), e1 = expf(b1 - m);
+    const float fg = e1 / (e0 + e1);
+    logits[(n * 3) * HW + p] = b0;
+    logits[(n * 3 + 1) * HW + p] = b1 + t0 * fg;
+    logits[(n * 3 + 2) * HW + p] = b1 + t1 * fg;
+  }
+}
+
+// elementwise map on fp32: 0 sigmoid(x) ; 1 sigmoid((x - *param) * 10)  (DistanceTransformDecoder ..._refinement.py:341)
+__global__ void map_f32_kernel(const float* __restrict__ in, long long total, int op, const float* __restrict__ param, float* __restrict__ out) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const float x = in[idx];
+    out[idx] = op == 0 ? 1.0f / (1.0f + expf(-x)) : 1.0f / (1.0f + expf(-((x - __ldg(param)) * 10.0f)));
+  }
+}
+
+// NHWC fp16 slice -> NCHW fp32 (aux outputs: shared_features, fg_attention)
+__global__ void nhwc_half_to_nchw_float_kernel(const __half* __restrict__ in, int N, int HW, int C, int cs, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? __half2float(in[((long long)n * HW + p) * cs + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) out[((long long)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------ UNet input / output
+// PreTrainedPeopleSegmentationUNet.normalize_input (..._unet.py:1885-1890): x/255 iff x.max() > 1, then (x-mean)/std.
+// The max is reduced on the device (no host sync); affine = [a0,a1,a2,b0,b1,b2] with x*a+b.
+__global__ void max_reduce_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ flag) {
+  unsigned int over = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) over |= (x[i] > 1.0f);
+  over = __any_sync(0xffffffffu, over);
+  if ((threadIdx.x & 31) == 0 && over) atomicOr(flag, 1u);
+}
+__global__ void input_affine_kernel(const unsigned int* __restrict__ flag, float m0, float m1, float m2, float s0, float s1, float s2,
+                                    float* __restrict__ affine) {
+  const float d = *flag ? 255.0f : 1.0f;
+  const float m[3] = {m0, m1, m2}, s[3] = {s0, s1, s2};
+  for (int c = 0; c < 3; ++c) { affine[c] = 1.0f / (d * s[c]); affine[3 + c] = -m[c] / s[c]; }
+}
+
+// output_conv 1x1 (1->2) + export-wrapper binary mask: two = [w0*x+b0, w1*x+b1]; binary = softmax(two)[:,0]
+__global__ void unet_outputs_kernel(const float* __restrict__ one, int B, long long HW, float w0, float w1, float b0, float b1,
+                                    float* __restrict__ two, float* __restrict__ binary) {
+  const long long total = (long long)B * HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / HW, p = idx % HW;
+    const float x = one[idx];
+    const float a = w0 * x + b0, b = w1 * x + b1;
+    if (two) { two[(n * 2) * HW + p] = a; two[(n * 2 + 1) * HW + p] = b; }
+    if (binary) { const float m = fmaxf(a, b); const float ea = expf(a - m), eb = expf(b - m); binary[idx] = ea / (ea + eb); }
+  }
+}
+
+__global__ void fill_u32_kernel(unsigned int* p, long long n, unsigned int v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+int his_set_error(int code, const char* msg) {
+  snprintf(g_err, sizeof g_err, "%s", msg ? msg : "");
+  return code;
+}
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+const char* his_last_error(void) { return g_err; }
+
+int his_version(void) { return 100; }
+
+int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC, long long sH, long long sW, int B, int C, int H, int W,
+                  const float* rois, int n_rois, int oh, int ow, float scale_h, float scale_w, int aligned, void* out_half, int out_cs,
+                  float* out_f32, void* stream) {
+  if (!feat || (!out_half && !out_f32) || (n_rois > 0 && !rois)) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: null pointer");
+  if (n_rois == 0) return HIS_OK;
+  if (oh <= 0 || ow <= 0 || C <= 0) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: bad shape");
+  const long long total = (long long)n_rois * oh * ow;
+  if (feat_is_half)
+    roi_align_kernel<__half><<<grid_for(total), kThreads, 0, ST>>>((const __half*)feat, sN, sC, sH, sW, B, C, H, W, rois, n_rois, oh, ow,
+                                                                  scale_h, scale_w, aligned, (__half*)out_half, out_cs, out_f32);
+  else
+    roi_align_kernel<float><<<grid_for(total), kThreads, 0, ST>>>((const float*)feat, sN, sC, sH, sW, B, C, H, W, rois, n_rois, oh, ow,
+                                                                 scale_h, scale_w, aligned, (__half*)out_half, out_cs, out_f32);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, int H, int W, int cin, int in_cs, const void* w,
+                    const float* scale, const float* shift, int cout, int kh, int kw, int stride, int pad, int act, float act_beta,
+                    int res_mode, const void* res, int res_cs, void* out_half, int out_cs, float* out_f32, void* stream) {
+  if (!in || !w || !scale || !shift || (!out_half && !out_f32)) return his_set_error(HIS_ERR_INVALID_ARG, "conv_direct: null pointer");
+  if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "conv_direct: res_mode without residual");
+  DirectConvParams p;
+  p.in = in; p.in_fmt = in_fmt; p.in_affine = in_affine; p.N = N; p.H = H; p.W = W; p.Cin = cin; p.in_cs = in_cs;
+  p.w = (const __half*)w; p.scale = scale; p.shift = shift; p.Cout = cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+  p.Ho = (H + 2 * pad - kh) / stride + 1; p.Wo = (W + 2 * pad - kw) / stride + 1;
+  p.act = act; p.act_beta = act_beta; p.res_mode = res_mode; p.res = (const __half*)res; p.res_cs = res_cs;
+  p.out_h = (__half*)out_half; p.out_cs = out_cs; p.out_f = out_f32;
+  if (N == 0) return HIS_OK;
+  const int cot = (cout % 8 == 0) ? 8 : (cout % 4 == 0) ? 4 : (cout % 2 == 0) ? 2 : 1;
+  const long long total = (long long)N * p.Ho * p.Wo * (cout / cot);
+  const int g = grid_for(total);
+  switch (cot) {
+    case 8: direct_conv_kernel<8><<<g, kThreads, 0, ST>>>(p); break;
+    case 4: direct_conv_kernel<4><<<g, kThreads, 0, ST>>>(p); break;
+    case 2: direct_conv_kernel<2><<<g, kThreads, 0, ST>>>(p); break;
+    default: direct_conv_kernel<1><<<g, kThreads, 0, ST>>>(p); break;
+  }
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale, const float* shift, int k,
+                       int stride, int act, void* out, int out_cs, float* pool_sums, void* stream) {
+  if (!in || !w || !scale || !shift || !out) return his_set_error(HIS_ERR_INVALID_ARG, "depthwise: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: channels must be multiples of 8");
+  if (N == 0) return HIS_OK;
+  DwParams p;
+  p.in = (const __half*)in; p.N = N; p.H = H; p.W = W; p.C = C; p.in_cs = in_cs; p.w = (const __half*)w; p.scale = scale; p.shift = shift;
+  p.k = k; p.stride = stride; p.pad = ((stride - 1) + (k - 1)) / 2; p.Ho = (H + 2 * p.pad - k) / stride + 1; p.Wo = (W + 2 * p.pad - k) / stride + 1;
+  p.act = act; p.out = (__half*)out; p.out_cs = out_cs; p.pool = pool_sums;
+  const long long per_img = (long long)p.Ho * p.Wo * (C / 8);
+  const int threads = threads_multiple_of(C / 8);
+  if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: more than 8192 channels");
+  int gx = (int)((per_img + threads - 1) / threads);
+  const int cap = (148 * 16 + N - 1) / N;      // ~16 resident blocks per SM over the whole batch
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, N);
+  depthwise_kernel<<<grid, threads, pool_sums ? C * sizeof(float) : 0, ST>>>(p);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, void* stream) {
+  if (!in || !pool_sums) return his_set_error(HIS_ERR_INVALID_ARG, "pool_sum: null pointer");
+  if (C % 8 || cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: channels must be multiples of 8");
+  if (N == 0) return HIS_OK;
+  const long long per_img = (long long)HW * (C / 8);
+  const int threads = threads_multiple_of(C / 8);
+  if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: more than 8192 channels");
+  int gx = (int)((per_img + threads * 8 - 1) / (threads * 8));
+  const int cap = (148 * 8 + N - 1) / N;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, N);
+  pool_sum_kernel<<<grid, threads, C * sizeof(float), ST>>>((const __half*)in, HW, C, cs, pool_sums);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_se_gate(const float* pool_sums, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2, const float* b2,
+                int act, float act_beta, float* gate, void* stream) {
+  if (!pool_sums || !w1 || !w2 || !gate) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: null pointer");
+  if (N == 0) return HIS_OK;
+  se_gate_kernel<<<N, kThreads, (C + R) * sizeof(float), ST>>>(pool_sums, 1.0f / (float)HW, C, R, w1, b1, w2, b2, act, act_beta, gate);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream) {
+  if (!in || !gate || !out) return his_set_error(HIS_ERR_INVALID_ARG, "scale_channels: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "scale_channels: channels must be multiples of 8");
+  const long long total = (long long)N * HW * (C / 8);
+  if (total == 0) return HIS_OK;
+  scale_channels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, gate, HW, C, total, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "maxpool2: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "maxpool2: channels must be multiples of 8");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return HIS_OK;
+  maxpool2_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "resize_nearest: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "resize_nearest: channels must be multiples of 8");
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  if (total == 0) return HIS_OK;
+  resize_nearest_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_resize_bilinear_f32(const float* in, int NC, int H, int W, int Ho, int Wo, float* out, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "resize_bilinear: null pointer");
+  const long long total = (long long)NC * Ho * Wo;
+  if (total == 0) return HIS_OK;
+  resize_bilinear_f32_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, NC, H, W, Ho, Wo, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs, const float* w, int k, float* stats_ws, void* out,
+                          int out_cs, void* stream) {
+  if (!in || !w || !stats_ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "spatial_attention: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "spatial_attention: channels must be multiples of 8");
+  const long long pixels = (long long)N * H * W;
+  if (pixels == 0) return HIS_OK;
+  channel_stats_kernel<<<grid_for(pixels * 32), kThreads, 0, ST>>>((const __half*)in, pixels, C, in_cs, stats_ws);
+  HIS_CHECK_LAUNCH();
+  spatial_attention_apply_kernel<<<grid_for(pixels * 32), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, stats_ws, w, k,
+                                                                            (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_upsample_bgfg(const float* low, int N, int h, int w, const float* wt, const float* scale, const float* shift, const float* w1,
+                      const float* b1, int act, float act_beta, float* out, void* stream) {
+  if (!low || !wt || !scale || !shift || !w1 || !b1 || !out) return his_set_error(HIS_ERR_INVALID_ARG, "upsample_bgfg: null pointer");
+  const long long total = (long long)N * 4 * h * w;
+  if (total == 0) return HIS_OK;
+  upsample_bgfg_kernel<<<grid_for(total), kThreads, 0, ST>>>(low, N, h, w, wt, scale, shift, w1, b1, act, act_beta, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_head_combine(const float* bgfg, const float* tn, int N, int H, int W, float* logits, void* stream) {
+  if (!bgfg || !tn || !logits) return his_set_error(HIS_ERR_INVALID_ARG, "head_combine: null pointer");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  head_combine_kernel<<<grid_for(total), kThreads, 0, ST>>>(bgfg, tn, N, (long long)H * W, logits);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_map_f32(const float* in, long long total, int op, const float* param, float* out, void* stream) {
+  if (!in || !out || (op == 1 && !param)) return his_set_error(HIS_ERR_INVALID_ARG, "map_f32: null pointer");
+  if (total == 0) return HIS_OK;
+  map_f32_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, total, op, param, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "layout: null pointer");
+  if (N == 0) return HIS_OK;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nhwc_half_to_nchw_float_kernel<<<grid, block, 0, ST>>>((const __half*)in, N, HW, C, cs, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_unet_input_affine(const float* images, long long count, const float* mean3, const float* std3, unsigned int* flag_ws,
+                          float* affine6, void* stream) {
+  if (!images || !mean3 || !std3 || !flag_ws || !affine6) return his_set_error(HIS_ERR_INVALID_ARG, "input_affine: null pointer");
+  fill_u32_kernel<<<1, 32, 0, ST>>>(flag_ws, 1, 0u);
+  if (count > 0) max_reduce_kernel<<<grid_for(count), kThreads, 0, ST>>>(images, count, flag_ws);
+  input_affine_kernel<<<1, 1, 0, ST>>>(flag_ws, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], affine6);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_unet_outputs(const float* one, int B, int H, int W, float w0, float w1, float b0, float b1, float* two, float* binary, void* stream) {
+  if (!one || (!two && !binary)) return his_set_error(HIS_ERR_INVALID_ARG, "unet_outputs: null pointer");
+  const long long total = (long long)B * H * W;
+  if (total == 0) return HIS_OK;
+  unet_outputs_kernel<<<grid_for(total), kThreads, 0, ST>>>(one, B, (long long)H * W, w0, w1, b0, b1, two, binary);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_memset_async(void* ptr, int value, long long bytes, void* stream) {
+  if (bytes == 0) return HIS_OK;
+  if (!ptr) return his_set_error(HIS_ERR_INVALID_ARG, "memset: null pointer");
+  if (cudaMemsetAsync(ptr, value, (size_t)bytes, ST) != cudaSuccess) return his_set_error(HIS_ERR_LAUNCH, "cudaMemsetAsync failed");
+  return HIS_OK;
+}
+
+}  // extern "C"

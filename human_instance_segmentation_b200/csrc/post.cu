@@ -1,0 +1,286 @@
+// Post-processing stencils of the exported pipeline: 3-class argmax ->
+// instance mask, MaskDilationModule, BinaryMaskEdgeSmoothing, BinaryMaskBilateralFilter,
+// MorphologicalBilateralFilter and NEAREST paste-back.  All HBM-bound: one thread per output
+// pixel, rows walked by consecutive lanes (coalesced), neighbourhood re-reads served by L1/L2.
+// Float stages keep the reference's operation order (no fast-math) because their final
+// thresholds can sit within a few ulp of a tie.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid_for(long long work) {
+  long long g = (work + kThreads - 1) / kThreads;
+  if (g > 148LL * 64) g = 148LL * 64;
+  return (int)(g < 1 ? 1 : g);
+}
+#define GRID_STRIDE(idx, total) \
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (total); idx += (long long)gridDim.x * blockDim.x)
+
+// hed/export_onnx_advanced.py:360-364: where(argmax(masks,1)==1, 1, 0) (argmax returns the FIRST maximum);
+// test_hierarchical_instance_peopleseg_onnx.py:250-262: (argmax(softmax)==1) & (max prob > score_threshold).
+__global__ void instance_mask_kernel(const float* __restrict__ logits, int N, long long HW, float thr, float* __restrict__ out_f,
+                                     unsigned char* __restrict__ out_u8) {
+  const long long total = (long long)N * HW;
+  GRID_STRIDE(idx, total) {
+    const long long n = idx / HW, p = idx % HW;
+    const float l0 = logits[(n * 3) * HW + p], l1 = logits[(n * 3 + 1) * HW + p], l2 = logits[(n * 3 + 2) * HW + p];
+    bool on = (l1 > l0) && (l1 >= l2);
+    if (on && thr > 0.0f) {
+      const float m = l1;
+      const float s = expf(l0 - m) + 1.0f + expf(l2 - m);
+      on = (1.0f / s) > thr;
+    }
+    if (out_f) out_f[idx] = on ? 1.0f : 0.0f;
+    if (out_u8) out_u8[idx] = on ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ float softmax_p1(const float* __restrict__ logits, long long n, long long HW, long long p) {
+  const float l0 = logits[(n * 3) * HW + p], l1 = logits[(n * 3 + 1) * HW + p], l2 = logits[(n * 3 + 2) * HW + p];
+  const float m = fmaxf(l0, fmaxf(l1, l2));
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+  return e1 / ((e0 + e1) + e2);
+}
+
+// MaskDilationModule, export_hierarchical_instance_peopleseg_onnx.py:85-141
+__global__ void dilate_logits_kernel(const float* __restrict__ logits, int N, int H, int W, int k, float* __restrict__ out) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  GRID_STRIDE(idx, total) {
+    const long long n = idx / HW, p = idx % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
+    const float p1 = softmax_p1(logits, n, HW, p);
+    float d = p1;
+    for (int dy = -k; dy <= k; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -k; dx <= k; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W || (dx == 0 && dy == 0)) continue;
+        d = fmaxf(d, softmax_p1(logits, n, HW, (long long)yy * W + xx));
+      }
+    }
+    const float l0 = logits[(n * 3) * HW + p], l1 = logits[(n * 3 + 1) * HW + p], l2 = logits[(n * 3 + 2) * HW + p];
+    out[(n * 3) * HW + p] = l0;
+    out[(n * 3 + 1) * HW + p] = ((d - p1) > 0.1f) ? l1 + 2.0f : l1;
+    out[(n * 3 + 2) * HW + p] = l2;
+  }
+}
+
+__device__ __forceinline__ float at0(const float* __restrict__ img, int H, int W, int y, int x) {
+  return (y >= 0 && y < H && x >= 0 && x < W) ? img[(long long)y * W + x] : 0.0f;
+}
+
+// BinaryMaskEdgeSmoothing, hed/edge_smoothing.py:10-90 (per channel == per plane here)
+__global__ void edge_smooth_kernel(const float* __restrict__ mask, int N, int H, int W, float thr, float strength, float* __restrict__ out) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  GRID_STRIDE(idx, total) {
+    const long long n = idx / HW, p = idx % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
+    const float* img = mask + n * HW;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = at0(img, H, W, y + t / 3 - 1, x + t % 3 - 1);
+    float lap = 0.0f, g = 0.0f;
+    const float gk[9] = {1.f / 16, 2.f / 16, 1.f / 16, 2.f / 16, 4.f / 16, 2.f / 16, 1.f / 16, 2.f / 16, 1.f / 16};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { lap = fmaf(v[t], t == 4 ? 8.0f : -1.0f, lap); g = fmaf(v[t], gk[t], g); }
+    const float e = fabsf(lap) * strength;
+    const float w = 1.0f / (1.0f + expf(-e));
+    const float sm = __fadd_rn(__fmul_rn(v[4], __fsub_rn(1.0f, w)), __fmul_rn(g, w));
+    out[idx] = sm > thr ? 1.0f : 0.0f;
+  }
+}
+
+// one iteration of BinaryMaskBilateralFilter (hed/bilateral_filter.py:299-406); `first` clamps the input to [0,1]
+__global__ void binary_bilateral_iter_kernel(const float* __restrict__ in, int N, int H, int W, const float* __restrict__ gk, int k, int clamp_in,
+                                             int last, float thr, float* __restrict__ out) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  const int r = k / 2;
+  GRID_STRIDE(idx, total) {
+    const long long n = idx / HW, p = idx % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
+    const float* img = in + n * HW;
+    float f = 0.0f, f2 = 0.0f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int yy = y + ky - r;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int xx = x + kx - r;
+        if (xx < 0 || xx >= W) continue;
+        float v = img[(long long)yy * W + xx];
+        if (clamp_in) v = fminf(fmaxf(v, 0.0f), 1.0f);
+        const float wgt = __ldg(gk + ky * k + kx);
+        f = fmaf(v, wgt, f);
+        f2 = fmaf(__fmul_rn(v, v), wgt, f2);
+      }
+    }
+    float c = img[p];
+    if (clamp_in) c = fminf(fmaxf(c, 0.0f), 1.0f);
+    const float var = fmaxf(__fsub_rn(f2, __fmul_rn(f, f)), 0.0f);
+    const float ew = expf(__fmul_rn(-var, 10.0f));
+    const float m = __fadd_rn(__fmul_rn(ew, f), __fmul_rn(__fsub_rn(1.0f, ew), c));
+    out[idx] = last ? (m > thr ? 1.0f : 0.0f) : m;
+  }
+}
+
+// window max / min with the window clipped at the border (max_pool2d pads with -inf; erosion = -maxpool(-x))
+__global__ void minmax_kernel(const float* __restrict__ in, int N, int H, int W, int k, int is_max, int clamp_in, float* __restrict__ out) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  const int r = k / 2;
+  GRID_STRIDE(idx, total) {
+    const long long n = idx / HW, p = idx % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
+    const float* img = in + n * HW;
+    float m = is_max ? -INFINITY : INFINITY;
+    for (int dy = -r; dy <= r; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -r; dx <= r; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        float v = img[(long long)yy * W + xx];
+        if (clamp_in) v = fminf(fmaxf(v, 0.0f), 1.0f);
+        m = is_max ? fmaxf(m, v) : fminf(m, v);
+      }
+    }
+    out[idx] = m;
+  }
+}
+
+__global__ void conv_zero_pad_kernel(const float* __restrict__ in, int N, int H, int W, const float* __restrict__ kern, int k, float* __restrict__ out) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  const int r = k / 2;
+  GRID_STRIDE(idx, total) {
+    const long long n = idx / HW, p = idx % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
+    const float* img = in + n * HW;
+    float f = 0.0f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int yy = y + ky - r;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int xx = x + kx - r;
+        if (xx < 0 || xx >= W) continue;
+        f = fmaf(img[(long long)yy * W + xx], __ldg(kern + ky * k + kx), f);
+      }
+    }
+    out[idx] = f;
+  }
+}
+
+__global__ void threshold_kernel(const float* __restrict__ in, long long total, float thr, float* __restrict__ out) {
+  GRID_STRIDE(idx, total) out[idx] = in[idx] > thr ? 1.0f : 0.0f;
+}
+
+// Paste-back (test_hierarchical_instance_peopleseg_onnx.py:144-161,264-278,369-374): box = int(x1*W) ... (fp32 product,
+// truncation), cv2.resize(..., INTER_NEAREST): src = min(floor(dst * (1/(dst_size/src_size))), src_size-1) in double,
+// full[y1:y2, x1:x2] = mask; later instances win.  canvas[b,y,x] = 1 + index of the last ROI whose pasted mask is 1.
+__global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int mh, int mw, const float* __restrict__ rois, int* __restrict__ canvas,
+                             int B, int H, int W) {
+  const int roi = blockIdx.y;
+  const float* r = rois + 5 * roi;
+  const int b = (int)r[0];
+  if (b < 0 || b >= B) return;
+  const int x1 = (int)__fmul_rn(r[1], (float)W), y1 = (int)__fmul_rn(r[2], (float)H);
+  const int x2 = (int)__fmul_rn(r[3], (float)W), y2 = (int)__fmul_rn(r[4], (float)H);
+  const int bw = x2 - x1, bh = y2 - y1;
+  if (bw <= 0 || bh <= 0) return;
+  const double sx = 1.0 / ((double)bw / (double)mw), sy = 1.0 / ((double)bh / (double)mh);
+  const long long total = (long long)bw * bh;
+  GRID_STRIDE(idx, total) {
+    const int dx = (int)(idx % bw), dy = (int)(idx / bw);
+    const int X = x1 + dx, Y = y1 + dy;
+    if (X < 0 || X >= W || Y < 0 || Y >= H) continue;
+    const int sxi = min((int)floor((double)dx * sx), mw - 1), syi = min((int)floor((double)dy * sy), mh - 1);
+    if (masks[((long long)roi * mh + syi) * mw + sxi]) atomicMax(canvas + ((long long)b * H + Y) * W + X, roi + 1);
+  }
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+int his_post_instance_mask(const float* logits, int N, int H, int W, float score_threshold, float* out_f32, unsigned char* out_u8, void* stream) {
+  if (!logits || (!out_f32 && !out_u8)) return his_set_error(HIS_ERR_INVALID_ARG, "instance_mask: null pointer");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  instance_mask_kernel<<<grid_for(total), kThreads, 0, ST>>>(logits, N, (long long)H * W, score_threshold, out_f32, out_u8);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_dilate_logits(const float* logits, int N, int H, int W, int dilation_pixels, float* out, void* stream) {
+  if (!logits || !out) return his_set_error(HIS_ERR_INVALID_ARG, "dilate_logits: null pointer");
+  if (dilation_pixels < 0 || dilation_pixels > 16) return his_set_error(HIS_ERR_UNSUPPORTED, "dilate_logits: dilation_pixels must be in [0,16]");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  if (dilation_pixels == 0) {
+    if (cudaMemcpyAsync(out, logits, (size_t)total * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ST) != cudaSuccess)
+      return his_set_error(HIS_ERR_LAUNCH, "memcpy failed");
+    return HIS_OK;
+  }
+  dilate_logits_kernel<<<grid_for(total), kThreads, 0, ST>>>(logits, N, H, W, dilation_pixels, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_edge_smooth(const float* mask, int N, int H, int W, float threshold, float blur_strength, float* out, void* stream) {
+  if (!mask || !out) return his_set_error(HIS_ERR_INVALID_ARG, "edge_smooth: null pointer");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  edge_smooth_kernel<<<grid_for(total), kThreads, 0, ST>>>(mask, N, H, W, threshold, blur_strength, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_binary_bilateral(const float* mask, int N, int H, int W, const float* gauss, int k, int iterations, float threshold, float* ws0,
+                              float* ws1, float* out, void* stream) {
+  if (!mask || !gauss || !out || (iterations > 1 && (!ws0 || !ws1))) return his_set_error(HIS_ERR_INVALID_ARG, "binary_bilateral: null pointer");
+  if (k < 1 || !(k & 1) || iterations < 1) return his_set_error(HIS_ERR_INVALID_ARG, "binary_bilateral: kernel size must be odd, iterations >= 1");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  const float* src = mask;
+  for (int it = 0; it < iterations; ++it) {
+    const int last = it == iterations - 1;
+    float* dst = last ? out : (it & 1 ? ws1 : ws0);
+    binary_bilateral_iter_kernel<<<grid_for(total), kThreads, 0, ST>>>(src, N, H, W, gauss, k, it == 0, last, threshold, dst);
+    HIS_CHECK_LAUNCH();
+    src = dst;
+  }
+  return HIS_OK;
+}
+
+int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float* kernel2d, int k, int morph, float* ws0, float* ws1, float* out,
+                             void* stream) {
+  if (!mask || !kernel2d || !ws0 || !ws1 || !out) return his_set_error(HIS_ERR_INVALID_ARG, "morph_bilateral: null pointer");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  const int g = grid_for(total);
+  minmax_kernel<<<g, kThreads, 0, ST>>>(mask, N, H, W, morph, 0, 1, ws0);        // open: erode(clamp(x))
+  minmax_kernel<<<g, kThreads, 0, ST>>>(ws0, N, H, W, morph, 1, 0, ws1);         //       dilate
+  conv_zero_pad_kernel<<<g, kThreads, 0, ST>>>(ws1, N, H, W, kernel2d, k, ws0);  // gaussian, zero padded
+  minmax_kernel<<<g, kThreads, 0, ST>>>(ws0, N, H, W, morph, 1, 0, ws1);         // close: dilate
+  minmax_kernel<<<g, kThreads, 0, ST>>>(ws1, N, H, W, morph, 0, 0, ws0);         //        erode
+  threshold_kernel<<<g, kThreads, 0, ST>>>(ws0, total, 0.5f, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W, void* stream) {
+  if (!masks || !rois || !canvas) return his_set_error(HIS_ERR_INVALID_ARG, "paste: null pointer");
+  if (N == 0) return HIS_OK;
+  if (N > 65535) return his_set_error(HIS_ERR_UNSUPPORTED, "paste: at most 65535 ROIs per call (chunk the batch)");
+  dim3 grid(32, N);
+  paste_kernel<<<grid, kThreads, 0, ST>>>(masks, N, mh, mw, rois, canvas, B, H, W);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""Launch-plan builder/executor for the B200 path.
+
+A ``Plan`` is a flat list of ``(c_function, args)`` records bound to pre-allocated HBM buffers
+(activations NHWC fp16, tails NCHW fp32).  It is built once per input geometry
+``(B, H, W, n_rois)`` from the model's parameters (BatchNorm folded, weights repacked to the
+kernels' layouts) and replayed every forward on the caller's current CUDA stream -- optionally
+captured into a CUDA graph.  torch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import lib as _lib
+
+ACT = {"none": 0, "relu": 1, "silu": 2, "sigmoid": 3, "swish": 4, "gelu": 5}
+RES_NONE, RES_ADD, RES_MUL = 0, 1, 2
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Act:
+    """A channel slice [c_off, c_off+C) of an NHWC fp16 buffer [N,H,W,cs]."""
+
+    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off")
+
+    def __init__(self, buf: torch.Tensor, C: int, c_off: int = 0):
+        assert buf.dtype == torch.float16 and buf.dim() == 4 and buf.is_contiguous()
+        self.buf = buf
+        self.N, self.H, self.W, self.cs = buf.shape
+        self.C, self.c_off = C, c_off
+        assert c_off % 8 == 0 and self.cs % 8 == 0 and c_off + C <= self.cs
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + 2 * self.c_off
+
+    def slice(self, c_off: int, C: int) -> "Act":
+        return Act(self.buf, C, self.c_off + c_off)
+
+    def torch_nchw(self) -> torch.Tensor:
+        """Debug view (fp32 NCHW copy through torch) -- tests only."""
+        return self.buf[..., self.c_off:self.c_off + self.C].permute(0, 3, 1, 2).float().contiguous()
+
+
+class Plan:
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.lib = _lib.load()
+        self.ops: List[Tuple] = []          # (name, cfunc, args-without-stream)
+        self.keep: List[object] = []        # tensors / gemm plans the ops point into
+        self.gemm_plans: List[ctypes.c_void_p] = []
+        self.flops = 0                      # algorithmic FLOPs (2*MAC, true channel counts) of one replay
+        self.flops_by_tag: Dict[str, int] = {}
+        self.tensor_flops = 0               # the part issued on tcgen05
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches = 0
+        self.tag = ""
+
+    # -------------------------------------------------------------- allocation
+    def act(self, N, H, W, C, cs=None) -> Act:
+        cs = cs or round_up(C, 8)
+        buf = torch.empty((N, H, W, cs), dtype=torch.float16, device=self.device)
+        self.keep.append(buf)
+        return Act(buf, C)
+
+    def f32(self, *shape, zero=False) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def const(self, t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    def _add_flops(self, f: int, tensor: bool):
+        self.flops += f
+        self.flops_by_tag[self.tag] = self.flops_by_tag.get(self.tag, 0) + f
+        if tensor:
+            self.tensor_flops += f
+
+    def add(self, name: str, fn, *args):
+        self.ops.append((name, fn, args))
+        self.launches += 1
+
+    # -------------------------------------------------------------- ops
+    def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, scale: torch.Tensor, shift: torch.Tensor, out: Act,
+                  ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
+                  transposed: bool = False):
+        L = self.lib
+        h = ctypes.c_void_p()
+        if transposed:
+            assert out.H == 2 * x.H and out.W == 2 * x.W
+        else:
+            assert (out.N, out.H, out.W) == (x.N, x.H, x.W)
+        _lib.check(L.his_conv_gemm_create(ctypes.byref(h), x.ptr, x.N, x.H, x.W, x.C, x.cs, w_packed.data_ptr(), cin_pad,
+                                          out.ptr, out.C, out.cs, res.ptr if res is not None else None,
+                                          res.cs if res is not None else 0, scale.data_ptr(), shift.data_ptr(), ksize,
+                                          1 if transposed else 0, act, beta, res_mode), "his_conv_gemm_create")
+        self.gemm_plans.append(h)
+        self.keep += [w_packed, scale, shift]
+        taps = 4 if transposed else ksize * ksize
+        self._add_flops(2 * x.N * x.H * x.W * x.C * out.C * taps, True)
+        self.add("conv_gemm", L.his_conv_gemm_run, h)
+
+    def conv_direct(self, x, in_fmt: int, N, H, W, cin, in_cs, w: torch.Tensor, scale, shift, cout, k, stride, pad, act, beta=1.0,
+                    in_affine: Optional[torch.Tensor] = None, res: Optional[Act] = None, res_mode: int = RES_NONE,
+                    out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None):
+        L = self.lib
+        xptr = x.ptr if isinstance(x, Act) else x.data_ptr()
+        self.keep += [w, scale, shift]
+        ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        self._add_flops(2 * N * ho * wo * cin * cout * k * k, False)
+        self.add("conv_direct", L.his_conv_direct, xptr, in_fmt, in_affine.data_ptr() if in_affine is not None else None, N, H, W,
+                 cin, in_cs, w.data_ptr(), scale.data_ptr(), shift.data_ptr(), cout, k, k, stride, pad, act, beta, res_mode,
+                 res.ptr if res is not None else None, res.cs if res is not None else 0,
+                 out.ptr if out is not None else None, out.cs if out is not None else 0,
+                 out_f32.data_ptr() if out_f32 is not None else None)
+
+    # -------------------------------------------------------------- execution
+    def run(self, stream_ptr: int):
+        s = ctypes.c_void_p(stream_ptr)
+        for name, fn, args in self.ops:
+            rc = fn(*args, s)
+            if rc != 0:
+                _lib.check(rc, name)
+
+    def replay(self):
+        """Runs the plan on the current torch stream (through a CUDA graph once captured)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def capture(self):
+        """Captures the launch list into a CUDA graph (launch-bound tails become one submission)."""
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(self.device)
+        with torch.cuda.stream(side):
+            self.run(side.cuda_stream)          # warm-up outside capture (module load, attribute sets)
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self.run(torch.cuda.current_stream(self.device).cuda_stream)
+        self.graph = g
+
+    def __del__(self):
+        try:
+            for h in self.gemm_plans:
+                self.lib.his_conv_gemm_destroy(h)
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------- weight packing
+def fold_bn(conv_bias: Optional[torch.Tensor], bn, cout: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """y = conv(x)*scale + shift  ==  BN_eval(conv(x) + bias)   (BatchNorm2d eps from the module)."""
+    bias = conv_bias.detach().float().cpu() if conv_bias is not None else torch.zeros(cout)
+    if bn is None:
+        return torch.ones(cout), bias
+    g, b = bn.weight.detach().float().cpu(), bn.bias.detach().float().cpu()
+    m, v = bn.running_mean.detach().float().cpu(), bn.running_var.detach().float().cpu()
+    scale = g / torch.sqrt(v + bn.eps)
+    return scale, b - m * scale + bias * scale
+
+
+def pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.zeros(n, dtype=torch.float32)
+    out[: v.numel()] = v
+    return out
+
+
+def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False) -> Tuple[torch.Tensor, int]:
+    """Conv2d weight [Cout,Cin,kh,kw] -> fp16 [1][taps][cout_slab][cin_pad];
+    ConvTranspose2d(k2,s2) weight [Cin,Cout,2,2] -> fp16 [4 groups (dy,dx)][1][cout_slab][cin_pad]."""
+    w = w.detach().float().cpu()
+    if transposed:
+        cin, cout = w.shape[0], w.shape[1]
+        cin_pad = round_up(cin, 8)
+        out = torch.zeros(4, 1, cout_slab, cin_pad, dtype=torch.float16)
+        for dy in range(2):
+            for dx in range(2):
+                out[dy * 2 + dx, 0, :cout, :cin] = w[:, :, dy, dx].t().half()
+        return out.contiguous(), cin_pad
+    cout, cin, kh, kw = w.shape
+    cin_pad = round_up(cin, 8)
+    out = torch.zeros(1, kh * kw, cout_slab, cin_pad, dtype=torch.float16)
+    out[0, :, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).half()
+    return out.contiguous(), cin_pad
+
+
+def pack_direct_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] -> fp16 [kh][kw][Cin][Cout]."""
+    return w.detach().float().cpu().permute(2, 3, 1, 0).contiguous().half()

@@ -1,0 +1,142 @@
+"""ctypes binding of ``libhis_b200.so`` (include/his_b200.h) and its in-tree nvcc build.
+
+There is no fallback: if the library cannot be built/loaded, or a call fails, a
+``HisError`` is raised.  Nothing in this package routes compute through torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_uint, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libhis_b200.so")
+SOURCES = ["kernels.cu", "conv_gemm_sm100.cu", "post.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC"]
+
+
+class HisError(RuntimeError):
+    pass
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in os.listdir(CSRC):
+        if f.endswith((".cu", ".cuh", ".h")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles csrc/*.cu for sm_100a into libhis_b200.so next to this file (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise HisError(f"nvcc failed on {src}:\n{out.decode(errors='replace')}")
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        raise HisError(f"link failed:\n{r.stdout.decode(errors='replace')}")
+    return LIB_PATH
+
+
+_P = c_void_p
+_F = POINTER(c_float)
+_LL = c_longlong
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/his_b200.h
+SIGNATURES = {
+    "his_last_error": [],
+    "his_version": [],
+    "his_roi_align": [_P, c_int, _LL, _LL, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_float, c_float,
+                      c_int, _P, c_int, _P, _P],
+    "his_conv_gemm_tile_n": [c_int, POINTER(c_int), POINTER(c_int)],
+    "his_conv_gemm_create": [POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int,
+                             _P, _P, c_int, c_int, c_int, c_float, c_int],
+    "his_conv_gemm_run": [_P, _P],
+    "his_conv_gemm_destroy": [_P],
+    "his_conv_gemm_issued_macs": [_P],
+    "his_conv_direct": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
+                        c_float, c_int, _P, c_int, _P, c_int, _P, _P],
+    "his_depthwise_conv": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P],
+    "his_pool_sum": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "his_se_gate": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P],
+    "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
+    "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P],
+    "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "his_resize_nearest": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "his_resize_bilinear_f32": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "his_upsample_bgfg": [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P],
+    "his_head_combine": [_P, _P, c_int, c_int, c_int, _P, _P],
+    "his_map_f32": [_P, _LL, c_int, _P, _P, _P],
+    "his_nhwc_half_to_nchw_float": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "his_unet_input_affine": [_P, _LL, _F, _F, _P, _P, _P],
+    "his_unet_outputs": [_P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, _P, _P, _P],
+    "his_memset_async": [_P, c_int, _LL, _P],
+    # post-processing (csrc/post.cu)
+    "his_post_instance_mask": [_P, c_int, c_int, c_int, c_float, _P, _P, _P],
+    "his_post_dilate_logits": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "his_post_edge_smooth": [_P, c_int, c_int, c_int, c_float, c_float, _P, _P],
+    "his_post_binary_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P],
+    "his_post_morph_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P],
+    "his_post_paste": [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
+}
+_RESTYPES = {"his_last_error": c_char_p, "his_conv_gemm_issued_macs": _LL}
+
+_lib = None
+
+
+def load():
+    """Loads libhis_b200.so (building it if it is missing/stale).  Raises HisError -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        path = build()
+    except HisError:
+        if os.path.exists(LIB_PATH):
+            path = LIB_PATH   # e.g. GPU box without a writable tree: use the shipped build
+        else:
+            raise
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as e:
+        raise HisError(f"cannot load {path}: {e}") from e
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise HisError(f"{path} does not export {name}") from e
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().his_last_error()
+        raise HisError(f"{what or 'his call'} failed with code {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,602 @@
+"""Host-side mirror of the reference model API, executing on ``libhis_b200.so``.
+
+Mirrors (same names, kwargs, state-dict keys, return structure):
+  * ``create_rgb_hierarchical_model``  hed/advanced/hierarchical_segmentation_rgb.py:925-1026
+  * ``HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet``  rgb.py:564-774
+  * ``PreTrainedPeopleSegmentationUNetWrapper`` / ``PreTrainedPeopleSegmentationUNet``
+    hed/advanced/hierarchical_segmentation_unet.py:1708-1992
+  * ``RGBHierarchicalWrapper`` outputs (``infer``)  hed/export_onnx_advanced.py:353-420
+
+``forward(images, rois) -> (logits [N,3,mh,mw] fp32, aux dict)``.  Inference only (eval semantics:
+BatchNorm uses running statistics, dropout is identity).  Arithmetic: fp16 operands / activations,
+fp32 accumulation and fp32 tails (logits, softmax, combine) -- see DESIGN.md for the tolerance.
+There is no torch-op fallback: without a CUDA device or the built library the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+from . import param_tree as pt
+from .engine import ACT, RES_ADD, RES_MUL, RES_NONE, Act, Plan, fold_bn, pack_direct_weight, pack_gemm_weight, pad_vec, round_up
+from .roi_align import DynamicRoIAlign
+
+
+def _pair(v) -> Tuple[int, int]:
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _conv_out(n: int, k: int, s: int) -> int:
+    p = ((s - 1) + (k - 1)) // 2
+    return (n + 2 * p - k) // s + 1
+
+
+class PreTrainedPeopleSegmentationUNet(nn.Module):
+    """Parameter holder + input normalisation constants (..._unet.py:1708-1916)."""
+
+    def __init__(self, in_channels=3, classes=1, pretrained_weights_path="ext_extractor/2020-09-23a.pth", mean=None, std=None,
+                 freeze_weights=False, encoder_name="timm-efficientnet-b3"):
+        super().__init__()
+        if in_channels != 3 or classes != 1:
+            raise NotImplementedError("the B200 path implements the reference's in_channels=3, classes=1 configuration")
+        self.encoder_name = encoder_name
+        if mean is not None and std is not None:
+            self.mean, self.std = list(mean), list(std)
+        elif any(v in pretrained_weights_path.lower() for v in ("b0", "b1", "b7")):   # ..._unet.py:1744-1758
+            self.mean, self.std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+        else:
+            self.mean, self.std = [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]
+        self.model = pt.SmpUnetParams(encoder_name)
+        self._freeze_bn = bool(freeze_weights)
+        if freeze_weights:
+            for p in self.model.parameters():
+                p.requires_grad = False
+        self.register_buffer("norm_mean", torch.tensor(self.mean).view(1, 3, 1, 1))
+        self.register_buffer("norm_std", torch.tensor(self.std).view(1, 3, 1, 1))
+
+
+class PreTrainedPeopleSegmentationUNetWrapper(nn.Module):
+    """..._unet.py:1919-1992; ``output_conv`` weights pinned to [+1,-1], bias 0 (:1963-1971)."""
+
+    def __init__(self, in_channels=3, pretrained_weights_path="ext_extractor/2020-09-23a.pth", freeze_weights=False,
+                 encoder_name="timm-efficientnet-b3", **_ignored):
+        super().__init__()
+        self.model = PreTrainedPeopleSegmentationUNet(in_channels, 1, pretrained_weights_path, None, None, freeze_weights, encoder_name)
+        self.output_conv = nn.Conv2d(1, 2, kernel_size=1)
+        with torch.no_grad():
+            self.output_conv.weight.data[0, 0, 0, 0] = 1.0
+            self.output_conv.weight.data[1, 0, 0, 0] = -1.0
+            self.output_conv.bias.data.zero_()
+
+    def forward(self, x):
+        """Standalone use (the exporter calls ``model.pretrained_unet(images)``, export_onnx_advanced.py:374-377).
+        Returns ``(two_channel_logits [B,2,H,W], [])`` like the reference."""
+        owner = getattr(self, "_owner", None)
+        if owner is None:
+            raise _lib.HisError("PreTrainedPeopleSegmentationUNetWrapper must be owned by a B200 model to run")
+        return owner()._run_unet_only(x), []
+
+
+class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
+    """rgb.py:564-774 on the B200 kernels."""
+
+    def __init__(self, roi_size: Union[int, Tuple[int, int]] = 28, mask_size: Union[int, Tuple[int, int]] = 56,
+                 pretrained_weights_path: str = "ext_extractor/2020-09-23a.pth", use_attention_module: bool = False,
+                 freeze_pretrained_weights: bool = False, use_boundary_refinement: bool = False,
+                 use_progressive_upsampling: bool = False, use_subpixel_conv: bool = False, use_contour_detection: bool = False,
+                 use_distance_transform: bool = False, normalization_type: str = "layernorm2d", normalization_groups: int = 8,
+                 activation_function: str = "relu", activation_beta: float = 1.0, **kwargs):
+        super().__init__()
+        base = kwargs.get("hierarchical_base_channels", 96)
+        depth = kwargs.get("hierarchical_depth", 3)
+        self.roi_size = _pair(roi_size)
+        self.mask_size = _pair(mask_size)
+        self.activation_function = pt.check_activation(activation_function)
+        self.activation_beta = float(activation_beta)
+        self.normalization_type = normalization_type
+        self.use_attention_module = bool(use_attention_module)
+        self.use_contour_detection = bool(use_contour_detection)
+        self.use_distance_transform = bool(use_distance_transform)
+        if use_boundary_refinement or use_progressive_upsampling or use_subpixel_conv:
+            raise NotImplementedError("boundary refinement / progressive upsampling / sub-pixel decoders are not part of the "
+                                      "preset path (all three presets disable them) and are not implemented on B200")
+        if not (use_contour_detection or use_distance_transform):
+            raise NotImplementedError("PretrainedUNetGuidedSegmentationHead (no refinement flag) is not implemented on B200 yet; "
+                                      "the presets enable contour detection + distance transform")
+        self.pretrained_unet = PreTrainedPeopleSegmentationUNetWrapper(
+            in_channels=3, pretrained_weights_path=pretrained_weights_path, freeze_weights=freeze_pretrained_weights,
+            encoder_name=kwargs.get("encoder_name", "timm-efficientnet-b3"))
+        import weakref
+        object.__setattr__(self.pretrained_unet, "_owner", weakref.ref(self))
+        self.roi_align_mask = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=True)
+        self.roi_align_rgb = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=True)
+        n = normalization_type
+        self.rgb_feature_extractor = nn.Sequential(
+            nn.Conv2d(3, 64, 3, padding=1), pt.norm_params(n, 64), pt.Slot(), pt.ResidualBlockParams(64, n),
+            nn.Conv2d(64, 128, 3, padding=1), pt.norm_params(n, 128), pt.Slot(), pt.ResidualBlockParams(128, n),
+            nn.Conv2d(128, 256, 3, padding=1), pt.norm_params(n, 256), pt.Slot(), pt.ResidualBlockParams(256, n),
+            nn.Conv2d(256, 256, 1), pt.norm_params(n, 256), pt.Slot())
+        self.feature_combiner = nn.Conv2d(258, 256, 1)
+        self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
+                                                      self.use_distance_transform, base, depth)
+        self.hierarchical_depth = depth
+        # execution state
+        self.aux_outputs = "full"        # "full" (reference dict) | "light" (no 256-channel tensors) | "none"
+        self.copy_outputs = True         # return fresh tensors (False: views of the plan's static buffers)
+        self.use_cuda_graph = False
+        self._plans: Dict[tuple, "_BuiltPlan"] = {}
+        self._param_version = 0
+        self.eval()
+
+    # ------------------------------------------------------------------ nn.Module plumbing
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("the B200 path is inference-only (eval semantics); train with the reference")
+        return super().train(False)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.invalidate()
+        return r
+
+    def invalidate(self):
+        """Drop packed weights / plans (call after mutating parameters in place)."""
+        self._plans.clear()
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._plans.clear()
+        return r
+
+    # ------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor, rois: torch.Tensor):
+        bp = self._get_plan(images, rois)
+        bp.load_inputs(images, rois)
+        bp.plan.replay()
+        return bp.outputs(self.copy_outputs)
+
+    @torch.no_grad()
+    def infer(self, images: torch.Tensor, rois: torch.Tensor, raw_logits: bool = False):
+        """Exported-ONNX contract (hed/export_onnx_advanced.py:353-457): returns
+        ``(instance_masks [N,1,mh,mw] in {0,1}, binary_masks [B,1,H,W])``; ``raw_logits=True`` gives the older
+        released flavour ``(masks [N,3,mh,mw], binary_masks)`` (README.md:537)."""
+        from . import postprocess
+        bp = self._get_plan(images, rois)
+        bp.load_inputs(images, rois)
+        bp.plan.replay()
+        logits, binary = bp.logits, bp.binary
+        if raw_logits:
+            return (logits.clone(), binary.clone()) if self.copy_outputs else (logits, binary)
+        inst = postprocess.instance_masks(logits)
+        return inst, (binary.clone() if self.copy_outputs else binary)
+
+    def _run_unet_only(self, images: torch.Tensor) -> torch.Tensor:
+        rois = torch.zeros((0, 5), dtype=torch.float32, device=images.device)
+        bp = self._get_plan(images, rois)
+        bp.load_inputs(images, rois)
+        bp.plan.replay()
+        return bp.two.clone()
+
+    # ------------------------------------------------------------------ plan management
+    def _get_plan(self, images: torch.Tensor, rois: torch.Tensor) -> "_BuiltPlan":
+        if not images.is_cuda and not torch.cuda.is_available():
+            raise _lib.HisError("human_instance_segmentation_b200 needs a CUDA (B200) device; there is no CPU fallback")
+        if images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError(f"images must be [B,3,H,W], got {tuple(images.shape)}")
+        if rois.dim() != 2 or rois.shape[1] != 5:
+            raise ValueError(f"rois must be [N,5] = [batch_idx,x1,y1,x2,y2], got {tuple(rois.shape)}")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.HisError("move the model to a CUDA device first (model.to('cuda')); there is no CPU fallback")
+        B, _, H, W = images.shape
+        key = (B, H, W, rois.shape[0], self.aux_outputs, tuple(_scale_hw(self.roi_align_mask)), tuple(_scale_hw(self.roi_align_rgb)),
+               self.roi_align_mask.aligned, self.roi_align_rgb.aligned, dev.index)
+        bp = self._plans.get(key)
+        if bp is None:
+            bp = _BuiltPlan(self, dev, B, H, W, rois.shape[0])
+            if self.use_cuda_graph:
+                bp.plan.capture()
+            self._plans[key] = bp
+        return bp
+
+
+def _scale_hw(ra: DynamicRoIAlign):
+    return float(ra.spatial_scale_h), float(ra.spatial_scale_w)
+
+
+# ======================================================================================= plan construction
+class _BuiltPlan:
+    """One launch plan for a fixed (B,H,W,N): static input/output buffers + the op list."""
+
+    def __init__(self, m: HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet, dev, B, H, W, N):
+        self.m, self.dev, self.B, self.H, self.W, self.N = m, dev, B, H, W, N
+        self.plan = Plan(dev)
+        p = self.plan
+        self.images = p.f32(B, 3, H, W)
+        self.rois = p.f32(max(N, 1), 5, zero=True)
+        self.aux: Dict[str, torch.Tensor] = {}
+        self._scratch_free = []
+        self.act_rgb = {"relu": ACT["relu"], "swish": ACT["silu"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
+        self.act_ref = {"relu": ACT["relu"], "swish": ACT["swish"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
+        self.beta = m.activation_beta
+        p.tag = "unet"
+        self._build_unet()
+        p.tag = "head"
+        self._build_head()
+
+    # -------------------------------------------------------------- I/O
+    def load_inputs(self, images: torch.Tensor, rois: torch.Tensor):
+        self.images.copy_(images, non_blocking=True)
+        if self.N:
+            self.rois[: self.N].copy_(rois, non_blocking=True)
+
+    def outputs(self, copy: bool):
+        f = (lambda t: t.clone()) if copy else (lambda t: t)
+        aux = {k: f(v) for k, v in self.aux.items()}
+        return f(self.logits), aux
+
+    # -------------------------------------------------------------- helpers
+    def _is_bn(self, norm) -> bool:
+        return isinstance(norm, nn.BatchNorm2d)
+
+    def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
+             out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None) -> Optional[Act]:
+        """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel."""
+        p = self.plan
+        if norm is not None and not self._is_bn(norm):
+            raise NotImplementedError("normalization_type='layernorm2d' is not implemented on the B200 path yet "
+                                      "(all production presets use 'batchnorm')")
+        transposed = isinstance(conv, nn.ConvTranspose2d)
+        w = conv.weight
+        cout = w.shape[1] if transposed else w.shape[0]
+        cin = w.shape[0] if transposed else w.shape[1]
+        k = 1 if transposed else w.shape[2]
+        assert cin == x.C, (cin, x.C)
+        scale, shift = fold_bn(conv.bias, norm, cout)
+        oh, ow = (2 * x.H, 2 * x.W) if transposed else (x.H, x.W)
+        use_gemm = cin >= 16 and cout >= 16 and (transposed or k in (1, 3)) and out_f32 is None
+        if out is None and out_f32 is None:
+            out = p.act(x.N, oh, ow, cout)
+        if use_gemm:
+            nt, bn = ctypes.c_int(), ctypes.c_int()
+            p.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
+            slab = nt.value * bn.value
+            wp, cin_pad = pack_gemm_weight(w, slab, transposed)
+            p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(scale, slab)), p.const(pad_vec(shift, slab)), out,
+                        k, act, self.beta, res, res_mode, transposed)
+        else:
+            if transposed:
+                raise NotImplementedError("direct transposed convolution")
+            p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, p.const(pack_direct_weight(w), torch.float16), p.const(scale), p.const(shift),
+                          cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
+        return out
+
+    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None) -> Act:
+        t = self.conv(x, rb.conv1, rb.norm1, act)
+        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out)
+
+    def to_mask_size(self, t: torch.Tensor) -> torch.Tensor:
+        """F.interpolate(size=mask, bilinear, align_corners=False) when sizes differ (..._refinement.py:561-566)."""
+        mh, mw = self.m.mask_size
+        n, c, h, w = t.shape
+        if (h, w) == (mh, mw):
+            return t
+        out = self.plan.f32(n, c, mh, mw)
+        self.plan.add("resize_bilinear", self.plan.lib.his_resize_bilinear_f32, t.data_ptr(), n * c, h, w, mh, mw, out.data_ptr())
+        return out
+
+    def export_nchw(self, x: Act) -> torch.Tensor:
+        out = self.plan.f32(x.N, x.C, x.H, x.W)
+        self.plan.add("nhwc2nchw", self.plan.lib.his_nhwc_half_to_nchw_float, x.ptr, x.N, x.H * x.W, x.C, x.cs, out.data_ptr())
+        return out
+
+    # -------------------------------------------------------------- EfficientNet-UNet (full image)
+    def _build_unet(self):
+        m, p, L = self.m, self.plan, self.plan.lib
+        B, H, W = self.B, self.H, self.W
+        holder = m.pretrained_unet.model
+        net = holder.model
+        enc, dec = net.encoder, net.decoder
+        # input normalisation folded into the stem loader (device-side max check, no host sync)
+        flag = torch.zeros(1, dtype=torch.int32, device=self.dev); p.keep.append(flag)
+        affine = p.f32(6)
+        mean = (ctypes.c_float * 3)(*[float(v) for v in holder.norm_mean.flatten().tolist()])
+        std = (ctypes.c_float * 3)(*[float(v) for v in holder.norm_std.flatten().tolist()])
+        p.keep += [mean, std]
+        p.add("input_affine", L.his_unet_input_affine, self.images.data_ptr(), B * 3 * H * W, mean, std, flag.data_ptr(), affine.data_ptr())
+
+        # geometry of the five feature levels and the decoder concat buffers
+        sizes = [(H, W)]
+        h, w = _conv_out(H, 3, 2), _conv_out(W, 3, 2)
+        sizes.append((h, w))
+        stage_last = {1: None, 2: None, 4: None, 6: None}
+        for si, stage in enumerate(enc.blocks):
+            for blk in stage:
+                h, w = _conv_out(h, blk.k, blk.s), _conv_out(w, blk.k, blk.s)
+            if si in stage_last:
+                sizes.append((h, w))
+        oc = enc.out_channels                     # (3, c1, c2, c3, c4, c5)
+        cats = []
+        for i, blk in enumerate(dec.blocks):
+            th, tw = sizes[4 - i]                 # block i upsamples to feature level (4-i); level 0 = the image
+            cats.append(p.act(B, th, tw, blk.cin + blk.cskip))
+        skip_slot = {1: cats[3].slice(dec.blocks[3].cin, oc[1]), 2: cats[2].slice(dec.blocks[2].cin, oc[2]),
+                     3: cats[1].slice(dec.blocks[1].cin, oc[3]), 4: cats[0].slice(dec.blocks[0].cin, oc[4])}
+
+        # stem: conv3x3 s2 (no bias) + BN + SiLU, reading the NCHW fp32 images directly
+        stem_c = oc[1]
+        x = skip_slot[1]
+        scale, shift = fold_bn(None, enc.bn1, stem_c)
+        p.conv_direct(self.images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
+                      p.const(shift), stem_c, 3, 2, 1, ACT["silu"], 1.0, in_affine=affine, out=x)
+        level_of_stage = {1: 2, 2: 3, 4: 4}
+        for si, stage in enumerate(enc.blocks):
+            for bi, blk in enumerate(stage):
+                last_of_stage = bi == len(stage) - 1
+                dst = skip_slot[level_of_stage[si]] if (last_of_stage and si in level_of_stage) else None
+                x = self._mbconv(x, blk, dst)
+        # decoder (smp UnetDecoder, nearest resize + concat + 2x conv3x3-BN-ReLU)
+        for i, blk in enumerate(dec.blocks):
+            cat = cats[i]
+            up = cat.slice(0, blk.cin)
+            p.add("resize_nearest", L.his_resize_nearest, x.ptr, B, x.H, x.W, x.C, x.cs, cat.H, cat.W, up.ptr, up.cs)
+            full = Act(cat.buf, blk.cin + blk.cskip)
+            y = self.conv(full, blk.conv1[0], blk.conv1[1], ACT["relu"])
+            x = self.conv(y, blk.conv2[0], blk.conv2[1], ACT["relu"])
+        # segmentation head conv3x3 16->1 (+bias) -> fp32 logits; output_conv 1->2; export-wrapper binary mask
+        head = net.segmentation_head[0]
+        self.one = p.f32(B, 1, H, W)
+        p.conv_direct(x, 0, B, H, W, x.C, x.cs, p.const(pack_direct_weight(head.weight), torch.float16), p.const(torch.ones(1)),
+                      p.const(head.bias.detach().float()), 1, 3, 1, 1, ACT["none"], out_f32=self.one)
+        oc_w = m.pretrained_unet.output_conv.weight.detach().float().flatten().tolist()
+        oc_b = m.pretrained_unet.output_conv.bias.detach().float().flatten().tolist()
+        self.two = p.f32(B, 2, H, W)
+        self.binary = p.f32(B, 1, H, W)
+        p.add("unet_outputs", L.his_unet_outputs, self.one.data_ptr(), B, H, W, oc_w[0], oc_w[1], oc_b[0], oc_b[1], self.two.data_ptr(),
+              self.binary.data_ptr())
+
+    def _mbconv(self, x: Act, blk, dst: Optional[Act]) -> Act:
+        """timm DepthwiseSeparableConv / InvertedResidual (oracle/effunet.py _DS/_IR restates them)."""
+        p, L = self.plan, self.plan.lib
+        B = x.N
+        has_skip = blk.s == 1 and blk.cin == blk.cout
+        if blk.kind == "ir":
+            t = self.conv(x, blk.conv_pw, blk.bn1, ACT["silu"])
+            dw_bn, proj, proj_bn = blk.bn2, blk.conv_pwl, blk.bn3
+        else:
+            t = x
+            dw_bn, proj, proj_bn = blk.bn1, blk.conv_pw, blk.bn2
+        ho, wo = _conv_out(t.H, blk.k, blk.s), _conv_out(t.W, blk.k, blk.s)
+        d = p.act(B, ho, wo, blk.mid)
+        pool = p.f32(B, blk.mid)
+        p.add("memset", L.his_memset_async, pool.data_ptr(), 0, pool.numel() * 4)
+        wdw = blk.conv_dw.weight.detach().float().cpu().reshape(blk.mid, blk.k * blk.k).t().contiguous().half()
+        scale, shift = fold_bn(None, dw_bn, blk.mid)
+        p.add("depthwise", L.his_depthwise_conv, t.ptr, B, t.H, t.W, blk.mid, t.cs, p.const(wdw, torch.float16).data_ptr(),
+              p.const(scale).data_ptr(), p.const(shift).data_ptr(), blk.k, blk.s, ACT["silu"], d.ptr, d.cs, pool.data_ptr())
+        p._add_flops(2 * B * ho * wo * blk.mid * blk.k * blk.k, False)
+        se = blk.se
+        r = se.conv_reduce.weight.shape[0]
+        gate = p.f32(B, blk.mid)
+        p.add("se_gate", L.his_se_gate, pool.data_ptr(), B, ho * wo, blk.mid, r,
+              p.const(se.conv_reduce.weight.reshape(r, blk.mid)).data_ptr(), p.const(se.conv_reduce.bias).data_ptr(),
+              p.const(se.conv_expand.weight.reshape(blk.mid, r)).data_ptr(), p.const(se.conv_expand.bias).data_ptr(),
+              ACT["silu"], 1.0, gate.data_ptr())
+        p.add("scale_channels", L.his_scale_channels, d.ptr, d.cs, gate.data_ptr(), B, ho * wo, blk.mid, d.ptr, d.cs)
+        return self.conv(d, proj, proj_bn, ACT["none"], res=x if has_skip else None, res_mode=RES_ADD if has_skip else RES_NONE, out=dst)
+
+    # -------------------------------------------------------------- per-ROI head
+    def _build_head(self):
+        m, p, L = self.m, self.plan, self.plan.lib
+        N, B, H, W = self.N, self.B, self.H, self.W
+        rh, rw = m.roi_size
+        mh, mw = m.mask_size
+        aux_level = m.aux_outputs
+        self.logits = p.f32(N, 3, mh, mw)
+        self.aux = {}
+        if aux_level != "none":
+            self.aux["full_image_logits"] = self.two
+        if N == 0:
+            return
+        A_rgb, A_ref = self.act_rgb, self.act_ref
+
+        # --- Dynamic RoI Align (rgb.py:751-755): UNet logits -> channels 256..257 of the combiner input, RGB -> patches
+        comb_in = p.act(N, rh, rw, 258)
+        patches = p.act(N, rh, rw, 3)
+        roi_feat = p.f32(N, 2, rh, rw)
+        roi_patch = p.f32(N, 3, rh, rw) if aux_level != "none" else None
+        ram, rar = m.roi_align_mask, m.roi_align_rgb
+        msk = comb_in.slice(256, 2)
+        p.add("roi_align_mask", L.his_roi_align, self.two.data_ptr(), 0, 2 * H * W, H * W, W, 1, B, 2, H, W, self.rois.data_ptr(), N, rh, rw,
+              float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0, msk.ptr, msk.cs, roi_feat.data_ptr())
+        p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.rois.data_ptr(), N, rh, rw,
+              float(rar.spatial_scale_h), float(rar.spatial_scale_w), 1 if rar.aligned else 0, patches.ptr, patches.cs,
+              roi_patch.data_ptr() if roi_patch is not None else None)
+
+        # --- rgb_feature_extractor (rgb.py:657-673)
+        fe = m.rgb_feature_extractor
+        x = patches
+        for i in (0, 4, 8):
+            x = self.conv(x, fe[i], fe[i + 1], A_rgb)
+            x = self.residual_block(x, fe[i + 3], A_ref)
+        self.conv(x, fe[12], fe[13], A_rgb, out=comb_in.slice(0, 256))
+        # --- feature_combiner 1x1 258->256 (rgb.py:695,758-762); the concat is the buffer layout itself
+        feats = self.conv(Act(comb_in.buf, 258), m.feature_combiner, None, ACT["none"])
+
+        bh = m.segmentation_head.base_head
+        # --- shared trunk (..._refinement.py:479-487)
+        sf = bh.shared_features
+        shared = self.conv(feats, sf[0], sf[1], A_ref)
+        shared = self.residual_block(shared, sf[4], A_ref)
+        shared = self.residual_block(shared, sf[6], A_ref)
+        # --- bg/fg EnhancedUNet -> low-res logits (fp32 NCHW)
+        low = p.f32(N, 2, rh, rw)
+        self._enhanced_unet(shared, bh.bg_vs_fg_unet, low)
+        # --- upsample_bg_fg (fused) + resize + softmax happens inside the combine
+        up = bh.upsample_bg_fg
+        s32, t32 = fold_bn(up[0].bias, up[1] if self._is_bn(up[1]) else self._ln_unsupported(), 32)
+        bgfg_nat = p.f32(N, 2, 2 * rh, 2 * rw)
+        p.add("upsample_bgfg", L.his_upsample_bgfg, low.data_ptr(), N, rh, rw, p.const(up[0].weight).data_ptr(), p.const(s32).data_ptr(),
+              p.const(t32).data_ptr(), p.const(up[3].weight.reshape(2, 32)).data_ptr(), p.const(up[3].bias).data_ptr(), A_ref, self.beta,
+              bgfg_nat.data_ptr())
+        bgfg = self.to_mask_size(bgfg_nat)
+        # --- fg_gate (..._refinement.py:537-545,569-570): 1x1 2->64 (from the fp32 logits), 64->128, 128->256, sigmoid, * shared
+        fg = bh.fg_gate
+        g1 = p.act(N, rh, rw, 64)
+        sc, sh = fold_bn(fg[0].bias, None, 64)
+        p.conv_direct(low, 1, N, rh, rw, 2, 0, p.const(pack_direct_weight(fg[0].weight), torch.float16), p.const(sc), p.const(sh), 64, 1, 1, 0,
+                      A_ref, self.beta, out=g1)
+        g2 = self.conv(g1, fg[3], None, A_ref)
+        if aux_level == "full":
+            gate = self.conv(g2, fg[5], None, ACT["sigmoid"])
+            self.aux["fg_attention"] = self.export_nchw(gate)
+        gated = self.conv(g2, fg[5], None, ACT["sigmoid"], res=shared, res_mode=RES_MUL)
+        # --- target vs non-target branch
+        tb = bh.target_vs_nontarget_branch
+        x = self.residual_block(gated, tb[0], A_ref)
+        if m.use_attention_module:
+            sa = p.act(N, rh, rw, 256)
+            stats = p.f32(N, rh, rw, 2)
+            kk = tb[1].conv.weight.shape[-1]
+            p.add("spatial_attention", L.his_spatial_attention, x.ptr, N, rh, rw, 256, x.cs, p.const(tb[1].conv.weight.reshape(2, kk, kk)).data_ptr(),
+                  kk, stats.data_ptr(), sa.ptr, sa.cs)
+            x = self.conv(sa, tb[3], tb[4], A_ref)                       # ConvT 256->128 k2s2 + norm + act
+            ca = tb[6]
+            r = ca.fc1.weight.shape[0]
+            pool = p.f32(N, 128); gate_c = p.f32(N, 128)
+            p.add("memset", L.his_memset_async, pool.data_ptr(), 0, pool.numel() * 4)
+            p.add("pool_sum", L.his_pool_sum, x.ptr, N, x.H * x.W, 128, x.cs, pool.data_ptr())
+            p.add("se_gate", L.his_se_gate, pool.data_ptr(), N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
+                  p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, gate_c.data_ptr())
+            p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
+            x = self.residual_block(x, tb[8], A_ref)
+            tail = tb[9]
+        else:
+            x = self.conv(x, tb[2], tb[3], A_ref)
+            x = self.residual_block(x, tb[6], A_ref)
+            tail = tb[7]
+        tn_nat = p.f32(N, 2, 2 * rh, 2 * rw)
+        self.conv(x, tail, None, ACT["none"], out_f32=tn_nat)
+        tn = self.to_mask_size(tn_nat)
+        p.add("head_combine", L.his_head_combine, bgfg.data_ptr(), tn.data_ptr(), N, mh, mw, self.logits.data_ptr())
+
+        if aux_level != "none":
+            self.aux.update({"bg_fg_logits": bgfg, "bg_fg_logits_low": low, "target_nontarget_logits": tn})
+            if aux_level == "full":
+                self.aux["shared_features"] = self.export_nchw(shared)
+        # --- auxiliary branches (..._refinement.py:772-802); computed like the reference forward does
+        head = m.segmentation_head
+        if m.use_contour_detection:
+            cb = head.contour_branch.contour_branch
+            c = self.conv(shared, cb[0], cb[1], A_ref)
+            c = self.conv(c, cb[3], cb[4], A_ref)
+            c_low = p.f32(N, 1, rh, rw)
+            self.conv(c, cb[6], None, ACT["sigmoid"], out_f32=c_low)
+            contours = self.to_mask_size(c_low)
+            if aux_level != "none":
+                self.aux["contours"] = contours
+        if m.use_distance_transform:
+            dd = head.distance_decoder
+            dh = dd.distance_head
+            d = self.conv(shared, dh[0], dh[1], A_ref)
+            d = self.residual_block(d, dh[3], A_ref)
+            d_low = p.f32(N, 1, rh, rw)
+            self.conv(d, dh[4], None, ACT["none"], out_f32=d_low)
+            m_low = p.f32(N, 1, rh, rw)
+            thr = p.const(dd.threshold.detach().reshape(1))
+            p.add("distance_mask", L.his_map_f32, d_low.data_ptr(), d_low.numel(), 1, thr.data_ptr(), m_low.data_ptr())
+            dmask, dmap = self.to_mask_size(m_low), self.to_mask_size(d_low)
+            if aux_level != "none":
+                self.aux["distance_mask"], self.aux["distance_map"] = dmask, dmap
+        if aux_level != "none":
+            self.aux["roi_features"] = roi_feat
+            self.aux["roi_patches"] = roi_patch
+
+    def _ln_unsupported(self):
+        raise NotImplementedError("normalization_type='layernorm2d' is not implemented on the B200 path yet")
+
+    def _enhanced_unet(self, x: Act, u: pt.EnhancedUNetParams, low_out: torch.Tensor):
+        """EnhancedUNet.forward (..._unet.py:375-417).  Skip concats are buffer layouts: decoder level i reads
+        [ConvT output | encoder skip] from one [N,h,w,2c] buffer."""
+        p, L = self.plan, self.plan.lib
+        A = self.act_rgb
+        d, ch, N = u.depth, u.channels, x.N
+        # spatial size per level
+        hw = [(x.H, x.W)]
+        for i in range(1, d):
+            hw.append((hw[-1][0] // 2, hw[-1][1] // 2))
+        cats = {}
+        for lvl in range(d - 1):                                     # level lvl has ch[lvl+1] channels
+            c = ch[lvl + 1]
+            if hw[lvl] != (hw[lvl + 1][0] * 2, hw[lvl + 1][1] * 2):
+                raise NotImplementedError("EnhancedUNet with odd intermediate sizes (bilinear re-alignment of the skip, "
+                                          "..._unet.py:408) is not implemented; use roi sizes divisible by 2**(depth-1)")
+            cats[lvl] = p.act(N, hw[lvl][0], hw[lvl][1], 2 * c)
+        for i in range(d):
+            e = u.encoders[i]
+            dst = cats[i].slice(ch[i + 1], ch[i + 1]) if i < d - 1 else None
+            if i == 0:
+                x = self.conv(x, e[0], e[1], A)
+                x = self.residual_block(x, e[3], A)
+                x = self.residual_block(x, e[4], A, out=dst)
+            else:
+                x = self.residual_block(x, e[0], A)
+                x = self.residual_block(x, e[1], A)
+                x = self.conv(x, e[2], e[3], A, out=dst)
+            if i < d - 1:
+                pooled = p.act(N, hw[i + 1][0], hw[i + 1][1], ch[i + 1])
+                p.add("maxpool2", L.his_maxpool2, x.ptr, N, x.H, x.W, x.C, x.cs, pooled.ptr, pooled.cs)
+                x = pooled
+        b = u.bottleneck
+        a = self.residual_block(x, b[0], A)
+        a = self.residual_block(a, b[1], A)
+        a = self.conv(a, b[2], b[3], A)
+        a = self.conv(a, b[5], None, ACT["sigmoid"])
+        x = self.conv(x, u.bottleneck_conv, None, ACT["none"], res=a, res_mode=RES_MUL)
+        for i in range(d - 1):
+            lvl = d - 2 - i
+            c = ch[lvl + 1]
+            self.conv(x, u.upconvs[i], None, ACT["none"], out=cats[lvl].slice(0, c))
+            dec = u.decoders[i]
+            x = self.conv(Act(cats[lvl].buf, 2 * c), dec[0], dec[1], A)
+            x = self.residual_block(x, dec[3], A)
+            x = self.residual_block(x, dec[4], A)
+        f = u.final
+        x = self.conv(x, f[0], f[1], A)
+        self.conv(x, f[3], None, ACT["none"], out_f32=low_out)
+
+
+# ======================================================================================= factory
+def create_rgb_hierarchical_model(roi_size: Union[int, Tuple[int, int]] = 28, mask_size: Union[int, Tuple[int, int]] = 56,
+                                  multi_scale: bool = False, activation_function: str = "relu", activation_beta: float = 1.0,
+                                  normalization_type: str = "layernorm2d", normalization_groups: int = 8, **kwargs) -> nn.Module:
+    """Same signature and kwarg handling as the reference factory (rgb.py:925-1026)."""
+    use_attention_module = kwargs.pop("use_attention_module", False)
+    use_boundary_refinement = kwargs.pop("use_boundary_refinement", False)
+    use_progressive_upsampling = kwargs.pop("use_progressive_upsampling", False)
+    use_subpixel_conv = kwargs.pop("use_subpixel_conv", False)
+    use_contour_detection = kwargs.pop("use_contour_detection", False)
+    use_distance_transform = kwargs.pop("use_distance_transform", False)
+    use_pretrained_unet = kwargs.pop("use_pretrained_unet", False)
+    pretrained_weights_path = kwargs.pop("pretrained_weights_path", "")
+    freeze_pretrained_weights = kwargs.pop("freeze_pretrained_weights", False)
+    use_full_image_unet = kwargs.pop("use_full_image_unet", False)
+    kwargs.pop("roi_sizes", None)
+    kwargs.pop("fusion_method", None)
+    if multi_scale:
+        raise NotImplementedError("MultiScaleRGBSegmentationModel (rgb.py:777-922) is outside the B200 hot path (SURVEY §8f rank 4)")
+    if not (use_pretrained_unet and use_full_image_unet):
+        raise NotImplementedError("only the full-image pretrained-UNet model (use_pretrained_unet=True, use_full_image_unet=True) "
+                                  "-- the path every B0/B1/B7 preset takes -- is implemented on B200")
+    return HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(
+        roi_size=roi_size, mask_size=mask_size, pretrained_weights_path=pretrained_weights_path,
+        use_attention_module=use_attention_module, freeze_pretrained_weights=freeze_pretrained_weights,
+        use_boundary_refinement=use_boundary_refinement, use_progressive_upsampling=use_progressive_upsampling,
+        use_subpixel_conv=use_subpixel_conv, use_contour_detection=use_contour_detection,
+        use_distance_transform=use_distance_transform, normalization_type=normalization_type,
+        normalization_groups=normalization_groups, activation_function=activation_function, activation_beta=activation_beta, **kwargs)

@@ -1,0 +1,271 @@
+"""Parameter containers that reproduce the reference's state-dict key names and shapes.
+
+The modules here only *hold* parameters (``nn.Conv2d`` / ``nn.BatchNorm2d`` are used as typed
+containers so shapes, dtypes and default initialisation match the reference); their
+``forward`` is never called -- the compute runs in ``libhis_b200.so`` (see ``engine.py``).
+
+Key-name sources in the reference (``hed/`` = src/human_edge_detection/):
+  * hed/advanced/hierarchical_segmentation_rgb.py:564-727 (model), :657-673 (feature extractor)
+  * hed/advanced/hierarchical_segmentation_refinement.py:31-55, 255-344, 434-548, 609-732
+  * hed/advanced/hierarchical_segmentation_unet.py:35-58, 277-372, 1708-1971
+  * smp 0.5.0 / timm 1.0.19 EfficientNet-UNet key scheme (evidence: ..._unet.py:1815-1828,
+    export_peopleseg_onnx.py:111-136)
+"""
+from __future__ import annotations
+
+import math
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+
+class Slot(nn.Identity):
+    """Index placeholder for parameter-free reference modules (activations, dropout, sigmoid)."""
+
+
+class LayerNorm2dParams(nn.Module):
+    """hed/model.py:18-38 -- affine kept as [1,C,1,1]."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(1, c, 1, 1))
+        self.bias = nn.Parameter(torch.zeros(1, c, 1, 1))
+        self.eps = 1e-5
+
+
+def norm_params(kind: str, c: int) -> nn.Module:
+    """hed/advanced/normalization_comparison.py:159-206 (the two kinds the B200 path implements)."""
+    k = kind.lower()
+    if k in ("layer", "layernorm", "layernorm2d"):
+        return LayerNorm2dParams(c)
+    if k in ("batch", "batchnorm", "batchnorm2d"):
+        return nn.BatchNorm2d(c)
+    if k in ("instance", "instancenorm", "instancenorm2d", "group", "groupnorm", "adaptive_instance", "spatial_group",
+             "foreground_aware", "mixed"):
+        raise NotImplementedError(f"normalization_type={kind!r} is not implemented by the B200 path "
+                                  "(presets use 'batchnorm'; 'layernorm2d' is the factory default)")
+    raise ValueError(f"Unknown normalization type: {k}")
+
+
+def check_activation(name: str) -> str:
+    n = name.lower()
+    if n not in ("relu", "swish", "gelu", "silu"):
+        raise ValueError(f"Unknown activation function: {n}")
+    return n
+
+
+class ResidualBlockParams(nn.Module):
+    def __init__(self, c: int, norm: str):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, padding=1)
+        self.norm1 = norm_params(norm, c)
+        self.conv2 = nn.Conv2d(c, c, 3, padding=1)
+        self.norm2 = norm_params(norm, c)
+
+
+class EnhancedUNetParams(nn.Module):
+    """..._unet.py:277-372."""
+
+    def __init__(self, cin: int, base: int, depth: int, norm: str):
+        super().__init__()
+        self.depth = depth
+        ch = [cin] + [base * (2 ** i) for i in range(depth)]
+        self.channels = ch
+        self.encoders = nn.ModuleList()
+        for i in range(depth):
+            if i == 0:
+                enc = nn.Sequential(nn.Conv2d(ch[0], ch[1], 3, padding=1), norm_params(norm, ch[1]), Slot(),
+                                    ResidualBlockParams(ch[1], norm), ResidualBlockParams(ch[1], norm))
+            else:
+                enc = nn.Sequential(ResidualBlockParams(ch[i], norm), ResidualBlockParams(ch[i], norm),
+                                    nn.Conv2d(ch[i], ch[i + 1], 3, padding=1), norm_params(norm, ch[i + 1]), Slot())
+            self.encoders.append(enc)
+        self.pools = nn.ModuleList([Slot() for _ in range(depth - 1)])
+        self.bottleneck = nn.Sequential(ResidualBlockParams(ch[-1], norm), ResidualBlockParams(ch[-1], norm),
+                                        nn.Conv2d(ch[-1], ch[-1], 3, padding=1), norm_params(norm, ch[-1]), Slot(),
+                                        nn.Conv2d(ch[-1], ch[-1], 1), Slot())
+        self.bottleneck_conv = nn.Conv2d(ch[-1], ch[-1], 3, padding=1)
+        self.upconvs = nn.ModuleList()
+        self.decoders = nn.ModuleList()
+        for i in range(depth - 1, 0, -1):
+            self.upconvs.append(nn.ConvTranspose2d(ch[i + 1], ch[i], 2, stride=2))
+            self.decoders.append(nn.Sequential(nn.Conv2d(ch[i] * 2, ch[i], 3, padding=1), norm_params(norm, ch[i]), Slot(),
+                                               ResidualBlockParams(ch[i], norm), ResidualBlockParams(ch[i], norm)))
+        self.final = nn.Sequential(nn.Conv2d(ch[1], ch[1] // 2, 3, padding=1), norm_params(norm, ch[1] // 2), Slot(),
+                                   nn.Conv2d(ch[1] // 2, 2, 1))
+
+
+class ChannelAttentionParams(nn.Module):
+    def __init__(self, c: int, reduction: int = 8, min_channels: int = 8):
+        super().__init__()
+        r = max(c // reduction, min_channels)
+        self.fc1 = nn.Conv2d(c, r, 1, bias=False)
+        self.activation = Slot()
+        self.fc2 = nn.Conv2d(r, c, 1, bias=False)
+        self.sigmoid = Slot()
+
+
+class SpatialAttentionParams(nn.Module):
+    def __init__(self, k: int = 7):
+        super().__init__()
+        self.conv = nn.Conv2d(2, 1, k, padding=k // 2, bias=False)
+        self.sigmoid = Slot()
+
+
+class BaseHeadParams(nn.Module):
+    """ExtendedHierarchicalSegmentationHeadUNetV2, ..._refinement.py:434-548."""
+
+    def __init__(self, cin: int, mid: int, norm: str, attention: bool, base: int, depth: int):
+        super().__init__()
+        self.shared_features = nn.Sequential(nn.Conv2d(cin, mid, 3, padding=1), norm_params(norm, mid), Slot(), Slot(),
+                                             ResidualBlockParams(mid, norm), Slot(), ResidualBlockParams(mid, norm))
+        self.bg_vs_fg_unet = EnhancedUNetParams(mid, base, depth, norm)
+        self.upsample_bg_fg = nn.Sequential(nn.ConvTranspose2d(2, 32, 2, stride=2), norm_params(norm, 32), Slot(), nn.Conv2d(32, 2, 1))
+        h = mid // 2
+        if attention:
+            self.target_vs_nontarget_branch = nn.ModuleList([
+                ResidualBlockParams(mid, norm), SpatialAttentionParams(7), Slot(), nn.ConvTranspose2d(mid, h, 2, stride=2),
+                norm_params(norm, h), Slot(), ChannelAttentionParams(h, 8), Slot(), ResidualBlockParams(h, norm), nn.Conv2d(h, 2, 1)])
+        else:
+            self.target_vs_nontarget_branch = nn.Sequential(
+                ResidualBlockParams(mid, norm), Slot(), nn.ConvTranspose2d(mid, h, 2, stride=2), norm_params(norm, h), Slot(), Slot(),
+                ResidualBlockParams(h, norm), nn.Conv2d(h, 2, 1))
+        self.fg_gate = nn.Sequential(nn.Conv2d(2, mid // 4, 1), Slot(), Slot(), nn.Conv2d(mid // 4, mid // 2, 1), Slot(),
+                                     nn.Conv2d(mid // 2, mid, 1), Slot())
+
+
+class ContourBranchParams(nn.Module):
+    def __init__(self, cin: int, c: int, norm: str):
+        super().__init__()
+        self.contour_branch = nn.Sequential(nn.Conv2d(cin, c, 3, padding=1), norm_params(norm, c), Slot(),
+                                            nn.Conv2d(c, c, 3, padding=1), norm_params(norm, c), Slot(), nn.Conv2d(c, 1, 1), Slot())
+
+
+class DistanceDecoderParams(nn.Module):
+    def __init__(self, cin: int, c: int, norm: str):
+        super().__init__()
+        self.distance_head = nn.Sequential(nn.Conv2d(cin, c, 3, padding=1), norm_params(norm, c), Slot(),
+                                           ResidualBlockParams(c, norm), nn.Conv2d(c, 1, 1))
+        self.threshold = nn.Parameter(torch.tensor(0.3))
+
+
+class RefinedHeadParams(nn.Module):
+    """RefinedHierarchicalSegmentationHead, ..._refinement.py:609-732 (preset flags)."""
+
+    def __init__(self, cin, mid, norm, attention, contour, distance, base, depth):
+        super().__init__()
+        self.base_head = BaseHeadParams(cin, mid, norm, attention, base, depth)
+        if contour:
+            self.contour_branch = ContourBranchParams(mid, 64, norm)
+        if distance:
+            self.distance_decoder = DistanceDecoderParams(mid, 128, norm)
+
+
+# ----------------------------------------------------------------------------- EfficientNet-UNet (smp/timm key scheme)
+_ARCH = [("ds", 1, 3, 1, 1, 16), ("ir", 2, 3, 2, 6, 24), ("ir", 2, 5, 2, 6, 40), ("ir", 3, 3, 2, 6, 80),
+         ("ir", 3, 5, 1, 6, 112), ("ir", 4, 5, 2, 6, 192), ("ir", 1, 3, 1, 6, 320)]
+_SCALING = {"b0": (1.0, 1.0), "b1": (1.0, 1.1), "b2": (1.1, 1.2), "b3": (1.2, 1.4), "b4": (1.4, 1.8), "b5": (1.6, 2.2),
+            "b6": (1.8, 2.6), "b7": (2.0, 3.1)}
+DECODER_CHANNELS = (256, 128, 64, 32, 16)
+
+
+def round_channels(c: float, mult: float = 1.0, div: int = 8) -> int:
+    v = c * mult
+    n = max(div, int(v + div / 2) // div * div)
+    return n + div if n < 0.9 * v else n
+
+
+def encoder_variant(encoder_name: str) -> str:
+    n = encoder_name.lower()
+    if "efficientnet" not in n:
+        raise NotImplementedError(f"encoder {encoder_name!r}: only timm-efficientnet-b0..b7 are implemented")
+    for k in _SCALING:
+        if n.endswith(k):
+            return k
+    raise NotImplementedError(f"encoder {encoder_name!r}: only timm-efficientnet-b0..b7 are implemented")
+
+
+class SEParams(nn.Module):
+    def __init__(self, c, r):
+        super().__init__()
+        self.conv_reduce = nn.Conv2d(c, r, 1)
+        self.conv_expand = nn.Conv2d(r, c, 1)
+
+
+class DSBlockParams(nn.Module):
+    kind = "ds"
+
+    def __init__(self, k, s, cin, cout):
+        super().__init__()
+        self.k, self.s, self.cin, self.cout, self.mid = k, s, cin, cout, cin
+        self.conv_dw = nn.Conv2d(cin, cin, k, s, ((s - 1) + (k - 1)) // 2, groups=cin, bias=False)
+        self.bn1 = nn.BatchNorm2d(cin)
+        self.se = SEParams(cin, round(cin * 0.25))
+        self.conv_pw = nn.Conv2d(cin, cout, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+
+
+class IRBlockParams(nn.Module):
+    kind = "ir"
+
+    def __init__(self, k, s, e, cin, cout):
+        super().__init__()
+        mid = round_channels(cin * e)
+        self.k, self.s, self.cin, self.cout, self.mid = k, s, cin, cout, mid
+        self.conv_pw = nn.Conv2d(cin, mid, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(mid)
+        self.conv_dw = nn.Conv2d(mid, mid, k, s, ((s - 1) + (k - 1)) // 2, groups=mid, bias=False)
+        self.bn2 = nn.BatchNorm2d(mid)
+        self.se = SEParams(mid, round(mid * (0.25 / e)))
+        self.conv_pwl = nn.Conv2d(mid, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout)
+
+
+class EncoderParams(nn.Module):
+    def __init__(self, variant: str):
+        super().__init__()
+        w, d = _SCALING[variant]
+        stem = round_channels(32, w)
+        self.conv_stem = nn.Conv2d(3, stem, 3, 2, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(stem)
+        stages, cin = [], stem
+        for kind, r, k, s, e, c in _ARCH:
+            cout = round_channels(c, w)
+            blocks = []
+            for i in range(int(math.ceil(r * d))):
+                st = s if i == 0 else 1
+                blocks.append(DSBlockParams(k, st, cin, cout) if kind == "ds" else IRBlockParams(k, st, e, cin, cout))
+                cin = cout
+            stages.append(nn.Sequential(*blocks))
+        self.blocks = nn.Sequential(*stages)
+        self.conv_head = nn.Conv2d(cin, round_channels(1280, w), 1, bias=False)   # in the state dict, unused in forward
+        self.bn2 = nn.BatchNorm2d(round_channels(1280, w))
+        self.out_channels: Tuple[int, ...] = (3, stem, stages[1][-1].cout, stages[2][-1].cout, stages[4][-1].cout, stages[6][-1].cout)
+
+
+class DecoderBlockParams(nn.Module):
+    def __init__(self, cin, cskip, cout):
+        super().__init__()
+        self.cin, self.cskip, self.cout = cin, cskip, cout
+        self.conv1 = nn.Sequential(nn.Conv2d(cin + cskip, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), Slot())
+        self.conv2 = nn.Sequential(nn.Conv2d(cout, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), Slot())
+
+
+class DecoderParams(nn.Module):
+    def __init__(self, enc_channels):
+        super().__init__()
+        enc = list(enc_channels[1:])[::-1]
+        ins = [enc[0]] + list(DECODER_CHANNELS[:-1])
+        skips = enc[1:] + [0]
+        self.blocks = nn.ModuleList([DecoderBlockParams(i, s, o) for i, s, o in zip(ins, skips, DECODER_CHANNELS)])
+
+
+class SmpUnetParams(nn.Module):
+    """Same keys as ``smp.Unet(encoder_name, classes=1, encoder_weights=None)`` (..._unet.py:1770-1774)."""
+
+    def __init__(self, encoder_name: str):
+        super().__init__()
+        self.encoder = EncoderParams(encoder_variant(encoder_name))
+        self.decoder = DecoderParams(self.encoder.out_channels)
+        self.segmentation_head = nn.Sequential(nn.Conv2d(DECODER_CHANNELS[-1], 1, 3, padding=1), Slot(), Slot())

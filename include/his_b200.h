@@ -1,0 +1,147 @@
+/*
+ * his_b200.h -- C ABI of libhis_b200.so, the B200 (sm_100a) kernels behind the reference's
+ * `src/human_edge_detection` model / ROI API (PINTO0309/human-instance-segmentation).
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); each entry point below replaces
+ * the ATen op(s) the reference dispatches at the cited file:line.  Conventions:
+ *   - every function returns 0 (HIS_OK) or a negative error code; his_last_error() gives text;
+ *   - plain pointers + explicit shapes/strides, no torch types; nothing allocates device memory
+ *     (the caller owns every buffer); `stream` is a cudaStream_t passed as void*;
+ *   - "NHWC half slice": fp16, channel-last, per-pixel stride `cs` elements (cs % 8 == 0), the
+ *     pointer already offset to the first channel of the slice (offset % 8 == 0);
+ *   - small (<= 3 channel) tensors that the reference returns to callers are NCHW fp32.
+ * Citations are relative to /root/reference/ ("hed/" = src/human_edge_detection/).
+ */
+#ifndef HIS_B200_H_
+#define HIS_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIS_OK 0
+#define HIS_ERR_INVALID_ARG (-1)
+#define HIS_ERR_UNSUPPORTED (-2)
+#define HIS_ERR_LAUNCH (-3)
+#define HIS_ERR_DRIVER (-4)
+#define HIS_ERR_NO_DEVICE (-5)
+
+/* activation codes: hed/advanced/activation_utils.py:71-103, hierarchical_segmentation_rgb.py:21-40 */
+#define HIS_ACT_NONE 0
+#define HIS_ACT_RELU 1
+#define HIS_ACT_SILU 2
+#define HIS_ACT_SIGMOID 3
+#define HIS_ACT_SWISH 4 /* x*sigmoid(beta*x) */
+#define HIS_ACT_GELU 5
+/* epilogue second operand: ADD = residual before the activation (ResidualBlock, ..._refinement.py:46-55),
+ * MUL = gate after the activation (fg_gate ..._refinement.py:569-570, bottleneck attention ..._unet.py:394-395) */
+#define HIS_RES_NONE 0
+#define HIS_RES_ADD 1
+#define HIS_RES_MUL 2
+
+const char* his_last_error(void);
+int his_version(void);
+
+/* ---- DynamicRoIAlign.forward, hed/dynamic_roi_align.py:56-171 (index_select + grid_sample).
+ * feat: [B,C,H,W] with element strides sN,sC,sH,sW (fp32, or fp16 if feat_is_half).
+ * rois: device [n_rois,5] fp32 {batch_idx,x1,y1,x2,y2}, normalised coordinates.
+ * Writes an NHWC half slice [n_rois,oh,ow,C] and/or NCHW fp32 [n_rois,C,oh,ow] (either may be NULL). */
+int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC, long long sH, long long sW,
+                  int B, int C, int H, int W, const float* rois, int n_rois, int oh, int ow,
+                  float scale_h, float scale_w, int aligned, void* out_half, int out_cs, float* out_f32, void* stream);
+
+/* ---- dense conv2d 3x3(pad 1)/1x1, stride 1, and conv_transpose2d k2 s2, as tcgen05 implicit GEMM
+ * (hed/advanced/hierarchical_segmentation_rgb.py:657-673,695; ..._refinement.py:37-39,479-523,537-545;
+ *  ..._unet.py:44-47,313-372; smp decoder convs / timm 1x1 convs, see oracle/effunet.py).
+ * y = act(conv(x)*scale[c] + shift[c] (+res)) (*res), fp16 in/out, fp32 accumulate.
+ * w_packed: fp16 [groups][taps][cout_slab][cin_pad] (groups = 4 for transposed: (dy,dx) = (g>>1,g&1)),
+ * cout_slab = n_tiles*block_n from his_conv_gemm_tile_n; scale/shift: device fp32 [cout_slab].
+ * The plan captures the pointers (TMA descriptors); run it any number of times. */
+int his_conv_gemm_tile_n(int cout, int* n_tiles, int* block_n);
+int his_conv_gemm_create(void** plan, const void* in, int n_img, int H, int W, int cin, int in_cs,
+                         const void* w_packed, int cin_pad, void* out, int cout, int out_cs,
+                         const void* res, int res_cs, const float* scale, const float* shift,
+                         int ksize, int transposed, int act, float act_beta, int res_mode);
+int his_conv_gemm_run(void* plan, void* stream);
+int his_conv_gemm_destroy(void* plan);
+long long his_conv_gemm_issued_macs(void* plan);
+
+/* ---- direct convolution for the shapes that are not GEMM-worthy (Cin = 2/3, Cout <= 2 tails, strided stem,
+ * segmentation head): rgb.py:657 (3->64), ..._refinement.py:506,523,537 (tails / 2->64), ..._unet.py:371,
+ * timm conv_stem, smp segmentation_head.  in_fmt 0: NHWC half slice; 1: NCHW fp32 with optional per-channel
+ * input affine x*a[c]+b[c] (device [2*cin], applied to in-bounds samples only = normalise-then-zero-pad).
+ * w: fp16 [kh][kw][cin][cout]. Writes NHWC half slice and/or NCHW fp32. */
+int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, int H, int W, int cin, int in_cs,
+                    const void* w, const float* scale, const float* shift, int cout, int kh, int kw, int stride, int pad,
+                    int act, float act_beta, int res_mode, const void* res, int res_cs,
+                    void* out_half, int out_cs, float* out_f32, void* stream);
+
+/* ---- timm DepthwiseSeparableConv / InvertedResidual depthwise conv + BN + act (oracle/effunet.py _DS/_IR);
+ * symmetric padding ((s-1)+(k-1))/2; w: fp16 [k*k][C]; optionally accumulates per-(n,c) sums of the output
+ * (fp32 [N,C], caller zeroes) for the squeeze-excite pooling that follows. */
+int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale,
+                       const float* shift, int k, int stride, int act, void* out, int out_cs, float* pool_sums, void* stream);
+
+/* ---- squeeze-excite (timm SqueezeExcite) and ChannelAttentionModule (hed/advanced/attention_modules.py:10-64):
+ * pool_sum: per-(n,c) sums (caller zeroes pool_sums); se_gate: gate = sigmoid(W2*act(W1*mean+b1)+b2), fp32 weights
+ * w1 [R,C], w2 [C,R], biases may be NULL; scale_channels: out = in * gate[n,c]. */
+int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, void* stream);
+int his_se_gate(const float* pool_sums, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2,
+                const float* b2, int act, float act_beta, float* gate, void* stream);
+int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream);
+
+/* ---- SpatialAttentionModule, hed/advanced/attention_modules.py:67-113: out = x*sigmoid(conv_kxk([mean_c,max_c])).
+ * w: fp32 [2][k][k]; stats_ws: fp32 workspace [N*H*W*2]. */
+int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs, const float* w, int k, float* stats_ws,
+                          void* out, int out_cs, void* stream);
+
+/* ---- nn.MaxPool2d(2) (..._unet.py:332), nearest resize (smp UnetDecoderBlock), bilinear align_corners=False
+ * (F.interpolate at ..._refinement.py:561-566,581-586,772-802) */
+int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, void* stream);
+int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream);
+int his_resize_bilinear_f32(const float* in, int NC, int H, int W, int Ho, int Wo, float* out, void* stream);
+
+/* ---- head tails: upsample_bg_fg (..._refinement.py:501-506) fused ConvT(2->32,k2,s2)+BN+act+1x1(32->2), NCHW fp32;
+ * hierarchical combine (:588-596); elementwise sigmoid / sigmoid((x-*param)*10) (:294,:341). */
+int his_upsample_bgfg(const float* low, int N, int h, int w, const float* wt, const float* scale, const float* shift,
+                      const float* w1, const float* b1, int act, float act_beta, float* out, void* stream);
+int his_head_combine(const float* bgfg, const float* tn, int N, int H, int W, float* logits, void* stream);
+int his_map_f32(const float* in, long long total, int op, const float* param, float* out, void* stream);
+int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, void* stream);
+
+/* ---- PreTrainedPeopleSegmentationUNet.normalize_input (..._unet.py:1885-1890) without the host sync:
+ * affine6 = {a0,a1,a2,b0,b1,b2}, a = 1/(d*std), b = -mean/std, d = 255 iff max(images) > 1.  mean3/std3 are HOST arrays.
+ * his_unet_outputs: output_conv 1x1 1->2 (:1963-1971) and the export wrapper's binary mask
+ * softmax(two)[:,0] (hed/export_onnx_advanced.py:374-387). */
+int his_unet_input_affine(const float* images, long long count, const float* mean3, const float* std3,
+                          unsigned int* flag_ws, float* affine6, void* stream);
+int his_unet_outputs(const float* one, int B, int H, int W, float w0, float w1, float b0, float b1, float* two,
+                     float* binary, void* stream);
+
+int his_memset_async(void* ptr, int value, long long bytes, void* stream);
+
+/* ---- post-processing; masks/logits are NCHW fp32 planes like the reference modules take.
+ * instance_mask: where(argmax(masks,1)==1,1,0) (hed/export_onnx_advanced.py:360-364; first-max tie rule), optionally
+ *   AND (max softmax prob > score_threshold) (test_hierarchical_instance_peopleseg_onnx.py:250-262; <= 0 disables);
+ *   writes fp32 [N,1,H,W] and/or u8 [N,H,W].
+ * dilate_logits: MaskDilationModule (export_hierarchical_instance_peopleseg_onnx.py:85-141).
+ * edge_smooth: BinaryMaskEdgeSmoothing (hed/edge_smoothing.py:10-90), N = B*C planes.
+ * binary_bilateral: BinaryMaskBilateralFilter (hed/bilateral_filter.py:299-406); gauss = device fp32 [k*k] (normalised).
+ * morph_bilateral: MorphologicalBilateralFilter (hed/bilateral_filter.py:409-501); kernel2d = device fp32 [k*k].
+ * paste: NEAREST paste-back (test_hierarchical_instance_peopleseg_onnx.py:144-161,264-278,369-374) of u8 ROI masks
+ *   [N,mh,mw] into an int32 label canvas [B,H,W] (caller zeroes): pixel = 1 + index of the last ROI covering it. */
+int his_post_instance_mask(const float* logits, int N, int H, int W, float score_threshold, float* out_f32,
+                           unsigned char* out_u8, void* stream);
+int his_post_dilate_logits(const float* logits, int N, int H, int W, int dilation_pixels, float* out, void* stream);
+int his_post_edge_smooth(const float* mask, int N, int H, int W, float threshold, float blur_strength, float* out, void* stream);
+int his_post_binary_bilateral(const float* mask, int N, int H, int W, const float* gauss, int k, int iterations,
+                              float threshold, float* ws0, float* ws1, float* out, void* stream);
+int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float* kernel2d, int k, int morph,
+                             float* ws0, float* ws1, float* out, void* stream);
+int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIS_B200_H_ */

@@ -1,0 +1,98 @@
+"""GPU: the tcgen05 implicit-GEMM convolution against a plain torch fp32 reference of the same op on the same
+fp16-rounded operands (tolerance: fp32 accumulation-order noise + one fp16 output rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from human_instance_segmentation_b200 import engine
+from human_instance_segmentation_b200.engine import ACT, RES_ADD, RES_MUL, RES_NONE
+
+pytestmark = pytest.mark.gpu
+
+
+def _act(y, code, beta):
+    return {0: lambda v: v, 1: F.relu, 2: F.silu, 3: torch.sigmoid, 4: lambda v: v * torch.sigmoid(beta * v), 5: F.gelu}[code](y)
+
+
+def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, in_slice=None, out_slice=None, beta=1.0, seed=0):
+    import ctypes
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(seed)
+    plan = engine.Plan(dev)
+    # input as a slice of a wider buffer when requested
+    in_total, in_off = in_slice or (cin, 0)
+    xbuf = plan.act(n, h, w, in_total)
+    xbuf.buf.copy_((torch.randn(n, h, w, xbuf.cs, generator=g)).half())
+    x = xbuf.slice(in_off, cin)
+    if transposed:
+        wt = torch.randn(cin, cout, 2, 2, generator=g) * (1.0 / cin) ** 0.5
+    else:
+        wt = torch.randn(cout, cin, k, k, generator=g) * (1.0 / (cin * k * k)) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    nt, bn = ctypes.c_int(), ctypes.c_int()
+    plan.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
+    slab = nt.value * bn.value
+    wp, cin_pad = engine.pack_gemm_weight(wt, slab, transposed)
+    oh, ow = (2 * h, 2 * w) if transposed else (h, w)
+    out_total, out_off = out_slice or (cout, 0)
+    obuf = plan.act(n, oh, ow, out_total)
+    obuf.buf.fill_(7.0)
+    out = obuf.slice(out_off, cout)
+    res = None
+    if res_mode != RES_NONE:
+        res = plan.act(n, oh, ow, cout)
+        res.buf.copy_(torch.randn(n, oh, ow, res.cs, generator=g).half())
+    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(scale, slab)), plan.const(engine.pad_vec(shift, slab)),
+                   out, k, act, beta, res, res_mode, transposed)
+    plan.replay()
+    torch.cuda.synchronize()
+    got = out.torch_nchw().cpu()
+    # reference
+    xin = x.torch_nchw().cpu()
+    wh = wt.half().float()
+    if transposed:
+        y = F.conv_transpose2d(xin, wh, stride=2)
+    else:
+        y = F.conv2d(xin, wh, padding=k // 2)
+    y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if res_mode == RES_ADD:
+        y = y + res.torch_nchw().cpu()
+    y = _act(y, act, beta)
+    if res_mode == RES_MUL:
+        y = y * res.torch_nchw().cpu()
+    err = (got - y).abs().max().item()
+    ref = y.abs().max().item()
+    # untouched channels of a sliced output buffer must keep their fill value
+    if out_slice:
+        full = obuf.buf.float().cpu()
+        mask = torch.ones(full.shape[-1], dtype=torch.bool)
+        mask[out_off:out_off + cout] = False
+        assert (full[..., mask] == 7.0).all(), "store spilled outside the output channel slice"
+    return err, ref
+
+
+CASES = [
+    dict(n=2, h=64, w=48, cin=256, cout=256, k=3),                           # the hot shape
+    dict(n=3, h=64, w=48, cin=64, cout=64, k=3, res_mode=RES_ADD),           # residual block tail
+    dict(n=2, h=16, w=12, cin=128, cout=256, k=3),                           # small spatial (partial tiles)
+    dict(n=2, h=20, w=15, cin=144, cout=288, k=3),                           # bc72: odd width, 2 N-tiles, K tail
+    dict(n=1, h=80, w=60, cin=72, cout=72, k=3, res_mode=RES_ADD),           # channel counts not multiples of 16/64
+    dict(n=2, h=64, w=48, cin=258, cout=256, k=1, act=0, in_slice=(258, 0)),  # feature_combiner: K tail of 2
+    dict(n=2, h=64, w=48, cin=128, cout=256, k=1, act=3, res_mode=RES_MUL),  # fg_gate: sigmoid * shared
+    dict(n=2, h=32, w=24, cin=256, cout=128, k=1, act=1, transposed=True),   # ConvT k2s2
+    dict(n=2, h=16, w=12, cin=256, cout=128, k=1, act=0, transposed=True, out_slice=(256, 0)),   # ConvT into concat slice
+    dict(n=2, h=32, w=24, cin=128, cout=64, k=3, act=1, out_slice=(128, 64)),  # skip written into upper concat slice
+    dict(n=1, h=96, w=128, cin=32, cout=16, k=3),                            # smp decoder tail (narrow)
+    dict(n=1, h=30, w=40, cin=432, cout=256, k=3),                           # smp decoder block 0 (K = 7 blocks, tail 48)
+    dict(n=2, h=24, w=32, cin=16, cout=96, k=1, act=2),                      # MBConv expand, SiLU
+    dict(n=1, h=12, w=16, cin=384, cout=768, k=3),                           # B7 bottleneck width: 3 N-tiles
+    dict(n=5, h=64, w=48, cin=256, cout=64, k=3, act=4, beta=1.5),           # swish(beta)
+    dict(n=1, h=7, w=5, cin=64, cout=32, k=3, act=5),                        # tiny image, gelu
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items() if k in ("h", "w", "cin", "cout", "k")))
+def test_conv_gemm_matches_torch_fp32(case):
+    err, ref = run_case(**case)
+    assert err <= 2e-3 * max(ref, 1.0), (err, ref)   # fp16 output rounding: 2^-11 relative

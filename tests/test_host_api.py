@@ -1,0 +1,81 @@
+"""CPU: host-side logic of the product package (no compute): state-dict contract, factory behaviour, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import human_instance_segmentation_b200 as his
+from oracle import headport
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("preset", ["b0", "b1_enhanced", "b7_ultra"])
+def test_state_dict_keys_and_shapes_match_reference(preset):
+    cfg = headport.PRESETS[preset]
+    model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    want = common.golden_keys()["preset_" + preset]
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert list(got.keys()) == list(want.keys())
+    assert got == want
+
+
+def test_reference_checkpoint_roundtrip_and_pinned_constants():
+    cfg = headport.PRESETS["b0"]
+    model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    w = model.pretrained_unet.output_conv.weight.flatten().tolist()
+    assert w == [1.0, -1.0] and model.pretrained_unet.output_conv.bias.abs().sum() == 0   # ..._unet.py:1963-1971
+    assert model.pretrained_unet.model.mean == [0.485, 0.456, 0.406]                        # path string contains "b0"
+    sd = common.procedural_state(common.golden_keys()["preset_b0"])
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert model.roi_align_mask.spatial_scale == 640.0 and model.roi_align_rgb.aligned is True  # rgb.py:636-647
+
+
+def test_normalisation_follows_path_string():
+    m = his.PreTrainedPeopleSegmentationUNet(pretrained_weights_path="ext_extractor/2020-09-23a.pth", encoder_name="timm-efficientnet-b3")
+    assert m.mean == [0.5, 0.5, 0.5] and m.std == [0.5, 0.5, 0.5]
+
+
+def test_factory_errors_match_reference_behaviour():
+    kw = headport.PRESETS["b0"].factory_kwargs()
+    with pytest.raises(ValueError):     # activation_utils.py:103
+        his.create_rgb_hierarchical_model(**{**kw, "activation_function": "tanh"})
+    with pytest.raises(ValueError):     # normalization_comparison.py:206
+        his.create_rgb_hierarchical_model(**{**kw, "normalization_type": "nonsense"})
+    with pytest.raises(NotImplementedError):
+        his.create_rgb_hierarchical_model(**{**kw, "multi_scale": True})
+
+
+def test_no_cpu_fallback():
+    model = his.create_rgb_hierarchical_model(**headport.PRESETS["b0"].factory_kwargs())
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(his.HisError):
+        model(torch.rand(1, 3, 64, 64), torch.tensor([[0, 0.1, 0.1, 0.9, 0.9]]))
+    with pytest.raises(his.HisError):
+        his.postprocess.instance_masks(torch.zeros(1, 3, 4, 4))
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "his_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(his_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 30
+    path = his.build()
+    lib = ctypes.CDLL(path)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/his_b200.h but not exported"
+    from human_instance_segmentation_b200 import lib as L
+    assert set(L.SIGNATURES) == set(names)
+    assert lib.his_version() == 100
+
+
+def test_tile_n_policy():
+    lib = his.load()
+    nt, bn = ctypes.c_int(), ctypes.c_int()
+    for cout, want in [(256, (1, 256)), (128, (1, 128)), (72, (1, 80)), (36, (1, 48)), (288, (2, 192)), (384, (2, 192)), (768, (3, 256)), (16, (1, 16))]:
+        assert lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn)) == 0
+        assert (nt.value, bn.value) == want, cout
