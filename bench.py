@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: RGB hierarchical instance-segmentation forward, ROI-masks/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b0|b1|b7|b0_160x120] [--impl reference]
+
+A step = one pass of ``model(images, rois)`` (full-image EfficientNet-UNet, Dynamic RoI Align, ROI feature extractor,
+hierarchical head with contour/distance branches -> logits [N,3,mh,mw] + binary masks) over one synthetic batch.
+  * value : ROI-masks/s with the batch already resident in HBM (CUDA events, max over ranks, barrier+sync both sides)
+  * e2e   : the same through the public API with HOST (pinned) inputs: H2D of images+rois and D2H of
+            instance_masks+binary_masks inside the timed region
+  * roofline : tcgen05 implicit-GEMM kernel, algorithmic FLOPs / event-timed launch durations vs the measured peak
+  * cpu_baseline : the reference path on the box's host cores (oracle port: the reference tree cannot travel)
+N > 1 (torchrun): every rank runs the same per-GPU batch on its own images (weak scaling, no collective on the path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, images per GPU, H, W, rois per image)
+    "b0": ("b0", 64, 480, 640, 10),            # the metric's model (B0, 640x480) on configs[1]'s 1xB200 batch geometry
+    "b1": ("b1_enhanced", 64, 480, 640, 10),   # BASELINE.json configs[1]
+    "b7": ("b7_ultra", 4, 480, 640, 10),       # configs[2] per-GPU share at 8 GPUs (32 images / 8)
+    "b0_160x120": ("b0", 512, 120, 160, 10),   # configs[3] per-GPU share at 8 GPUs (4096 / 8)
+}
+HEAD_GFLOP_PER_ROI = {"b0": 57.84, "b1_enhanced": 93.01, "b7_ultra": 278.44}      # SURVEY §8d / BASELINE.md §2
+UNET_GFLOP_PER_IMG = {"b0": 27.72, "b1_enhanced": 29.97, "b7_ultra": 90.21}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"tflops": p.get("bf16_tflops_sustained", 1367.9), "tflops_burst": p.get("bf16_tflops", 1660.9),
+                "hbm_gbs": p.get("hbm_gbs", 6555.2), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batch(seed, n_images, h, w, per_image):
+    from human_instance_segmentation_b200.synthetic import synth_images, synth_rois
+    return synth_images(seed, n_images, h, w), synth_rois(seed, n_images, per_image)
+
+
+def build_model(preset):
+    """The product arm: nothing under oracle/ is imported here."""
+    import human_instance_segmentation_b200 as his
+    from human_instance_segmentation_b200 import presets, synthetic
+    kw = presets.PRESETS[preset]
+    model = his.create_rgb_hierarchical_model(**kw)
+    # random-init weights of that architecture (no checkpoints exist offline); BatchNorm statistics randomised so that
+    # nothing folds to a no-op
+    model.load_state_dict(synthetic.fill_state_dict(model.state_dict(), seed=0))
+    return kw, model
+
+
+def cpu_reference_rate(preset, h, w, n_images, per_image, iters, threads):
+    """ROI-masks/s of the reference path on host cores (oracle port of the reference modules, fp32, all threads)."""
+    import torch
+    from oracle import headport, paramfill
+    import human_instance_segmentation_b200 as his
+    torch.set_num_threads(threads)
+    cfg = headport.PRESETS[preset]
+    holder = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())           # parameter container only (key names/shapes)
+    sd = paramfill.fill_state_dict(holder.state_dict(), seed=0)
+    images, rois = synth_batch(1, n_images, h, w, per_image)
+    headport.forward(sd, images, rois, cfg)                                      # warm-up
+    times = []
+    for _ in range(iters):
+        t = time.perf_counter()
+        headport.forward(sd, images, rois, cfg)
+        times.append(time.perf_counter() - t)
+    return rois.shape[0] / min(times), min(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    preset, n_img, h, w, per_image = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sample_images = 2
+    import torch
+    from oracle import headport, paramfill
+    import human_instance_segmentation_b200 as his
+    torch.set_num_threads(threads)
+    cfg = headport.PRESETS[preset]
+    holder = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    sd = paramfill.fill_state_dict(holder.state_dict(), seed=0)
+    images, rois = synth_batch(1, sample_images, h, w, per_image)
+    for _ in range(max(1, min(args.warmup, 2))):
+        headport.forward(sd, images, rois, cfg)
+    steps = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        headport.forward(sd, images, rois, cfg)
+    dt = (time.perf_counter() - t0) / steps
+    value = rois.shape[0] / dt
+    sample = f"{sample_images} images x {per_image} ROIs of the {args.workload} workload per step, fp32, torch CPU ({threads} threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": "roi_masks_per_sec", "value": value, "unit": "ROI-masks/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.workload, sample_images),
+        "cpu_baseline": {"value": value, "unit": "ROI-masks/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "ROI-masks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference path = oracle port of the reference modules (the reference tree and smp/timm cannot travel to the GPU box)"}))
+
+
+def workload_config(name, n_img=None):
+    preset, b, h, w, per_image = WORKLOADS[name]
+    b = n_img or b
+    from human_instance_segmentation_b200 import presets
+    kw = presets.PRESETS[preset]
+    rs, msz = kw["roi_size"], kw["mask_size"]
+    return {"workload": f"{preset} hierarchical RGB model, {w}x{h} input, batch {b} per GPU, {per_image} ROIs/image, ROI {rs[0]}x{rs[1]} -> mask "
+                        f"{msz[0]}x{msz[1]}, random-init weights", "images_per_gpu": b, "rois_per_gpu": b * per_image,
+            "encoder": kw["encoder_name"], "cache": "inputs larger than L2 (236 MB images, multi-GB activations per step)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="b0", choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-op time table of one instrumented step to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    preset, n_img, h, w, per_image = WORKLOADS[args.workload]
+    cfg, model = build_model(preset)
+    model = model.to(dev)
+    for ra in (model.roi_align_mask, model.roi_align_rgb):       # exporter convention spatial_scale=(H,W)
+        ra.spatial_scale = (float(h), float(w)); ra.spatial_scale_h, ra.spatial_scale_w = float(h), float(w)
+    model.copy_outputs = False
+    images_h, rois_h = synth_batch(100 + rank, n_img, h, w, per_image)
+    images_h, rois_h = images_h.pin_memory(), rois_h.pin_memory()
+    images_d, rois_d = images_h.to(dev), rois_h.to(dev)
+    n_rois = rois_h.shape[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: inputs resident in HBM
+    for _ in range(warmup):
+        model(images_d, rois_d)
+    bp = model._get_plan(images_d, rois_d)
+    plan = bp.plan
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model(images_d, rois_d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- e2e: host (pinned) buffers in, instance/binary masks back to host, through model.infer()
+    inst_h = torch.empty((n_rois, 1) + tuple(cfg["mask_size"]), dtype=torch.float32).pin_memory()
+    bin_h = torch.empty((n_img, 1, h, w), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        inst, binary = model.infer(images_h, rois_h)
+        inst_h.copy_(inst, non_blocking=True)
+        bin_h.copy_(binary, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    # ---------------- per-kernel timing for the roofline (instrumented replay right after the timed region)
+    timed = plan.run_timed()
+    timed = plan.run_timed()
+    gemm = [(t, f) for name, t, f in timed if name == "conv_gemm"]
+    gemm_ms, gemm_flops = sum(t for t, _ in gemm), sum(f for _, f in gemm)
+    step_ms_instr = sum(t for _, t, _ in timed)
+    by_name = {}
+    for name, t, f in timed:
+        by_name.setdefault(name, [0, 0.0]); by_name[name][0] += 1; by_name[name][1] += t
+    if args.breakdown and rank == 0:
+        for name, (cnt, t) in sorted(by_name.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {name:22s} x{cnt:4d} {t:9.3f} ms {100 * t / step_ms_instr:5.1f}%", file=sys.stderr)
+        rows = sorted(zip([t for n_, t, f in timed if n_ == "conv_gemm"], plan.gemm_shapes, [f for n_, t, f in timed if n_ == "conv_gemm"]), reverse=True)
+        for t, shp, f in rows[:25]:
+            print(f"  gemm N{shp[0]} {shp[1]}x{shp[2]} cin{shp[3]} cout{shp[4]} k{shp[5]} T{shp[6]}: {t:7.3f} ms {f / t / 1e9:8.1f} TFLOP/s", file=sys.stderr)
+
+    t_all = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t_all[0]), float(t_all[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    out = {
+        "metric": "roi_masks_per_sec", "value": world * n_rois / (ms * 1e-3), "unit": "ROI-masks/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate", "data": "synthetic", "config": workload_config(args.workload),
+        "clocks": clocks,
+        "e2e": {"value": world * n_rois / (ms_e2e * 1e-3), "unit": "ROI-masks/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": images_h.numel() * 4 + rois_h.numel() * 4, "d2h_bytes_per_step": inst_h.numel() * 4 + bin_h.numel() * 4,
+                "api": "model.infer(images_host_pinned, rois_host) -> (instance_masks, binary_masks) copied to pinned host"},
+        "gpu_launches": plan.launches * args.steps,
+        "launches_per_step": plan.launches,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_sm100_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                     "launches_per_step": len(gemm), "avg_launch_ms": gemm_ms / max(len(gemm), 1),
+                     "algorithmic_flop_per_launch": gemm_flops / max(len(gemm), 1), "share_of_step": gemm_ms / step_ms_instr,
+                     "how": "sum of algorithmic FLOPs of all conv_gemm launches of one step / sum of their CUDA-event durations "
+                            "(instrumented replay immediately after the timed region)"},
+        "step_algorithmic_tflop": plan.flops / 1e12,
+        "step_tflops": plan.flops / (ms * 1e-3) / 1e12,
+        "time_share_by_op": {k: round(v[1] / step_ms_instr, 4) for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][1])},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        rate, t_iter = cpu_reference_rate(preset, h, w, 2, per_image, 2, threads)
+        out["cpu_baseline"] = {"value": rate, "unit": "ROI-masks/s", "cores": threads, "kind": "port",
+                               "sample": f"2 images x {per_image} ROIs of the same workload, min of 2 iterations ({t_iter:.2f} s each), fp32 torch CPU; "
+                                         "oracle port of the reference modules (reference tree cannot travel)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -528,8 +528,8 @@ int his_version(void) { return 100; }
 int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC, long long sH, long long sW, int B, int C, int H, int W,
                   const float* rois, int n_rois, int oh, int ow, float scale_h, float scale_w, int aligned, void* out_half, int out_cs,
                   float* out_f32, void* stream) {
-  if (!feat || (!out_half && !out_f32) || (n_rois > 0 && !rois)) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: null pointer");
   if (n_rois == 0) return HIS_OK;
+  if (!feat || (!out_half && !out_f32) || !rois) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: null pointer");
   if (oh <= 0 || ow <= 0 || C <= 0) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: bad shape");
   const long long total = (long long)n_rois * oh * ow;
   if (feat_is_half)

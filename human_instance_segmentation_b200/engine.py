@@ -54,11 +54,13 @@ class Plan:
         self.ops: List[Tuple] = []          # (name, cfunc, args-without-stream)
         self.keep: List[object] = []        # tensors / gemm plans the ops point into
         self.gemm_plans: List[ctypes.c_void_p] = []
+        self.gemm_shapes: List[Tuple] = []
         self.flops = 0                      # algorithmic FLOPs (2*MAC, true channel counts) of one replay
         self.flops_by_tag: Dict[str, int] = {}
         self.tensor_flops = 0               # the part issued on tcgen05
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches = 0
+        self.op_flops: List[int] = []
         self.tag = ""
 
     # -------------------------------------------------------------- allocation
@@ -84,9 +86,13 @@ class Plan:
         if tensor:
             self.tensor_flops += f
 
-    def add(self, name: str, fn, *args):
+    # kernels launched per op (cudaMemsetAsync is not one of ours)
+    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0}
+
+    def add(self, name: str, fn, *args, flops: int = 0):
         self.ops.append((name, fn, args))
-        self.launches += 1
+        self.op_flops.append(flops)
+        self.launches += self.KERNELS_PER_OP.get(name, 1)
 
     # -------------------------------------------------------------- ops
     def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, scale: torch.Tensor, shift: torch.Tensor, out: Act,
@@ -105,8 +111,10 @@ class Plan:
         self.gemm_plans.append(h)
         self.keep += [w_packed, scale, shift]
         taps = 4 if transposed else ksize * ksize
-        self._add_flops(2 * x.N * x.H * x.W * x.C * out.C * taps, True)
-        self.add("conv_gemm", L.his_conv_gemm_run, h)
+        f = 2 * x.N * x.H * x.W * x.C * out.C * taps
+        self._add_flops(f, True)
+        self.add("conv_gemm", L.his_conv_gemm_run, h, flops=f)
+        self.gemm_shapes.append((x.N, x.H, x.W, x.C, out.C, ksize, int(transposed)))
 
     def conv_direct(self, x, in_fmt: int, N, H, W, cin, in_cs, w: torch.Tensor, scale, shift, cout, k, stride, pad, act, beta=1.0,
                     in_affine: Optional[torch.Tensor] = None, res: Optional[Act] = None, res_mode: int = RES_NONE,
@@ -129,6 +137,21 @@ class Plan:
             rc = fn(*args, s)
             if rc != 0:
                 _lib.check(rc, name)
+
+    def run_timed(self) -> List[Tuple[str, float, int]]:
+        """Instrumented replay: every op bracketed by CUDA events on the launching stream.
+        Returns [(op name, milliseconds, algorithmic flops)]; used by bench.py for the roofline figures."""
+        stream = torch.cuda.current_stream(self.device)
+        s = ctypes.c_void_p(stream.cuda_stream)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        evs[0].record(stream)
+        for i, (name, fn, args) in enumerate(self.ops):
+            rc = fn(*args, s)
+            if rc != 0:
+                _lib.check(rc, name)
+            evs[i + 1].record(stream)
+        stream.synchronize()
+        return [(self.ops[i][0], evs[i].elapsed_time(evs[i + 1]), self.op_flops[i]) for i in range(len(self.ops))]
 
     def replay(self):
         """Runs the plan on the current torch stream (through a CUDA graph once captured)."""

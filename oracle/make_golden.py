@@ -24,27 +24,7 @@ from . import headport, paramfill, refload
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-# ----------------------------------------------------------------------------- seeded inputs (shared with tests)
-def synth_images(seed: int, b: int, h: int, w: int) -> torch.Tensor:
-    g = torch.Generator().manual_seed(seed)
-    return torch.rand(b, 3, h, w, generator=g)
-
-
-def synth_rois(seed: int, n_images: int, per_image: int) -> torch.Tensor:
-    """SURVEY §8d box law: x1,y1~U[0,.5), w,h~U[.2,.5), x2=min(x1+w,1), y2=min(y1+h,1)."""
-    g = torch.Generator().manual_seed(seed + 7919)
-    n = n_images * per_image
-    xy = torch.rand(n, 2, generator=g) * 0.5
-    wh = torch.rand(n, 2, generator=g) * 0.3 + 0.2
-    b = torch.arange(n_images, dtype=torch.float32).repeat_interleave(per_image)[:, None]
-    return torch.cat([b, xy, (xy + wh).clamp(max=1.0)], 1)
-
-
-def edge_rois(n_images: int) -> torch.Tensor:
-    """Edge cases of SURVEY §8d: x2=1/y2=1, zero-area ROI, ROI outside [0,1], reversed box."""
-    r = [[0, 0.0, 0.0, 1.0, 1.0], [n_images - 1, 0.25, 0.5, 0.25, 0.5], [0, -0.2, -0.1, 0.4, 0.6],
-         [n_images - 1, 0.6, 0.7, 1.3, 1.2], [0, 0.7, 0.6, 0.3, 0.2], [0, 0.1, 0.2, 0.9, 0.95]]
-    return torch.tensor(r, dtype=torch.float32)
+from human_instance_segmentation_b200.synthetic import edge_rois, synth_images, synth_rois  # noqa: E402,F401
 
 
 SMALL_CASES = {
@@ -70,9 +50,9 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def _run_reference(cfg: headport.PathConfig, images, rois, seed=0):
+def _run_reference(cfg: headport.PathConfig, images, rois, seed=0, mode="stress"):
     model = refload.build_reference_model(**cfg.factory_kwargs())
-    sd = paramfill.fill_state_dict(model.state_dict(), seed=seed)
+    sd = paramfill.fill_state_dict(model.state_dict(), seed=seed, mode=mode)
     model.load_state_dict(sd)
     for ra in (model.roi_align_mask, model.roi_align_rgb):      # export_onnx_advanced.py:80-98 mutates these
         ra.spatial_scale = cfg.spatial_scale
@@ -125,6 +105,19 @@ def make_model_goldens():
           "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
 
 
+def make_default_init_golden():
+    """BASELINE config 1 again, with PyTorch-default-initialisation statistics ("random-init weights")."""
+    cfg = headport.PRESETS["b0"]
+    images = synth_images(1, 2, 480, 640)
+    rois = synth_rois(1, 2, 4)
+    model, sd, logits, aux = _run_reference(cfg, images, rois, mode="torch_default")
+    out = {"logits": _np(logits), "bg_fg_logits_low": _np(aux["bg_fg_logits_low"]),
+           "full_image_logits_ch0_s4": _np(aux["full_image_logits"][:, 0, ::4, ::4])}
+    np.savez_compressed(os.path.join(GOLDEN, "cfg1_b0_default_init.npz"), **{k: v.astype(np.float32) for k, v in out.items()})
+    print("cfg1_b0_default_init logits range", float(logits.min()), float(logits.max()), "std", logits.std((0, 2, 3)).tolist(),
+          "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
+
+
 def make_roi_goldens():
     """DynamicRoIAlign itself (hed/dynamic_roi_align.py) on random feature maps, all conventions."""
     mod = refload.ref_import("dynamic_roi_align")
@@ -150,6 +143,8 @@ def main():
         make_roi_goldens()
     if args.only in ("all", "model"):
         make_model_goldens()
+    if args.only in ("all", "model", "default"):
+        make_default_init_golden()
     if args.only in ("all", "post"):
         from . import make_golden_post
         make_golden_post.make_post_goldens(GOLDEN)

@@ -31,7 +31,7 @@ def cfg1_inputs():
     return headport.PRESETS["b0"], synth_images(1, 2, 480, 640), synth_rois(1, 2, 4)
 
 
-def procedural_state(shapes: dict, seed=0, weights_path="ext_extractor/best_model_b0_0.8741.pth"):
+def procedural_state(shapes: dict, seed=0, weights_path="ext_extractor/best_model_b0_0.8741.pth", mode="stress"):
     """Builds the procedural state dict for a key->shape table (tests/golden/state_dict_keys.json)."""
     sd = {}
     for k, shp in shapes.items():
@@ -47,7 +47,7 @@ def procedural_state(shapes: dict, seed=0, weights_path="ext_extractor/best_mode
     for k in sd:
         if k.endswith("distance_decoder.threshold"):
             sd[k] = torch.tensor(0.3)
-    return paramfill.fill_state_dict(sd, seed=seed)
+    return paramfill.fill_state_dict(sd, seed=seed, mode=mode)
 
 
 def shapes_for_case(name):

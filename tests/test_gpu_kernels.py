@@ -1,0 +1,146 @@
+"""GPU: the non-GEMM kernels through the C-ABI wrappers against golden vectors / plain torch fp32 references."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import human_instance_segmentation_b200 as his
+from human_instance_segmentation_b200 import engine, lib as L
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dynamic_roi_align_matches_reference_golden():
+    g = common.golden("roi_align")
+    feat, rois = g["feat"].cuda(), g["rois"].cuda()
+    for tag, scale, aligned, (oh, ow) in [("a640", 640.0, True, (16, 12)), ("ahw", (37.0, 53.0), True, (16, 12)),
+                                          ("u_hw", (37.0, 53.0), False, (7, 9)), ("a64", 64.0, True, (5, 3))]:
+        ra = his.DynamicRoIAlign(spatial_scale=scale, sampling_ratio=2, aligned=aligned)
+        out = ra(feat, rois, oh, ow).cpu()
+        assert (out - g[tag]).abs().max() < 2e-5, tag
+    assert his.DynamicRoIAlign(640.0)(feat, rois[:0], 4, 4).shape == (0, 5, 4, 4)
+    # channels-last / non-contiguous feature maps go through the stride arguments
+    out = his.DynamicRoIAlign((37.0, 53.0), aligned=True)(feat.to(memory_format=torch.channels_last), rois, 16, 12).cpu()
+    assert (out - g["ahw"]).abs().max() < 2e-5
+
+
+def _plan():
+    return engine.Plan(torch.device("cuda"))
+
+
+@pytest.mark.parametrize("k,s,c", [(3, 1, 32), (3, 2, 96), (5, 2, 144), (5, 1, 672), (3, 1, 1152)])
+def test_depthwise_se_matches_torch(k, s, c):
+    p = _plan()
+    lib = p.lib
+    g = torch.Generator().manual_seed(k * 100 + c)
+    n, h, w = 2, 23, 31
+    x = p.act(n, h, w, c); x.buf.copy_(torch.randn(n, h, w, x.cs, generator=g).half())
+    wt = torch.randn(c, 1, k, k, generator=g) * 0.3
+    scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    pad = ((s - 1) + (k - 1)) // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    out = p.act(n, ho, wo, c)
+    pool = p.f32(n, c, zero=True)
+    wdw = p.const(wt.reshape(c, k * k).t().contiguous(), torch.float16)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.his_depthwise_conv(x.ptr, n, h, w, c, x.cs, wdw.data_ptr(), p.const(scale).data_ptr(), p.const(shift).data_ptr(), k, s, 2,
+                                   out.ptr, out.cs, pool.data_ptr(), st))
+    r = max(c // 4, 1)
+    w1, b1 = torch.randn(r, c, generator=g) * 0.2, torch.randn(r, generator=g) * 0.1
+    w2, b2 = torch.randn(c, r, generator=g) * 0.2, torch.randn(c, generator=g) * 0.1
+    gate = p.f32(n, c)
+    L.check(lib.his_se_gate(pool.data_ptr(), n, ho * wo, c, r, p.const(w1).data_ptr(), p.const(b1).data_ptr(), p.const(w2).data_ptr(),
+                            p.const(b2).data_ptr(), 2, 1.0, gate.data_ptr(), st))
+    scaled = p.act(n, ho, wo, c)
+    L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), n, ho * wo, c, scaled.ptr, scaled.cs, st))
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(x.torch_nchw().cpu(), wt.half().float(), None, s, pad, 1, c) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    got = out.torch_nchw().cpu()
+    assert (got - ref).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+    mean = got.mean((2, 3))
+    gref = torch.sigmoid(F.silu(mean @ w1.t() + b1) @ w2.t() + b2)
+    assert (gate.cpu() - gref).abs().max() < 1e-4
+    assert (scaled.torch_nchw().cpu() - got * gref[:, :, None, None]).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_direct_conv_variants_match_torch():
+    p = _plan()
+    g = torch.Generator().manual_seed(4)
+    # (a) NCHW fp32 input + input affine + stride 2 (the UNet stem)
+    n, h, w = 2, 37, 50
+    img = torch.rand(n, 3, h, w, generator=g)
+    aff = torch.tensor([2.0, 3.0, 4.0, -0.5, 0.25, 0.1])
+    wt = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    out = p.act(n, ho, wo, 32)
+    p.conv_direct(p.const(img), 1, n, h, w, 3, 0, p.const(engine.pack_direct_weight(wt), torch.float16), p.const(scale), p.const(shift), 32, 3, 2, 1,
+                  2, 1.0, in_affine=p.const(aff), out=out)
+    # (b) NHWC half input, tail 1x1 to 2 channels, fp32 NCHW output
+    x = p.act(n, 9, 11, 128); x.buf.copy_(torch.randn(n, 9, 11, 128, generator=g).half())
+    w2 = torch.randn(2, 128, 1, 1, generator=g) * 0.1
+    tail = p.f32(n, 2, 9, 11)
+    p.conv_direct(x, 0, n, 9, 11, 128, x.cs, p.const(engine.pack_direct_weight(w2), torch.float16), p.const(torch.ones(2)), p.const(torch.tensor([0.1, -0.2])),
+                  2, 1, 1, 0, 0, out_f32=tail)
+    p.replay(); torch.cuda.synchronize()
+    xin = img * aff[:3].view(1, 3, 1, 1) + aff[3:].view(1, 3, 1, 1)
+    ref = F.silu(F.conv2d(xin, wt.half().float(), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert (out.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * float(ref.abs().max())
+    ref2 = F.conv2d(x.torch_nchw().cpu(), w2.half().float(), torch.tensor([0.1, -0.2]))
+    assert (tail.cpu() - ref2).abs().max() <= 1e-4 * max(1.0, float(ref2.abs().max()))
+
+
+def test_glue_kernels_match_torch():
+    p = _plan(); lib = p.lib
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(9)
+    n, h, w, c = 3, 16, 12, 256
+    x = p.act(n, h, w, c); x.buf.copy_(torch.randn(n, h, w, c, generator=g).half())
+    xr = x.torch_nchw().cpu()
+    # maxpool
+    mp = p.act(n, h // 2, w // 2, c)
+    L.check(lib.his_maxpool2(x.ptr, n, h, w, c, x.cs, mp.ptr, mp.cs, st))
+    # spatial attention 7x7
+    wsa = torch.randn(1, 2, 7, 7, generator=g) * 0.2
+    sa = p.act(n, h, w, c); stats = p.f32(n, h, w, 2)
+    L.check(lib.his_spatial_attention(x.ptr, n, h, w, c, x.cs, p.const(wsa.reshape(2, 7, 7)).data_ptr(), 7, stats.data_ptr(), sa.ptr, sa.cs, st))
+    # nearest resize into a slice, bilinear fp32, NHWC->NCHW
+    cat = p.act(n, 31, 25, c + 8)
+    L.check(lib.his_resize_nearest(x.ptr, n, h, w, c, x.cs, 31, 25, cat.slice(8, c).ptr, cat.cs, st))
+    t = torch.randn(n, 2, 10, 14, generator=g)
+    bl = p.f32(n, 2, 23, 17)
+    L.check(lib.his_resize_bilinear_f32(p.const(t).data_ptr(), n * 2, 10, 14, 23, 17, bl.data_ptr(), st))
+    nchw = p.f32(n, c, h, w)
+    L.check(lib.his_nhwc_half_to_nchw_float(x.ptr, n, h * w, c, x.cs, nchw.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(mp.torch_nchw().cpu(), F.max_pool2d(xr, 2))
+    s = torch.cat([xr.mean(1, keepdim=True), xr.max(1, keepdim=True)[0]], 1)
+    ref = xr * torch.sigmoid(F.conv2d(s, wsa, padding=3))
+    assert (sa.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * float(ref.abs().max())
+    assert torch.equal(cat.slice(8, c).torch_nchw().cpu(), F.interpolate(xr, size=(31, 25), mode="nearest"))
+    assert (bl.cpu() - F.interpolate(t, size=(23, 17), mode="bilinear", align_corners=False)).abs().max() < 1e-5
+    assert torch.equal(nchw.cpu(), xr)
+
+
+def test_head_tail_kernels_match_torch():
+    p = _plan(); lib = p.lib
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(2)
+    n, h, w = 3, 8, 6
+    low = torch.randn(n, 2, h, w, generator=g)
+    wt = torch.randn(2, 32, 2, 2, generator=g) * 0.5
+    s, t = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+    w1, b1 = torch.randn(2, 32, generator=g) * 0.3, torch.randn(2, generator=g) * 0.1
+    out = p.f32(n, 2, 2 * h, 2 * w)
+    L.check(lib.his_upsample_bgfg(p.const(low).data_ptr(), n, h, w, p.const(wt).data_ptr(), p.const(s).data_ptr(), p.const(t).data_ptr(),
+                                  p.const(w1).data_ptr(), p.const(b1).data_ptr(), 1, 1.0, out.data_ptr(), st))
+    tn = torch.randn(n, 2, 2 * h, 2 * w, generator=g)
+    logits = p.f32(n, 3, 2 * h, 2 * w)
+    L.check(lib.his_head_combine(out.data_ptr(), p.const(tn).data_ptr(), n, 2 * h, 2 * w, logits.data_ptr(), st))
+    torch.cuda.synchronize()
+    y = F.relu(F.conv_transpose2d(low, wt, stride=2) * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1))
+    ref = F.conv2d(y, w1.view(2, 32, 1, 1), b1)
+    assert (out.cpu() - ref).abs().max() < 1e-4
+    fg = F.softmax(ref, 1)[:, 1]
+    want = torch.stack([ref[:, 0], ref[:, 1] + tn[:, 0] * fg, ref[:, 1] + tn[:, 1] * fg], 1)
+    assert (logits.cpu() - want).abs().max() < 1e-4
