@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op time table of one instrumented step to stderr")
+    ap.add_argument("--top", type=int, default=45)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -254,9 +255,9 @@ def main():
     if args.breakdown and rank == 0:
         for name, (cnt, t) in sorted(by_name.items(), key=lambda kv: -kv[1][1]):
             print(f"  {name:22s} x{cnt:4d} {t:9.3f} ms {100 * t / step_ms_instr:5.1f}%", file=sys.stderr)
-        rows = sorted(zip([t for n_, t, f in timed if n_ == "conv_gemm"], plan.gemm_shapes, [f for n_, t, f in timed if n_ == "conv_gemm"]), reverse=True)
-        for t, shp, f in rows[:25]:
-            print(f"  gemm N{shp[0]} {shp[1]}x{shp[2]} cin{shp[3]} cout{shp[4]} k{shp[5]} T{shp[6]}: {t:7.3f} ms {f / t / 1e9:8.1f} TFLOP/s", file=sys.stderr)
+        rows = sorted(((t, plan.op_desc[i], f) for i, (n_, t, f) in enumerate(timed)), reverse=True)
+        for t, desc, f in rows[:args.top]:
+            print(f"  {t:7.3f} ms {f / t / 1e9 if f else 0:8.1f} TFLOP/s  {desc}", file=sys.stderr)
 
     t_all = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:

@@ -28,21 +28,33 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kStages = 4;
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                       // fp16 elements = 128 B = one swizzle row
-constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kBBytesMax = 256 * kBlockK * 2;     // 32 KB
-constexpr int kStageBytes = kABytes + kBBytesMax; // 48 KB
 constexpr int kStagingBytes = kBlockM * 64 * 2;   // 16 KB : 128 rows x 64 channels fp16
 constexpr int kNumStaging = 2;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kMaxStages = 12;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kBarrierBytes = 512;
+
+// K-block width BK (fp16 elements) selects the shared-memory swizzle: one row of the operand tile is BK*2 bytes.
+template <int BK> struct KCfg {
+  static constexpr int kABytes = kBlockM * BK * 2;
+  static constexpr int kBBytesMax = 256 * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytesMax;     // 48 / 24 / 12 KB
+  static constexpr int kStagesFit = (kSmemBudget - kNumStaging * kStagingBytes - 1024 - kBarrierBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 + kBarrierBytes;
+  static constexpr uint32_t kSbo = 8 * BK * 2;                 // bytes between 8-row groups
+  static constexpr uint64_t kLayout = BK == 64 ? 2 : BK == 32 ? 4 : 6;   // SWIZZLE_128B / 64B / 32B
+};
+
+enum { ACTC_CLAMP = 0, ACTC_SIGMOID = 1, ACTC_GELU = 2 };
 
 struct ConvGemmParams {
   int n_img, H, W;
@@ -53,9 +65,12 @@ struct ConvGemmParams {
   int groups;           // 1, or 4 for conv-transpose k2s2
   int cout_slab;        // n_tiles * block_n  (rows of one slab in B, scale/shift length per group)
   int num_work;
-  int act;
-  float act_beta;
-  int res_mode;
+  // activation, compile-time class + runtime parameters:
+  //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
+  //   SIGMOID: s = 1/(1+exp(-act_beta*y)); y = act_mul_x ? y*s : s   (sigmoid / silu / swish(beta))
+  //   GELU:    exact erf form
+  float act_lo, act_beta;
+  int act_mul_x;
   const float* scale;   // [cout_slab]
   const float* shift;   // [cout_slab]
 };
@@ -108,15 +123,15 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for one swizzle atom along K) | [32,46) SBO>>4 (8 rows * 128 B)
-//   [46,48) version=1 | [61,64) layout: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+// K-major swizzled shared-memory matrix descriptor (sm_100 format), one swizzle atom along K (row = BK*2 bytes):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused) | [32,46) SBO>>4 (8 rows) | [46,48) version=1 | [61,64) swizzle mode
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(KCfg<BK>::kSbo >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= KCfg<BK>::kLayout << 61;
   return d;
 }
 
@@ -152,7 +167,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int ACTC>
+__device__ __forceinline__ float epi_act(float y, const ConvGemmParams& p) {
+  if (ACTC == ACTC_CLAMP) return fmaxf(y, p.act_lo);
+  if (ACTC == ACTC_SIGMOID) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-p.act_beta * y));
+    return p.act_mul_x ? y * s : s;
+  }
+  return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
+}
 
 struct WorkItem { int img, y0, x0, n_tile, group; };
 
@@ -167,17 +200,20 @@ __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) 
 }
 
 // ------------------------------------------------------------------------------------ kernel
+template <int BK, int ACTC, int RES>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
                        const __grid_constant__ CUtensorMap tmR, const ConvGemmParams p) {
+  using Cfg = KCfg<BK>;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base;
-  const uint32_t staging_base = smem_base + kStages * kStageBytes;
+  const uint32_t staging_base = smem_base + kStages * Cfg::kStageBytes;
   const uint32_t bar_base = staging_base + kNumStaging * kStagingBytes;
-  // barrier slots (8 B each): full[4] empty[4] tmem_full[2] tmem_empty[2] res_full[2]; then tmem ptr
+  // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[2]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
@@ -189,11 +225,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.ksize * p.ksize;
   const int kiters = taps * p.kblocks_per_tap;
-  const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+  const uint32_t b_bytes = (uint32_t)p.block_n * BK * 2;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO0);
-    if (p.res_mode) prefetch_tmap(&tmR);
+    if (RES) prefetch_tmap(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -212,18 +248,21 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
     int stage = 0; uint32_t phase = 0;
+    const int pad = p.ksize >> 1;
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
-      const int pad = p.ksize >> 1;
+      const int brow0 = it.group * taps * p.cout_slab + it.n_tile * p.block_n;
+      int tap = 0, cb = 0;
       for (int k = 0; k < kiters; ++k) {
-        const int tap = k / p.kblocks_per_tap, cb = k - tap * p.kblocks_per_tap;
-        const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+        const int ty = tap / p.ksize;
+        const int dy = ty - pad, dx = tap - ty * p.ksize - pad;
         mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = stage_base + stage * kStageBytes, sb = sa + kABytes;
-        mbar_expect_tx(full_bar(stage), kABytes + b_bytes);
-        tma_load_4d(sa, &tmA, full_bar(stage), cb * kBlockK, it.x0 + dx, it.y0 + dy, it.img);
-        tma_load_2d(sb, &tmB, full_bar(stage), cb * kBlockK, (it.group * taps + tap) * p.cout_slab + it.n_tile * p.block_n);
+        const uint32_t sa = stage_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+        mbar_expect_tx(full_bar(stage), Cfg::kABytes + b_bytes);
+        tma_load_4d(sa, &tmA, full_bar(stage), cb * BK, it.x0 + dx, it.y0 + dy, it.img);
+        tma_load_2d(sb, &tmB, full_bar(stage), cb * BK, brow0 + tap * p.cout_slab);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++cb == p.kblocks_per_tap) { cb = 0; ++tap; }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -238,10 +277,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int k = 0; k < kiters; ++k) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = stage_base + stage * kStageBytes, sb = sa + kABytes;
-        const uint64_t adesc = make_kmajor_sw128_desc(sa), bdesc = make_kmajor_sw128_desc(sb);
+        const uint32_t sa = stage_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
+        const uint64_t adesc = make_kmajor_desc<BK>(sa), bdesc = make_kmajor_desc<BK>(sb);
 #pragma unroll
-        for (int kk = 0; kk < kBlockK / 16; ++kk)
+        for (int kk = 0; kk < BK / 16; ++kk)
           umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
         umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
         if (k == kiters - 1) umma_commit(tfull_bar(acc));
@@ -258,15 +297,25 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const WorkItem it = decode_work(p, w);
       const int acc = iter & 1; const uint32_t acc_phase = (iter >> 1) & 1;
       const CUtensorMap* tmO = it.group == 0 ? &tmO0 : it.group == 1 ? &tmO1 : it.group == 2 ? &tmO2 : &tmO3;
+      const int chbase = it.n_tile * p.block_n;
+      if (RES && te == 0) {                     // prefetch the first two residual chunks while the MMAs run
+        tma_wait_read<0>();
+        for (int j = 0; j < 2 && j < nchunks; ++j) {
+          const int b = (cc + j) & 1;
+          mbar_expect_tx(res_bar(b), kStagingBytes);
+          tma_load_4d(staging_base + b * kStagingBytes, &tmR, res_bar(b), chbase + j * 64, it.x0, it.y0, it.img);
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int j = 0; j < nchunks; ++j, ++cc) {
         const int b = cc & 1;
         const uint32_t stg = staging_base + b * kStagingBytes;
-        const int ch0 = it.n_tile * p.block_n + j * 64;   // first output channel of this chunk
-        if (te == 0) {
+        const int ch0 = chbase + j * 64;        // first output channel of this chunk
+        const int ncol = min(64, p.block_n - j * 64);   // valid accumulator columns in this chunk (multiple of 16)
+        if (te == 0 && (!RES || j >= 2)) {
           tma_wait_read<1>();                    // the store that last read staging[b] has drained
-          if (p.res_mode) {
+          if (RES) {
             mbar_expect_tx(res_bar(b), kStagingBytes);
             tma_load_4d(stg, &tmR, res_bar(b), ch0, it.x0, it.y0, it.img);
           }
@@ -274,41 +323,47 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         asm volatile("bar.sync 1, 128;" ::: "memory");
         uint32_t v[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * 64);
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + 32, v + 32);
+        if (ncol > 32) { tmem_ld32(taddr, v); tmem_ld32(taddr + 32, v + 32); }
+        else if (ncol > 16) { tmem_ld32(taddr, v); }
+        else { tmem_ld16(taddr, v); }
         tmem_ld_wait();
         if (j == nchunks - 1) {                  // accumulator fully read -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (p.res_mode) mbar_wait(res_bar(b), (cc >> 1) & 1);
+        if (RES) mbar_wait(res_bar(b), (cc >> 1) & 1);
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int c = ch0 + i * 8;
-          uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ (te & 7)) << 4));
-          float r[8];
-          if (p.res_mode) {
-            const uint4 rv = *cell;
-            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+          if (i * 8 < ncol) {
+            const int c = ch0 + i * 8;
+            uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ (te & 7)) << 4));
+            float r[8];
+            if (RES) {
+              const uint4 rv = *cell;
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
-          }
-          __half2 o[4];
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float y0 = 0.f, y1 = 0.f;
-            if (c + e < p.cout_slab) {           // cout_slab is a multiple of 16 -> pairs never straddle
-              y0 = __uint_as_float(v[i * 8 + e]) * __ldg(p.scale + c + e) + __ldg(p.shift + c + e);
-              y1 = __uint_as_float(v[i * 8 + e + 1]) * __ldg(p.scale + c + e + 1) + __ldg(p.shift + c + e + 1);
+              for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
             }
-            if (p.res_mode == HIS_RES_ADD) { y0 += r[e]; y1 += r[e + 1]; }
-            y0 = his_act(y0, p.act, p.act_beta); y1 = his_act(y1, p.act, p.act_beta);
-            if (p.res_mode == HIS_RES_MUL) { y0 *= r[e]; y1 *= r[e + 1]; }
-            o[e >> 1] = __floats2half2_rn(y0, y1);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + c)), t1 = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
+            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float t = fmaf(__uint_as_float(v[i * 8 + e]), sc[e], sh[e]);
+              if (RES == HIS_RES_ADD) t += r[e];
+              t = epi_act<ACTC>(t, p);
+              if (RES == HIS_RES_MUL) t *= r[e];
+              y[e] = t;
+            }
+            __half2 o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
+            *cell = *reinterpret_cast<uint4*>(o);
           }
-          *cell = *reinterpret_cast<uint4*>(o);
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -329,6 +384,22 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+typedef void (*ConvGemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                               const CUtensorMap, const CUtensorMap, const ConvGemmParams);
+
+template <int BK, int ACTC>
+ConvGemmKernel pick_res(int res) {
+  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1> : conv_gemm_sm100_kernel<BK, ACTC, 2>;
+}
+template <int BK>
+ConvGemmKernel pick_act(int actc, int res) {
+  return actc == 0 ? pick_res<BK, 0>(res) : actc == 1 ? pick_res<BK, 1>(res) : pick_res<BK, 2>(res);
+}
+ConvGemmKernel pick_kernel(int bk, int actc, int res) {
+  return bk == 64 ? pick_act<64>(actc, res) : bk == 32 ? pick_act<32>(actc, res) : pick_act<16>(actc, res);
+}
+int smem_for(int bk) { return bk == 64 ? KCfg<64>::kSmemBytes : bk == 32 ? KCfg<32>::kSmemBytes : KCfg<16>::kSmemBytes; }
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -347,6 +418,10 @@ PFN_encodeTiled get_encode() {
 }
 
 // NHWC fp16 activation slice -> 4-D map {C, W, H, N}; strides in elements of the *buffer*.
+CUtensorMapSwizzle swizzle_for(int box_c) {
+  return box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+
 int encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH, long long sN,
                    int box_c, int box_w, int box_h) {
   PFN_encodeTiled enc = get_encode();
@@ -358,7 +433,7 @@ int encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N,
   if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
     return his_set_error(HIS_ERR_INVALID_ARG, "activation slice is not 16-byte aligned (channel offset/stride must be multiples of 8)");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128]; snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act) failed: %d", (int)r);
@@ -367,16 +442,16 @@ int encode_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N,
   return HIS_OK;
 }
 
-int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, int box_rows) {
+int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, int box_rows, int bk) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return his_set_error(HIS_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   if (((uintptr_t)base & 15) || (strides[0] & 15)) return his_set_error(HIS_ERR_INVALID_ARG, "packed weights must be 16-byte aligned, K % 8 == 0");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[128]; snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
@@ -388,8 +463,17 @@ int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, i
 struct ConvGemmPlan {
   CUtensorMap tmA, tmB, tmO[4], tmR;
   ConvGemmParams p;
-  int grid;
+  int grid, bk, smem;
+  ConvGemmKernel kernel;
 };
+
+// K-block width: the largest of {64,32,16} whose padded K stays within 25 % of the best padding
+int pick_bk(int cin) {
+  const int c16 = (cin + 15) / 16 * 16, c32 = (cin + 31) / 32 * 32, c64 = (cin + 63) / 64 * 64;
+  if (c64 * 4 <= c16 * 5) return 64;
+  if (c32 * 4 <= c16 * 5) return 32;
+  return 16;
+}
 
 int g_num_sms = 0;
 
@@ -426,9 +510,12 @@ int his_conv_gemm_create(void** out_plan,
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return his_set_error(HIS_ERR_NO_DEVICE, "no CUDA device");
     if (prop.major != 10) return his_set_error(HIS_ERR_UNSUPPORTED, "conv_gemm_sm100 needs a compute-capability 10.x device (B200)");
+    for (int bk = 16; bk <= 64; bk *= 2)
+      for (int a = 0; a < 3; ++a)
+        for (int r = 0; r < 3; ++r)
+          if (cudaFuncSetAttribute(pick_kernel(bk, a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
+            return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     g_num_sms = prop.multiProcessorCount;
-    if (cudaFuncSetAttribute(conv_gemm_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
-      return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
   }
   ConvGemmPlan* pl = new ConvGemmPlan();
   memset(pl, 0, sizeof(*pl));
@@ -442,16 +529,32 @@ int his_conv_gemm_create(void** out_plan,
     if (best < 0 || area < best || (area == best && bw >= 8 && bw <= 32)) { best = area; p.bw = bw; p.bh = bh; }
   }
   p.tiles_x = his_div_up(W, p.bw); p.tiles_y = his_div_up(H, p.bh);
-  p.kblocks_per_tap = his_div_up(cin, kBlockK);
+  const int bk = pick_bk(cin);
+  pl->bk = bk;
+  p.kblocks_per_tap = his_div_up(cin, bk);
   his_conv_gemm_tile_n(cout, &p.n_tiles, &p.block_n);
   p.groups = transposed ? 4 : 1;
   p.cout_slab = p.n_tiles * p.block_n;
   p.num_work = n_img * p.tiles_y * p.tiles_x * p.n_tiles * p.groups;
-  p.act = act; p.act_beta = act_beta; p.res_mode = res_mode; p.scale = scale; p.shift = shift;
+  int actc = ACTC_CLAMP;
+  p.act_lo = -INFINITY; p.act_beta = 1.0f; p.act_mul_x = 0;
+  switch (act) {
+    case HIS_ACT_NONE: break;
+    case HIS_ACT_RELU: p.act_lo = 0.0f; break;
+    case HIS_ACT_SILU: actc = ACTC_SIGMOID; p.act_mul_x = 1; break;
+    case HIS_ACT_SIGMOID: actc = ACTC_SIGMOID; break;
+    case HIS_ACT_SWISH: actc = ACTC_SIGMOID; p.act_mul_x = 1; p.act_beta = act_beta; break;
+    case HIS_ACT_GELU: actc = ACTC_GELU; break;
+    default: delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown activation code");
+  }
+  if (res_mode < 0 || res_mode > 2) { delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown res_mode"); }
+  pl->kernel = pick_kernel(bk, actc, res_mode);
+  pl->smem = smem_for(bk);
+  p.scale = scale; p.shift = shift;
   int taps = ksize * ksize;
   int rc;
-  if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, kBlockK, p.bw, p.bh))) { delete pl; return rc; }
-  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, p.block_n))) { delete pl; return rc; }
+  if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, bk, p.bw, p.bh))) { delete pl; return rc; }
+  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, p.block_n, bk))) { delete pl; return rc; }
   if (!transposed) {
     if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
     pl->tmO[1] = pl->tmO[2] = pl->tmO[3] = pl->tmO[0];
@@ -476,8 +579,8 @@ int his_conv_gemm_run(void* plan, void* stream) {
   if (!plan) return his_set_error(HIS_ERR_INVALID_ARG, "null plan");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
   if (pl->p.num_work == 0) return HIS_OK;
-  conv_gemm_sm100_kernel<<<pl->grid, 256, kSmemBytes, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2],
-                                                                            pl->tmO[3], pl->tmR, pl->p);
+  pl->kernel<<<pl->grid, 256, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
+                                                               pl->p);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -492,7 +595,7 @@ int his_conv_gemm_destroy(void* plan) {
 long long his_conv_gemm_issued_macs(void* plan) {
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
   const ConvGemmParams& p = pl->p;
-  return (long long)p.num_work * kBlockM * p.block_n * (long long)(p.ksize * p.ksize * p.kblocks_per_tap * kBlockK);
+  return (long long)p.num_work * kBlockM * p.block_n * (long long)(p.ksize * p.ksize * p.kblocks_per_tap * pl->bk);
 }
 
 }  // extern "C"

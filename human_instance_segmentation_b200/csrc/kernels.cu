@@ -177,14 +177,13 @@ struct DwParams {
   const float* scale; const float* shift;
   int k, stride, pad, Ho, Wo, act;
   __half* out; int out_cs;
-  float* pool;                // [N][C] sums of the activated output (may be null)
+  float* pool;                // [N][gridDim.x][C] per-block partial sums of the activated output (may be null)
 };
 
 __global__ void depthwise_kernel(const DwParams p) {
-  extern __shared__ float s_pool[];     // [C] partial sums of this block (one image per block-row)
+  extern __shared__ float s_pool[];     // [blockDim.x][8] per-thread sums, reduced in a fixed order (deterministic)
   const int cgs = p.C / 8;
   const int n = blockIdx.y;
-  if (p.pool) { for (int c = threadIdx.x; c < p.C; c += blockDim.x) s_pool[c] = 0.0f; __syncthreads(); }
   const long long per_img = (long long)p.Ho * p.Wo * cgs;
   float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += (long long)gridDim.x * blockDim.x) {
@@ -227,54 +226,58 @@ __global__ void depthwise_kernel(const DwParams p) {
   }
   if (p.pool) {
     // blockDim.x is a multiple of C/8 (host guarantees), so this thread always saw channel group threadIdx.x % cgs
-    const int c0 = (threadIdx.x % cgs) * 8;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&s_pool[c0 + e], psum[e]);
+    for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = psum[e];
     __syncthreads();
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) atomicAdd(p.pool + (long long)n * p.C + c, s_pool[c]);
+    float* dst = p.pool + ((long long)n * gridDim.x + blockIdx.x) * p.C;
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const int cg = c >> 3, e = c & 7;
+      float s = 0.0f;
+      for (int t = cg; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
+      dst[c] = s;
+    }
   }
 }
 
-// per-(n,c) sums of an NHWC fp16 tensor (ChannelAttentionModule's adaptive_avg_pool2d)
+// per-(n,c) sums of an NHWC fp16 tensor (ChannelAttentionModule's adaptive_avg_pool2d): per-block partials
+// [N][gridDim.x][C], reduced in a fixed order (deterministic); blockDim.x is a multiple of C/8.
 __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, int cs, float* __restrict__ pool) {
   extern __shared__ float s_pool[];
   const int n = blockIdx.y, cgs = C / 8;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_pool[c] = 0.0f;
-  __syncthreads();
   const long long per_img = (long long)HW * cgs;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int my_cg = -1;
-  const bool fixed_cg = true;   // host launches blockDim.x as a multiple of C/8
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = idx / cgs;
     const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-    if (fixed_cg) {
-      my_cg = cg;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); atomicAdd(&s_pool[cg * 8 + 2 * e], f.x); atomicAdd(&s_pool[cg * 8 + 2 * e + 1], f.y); }
-    }
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
   }
-  if (fixed_cg && my_cg >= 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&s_pool[my_cg * 8 + e], acc[e]);
-  }
+  for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = acc[e];
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(pool + (long long)n * C + c, s_pool[c]);
+  float* dst = pool + ((long long)n * gridDim.x + blockIdx.x) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cg = c >> 3, e = c & 7;
+    float s = 0.0f;
+    for (int t = cg; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
+    dst[c] = s;
+  }
 }
 
 // gate[n][c] = sigmoid(W2 * act(W1 * (pool[n]/HW) + b1) + b2): one block per image.
-__global__ void se_gate_kernel(const float* __restrict__ pool, float inv_hw, int C, int R, const float* __restrict__ w1,
+__global__ void se_gate_kernel(const float* __restrict__ pool, int nparts, float inv_hw, int C, int R, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int act,
                                float act_beta, float* __restrict__ gate) {
   extern __shared__ float sm[];      // [C] means, [R] hidden
   float* mean = sm; float* hid = sm + C;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pool[(long long)n * C + c] * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f;
+    for (int part = 0; part < nparts; ++part) s += pool[((long long)n * nparts + part) * C + c];
+    mean[c] = s * inv_hw;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int r = warp; r < R; r += nw) {
@@ -567,6 +570,27 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
   return HIS_OK;
 }
 
+static int pool_grid_x(long long per_img, int threads, int N, int per_sm) {
+  long long gx = (per_img + threads - 1) / threads;
+  const long long cap = (148LL * per_sm + N - 1) / (N > 0 ? N : 1);
+  if (gx > cap) gx = cap;
+  return (int)(gx < 1 ? 1 : gx);
+}
+
+int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride) {
+  const int pad = ((stride - 1) + (k - 1)) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int threads = threads_multiple_of(C / 8);
+  if (threads == 0) return 0;
+  return pool_grid_x((long long)Ho * Wo * (C / 8), threads, N, 16);
+}
+
+int his_pool_sum_parts(int N, int HW, int C) {
+  const int threads = threads_multiple_of(C / 8);
+  if (threads == 0) return 0;
+  return pool_grid_x(((long long)HW * (C / 8) + 7) / 8, threads, N, 8);
+}
+
 int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale, const float* shift, int k,
                        int stride, int act, void* out, int out_cs, float* pool_sums, void* stream) {
   if (!in || !w || !scale || !shift || !out) return his_set_error(HIS_ERR_INVALID_ARG, "depthwise: null pointer");
@@ -579,12 +603,9 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   const long long per_img = (long long)p.Ho * p.Wo * (C / 8);
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: more than 8192 channels");
-  int gx = (int)((per_img + threads - 1) / threads);
-  const int cap = (148 * 16 + N - 1) / N;      // ~16 resident blocks per SM over the whole batch
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
+  const int gx = pool_grid_x(per_img, threads, N, 16);      // ~16 resident blocks per SM over the whole batch
   dim3 grid(gx, N);
-  depthwise_kernel<<<grid, threads, pool_sums ? C * sizeof(float) : 0, ST>>>(p);
+  depthwise_kernel<<<grid, threads, pool_sums ? threads * 8 * sizeof(float) : 0, ST>>>(p);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -596,21 +617,19 @@ int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums,
   const long long per_img = (long long)HW * (C / 8);
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: more than 8192 channels");
-  int gx = (int)((per_img + threads * 8 - 1) / (threads * 8));
-  const int cap = (148 * 8 + N - 1) / N;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
+  const int gx = pool_grid_x((per_img + 7) / 8, threads, N, 8);
   dim3 grid(gx, N);
-  pool_sum_kernel<<<grid, threads, C * sizeof(float), ST>>>((const __half*)in, HW, C, cs, pool_sums);
+  pool_sum_kernel<<<grid, threads, threads * 8 * sizeof(float), ST>>>((const __half*)in, HW, C, cs, pool_sums);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
-int his_se_gate(const float* pool_sums, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2, const float* b2,
-                int act, float act_beta, float* gate, void* stream) {
+int his_se_gate(const float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2,
+                const float* b2, int act, float act_beta, float* gate, void* stream) {
   if (!pool_sums || !w1 || !w2 || !gate) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: null pointer");
   if (N == 0) return HIS_OK;
-  se_gate_kernel<<<N, kThreads, (C + R) * sizeof(float), ST>>>(pool_sums, 1.0f / (float)HW, C, R, w1, b1, w2, b2, act, act_beta, gate);
+  if (nparts < 1) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: nparts must be >= 1");
+  se_gate_kernel<<<N, kThreads, (C + R) * sizeof(float), ST>>>(pool_sums, nparts, 1.0f / (float)HW, C, R, w1, b1, w2, b2, act, act_beta, gate);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -61,6 +61,7 @@ class Plan:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches = 0
         self.op_flops: List[int] = []
+        self.op_desc: List[str] = []
         self.tag = ""
 
     # -------------------------------------------------------------- allocation
@@ -89,9 +90,10 @@ class Plan:
     # kernels launched per op (cudaMemsetAsync is not one of ours)
     KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0}
 
-    def add(self, name: str, fn, *args, flops: int = 0):
+    def add(self, name: str, fn, *args, flops: int = 0, desc: str = ""):
         self.ops.append((name, fn, args))
         self.op_flops.append(flops)
+        self.op_desc.append(f"{self.tag}:{name} {desc}")
         self.launches += self.KERNELS_PER_OP.get(name, 1)
 
     # -------------------------------------------------------------- ops
@@ -113,7 +115,8 @@ class Plan:
         taps = 4 if transposed else ksize * ksize
         f = 2 * x.N * x.H * x.W * x.C * out.C * taps
         self._add_flops(f, True)
-        self.add("conv_gemm", L.his_conv_gemm_run, h, flops=f)
+        self.add("conv_gemm", L.his_conv_gemm_run, h, flops=f,
+                 desc=f"N{x.N} {x.H}x{x.W} cin{x.C} cout{out.C} k{ksize}{' T' if transposed else ''}{' res%d' % res_mode if res_mode else ''}")
         self.gemm_shapes.append((x.N, x.H, x.W, x.C, out.C, ksize, int(transposed)))
 
     def conv_direct(self, x, in_fmt: int, N, H, W, cin, in_cs, w: torch.Tensor, scale, shift, cout, k, stride, pad, act, beta=1.0,
@@ -123,12 +126,14 @@ class Plan:
         xptr = x.ptr if isinstance(x, Act) else x.data_ptr()
         self.keep += [w, scale, shift]
         ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-        self._add_flops(2 * N * ho * wo * cin * cout * k * k, False)
+        fd = 2 * N * ho * wo * cin * cout * k * k
+        self._add_flops(fd, False)
         self.add("conv_direct", L.his_conv_direct, xptr, in_fmt, in_affine.data_ptr() if in_affine is not None else None, N, H, W,
                  cin, in_cs, w.data_ptr(), scale.data_ptr(), shift.data_ptr(), cout, k, k, stride, pad, act, beta, res_mode,
                  res.ptr if res is not None else None, res.cs if res is not None else 0,
                  out.ptr if out is not None else None, out.cs if out is not None else 0,
-                 out_f32.data_ptr() if out_f32 is not None else None)
+                 out_f32.data_ptr() if out_f32 is not None else None, flops=fd,
+                 desc=f"N{N} {H}x{W} cin{cin} cout{cout} k{k} s{stride} fmt{in_fmt}")
 
     # -------------------------------------------------------------- execution
     def run(self, stream_ptr: int):

@@ -83,7 +83,9 @@ SIGNATURES = {
                         c_float, c_int, _P, c_int, _P, c_int, _P, _P],
     "his_depthwise_conv": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P],
     "his_pool_sum": [_P, c_int, c_int, c_int, c_int, _P, _P],
-    "his_se_gate": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P],
+    "his_se_gate": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P],
+    "his_depthwise_pool_parts": [c_int, c_int, c_int, c_int, c_int, c_int],
+    "his_pool_sum_parts": [c_int, c_int, c_int],
     "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
     "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P],
     "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],

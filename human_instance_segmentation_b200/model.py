@@ -373,17 +373,18 @@ class _BuiltPlan:
             dw_bn, proj, proj_bn = blk.bn1, blk.conv_pw, blk.bn2
         ho, wo = _conv_out(t.H, blk.k, blk.s), _conv_out(t.W, blk.k, blk.s)
         d = p.act(B, ho, wo, blk.mid)
-        pool = p.f32(B, blk.mid)
-        p.add("memset", L.his_memset_async, pool.data_ptr(), 0, pool.numel() * 4)
+        parts = L.his_depthwise_pool_parts(B, t.H, t.W, blk.mid, blk.k, blk.s)
+        pool = p.f32(B, parts, blk.mid)
         wdw = blk.conv_dw.weight.detach().float().cpu().reshape(blk.mid, blk.k * blk.k).t().contiguous().half()
         scale, shift = fold_bn(None, dw_bn, blk.mid)
         p.add("depthwise", L.his_depthwise_conv, t.ptr, B, t.H, t.W, blk.mid, t.cs, p.const(wdw, torch.float16).data_ptr(),
-              p.const(scale).data_ptr(), p.const(shift).data_ptr(), blk.k, blk.s, ACT["silu"], d.ptr, d.cs, pool.data_ptr())
+              p.const(scale).data_ptr(), p.const(shift).data_ptr(), blk.k, blk.s, ACT["silu"], d.ptr, d.cs, pool.data_ptr(),
+              desc=f"N{B} {t.H}x{t.W} C{blk.mid} k{blk.k} s{blk.s}")
         p._add_flops(2 * B * ho * wo * blk.mid * blk.k * blk.k, False)
         se = blk.se
         r = se.conv_reduce.weight.shape[0]
         gate = p.f32(B, blk.mid)
-        p.add("se_gate", L.his_se_gate, pool.data_ptr(), B, ho * wo, blk.mid, r,
+        p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, B, ho * wo, blk.mid, r,
               p.const(se.conv_reduce.weight.reshape(r, blk.mid)).data_ptr(), p.const(se.conv_reduce.bias).data_ptr(),
               p.const(se.conv_expand.weight.reshape(blk.mid, r)).data_ptr(), p.const(se.conv_expand.bias).data_ptr(),
               ACT["silu"], 1.0, gate.data_ptr())
@@ -468,10 +469,10 @@ class _BuiltPlan:
             x = self.conv(sa, tb[3], tb[4], A_ref)                       # ConvT 256->128 k2s2 + norm + act
             ca = tb[6]
             r = ca.fc1.weight.shape[0]
-            pool = p.f32(N, 128); gate_c = p.f32(N, 128)
-            p.add("memset", L.his_memset_async, pool.data_ptr(), 0, pool.numel() * 4)
+            parts = L.his_pool_sum_parts(N, x.H * x.W, 128)
+            pool = p.f32(N, parts, 128); gate_c = p.f32(N, 128)
             p.add("pool_sum", L.his_pool_sum, x.ptr, N, x.H * x.W, 128, x.cs, pool.data_ptr())
-            p.add("se_gate", L.his_se_gate, pool.data_ptr(), N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
+            p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
                   p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, gate_c.data_ptr())
             p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
             x = self.residual_block(x, tb[8], A_ref)

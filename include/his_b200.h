@@ -77,17 +77,21 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
                     void* out_half, int out_cs, float* out_f32, void* stream);
 
 /* ---- timm DepthwiseSeparableConv / InvertedResidual depthwise conv + BN + act (oracle/effunet.py _DS/_IR);
- * symmetric padding ((s-1)+(k-1))/2; w: fp16 [k*k][C]; optionally accumulates per-(n,c) sums of the output
- * (fp32 [N,C], caller zeroes) for the squeeze-excite pooling that follows. */
+ * symmetric padding ((s-1)+(k-1))/2; w: fp16 [k*k][C]; optionally writes per-block partial sums of the output,
+ * fp32 [N][parts][C] with parts = his_depthwise_pool_parts(...), for the squeeze-excite pooling that follows
+ * (fixed-order reduction: bit-reproducible run to run, no atomics). */
+int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride);
 int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale,
                        const float* shift, int k, int stride, int act, void* out, int out_cs, float* pool_sums, void* stream);
 
 /* ---- squeeze-excite (timm SqueezeExcite) and ChannelAttentionModule (hed/advanced/attention_modules.py:10-64):
- * pool_sum: per-(n,c) sums (caller zeroes pool_sums); se_gate: gate = sigmoid(W2*act(W1*mean+b1)+b2), fp32 weights
- * w1 [R,C], w2 [C,R], biases may be NULL; scale_channels: out = in * gate[n,c]. */
+ * pool_sum: per-block partial sums fp32 [N][parts][C], parts = his_pool_sum_parts(...); se_gate: mean = sum of the
+ * `nparts` partials / HW, gate = sigmoid(W2*act(W1*mean+b1)+b2), fp32 weights w1 [R,C], w2 [C,R], biases may be NULL;
+ * scale_channels: out = in * gate[n,c]. */
+int his_pool_sum_parts(int N, int HW, int C);
 int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, void* stream);
-int his_se_gate(const float* pool_sums, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2,
-                const float* b2, int act, float act_beta, float* gate, void* stream);
+int his_se_gate(const float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1,
+                const float* w2, const float* b2, int act, float act_beta, float* gate, void* stream);
 int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream);
 
 /* ---- SpatialAttentionModule, hed/advanced/attention_modules.py:67-113: out = x*sigmoid(conv_kxk([mean_c,max_c])).

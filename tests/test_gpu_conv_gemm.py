@@ -89,6 +89,11 @@ CASES = [
     dict(n=1, h=12, w=16, cin=384, cout=768, k=3),                           # B7 bottleneck width: 3 N-tiles
     dict(n=5, h=64, w=48, cin=256, cout=64, k=3, act=4, beta=1.5),           # swish(beta)
     dict(n=1, h=7, w=5, cin=64, cout=32, k=3, act=5),                        # tiny image, gelu
+    dict(n=2, h=48, w=64, cin=16, cout=16, k=3),                             # BK=16 path (SWIZZLE_32B operands)
+    dict(n=2, h=30, w=40, cin=24, cout=144, k=1, act=2),                     # BK=32 path (SWIZZLE_64B), K tail
+    dict(n=2, h=15, w=20, cin=40, cout=240, k=1, act=2),                     # BK=16, 3 K blocks
+    dict(n=1, h=60, w=80, cin=96, cout=32, k=3, out_slice=(64, 32)),         # BK=32, 3 blocks per tap
+    dict(n=2, h=30, w=40, cin=144, cout=24, k=1, act=0, res_mode=RES_ADD),   # MBConv project + skip, N=32 tile with 24 valid
 ]
 
 

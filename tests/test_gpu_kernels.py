@@ -40,7 +40,8 @@ def test_depthwise_se_matches_torch(k, s, c):
     pad = ((s - 1) + (k - 1)) // 2
     ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
     out = p.act(n, ho, wo, c)
-    pool = p.f32(n, c, zero=True)
+    parts = lib.his_depthwise_pool_parts(n, h, w, c, k, s)
+    pool = p.f32(n, parts, c)
     wdw = p.const(wt.reshape(c, k * k).t().contiguous(), torch.float16)
     st = torch.cuda.current_stream().cuda_stream
     L.check(lib.his_depthwise_conv(x.ptr, n, h, w, c, x.cs, wdw.data_ptr(), p.const(scale).data_ptr(), p.const(shift).data_ptr(), k, s, 2,
@@ -49,7 +50,7 @@ def test_depthwise_se_matches_torch(k, s, c):
     w1, b1 = torch.randn(r, c, generator=g) * 0.2, torch.randn(r, generator=g) * 0.1
     w2, b2 = torch.randn(c, r, generator=g) * 0.2, torch.randn(c, generator=g) * 0.1
     gate = p.f32(n, c)
-    L.check(lib.his_se_gate(pool.data_ptr(), n, ho * wo, c, r, p.const(w1).data_ptr(), p.const(b1).data_ptr(), p.const(w2).data_ptr(),
+    L.check(lib.his_se_gate(pool.data_ptr(), parts, n, ho * wo, c, r, p.const(w1).data_ptr(), p.const(b1).data_ptr(), p.const(w2).data_ptr(),
                             p.const(b2).data_ptr(), 2, 1.0, gate.data_ptr(), st))
     scaled = p.act(n, ho, wo, c)
     L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), n, ho * wo, c, scaled.ptr, scaled.cs, st))

