@@ -73,6 +73,11 @@ struct ConvGemmParams {
   int act_mul_x;
   const float* scale;   // [cout_slab]
   const float* shift;   // [cout_slab]
+  // fused 1x1 tail to <= 2 channels (TAIL kernels): tail[o] = sum_c y[c]*tail_w[o][c] + tail_b[o], NCHW fp32 out
+  const float* tail_w;  // [tail_c][cout_slab]
+  float* tail_out;      // [n_img][tail_c][H][W]
+  float tail_b0, tail_b1;
+  int tail_c, tail_sigmoid, store_main;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -200,7 +205,7 @@ __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) 
 }
 
 // ------------------------------------------------------------------------------------ kernel
-template <int BK, int ACTC, int RES>
+template <int BK, int ACTC, int RES, bool TAIL>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
@@ -308,6 +313,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      float tacc0 = 0.0f, tacc1 = 0.0f;
+      const bool store_main = !TAIL || p.store_main;
       for (int j = 0; j < nchunks; ++j, ++cc) {
         const int b = cc & 1;
         const uint32_t stg = staging_base + b * kStagingBytes;
@@ -359,17 +366,40 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               if (RES == HIS_RES_MUL) t *= r[e];
               y[e] = t;
             }
-            __half2 o[4];
+            if (TAIL) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.tail_w + c)), w1 = __ldg(reinterpret_cast<const float4*>(p.tail_w + c + 4));
+              tacc0 += y[0] * w0.x + y[1] * w0.y + y[2] * w0.z + y[3] * w0.w + y[4] * w1.x + y[5] * w1.y + y[6] * w1.z + y[7] * w1.w;
+              if (p.tail_c > 1) {
+                const float4 u0 = __ldg(reinterpret_cast<const float4*>(p.tail_w + p.cout_slab + c));
+                const float4 u1 = __ldg(reinterpret_cast<const float4*>(p.tail_w + p.cout_slab + c + 4));
+                tacc1 += y[0] * u0.x + y[1] * u0.y + y[2] * u0.z + y[3] * u0.w + y[4] * u1.x + y[5] * u1.y + y[6] * u1.z + y[7] * u1.w;
+              }
+            }
+            if (store_main) {
+              __half2 o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
-            *cell = *reinterpret_cast<uint4*>(o);
+              for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
+              *cell = *reinterpret_cast<uint4*>(o);
+            }
           }
         }
-        fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (te == 0) {
-          tma_store_4d(tmO, stg, ch0, it.x0, it.y0, it.img);
-          tma_commit();
+        if (store_main) {
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (te == 0) {
+            tma_store_4d(tmO, stg, ch0, it.x0, it.y0, it.img);
+            tma_commit();
+          }
+        }
+      }
+      if (TAIL) {
+        const int py = it.y0 + te / p.bw, px = it.x0 + te % p.bw;
+        if (py < p.H && px < p.W) {
+          float o0 = tacc0 + p.tail_b0, o1 = tacc1 + p.tail_b1;
+          if (p.tail_sigmoid) { o0 = 1.0f / (1.0f + __expf(-o0)); o1 = 1.0f / (1.0f + __expf(-o1)); }
+          float* dst = p.tail_out + ((long long)it.img * p.tail_c * p.H + py) * p.W + px;
+          dst[0] = o0;
+          if (p.tail_c > 1) dst[(long long)p.H * p.W] = o1;
         }
       }
     }
@@ -389,7 +419,8 @@ typedef void (*ConvGemmKernel)(const CUtensorMap, const CUtensorMap, const CUten
 
 template <int BK, int ACTC>
 ConvGemmKernel pick_res(int res) {
-  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1> : conv_gemm_sm100_kernel<BK, ACTC, 2>;
+  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0, false> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1, false>
+                                                                            : conv_gemm_sm100_kernel<BK, ACTC, 2, false>;
 }
 template <int BK>
 ConvGemmKernel pick_act(int actc, int res) {
@@ -397,6 +428,12 @@ ConvGemmKernel pick_act(int actc, int res) {
 }
 ConvGemmKernel pick_kernel(int bk, int actc, int res) {
   return bk == 64 ? pick_act<64>(actc, res) : bk == 32 ? pick_act<32>(actc, res) : pick_act<16>(actc, res);
+}
+// fused-tail variants exist for the shapes that need them: clamp activations (none/relu), no residual or residual-add
+ConvGemmKernel pick_tail_kernel(int bk, int res) {
+  if (bk == 64) return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, true> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, true>;
+  if (bk == 32) return res == 0 ? conv_gemm_sm100_kernel<32, ACTC_CLAMP, 0, true> : conv_gemm_sm100_kernel<32, ACTC_CLAMP, 1, true>;
+  return res == 0 ? conv_gemm_sm100_kernel<16, ACTC_CLAMP, 0, true> : conv_gemm_sm100_kernel<16, ACTC_CLAMP, 1, true>;
 }
 int smem_for(int bk) { return bk == 64 ? KCfg<64>::kSmemBytes : bk == 32 ? KCfg<32>::kSmemBytes : KCfg<16>::kSmemBytes; }
 
@@ -463,7 +500,7 @@ int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, i
 struct ConvGemmPlan {
   CUtensorMap tmA, tmB, tmO[4], tmR;
   ConvGemmParams p;
-  int grid, bk, smem;
+  int grid, bk, smem, actc, res_mode, transposed;
   ConvGemmKernel kernel;
 };
 
@@ -515,6 +552,10 @@ int his_conv_gemm_create(void** out_plan,
         for (int r = 0; r < 3; ++r)
           if (cudaFuncSetAttribute(pick_kernel(bk, a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
             return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
+    for (int bk = 16; bk <= 64; bk *= 2)
+      for (int r = 0; r < 2; ++r)
+        if (cudaFuncSetAttribute(pick_tail_kernel(bk, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
+          return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     g_num_sms = prop.multiProcessorCount;
   }
   ConvGemmPlan* pl = new ConvGemmPlan();
@@ -550,6 +591,8 @@ int his_conv_gemm_create(void** out_plan,
   if (res_mode < 0 || res_mode > 2) { delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown res_mode"); }
   pl->kernel = pick_kernel(bk, actc, res_mode);
   pl->smem = smem_for(bk);
+  pl->actc = actc; pl->res_mode = res_mode; pl->transposed = transposed;
+  p.tail_c = 0; p.store_main = 1;
   p.scale = scale; p.shift = shift;
   int taps = ksize * ksize;
   int rc;
@@ -572,6 +615,19 @@ int his_conv_gemm_create(void** out_plan,
   }
   pl->grid = p.num_work < g_num_sms ? p.num_work : g_num_sms;
   *out_plan = pl;
+  return HIS_OK;
+}
+
+int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float tail_b1, int tail_c, int tail_sigmoid, float* tail_out,
+                           int store_main) {
+  if (!plan || !tail_w || !tail_out) return his_set_error(HIS_ERR_INVALID_ARG, "set_tail: null pointer");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  if (tail_c < 1 || tail_c > 2) return his_set_error(HIS_ERR_INVALID_ARG, "set_tail: tail_c must be 1 or 2");
+  if (pl->p.n_tiles != 1 || pl->transposed || pl->actc != ACTC_CLAMP || pl->res_mode == HIS_RES_MUL)
+    return his_set_error(HIS_ERR_UNSUPPORTED, "set_tail: needs a single N tile, none/relu activation, no MUL operand, not transposed");
+  pl->p.tail_w = tail_w; pl->p.tail_b0 = tail_b0; pl->p.tail_b1 = tail_b1; pl->p.tail_c = tail_c; pl->p.tail_sigmoid = tail_sigmoid;
+  pl->p.tail_out = tail_out; pl->p.store_main = store_main;
+  pl->kernel = pick_tail_kernel(pl->bk, pl->res_mode);
   return HIS_OK;
 }
 

@@ -24,11 +24,11 @@ inline int grid_for(long long work, int per_block = kThreads) {
   return (int)g;
 }
 
-// block size that is a multiple of the number of 8-channel groups, so a thread keeps one group
-inline int threads_multiple_of(int cgs) {
-  if (cgs <= 0 || cgs > 1024) return 0;
-  return cgs <= kThreads ? cgs * (kThreads / cgs) : cgs;
-}
+// Reductions over pixels keep one 8-channel group per thread: with 256-thread blocks that holds when the grid
+// stride gridDim.x*256 is a multiple of the number of groups, i.e. gridDim.x is a multiple of cgs/gcd(cgs,256).
+inline int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+inline int threads_multiple_of(int cgs) { return cgs > 0 ? kThreads : 0; }
+inline int grid_multiple(int cgs) { return cgs / gcd_int(cgs, kThreads); }
 
 // ------------------------------------------------------------------------------------ RoI Align
 // reference hed/dynamic_roi_align.py:56-171 (see oracle/headport.py:roi_align for the derivation).
@@ -166,6 +166,115 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
   }
 }
 
+// Small-Cin convolution (Cin <= 4: UNet stem 3->32 s2 from NCHW fp32, ROI feature extractor 3->64, fg_gate 2->64):
+// one thread = one output pixel x 32 output channels; the k*k*Cin input window sits in registers, weights are staged
+// in shared memory as fp32 and read as broadcast float4s.
+template <int KK /*k*k*/, int CIN>
+__global__ void small_cin_conv_kernel(const DirectConvParams p) {
+  extern __shared__ float s_w[];            // [KK*CIN][Cout]
+  const int nw = KK * CIN * p.Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = __half2float(p.w[i]);
+  __syncthreads();
+  const int groups = p.Cout / 32;
+  const long long total = (long long)p.N * p.Ho * p.Wo * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int ox = (int)(pix % p.Wo), oy = (int)((pix / p.Wo) % p.Ho), n = (int)(pix / ((long long)p.Wo * p.Ho));
+    float xin[KK * CIN];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+      const int ky = t / p.kw, kx = t - ky * p.kw;
+      const int iy = oy * p.stride - p.pad + ky, ix = ox * p.stride - p.pad + kx;
+      const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        float v = 0.0f;
+        if (ok) {
+          if (p.in_fmt == 0) v = __half2float(__ldg((const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs + ci));
+          else {
+            v = __ldg((const float*)p.in + ((long long)(n * CIN + ci) * p.H + iy) * p.W + ix);
+            if (p.in_affine) v = fmaf(v, __ldg(p.in_affine + ci), __ldg(p.in_affine + CIN + ci));
+          }
+        }
+        xin[t * CIN + ci] = v;
+      }
+    }
+    const int co = cg * 32;
+    float acc[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) acc[t] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KK * CIN; ++j) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w + j * p.Cout + co);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 wv = wr[q];
+        acc[4 * q] = fmaf(xin[j], wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xin[j], wv.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(xin[j], wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xin[j], wv.w, acc[4 * q + 3]);
+      }
+    }
+    __half* op = p.out_h + pix * p.out_cs + co;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __half2 o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = q * 8 + 2 * e;
+        const float y0 = his_act(acc[c] * __ldg(p.scale + co + c) + __ldg(p.shift + co + c), p.act, p.act_beta);
+        const float y1 = his_act(acc[c + 1] * __ldg(p.scale + co + c + 1) + __ldg(p.shift + co + c + 1), p.act, p.act_beta);
+        o[e] = __floats2half2_rn(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(op + q * 8) = *reinterpret_cast<uint4*>(o);
+    }
+  }
+}
+
+// Small-Cout convolution from an NHWC fp16 slice (smp segmentation head 3x3 16->1, un-fused 1x1 tails): one thread =
+// one output pixel, 16-byte channel vectors, fp32 weights in shared memory, fp32 NCHW output.
+template <int COUT>
+__global__ void small_cout_conv_kernel(const DirectConvParams p) {
+  extern __shared__ float s_w[];            // [kh*kw][Cin][COUT]
+  const int nw = p.kh * p.kw * p.Cin * COUT;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = __half2float(p.w[i]);
+  __syncthreads();
+  const long long total = (long long)p.N * p.Ho * p.Wo;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(pix % p.Wo), oy = (int)((pix / p.Wo) % p.Ho), n = (int)(pix / ((long long)p.Wo * p.Ho));
+    float acc[COUT];
+#pragma unroll
+    for (int t = 0; t < COUT; ++t) acc[t] = 0.0f;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int iy = oy * p.stride - p.pad + ky;
+      if (iy < 0 || iy >= p.H) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int ix = ox * p.stride - p.pad + kx;
+        if (ix < 0 || ix >= p.W) continue;
+        const __half* ip = (const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs;
+        const float* wr = s_w + (long long)(ky * p.kw + kx) * p.Cin * COUT;
+        for (int c8 = 0; c8 < p.Cin; c8 += 8) {
+          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(ip + c8));
+          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(xh[e]);
+#pragma unroll
+            for (int t = 0; t < COUT; ++t) {
+              acc[t] = fmaf(f.x, wr[(c8 + 2 * e) * COUT + t], acc[t]);
+              acc[t] = fmaf(f.y, wr[(c8 + 2 * e + 1) * COUT + t], acc[t]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < COUT; ++t) {
+      const float y = his_act(acc[t] * __ldg(p.scale + t) + __ldg(p.shift + t), p.act, p.act_beta);
+      p.out_f[(((long long)n * COUT + t) * p.Ho + oy) * p.Wo + ox] = y;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ depthwise conv
 // NHWC fp16, 8 channels (16 B) per thread, fused BN scale/shift + activation, optional per-(n,c)
 // sums for the squeeze-excite pooling that follows (fp32 atomics, one per thread per channel after
@@ -180,43 +289,63 @@ struct DwParams {
   float* pool;                // [N][gridDim.x][C] per-block partial sums of the activated output (may be null)
 };
 
-__global__ void depthwise_kernel(const DwParams p) {
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+  if (ACT == HIS_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == HIS_ACT_SILU) return v * __fdividef(1.0f, 1.0f + __expf(-v));
+  if (ACT == HIS_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+  return v;
+}
+
+template <int K, int S, int ACT>
+__global__ void __launch_bounds__(256, 2) depthwise_kernel(const DwParams p) {
+  // one thread = one output pixel x one 8-channel group (16-byte vectors).  All K*K input vectors of the window are
+  // requested before the first FMA (fully unrolled, predicated loads) so that ~K*K 16-byte loads per thread are in
+  // flight; horizontal/vertical window overlap between neighbouring threads is served by L1/L2.
   extern __shared__ float s_pool[];     // [blockDim.x][8] per-thread sums, reduced in a fixed order (deterministic)
   const int cgs = p.C / 8;
   const int n = blockIdx.y;
-  const long long per_img = (long long)p.Ho * p.Wo * cgs;
+  const int per_img = p.Ho * p.Wo * cgs;
+  // fixed channel group per thread: the grid stride gridDim.x*blockDim.x is a multiple of cgs (host guarantees)
+  const int cg = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % cgs);
+  const int c0 = cg * 8;
   float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(idx % cgs);
-    const long long pix = idx / cgs;
-    const int ox = (int)(pix % p.Wo), oy = (int)(pix / p.Wo);
-    const int c0 = cg * 8;
-    float acc[8];
+  float sc[8], sh[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) acc[t] = 0.0f;
-    for (int ky = 0; ky < p.k; ++ky) {
-      const int iy = oy * p.stride - p.pad + ky;
-      if (iy < 0 || iy >= p.H) continue;
-      for (int kx = 0; kx < p.k; ++kx) {
-        const int ix = ox * p.stride - p.pad + kx;
-        if (ix < 0 || ix >= p.W) continue;
-        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs + c0));
-        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)(ky * p.k + kx) * p.C + c0));
-        const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-        const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+  for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+  const __half* inb = p.in + (long long)n * p.H * p.W * p.in_cs + c0;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per_img; idx += gridDim.x * blockDim.x) {
+    const int pix = idx / cgs;
+    const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+    const int iy0 = oy * S - p.pad, ix0 = ox * S - p.pad;
+    // branch-free window fetch: clamped (always valid) addresses, out-of-image taps zeroed by select afterwards
+    uint4 xv[K * K];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
-          acc[2 * e] = fmaf(xf.x, wf.x, acc[2 * e]);
-          acc[2 * e + 1] = fmaf(xf.y, wf.y, acc[2 * e + 1]);
-        }
+    for (int t = 0; t < K * K; ++t) {
+      const int iy = min(max(iy0 + t / K, 0), p.H - 1), ix = min(max(ix0 + t % K, 0), p.W - 1);
+      xv[t] = __ldg(reinterpret_cast<const uint4*>(inb + ((long long)iy * p.W + ix) * p.in_cs));
+    }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+      const int iy = iy0 + t / K, ix = ix0 + t % K;
+      const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+      uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)t * p.C + c0));
+      if (!ok) wv = make_uint4(0u, 0u, 0u, 0u);
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv[t]);
+      const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
+        acc[2 * e] = fmaf(xf.x, wf.x, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(xf.y, wf.y, acc[2 * e + 1]);
       }
     }
     __half2 o[4];
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
-      float y0 = his_act(acc[e] * __ldg(p.scale + c0 + e) + __ldg(p.shift + c0 + e), p.act, 1.0f);
-      float y1 = his_act(acc[e + 1] * __ldg(p.scale + c0 + e + 1) + __ldg(p.shift + c0 + e + 1), p.act, 1.0f);
+      const float y0 = act_ct<ACT>(acc[e] * sc[e] + sh[e]);
+      const float y1 = act_ct<ACT>(acc[e + 1] * sc[e + 1] + sh[e + 1]);
       o[e >> 1] = __floats2half2_rn(y0, y1);
       // pool what the next layer will actually read (the fp16-rounded value)
       const float2 rf = __half22float2(o[e >> 1]);
@@ -225,15 +354,15 @@ __global__ void depthwise_kernel(const DwParams p) {
     *reinterpret_cast<uint4*>(p.out + ((long long)n * p.Ho * p.Wo + pix) * p.out_cs + c0) = *reinterpret_cast<uint4*>(o);
   }
   if (p.pool) {
-    // blockDim.x is a multiple of C/8 (host guarantees), so this thread always saw channel group threadIdx.x % cgs
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = psum[e];
     __syncthreads();
     float* dst = p.pool + ((long long)n * gridDim.x + blockIdx.x) * p.C;
+    const int first = (int)((blockIdx.x * (long long)blockDim.x) % cgs);   // channel group of thread 0
     for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-      const int cg = c >> 3, e = c & 7;
+      const int g2 = c >> 3, e = c & 7;
       float s = 0.0f;
-      for (int t = cg; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
+      for (int t = (g2 - first + cgs) % cgs; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
       dst[c] = s;
     }
   }
@@ -258,10 +387,11 @@ __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, in
   for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = acc[e];
   __syncthreads();
   float* dst = pool + ((long long)n * gridDim.x + blockIdx.x) * C;
+  const int first = (int)((blockIdx.x * (long long)blockDim.x) % cgs);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int cg = c >> 3, e = c & 7;
     float s = 0.0f;
-    for (int t = cg; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
+    for (int t = (cg - first + cgs) % cgs; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
     dst[c] = s;
   }
 }
@@ -557,6 +687,28 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
   p.act = act; p.act_beta = act_beta; p.res_mode = res_mode; p.res = (const __half*)res; p.res_cs = res_cs;
   p.out_h = (__half*)out_half; p.out_cs = out_cs; p.out_f = out_f32;
   if (N == 0) return HIS_OK;
+  // specialised kernels for the shapes the path actually uses
+  if (cin <= 4 && cout % 32 == 0 && out_half && !out_f32 && !res_mode && (out_cs % 8) == 0 && kh == kw && (kh == 1 || kh == 3) &&
+      (size_t)kh * kw * cin * cout * sizeof(float) <= 48 * 1024 && (in_fmt == 1 || in_fmt == 0)) {
+    const long long total = (long long)N * p.Ho * p.Wo * (cout / 32);
+    const int g = grid_for(total, 128);
+    const size_t sm = (size_t)kh * kw * cin * cout * sizeof(float);
+    bool done = true;
+    if (kh == 3 && cin == 3) small_cin_conv_kernel<9, 3><<<g, 128, sm, ST>>>(p);
+    else if (kh == 1 && cin == 2) small_cin_conv_kernel<1, 2><<<g, 128, sm, ST>>>(p);
+    else if (kh == 1 && cin == 3) small_cin_conv_kernel<1, 3><<<g, 128, sm, ST>>>(p);
+    else done = false;
+    if (done) { HIS_CHECK_LAUNCH(); return HIS_OK; }
+  }
+  if (in_fmt == 0 && cout <= 2 && out_f32 && !out_half && !res_mode && cin % 8 == 0 && in_cs % 8 == 0 &&
+      (size_t)kh * kw * cin * cout * sizeof(float) <= 48 * 1024) {
+    const long long total = (long long)N * p.Ho * p.Wo;
+    const size_t sm = (size_t)kh * kw * cin * cout * sizeof(float);
+    if (cout == 1) small_cout_conv_kernel<1><<<grid_for(total), kThreads, sm, ST>>>(p);
+    else small_cout_conv_kernel<2><<<grid_for(total), kThreads, sm, ST>>>(p);
+    HIS_CHECK_LAUNCH();
+    return HIS_OK;
+  }
   const int cot = (cout % 8 == 0) ? 8 : (cout % 4 == 0) ? 4 : (cout % 2 == 0) ? 2 : 1;
   const long long total = (long long)N * p.Ho * p.Wo * (cout / cot);
   const int g = grid_for(total);
@@ -570,11 +722,13 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
   return HIS_OK;
 }
 
-static int pool_grid_x(long long per_img, int threads, int N, int per_sm) {
+static int pool_grid_x(long long per_img, int threads, int N, int per_sm, int cgs) {
   long long gx = (per_img + threads - 1) / threads;
   const long long cap = (148LL * per_sm + N - 1) / (N > 0 ? N : 1);
   if (gx > cap) gx = cap;
-  return (int)(gx < 1 ? 1 : gx);
+  if (gx < 1) gx = 1;
+  const int m = grid_multiple(cgs);
+  return (int)((gx + m - 1) / m * m);
 }
 
 int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride) {
@@ -582,13 +736,13 @@ int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride) {
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return 0;
-  return pool_grid_x((long long)Ho * Wo * (C / 8), threads, N, 16);
+  return pool_grid_x((long long)Ho * Wo * (C / 8), threads, N, 16, C / 8);
 }
 
 int his_pool_sum_parts(int N, int HW, int C) {
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return 0;
-  return pool_grid_x(((long long)HW * (C / 8) + 7) / 8, threads, N, 8);
+  return pool_grid_x(((long long)HW * (C / 8) + 7) / 8, threads, N, 8, C / 8);
 }
 
 int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale, const float* shift, int k,
@@ -603,9 +757,22 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   const long long per_img = (long long)p.Ho * p.Wo * (C / 8);
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: more than 8192 channels");
-  const int gx = pool_grid_x(per_img, threads, N, 16);      // ~16 resident blocks per SM over the whole batch
+  if (per_img >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: image too large");
+  const int gx = pool_grid_x(per_img, threads, N, 16, C / 8);      // ~16 blocks per SM over the whole batch
   dim3 grid(gx, N);
-  depthwise_kernel<<<grid, threads, pool_sums ? threads * 8 * sizeof(float) : 0, ST>>>(p);
+  const size_t sm = pool_sums ? threads * 8 * sizeof(float) : 0;
+  if (act != HIS_ACT_SILU && act != HIS_ACT_NONE) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: activation must be SiLU or none");
+#define DW_LAUNCH(K_, S_)                                                                          \
+  do {                                                                                             \
+    if (act == HIS_ACT_SILU) depthwise_kernel<K_, S_, HIS_ACT_SILU><<<grid, threads, sm, ST>>>(p); \
+    else depthwise_kernel<K_, S_, HIS_ACT_NONE><<<grid, threads, sm, ST>>>(p);                     \
+  } while (0)
+  if (k == 3 && stride == 1) DW_LAUNCH(3, 1);
+  else if (k == 3 && stride == 2) DW_LAUNCH(3, 2);
+  else if (k == 5 && stride == 1) DW_LAUNCH(5, 1);
+  else if (k == 5 && stride == 2) DW_LAUNCH(5, 2);
+  else return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: kernel size must be 3 or 5, stride 1 or 2");
+#undef DW_LAUNCH
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -617,7 +784,7 @@ int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums,
   const long long per_img = (long long)HW * (C / 8);
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: more than 8192 channels");
-  const int gx = pool_grid_x((per_img + 7) / 8, threads, N, 8);
+  const int gx = pool_grid_x((per_img + 7) / 8, threads, N, 8, C / 8);
   dim3 grid(gx, N);
   pool_sum_kernel<<<grid, threads, threads * 8 * sizeof(float), ST>>>((const __half*)in, HW, C, cs, pool_sums);
   HIS_CHECK_LAUNCH();

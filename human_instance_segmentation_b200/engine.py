@@ -47,6 +47,14 @@ class Act:
         return self.buf[..., self.c_off:self.c_off + self.C].permute(0, 3, 1, 2).float().contiguous()
 
 
+class NullAct(Act):
+    """Geometry-only stand-in for an activation that is never written (GEMM with a fused tail and store_main=0)."""
+
+    def __init__(self, buf: torch.Tensor, N: int, H: int, W: int, C: int):
+        self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
+        self.cs, self.c_off = round_up(C, 8), 0
+
+
 class Plan:
     def __init__(self, device: torch.device):
         self.device = device
@@ -70,6 +78,11 @@ class Plan:
         buf = torch.empty((N, H, W, cs), dtype=torch.float16, device=self.device)
         self.keep.append(buf)
         return Act(buf, C)
+
+    def null_act(self, N, H, W, C) -> NullAct:
+        buf = torch.zeros(64, dtype=torch.float16, device=self.device)
+        self.keep.append(buf)
+        return NullAct(buf, N, H, W, C)
 
     def f32(self, *shape, zero=False) -> torch.Tensor:
         t = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.device)
@@ -99,7 +112,9 @@ class Plan:
     # -------------------------------------------------------------- ops
     def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, scale: torch.Tensor, shift: torch.Tensor, out: Act,
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
-                  transposed: bool = False):
+                  transposed: bool = False, tail=None):
+        """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
+        channels into the epilogue (his_conv_gemm_set_tail)."""
         L = self.lib
         h = ctypes.c_void_p()
         if transposed:
@@ -114,9 +129,16 @@ class Plan:
         self.keep += [w_packed, scale, shift]
         taps = 4 if transposed else ksize * ksize
         f = 2 * x.N * x.H * x.W * x.C * out.C * taps
+        if tail is not None:
+            tw, (b0, b1), tc, sig, tout, store_main = tail
+            _lib.check(L.his_conv_gemm_set_tail(h, tw.data_ptr(), float(b0), float(b1), tc, 1 if sig else 0, tout.data_ptr(),
+                                                1 if store_main else 0), "his_conv_gemm_set_tail")
+            self.keep += [tw, tout]
+            f += 2 * x.N * x.H * x.W * out.C * tc
         self._add_flops(f, True)
         self.add("conv_gemm", L.his_conv_gemm_run, h, flops=f,
-                 desc=f"N{x.N} {x.H}x{x.W} cin{x.C} cout{out.C} k{ksize}{' T' if transposed else ''}{' res%d' % res_mode if res_mode else ''}")
+                 desc=f"N{x.N} {x.H}x{x.W} cin{x.C} cout{out.C} k{ksize}{' T' if transposed else ''}{' res%d' % res_mode if res_mode else ''}"
+                      f"{' +tail%d' % tail[2] if tail is not None else ''}")
         self.gemm_shapes.append((x.N, x.H, x.W, x.C, out.C, ksize, int(transposed)))
 
     def conv_direct(self, x, in_fmt: int, N, H, W, cin, in_cs, w: torch.Tensor, scale, shift, cout, k, stride, pad, act, beta=1.0,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "his_conv_gemm_tile_n": [c_int, POINTER(c_int), POINTER(c_int)],
     "his_conv_gemm_create": [POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int,
                              _P, _P, c_int, c_int, c_int, c_float, c_int],
+    "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
     "his_conv_gemm_run": [_P, _P],
     "his_conv_gemm_destroy": [_P],
     "his_conv_gemm_issued_macs": [_P],

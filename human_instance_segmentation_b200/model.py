@@ -245,8 +245,10 @@ class _BuiltPlan:
         return isinstance(norm, nn.BatchNorm2d)
 
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
-             out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None) -> Optional[Act]:
-        """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel."""
+             out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None) -> Optional[Act]:
+        """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
+        tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
+        epilogue; the wide activation itself is then not written (its only consumer is the tail)."""
         p = self.plan
         if norm is not None and not self._is_bn(norm):
             raise NotImplementedError("normalization_type='layernorm2d' is not implemented on the B200 path yet "
@@ -261,24 +263,37 @@ class _BuiltPlan:
         oh, ow = (2 * x.H, 2 * x.W) if transposed else (x.H, x.W)
         use_gemm = cin >= 16 and cout >= 16 and (transposed or k in (1, 3)) and out_f32 is None
         if out is None and out_f32 is None:
-            out = p.act(x.N, oh, ow, cout)
+            out = p.null_act(x.N, oh, ow, cout) if (tail is not None and use_gemm) else p.act(x.N, oh, ow, cout)
         if use_gemm:
             nt, bn = ctypes.c_int(), ctypes.c_int()
             p.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
             slab = nt.value * bn.value
             wp, cin_pad = pack_gemm_weight(w, slab, transposed)
+            tl = None
+            if tail is not None:
+                tconv, tsig, tout = tail
+                tc = tconv.weight.shape[0]
+                tw = torch.zeros(tc, slab)
+                tw[:, :cout] = tconv.weight.detach().float().cpu().reshape(tc, cout)
+                tb = tconv.bias.detach().float().cpu().tolist() + [0.0]
+                tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(scale, slab)), p.const(pad_vec(shift, slab)), out,
-                        k, act, self.beta, res, res_mode, transposed)
+                        k, act, self.beta, res, res_mode, transposed, tail=tl)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
+            assert tail is None
             p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, p.const(pack_direct_weight(w), torch.float16), p.const(scale), p.const(shift),
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
 
-    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None) -> Act:
+    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None) -> Act:
         t = self.conv(x, rb.conv1, rb.norm1, act)
-        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out)
+        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail)
+
+    def _tail_ok(self, act: int) -> bool:
+        """The fused tail exists for none/relu epilogues (every preset); other activations use the separate 1x1 kernel."""
+        return act in (ACT["none"], ACT["relu"])
 
     def to_mask_size(self, t: torch.Tensor) -> torch.Tensor:
         """F.interpolate(size=mask, bilinear, align_corners=False) when sizes differ (..._refinement.py:561-566)."""
@@ -475,14 +490,16 @@ class _BuiltPlan:
             p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
                   p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, gate_c.data_ptr())
             p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
-            x = self.residual_block(x, tb[8], A_ref)
-            tail = tb[9]
+            last_rb, tail = tb[8], tb[9]
         else:
             x = self.conv(x, tb[2], tb[3], A_ref)
-            x = self.residual_block(x, tb[6], A_ref)
-            tail = tb[7]
+            last_rb, tail = tb[6], tb[7]
         tn_nat = p.f32(N, 2, 2 * rh, 2 * rw)
-        self.conv(x, tail, None, ACT["none"], out_f32=tn_nat)
+        if self._tail_ok(A_ref):
+            self.residual_block(x, last_rb, A_ref, tail=(tail, False, tn_nat))
+        else:
+            x = self.residual_block(x, last_rb, A_ref)
+            self.conv(x, tail, None, ACT["none"], out_f32=tn_nat)
         tn = self.to_mask_size(tn_nat)
         p.add("head_combine", L.his_head_combine, bgfg.data_ptr(), tn.data_ptr(), N, mh, mw, self.logits.data_ptr())
 
@@ -495,9 +512,12 @@ class _BuiltPlan:
         if m.use_contour_detection:
             cb = head.contour_branch.contour_branch
             c = self.conv(shared, cb[0], cb[1], A_ref)
-            c = self.conv(c, cb[3], cb[4], A_ref)
             c_low = p.f32(N, 1, rh, rw)
-            self.conv(c, cb[6], None, ACT["sigmoid"], out_f32=c_low)
+            if self._tail_ok(A_ref):
+                self.conv(c, cb[3], cb[4], A_ref, tail=(cb[6], True, c_low))
+            else:
+                c = self.conv(c, cb[3], cb[4], A_ref)
+                self.conv(c, cb[6], None, ACT["sigmoid"], out_f32=c_low)
             contours = self.to_mask_size(c_low)
             if aux_level != "none":
                 self.aux["contours"] = contours
@@ -505,9 +525,12 @@ class _BuiltPlan:
             dd = head.distance_decoder
             dh = dd.distance_head
             d = self.conv(shared, dh[0], dh[1], A_ref)
-            d = self.residual_block(d, dh[3], A_ref)
             d_low = p.f32(N, 1, rh, rw)
-            self.conv(d, dh[4], None, ACT["none"], out_f32=d_low)
+            if self._tail_ok(A_ref):
+                self.residual_block(d, dh[3], A_ref, tail=(dh[4], False, d_low))
+            else:
+                d = self.residual_block(d, dh[3], A_ref)
+                self.conv(d, dh[4], None, ACT["none"], out_f32=d_low)
             m_low = p.f32(N, 1, rh, rw)
             thr = p.const(dd.threshold.detach().reshape(1))
             p.add("distance_mask", L.his_map_f32, d_low.data_ptr(), d_low.numel(), 1, thr.data_ptr(), m_low.data_ptr())
@@ -568,8 +591,11 @@ class _BuiltPlan:
             x = self.residual_block(x, dec[3], A)
             x = self.residual_block(x, dec[4], A)
         f = u.final
-        x = self.conv(x, f[0], f[1], A)
-        self.conv(x, f[3], None, ACT["none"], out_f32=low_out)
+        if self._tail_ok(A):
+            self.conv(x, f[0], f[1], A, tail=(f[3], False, low_out))
+        else:
+            x = self.conv(x, f[0], f[1], A)
+            self.conv(x, f[3], None, ACT["none"], out_f32=low_out)
 
 
 # ======================================================================================= factory

@@ -62,6 +62,11 @@ int his_conv_gemm_create(void** plan, const void* in, int n_img, int H, int W, i
                          const void* w_packed, int cin_pad, void* out, int cout, int out_cs,
                          const void* res, int res_cs, const float* scale, const float* shift,
                          int ksize, int transposed, int act, float act_beta, int res_mode);
+/* Optional fused 1x1 tail to 1-2 channels computed in the epilogue from the fp32 activations (the Cout<=2 convs at
+ * ..._refinement.py:293,335,523 and ..._unet.py:371): tail_out[n,o,y,x] = (sigmoid)(sum_c y[c]*tail_w[o][c] + tail_b[o]),
+ * NCHW fp32; tail_w: device fp32 [tail_c][cout_slab]; store_main=0 skips writing the wide activation altogether. */
+int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float tail_b1, int tail_c, int tail_sigmoid,
+                           float* tail_out, int store_main);
 int his_conv_gemm_run(void* plan, void* stream);
 int his_conv_gemm_destroy(void* plan);
 long long his_conv_gemm_issued_macs(void* plan);

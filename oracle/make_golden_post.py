@@ -1,0 +1,72 @@
+"""Oracle (test infrastructure): golden vectors of the post-processing family from the REAL reference modules/functions."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from human_instance_segmentation_b200.synthetic import synth_rois
+from . import refload
+
+
+def blob_masks(seed: int, n: int, h: int, w: int) -> torch.Tensor:
+    """SURVEY §8d cfg 5: (rand > 0.5) smoothed by a 15x15 box blur, re-thresholded -> blob-like binary masks."""
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, 1, h, w, generator=g) > 0.5).float()
+    x = F.avg_pool2d(F.pad(x, (7, 7, 7, 7), mode="replicate"), 15, 1)
+    return (x > 0.5).float()
+
+
+def all_3x3_patterns() -> torch.Tensor:
+    """Every binary 3x3 neighbourhood once, centre pixels on a 5-pixel pitch (the tie-sensitive cases of SURVEY §8 a16)."""
+    img = torch.zeros(1, 1, 16 * 5 + 2, 32 * 5 + 2)
+    for p in range(512):
+        r, c = divmod(p, 32)
+        for b in range(9):
+            if (p >> b) & 1:
+                img[0, 0, 1 + r * 5 + b // 3, 1 + c * 5 + b % 3] = 1.0
+    return img
+
+
+def make_post_goldens(golden_dir: str):
+    es = refload.ref_import("edge_smoothing")
+    bf = refload.ref_import("bilateral_filter")
+    out = {}
+    masks = blob_masks(5, 3, 96, 128)
+    noisy = (masks + 0.15 * torch.randn(masks.shape, generator=torch.Generator().manual_seed(6))).contiguous()   # float-valued, outside [0,1]
+    out["masks"], out["noisy"] = masks.numpy(), noisy.numpy()
+    with torch.no_grad():
+        out["edge_smooth"] = es.BinaryMaskEdgeSmoothing()(masks).numpy()
+        out["edge_smooth_t04_s2"] = es.BinaryMaskEdgeSmoothing(0.4, 2.0)(masks).numpy()
+        pat = all_3x3_patterns()
+        out["patterns"] = pat.numpy()
+        out["edge_smooth_patterns"] = es.BinaryMaskEdgeSmoothing()(pat).numpy()
+        out["binary_bilateral"] = bf.BinaryMaskBilateralFilter()(masks).numpy()
+        out["binary_bilateral_noisy"] = bf.BinaryMaskBilateralFilter()(noisy).numpy()
+        out["binary_bilateral_k5_it3"] = bf.BinaryMaskBilateralFilter(5, 1.0, 0.5, 3)(masks).numpy()
+        out["morph_bilateral"] = bf.MorphologicalBilateralFilter()(masks).numpy()
+        out["morph_bilateral_noisy"] = bf.MorphologicalBilateralFilter()(noisy).numpy()
+    # paste-back through the reference script's own functions
+    fn = refload.ref_functions_from_script("test_hierarchical_instance_peopleseg_onnx.py", ["denormalize_bbox", "process_mask_output"])
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randn(7, 3, 32, 24, generator=g) * 2
+    rois = synth_rois(9, 1, 7)
+    rois[3, 1:] = torch.tensor([0.7, 0.699999988, 0.95, 1.0])     # products that land next to an integer
+    H, W = 480, 640
+    res = fn["process_mask_output"](logits.numpy(), rois.numpy(), W, H, 0.5)
+    canvas = np.zeros((1, H, W), np.int32)
+    target = np.zeros((7, 32, 24), np.uint8)
+    for i, r in enumerate(res):
+        x1, y1, x2, y2 = r["bbox"]
+        full = np.zeros((H, W), np.uint8)
+        if x2 > x1 and y2 > y1:
+            full[y1:y2, x1:x2] = r["mask"]
+        canvas[0][full > 0] = i + 1
+        sm = F.softmax(logits[i], 0).numpy()
+        target[i] = ((r["raw_mask"] == 1) & (sm.max(0) > 0.5)).astype(np.uint8)
+    assert len(res) == 7
+    out["paste_logits"], out["paste_rois"], out["paste_canvas"], out["paste_target"] = logits.numpy(), rois.numpy(), canvas, target
+    np.savez_compressed(os.path.join(golden_dir, "post.npz"), **out)
+    print("post goldens:", {k: v.shape for k, v in out.items()})

@@ -80,6 +80,24 @@ def ref_class_from_script(script: str, class_name: str):
     raise KeyError(f"{class_name} not found in {script}")
 
 
+def ref_functions_from_script(script: str, names):
+    """Like ``ref_class_from_script`` for top-level functions (e.g. ``denormalize_bbox`` / ``process_mask_output`` of
+    test_hierarchical_instance_peopleseg_onnx.py, whose module-level imports need onnxruntime/pycocotools)."""
+    import ast
+    import typing
+    import cv2
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    path = os.path.join(REFERENCE_ROOT, script)
+    tree = ast.parse(open(path).read(), filename=path)
+    ns = {"torch": torch, "F": F, "np": np, "cv2": cv2, "__name__": "ref_funcs"}
+    ns.update({k: getattr(typing, k) for k in ("Optional", "Union", "Tuple", "List", "Dict", "Any")})
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return {n: ns[n] for n in names}
+
+
 def build_reference_model(**kwargs):
     """``create_rgb_hierarchical_model(**kwargs)`` of the reference, stdout silenced, eval mode."""
     mod = ref_import("advanced.hierarchical_segmentation_rgb")
