@@ -128,6 +128,8 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
         self.aux_outputs = "full"        # "full" (reference dict) | "light" (no 256-channel tensors) | "none"
         self.copy_outputs = True         # return fresh tensors (False: views of the plan's static buffers)
         self.use_cuda_graph = False
+        self.max_rois_per_pass = None    # None: derived from the ROI size (bounds the activation footprint)
+        self.max_images_per_pass = None  # None: derived from the image size / encoder width
         self._plans: Dict[tuple, "_BuiltPlan"] = {}
         self._param_version = 0
         self.eval()
@@ -194,7 +196,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
         if dev.type != "cuda":
             raise _lib.HisError("move the model to a CUDA device first (model.to('cuda')); there is no CPU fallback")
         B, _, H, W = images.shape
-        key = (B, H, W, rois.shape[0], self.aux_outputs, tuple(_scale_hw(self.roi_align_mask)), tuple(_scale_hw(self.roi_align_rgb)),
+        key = (B, H, W, rois.shape[0], self.aux_outputs, self.max_rois_per_pass, self.max_images_per_pass, tuple(_scale_hw(self.roi_align_mask)), tuple(_scale_hw(self.roi_align_rgb)),
                self.roi_align_mask.aligned, self.roi_align_rgb.aligned, dev.index)
         bp = self._plans.get(key)
         if bp is None:
@@ -210,26 +212,114 @@ def _scale_hw(ra: DynamicRoIAlign):
 
 
 # ======================================================================================= plan construction
+class _CompositePlan:
+    """bench/graph-facing view of the (UNet sub-plan x image chunks) + (head sub-plan x ROI chunks) schedule."""
+
+    def __init__(self, bp: "_BuiltPlan"):
+        self.bp = bp
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def _parts(self):
+        bp = self.bp
+        parts = [(bp.unet_plan, bp.n_unet_chunks)]
+        if bp.head_plan is not None:
+            parts.append((bp.head_plan, bp.n_head_chunks))
+        return parts
+
+    @property
+    def launches(self) -> int:
+        extra = self.bp.n_unet_chunks if self.bp.chunked_unet else 0
+        return sum(pl.launches * reps for pl, reps in self._parts()) + extra
+
+    @property
+    def flops(self) -> int:
+        return sum(pl.flops * reps for pl, reps in self._parts())
+
+    @property
+    def tensor_flops(self) -> int:
+        return sum(pl.tensor_flops * reps for pl, reps in self._parts())
+
+    @property
+    def op_desc(self):
+        return [d for pl, reps in self._parts() for _ in range(reps) for d in pl.op_desc]
+
+    def run_timed(self):
+        """Per-op CUDA-event times of one full step (chunk copies excluded)."""
+        return self.bp.run(timed=True)
+
+    def replay(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.bp.run()
+
+    def capture(self):
+        dev = self.bp.dev
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(dev)
+        with torch.cuda.stream(side):
+            self.bp.run()                       # warm-up outside capture (module load, attribute sets)
+        side.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self.bp.run()
+        self.graph = g
+
+
+def _rois_per_pass(roi_hw) -> int:
+    """ROIs per head pass: bounds the activation footprint (~40 B0-equivalent bytes/ROI-pixel x 2e6 ROI-pixels)."""
+    return max(1, int(2.0e6 // (roi_hw[0] * roi_hw[1])) // 32 * 32 or 1)
+
+
+def _images_per_pass(h: int, w: int, stem_c: int) -> int:
+    return max(1, int(64 * 480 * 640 * 32 // (h * w * stem_c)))
+
+
 class _BuiltPlan:
-    """One launch plan for a fixed (B,H,W,N): static input/output buffers + the op list."""
+    """Launch schedule for a fixed (B,H,W,N): static input/output buffers, one UNet sub-plan replayed per image chunk
+    and one head sub-plan replayed per ROI chunk (chunks bound the HBM footprint; a single chunk aliases the full
+    buffers, so the common case has no extra copies)."""
 
     def __init__(self, m: HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet, dev, B, H, W, N):
         self.m, self.dev, self.B, self.H, self.W, self.N = m, dev, B, H, W, N
-        self.plan = Plan(dev)
-        p = self.plan
-        self.images = p.f32(B, 3, H, W)
-        self.rois = p.f32(max(N, 1), 5, zero=True)
-        self.aux: Dict[str, torch.Tensor] = {}
-        self._scratch_free = []
         self.act_rgb = {"relu": ACT["relu"], "swish": ACT["silu"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
         self.act_ref = {"relu": ACT["relu"], "swish": ACT["swish"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
         self.beta = m.activation_beta
+        stem_c = m.pretrained_unet.model.model.encoder.out_channels[1]
+        self.Bc = min(B, m.max_images_per_pass or _images_per_pass(H, W, stem_c))
+        self.Nc = min(N, m.max_rois_per_pass or _rois_per_pass(m.roi_size))
+        self.chunked_unet, self.chunked_head = self.Bc < B, self.Nc < N
+        self.n_unet_chunks = (B + self.Bc - 1) // self.Bc
+        self.n_head_chunks = (N + self.Nc - 1) // self.Nc if N else 0
+        # ---- UNet sub-plan
+        self.unet_plan = self.plan = Plan(dev)
+        p = self.plan
         p.tag = "unet"
+        self.images = p.f32(B, 3, H, W)
+        self.rois = p.f32(max(N, 1), 5, zero=True)
+        self.two = p.f32(B, 2, H, W)
+        self.binary = p.f32(B, 1, H, W)
+        self.u_images = p.f32(self.Bc, 3, H, W) if self.chunked_unet else self.images
         self._build_unet()
-        p.tag = "head"
-        self._build_head()
+        # ---- head sub-plan
+        self.aux: Dict[str, torch.Tensor] = {}
+        self.h_aux: Dict[str, torch.Tensor] = {}
+        self.head_plan = None
+        mh, mw = m.mask_size
+        self.logits = self.unet_plan.f32(N, 3, mh, mw)
+        if m.aux_outputs != "none":
+            self.aux["full_image_logits"] = self.two
+        if N:
+            self.head_plan = self.plan = Plan(dev)
+            self.plan.tag = "head"
+            self.h_rois = self.plan.f32(self.Nc, 5, zero=True) if self.chunked_head else self.rois
+            self.h_logits = self.plan.f32(self.Nc, 3, mh, mw) if self.chunked_head else self.logits
+            self._build_head()
+            for k, v in self.h_aux.items():
+                self.aux[k] = self.plan.f32(N, *v.shape[1:]) if self.chunked_head else v
+        self.plan = _CompositePlan(self)
 
-    # -------------------------------------------------------------- I/O
+    # -------------------------------------------------------------- I/O + schedule
     def load_inputs(self, images: torch.Tensor, rois: torch.Tensor):
         self.images.copy_(images, non_blocking=True)
         if self.N:
@@ -239,6 +329,37 @@ class _BuiltPlan:
         f = (lambda t: t.clone()) if copy else (lambda t: t)
         aux = {k: f(v) for k, v in self.aux.items()}
         return f(self.logits), aux
+
+    def run(self, timed: bool = False):
+        L = self.unet_plan.lib
+        H, W = self.H, self.W
+        out = []
+        for i0 in range(0, self.B, self.Bc):
+            n = min(self.Bc, self.B - i0)
+            if self.chunked_unet:
+                self.u_images[:n].copy_(self.images[i0:i0 + n])
+            if timed:
+                out += self.unet_plan.run_timed()
+            else:
+                self.unet_plan.replay()
+            if self.chunked_unet:
+                st = torch.cuda.current_stream(self.dev).cuda_stream
+                _lib.check(L.his_unet_outputs(self.u_one.data_ptr(), n, H, W, *self._oc, self.two.data_ptr() + i0 * 2 * H * W * 4,
+                                              self.binary.data_ptr() + i0 * H * W * 4, ctypes.c_void_p(st)), "his_unet_outputs")
+        for j0 in range(0, self.N, max(self.Nc, 1)):
+            n = min(self.Nc, self.N - j0)
+            if self.chunked_head:
+                self.h_rois.zero_()
+                self.h_rois[:n].copy_(self.rois[j0:j0 + n])
+            if timed:
+                out += self.head_plan.run_timed()
+            else:
+                self.head_plan.replay()
+            if self.chunked_head:
+                self.logits[j0:j0 + n].copy_(self.h_logits[:n])
+                for k, v in self.h_aux.items():
+                    self.aux[k][j0:j0 + n].copy_(v[:n])
+        return out
 
     # -------------------------------------------------------------- helpers
     def _is_bn(self, norm) -> bool:
@@ -313,7 +434,7 @@ class _BuiltPlan:
     # -------------------------------------------------------------- EfficientNet-UNet (full image)
     def _build_unet(self):
         m, p, L = self.m, self.plan, self.plan.lib
-        B, H, W = self.B, self.H, self.W
+        B, H, W = self.Bc, self.H, self.W
         holder = m.pretrained_unet.model
         net = holder.model
         enc, dec = net.encoder, net.decoder
@@ -323,7 +444,8 @@ class _BuiltPlan:
         mean = (ctypes.c_float * 3)(*[float(v) for v in holder.norm_mean.flatten().tolist()])
         std = (ctypes.c_float * 3)(*[float(v) for v in holder.norm_std.flatten().tolist()])
         p.keep += [mean, std]
-        p.add("input_affine", L.his_unet_input_affine, self.images.data_ptr(), B * 3 * H * W, mean, std, flag.data_ptr(), affine.data_ptr())
+        # the reference tests x.max() over the WHOLE batch tensor (..._unet.py:1888), so the flag always comes from self.images
+        p.add("input_affine", L.his_unet_input_affine, self.images.data_ptr(), self.B * 3 * H * W, mean, std, flag.data_ptr(), affine.data_ptr())
 
         # geometry of the five feature levels and the decoder concat buffers
         sizes = [(H, W)]
@@ -347,7 +469,7 @@ class _BuiltPlan:
         stem_c = oc[1]
         x = skip_slot[1]
         scale, shift = fold_bn(None, enc.bn1, stem_c)
-        p.conv_direct(self.images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
+        p.conv_direct(self.u_images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
                       p.const(shift), stem_c, 3, 2, 1, ACT["silu"], 1.0, in_affine=affine, out=x)
         level_of_stage = {1: 2, 2: 3, 4: 4}
         for si, stage in enumerate(enc.blocks):
@@ -365,15 +487,14 @@ class _BuiltPlan:
             x = self.conv(y, blk.conv2[0], blk.conv2[1], ACT["relu"])
         # segmentation head conv3x3 16->1 (+bias) -> fp32 logits; output_conv 1->2; export-wrapper binary mask
         head = net.segmentation_head[0]
-        self.one = p.f32(B, 1, H, W)
+        self.u_one = p.f32(B, 1, H, W)
         p.conv_direct(x, 0, B, H, W, x.C, x.cs, p.const(pack_direct_weight(head.weight), torch.float16), p.const(torch.ones(1)),
-                      p.const(head.bias.detach().float()), 1, 3, 1, 1, ACT["none"], out_f32=self.one)
+                      p.const(head.bias.detach().float()), 1, 3, 1, 1, ACT["none"], out_f32=self.u_one)
         oc_w = m.pretrained_unet.output_conv.weight.detach().float().flatten().tolist()
         oc_b = m.pretrained_unet.output_conv.bias.detach().float().flatten().tolist()
-        self.two = p.f32(B, 2, H, W)
-        self.binary = p.f32(B, 1, H, W)
-        p.add("unet_outputs", L.his_unet_outputs, self.one.data_ptr(), B, H, W, oc_w[0], oc_w[1], oc_b[0], oc_b[1], self.two.data_ptr(),
-              self.binary.data_ptr())
+        self._oc = (oc_w[0], oc_w[1], oc_b[0], oc_b[1])
+        if not self.chunked_unet:          # chunked: run() writes each chunk's slice of the full-batch outputs
+            p.add("unet_outputs", L.his_unet_outputs, self.u_one.data_ptr(), B, H, W, *self._oc, self.two.data_ptr(), self.binary.data_ptr())
 
     def _mbconv(self, x: Act, blk, dst: Optional[Act]) -> Act:
         """timm DepthwiseSeparableConv / InvertedResidual (oracle/effunet.py _DS/_IR restates them)."""
@@ -409,16 +530,10 @@ class _BuiltPlan:
     # -------------------------------------------------------------- per-ROI head
     def _build_head(self):
         m, p, L = self.m, self.plan, self.plan.lib
-        N, B, H, W = self.N, self.B, self.H, self.W
+        N, B, H, W = self.Nc, self.B, self.H, self.W
         rh, rw = m.roi_size
         mh, mw = m.mask_size
         aux_level = m.aux_outputs
-        self.logits = p.f32(N, 3, mh, mw)
-        self.aux = {}
-        if aux_level != "none":
-            self.aux["full_image_logits"] = self.two
-        if N == 0:
-            return
         A_rgb, A_ref = self.act_rgb, self.act_ref
 
         # --- Dynamic RoI Align (rgb.py:751-755): UNet logits -> channels 256..257 of the combiner input, RGB -> patches
@@ -428,9 +543,9 @@ class _BuiltPlan:
         roi_patch = p.f32(N, 3, rh, rw) if aux_level != "none" else None
         ram, rar = m.roi_align_mask, m.roi_align_rgb
         msk = comb_in.slice(256, 2)
-        p.add("roi_align_mask", L.his_roi_align, self.two.data_ptr(), 0, 2 * H * W, H * W, W, 1, B, 2, H, W, self.rois.data_ptr(), N, rh, rw,
+        p.add("roi_align_mask", L.his_roi_align, self.two.data_ptr(), 0, 2 * H * W, H * W, W, 1, B, 2, H, W, self.h_rois.data_ptr(), N, rh, rw,
               float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0, msk.ptr, msk.cs, roi_feat.data_ptr())
-        p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.rois.data_ptr(), N, rh, rw,
+        p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
               float(rar.spatial_scale_h), float(rar.spatial_scale_w), 1 if rar.aligned else 0, patches.ptr, patches.cs,
               roi_patch.data_ptr() if roi_patch is not None else None)
 
@@ -470,7 +585,7 @@ class _BuiltPlan:
         g2 = self.conv(g1, fg[3], None, A_ref)
         if aux_level == "full":
             gate = self.conv(g2, fg[5], None, ACT["sigmoid"])
-            self.aux["fg_attention"] = self.export_nchw(gate)
+            self.h_aux["fg_attention"] = self.export_nchw(gate)
         gated = self.conv(g2, fg[5], None, ACT["sigmoid"], res=shared, res_mode=RES_MUL)
         # --- target vs non-target branch
         tb = bh.target_vs_nontarget_branch
@@ -501,12 +616,12 @@ class _BuiltPlan:
             x = self.residual_block(x, last_rb, A_ref)
             self.conv(x, tail, None, ACT["none"], out_f32=tn_nat)
         tn = self.to_mask_size(tn_nat)
-        p.add("head_combine", L.his_head_combine, bgfg.data_ptr(), tn.data_ptr(), N, mh, mw, self.logits.data_ptr())
+        p.add("head_combine", L.his_head_combine, bgfg.data_ptr(), tn.data_ptr(), N, mh, mw, self.h_logits.data_ptr())
 
         if aux_level != "none":
-            self.aux.update({"bg_fg_logits": bgfg, "bg_fg_logits_low": low, "target_nontarget_logits": tn})
+            self.h_aux.update({"bg_fg_logits": bgfg, "bg_fg_logits_low": low, "target_nontarget_logits": tn})
             if aux_level == "full":
-                self.aux["shared_features"] = self.export_nchw(shared)
+                self.h_aux["shared_features"] = self.export_nchw(shared)
         # --- auxiliary branches (..._refinement.py:772-802); computed like the reference forward does
         head = m.segmentation_head
         if m.use_contour_detection:
@@ -520,7 +635,7 @@ class _BuiltPlan:
                 self.conv(c, cb[6], None, ACT["sigmoid"], out_f32=c_low)
             contours = self.to_mask_size(c_low)
             if aux_level != "none":
-                self.aux["contours"] = contours
+                self.h_aux["contours"] = contours
         if m.use_distance_transform:
             dd = head.distance_decoder
             dh = dd.distance_head
@@ -536,10 +651,10 @@ class _BuiltPlan:
             p.add("distance_mask", L.his_map_f32, d_low.data_ptr(), d_low.numel(), 1, thr.data_ptr(), m_low.data_ptr())
             dmask, dmap = self.to_mask_size(m_low), self.to_mask_size(d_low)
             if aux_level != "none":
-                self.aux["distance_mask"], self.aux["distance_map"] = dmask, dmap
+                self.h_aux["distance_mask"], self.h_aux["distance_map"] = dmask, dmap
         if aux_level != "none":
-            self.aux["roi_features"] = roi_feat
-            self.aux["roi_patches"] = roi_patch
+            self.h_aux["roi_features"] = roi_feat
+            self.h_aux["roi_patches"] = roi_patch
 
     def _ln_unsupported(self):
         raise NotImplementedError("normalization_type='layernorm2d' is not implemented on the B200 path yet")

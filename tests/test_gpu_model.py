@@ -128,6 +128,24 @@ def test_model_matches_oracle_fresh_inputs_edge_cases():
     assert got0.shape == (0, 3, 32, 24) and aux0["full_image_logits"].shape == (3, 2, 64, 96)
 
 
+def test_chunked_schedule_matches_single_pass():
+    """Image / ROI chunking (bounded HBM footprint) must not change results beyond rounding noise, and ROI order is kept."""
+    cfg, images, rois = common.small_case_inputs("small_b0_bn_relu")
+    m = build(cfg, common.shapes_for_case("small_b0_bn_relu"))
+    a, aux_a = m(images.cuda(), rois.cuda())
+    m.max_rois_per_pass, m.max_images_per_pass = 3, 1
+    b, aux_b = m(images.cuda(), rois.cuda())
+    bp = m._get_plan(images.cuda(), rois.cuda())
+    assert bp.n_head_chunks == 4 and bp.n_unet_chunks == 2
+    assert l2_rel(b.cpu(), a.cpu()) < 2e-3
+    assert common.argmax_agreement(b.cpu(), a.cpu()) > 0.998
+    for k in aux_a:
+        assert aux_b[k].shape == aux_a[k].shape, k
+    assert l2_rel(aux_b["bg_fg_logits_low"].cpu(), aux_a["bg_fg_logits_low"].cpu()) < 2e-3
+    g = common.golden("small_b0_bn_relu")
+    check(b, g["logits"], "logits(chunked)")
+
+
 def test_cuda_graph_replay_is_bit_identical():
     cfg, images, rois = common.small_case_inputs("small_b0_bn_relu")
     m = build(cfg, common.shapes_for_case("small_b0_bn_relu"))
