@@ -444,6 +444,89 @@ __global__ void scale_channels_kernel(const __half* __restrict__ in, int in_cs, 
   }
 }
 
+// ------------------------------------------------------------------------------------ LayerNorm2d (hed/model.py:18-38)
+// Statistics over (C,H,W) per sample (biased variance, eps 1e-5), affine [C].  Two launches: fixed-order partial sums
+// (fp32 per thread, double per block -> bit-reproducible), then normalise + affine (+residual) + activation.
+__global__ void ln_stats_kernel(const __half* __restrict__ in, long long per_img_vec, int HW, int C, int cs, double* __restrict__ partials) {
+  __shared__ double s_sum[kThreads], s_sq[kThreads];
+  const int n = blockIdx.y, cgs = C / 8;
+  float a = 0.0f, b = 0.0f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
+    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); a += f.x + f.y; b = fmaf(f.x, f.x, fmaf(f.y, f.y, b)); }
+  }
+  s_sum[threadIdx.x] = (double)a; s_sq[threadIdx.x] = (double)b;
+  __syncthreads();
+  for (int o = kThreads / 2; o; o >>= 1) {
+    if ((int)threadIdx.x < o) { s_sum[threadIdx.x] += s_sum[threadIdx.x + o]; s_sq[threadIdx.x] += s_sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[((long long)n * gridDim.x + blockIdx.x) * 2] = s_sum[0];
+    partials[((long long)n * gridDim.x + blockIdx.x) * 2 + 1] = s_sq[0];
+  }
+}
+
+__global__ void ln_apply_kernel(const __half* __restrict__ in, int HW, int C, int cs, const double* __restrict__ partials, int nparts,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, float act_beta,
+                                int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs) {
+  __shared__ float s_mu, s_rstd;
+  const int n = blockIdx.y, cgs = C / 8;
+  if (threadIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nparts; ++i) { s += partials[((long long)n * nparts + i) * 2]; q += partials[((long long)n * nparts + i) * 2 + 1]; }
+    const double cnt = (double)HW * (double)C;
+    const double mu = s / cnt;
+    double var = q / cnt - mu * mu;
+    if (var < 0.0) var = 0.0;
+    s_mu = (float)mu; s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float mu = s_mu, rstd = s_rstd;
+  const long long per_img_vec = (long long)HW * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = (long long)n * HW + idx / cgs;
+    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * cs + cg * 8));
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (res_mode) rv = __ldg(reinterpret_cast<const uint4*>(res + pix * res_cs + cg * 8));
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(xh[e]), r = __half22float2(rh[e]);
+      const int c = cg * 8 + 2 * e;
+      float y0 = (f.x - mu) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      float y1 = (f.y - mu) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+      if (res_mode == HIS_RES_ADD) { y0 += r.x; y1 += r.y; }
+      y0 = his_act(y0, act, act_beta); y1 = his_act(y1, act, act_beta);
+      if (res_mode == HIS_RES_MUL) { y0 *= r.x; y1 *= r.y; }
+      xh[e] = __floats2half2_rn(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+  }
+}
+
+// ConvTranspose2d(k2,s2) for tiny Cin (upsample_bg_fg.0 in LayerNorm mode: 2 -> 32): NCHW fp32 in, NHWC fp16 out (+bias)
+__global__ void convT2x2_small_kernel(const float* __restrict__ in, int N, int Cin, int h, int w, const float* __restrict__ wt,
+                                      const float* __restrict__ bias, int Cout, __half* __restrict__ out, int out_cs) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)N * Ho * Wo * Cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cout);
+    const long long pix = idx / Cout;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float v = bias ? bias[c] : 0.0f;
+    for (int ci = 0; ci < Cin; ++ci)
+      v = fmaf(in[((long long)(n * Cin + ci) * h + (oy >> 1)) * w + (ox >> 1)], wt[((ci * Cout + c) * 2 + (oy & 1)) * 2 + (ox & 1)], v);
+    out[pix * out_cs + c] = __float2half_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------ pooling / resize
 __global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, __half* __restrict__ out, int out_cs) {
   const int Ho = H / 2, Wo = W / 2, cgs = C / 8;
@@ -807,6 +890,43 @@ int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int 
   const long long total = (long long)N * HW * (C / 8);
   if (total == 0) return HIS_OK;
   scale_channels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, gate, HW, C, total, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_layernorm2d_parts(int N, int HW, int C) {
+  long long gx = ((long long)HW * (C / 8) + kThreads * 4 - 1) / (kThreads * 4);
+  const long long cap = (148LL * 8 + N - 1) / (N > 0 ? N : 1);
+  if (gx > cap) gx = cap;
+  return (int)(gx < 1 ? 1 : gx);
+}
+
+int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps, int act,
+                        float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws, void* out, int out_cs, void* stream) {
+  if (!in || !gamma || !beta || !partials_ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "layernorm2d: null pointer");
+  if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "layernorm2d: res_mode without residual");
+  if (C % 8 || in_cs % 8 || out_cs % 8 || (res_mode && res_cs % 8)) return his_set_error(HIS_ERR_UNSUPPORTED, "layernorm2d: channels must be multiples of 8");
+  if (N == 0) return HIS_OK;
+  const int parts = his_layernorm2d_parts(N, HW, C);
+  const long long per_img_vec = (long long)HW * (C / 8);
+  dim3 g1(parts, N);
+  ln_stats_kernel<<<g1, kThreads, 0, ST>>>((const __half*)in, per_img_vec, HW, C, in_cs, partials_ws);
+  long long gx = (per_img_vec + kThreads - 1) / kThreads;
+  const long long cap = (148LL * 16 + N - 1) / N;
+  if (gx > cap) gx = cap;
+  dim3 g2((int)(gx < 1 ? 1 : gx), N);
+  ln_apply_kernel<<<g2, kThreads, 0, ST>>>((const __half*)in, HW, C, in_cs, partials_ws, parts, gamma, beta, eps, act, act_beta, res_mode,
+                                          (const __half*)res, res_cs, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const float* wt, const float* bias, int cout, void* out, int out_cs,
+                       void* stream) {
+  if (!in || !wt || !out) return his_set_error(HIS_ERR_INVALID_ARG, "convT2x2_small: null pointer");
+  const long long total = (long long)N * 4 * h * w * cout;
+  if (total == 0) return HIS_OK;
+  convT2x2_small_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, N, cin, h, w, wt, bias, cout, (__half*)out, out_cs);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -88,6 +88,9 @@ SIGNATURES = {
     "his_depthwise_pool_parts": [c_int, c_int, c_int, c_int, c_int, c_int],
     "his_pool_sum_parts": [c_int, c_int, c_int],
     "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
+    "his_layernorm2d_parts": [c_int, c_int, c_int],
+    "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],
+    "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P],
     "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P],
     "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_resize_nearest": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],

@@ -372,8 +372,11 @@ class _BuiltPlan:
         epilogue; the wide activation itself is then not written (its only consumer is the tail)."""
         p = self.plan
         if norm is not None and not self._is_bn(norm):
-            raise NotImplementedError("normalization_type='layernorm2d' is not implemented on the B200 path yet "
-                                      "(all production presets use 'batchnorm')")
+            # LayerNorm2d (hed/model.py:18-38): per-sample statistics over (C,H,W) cannot fold into the conv ->
+            # conv(+bias) to fp16, then the two-launch LayerNorm kernel applies norm + residual + activation.
+            assert tail is None and out_f32 is None
+            raw = self.conv(x, conv, None, ACT["none"])
+            return self.layernorm(raw, norm, act, res, res_mode, out)
         transposed = isinstance(conv, nn.ConvTranspose2d)
         w = conv.weight
         cout = w.shape[1] if transposed else w.shape[0]
@@ -408,13 +411,26 @@ class _BuiltPlan:
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
 
+    def layernorm(self, x: Act, norm: pt.LayerNorm2dParams, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
+                  out: Optional[Act] = None) -> Act:
+        p, L = self.plan, self.plan.lib
+        if out is None:
+            out = p.act(x.N, x.H, x.W, x.C)
+        parts = L.his_layernorm2d_parts(x.N, x.H * x.W, x.C)
+        ws = torch.empty((x.N, parts, 2), dtype=torch.float64, device=self.dev)
+        p.keep.append(ws)
+        p.add("layernorm2d", L.his_layernorm2d_act, x.ptr, x.N, x.H * x.W, x.C, x.cs, p.const(norm.weight.reshape(-1)).data_ptr(),
+              p.const(norm.bias.reshape(-1)).data_ptr(), float(norm.eps), act, self.beta, res_mode, res.ptr if res is not None else None,
+              res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs)
+        return out
+
     def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None) -> Act:
         t = self.conv(x, rb.conv1, rb.norm1, act)
         return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail)
 
     def _tail_ok(self, act: int) -> bool:
-        """The fused tail exists for none/relu epilogues (every preset); other activations use the separate 1x1 kernel."""
-        return act in (ACT["none"], ACT["relu"])
+        """The fused tail exists for BatchNorm + none/relu epilogues (every preset); otherwise the separate 1x1 kernel runs."""
+        return act in (ACT["none"], ACT["relu"]) and self.m.normalization_type.lower() in ("batch", "batchnorm", "batchnorm2d")
 
     def to_mask_size(self, t: torch.Tensor) -> torch.Tensor:
         """F.interpolate(size=mask, bilinear, align_corners=False) when sizes differ (..._refinement.py:561-566)."""
@@ -570,11 +586,18 @@ class _BuiltPlan:
         self._enhanced_unet(shared, bh.bg_vs_fg_unet, low)
         # --- upsample_bg_fg (fused) + resize + softmax happens inside the combine
         up = bh.upsample_bg_fg
-        s32, t32 = fold_bn(up[0].bias, up[1] if self._is_bn(up[1]) else self._ln_unsupported(), 32)
         bgfg_nat = p.f32(N, 2, 2 * rh, 2 * rw)
-        p.add("upsample_bgfg", L.his_upsample_bgfg, low.data_ptr(), N, rh, rw, p.const(up[0].weight).data_ptr(), p.const(s32).data_ptr(),
-              p.const(t32).data_ptr(), p.const(up[3].weight.reshape(2, 32)).data_ptr(), p.const(up[3].bias).data_ptr(), A_ref, self.beta,
-              bgfg_nat.data_ptr())
+        if self._is_bn(up[1]):
+            s32, t32 = fold_bn(up[0].bias, up[1], 32)
+            p.add("upsample_bgfg", L.his_upsample_bgfg, low.data_ptr(), N, rh, rw, p.const(up[0].weight).data_ptr(), p.const(s32).data_ptr(),
+                  p.const(t32).data_ptr(), p.const(up[3].weight.reshape(2, 32)).data_ptr(), p.const(up[3].bias).data_ptr(), A_ref, self.beta,
+                  bgfg_nat.data_ptr())
+        else:   # LayerNorm2d over (32, 2rh, 2rw) needs the whole sample: ConvT -> LN+act -> 1x1
+            u = p.act(N, 2 * rh, 2 * rw, 32)
+            p.add("convT2x2_small", L.his_convT2x2_small, low.data_ptr(), N, 2, rh, rw, p.const(up[0].weight).data_ptr(),
+                  p.const(up[0].bias).data_ptr(), 32, u.ptr, u.cs)
+            u = self.layernorm(u, up[1], A_ref)
+            self.conv(u, up[3], None, ACT["none"], out_f32=bgfg_nat)
         bgfg = self.to_mask_size(bgfg_nat)
         # --- fg_gate (..._refinement.py:537-545,569-570): 1x1 2->64 (from the fp32 logits), 64->128, 128->256, sigmoid, * shared
         fg = bh.fg_gate
@@ -655,9 +678,6 @@ class _BuiltPlan:
         if aux_level != "none":
             self.h_aux["roi_features"] = roi_feat
             self.h_aux["roi_patches"] = roi_patch
-
-    def _ln_unsupported(self):
-        raise NotImplementedError("normalization_type='layernorm2d' is not implemented on the B200 path yet")
 
     def _enhanced_unet(self, x: Act, u: pt.EnhancedUNetParams, low_out: torch.Tensor):
         """EnhancedUNet.forward (..._unet.py:375-417).  Skip concats are buffer layouts: decoder level i reads

@@ -99,6 +99,17 @@ int his_se_gate(const float* pool_sums, int nparts, int N, int HW, int C, int R,
                 const float* w2, const float* b2, int act, float act_beta, float* gate, void* stream);
 int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream);
 
+/* ---- LayerNorm2d, hed/model.py:18-38 (statistics over C,H,W per sample, biased variance) + optional residual +
+ * activation, on an NHWC half slice.  partials_ws: device double [N][his_layernorm2d_parts(...)][2].
+ * his_convT2x2_small: ConvTranspose2d(k2,s2) for tiny Cin (upsample_bg_fg.0 when it is followed by LayerNorm2d):
+ * NCHW fp32 in, PyTorch weight layout [Cin][Cout][2][2] fp32, NHWC half out. */
+int his_layernorm2d_parts(int N, int HW, int C);
+int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps,
+                        int act, float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws,
+                        void* out, int out_cs, void* stream);
+int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const float* wt, const float* bias, int cout,
+                       void* out, int out_cs, void* stream);
+
 /* ---- SpatialAttentionModule, hed/advanced/attention_modules.py:67-113: out = x*sigmoid(conv_kxk([mean_c,max_c])).
  * w: fp32 [2][k][k]; stats_ws: fp32 workspace [N*H*W*2]. */
 int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs, const float* w, int k, float* stats_ws,

@@ -45,7 +45,7 @@ def check(got, want, name, l2=L2_TOL, mx=MAX_TOL):
     return e2, em
 
 
-SMALL = [n for n in common.SMALL_CASES if "ln_" not in n]
+SMALL = list(common.SMALL_CASES)
 
 
 @pytest.mark.parametrize("name", SMALL)
