@@ -28,6 +28,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -38,18 +39,18 @@ constexpr int kBlockM = 128;
 constexpr int kStagingBytes = kBlockM * 64 * 2;   // 16 KB : 128 rows x 64 channels fp16
 constexpr int kNumStaging = 2;
 constexpr int kTmemCols = 512;
-constexpr int kMaxStages = 12;
+constexpr int kMaxStages = 48;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kBarrierBytes = 512;
+constexpr int kBarrierBytes = 1024;
 
 // K-block width BK (fp16 elements) selects the shared-memory swizzle: one row of the operand tile is BK*2 bytes.
 template <int BK> struct KCfg {
   static constexpr int kABytes = kBlockM * BK * 2;
   static constexpr int kBBytesMax = 256 * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytesMax;     // 48 / 24 / 12 KB
-  static constexpr int kStagesFit = (kSmemBudget - kNumStaging * kStagingBytes - 1024 - kBarrierBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + 1024 + kBarrierBytes;
+  // the ring gets whatever the 227 KB leave after the staging buffers, barriers and the 1 KB alignment slack; its depth is a
+  // run-time parameter (stage = A + the layer's actual B tile), so narrow layers keep many more loads in flight
+  static constexpr int kRingBytes = kSmemBudget - kNumStaging * kStagingBytes - 1024 - kBarrierBytes;
+  static constexpr int kSmemBytes = kSmemBudget;
   static constexpr uint32_t kSbo = 8 * BK * 2;                 // bytes between 8-row groups
   static constexpr uint64_t kLayout = BK == 64 ? 2 : BK == 32 ? 4 : 6;   // SWIZZLE_128B / 64B / 32B
 };
@@ -65,6 +66,8 @@ struct ConvGemmParams {
   int groups;           // 1, or 4 for conv-transpose k2s2
   int cout_slab;        // n_tiles * block_n  (rows of one slab in B, scale/shift length per group)
   int num_work;
+  int b_img_rows;       // rows to skip in B per image (0: shared weights; >0: per-image weights, e.g. SE gate folded in)
+  int stages, stage_bytes;   // smem ring: stage = A tile (128 x BK) + B tile (block_n x BK), rounded up to 1 KB
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
   //   SIGMOID: s = 1/(1+exp(-act_beta*y)); y = act_mul_x ? y*s : s   (sigmoid / silu / swish(beta))
@@ -78,6 +81,9 @@ struct ConvGemmParams {
   float* tail_out;      // [n_img][tail_c][H][W]
   float tail_b0, tail_b1;
   int tail_c, tail_sigmoid, store_main;
+  // fp32 NCHW copy of the layer output (EPI_AUX kernels): aux[n][c][y][x] = y, or the gate itself (before the product) for RES_MUL
+  float* aux_out;
+  int cout;             // true output channel count
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -100,6 +106,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@P1 bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// one lane of the (converged) warp; keeps the surrounding code warp-uniform so that the uniform-datapath instructions
+// (UTMALDG / UTCHMMA / UTCBAR) are issued directly instead of through a per-lane election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -205,18 +218,20 @@ __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) 
 }
 
 // ------------------------------------------------------------------------------------ kernel
-template <int BK, int ACTC, int RES, bool TAIL>
+enum { EPI_PLAIN = 0, EPI_TAIL = 1, EPI_AUX = 2 };
+
+template <int BK, int ACTC, int RES, int EPI>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
                        const __grid_constant__ CUtensorMap tmR, const ConvGemmParams p) {
   using Cfg = KCfg<BK>;
-  constexpr int kStages = Cfg::kStages;
+  const int kStages = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base;
-  const uint32_t staging_base = smem_base + kStages * Cfg::kStageBytes;
+  const uint32_t staging_base = smem_base + kStages * p.stage_bytes;
   const uint32_t bar_base = staging_base + kNumStaging * kStagingBytes;
   // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[2]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -250,28 +265,29 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
+  if (warp == 0) {
+    // ================================ TMA producer (whole warp converged, one elected lane issues) ================================
     int stage = 0; uint32_t phase = 0;
     const int pad = p.ksize >> 1;
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
-      const int brow0 = it.group * taps * p.cout_slab + it.n_tile * p.block_n;
-      int tap = 0, cb = 0;
+      int brow = it.group * taps * p.cout_slab + it.n_tile * p.block_n + it.img * p.b_img_rows;
+      int dy = -pad, dx = -pad, cb = 0;
       for (int k = 0; k < kiters; ++k) {
-        const int ty = tap / p.ksize;
-        const int dy = ty - pad, dx = tap - ty * p.ksize - pad;
         mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = stage_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
-        mbar_expect_tx(full_bar(stage), Cfg::kABytes + b_bytes);
-        tma_load_4d(sa, &tmA, full_bar(stage), cb * BK, it.x0 + dx, it.y0 + dy, it.img);
-        tma_load_2d(sb, &tmB, full_bar(stage), cb * BK, brow0 + tap * p.cout_slab);
+        if (elect_one()) {
+          const uint32_t sa = stage_base + stage * p.stage_bytes, sb = sa + Cfg::kABytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kABytes + b_bytes);
+          tma_load_4d(sa, &tmA, full_bar(stage), cb * BK, it.x0 + dx, it.y0 + dy, it.img);
+          tma_load_2d(sb, &tmB, full_bar(stage), cb * BK, brow);
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
-        if (++cb == p.kblocks_per_tap) { cb = 0; ++tap; }
+        if (++cb == p.kblocks_per_tap) { cb = 0; brow += p.cout_slab; if (++dx > pad) { dx = -pad; ++dy; } }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1) {
+    // ================================ MMA issuer (whole warp converged, one elected lane issues) ================================
     const uint32_t idesc = make_idesc_f16(p.block_n);
     int stage = 0; uint32_t phase = 0; int iter = 0;
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
@@ -282,13 +298,16 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int k = 0; k < kiters; ++k) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = stage_base + stage * Cfg::kStageBytes, sb = sa + Cfg::kABytes;
-        const uint64_t adesc = make_kmajor_desc<BK>(sa), bdesc = make_kmajor_desc<BK>(sb);
+        if (elect_one()) {
+          const uint32_t sa = stage_base + stage * p.stage_bytes, sb = sa + Cfg::kABytes;
+          const uint64_t adesc = make_kmajor_desc<BK>(sa), bdesc = make_kmajor_desc<BK>(sb);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk)
-          umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-        umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
-        if (k == kiters - 1) umma_commit(tfull_bar(acc));
+          for (int kk = 0; kk < BK / 16; ++kk)
+            umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+          umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+          if (k == kiters - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -303,7 +322,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int acc = iter & 1; const uint32_t acc_phase = (iter >> 1) & 1;
       const CUtensorMap* tmO = it.group == 0 ? &tmO0 : it.group == 1 ? &tmO1 : it.group == 2 ? &tmO2 : &tmO3;
       const int chbase = it.n_tile * p.block_n;
-      if (RES && te == 0) {                     // prefetch the first two residual chunks while the MMAs run
+      if (RES && warp == 4 && elect_one()) {    // prefetch the first two residual chunks while the MMAs run
         tma_wait_read<0>();
         for (int j = 0; j < 2 && j < nchunks; ++j) {
           const int b = (cc + j) & 1;
@@ -314,13 +333,17 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       float tacc0 = 0.0f, tacc1 = 0.0f;
+      constexpr bool TAIL = EPI == EPI_TAIL;
       const bool store_main = !TAIL || p.store_main;
+      const int py = it.y0 + te / p.bw, px = it.x0 + te % p.bw;
+      float* aux_px = nullptr;
+      if (EPI == EPI_AUX && py < p.H && px < p.W) aux_px = p.aux_out + ((long long)it.img * p.cout * p.H + py) * p.W + px;
       for (int j = 0; j < nchunks; ++j, ++cc) {
         const int b = cc & 1;
         const uint32_t stg = staging_base + b * kStagingBytes;
         const int ch0 = chbase + j * 64;        // first output channel of this chunk
         const int ncol = min(64, p.block_n - j * 64);   // valid accumulator columns in this chunk (multiple of 16)
-        if (te == 0 && (!RES || j >= 2)) {
+        if ((!RES || j >= 2) && warp == 4 && elect_one()) {
           tma_wait_read<1>();                    // the store that last read staging[b] has drained
           if (RES) {
             mbar_expect_tx(res_bar(b), kStagingBytes);
@@ -363,6 +386,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               float t = fmaf(__uint_as_float(v[i * 8 + e]), sc[e], sh[e]);
               if (RES == HIS_RES_ADD) t += r[e];
               t = epi_act<ACTC>(t, p);
+              if (EPI == EPI_AUX) { if (aux_px && c + e < p.cout) aux_px[(long long)(c + e) * p.H * p.W] = t; }
               if (RES == HIS_RES_MUL) t *= r[e];
               y[e] = t;
             }
@@ -386,14 +410,13 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (store_main) {
           fence_proxy_async();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (te == 0) {
+          if (warp == 4 && elect_one()) {
             tma_store_4d(tmO, stg, ch0, it.x0, it.y0, it.img);
             tma_commit();
           }
         }
       }
       if (TAIL) {
-        const int py = it.y0 + te / p.bw, px = it.x0 + te % p.bw;
         if (py < p.H && px < p.W) {
           float o0 = tacc0 + p.tail_b0, o1 = tacc1 + p.tail_b1;
           if (p.tail_sigmoid) { o0 = 1.0f / (1.0f + __expf(-o0)); o1 = 1.0f / (1.0f + __expf(-o1)); }
@@ -403,7 +426,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       }
     }
-    if (te == 0) tma_wait_all();
+    if (warp == 4 && elect_one()) tma_wait_all();
   }
 
   tc_fence_before();
@@ -419,8 +442,8 @@ typedef void (*ConvGemmKernel)(const CUtensorMap, const CUtensorMap, const CUten
 
 template <int BK, int ACTC>
 ConvGemmKernel pick_res(int res) {
-  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0, false> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1, false>
-                                                                            : conv_gemm_sm100_kernel<BK, ACTC, 2, false>;
+  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0, EPI_PLAIN> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1, EPI_PLAIN>
+                                                                            : conv_gemm_sm100_kernel<BK, ACTC, 2, EPI_PLAIN>;
 }
 template <int BK>
 ConvGemmKernel pick_act(int actc, int res) {
@@ -431,9 +454,18 @@ ConvGemmKernel pick_kernel(int bk, int actc, int res) {
 }
 // fused-tail variants exist for the shapes that need them: clamp activations (none/relu), no residual or residual-add
 ConvGemmKernel pick_tail_kernel(int bk, int res) {
-  if (bk == 64) return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, true> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, true>;
-  if (bk == 32) return res == 0 ? conv_gemm_sm100_kernel<32, ACTC_CLAMP, 0, true> : conv_gemm_sm100_kernel<32, ACTC_CLAMP, 1, true>;
-  return res == 0 ? conv_gemm_sm100_kernel<16, ACTC_CLAMP, 0, true> : conv_gemm_sm100_kernel<16, ACTC_CLAMP, 1, true>;
+  if (bk == 64) return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, EPI_TAIL> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, EPI_TAIL>;
+  if (bk == 32) return res == 0 ? conv_gemm_sm100_kernel<32, ACTC_CLAMP, 0, EPI_TAIL> : conv_gemm_sm100_kernel<32, ACTC_CLAMP, 1, EPI_TAIL>;
+  return res == 0 ? conv_gemm_sm100_kernel<16, ACTC_CLAMP, 0, EPI_TAIL> : conv_gemm_sm100_kernel<16, ACTC_CLAMP, 1, EPI_TAIL>;
+}
+// fp32 NCHW export variants: BK = 64 layers only (the 256-channel trunk / gate layers whose outputs the reference returns)
+template <int ACTC>
+ConvGemmKernel pick_aux_res(int res) {
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_AUX> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_AUX>
+                                                                           : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_AUX>;
+}
+ConvGemmKernel pick_aux_kernel(int actc, int res) {
+  return actc == 0 ? pick_aux_res<0>(res) : actc == 1 ? pick_aux_res<1>(res) : pick_aux_res<2>(res);
 }
 int smem_for(int bk) { return bk == 64 ? KCfg<64>::kSmemBytes : bk == 32 ? KCfg<32>::kSmemBytes : KCfg<16>::kSmemBytes; }
 
@@ -500,7 +532,7 @@ int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, i
 struct ConvGemmPlan {
   CUtensorMap tmA, tmB, tmO[4], tmR;
   ConvGemmParams p;
-  int grid, bk, smem, actc, res_mode, transposed;
+  int grid, bk, smem, actc, res_mode, transposed, cin_pad;
   ConvGemmKernel kernel;
 };
 
@@ -556,6 +588,10 @@ int his_conv_gemm_create(void** out_plan,
       for (int r = 0; r < 2; ++r)
         if (cudaFuncSetAttribute(pick_tail_kernel(bk, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
           return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
+    for (int a = 0; a < 3; ++a)
+      for (int r = 0; r < 3; ++r)
+        if (cudaFuncSetAttribute(pick_aux_kernel(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess)
+          return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     g_num_sms = prop.multiProcessorCount;
   }
   ConvGemmPlan* pl = new ConvGemmPlan();
@@ -591,8 +627,12 @@ int his_conv_gemm_create(void** out_plan,
   if (res_mode < 0 || res_mode > 2) { delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown res_mode"); }
   pl->kernel = pick_kernel(bk, actc, res_mode);
   pl->smem = smem_for(bk);
-  pl->actc = actc; pl->res_mode = res_mode; pl->transposed = transposed;
-  p.tail_c = 0; p.store_main = 1;
+  p.stage_bytes = (kBlockM * bk * 2 + p.block_n * bk * 2 + 1023) / 1024 * 1024;
+  p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
+  pl->actc = actc; pl->res_mode = res_mode; pl->transposed = transposed; pl->cin_pad = cin_pad;
+  p.tail_c = 0; p.store_main = 1; p.aux_out = nullptr; p.cout = cout;
   p.scale = scale; p.shift = shift;
   int taps = ksize * ksize;
   int rc;
@@ -628,6 +668,28 @@ int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float
   pl->p.tail_w = tail_w; pl->p.tail_b0 = tail_b0; pl->p.tail_b1 = tail_b1; pl->p.tail_c = tail_c; pl->p.tail_sigmoid = tail_sigmoid;
   pl->p.tail_out = tail_out; pl->p.store_main = store_main;
   pl->kernel = pick_tail_kernel(pl->bk, pl->res_mode);
+  return HIS_OK;
+}
+
+int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image) {
+  if (!plan || !w_packed_per_image) return his_set_error(HIS_ERR_INVALID_ARG, "set_image_weights: null pointer");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  ConvGemmParams& p = pl->p;
+  const long long rows = (long long)p.groups * p.ksize * p.ksize * p.cout_slab;
+  if (rows * p.n_img >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "set_image_weights: too many weight rows");
+  int rc = encode_weight_map(&pl->tmB, w_packed_per_image, pl->cin_pad, rows * p.n_img, p.block_n, pl->bk);
+  if (rc) return rc;
+  p.b_img_rows = (int)rows;
+  return HIS_OK;
+}
+
+int his_conv_gemm_set_aux(void* plan, float* aux_out) {
+  if (!plan || !aux_out) return his_set_error(HIS_ERR_INVALID_ARG, "set_aux: null pointer");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  if (pl->bk != 64 || pl->transposed || pl->p.tail_c)
+    return his_set_error(HIS_ERR_UNSUPPORTED, "set_aux: needs a 64-wide K block (Cin >= 64), not transposed, no fused tail");
+  pl->p.aux_out = aux_out;
+  pl->kernel = pick_aux_kernel(pl->actc, pl->res_mode);
   return HIS_OK;
 }
 

@@ -28,7 +28,7 @@ inline int grid_for(long long work, int per_block = kThreads) {
 // stride gridDim.x*256 is a multiple of the number of groups, i.e. gridDim.x is a multiple of cgs/gcd(cgs,256).
 inline int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 inline int threads_multiple_of(int cgs) { return cgs > 0 ? kThreads : 0; }
-inline int grid_multiple(int cgs) { return cgs / gcd_int(cgs, kThreads); }
+inline int grid_multiple(int cgs, int threads = kThreads) { return cgs / gcd_int(cgs, threads); }
 
 // ------------------------------------------------------------------------------------ RoI Align
 // reference hed/dynamic_roi_align.py:56-171 (see oracle/headport.py:roi_align for the derivation).
@@ -297,72 +297,113 @@ __device__ __forceinline__ float act_ct(float v) {
   return v;
 }
 
-template <int K, int S, int ACT>
-__global__ void __launch_bounds__(256, 2) depthwise_kernel(const DwParams p) {
-  // one thread = one output pixel x one 8-channel group (16-byte vectors).  All K*K input vectors of the window are
-  // requested before the first FMA (fully unrolled, predicated loads) so that ~K*K 16-byte loads per thread are in
-  // flight; horizontal/vertical window overlap between neighbouring threads is served by L1/L2.
-  extern __shared__ float s_pool[];     // [blockDim.x][8] per-thread sums, reduced in a fixed order (deterministic)
-  const int cgs = p.C / 8;
+// One thread = one VEC-channel group x one output column x a vertical strip of RY output rows.  The K*K filter taps of
+// the thread's channel group live in registers (the group is fixed per thread), and every input row of the strip is
+// loaded once (K vectors) and applied to all output rows it overlaps, so a thread issues K*((RY-1)*S+K)/RY loads per
+// output instead of 2*K*K (taps + weights): the kernel leaves the L1-bandwidth bound of the one-output-per-thread form.
+// VEC = 8 (16-byte vectors) for 3x3, 4 (8-byte vectors) for 5x5 so that 25 taps fit the register file.
+constexpr int kDwThreads = 128;
+template <int VEC> struct DwVec;
+template <> struct DwVec<8> { typedef uint4 T; };
+template <> struct DwVec<4> { typedef uint2 T; };
+
+template <int K, int S, int ACT, int VEC, int RY>
+__global__ void __launch_bounds__(kDwThreads, 3) depthwise_kernel(const DwParams p) {
+  typedef typename DwVec<VEC>::T V;
+  constexpr int RIN = (RY - 1) * S + K;
+  extern __shared__ float s_pool[];     // [blockDim.x][VEC] per-thread sums, reduced in a fixed order (deterministic)
+  const int cgs = p.C / VEC;
   const int n = blockIdx.y;
-  const int per_img = p.Ho * p.Wo * cgs;
+  const int strips = (p.Ho + RY - 1) / RY;
+  const int per_img = strips * p.Wo * cgs;
   // fixed channel group per thread: the grid stride gridDim.x*blockDim.x is a multiple of cgs (host guarantees)
   const int cg = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % cgs);
-  const int c0 = cg * 8;
-  float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float sc[8], sh[8];
+  const int c0 = cg * VEC;
+  float psum[VEC], sc[VEC], sh[VEC];
+  __half2 wreg[K * K][VEC / 2];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+  for (int e = 0; e < VEC; ++e) { psum[e] = 0.0f; sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) {
+    const V wv = __ldg(reinterpret_cast<const V*>(p.w + (long long)t * p.C + c0));
+#pragma unroll
+    for (int e = 0; e < VEC / 2; ++e) wreg[t][e] = reinterpret_cast<const __half2*>(&wv)[e];
+  }
   const __half* inb = p.in + (long long)n * p.H * p.W * p.in_cs + c0;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per_img; idx += gridDim.x * blockDim.x) {
-    const int pix = idx / cgs;
-    const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
-    const int iy0 = oy * S - p.pad, ix0 = ox * S - p.pad;
-    // branch-free window fetch: clamped (always valid) addresses, out-of-image taps zeroed by select afterwards
-    uint4 xv[K * K];
+    const int t2 = idx / cgs;
+    const int strip = t2 / p.Wo, ox = t2 - strip * p.Wo;
+    const int oy0 = strip * RY;
+    const int iy0 = oy0 * S - p.pad, ix0 = ox * S - p.pad;
+    float acc[RY][VEC];
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) {
-      const int iy = min(max(iy0 + t / K, 0), p.H - 1), ix = min(max(ix0 + t % K, 0), p.W - 1);
-      xv[t] = __ldg(reinterpret_cast<const uint4*>(inb + ((long long)iy * p.W + ix) * p.in_cs));
-    }
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < RY; ++j)
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) {
-      const int iy = iy0 + t / K, ix = ix0 + t % K;
-      const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-      uint4 wv = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)t * p.C + c0));
-      if (!ok) wv = make_uint4(0u, 0u, 0u, 0u);
-      const __half2* xh = reinterpret_cast<const __half2*>(&xv[t]);
-      const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+      for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 xf = __half22float2(xh[e]), wf = __half22float2(wh[e]);
-        acc[2 * e] = fmaf(xf.x, wf.x, acc[2 * e]);
-        acc[2 * e + 1] = fmaf(xf.y, wf.y, acc[2 * e + 1]);
+    for (int r = 0; r < RIN; ++r) {
+      const int iy = iy0 + r;
+      const bool rowok = iy >= 0 && iy < p.H;
+      const int iyc = min(max(iy, 0), p.H - 1);
+      V xv[K];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {      // clamped (always valid) address; out-of-image taps are zeroed below
+        const int ixc = min(max(ix0 + kx, 0), p.W - 1);
+        xv[kx] = __ldg(reinterpret_cast<const V*>(inb + ((long long)iyc * p.W + ixc) * p.in_cs));
+      }
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ix0 + kx;
+        const bool ok = rowok && ix >= 0 && ix < p.W;
+        float xf[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC / 2; ++e) {
+          const float2 f = __half22float2(reinterpret_cast<const __half2*>(&xv[kx])[e]);
+          xf[2 * e] = ok ? f.x : 0.0f; xf[2 * e + 1] = ok ? f.y : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          const int ky = r - j * S;         // compile-time after unrolling
+          if (ky >= 0 && ky < K) {
+#pragma unroll
+            for (int e = 0; e < VEC / 2; ++e) {
+              const float2 wf = __half22float2(wreg[ky * K + kx][e]);
+              acc[j][2 * e] = fmaf(xf[2 * e], wf.x, acc[j][2 * e]);
+              acc[j][2 * e + 1] = fmaf(xf[2 * e + 1], wf.y, acc[j][2 * e + 1]);
+            }
+          }
+        }
       }
     }
-    __half2 o[4];
 #pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      const float y0 = act_ct<ACT>(acc[e] * sc[e] + sh[e]);
-      const float y1 = act_ct<ACT>(acc[e + 1] * sc[e + 1] + sh[e + 1]);
-      o[e >> 1] = __floats2half2_rn(y0, y1);
-      // pool what the next layer will actually read (the fp16-rounded value)
-      const float2 rf = __half22float2(o[e >> 1]);
-      psum[e] += rf.x; psum[e + 1] += rf.y;
+    for (int j = 0; j < RY; ++j) {
+      const int oy = oy0 + j;
+      if (oy < p.Ho) {
+        V ov;
+        __half2* o = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < VEC; e += 2) {
+          const float y0 = act_ct<ACT>(acc[j][e] * sc[e] + sh[e]);
+          const float y1 = act_ct<ACT>(acc[j][e + 1] * sc[e + 1] + sh[e + 1]);
+          o[e >> 1] = __floats2half2_rn(y0, y1);
+          // pool what the next layer will actually read (the fp16-rounded value)
+          const float2 rf = __half22float2(o[e >> 1]);
+          psum[e] += rf.x; psum[e + 1] += rf.y;
+        }
+        *reinterpret_cast<V*>(p.out + ((long long)(n * p.Ho + oy) * p.Wo + ox) * p.out_cs + c0) = ov;
+      }
     }
-    *reinterpret_cast<uint4*>(p.out + ((long long)n * p.Ho * p.Wo + pix) * p.out_cs + c0) = *reinterpret_cast<uint4*>(o);
   }
   if (p.pool) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = psum[e];
+    for (int e = 0; e < VEC; ++e) s_pool[threadIdx.x * VEC + e] = psum[e];
     __syncthreads();
     float* dst = p.pool + ((long long)n * gridDim.x + blockIdx.x) * p.C;
     const int first = (int)((blockIdx.x * (long long)blockDim.x) % cgs);   // channel group of thread 0
     for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-      const int g2 = c >> 3, e = c & 7;
+      const int g2 = c / VEC, e = c % VEC;
       float s = 0.0f;
-      for (int t = (g2 - first + cgs) % cgs; t < (int)blockDim.x; t += cgs) s += s_pool[t * 8 + e];
+      for (int t = (g2 - first + cgs) % cgs; t < (int)blockDim.x; t += cgs) s += s_pool[t * VEC + e];
       dst[c] = s;
     }
   }
@@ -396,31 +437,73 @@ __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, in
   }
 }
 
-// gate[n][c] = sigmoid(W2 * act(W1 * (pool[n]/HW) + b1) + b2): one block per image.
-__global__ void se_gate_kernel(const float* __restrict__ pool, int nparts, float inv_hw, int C, int R, const float* __restrict__ w1,
-                               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int act,
-                               float act_beta, float* __restrict__ gate) {
-  extern __shared__ float sm[];      // [C] means, [R] hidden
-  float* mean = sm; float* hid = sm + C;
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+// Sums the per-block pooling partials [N][nparts][C] into part 0 (fixed order -> deterministic); each (n,c) is touched by
+// exactly one thread, so the in-place update is race-free.
+__global__ void pool_reduce_kernel(float* __restrict__ pool, int nparts, int C, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / C; const int c = (int)(idx - n * C);
+    float* base = pool + n * nparts * C + c;
     float s = 0.0f;
-    for (int part = 0; part < nparts; ++part) s += pool[((long long)n * nparts + part) * C + c];
-    mean[c] = s * inv_hw;
+    for (int part = 0; part < nparts; ++part) s += base[(long long)part * C];
+    base[0] = s;
   }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = warp; r < R; r += nw) {
-    float s = 0.0f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[(long long)r * C + c], mean[c], s);
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) hid[r] = his_act(s + (b1 ? b1[r] : 0.0f), act, act_beta);
+}
+
+// hidden[n][r] = act(W1[r,:] . (pool[n][part 0]/HW) + b1[r]): one warp per (n, r), lanes walk the contiguous weight row
+// four elements at a time, fixed-order shuffle reduction.
+__global__ void se_hidden_kernel(const float* __restrict__ pool, int nparts, float inv_hw, int C, int R, const float* __restrict__ w1,
+                                 const float* __restrict__ b1, int act, float act_beta, float* __restrict__ hidden) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* mean = pool + (long long)n * nparts * C;
+  const float* wr = w1 + (long long)r * C;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int c = lane;
+  for (; c + 96 < C; c += 128) {
+    s0 = fmaf(__ldg(wr + c), mean[c], s0); s1 = fmaf(__ldg(wr + c + 32), mean[c + 32], s1);
+    s2 = fmaf(__ldg(wr + c + 64), mean[c + 64], s2); s3 = fmaf(__ldg(wr + c + 96), mean[c + 96], s3);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = b2 ? b2[c] : 0.0f;
-    for (int r = 0; r < R; ++r) s = fmaf(w2[(long long)c * R + r], hid[r], s);
-    gate[(long long)n * C + c] = his_sigmoid(s);
+  for (; c < C; c += 32) s0 = fmaf(__ldg(wr + c), mean[c], s0);
+  float s = (s0 + s1) + (s2 + s3);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) hidden[(long long)n * R + r] = his_act(s * inv_hw + (b1 ? b1[r] : 0.0f), act, act_beta);
+}
+
+// gate[n][c] = sigmoid(W2[c,:] . hidden[n] + b2[c]): one warp per (n, c).
+__global__ void se_gate_kernel(const float* __restrict__ hidden, int C, int R, const float* __restrict__ w2, const float* __restrict__ b2,
+                               float* __restrict__ gate) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const float* h = hidden + (long long)n * R;
+  const float* wr = w2 + (long long)c * R;
+  float s = 0.0f;
+  for (int r = lane; r < R; r += 32) s = fmaf(__ldg(wr + r), h[r], s);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) gate[(long long)n * C + c] = his_sigmoid(s + (b2 ? b2[c] : 0.0f));
+}
+
+// Folds a per-(image, input-channel) gate into the packed GEMM weights: wout[n][row][k] = w[row][k] * gate[n][k].
+// conv(x * gate) == conv_{w*gate}(x), so the squeeze-excite product never touches the activation tensor; the projection
+// GEMM then reads image n's weight slab (his_conv_gemm_set_image_weights).
+__global__ void scale_weights_kernel(const __half* __restrict__ w, const float* __restrict__ gate, long long rows, int K, int C,
+                                     long long total, __half* __restrict__ out) {
+  const int kgs = K / 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kg = (int)(idx % kgs);
+    const long long row = (idx / kgs) % rows;
+    const long long n = idx / (kgs * rows);
+    uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + row * K + kg * 8));
+    __half2* wh = reinterpret_cast<__half2*>(&wv);
+    const float* g = gate + n * C + kg * 8;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k0 = kg * 8 + 2 * e;
+      const float2 f = __half22float2(wh[e]);
+      wh[e] = __floats2half2_rn(k0 < C ? f.x * __ldg(g + 2 * e) : 0.0f, k0 + 1 < C ? f.y * __ldg(g + 2 * e + 1) : 0.0f);
+    }
+    *reinterpret_cast<uint4*>(out + (n * rows + row) * K + kg * 8) = wv;
   }
 }
 
@@ -810,16 +893,23 @@ static int pool_grid_x(long long per_img, int threads, int N, int per_sm, int cg
   const long long cap = (148LL * per_sm + N - 1) / (N > 0 ? N : 1);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  const int m = grid_multiple(cgs);
+  const int m = grid_multiple(cgs, threads);
   return (int)((gx + m - 1) / m * m);
+}
+
+constexpr int kDwRows = 4;                                   // output rows per thread (RY)
+static inline int dw_vec(int k) { return k == 5 ? 4 : 8; }   // channels per thread
+static int dw_grid_x(int N, int Ho, int Wo, int C, int k) {
+  const int cgs = C / dw_vec(k);
+  const long long per_img = (long long)((Ho + kDwRows - 1) / kDwRows) * Wo * cgs;
+  return pool_grid_x(per_img, kDwThreads, N, 12, cgs);        // ~12 blocks (4 waves of 3 resident) per SM over the whole batch
 }
 
 int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride) {
   const int pad = ((stride - 1) + (k - 1)) / 2;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  const int threads = threads_multiple_of(C / 8);
-  if (threads == 0) return 0;
-  return pool_grid_x((long long)Ho * Wo * (C / 8), threads, N, 16, C / 8);
+  if (C <= 0 || C % 8) return 0;
+  return dw_grid_x(N, Ho, Wo, C, k);
 }
 
 int his_pool_sum_parts(int N, int HW, int C) {
@@ -833,28 +923,25 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   if (!in || !w || !scale || !shift || !out) return his_set_error(HIS_ERR_INVALID_ARG, "depthwise: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: channels must be multiples of 8");
   if (N == 0) return HIS_OK;
+  if (!((k == 3 || k == 5) && (stride == 1 || stride == 2)))
+    return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: kernel size must be 3 or 5, stride 1 or 2");
+  if (act != HIS_ACT_SILU && act != HIS_ACT_NONE) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: activation must be SiLU or none");
   DwParams p;
   p.in = (const __half*)in; p.N = N; p.H = H; p.W = W; p.C = C; p.in_cs = in_cs; p.w = (const __half*)w; p.scale = scale; p.shift = shift;
   p.k = k; p.stride = stride; p.pad = ((stride - 1) + (k - 1)) / 2; p.Ho = (H + 2 * p.pad - k) / stride + 1; p.Wo = (W + 2 * p.pad - k) / stride + 1;
   p.act = act; p.out = (__half*)out; p.out_cs = out_cs; p.pool = pool_sums;
-  const long long per_img = (long long)p.Ho * p.Wo * (C / 8);
-  const int threads = threads_multiple_of(C / 8);
-  if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: more than 8192 channels");
-  if (per_img >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: image too large");
-  const int gx = pool_grid_x(per_img, threads, N, 16, C / 8);      // ~16 blocks per SM over the whole batch
-  dim3 grid(gx, N);
-  const size_t sm = pool_sums ? threads * 8 * sizeof(float) : 0;
-  if (act != HIS_ACT_SILU && act != HIS_ACT_NONE) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: activation must be SiLU or none");
-#define DW_LAUNCH(K_, S_)                                                                          \
-  do {                                                                                             \
-    if (act == HIS_ACT_SILU) depthwise_kernel<K_, S_, HIS_ACT_SILU><<<grid, threads, sm, ST>>>(p); \
-    else depthwise_kernel<K_, S_, HIS_ACT_NONE><<<grid, threads, sm, ST>>>(p);                     \
+  if ((long long)p.Ho * p.Wo * (C / 4) >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: image too large");
+  dim3 grid(dw_grid_x(N, p.Ho, p.Wo, C, k), N);
+  const size_t sm = pool_sums ? kDwThreads * dw_vec(k) * sizeof(float) : 0;
+#define DW_LAUNCH(K_, S_, V_)                                                                                        \
+  do {                                                                                                               \
+    if (act == HIS_ACT_SILU) depthwise_kernel<K_, S_, HIS_ACT_SILU, V_, kDwRows><<<grid, kDwThreads, sm, ST>>>(p);    \
+    else depthwise_kernel<K_, S_, HIS_ACT_NONE, V_, kDwRows><<<grid, kDwThreads, sm, ST>>>(p);                        \
   } while (0)
-  if (k == 3 && stride == 1) DW_LAUNCH(3, 1);
-  else if (k == 3 && stride == 2) DW_LAUNCH(3, 2);
-  else if (k == 5 && stride == 1) DW_LAUNCH(5, 1);
-  else if (k == 5 && stride == 2) DW_LAUNCH(5, 2);
-  else return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: kernel size must be 3 or 5, stride 1 or 2");
+  if (k == 3 && stride == 1) DW_LAUNCH(3, 1, 8);
+  else if (k == 3 && stride == 2) DW_LAUNCH(3, 2, 8);
+  else if (k == 5 && stride == 1) DW_LAUNCH(5, 1, 4);
+  else DW_LAUNCH(5, 2, 4);
 #undef DW_LAUNCH
   HIS_CHECK_LAUNCH();
   return HIS_OK;
@@ -874,12 +961,25 @@ int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums,
   return HIS_OK;
 }
 
-int his_se_gate(const float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2,
-                const float* b2, int act, float act_beta, float* gate, void* stream) {
-  if (!pool_sums || !w1 || !w2 || !gate) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: null pointer");
+int his_se_gate(float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1, const float* w2,
+                const float* b2, int act, float act_beta, float* hidden_ws, float* gate, void* stream) {
+  if (!pool_sums || !w1 || !w2 || !gate || !hidden_ws) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: null pointer");
   if (N == 0) return HIS_OK;
   if (nparts < 1) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: nparts must be >= 1");
-  se_gate_kernel<<<N, kThreads, (C + R) * sizeof(float), ST>>>(pool_sums, nparts, 1.0f / (float)HW, C, R, w1, b1, w2, b2, act, act_beta, gate);
+  if (nparts > 1) pool_reduce_kernel<<<grid_for((long long)N * C), kThreads, 0, ST>>>(pool_sums, nparts, C, (long long)N * C);
+  const int wpb = kThreads / 32;
+  se_hidden_kernel<<<dim3((R + wpb - 1) / wpb, N), kThreads, 0, ST>>>(pool_sums, nparts, 1.0f / (float)HW, C, R, w1, b1, act, act_beta, hidden_ws);
+  se_gate_kernel<<<dim3((C + wpb - 1) / wpb, N), kThreads, 0, ST>>>(hidden_ws, C, R, w2, b2, gate);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_scale_weights(const void* w_packed, const float* gate, int N, long long rows, int K, int C, void* out, void* stream) {
+  if (!w_packed || !gate || !out) return his_set_error(HIS_ERR_INVALID_ARG, "scale_weights: null pointer");
+  if (K % 8 || C > K) return his_set_error(HIS_ERR_INVALID_ARG, "scale_weights: K must be a multiple of 8 and >= C");
+  const long long total = (long long)N * rows * (K / 8);
+  if (total == 0) return HIS_OK;
+  scale_weights_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)w_packed, gate, rows, K, C, total, (__half*)out);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -101,7 +101,7 @@ class Plan:
             self.tensor_flops += f
 
     # kernels launched per op (cudaMemsetAsync is not one of ours)
-    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0}
+    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0, "se_gate": 3}
 
     def add(self, name: str, fn, *args, flops: int = 0, desc: str = ""):
         self.ops.append((name, fn, args))
@@ -112,9 +112,12 @@ class Plan:
     # -------------------------------------------------------------- ops
     def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, scale: torch.Tensor, shift: torch.Tensor, out: Act,
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
-                  transposed: bool = False, tail=None):
+                  transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None):
         """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
-        channels into the epilogue (his_conv_gemm_set_tail)."""
+        channels into the epilogue (his_conv_gemm_set_tail).  aux_f32: fp32 NCHW copy of the output written from the
+        epilogue (his_conv_gemm_set_aux).  in_gate = (gate fp32 [N, Cin], fp16 scratch >= N*rows*cin_pad): per-image
+        input-channel gate, folded into per-image weights by a small kernel ahead of the GEMM (his_scale_weights +
+        his_conv_gemm_set_image_weights); the scratch may be shared by ops that run back to back on the stream."""
         L = self.lib
         h = ctypes.c_void_p()
         if transposed:
@@ -135,6 +138,16 @@ class Plan:
                                                 1 if store_main else 0), "his_conv_gemm_set_tail")
             self.keep += [tw, tout]
             f += 2 * x.N * x.H * x.W * out.C * tc
+        if aux_f32 is not None:
+            _lib.check(L.his_conv_gemm_set_aux(h, aux_f32.data_ptr()), "his_conv_gemm_set_aux")
+            self.keep.append(aux_f32)
+        if in_gate is not None:
+            gate, wimg = in_gate
+            rows = w_packed.numel() // cin_pad
+            assert wimg.dtype == torch.float16 and wimg.numel() >= x.N * rows * cin_pad
+            _lib.check(L.his_conv_gemm_set_image_weights(h, wimg.data_ptr()), "his_conv_gemm_set_image_weights")
+            self.add("scale_weights", L.his_scale_weights, w_packed.data_ptr(), gate.data_ptr(), x.N, rows, cin_pad, x.C, wimg.data_ptr())
+            self.keep += [gate, wimg]
         self._add_flops(f, True)
         self.add("conv_gemm", L.his_conv_gemm_run, h, flops=f,
                  desc=f"N{x.N} {x.H}x{x.W} cin{x.C} cout{out.C} k{ksize}{' T' if transposed else ''}{' res%d' % res_mode if res_mode else ''}"

@@ -77,6 +77,8 @@ SIGNATURES = {
     "his_conv_gemm_create": [POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int,
                              _P, _P, c_int, c_int, c_int, c_float, c_int],
     "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
+    "his_conv_gemm_set_aux": [_P, _P],
+    "his_conv_gemm_set_image_weights": [_P, _P],
     "his_conv_gemm_run": [_P, _P],
     "his_conv_gemm_destroy": [_P],
     "his_conv_gemm_issued_macs": [_P],
@@ -84,9 +86,10 @@ SIGNATURES = {
                         c_float, c_int, _P, c_int, _P, c_int, _P, _P],
     "his_depthwise_conv": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P],
     "his_pool_sum": [_P, c_int, c_int, c_int, c_int, _P, _P],
-    "his_se_gate": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P],
+    "his_se_gate": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P],
     "his_depthwise_pool_parts": [c_int, c_int, c_int, c_int, c_int, c_int],
     "his_pool_sum_parts": [c_int, c_int, c_int],
+    "his_scale_weights": [_P, _P, c_int, _LL, c_int, c_int, _P, _P],
     "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
     "his_layernorm2d_parts": [c_int, c_int, c_int],
     "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],

@@ -366,16 +366,18 @@ class _BuiltPlan:
         return isinstance(norm, nn.BatchNorm2d)
 
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
-             out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None) -> Optional[Act]:
+             out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
+             in_gate=None) -> Optional[Act]:
         """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
         tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
-        epilogue; the wide activation itself is then not written (its only consumer is the tail)."""
+        epilogue; the wide activation itself is then not written (its only consumer is the tail).
+        aux_f32: fp32 NCHW copy of the output from the epilogue; in_gate: see Plan.conv_gemm (GEMM shapes only)."""
         p = self.plan
         if norm is not None and not self._is_bn(norm):
             # LayerNorm2d (hed/model.py:18-38): per-sample statistics over (C,H,W) cannot fold into the conv ->
             # conv(+bias) to fp16, then the two-launch LayerNorm kernel applies norm + residual + activation.
-            assert tail is None and out_f32 is None
-            raw = self.conv(x, conv, None, ACT["none"])
+            assert tail is None and out_f32 is None and aux_f32 is None
+            raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate)
             return self.layernorm(raw, norm, act, res, res_mode, out)
         transposed = isinstance(conv, nn.ConvTranspose2d)
         w = conv.weight
@@ -402,11 +404,11 @@ class _BuiltPlan:
                 tb = tconv.bias.detach().float().cpu().tolist() + [0.0]
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(scale, slab)), p.const(pad_vec(shift, slab)), out,
-                        k, act, self.beta, res, res_mode, transposed, tail=tl)
+                        k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
-            assert tail is None
+            assert tail is None and aux_f32 is None and in_gate is None
             p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, p.const(pack_direct_weight(w), torch.float16), p.const(scale), p.const(shift),
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
@@ -424,9 +426,16 @@ class _BuiltPlan:
               res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs)
         return out
 
-    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None) -> Act:
+    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None, aux_f32=None) -> Act:
         t = self.conv(x, rb.conv1, rb.norm1, act)
-        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail)
+        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail, aux_f32=aux_f32)
+
+    def _aux_fusable(self, cin: int) -> bool:
+        """The epilogue export exists for BatchNorm-folded layers whose K block is 64 wide (Cin >= 52)."""
+        return self._is_bn_mode() and cin >= 52
+
+    def _is_bn_mode(self) -> bool:
+        return self.m.normalization_type.lower() in ("batch", "batchnorm", "batchnorm2d")
 
     def _tail_ok(self, act: int) -> bool:
         """The fused tail exists for BatchNorm + none/relu epilogues (every preset); otherwise the separate 1x1 kernel runs."""
@@ -488,6 +497,16 @@ class _BuiltPlan:
         p.conv_direct(self.u_images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
                       p.const(shift), stem_c, 3, 2, 1, ACT["silu"], 1.0, in_affine=affine, out=x)
         level_of_stage = {1: 2, 2: 3, 4: 4}
+        # scratch for the per-image gated projection weights, sized for the widest block (the blocks run back to back)
+        need = 0
+        for stage in enc.blocks:
+            for blk in stage:
+                proj = blk.conv_pwl if blk.kind == "ir" else blk.conv_pw
+                nt, bn = ctypes.c_int(), ctypes.c_int()
+                L.his_conv_gemm_tile_n(proj.weight.shape[0], ctypes.byref(nt), ctypes.byref(bn))
+                need = max(need, B * nt.value * bn.value * round_up(blk.mid, 8))
+        self._gated_w = torch.empty(max(need, 8), dtype=torch.float16, device=self.dev)
+        p.keep.append(self._gated_w)
         for si, stage in enumerate(enc.blocks):
             for bi, blk in enumerate(stage):
                 last_of_stage = bi == len(stage) - 1
@@ -539,9 +558,10 @@ class _BuiltPlan:
         p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, B, ho * wo, blk.mid, r,
               p.const(se.conv_reduce.weight.reshape(r, blk.mid)).data_ptr(), p.const(se.conv_reduce.bias).data_ptr(),
               p.const(se.conv_expand.weight.reshape(blk.mid, r)).data_ptr(), p.const(se.conv_expand.bias).data_ptr(),
-              ACT["silu"], 1.0, gate.data_ptr())
-        p.add("scale_channels", L.his_scale_channels, d.ptr, d.cs, gate.data_ptr(), B, ho * wo, blk.mid, d.ptr, d.cs)
-        return self.conv(d, proj, proj_bn, ACT["none"], res=x if has_skip else None, res_mode=RES_ADD if has_skip else RES_NONE, out=dst)
+              ACT["silu"], 1.0, p.f32(B, r).data_ptr(), gate.data_ptr())
+        # the SE product x*gate is folded into per-image projection weights (conv(x*g) == conv_{w*g}(x)): no pass over d
+        return self.conv(d, proj, proj_bn, ACT["none"], res=x if has_skip else None, res_mode=RES_ADD if has_skip else RES_NONE, out=dst,
+                         in_gate=(gate, self._gated_w))
 
     # -------------------------------------------------------------- per-ROI head
     def _build_head(self):
@@ -580,7 +600,8 @@ class _BuiltPlan:
         sf = bh.shared_features
         shared = self.conv(feats, sf[0], sf[1], A_ref)
         shared = self.residual_block(shared, sf[4], A_ref)
-        shared = self.residual_block(shared, sf[6], A_ref)
+        shared_nchw = p.f32(N, 256, rh, rw) if (aux_level == "full" and self._aux_fusable(256)) else None
+        shared = self.residual_block(shared, sf[6], A_ref, aux_f32=shared_nchw)
         # --- bg/fg EnhancedUNet -> low-res logits (fp32 NCHW)
         low = p.f32(N, 2, rh, rw)
         self._enhanced_unet(shared, bh.bg_vs_fg_unet, low)
@@ -606,10 +627,15 @@ class _BuiltPlan:
         p.conv_direct(low, 1, N, rh, rw, 2, 0, p.const(pack_direct_weight(fg[0].weight), torch.float16), p.const(sc), p.const(sh), 64, 1, 1, 0,
                       A_ref, self.beta, out=g1)
         g2 = self.conv(g1, fg[3], None, A_ref)
+        gate_nchw = None
         if aux_level == "full":
-            gate = self.conv(g2, fg[5], None, ACT["sigmoid"])
-            self.h_aux["fg_attention"] = self.export_nchw(gate)
-        gated = self.conv(g2, fg[5], None, ACT["sigmoid"], res=shared, res_mode=RES_MUL)
+            if self._aux_fusable(g2.C):
+                gate_nchw = p.f32(N, 256, rh, rw)
+                self.h_aux["fg_attention"] = gate_nchw
+            else:
+                gate = self.conv(g2, fg[5], None, ACT["sigmoid"])
+                self.h_aux["fg_attention"] = self.export_nchw(gate)
+        gated = self.conv(g2, fg[5], None, ACT["sigmoid"], res=shared, res_mode=RES_MUL, aux_f32=gate_nchw)
         # --- target vs non-target branch
         tb = bh.target_vs_nontarget_branch
         x = self.residual_block(gated, tb[0], A_ref)
@@ -626,7 +652,7 @@ class _BuiltPlan:
             pool = p.f32(N, parts, 128); gate_c = p.f32(N, 128)
             p.add("pool_sum", L.his_pool_sum, x.ptr, N, x.H * x.W, 128, x.cs, pool.data_ptr())
             p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
-                  p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, gate_c.data_ptr())
+                  p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, p.f32(N, r).data_ptr(), gate_c.data_ptr())
             p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
             last_rb, tail = tb[8], tb[9]
         else:
@@ -644,7 +670,7 @@ class _BuiltPlan:
         if aux_level != "none":
             self.h_aux.update({"bg_fg_logits": bgfg, "bg_fg_logits_low": low, "target_nontarget_logits": tn})
             if aux_level == "full":
-                self.h_aux["shared_features"] = self.export_nchw(shared)
+                self.h_aux["shared_features"] = shared_nchw if shared_nchw is not None else self.export_nchw(shared)
         # --- auxiliary branches (..._refinement.py:772-802); computed like the reference forward does
         head = m.segmentation_head
         if m.use_contour_detection:

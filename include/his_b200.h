@@ -67,6 +67,13 @@ int his_conv_gemm_create(void** plan, const void* in, int n_img, int H, int W, i
  * NCHW fp32; tail_w: device fp32 [tail_c][cout_slab]; store_main=0 skips writing the wide activation altogether. */
 int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float tail_b1, int tail_c, int tail_sigmoid,
                            float* tail_out, int store_main);
+/* fp32 NCHW copy [n_img][cout][H][W] of the layer output written from the epilogue (the 256-channel tensors the reference
+ * returns in its aux dict: shared_features ..._refinement.py:557, fg_attention :570); with res_mode MUL the copy is the
+ * activated value before the product (the gate).  Layers with Cin >= 64 only. */
+int his_conv_gemm_set_aux(void* plan, float* aux_out);
+/* Per-image weights: image n reads slab n of w_packed_per_image ([n_img] x the his_conv_gemm_create layout).  Used to fold
+ * the squeeze-excite gate of timm's MBConv into the projection conv (his_scale_weights). */
+int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image);
 int his_conv_gemm_run(void* plan, void* stream);
 int his_conv_gemm_destroy(void* plan);
 long long his_conv_gemm_issued_macs(void* plan);
@@ -91,12 +98,16 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
 
 /* ---- squeeze-excite (timm SqueezeExcite) and ChannelAttentionModule (hed/advanced/attention_modules.py:10-64):
  * pool_sum: per-block partial sums fp32 [N][parts][C], parts = his_pool_sum_parts(...); se_gate: mean = sum of the
- * `nparts` partials / HW, gate = sigmoid(W2*act(W1*mean+b1)+b2), fp32 weights w1 [R,C], w2 [C,R], biases may be NULL;
+ * `nparts` partials / HW (the partials are first summed IN PLACE into part 0, so pool_sums is clobbered),
+ * gate = sigmoid(W2*act(W1*mean+b1)+b2), fp32 weights w1 [R,C], w2 [C,R], biases may be NULL;
  * scale_channels: out = in * gate[n,c]. */
 int his_pool_sum_parts(int N, int HW, int C);
 int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, void* stream);
-int his_se_gate(const float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1,
-                const float* w2, const float* b2, int act, float act_beta, float* gate, void* stream);
+int his_se_gate(float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1,
+                const float* w2, const float* b2, int act, float act_beta, float* hidden_ws /* [N][R] */, float* gate,
+                void* stream);
+/* out[n][row][k] = w_packed[row][k] * gate[n][k] (k < C, else 0): folds an input-channel gate into packed GEMM weights. */
+int his_scale_weights(const void* w_packed, const float* gate, int N, long long rows, int K, int C, void* out, void* stream);
 int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream);
 
 /* ---- LayerNorm2d, hed/model.py:18-38 (statistics over C,H,W per sample, biased variance) + optional residual +

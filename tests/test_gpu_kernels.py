@@ -51,7 +51,7 @@ def test_depthwise_se_matches_torch(k, s, c):
     w2, b2 = torch.randn(c, r, generator=g) * 0.2, torch.randn(c, generator=g) * 0.1
     gate = p.f32(n, c)
     L.check(lib.his_se_gate(pool.data_ptr(), parts, n, ho * wo, c, r, p.const(w1).data_ptr(), p.const(b1).data_ptr(), p.const(w2).data_ptr(),
-                            p.const(b2).data_ptr(), 2, 1.0, gate.data_ptr(), st))
+                            p.const(b2).data_ptr(), 2, 1.0, p.f32(n, r).data_ptr(), gate.data_ptr(), st))
     scaled = p.act(n, ho, wo, c)
     L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), n, ho * wo, c, scaled.ptr, scaled.cs, st))
     torch.cuda.synchronize()
