@@ -14,14 +14,16 @@
 //  * B (weights) is pre-packed fp16 [group][tap][Cout_slab][Cin_pad], K-major, 2-D TMA tiles.
 //  * D accumulates in TMEM (fp32), double buffered (2 x block_n columns) so that the epilogue
 //    of tile i overlaps the MMAs of tile i+1.
-//  * Epilogue: tcgen05.ld -> y = act(acc*scale[c] + shift[c] (+res)) (*res) -> fp16 ->
-//    swizzled smem staging -> TMA store (clips partial tiles / channel tails).  The residual /
-//    multiplicand tile arrives through TMA into the same staging buffer.
+//  * Epilogue: tcgen05.ld -> y = act(acc + shift[c] (+res)) (*res) -> fp16 -> swizzled smem staging ->
+//    TMA store (clips partial tiles / channel tails), 32 channels at a time.  The BatchNorm scale is
+//    folded into the packed weights by the caller; the residual / multiplicand tile arrives through
+//    TMA into the same staging buffer.  Two epilogue warpgroups alternate tiles (one per TMEM
+//    accumulator), so two tiles drain concurrently while the MMAs of later tiles run.
 //  * conv_transpose k2s2 = 4 independent 1x1 GEMMs ("groups"), each scattered through its own
 //    strided output tensor map (pixel (2y+dy, 2x+dx)).
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over work items):
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: epilogue.
+// Warp roles (384 threads, 1 CTA/SM, persistent over work items):
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7 / 8-11: epilogue groups 0 / 1.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -36,8 +38,11 @@
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kStagingBytes = kBlockM * 64 * 2;   // 16 KB : 128 rows x 64 channels fp16
-constexpr int kNumStaging = 2;
+constexpr int kChunkC = 32;                            // output channels per epilogue chunk
+constexpr int kStagingBytes = kBlockM * kChunkC * 2;   // 8 KB : 128 rows x 32 channels fp16 (SWIZZLE_64B rows)
+constexpr int kNumStaging = 4;                         // two per epilogue group
+constexpr int kShiftBytes = 256 * 4;                   // per-channel shift of the (single) N tile
+constexpr int kThreadsGemm = 384;
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 48;
 constexpr int kSmemBudget = 227 * 1024;
@@ -49,7 +54,7 @@ template <int BK> struct KCfg {
   static constexpr int kBBytesMax = 256 * BK * 2;
   // the ring gets whatever the 227 KB leave after the staging buffers, barriers and the 1 KB alignment slack; its depth is a
   // run-time parameter (stage = A + the layer's actual B tile), so narrow layers keep many more loads in flight
-  static constexpr int kRingBytes = kSmemBudget - kNumStaging * kStagingBytes - 1024 - kBarrierBytes;
+  static constexpr int kRingBytes = kSmemBudget - kNumStaging * kStagingBytes - kShiftBytes - 1024 - kBarrierBytes;
   static constexpr int kSmemBytes = kSmemBudget;
   static constexpr uint32_t kSbo = 8 * BK * 2;                 // bytes between 8-row groups
   static constexpr uint64_t kLayout = BK == 64 ? 2 : BK == 32 ? 4 : 6;   // SWIZZLE_128B / 64B / 32B
@@ -74,8 +79,7 @@ struct ConvGemmParams {
   //   GELU:    exact erf form
   float act_lo, act_beta;
   int act_mul_x;
-  const float* scale;   // [cout_slab]
-  const float* shift;   // [cout_slab]
+  const float* shift;   // [cout_slab]  (conv bias + folded-BatchNorm shift; the BN scale lives in the weights)
   // fused 1x1 tail to <= 2 channels (TAIL kernels): tail[o] = sum_c y[c]*tail_w[o][c] + tail_b[o], NCHW fp32 out
   const float* tail_w;  // [tail_c][cout_slab]
   float* tail_out;      // [n_img][tail_c][H][W]
@@ -221,7 +225,7 @@ __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) 
 enum { EPI_PLAIN = 0, EPI_TAIL = 1, EPI_AUX = 2 };
 
 template <int BK, int ACTC, int RES, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreadsGemm, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
@@ -232,14 +236,15 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base;
   const uint32_t staging_base = smem_base + kStages * p.stage_bytes;
-  const uint32_t bar_base = staging_base + kNumStaging * kStagingBytes;
-  // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[2]; then the TMEM pointer
+  const uint32_t shift_base = staging_base + kNumStaging * kStagingBytes;
+  const uint32_t bar_base = shift_base + kShiftBytes;
+  // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[4]; then the TMEM pointer
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   auto res_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 8);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to the aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,13 +258,18 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); mbar_init(res_bar(a), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 4; ++a) mbar_init(res_bar(a), 1);
     fence_barrier_init();
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // single N tile: the per-channel shift stays in shared memory for the whole kernel
+  float* s_shift = reinterpret_cast<float*>(smem_gen + (shift_base - smem_base));
+  if (p.n_tiles == 1)
+    for (int i = threadIdx.x; i < p.block_n; i += kThreadsGemm) s_shift[i] = __ldg(p.shift + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -312,25 +322,31 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================
-    const int te = threadIdx.x - 128;           // 0..127 == output row of the tile == TMEM lane
+    // ================================ epilogue (two groups of 4 warps, group g drains accumulator g) ================================
+    const int g = (warp - 4) >> 2;
+    const int te = (threadIdx.x - 128) & 127;   // 0..127 == output row of the tile == TMEM lane
     const int q = warp & 3;                     // TMEM lane quarter this warp may touch
-    const int nchunks = (p.block_n + 63) >> 6;
-    int iter = 0; uint32_t cc = 0;
-    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
+    const bool issuer_warp = q == 0;            // first warp of the group issues the group's TMA traffic
+    const int nchunks = (p.block_n + kChunkC - 1) / kChunkC;
+    const uint32_t stg0 = staging_base + g * 2 * kStagingBytes;
+    const uint32_t acc_col = (uint32_t)(g * 256);
+    uint32_t cc = 0;
+    int iter_g = 0;
+    for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += 2 * gridDim.x, ++iter_g) {
       const WorkItem it = decode_work(p, w);
-      const int acc = iter & 1; const uint32_t acc_phase = (iter >> 1) & 1;
+      const uint32_t acc_phase = iter_g & 1;
       const CUtensorMap* tmO = it.group == 0 ? &tmO0 : it.group == 1 ? &tmO1 : it.group == 2 ? &tmO2 : &tmO3;
       const int chbase = it.n_tile * p.block_n;
-      if (RES && warp == 4 && elect_one()) {    // prefetch the first two residual chunks while the MMAs run
+      const float* shp = p.n_tiles == 1 ? s_shift : p.shift + chbase;
+      if (RES && issuer_warp && elect_one()) {  // prefetch the first two residual chunks while the MMAs run
         tma_wait_read<0>();
         for (int j = 0; j < 2 && j < nchunks; ++j) {
           const int b = (cc + j) & 1;
-          mbar_expect_tx(res_bar(b), kStagingBytes);
-          tma_load_4d(staging_base + b * kStagingBytes, &tmR, res_bar(b), chbase + j * 64, it.x0, it.y0, it.img);
+          mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
+          tma_load_4d(stg0 + b * kStagingBytes, &tmR, res_bar(2 * g + b), chbase + j * kChunkC, it.x0, it.y0, it.img);
         }
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(tfull_bar(g), acc_phase);
       tc_fence_after();
       float tacc0 = 0.0f, tacc1 = 0.0f;
       constexpr bool TAIL = EPI == EPI_TAIL;
@@ -340,35 +356,34 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (EPI == EPI_AUX && py < p.H && px < p.W) aux_px = p.aux_out + ((long long)it.img * p.cout * p.H + py) * p.W + px;
       for (int j = 0; j < nchunks; ++j, ++cc) {
         const int b = cc & 1;
-        const uint32_t stg = staging_base + b * kStagingBytes;
-        const int ch0 = chbase + j * 64;        // first output channel of this chunk
-        const int ncol = min(64, p.block_n - j * 64);   // valid accumulator columns in this chunk (multiple of 16)
-        if ((!RES || j >= 2) && warp == 4 && elect_one()) {
+        const uint32_t stg = stg0 + b * kStagingBytes;
+        const int cl0 = j * kChunkC;            // first channel of this chunk within the N tile
+        const int ch0 = chbase + cl0;           // ... and within the layer
+        const int ncol = min(kChunkC, p.block_n - cl0);   // valid accumulator columns in this chunk (16 or 32)
+        if ((!RES || j >= 2) && issuer_warp && elect_one()) {
           tma_wait_read<1>();                    // the store that last read staging[b] has drained
           if (RES) {
-            mbar_expect_tx(res_bar(b), kStagingBytes);
-            tma_load_4d(stg, &tmR, res_bar(b), ch0, it.x0, it.y0, it.img);
+            mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
+            tma_load_4d(stg, &tmR, res_bar(2 * g + b), ch0, it.x0, it.y0, it.img);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + j * 64);
-        if (ncol > 32) { tmem_ld32(taddr, v); tmem_ld32(taddr + 32, v + 32); }
-        else if (ncol > 16) { tmem_ld32(taddr, v); }
-        else { tmem_ld16(taddr, v); }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        uint32_t v[kChunkC];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)cl0;
+        if (ncol > 16) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_ld_wait();
         if (j == nchunks - 1) {                  // accumulator fully read -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) mbar_arrive(tempty_bar(g));
         }
-        if (RES) mbar_wait(res_bar(b), (cc >> 1) & 1);
-        uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * 128;
+        if (RES) mbar_wait(res_bar(2 * g + b), (cc >> 1) & 1);
+        uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kChunkC / 8; ++i) {
           if (i * 8 < ncol) {
-            const int c = ch0 + i * 8;
-            uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ (te & 7)) << 4));
+            const int cl = cl0 + i * 8, c = ch0 + i * 8;
+            uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ ((te >> 1) & 3)) << 4));   // SWIZZLE_64B
             float r[8];
             if (RES) {
               const uint4 rv = *cell;
@@ -376,14 +391,12 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
             }
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + c)), t1 = __ldg(reinterpret_cast<const float4*>(p.shift + c + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float4 t0 = *reinterpret_cast<const float4*>(shp + cl), t1 = *reinterpret_cast<const float4*>(shp + cl + 4);
             const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float t = fmaf(__uint_as_float(v[i * 8 + e]), sc[e], sh[e]);
+              float t = __uint_as_float(v[i * 8 + e]) + sh[e];
               if (RES == HIS_RES_ADD) t += r[e];
               t = epi_act<ACTC>(t, p);
               if (EPI == EPI_AUX) { if (aux_px && c + e < p.cout) aux_px[(long long)(c + e) * p.H * p.W] = t; }
@@ -409,8 +422,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         if (store_main) {
           fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (warp == 4 && elect_one()) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          if (issuer_warp && elect_one()) {
             tma_store_4d(tmO, stg, ch0, it.x0, it.y0, it.img);
             tma_commit();
           }
@@ -426,7 +439,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       }
     }
-    if (warp == 4 && elect_one()) tma_wait_all();
+    if (issuer_warp && elect_one()) tma_wait_all();
   }
 
   tc_fence_before();
@@ -556,7 +569,7 @@ int his_conv_gemm_tile_n(int cout, int* n_tiles, int* block_n) {
   int c16 = (cout + 15) / 16 * 16;
   if (c16 <= 256) { *n_tiles = 1; *block_n = c16; return HIS_OK; }
   int nt = (c16 + 255) / 256;
-  int bn = ((c16 + nt - 1) / nt + 63) / 64 * 64;   // multi-tile: block_n % 64 == 0 so 64-wide store chunks never overlap
+  int bn = ((c16 + nt - 1) / nt + 31) / 32 * 32;   // multi-tile: block_n % 32 == 0 so 32-wide store chunks never overlap
   *n_tiles = (c16 + bn - 1) / bn; *block_n = bn;
   return HIS_OK;
 }
@@ -566,9 +579,9 @@ int his_conv_gemm_create(void** out_plan,
                          const void* w_packed, int cin_pad,
                          void* out, int cout, int out_cs,
                          const void* res, int res_cs,
-                         const float* scale, const float* shift,
+                         const float* shift,
                          int ksize, int transposed, int act, float act_beta, int res_mode) {
-  if (!out_plan || !in || !w_packed || !out || !scale || !shift) return his_set_error(HIS_ERR_INVALID_ARG, "null pointer");
+  if (!out_plan || !in || !w_packed || !out || !shift) return his_set_error(HIS_ERR_INVALID_ARG, "null pointer");
   if (!(ksize == 1 || ksize == 3) || (transposed && ksize != 1)) return his_set_error(HIS_ERR_UNSUPPORTED, "ksize must be 1 or 3 (transposed: k2s2 packed as 4 1x1 groups)");
   if (res_mode != HIS_RES_NONE && !res) return his_set_error(HIS_ERR_INVALID_ARG, "res_mode set without residual tensor");
   if (res_mode != HIS_RES_NONE && transposed) return his_set_error(HIS_ERR_UNSUPPORTED, "residual with transposed conv");
@@ -633,23 +646,23 @@ int his_conv_gemm_create(void** out_plan,
   if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
   pl->actc = actc; pl->res_mode = res_mode; pl->transposed = transposed; pl->cin_pad = cin_pad;
   p.tail_c = 0; p.store_main = 1; p.aux_out = nullptr; p.cout = cout;
-  p.scale = scale; p.shift = shift;
+  p.shift = shift;
   int taps = ksize * ksize;
   int rc;
   if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, bk, p.bw, p.bh))) { delete pl; return rc; }
   if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, p.block_n, bk))) { delete pl; return rc; }
   if (!transposed) {
-    if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
+    if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, kChunkC, p.bw, p.bh))) { delete pl; return rc; }
     pl->tmO[1] = pl->tmO[2] = pl->tmO[3] = pl->tmO[0];
   } else {
     for (int g = 0; g < 4; ++g) {
       int dy = g >> 1, dx = g & 1;
       const __half* base = (const __half*)out + ((long long)dy * 2 * W + dx) * out_cs;
-      if ((rc = encode_act_map(&pl->tmO[g], base, cout, W, H, n_img, 2LL * out_cs, 4LL * W * out_cs, 4LL * H * W * out_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
+      if ((rc = encode_act_map(&pl->tmO[g], base, cout, W, H, n_img, 2LL * out_cs, 4LL * W * out_cs, 4LL * H * W * out_cs, kChunkC, p.bw, p.bh))) { delete pl; return rc; }
     }
   }
   if (res_mode != HIS_RES_NONE) {
-    if ((rc = encode_act_map(&pl->tmR, res, cout, W, H, n_img, res_cs, (long long)W * res_cs, (long long)H * W * res_cs, 64, p.bw, p.bh))) { delete pl; return rc; }
+    if ((rc = encode_act_map(&pl->tmR, res, cout, W, H, n_img, res_cs, (long long)W * res_cs, (long long)H * W * res_cs, kChunkC, p.bw, p.bh))) { delete pl; return rc; }
   } else {
     pl->tmR = pl->tmO[0];
   }
@@ -697,7 +710,7 @@ int his_conv_gemm_run(void* plan, void* stream) {
   if (!plan) return his_set_error(HIS_ERR_INVALID_ARG, "null plan");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
   if (pl->p.num_work == 0) return HIS_OK;
-  pl->kernel<<<pl->grid, 256, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
+  pl->kernel<<<pl->grid, kThreadsGemm, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
                                                                pl->p);
   HIS_CHECK_LAUNCH();
   return HIS_OK;

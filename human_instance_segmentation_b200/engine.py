@@ -110,7 +110,7 @@ class Plan:
         self.launches += self.KERNELS_PER_OP.get(name, 1)
 
     # -------------------------------------------------------------- ops
-    def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, scale: torch.Tensor, shift: torch.Tensor, out: Act,
+    def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, shift: torch.Tensor, out: Act,
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
                   transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None):
         """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
@@ -126,10 +126,10 @@ class Plan:
             assert (out.N, out.H, out.W) == (x.N, x.H, x.W)
         _lib.check(L.his_conv_gemm_create(ctypes.byref(h), x.ptr, x.N, x.H, x.W, x.C, x.cs, w_packed.data_ptr(), cin_pad,
                                           out.ptr, out.C, out.cs, res.ptr if res is not None else None,
-                                          res.cs if res is not None else 0, scale.data_ptr(), shift.data_ptr(), ksize,
+                                          res.cs if res is not None else 0, shift.data_ptr(), ksize,
                                           1 if transposed else 0, act, beta, res_mode), "his_conv_gemm_create")
         self.gemm_plans.append(h)
-        self.keep += [w_packed, scale, shift]
+        self.keep += [w_packed, shift]
         taps = 4 if transposed else ksize * ksize
         f = 2 * x.N * x.H * x.W * x.C * out.C * taps
         if tail is not None:
@@ -238,10 +238,16 @@ def pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
     return out
 
 
-def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False) -> Tuple[torch.Tensor, int]:
+def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False, scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
     """Conv2d weight [Cout,Cin,kh,kw] -> fp16 [1][taps][cout_slab][cin_pad];
-    ConvTranspose2d(k2,s2) weight [Cin,Cout,2,2] -> fp16 [4 groups (dy,dx)][1][cout_slab][cin_pad]."""
+    ConvTranspose2d(k2,s2) weight [Cin,Cout,2,2] -> fp16 [4 groups (dy,dx)][1][cout_slab][cin_pad].
+    ``scale`` [Cout] (the folded BatchNorm scale) multiplies the fp32 weights per output channel before the fp16 rounding."""
     w = w.detach().float().cpu()
+    if scale is not None:
+        sc = scale.detach().float().cpu()
+        w = w * (sc.view(1, -1, 1, 1) if transposed else sc.view(-1, 1, 1, 1))
+        if float(w.abs().max()) > 6.0e4:
+            raise _lib.HisError("folded conv*BatchNorm weight exceeds the fp16 range (|w*gamma/sqrt(var+eps)| > 6e4)")
     if transposed:
         cin, cout = w.shape[0], w.shape[1]
         cin_pad = round_up(cin, 8)

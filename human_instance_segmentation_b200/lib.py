@@ -75,7 +75,7 @@ SIGNATURES = {
                       c_int, _P, c_int, _P, _P],
     "his_conv_gemm_tile_n": [c_int, POINTER(c_int), POINTER(c_int)],
     "his_conv_gemm_create": [POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int,
-                             _P, _P, c_int, c_int, c_int, c_float, c_int],
+                             _P, c_int, c_int, c_int, c_float, c_int],
     "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
     "his_conv_gemm_set_aux": [_P, _P],
     "his_conv_gemm_set_image_weights": [_P, _P],

@@ -394,7 +394,7 @@ class _BuiltPlan:
             nt, bn = ctypes.c_int(), ctypes.c_int()
             p.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
             slab = nt.value * bn.value
-            wp, cin_pad = pack_gemm_weight(w, slab, transposed)
+            wp, cin_pad = pack_gemm_weight(w, slab, transposed, scale)
             tl = None
             if tail is not None:
                 tconv, tsig, tout = tail
@@ -403,7 +403,7 @@ class _BuiltPlan:
                 tw[:, :cout] = tconv.weight.detach().float().cpu().reshape(tc, cout)
                 tb = tconv.bias.detach().float().cpu().tolist() + [0.0]
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
-            p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(scale, slab)), p.const(pad_vec(shift, slab)), out,
+            p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(shift, slab)), out,
                         k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate)
         else:
             if transposed:

@@ -53,14 +53,16 @@ int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC
 /* ---- dense conv2d 3x3(pad 1)/1x1, stride 1, and conv_transpose2d k2 s2, as tcgen05 implicit GEMM
  * (hed/advanced/hierarchical_segmentation_rgb.py:657-673,695; ..._refinement.py:37-39,479-523,537-545;
  *  ..._unet.py:44-47,313-372; smp decoder convs / timm 1x1 convs, see oracle/effunet.py).
- * y = act(conv(x)*scale[c] + shift[c] (+res)) (*res), fp16 in/out, fp32 accumulate.
+ * y = act(conv_w(x) + shift[c] (+res)) (*res), fp16 in/out, fp32 accumulate.  An eval-mode BatchNorm that follows the
+ * conv is folded by the caller: w = weight * gamma/sqrt(var+eps) per output channel (before the fp16 rounding),
+ * shift = beta - mean*scale + bias*scale.
  * w_packed: fp16 [groups][taps][cout_slab][cin_pad] (groups = 4 for transposed: (dy,dx) = (g>>1,g&1)),
- * cout_slab = n_tiles*block_n from his_conv_gemm_tile_n; scale/shift: device fp32 [cout_slab].
+ * cout_slab = n_tiles*block_n from his_conv_gemm_tile_n; shift: device fp32 [cout_slab].
  * The plan captures the pointers (TMA descriptors); run it any number of times. */
 int his_conv_gemm_tile_n(int cout, int* n_tiles, int* block_n);
 int his_conv_gemm_create(void** plan, const void* in, int n_img, int H, int W, int cin, int in_cs,
                          const void* w_packed, int cin_pad, void* out, int cout, int out_cs,
-                         const void* res, int res_cs, const float* scale, const float* shift,
+                         const void* res, int res_cs, const float* shift,
                          int ksize, int transposed, int act, float act_beta, int res_mode);
 /* Optional fused 1x1 tail to 1-2 channels computed in the epilogue from the fp32 activations (the Cout<=2 convs at
  * ..._refinement.py:293,335,523 and ..._unet.py:371): tail_out[n,o,y,x] = (sigmoid)(sum_c y[c]*tail_w[o][c] + tail_b[o]),

@@ -33,7 +33,7 @@ def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, 
     nt, bn = ctypes.c_int(), ctypes.c_int()
     plan.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
     slab = nt.value * bn.value
-    wp, cin_pad = engine.pack_gemm_weight(wt, slab, transposed)
+    wp, cin_pad = engine.pack_gemm_weight(wt, slab, transposed, scale)   # BatchNorm scale folded into the weights
     oh, ow = (2 * h, 2 * w) if transposed else (h, w)
     out_total, out_off = out_slice or (cout, 0)
     obuf = plan.act(n, oh, ow, out_total)
@@ -43,19 +43,20 @@ def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, 
     if res_mode != RES_NONE:
         res = plan.act(n, oh, ow, cout)
         res.buf.copy_(torch.randn(n, oh, ow, res.cs, generator=g).half())
-    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(scale, slab)), plan.const(engine.pad_vec(shift, slab)),
+    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(shift, slab)),
                    out, k, act, beta, res, res_mode, transposed)
     plan.replay()
     torch.cuda.synchronize()
     got = out.torch_nchw().cpu()
     # reference
     xin = x.torch_nchw().cpu()
-    wh = wt.half().float()
+    # the kernel's operand: weights with the scale folded in, rounded to fp16
+    wh = (wt * (scale.view(1, -1, 1, 1) if transposed else scale.view(-1, 1, 1, 1))).half().float()
     if transposed:
         y = F.conv_transpose2d(xin, wh, stride=2)
     else:
         y = F.conv2d(xin, wh, padding=k // 2)
-    y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    y = y + shift.view(1, -1, 1, 1)
     if res_mode == RES_ADD:
         y = y + res.torch_nchw().cpu()
     y = _act(y, act, beta)

@@ -53,7 +53,7 @@ def bench(shape, reps):
     if res_mode != RES_NONE:
         res = plan.act(n, oh, ow, cout)
         res.buf.normal_()
-    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(torch.ones(slab)), plan.const(torch.zeros(slab)), out, k, 1, 1.0, res,
+    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(torch.zeros(slab)), out, k, 1, 1.0, res,
                    res_mode, transposed)
     for _ in range(2):
         plan.replay()

@@ -39,7 +39,7 @@ def gemm(n, h, w, cin, cout, k, res_mode=RES_NONE, aux=False, act=1):
     if res_mode != RES_NONE:
         res = p.act(n, h, w, cout); res.buf.normal_()
     auxt = p.f32(n, cout, h, w) if aux else None
-    p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(torch.ones(slab)), p.const(torch.zeros(slab)), out, k, act, 1.0, res, res_mode,
+    p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(torch.zeros(slab)), out, k, act, 1.0, res, res_mode,
                 False, aux_f32=auxt)
 
 
