@@ -437,15 +437,23 @@ __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, in
   }
 }
 
-// Sums the per-block pooling partials [N][nparts][C] into part 0 (fixed order -> deterministic); each (n,c) is touched by
-// exactly one thread, so the in-place update is race-free.
-__global__ void pool_reduce_kernel(float* __restrict__ pool, int nparts, int C, long long total) {
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long n = idx / C; const int c = (int)(idx - n * C);
-    float* base = pool + n * nparts * C + c;
-    float s = 0.0f;
-    for (int part = 0; part < nparts; ++part) s += base[(long long)part * C];
-    base[0] = s;
+// Sums the per-block pooling partials [N][nparts][C] into part 0.  Block = 32 channels x 32 part-lanes: lane y adds parts
+// y, y+32, ... (coalesced over channels), then the 32 partial sums are added in a fixed order -> deterministic.  Each
+// (n,c) of part 0 is written by exactly one thread after every read of the block (syncthreads), so in-place is race-free.
+__global__ void pool_reduce_kernel(float* __restrict__ pool, int nparts, int C) {
+  __shared__ float s[32][33];
+  const int n = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x;
+  float* base = pool + (long long)n * nparts * C;
+  float a = 0.0f;
+  if (c < C)
+    for (int part = threadIdx.y; part < nparts; part += 32) a += base[(long long)part * C + c];
+  s[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += s[y][threadIdx.x];
+    base[c] = t;
   }
 }
 
@@ -966,7 +974,7 @@ int his_se_gate(float* pool_sums, int nparts, int N, int HW, int C, int R, const
   if (!pool_sums || !w1 || !w2 || !gate || !hidden_ws) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: null pointer");
   if (N == 0) return HIS_OK;
   if (nparts < 1) return his_set_error(HIS_ERR_INVALID_ARG, "se_gate: nparts must be >= 1");
-  if (nparts > 1) pool_reduce_kernel<<<grid_for((long long)N * C), kThreads, 0, ST>>>(pool_sums, nparts, C, (long long)N * C);
+  if (nparts > 1) pool_reduce_kernel<<<dim3((C + 31) / 32, N), dim3(32, 32), 0, ST>>>(pool_sums, nparts, C);
   const int wpb = kThreads / 32;
   se_hidden_kernel<<<dim3((R + wpb - 1) / wpb, N), kThreads, 0, ST>>>(pool_sums, nparts, 1.0f / (float)HW, C, R, w1, b1, act, act_beta, hidden_ws);
   se_gate_kernel<<<dim3((C + wpb - 1) / wpb, N), kThreads, 0, ST>>>(hidden_ws, C, R, w2, b2, gate);
