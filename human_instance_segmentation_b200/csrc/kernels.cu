@@ -769,6 +769,62 @@ __global__ void map_f32_kernel(const float* __restrict__ in, long long total, in
   }
 }
 
+// ---- PretrainedUNetGuidedSegmentationHead glue (rgb.py:125-218)
+// fg_prob = sigmoid(channel c of an NCHW fp32 tensor) -> channel 0 of an NHWC fp16 slice (the concat slot) and/or fp32 [N,HW]
+__global__ void sigmoid_channel_kernel(const float* __restrict__ in, int C, long long HW, int c, long long total, __half* __restrict__ out_h,
+                                       int out_cs, float* __restrict__ out_f) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / HW, p = idx - n * HW;
+    const float v = 1.0f / (1.0f + expf(-in[(n * C + c) * HW + p]));
+    if (out_h) out_h[idx * out_cs] = __float2half_rn(v);
+    if (out_f) out_f[idx] = v;
+  }
+}
+
+// processed * (attention * (0.5 + 0.5 * fg_prob))  (rgb.py:169-173); a, f: fp32 per pixel
+__global__ void scale_pixels_kernel(const __half* __restrict__ in, int in_cs, const float* __restrict__ a, const float* __restrict__ f, int C,
+                                    long long total, __half* __restrict__ out, int out_cs) {
+  const int cgs = C / 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const float g = __ldg(a + pix) * (0.5f + 0.5f * __ldg(f + pix));
+    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * in_cs + cg * 8));
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 v = __half22float2(xh[e]); xh[e] = __floats2half2_rn(v.x * g, v.y * g); }
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+  }
+}
+
+// aux outputs of the guided head (rgb.py:187-216): m = bilinear(mask channel c -> (Ho,Wo)) (identity when equal),
+// fg = sigmoid(m), bg_fg_logits = [log(1-fg+1e-7), log(fg+1e-7)]
+__global__ void guided_aux_kernel(const float* __restrict__ in, int C, int c, int H, int W, int Ho, int Wo, long long total,
+                                  float* __restrict__ mask_out, float* __restrict__ fg_out, float* __restrict__ bgfg_out) {
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const bool same = H == Ho && W == Wo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
+    const long long n = idx / ((long long)Wo * Ho);
+    const float* b = in + (n * C + c) * (long long)H * W;
+    float m;
+    if (same) m = b[oy * W + ox];
+    else {
+      const float fy = fmaxf(((float)oy + 0.5f) * sy - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sx - 0.5f, 0.0f);
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+      const float ly = fy - (float)y0, lx = fx - (float)x0;
+      m = (1.0f - ly) * ((1.0f - lx) * b[y0 * W + x0] + lx * b[y0 * W + x1]) + ly * ((1.0f - lx) * b[y1 * W + x0] + lx * b[y1 * W + x1]);
+    }
+    const float fg = 1.0f / (1.0f + expf(-m));
+    const long long hw = (long long)Ho * Wo, p = idx - n * hw;
+    mask_out[idx] = m;
+    fg_out[idx] = fg;
+    bgfg_out[(n * 2) * hw + p] = logf((1.0f - fg) + 1e-7f);
+    bgfg_out[(n * 2 + 1) * hw + p] = logf(fg + 1e-7f);
+  }
+}
+
 // NHWC fp16 slice -> NCHW fp32 (aux outputs: shared_features, fg_attention)
 __global__ void nhwc_half_to_nchw_float_kernel(const __half* __restrict__ in, int N, int HW, int C, int cs, float* __restrict__ out) {
   __shared__ float tile[32][33];
@@ -874,11 +930,12 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
     else done = false;
     if (done) { HIS_CHECK_LAUNCH(); return HIS_OK; }
   }
-  if (in_fmt == 0 && cout <= 2 && out_f32 && !out_half && !res_mode && cin % 8 == 0 && in_cs % 8 == 0 &&
+  if (in_fmt == 0 && cout <= 3 && out_f32 && !out_half && !res_mode && cin % 8 == 0 && in_cs % 8 == 0 &&
       (size_t)kh * kw * cin * cout * sizeof(float) <= 48 * 1024) {
     const long long total = (long long)N * p.Ho * p.Wo;
     const size_t sm = (size_t)kh * kw * cin * cout * sizeof(float);
     if (cout == 1) small_cout_conv_kernel<1><<<grid_for(total), kThreads, sm, ST>>>(p);
+    else if (cout == 3) small_cout_conv_kernel<3><<<grid_for(total), kThreads, sm, ST>>>(p);
     else small_cout_conv_kernel<2><<<grid_for(total), kThreads, sm, ST>>>(p);
     HIS_CHECK_LAUNCH();
     return HIS_OK;
@@ -1105,6 +1162,38 @@ int his_map_f32(const float* in, long long total, int op, const float* param, fl
   if (!in || !out || (op == 1 && !param)) return his_set_error(HIS_ERR_INVALID_ARG, "map_f32: null pointer");
   if (total == 0) return HIS_OK;
   map_f32_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, total, op, param, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_sigmoid_channel(const float* in, int N, int C, int HW, int c, void* out_half, int out_cs, float* out_f32, void* stream) {
+  if (!in || (!out_half && !out_f32)) return his_set_error(HIS_ERR_INVALID_ARG, "sigmoid_channel: null pointer");
+  if (c < 0 || c >= C) return his_set_error(HIS_ERR_INVALID_ARG, "sigmoid_channel: channel out of range");
+  const long long total = (long long)N * HW;
+  if (total == 0) return HIS_OK;
+  sigmoid_channel_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, C, HW, c, total, (__half*)out_half, out_cs, out_f32);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_scale_pixels(const void* in, int in_cs, const float* attention, const float* fg_prob, long long pixels, int C, void* out, int out_cs,
+                     void* stream) {
+  if (!in || !attention || !fg_prob || !out) return his_set_error(HIS_ERR_INVALID_ARG, "scale_pixels: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "scale_pixels: channels must be multiples of 8");
+  const long long total = pixels * (C / 8);
+  if (total == 0) return HIS_OK;
+  scale_pixels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, attention, fg_prob, C, total, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, int Wo, float* mask_out, float* fg_out, float* bgfg_out,
+                   void* stream) {
+  if (!in || !mask_out || !fg_out || !bgfg_out) return his_set_error(HIS_ERR_INVALID_ARG, "guided_aux: null pointer");
+  if (c < 0 || c >= C) return his_set_error(HIS_ERR_INVALID_ARG, "guided_aux: channel out of range");
+  const long long total = (long long)N * Ho * Wo;
+  if (total == 0) return HIS_OK;
+  guided_aux_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, C, c, H, W, Ho, Wo, total, mask_out, fg_out, bgfg_out);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

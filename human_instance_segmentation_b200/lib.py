@@ -102,6 +102,9 @@ SIGNATURES = {
     "his_head_combine": [_P, _P, c_int, c_int, c_int, _P, _P],
     "his_map_f32": [_P, _LL, c_int, _P, _P, _P],
     "his_nhwc_half_to_nchw_float": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "his_sigmoid_channel": [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P],
+    "his_scale_pixels": [_P, c_int, _P, _P, _LL, c_int, _P, c_int, _P],
+    "his_guided_aux": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "his_unet_input_affine": [_P, _LL, _F, _F, _P, _P, _P],
     "his_unet_outputs": [_P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, _P, _P, _P],
     "his_memset_async": [_P, c_int, _LL, _P],

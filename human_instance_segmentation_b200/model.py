@@ -81,7 +81,70 @@ class PreTrainedPeopleSegmentationUNetWrapper(nn.Module):
         return owner()._run_unet_only(x), []
 
 
-class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
+class _PlannedModel(nn.Module):
+    """Shared execution plumbing: a launch plan per input geometry, replayed on the caller's stream (no torch-op fallback)."""
+
+    def _init_exec_state(self):
+        self.aux_outputs = "full"        # "full" (reference dict) | "light" (no 256-channel tensors) | "none"
+        self.copy_outputs = True         # return fresh tensors (False: views of the plan's static buffers)
+        self.use_cuda_graph = False
+        self.max_rois_per_pass = None    # None: derived from the ROI size (bounds the activation footprint)
+        self.max_images_per_pass = None  # None: derived from the image size / encoder width
+        self._plans: Dict[tuple, "_BuiltPlan"] = {}
+        self.eval()
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("the B200 path is inference-only (eval semantics); train with the reference")
+        return super().train(False)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.invalidate()
+        return r
+
+    def invalidate(self):
+        """Drop packed weights / plans (call after mutating parameters in place)."""
+        self._plans.clear()
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._plans.clear()
+        return r
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor, rois: torch.Tensor):
+        bp = self._get_plan(images, rois)
+        bp.load_inputs(images, rois)
+        bp.plan.replay()
+        return bp.outputs(self.copy_outputs)
+
+    def _aligners(self):
+        return [self.roi_align_mask, self.roi_align_rgb] if hasattr(self, "roi_align_mask") else [self.roi_align]
+
+    def _get_plan(self, images: torch.Tensor, rois: torch.Tensor) -> "_BuiltPlan":
+        if not images.is_cuda and not torch.cuda.is_available():
+            raise _lib.HisError("human_instance_segmentation_b200 needs a CUDA (B200) device; there is no CPU fallback")
+        if images.dim() != 4 or images.shape[1] != 3:
+            raise ValueError(f"images must be [B,3,H,W], got {tuple(images.shape)}")
+        if rois.dim() != 2 or rois.shape[1] != 5:
+            raise ValueError(f"rois must be [N,5] = [batch_idx,x1,y1,x2,y2], got {tuple(rois.shape)}")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.HisError("move the model to a CUDA device first (model.to('cuda')); there is no CPU fallback")
+        B, _, H, W = images.shape
+        key = (B, H, W, rois.shape[0], self.aux_outputs, self.max_rois_per_pass, self.max_images_per_pass,
+               tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index)
+        bp = self._plans.get(key)
+        if bp is None:
+            bp = _BuiltPlan(self, dev, B, H, W, rois.shape[0])
+            if self.use_cuda_graph:
+                bp.plan.capture()
+            self._plans[key] = bp
+        return bp
+
+
+class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel):
     """rgb.py:564-774 on the B200 kernels."""
 
     def __init__(self, roi_size: Union[int, Tuple[int, int]] = 28, mask_size: Union[int, Tuple[int, int]] = 56,
@@ -104,9 +167,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
         if use_boundary_refinement or use_progressive_upsampling or use_subpixel_conv:
             raise NotImplementedError("boundary refinement / progressive upsampling / sub-pixel decoders are not part of the "
                                       "preset path (all three presets disable them) and are not implemented on B200")
-        if not (use_contour_detection or use_distance_transform):
-            raise NotImplementedError("PretrainedUNetGuidedSegmentationHead (no refinement flag) is not implemented on B200 yet; "
-                                      "the presets enable contour detection + distance transform")
+        self.use_refinement = bool(use_contour_detection or use_distance_transform)      # rgb.py:683-689
         self.pretrained_unet = PreTrainedPeopleSegmentationUNetWrapper(
             in_channels=3, pretrained_weights_path=pretrained_weights_path, freeze_weights=freeze_pretrained_weights,
             encoder_name=kwargs.get("encoder_name", "timm-efficientnet-b3"))
@@ -120,48 +181,16 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
             nn.Conv2d(64, 128, 3, padding=1), pt.norm_params(n, 128), pt.Slot(), pt.ResidualBlockParams(128, n),
             nn.Conv2d(128, 256, 3, padding=1), pt.norm_params(n, 256), pt.Slot(), pt.ResidualBlockParams(256, n),
             nn.Conv2d(256, 256, 1), pt.norm_params(n, 256), pt.Slot())
-        self.feature_combiner = nn.Conv2d(258, 256, 1)
-        self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
-                                                      self.use_distance_transform, base, depth)
+        if self.use_refinement:
+            self.feature_combiner = nn.Conv2d(258, 256, 1)
+            self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
+                                                          self.use_distance_transform, base, depth)
+        else:                                  # rgb.py:715-727: the UNet-guided head takes (features, roi masks) directly
+            self.segmentation_head = pt.GuidedHeadParams(256, 256, n, self.use_attention_module)
         self.hierarchical_depth = depth
-        # execution state
-        self.aux_outputs = "full"        # "full" (reference dict) | "light" (no 256-channel tensors) | "none"
-        self.copy_outputs = True         # return fresh tensors (False: views of the plan's static buffers)
-        self.use_cuda_graph = False
-        self.max_rois_per_pass = None    # None: derived from the ROI size (bounds the activation footprint)
-        self.max_images_per_pass = None  # None: derived from the image size / encoder width
-        self._plans: Dict[tuple, "_BuiltPlan"] = {}
-        self._param_version = 0
-        self.eval()
-
-    # ------------------------------------------------------------------ nn.Module plumbing
-    def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError("the B200 path is inference-only (eval semantics); train with the reference")
-        return super().train(False)
-
-    def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        r = super().load_state_dict(state_dict, strict=strict, **kw)
-        self.invalidate()
-        return r
-
-    def invalidate(self):
-        """Drop packed weights / plans (call after mutating parameters in place)."""
-        self._plans.clear()
-
-    def _apply(self, fn, *a, **k):
-        r = super()._apply(fn, *a, **k)
-        self._plans.clear()
-        return r
+        self._init_exec_state()
 
     # ------------------------------------------------------------------ public API
-    @torch.no_grad()
-    def forward(self, images: torch.Tensor, rois: torch.Tensor):
-        bp = self._get_plan(images, rois)
-        bp.load_inputs(images, rois)
-        bp.plan.replay()
-        return bp.outputs(self.copy_outputs)
-
     @torch.no_grad()
     def infer(self, images: torch.Tensor, rois: torch.Tensor, raw_logits: bool = False):
         """Exported-ONNX contract (hed/export_onnx_advanced.py:353-457): returns
@@ -184,28 +213,42 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(nn.Module):
         bp.plan.replay()
         return bp.two.clone()
 
-    # ------------------------------------------------------------------ plan management
-    def _get_plan(self, images: torch.Tensor, rois: torch.Tensor) -> "_BuiltPlan":
-        if not images.is_cuda and not torch.cuda.is_available():
-            raise _lib.HisError("human_instance_segmentation_b200 needs a CUDA (B200) device; there is no CPU fallback")
-        if images.dim() != 4 or images.shape[1] != 3:
-            raise ValueError(f"images must be [B,3,H,W], got {tuple(images.shape)}")
-        if rois.dim() != 2 or rois.shape[1] != 5:
-            raise ValueError(f"rois must be [N,5] = [batch_idx,x1,y1,x2,y2], got {tuple(rois.shape)}")
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise _lib.HisError("move the model to a CUDA device first (model.to('cuda')); there is no CPU fallback")
-        B, _, H, W = images.shape
-        key = (B, H, W, rois.shape[0], self.aux_outputs, self.max_rois_per_pass, self.max_images_per_pass, tuple(_scale_hw(self.roi_align_mask)), tuple(_scale_hw(self.roi_align_rgb)),
-               self.roi_align_mask.aligned, self.roi_align_rgb.aligned, dev.index)
-        bp = self._plans.get(key)
-        if bp is None:
-            bp = _BuiltPlan(self, dev, B, H, W, rois.shape[0])
-            if self.use_cuda_graph:
-                bp.plan.capture()
-            self._plans[key] = bp
-        return bp
 
+class HierarchicalRGBSegmentationModel(_PlannedModel):
+    """rgb.py:298-439: the model the factory returns without a pre-trained UNet -- one DynamicRoIAlign (aligned=False) on the
+    RGB image, ``RGBFeatureExtractor`` (rgb.py:221-295; 3->64->128->192->256, ReLU), then ``HierarchicalSegmentationHeadUNetV2``
+    (..._unet.py:670-845; LayerNorm2d and ReLU hard-coded, EnhancedUNet 96/3) or, with a refinement flag, the refined head."""
+
+    def __init__(self, roi_size: Union[int, Tuple[int, int]] = 28, mask_size: Union[int, Tuple[int, int]] = 56, feature_channels: int = 256,
+                 num_classes: int = 3, use_attention_module: bool = False, use_boundary_refinement: bool = False,
+                 use_progressive_upsampling: bool = False, use_subpixel_conv: bool = False, use_contour_detection: bool = False,
+                 use_distance_transform: bool = False, **kwargs):
+        super().__init__()
+        if num_classes != 3:
+            raise AssertionError("Hierarchical model designed for 3 classes")           # ..._unet.py:703
+        if feature_channels != 256:
+            raise NotImplementedError("feature_channels != 256 is not implemented on B200 (the factory never passes it)")
+        if use_boundary_refinement or use_progressive_upsampling or use_subpixel_conv:
+            raise NotImplementedError("boundary refinement / progressive upsampling / sub-pixel decoders are not implemented on B200")
+        self.roi_size = _pair(roi_size)
+        self.mask_size = _pair(mask_size)
+        n = kwargs.get("normalization_type", "layernorm2d")
+        self.use_attention_module = bool(use_attention_module)
+        self.use_contour_detection = bool(use_contour_detection)
+        self.use_distance_transform = bool(use_distance_transform)
+        self.use_refinement = bool(use_contour_detection or use_distance_transform)
+        # the reference passes no activation to any sub-module here: everything is ReLU
+        self.activation_function, self.activation_beta = "relu", 1.0
+        self.normalization_type = n if self.use_refinement else "layernorm2d"       # head norm (V2 head: LayerNorm2d hard-coded)
+        self.extractor_normalization_type = n
+        self.rgb_extractor = pt.RGBFeatureExtractorParams(n)
+        if self.use_refinement:
+            self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
+                                                          self.use_distance_transform, 96, 3)
+        else:
+            self.segmentation_head = pt.BaseHeadParams(256, 256, "layernorm2d", self.use_attention_module, 96, 3)
+        self.roi_align = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=False)      # rgb.py:404-408
+        self._init_exec_state()
 
 def _scale_hw(ra: DynamicRoIAlign):
     return float(ra.spatial_scale_h), float(ra.spatial_scale_w)
@@ -285,11 +328,12 @@ class _BuiltPlan:
         self.act_rgb = {"relu": ACT["relu"], "swish": ACT["silu"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
         self.act_ref = {"relu": ACT["relu"], "swish": ACT["swish"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
         self.beta = m.activation_beta
-        stem_c = m.pretrained_unet.model.model.encoder.out_channels[1]
-        self.Bc = min(B, m.max_images_per_pass or _images_per_pass(H, W, stem_c))
+        self.has_unet = hasattr(m, "pretrained_unet")
+        stem_c = m.pretrained_unet.model.model.encoder.out_channels[1] if self.has_unet else 32
+        self.Bc = min(B, m.max_images_per_pass or _images_per_pass(H, W, stem_c)) if self.has_unet else B
         self.Nc = min(N, m.max_rois_per_pass or _rois_per_pass(m.roi_size))
         self.chunked_unet, self.chunked_head = self.Bc < B, self.Nc < N
-        self.n_unet_chunks = (B + self.Bc - 1) // self.Bc
+        self.n_unet_chunks = (B + self.Bc - 1) // self.Bc if self.has_unet else 0
         self.n_head_chunks = (N + self.Nc - 1) // self.Nc if N else 0
         # ---- UNet sub-plan
         self.unet_plan = self.plan = Plan(dev)
@@ -297,26 +341,30 @@ class _BuiltPlan:
         p.tag = "unet"
         self.images = p.f32(B, 3, H, W)
         self.rois = p.f32(max(N, 1), 5, zero=True)
-        self.two = p.f32(B, 2, H, W)
-        self.binary = p.f32(B, 1, H, W)
+        self.two = p.f32(B, 2, H, W) if self.has_unet else None
+        self.binary = p.f32(B, 1, H, W) if self.has_unet else None
         self.u_images = p.f32(self.Bc, 3, H, W) if self.chunked_unet else self.images
-        self._build_unet()
+        if self.has_unet:
+            self._build_unet()
         # ---- head sub-plan
         self.aux: Dict[str, torch.Tensor] = {}
         self.h_aux: Dict[str, torch.Tensor] = {}
         self.head_plan = None
         mh, mw = m.mask_size
         self.logits = self.unet_plan.f32(N, 3, mh, mw)
-        if m.aux_outputs != "none":
+        if m.aux_outputs != "none" and self.has_unet:
             self.aux["full_image_logits"] = self.two
         if N:
             self.head_plan = self.plan = Plan(dev)
             self.plan.tag = "head"
             self.h_rois = self.plan.f32(self.Nc, 5, zero=True) if self.chunked_head else self.rois
             self.h_logits = self.plan.f32(self.Nc, 3, mh, mw) if self.chunked_head else self.logits
-            self._build_head()
+            if self.has_unet:
+                self._build_head()
+            else:
+                self._build_head_standard()
             for k, v in self.h_aux.items():
-                self.aux[k] = self.plan.f32(N, *v.shape[1:]) if self.chunked_head else v
+                self.aux[k] = (self.plan.f32(N, *v.shape[1:]) if self.chunked_head else v) if v is not None else None
         self.plan = _CompositePlan(self)
 
     # -------------------------------------------------------------- I/O + schedule
@@ -327,14 +375,14 @@ class _BuiltPlan:
 
     def outputs(self, copy: bool):
         f = (lambda t: t.clone()) if copy else (lambda t: t)
-        aux = {k: f(v) for k, v in self.aux.items()}
+        aux = {k: (f(v) if v is not None else None) for k, v in self.aux.items()}
         return f(self.logits), aux
 
     def run(self, timed: bool = False):
         L = self.unet_plan.lib
         H, W = self.H, self.W
         out = []
-        for i0 in range(0, self.B, self.Bc):
+        for i0 in range(0, self.B if self.has_unet else 0, self.Bc):
             n = min(self.Bc, self.B - i0)
             if self.chunked_unet:
                 self.u_images[:n].copy_(self.images[i0:i0 + n])
@@ -358,7 +406,8 @@ class _BuiltPlan:
             if self.chunked_head:
                 self.logits[j0:j0 + n].copy_(self.h_logits[:n])
                 for k, v in self.h_aux.items():
-                    self.aux[k][j0:j0 + n].copy_(v[:n])
+                    if v is not None:
+                        self.aux[k][j0:j0 + n].copy_(v[:n])
         return out
 
     # -------------------------------------------------------------- helpers
@@ -573,14 +622,16 @@ class _BuiltPlan:
         A_rgb, A_ref = self.act_rgb, self.act_ref
 
         # --- Dynamic RoI Align (rgb.py:751-755): UNet logits -> channels 256..257 of the combiner input, RGB -> patches
-        comb_in = p.act(N, rh, rw, 258)
+        # (guided head: channel 256 of its 257-channel input_adjust input holds sigmoid(fg logit) instead)
+        comb_in = p.act(N, rh, rw, 258 if m.use_refinement else 257)
         patches = p.act(N, rh, rw, 3)
         roi_feat = p.f32(N, 2, rh, rw)
         roi_patch = p.f32(N, 3, rh, rw) if aux_level != "none" else None
         ram, rar = m.roi_align_mask, m.roi_align_rgb
-        msk = comb_in.slice(256, 2)
+        msk = comb_in.slice(256, 2) if m.use_refinement else None
         p.add("roi_align_mask", L.his_roi_align, self.two.data_ptr(), 0, 2 * H * W, H * W, W, 1, B, 2, H, W, self.h_rois.data_ptr(), N, rh, rw,
-              float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0, msk.ptr, msk.cs, roi_feat.data_ptr())
+              float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0, msk.ptr if msk else None, msk.cs if msk else 0,
+              roi_feat.data_ptr())
         p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
               float(rar.spatial_scale_h), float(rar.spatial_scale_w), 1 if rar.aligned else 0, patches.ptr, patches.cs,
               roi_patch.data_ptr() if roi_patch is not None else None)
@@ -592,10 +643,57 @@ class _BuiltPlan:
             x = self.conv(x, fe[i], fe[i + 1], A_rgb)
             x = self.residual_block(x, fe[i + 3], A_ref)
         self.conv(x, fe[12], fe[13], A_rgb, out=comb_in.slice(0, 256))
+        if not m.use_refinement:
+            self._build_guided_head(comb_in, roi_feat, roi_patch)
+            return
         # --- feature_combiner 1x1 258->256 (rgb.py:695,758-762); the concat is the buffer layout itself
         feats = self.conv(Act(comb_in.buf, 258), m.feature_combiner, None, ACT["none"])
+        self._hier_head(feats, m.segmentation_head.base_head, m.segmentation_head)
+        if aux_level != "none":
+            self.h_aux["roi_features"] = roi_feat
+            self.h_aux["roi_patches"] = roi_patch
 
-        bh = m.segmentation_head.base_head
+    def _build_head_standard(self):
+        """HierarchicalRGBSegmentationModel.forward (rgb.py:410-439): RoIAlign(aligned=False) -> RGBFeatureExtractor -> head."""
+        m, p, L = self.m, self.plan, self.plan.lib
+        N, B, H, W = self.Nc, self.B, self.H, self.W
+        rh, rw = m.roi_size
+        A = ACT["relu"]
+        patches = p.act(N, rh, rw, 3)
+        roi_patch = p.f32(N, 3, rh, rw) if m.aux_outputs != "none" else None
+        ra = m.roi_align
+        p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
+              float(ra.spatial_scale_h), float(ra.spatial_scale_w), 1 if ra.aligned else 0, patches.ptr, patches.cs,
+              roi_patch.data_ptr() if roi_patch is not None else None)
+        # RGBFeatureExtractor (rgb.py:221-295): [conv3x3, norm, ReLU] (+ ResidualBlock after every stage but the first)
+        saved = m.normalization_type
+        m.normalization_type = m.extractor_normalization_type        # _tail_ok/_aux_fusable look at the current norm kind
+        x = patches
+        for mod in m.rgb_extractor.features:
+            if isinstance(mod, nn.Conv2d):
+                conv = mod
+            elif isinstance(mod, (nn.BatchNorm2d, pt.LayerNorm2dParams)):
+                x = self.conv(x, conv, mod, A)
+            elif isinstance(mod, pt.ResidualBlockParams):
+                x = self.residual_block(x, mod, A)
+        m.normalization_type = saved
+        if m.use_refinement:
+            self._hier_head(x, m.segmentation_head.base_head, m.segmentation_head)
+        else:
+            self._hier_head(x, m.segmentation_head, None)
+            self.h_aux.pop("shared_features", None)                  # the V2 head returns 4 aux tensors (..._unet.py:836-841)
+        if m.aux_outputs != "none":
+            self.h_aux["roi_patches"] = roi_patch
+
+    def _hier_head(self, feats: Act, bh, head):
+        """ExtendedHierarchicalSegmentationHeadUNetV2 / HierarchicalSegmentationHeadUNetV2 (``bh``) and, when ``head`` is the
+        refined wrapper, its contour / distance branches (..._refinement.py:734-804)."""
+        m, p, L = self.m, self.plan, self.plan.lib
+        N = self.Nc
+        rh, rw = m.roi_size
+        mh, mw = m.mask_size
+        aux_level = m.aux_outputs
+        A_rgb, A_ref = self.act_rgb, self.act_ref
         # --- shared trunk (..._refinement.py:479-487)
         sf = bh.shared_features
         shared = self.conv(feats, sf[0], sf[1], A_ref)
@@ -672,7 +770,8 @@ class _BuiltPlan:
             if aux_level == "full":
                 self.h_aux["shared_features"] = shared_nchw if shared_nchw is not None else self.export_nchw(shared)
         # --- auxiliary branches (..._refinement.py:772-802); computed like the reference forward does
-        head = m.segmentation_head
+        if head is None:
+            return
         if m.use_contour_detection:
             cb = head.contour_branch.contour_branch
             c = self.conv(shared, cb[0], cb[1], A_ref)
@@ -701,9 +800,43 @@ class _BuiltPlan:
             dmask, dmap = self.to_mask_size(m_low), self.to_mask_size(d_low)
             if aux_level != "none":
                 self.h_aux["distance_mask"], self.h_aux["distance_map"] = dmask, dmap
-        if aux_level != "none":
-            self.h_aux["roi_features"] = roi_feat
-            self.h_aux["roi_patches"] = roi_patch
+
+    def _build_guided_head(self, comb_in: Act, roi_feat: torch.Tensor, roi_patch: Optional[torch.Tensor]):
+        """PretrainedUNetGuidedSegmentationHead.forward (rgb.py:125-218): the UNet's foreground probability is the 257th input
+        channel and modulates the optional attention; a direct 3-class classifier; aux log-probabilities from the resized mask."""
+        m, p, L = self.m, self.plan, self.plan.lib
+        N = self.Nc
+        rh, rw = m.roi_size
+        mh, mw = m.mask_size
+        A_rgb, A_ref = self.act_rgb, self.act_ref
+        hd = m.segmentation_head
+        fg_slot = comb_in.slice(256, 1)
+        fg_low = p.f32(N, 1, rh, rw)
+        p.add("sigmoid_channel", L.his_sigmoid_channel, roi_feat.data_ptr(), N, 2, rh * rw, 1, fg_slot.ptr, fg_slot.cs, fg_low.data_ptr())
+        x = self.conv(Act(comb_in.buf, 257), hd.input_adjust, None, ACT["none"])
+        fp = hd.feature_processor
+        x = self.conv(x, fp[0], fp[1], A_rgb)
+        x = self.residual_block(x, fp[4], A_ref)
+        x = self.residual_block(x, fp[6], A_ref)
+        attention = None
+        if m.use_attention_module:
+            am = hd.attention_module
+            a = self.conv(x, am[0], None, A_rgb)
+            attention = p.f32(N, 1, rh, rw)
+            self.conv(a, am[2], None, ACT["sigmoid"], out_f32=attention)
+            p.add("scale_pixels", L.his_scale_pixels, x.ptr, x.cs, attention.data_ptr(), fg_low.data_ptr(), N * rh * rw, 256, x.ptr, x.cs)
+        fc = hd.final_classifier
+        y = self.conv(x, fc[0], fc[1], A_rgb)
+        same = (rh, rw) == (mh, mw)
+        low = self.h_logits if same else p.f32(N, 3, rh, rw)
+        self.conv(y, fc[3], None, ACT["none"], out_f32=low)
+        if not same:
+            p.add("resize_bilinear", L.his_resize_bilinear_f32, low.data_ptr(), N * 3, rh, rw, mh, mw, self.h_logits.data_ptr())
+        if m.aux_outputs != "none":
+            mask_up, fg_up, bgfg = p.f32(N, 1, mh, mw), p.f32(N, 1, mh, mw), p.f32(N, 2, mh, mw)
+            p.add("guided_aux", L.his_guided_aux, roi_feat.data_ptr(), N, 2, 1, rh, rw, mh, mw, mask_up.data_ptr(), fg_up.data_ptr(), bgfg.data_ptr())
+            self.h_aux.update({"bg_fg_logits": bgfg, "target_nontarget_logits": self.h_logits[:, 1:3], "fg_prob": fg_up,
+                               "pretrained_bg_fg_mask": mask_up, "attention": attention, "roi_features": roi_feat, "roi_patches": roi_patch})
 
     def _enhanced_unet(self, x: Act, u: pt.EnhancedUNetParams, low_out: torch.Tensor):
         """EnhancedUNet.forward (..._unet.py:375-417).  Skip concats are buffer layouts: decoder level i reads
@@ -778,9 +911,18 @@ def create_rgb_hierarchical_model(roi_size: Union[int, Tuple[int, int]] = 28, ma
     kwargs.pop("fusion_method", None)
     if multi_scale:
         raise NotImplementedError("MultiScaleRGBSegmentationModel (rgb.py:777-922) is outside the B200 hot path (SURVEY §8f rank 4)")
-    if not (use_pretrained_unet and use_full_image_unet):
-        raise NotImplementedError("only the full-image pretrained-UNet model (use_pretrained_unet=True, use_full_image_unet=True) "
-                                  "-- the path every B0/B1/B7 preset takes -- is implemented on B200")
+    if use_pretrained_unet and not use_full_image_unet:
+        # rgb.py:442-561: the reference's own constructor dies on an undefined name (`kwargs`, :497) -> nothing to mirror
+        raise NotImplementedError("HierarchicalRGBSegmentationModelWithPretrainedUNet (ROI-level UNet) cannot be constructed in the "
+                                  "reference either (NameError at hierarchical_segmentation_rgb.py:497); not implemented")
+    if not use_pretrained_unet:       # rgb.py:1011-1026: activation kwargs are NOT forwarded to this model
+        pt.check_activation(activation_function)
+        return HierarchicalRGBSegmentationModel(
+            roi_size=roi_size, mask_size=mask_size, use_attention_module=use_attention_module,
+            use_boundary_refinement=use_boundary_refinement, use_progressive_upsampling=use_progressive_upsampling,
+            use_subpixel_conv=use_subpixel_conv, use_contour_detection=use_contour_detection,
+            use_distance_transform=use_distance_transform, normalization_type=normalization_type,
+            normalization_groups=normalization_groups)
     return HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(
         roi_size=roi_size, mask_size=mask_size, pretrained_weights_path=pretrained_weights_path,
         use_attention_module=use_attention_module, freeze_pretrained_weights=freeze_pretrained_weights,

@@ -162,6 +162,39 @@ class RefinedHeadParams(nn.Module):
             self.distance_decoder = DistanceDecoderParams(mid, 128, norm)
 
 
+class RGBFeatureExtractorParams(nn.Module):
+    """RGBFeatureExtractor, rgb.py:221-295 (num_layers=4: 3 -> 64 -> 128 -> 192 -> 256; a ResidualBlock after stages 1..3)."""
+
+    def __init__(self, norm: str):
+        super().__init__()
+        ch = [3, 64, 128, 192, 256]
+        layers = []
+        for i in range(4):
+            layers += [nn.Conv2d(ch[i], ch[i + 1], 3, padding=1), norm_params(norm, ch[i + 1]), Slot()]
+            if i >= 1:
+                layers.append(ResidualBlockParams(ch[i + 1], norm))
+        self.features = nn.Sequential(*layers)
+
+
+class GuidedHeadParams(nn.Module):
+    """PretrainedUNetGuidedSegmentationHead, rgb.py:43-123 (the head built when no refinement flag is set, :715-727)."""
+
+    def __init__(self, cin: int, mid: int, norm: str, attention: bool):
+        super().__init__()
+        self.use_attention_module = attention
+        self.input_adjust = nn.Conv2d(cin + 1, cin, 1)
+        self.feature_processor = nn.Sequential(nn.Conv2d(cin, mid, 3, padding=1), norm_params(norm, mid), Slot(), Slot(),
+                                               ResidualBlockParams(mid, norm), Slot(), ResidualBlockParams(mid, norm))
+        self.final_classifier = nn.Sequential(nn.Conv2d(mid, mid // 2, 3, padding=1), norm_params(norm, mid // 2), Slot(),
+                                              nn.Conv2d(mid // 2, 3, 1))
+        if attention:
+            self.attention_module = nn.Sequential(nn.Conv2d(mid, mid // 4, 1), Slot(), nn.Conv2d(mid // 4, 1, 1), Slot())
+        with torch.no_grad():                      # rgb.py:117-123
+            self.final_classifier[-1].bias.data[0] = 0.0
+            self.final_classifier[-1].bias.data[1] = 0.0
+            self.final_classifier[-1].bias.data[2] = -0.5
+
+
 # ----------------------------------------------------------------------------- EfficientNet-UNet (smp/timm key scheme)
 _ARCH = [("ds", 1, 3, 1, 1, 16), ("ir", 2, 3, 2, 6, 24), ("ir", 2, 5, 2, 6, 40), ("ir", 3, 3, 2, 6, 80),
          ("ir", 3, 5, 1, 6, 112), ("ir", 4, 5, 2, 6, 192), ("ir", 1, 3, 1, 6, 320)]

@@ -142,6 +142,19 @@ int his_head_combine(const float* bgfg, const float* tn, int N, int H, int W, fl
 int his_map_f32(const float* in, long long total, int op, const float* param, float* out, void* stream);
 int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, void* stream);
 
+/* ---- PretrainedUNetGuidedSegmentationHead glue, hed/advanced/hierarchical_segmentation_rgb.py:125-218 (the head the
+ * factory builds when no refinement flag is set, :715-727).
+ * his_sigmoid_channel: fg_prob = sigmoid(in[:,c]) of NCHW fp32 [N,C,HW] (:146) -> channel 0 of an NHWC half slice
+ *   (the concat slot of input_adjust, :161) and/or fp32 [N,HW]; either output may be NULL.
+ * his_scale_pixels: out = x * (attention * (0.5 + 0.5*fg_prob)) per pixel (:169-173); attention, fg_prob fp32 [pixels].
+ * his_guided_aux: m = bilinear(in[:,c] -> (Ho,Wo), align_corners=False) (identity when sizes match), fg = sigmoid(m),
+ *   bgfg = [log(1-fg+1e-7), log(fg+1e-7)] (:187-205); outputs NCHW fp32 [N,1,Ho,Wo] x2 and [N,2,Ho,Wo]. */
+int his_sigmoid_channel(const float* in, int N, int C, int HW, int c, void* out_half, int out_cs, float* out_f32, void* stream);
+int his_scale_pixels(const void* in, int in_cs, const float* attention, const float* fg_prob, long long pixels, int C, void* out,
+                     int out_cs, void* stream);
+int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, int Wo, float* mask_out, float* fg_out, float* bgfg_out,
+                   void* stream);
+
 /* ---- PreTrainedPeopleSegmentationUNet.normalize_input (..._unet.py:1885-1890) without the host sync:
  * affine6 = {a0,a1,a2,b0,b1,b2}, a = 1/(d*std), b = -mean/std, d = 255 iff max(images) > 1.  mean3/std3 are HOST arrays.
  * his_unet_outputs: output_conv 1x1 1->2 (:1963-1971) and the export wrapper's binary mask

@@ -9,7 +9,9 @@ golden fixtures in tests/golden/ (anywhere).  Citations are into /root/reference
 Covered: the preset path (`HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet`
 with the refined head), BatchNorm (eval) and LayerNorm2d normalisation, relu/silu/
 swish/gelu activations, attention and non-attention target branches, contour and
-distance branches, the export wrapper outputs and `MaskDilationModule`.
+distance branches, the export wrapper outputs and `MaskDilationModule`; and the
+secondary variant the same factory reaches when no refinement flag is set
+(`PretrainedUNetGuidedSegmentationHead`, rgb.py:43-218).
 """
 from __future__ import annotations
 
@@ -44,8 +46,15 @@ class PathConfig:
     # DynamicRoIAlign.spatial_scale of both aligners: 640.0 by default (rgb.py:636-647);
     # the exporter overrides it with (H, W) (export_onnx_advanced.py:80-98).
     spatial_scale: Tuple[float, float] = (640.0, 640.0)
+    # False -> HierarchicalRGBSegmentationModel (rgb.py:298-439): no UNet branch, one RoIAlign with aligned=False
+    use_pretrained_unet: bool = True
 
     def factory_kwargs(self) -> dict:
+        if not self.use_pretrained_unet:
+            return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
+                        use_attention_module=self.use_attention_module, use_contour_detection=self.use_contour_detection,
+                        use_distance_transform=self.use_distance_transform, normalization_type=self.normalization_type,
+                        normalization_groups=8)
         return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
                     use_attention_module=self.use_attention_module,
                     use_contour_detection=self.use_contour_detection,
@@ -353,9 +362,74 @@ def refined_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig):
     return logits, aux
 
 
+def guided_head(sd: SD, p: str, feats: Tensor, bg_fg_mask: Tensor, cfg: PathConfig):
+    """PretrainedUNetGuidedSegmentationHead.forward (rgb.py:125-218; ctor :46-123), eval mode (dropout = identity).
+    Stand-alone activations come from rgb.py's factory (swish == silu), the residual blocks are the refinement ones."""
+    if bg_fg_mask.shape[1] == 2:
+        bg_fg_mask = bg_fg_mask[:, 1:2]                                  # :139-141 foreground channel
+    fg_prob = torch.sigmoid(bg_fg_mask)
+    fg_low = fg_prob
+    if fg_low.shape[2:] != feats.shape[2:]:
+        fg_low = F.interpolate(fg_prob, size=feats.shape[2:], mode="bilinear", align_corners=False)
+    x = conv(sd, p + "input_adjust.", torch.cat([feats, fg_low], 1), 0)
+    q = p + "feature_processor."
+    x = act_rgb(norm(sd, q + "1.", conv(sd, q + "0.", x, 1), cfg), cfg)
+    x = residual_block(sd, q + "4.", x, cfg, act_ref)
+    x = residual_block(sd, q + "6.", x, cfg, act_ref)
+    attention = None
+    if cfg.use_attention_module:                                         # :168-173
+        a = p + "attention_module."
+        attention = torch.sigmoid(conv(sd, a + "2.", act_rgb(conv(sd, a + "0.", x, 0), cfg), 0))
+        x = x * (attention * (0.5 + 0.5 * fg_low))
+    c = p + "final_classifier."
+    y = act_rgb(norm(sd, c + "1.", conv(sd, c + "0.", x, 1), cfg), cfg)
+    logits = _to_mask_size(conv(sd, c + "3.", y, 0), cfg)
+    mh, mw = cfg.mask_size
+    if bg_fg_mask.shape[2] != mh or bg_fg_mask.shape[3] != mw:          # :188-196
+        bg_fg_mask = F.interpolate(bg_fg_mask, size=(mh, mw), mode="bilinear", align_corners=False)
+        fg_prob = torch.sigmoid(bg_fg_mask)
+    bg_fg_logits = torch.cat([torch.log(1 - fg_prob + 1e-7), torch.log(fg_prob + 1e-7)], 1)
+    aux = {"bg_fg_logits": bg_fg_logits, "target_nontarget_logits": logits[:, 1:3].clone(), "fg_prob": fg_prob,
+           "pretrained_bg_fg_mask": bg_fg_mask, "attention": attention}
+    return logits, aux
+
+
+def uses_refined_head(cfg: PathConfig) -> bool:
+    """rgb.py:683-689: any refinement flag selects RefinedHierarchicalSegmentationHead (+ feature_combiner)."""
+    return bool(cfg.use_contour_detection or cfg.use_distance_transform)
+
+
+@torch.no_grad()
+def forward_standard(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig):
+    """HierarchicalRGBSegmentationModel.forward (rgb.py:410-439; ctor :300-408): DynamicRoIAlign(aligned=False) ->
+    RGBFeatureExtractor (rgb.py:221-295) -> HierarchicalSegmentationHeadUNetV2 (..._unet.py:670-845: LayerNorm2d + ReLU
+    hard-coded, EnhancedUNet 96/3) or the refined head (normalisation from the kwargs).  The reference forwards no activation
+    kwarg to any sub-module of this model, so every activation is ReLU."""
+    from dataclasses import replace
+    rh, rw = cfg.roi_size
+    sh, sw = cfg.spatial_scale
+    ecfg = replace(cfg, activation_function="relu", hierarchical_base_channels=96, hierarchical_depth=3)
+    x = roi_align(images, rois, rh, rw, sh, sw, False)
+    roi_rgb = x
+    p = "rgb_extractor.features."
+    for i, base in enumerate((0, 3, 7, 11)):
+        x = act_rgb(norm(sd, f"{p}{base + 1}.", conv(sd, f"{p}{base}.", x, 1), ecfg), ecfg)
+        if i >= 1:
+            x = residual_block(sd, f"{p}{base + 3}.", x, ecfg, act_rgb)
+    if uses_refined_head(cfg):
+        logits, aux = refined_head(sd, "segmentation_head.", x, ecfg)
+    else:
+        logits, aux = base_head(sd, "segmentation_head.", x, replace(ecfg, normalization_type="layernorm2d"))
+        aux.pop("shared_features")
+    aux["roi_patches"] = roi_rgb
+    return logits, aux
+
+
 @torch.no_grad()
 def forward(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig, full_image_logits: Tensor = None):
     """HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet.forward (rgb.py:729-774)."""
+    if not cfg.use_pretrained_unet:
+        return forward_standard(sd, images, rois, cfg)
     if full_image_logits is None:
         full_image_logits = pretrained_unet_logits(sd, images, cfg)
     rh, rw = cfg.roi_size
@@ -363,8 +437,11 @@ def forward(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig, full_image_lo
     roi_masks = roi_align(full_image_logits, rois, rh, rw, sh, sw, True)
     roi_rgb = roi_align(images, rois, rh, rw, sh, sw, True)
     feats = rgb_feature_extractor(sd, roi_rgb, cfg)
-    comb = conv(sd, "feature_combiner.", torch.cat([feats, roi_masks], 1), 0)
-    logits, aux = refined_head(sd, "segmentation_head.", comb, cfg)
+    if uses_refined_head(cfg):
+        comb = conv(sd, "feature_combiner.", torch.cat([feats, roi_masks], 1), 0)
+        logits, aux = refined_head(sd, "segmentation_head.", comb, cfg)
+    else:
+        logits, aux = guided_head(sd, "segmentation_head.", feats, roi_masks, cfg)
     aux["full_image_logits"] = full_image_logits
     aux["roi_features"] = roi_masks
     aux["roi_patches"] = roi_rgb

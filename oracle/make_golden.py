@@ -42,6 +42,25 @@ SMALL_CASES = {
     "small_b0_resize": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28)), (96, 128)),
 }
 
+# a13: no refinement flag -> PretrainedUNetGuidedSegmentationHead (rgb.py:715-727): the factory-default normalisation
+# (layernorm2d, no attention) and a batchnorm + attention variant
+GUIDED_CASES = {
+    "small_b0_guided_ln": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="layernorm2d",
+                                   use_attention_module=False, use_contour_detection=False, use_distance_transform=False), (96, 128)),
+    "small_b0_guided_bn_att": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28), use_attention_module=True,
+                                       use_contour_detection=False, use_distance_transform=False), (96, 128)),
+}
+# a13: use_pretrained_unet=False -> HierarchicalRGBSegmentationModel (rgb.py:298-439) with the V2 head (LayerNorm2d) or the
+# refined head (batchnorm, attention, contour + distance)
+STANDARD_CASES = {
+    "small_std_v2_ln": (headport.PathConfig(roi_size=(16, 12), mask_size=(32, 24), normalization_type="layernorm2d",
+                                            use_attention_module=False, use_contour_detection=False, use_distance_transform=False,
+                                            use_pretrained_unet=False), (96, 128)),
+    "small_std_refined_bn_att": (headport.PathConfig(roi_size=(16, 12), mask_size=(40, 28), normalization_type="batchnorm",
+                                                     use_attention_module=True, use_pretrained_unet=False), (96, 128)),
+}
+SMALL_CASES_ALL = {**SMALL_CASES, **GUIDED_CASES, **STANDARD_CASES}
+
 _FULL_KEYS = ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_mask",
               "distance_map", "roi_features", "roi_patches")
 
@@ -54,7 +73,8 @@ def _run_reference(cfg: headport.PathConfig, images, rois, seed=0, mode="stress"
     model = refload.build_reference_model(**cfg.factory_kwargs())
     sd = paramfill.fill_state_dict(model.state_dict(), seed=seed, mode=mode)
     model.load_state_dict(sd)
-    for ra in (model.roi_align_mask, model.roi_align_rgb):      # export_onnx_advanced.py:80-98 mutates these
+    aligners = (model.roi_align_mask, model.roi_align_rgb) if hasattr(model, "roi_align_mask") else (model.roi_align,)
+    for ra in aligners:      # export_onnx_advanced.py:80-98 mutates these
         ra.spatial_scale = cfg.spatial_scale
         ra.spatial_scale_h, ra.spatial_scale_w = cfg.spatial_scale
     with torch.no_grad():
@@ -105,6 +125,31 @@ def make_model_goldens():
           "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
 
 
+def make_guided_goldens():
+    """The guided-head variant; adds its key/shape tables to state_dict_keys.json without touching the other entries."""
+    path = os.path.join(GOLDEN, "state_dict_keys.json")
+    keys_json = json.load(open(path))
+    for name, (cfg, (h, w)) in {**GUIDED_CASES, **STANDARD_CASES}.items():
+        images = synth_images(11, 2, h, w)
+        rois = torch.cat([synth_rois(11, 2, 2), edge_rois(2)], 0)
+        model, sd, logits, aux = _run_reference(cfg, images, rois)
+        out = {"logits": _np(logits)}
+        if "full_image_logits" in aux:
+            out["full_image_logits_ch0"] = _np(aux["full_image_logits"][:, 0])
+        if "fg_attention" in aux:
+            out["fg_attention_sub"] = _np(aux["fg_attention"][:, ::8])
+        for k in ("bg_fg_logits", "target_nontarget_logits", "fg_prob", "pretrained_bg_fg_mask", "attention", "roi_features", "roi_patches",
+                  "bg_fg_logits_low", "contours", "distance_mask", "distance_map"):
+            if aux.get(k) is not None:
+                out[k] = _np(aux[k])
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **{k: v.astype(np.float32) for k, v in out.items()})
+        keys_json[name] = {k: list(v.shape) for k, v in sd.items()}
+        print(name, "logits", tuple(logits.shape), "absmax", float(logits.abs().max()),
+              "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist(), "aux", sorted(aux))
+    with open(path, "w") as f:
+        json.dump(keys_json, f)
+
+
 def make_default_init_golden():
     """BASELINE config 1 again, with PyTorch-default-initialisation statistics ("random-init weights")."""
     cfg = headport.PRESETS["b0"]
@@ -145,6 +190,8 @@ def main():
         make_model_goldens()
     if args.only in ("all", "model", "default"):
         make_default_init_golden()
+    if args.only in ("all", "guided"):
+        make_guided_goldens()
     if args.only in ("all", "post"):
         from . import make_golden_post
         make_golden_post.make_post_goldens(GOLDEN)

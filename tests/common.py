@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from oracle import headport, paramfill
-from oracle.make_golden import SMALL_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
+from oracle.make_golden import GUIDED_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -21,7 +21,7 @@ def golden_keys():
 
 
 def small_case_inputs(name):
-    cfg, (h, w) = SMALL_CASES[name]
+    cfg, (h, w) = SMALL_CASES_ALL[name]
     images = synth_images(11, 2, h, w)
     rois = torch.cat([synth_rois(11, 2, 2), edge_rois(2)], 0)
     return cfg, images, rois
@@ -55,7 +55,7 @@ def shapes_for_case(name):
     keys = golden_keys()
     if name in keys:
         return keys[name]
-    cfg = SMALL_CASES[name][0]
+    cfg = SMALL_CASES_ALL[name][0]
     for pname, p in headport.PRESETS.items():
         if (p.encoder_name, p.hierarchical_base_channels, p.hierarchical_depth) == \
                 (cfg.encoder_name, cfg.hierarchical_base_channels, cfg.hierarchical_depth):

@@ -66,6 +66,50 @@ def test_model_matches_reference_golden_small(name):
                         "distance_mask", "distance_map", "full_image_logits", "roi_features", "roi_patches"}   # rgb.py:767-772
 
 
+@pytest.mark.parametrize("name", list(common.GUIDED_CASES))
+def test_guided_head_variant_matches_reference_golden(name):
+    """a13: no refinement flag -> PretrainedUNetGuidedSegmentationHead (rgb.py:43-218, :715-727), incl. the factory-default
+    LayerNorm2d normalisation."""
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    m = build(cfg, common.shapes_for_case(name))
+    logits, aux = m(images.cuda(), rois.cuda())
+    check(logits, g["logits"], "logits")
+    for k in ("bg_fg_logits", "target_nontarget_logits", "fg_prob", "pretrained_bg_fg_mask", "roi_features", "roi_patches"):
+        check(aux[k], g[k], k)
+    if cfg.use_attention_module:
+        check(aux["attention"], g["attention"], "attention")
+    else:
+        assert aux["attention"] is None
+    assert set(aux) == {"bg_fg_logits", "target_nontarget_logits", "fg_prob", "pretrained_bg_fg_mask", "attention", "full_image_logits",
+                        "roi_features", "roi_patches"}                  # rgb.py:207-213, 767-772
+    # chunked ROI schedule keeps the variant's outputs
+    m.max_rois_per_pass = 4
+    logits2, aux2 = m(images.cuda(), rois.cuda())
+    assert l2_rel(logits2.cpu(), logits.cpu()) < 2e-3 and aux2["target_nontarget_logits"].shape == aux["target_nontarget_logits"].shape
+
+
+@pytest.mark.parametrize("name", list(common.STANDARD_CASES))
+def test_standard_model_variant_matches_reference_golden(name):
+    """a13: use_pretrained_unet=False -> HierarchicalRGBSegmentationModel (rgb.py:298-439): RoIAlign(aligned=False),
+    RGBFeatureExtractor, HierarchicalSegmentationHeadUNetV2 (LayerNorm2d hard-coded) or the refined head."""
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    m = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    assert type(m).__name__ == "HierarchicalRGBSegmentationModel" and m.roi_align.aligned is False
+    m.load_state_dict(common.procedural_state(common.shapes_for_case(name)))
+    m = m.to("cuda")
+    logits, aux = m(images.cuda(), rois.cuda())
+    check(logits, g["logits"], "logits")
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= 0.998
+    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention")
+    keys = [k for k in g if k not in ("logits", "fg_attention_sub")]
+    for k in keys:
+        tol = dict(l2=1e-2, mx=3e-2) if k == "distance_mask" else {}
+        check(aux[k], g[k], k, **tol)
+    assert set(aux) == set(keys) | {"fg_attention"} | ({"shared_features"} if headport.uses_refined_head(cfg) else set())
+
+
 def test_model_matches_reference_golden_config1():
     """BASELINE.json configs[0]: B0 std, 2x3x480x640, 8 ROIs, 64x48 -> 128x96."""
     cfg, images, rois = common.cfg1_inputs()

@@ -23,6 +23,33 @@ def test_state_dict_keys_and_shapes_match_reference(preset):
     assert got == want
 
 
+@pytest.mark.parametrize("name", list(common.GUIDED_CASES))
+def test_guided_variant_state_dict_matches_reference(name):
+    cfg = common.GUIDED_CASES[name][0]
+    model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    want = common.golden_keys()[name]
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert got == want and list(got) == list(want)
+    assert model.segmentation_head.final_classifier[-1].bias.tolist() == [0.0, 0.0, -0.5]      # rgb.py:117-123
+    assert not hasattr(model, "feature_combiner")
+
+
+@pytest.mark.parametrize("name", list(common.STANDARD_CASES))
+def test_standard_variant_state_dict_matches_reference(name):
+    cfg = common.STANDARD_CASES[name][0]
+    model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    want = common.golden_keys()[name]
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert got == want and list(got) == list(want)
+    assert model.roi_align.aligned is False and model.roi_align.spatial_scale == 640.0          # rgb.py:404-408
+
+
+def test_roi_level_unet_variant_is_unconstructible_like_the_reference():
+    kw = dict(headport.PRESETS["b0"].factory_kwargs(), use_full_image_unet=False)
+    with pytest.raises(NotImplementedError):     # the reference raises NameError at rgb.py:497
+        his.create_rgb_hierarchical_model(**kw)
+
+
 def test_reference_checkpoint_roundtrip_and_pinned_constants():
     cfg = headport.PRESETS["b0"]
     model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())

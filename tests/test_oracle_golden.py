@@ -7,7 +7,7 @@ from oracle import headport
 from tests import common
 
 def _state(name):
-    cfg = common.SMALL_CASES[name][0] if name in common.SMALL_CASES else headport.PRESETS["b0"]
+    cfg = common.SMALL_CASES_ALL[name][0] if name in common.SMALL_CASES_ALL else headport.PRESETS["b0"]
     return common.procedural_state(common.shapes_for_case(name), weights_path=cfg.pretrained_weights_path)
 
 
@@ -26,6 +26,35 @@ def test_port_matches_reference_small(name):
     for d in (1, 2):   # MaskDilationModule applied to the *golden* logits -> thresholds see identical inputs
         out = headport.mask_dilation(g["logits"], d)
         assert torch.equal(out, g[f"dilated{d}"])
+
+
+@pytest.mark.parametrize("name", list(common.GUIDED_CASES))
+def test_guided_head_port_matches_reference(name):
+    """a13: PretrainedUNetGuidedSegmentationHead (rgb.py:43-218), the head the factory builds with no refinement flag."""
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    logits, aux = headport.forward(_state(name), images, rois, cfg)
+    assert common.rel_err(logits, g["logits"]) < 2e-5
+    for k in ("bg_fg_logits", "target_nontarget_logits", "fg_prob", "pretrained_bg_fg_mask", "roi_features", "roi_patches"):
+        assert common.rel_err(aux[k], g[k]) < 5e-5, k
+    if cfg.use_attention_module:
+        assert common.rel_err(aux["attention"], g["attention"]) < 5e-5
+    else:
+        assert aux["attention"] is None and "attention" not in g
+
+
+@pytest.mark.parametrize("name", list(common.STANDARD_CASES))
+def test_standard_model_port_matches_reference(name):
+    """a13: HierarchicalRGBSegmentationModel (rgb.py:298-439) + HierarchicalSegmentationHeadUNetV2 (..._unet.py:670-845)."""
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    logits, aux = headport.forward(_state(name), images, rois, cfg)
+    assert common.rel_err(logits, g["logits"]) < 2e-5
+    assert common.rel_err(aux["fg_attention"][:, ::8], g["fg_attention_sub"]) < 2e-5
+    keys = [k for k in g if k not in ("logits", "fg_attention_sub")]
+    assert set(keys) | {"fg_attention"} | ({"shared_features"} if headport.uses_refined_head(cfg) else set()) == set(aux)
+    for k in keys:
+        assert common.rel_err(aux[k], g[k]) < 5e-5, k
 
 
 def test_port_matches_reference_cfg1():
