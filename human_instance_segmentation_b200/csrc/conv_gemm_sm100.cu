@@ -47,6 +47,15 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 48;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarrierBytes = 1024;
+// Halo mode (3x3 convs): the A operand of a tile is the (bh+2) x (bw+2) input window, loaded ONCE per K block by two
+// cp.async producer warps into an un-swizzled K-major layout [8-channel plane][halo row][halo col][16 B]; the nine filter taps
+// are nine start addresses into that window (8-row core-matrix groups = tile rows, SBO = one halo row).  The 9x re-read of A
+// through L2 -- the bound of every layer with Cout < ~192 (L2 serves ~42 B/clk/SM) -- disappears.
+constexpr int kHaloBw = 8, kHaloBh = 16;               // tile = 8 x 16 output pixels (row m = y*8 + x)
+constexpr int kHaloW = kHaloBw + 2, kHaloH = kHaloBh + 2, kHaloPix = kHaloW * kHaloH;
+constexpr int kPlaneBytes = (kHaloPix + 1) * 16;       // 2896: +16 B so the planes of one pixel fall in distinct 16-byte bank groups
+constexpr int kAProducerThreads = 64;                  // warps 2 and 3
+constexpr int kMaxAStages = 24, kMaxBStages = 16;
 
 // K-block width BK (fp16 elements) selects the shared-memory swizzle: one row of the operand tile is BK*2 bytes.
 template <int BK> struct KCfg {
@@ -73,6 +82,18 @@ struct ConvGemmParams {
   int num_work;
   int b_img_rows;       // rows to skip in B per image (0: shared weights; >0: per-image weights, e.g. SE gate folded in)
   int stages, stage_bytes;   // smem ring: stage = A tile (128 x BK) + B tile (block_n x BK), rounded up to 1 KB
+                             // (halo mode: the B ring; stage = taps_per_b weight tiles)
+  // halo mode
+  const __half* in; long long in_sn; int in_cs, cin;   // raw NHWC input (element strides) for the cp.async producers
+  int a_stages, a_stage_bytes, taps_per_b;
+  // direct (register -> global) epilogue path for clipped chunks / tiles (non-transposed layers)
+  __half* out; const __half* res; int out_cs, res_cs, direct_ok;
+  int n_acc, acc_stride; // TMEM accumulator ring: n_acc (even, <= 8) buffers of acc_stride columns
+  int taps_per_box;     // halo mode: taps per weight TMA box (taps_per_b / taps_per_box boxes fill one B stage)
+  int b_resident;       // halo mode: the whole weight set stays in shared memory (loaded once per CTA)
+  float inv_tiles_x, inv_tiles_y;   // fast work decode (num_work < 2^21, single N tile, no groups)
+  int fast_decode;
+  int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
   //   SIGMOID: s = 1/(1+exp(-act_beta*y)); y = act_mul_x ? y*s : s   (sigmoid / silu / swish(beta))
@@ -157,6 +178,23 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
   return d;
 }
 
+// K-major un-swizzled (INTERLEAVE) descriptor of the halo window: core matrix = 8 rows x 16 B, rows 16 B apart;
+// SBO = bytes between 8-row groups (one halo row), LBO = bytes between the two 8-channel planes of one K=16 step.
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(kPlaneBytes >> 4) << 16;
+  d |= (uint64_t)((kHaloW * 16) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n.
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
   uint32_t d = 0;
@@ -172,6 +210,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// accumulate form (enable-input-d = true) without the predicate set-up: all but the first MMA of a tile
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -213,6 +258,13 @@ struct WorkItem { int img, y0, x0, n_tile, group; };
 
 __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) {
   WorkItem it;
+  if (p.fast_decode) {   // exact for w < 2^21: |fl((w+.5)*inv) - (w+.5)/d| < .5/d
+    const int r = __float2int_rz(((float)w + 0.5f) * p.inv_tiles_x);      // w / tiles_x
+    const int tx = w - r * p.tiles_x;
+    const int im = __float2int_rz(((float)r + 0.5f) * p.inv_tiles_y);     // r / tiles_y
+    it.n_tile = 0; it.group = 0; it.img = im; it.y0 = (r - im * p.tiles_y) * p.bh; it.x0 = tx * p.bw;
+    return it;
+  }
   it.n_tile = w % p.n_tiles; w /= p.n_tiles;
   it.group = w % p.groups;   w /= p.groups;
   int tx = w % p.tiles_x;    w /= p.tiles_x;
@@ -224,7 +276,7 @@ __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) 
 // ------------------------------------------------------------------------------------ kernel
 enum { EPI_PLAIN = 0, EPI_TAIL = 1, EPI_AUX = 2 };
 
-template <int BK, int ACTC, int RES, int EPI>
+template <int BK, int ACTC, int RES, int EPI, bool HALO>
 __global__ void __launch_bounds__(kThreadsGemm, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
@@ -238,13 +290,18 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t staging_base = smem_base + kStages * p.stage_bytes;
   const uint32_t shift_base = staging_base + kNumStaging * kStagingBytes;
   const uint32_t bar_base = shift_base + kShiftBytes;
-  // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[4]; then the TMEM pointer
+  // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[4], the TMEM pointer, then (halo
+  // mode) afull[a_stages] aempty[a_stages]; the halo ring itself follows the barrier block
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  auto res_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 4 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 8);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 8 + a); };
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 16 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 20);
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + p.a_stages + s); };
+  const int n_acc = p.n_acc;
+  const uint32_t a_base = bar_base + kBarrierBytes;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to the aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,8 +315,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 8; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     for (int a = 0; a < 4; ++a) mbar_init(res_bar(a), 1);
+    if (HALO)
+      for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kAProducerThreads); mbar_init(aempty_bar(s), 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -275,7 +334,141 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  if (warp == 0) {
+  if (HALO) {
+    const int nblk = p.kblocks_per_tap;                  // K blocks of BK channels
+    const int tgroups = 9 / p.taps_per_b;                // B stages per K block
+    if (warp == 0) {
+      // ================================ halo mode: weight-tile TMA producer ================================
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t stage_tx = (uint32_t)p.taps_per_b * b_bytes;
+      if (p.b_resident) {       // every (K block, tap) weight tile once, all on full_bar(0)
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(0), (uint32_t)(nblk * 9) * b_bytes);
+          for (int cb = 0; cb < nblk; ++cb)
+            for (int tap = 0; tap < 9; tap += p.taps_per_box)
+              tma_load_2d(stage_base + (uint32_t)(cb * 9 + tap) * b_bytes, &tmB, full_bar(0), cb * BK, tap * p.cout_slab);
+        }
+        __syncwarp();
+      }
+      for (int w = blockIdx.x; w < p.num_work && !p.b_resident; w += gridDim.x) {
+        const WorkItem it = decode_work(p, w);
+        const int brow0 = it.n_tile * p.block_n + it.img * p.b_img_rows;
+        for (int cb = 0; cb < nblk; ++cb)
+          for (int tg = 0; tg < tgroups; ++tg) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (elect_one()) {
+              const uint32_t sb = stage_base + stage * p.stage_bytes;
+              if (p.debug & 4) mbar_arrive(full_bar(stage));
+              else {
+                mbar_expect_tx(full_bar(stage), stage_tx);
+                // a box spans taps_per_box taps (> 1 only with a single N tile, where the taps' weight rows are contiguous)
+                for (int t = 0; t < p.taps_per_b; t += p.taps_per_box)
+                  tma_load_2d(sb + (uint32_t)t * b_bytes, &tmB, full_bar(stage), cb * BK, brow0 + (tg * p.taps_per_b + t) * p.cout_slab);
+              }
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+      }
+    } else if (warp == 1) {
+      // ================================ halo mode: MMA issuer ================================
+      // One thread feeds the tensor pipe, so the loop is kept short: descriptors are a constant high word plus a 14-bit
+      // address that advances by adds, the K=16 steps of a block are unrolled, and a B stage carries up to nine taps.
+      const uint32_t idesc = make_idesc_f16(p.block_n);
+      const uint64_t adesc_hi = make_halo_desc(0), bdesc_hi = make_kmajor_desc<BK>(0);
+      const int T = p.taps_per_b, cin = p.cin, a_stages = p.a_stages;
+      const uint32_t b_tap_units = b_bytes >> 4, b_stage_units = (uint32_t)p.stage_bytes >> 4, a_stage_units = (uint32_t)p.a_stage_bytes >> 4;
+      const uint32_t a_units0 = a_base >> 4, b_units0 = stage_base >> 4;
+      int stage = 0, astage = 0; uint32_t phase = 0, aphase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t a_units = a_units0, b_units = b_units0;
+      if (p.b_resident) { mbar_wait(full_bar(0), 0); tc_fence_after(); }      // weights: loaded once, never released
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        for (int cb = 0; cb < nblk; ++cb) {
+          mbar_wait(afull_bar(astage), aphase);
+          fence_proxy_async();                 // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
+          tc_fence_after();
+          const int nk16 = min(BK / 16, (cin - cb * BK + 15) >> 4);
+          if (p.b_resident) b_units = b_units0 + (uint32_t)(cb * 9) * b_tap_units;
+          for (int tg = 0; tg < tgroups; ++tg) {
+            if (!p.b_resident) { mbar_wait(full_bar(stage), phase); tc_fence_after(); }
+            if (elect_one()) {
+              const int tap0 = tg * T;
+              const int dy0 = (tap0 * 11) >> 5;                       // tap0 / 3 for 0..8
+              uint32_t au = a_units + (uint32_t)(dy0 * kHaloW + (tap0 - dy0 * 3)), bu = b_units;
+              int dx = tap0 - dy0 * 3;
+              for (int t = 0; t < T; ++t) {
+                const uint64_t ad = adesc_hi | au, bd = bdesc_hi | bu;
+                if (!(p.debug & 8)) {
+                  umma_f16(d_tmem, ad, bd, idesc, (cb | tg | t) ? 1u : 0u);
+#pragma unroll
+                  for (int kk = 1; kk < BK / 16; ++kk)
+                    if (kk < nk16) umma_f16_acc(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
+                }
+                bu += b_tap_units; ++au;
+                if (++dx == 3) { dx = 0; au += kHaloW - 3; }
+              }
+              if (!p.b_resident) umma_commit(empty_bar(stage));
+              if (tg == tgroups - 1) {
+                umma_commit(aempty_bar(astage));
+                if (cb == nblk - 1) umma_commit(tfull_bar(acc));
+              }
+            }
+            __syncwarp();
+            if (!p.b_resident) {
+              b_units += b_stage_units;
+              if (++stage == kStages) { stage = 0; phase ^= 1; b_units = b_units0; }
+            } else {
+              b_units += (uint32_t)T * b_tap_units;
+            }
+          }
+          a_units += a_stage_units;
+          if (++astage == a_stages) { astage = 0; aphase ^= 1; a_units = a_units0; }
+        }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (warp < 4) {
+      // ================================ halo mode: cp.async producers of the input window ================================
+      constexpr int CL = BK / 8;                           // chunk lanes: the 16-byte pieces of one pixel in this K block
+      constexpr int PL = kAProducerThreads / CL;           // pixels in flight per pass
+      constexpr int QY = PL / kHaloW, QX = PL % kHaloW;    // window-coordinate step of one pass
+      const int ptid = threadIdx.x - 64;
+      const int c = ptid % CL, pl = ptid / CL;
+      const int hy_first = pl / kHaloW, hx_first = pl - hy_first * kHaloW;
+      const int row_elems = p.W * p.in_cs;
+      int astage = 0; uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const WorkItem it = decode_work(p, w);
+        const __half* img = p.in + (long long)it.img * p.in_sn;
+        const int gy0 = it.y0 - 1, gx0 = it.x0 - 1;
+        for (int cb = 0; cb < nblk; ++cb) {
+          mbar_wait(aempty_bar(astage), aphase ^ 1);
+          const int ch = cb * BK + c * 8;
+          const bool chok = ch < p.cin && !(p.debug & 2);
+          uint32_t dst = a_base + astage * p.a_stage_bytes + (uint32_t)c * kPlaneBytes + (uint32_t)pl * 16u;
+          // the address walks the window incrementally: no division, 32-bit element offsets inside the image
+          int hy = hy_first, hx = hx_first;
+          int off = (gy0 + hy) * row_elems + gx0 * p.in_cs + ch;       // element offset of window pixel (hy, 0)
+#pragma unroll 4
+          for (int px = pl; px < kHaloPix; px += PL) {
+            const bool ok = chok && (unsigned)(gy0 + hy) < (unsigned)p.H && (unsigned)(gx0 + hx) < (unsigned)p.W;
+            const __half* src = ok ? img + (off + hx * p.in_cs) : p.in;
+            cp_async16(dst, src, ok ? 16u : 0u);
+            dst += PL * 16u;
+            hx += QX; hy += QY; off += QY * row_elems;
+            if (hx >= kHaloW) { hx -= kHaloW; ++hy; off += row_elems; }
+          }
+          cp_async_arrive_noinc(afull_bar(astage));
+          if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+  }
+  if (!HALO && warp == 0) {
     // ================================ TMA producer (whole warp converged, one elected lane issues) ================================
     int stage = 0; uint32_t phase = 0;
     const int pad = p.ksize >> 1;
@@ -296,15 +489,15 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (++cb == p.kblocks_per_tap) { cb = 0; brow += p.cout_slab; if (++dx > pad) { dx = -pad; ++dy; } }
       }
     }
-  } else if (warp == 1) {
+  } else if (!HALO && warp == 1) {
     // ================================ MMA issuer (whole warp converged, one elected lane issues) ================================
     const uint32_t idesc = make_idesc_f16(p.block_n);
-    int stage = 0; uint32_t phase = 0; int iter = 0;
-    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++iter) {
-      const int acc = iter & 1; const uint32_t acc_phase = (iter >> 1) & 1;
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
       for (int k = 0; k < kiters; ++k) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -320,6 +513,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue (two groups of 4 warps, group g drains accumulator g) ================================
@@ -329,45 +523,54 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool issuer_warp = q == 0;            // first warp of the group issues the group's TMA traffic
     const int nchunks = (p.block_n + kChunkC - 1) / kChunkC;
     const uint32_t stg0 = staging_base + g * 2 * kStagingBytes;
-    const uint32_t acc_col = (uint32_t)(g * 256);
     uint32_t cc = 0;
-    int iter_g = 0;
-    for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += 2 * gridDim.x, ++iter_g) {
+    int acc = g; uint32_t acc_phase = 0;          // group g drains the accumulators of parity g (n_acc is even)
+    for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += 2 * gridDim.x) {
       const WorkItem it = decode_work(p, w);
-      const uint32_t acc_phase = iter_g & 1;
+      const uint32_t acc_col = (uint32_t)(acc * p.acc_stride);
       const CUtensorMap* tmO = it.group == 0 ? &tmO0 : it.group == 1 ? &tmO1 : it.group == 2 ? &tmO2 : &tmO3;
       const int chbase = it.n_tile * p.block_n;
       const float* shp = p.n_tiles == 1 ? s_shift : p.shift + chbase;
+      // A chunk goes through the swizzled staging buffer + TMA when its 32-channel x 128-pixel box lies fully inside the tensor.
+      // Clipped boxes (channel tail, image edge) take a far slower path inside the TMA unit (measured: a half-clipped store box
+      // costs ~20 full ones), so those chunks are read / written straight from registers, 16 bytes per 8 channels.
+      const bool tile_full = it.y0 + p.bh <= p.H && it.x0 + p.bw <= p.W;
+      const int ntma = !p.direct_ok ? nchunks : !tile_full ? 0 : min(nchunks, max(0, (p.cout - chbase) / kChunkC));
       if (RES && issuer_warp && elect_one()) {  // prefetch the first two residual chunks while the MMAs run
         tma_wait_read<0>();
-        for (int j = 0; j < 2 && j < nchunks; ++j) {
+        for (int j = 0; j < 2 && j < ntma; ++j) {
           const int b = (cc + j) & 1;
           mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
           tma_load_4d(stg0 + b * kStagingBytes, &tmR, res_bar(2 * g + b), chbase + j * kChunkC, it.x0, it.y0, it.img);
         }
       }
-      mbar_wait(tfull_bar(g), acc_phase);
+      mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       float tacc0 = 0.0f, tacc1 = 0.0f;
       constexpr bool TAIL = EPI == EPI_TAIL;
-      const bool store_main = !TAIL || p.store_main;
+      const bool store_main = (!TAIL || p.store_main) && !(p.debug & 1);
       const int py = it.y0 + te / p.bw, px = it.x0 + te % p.bw;
+      const bool inb = py < p.H && px < p.W;
+      const long long pix = ((long long)it.img * p.H + py) * p.W + px;
       float* aux_px = nullptr;
-      if (EPI == EPI_AUX && py < p.H && px < p.W) aux_px = p.aux_out + ((long long)it.img * p.cout * p.H + py) * p.W + px;
-      for (int j = 0; j < nchunks; ++j, ++cc) {
+      if (EPI == EPI_AUX && inb) aux_px = p.aux_out + ((long long)it.img * p.cout * p.H + py) * p.W + px;
+      for (int j = 0; j < nchunks; ++j) {
+        const bool direct = j >= ntma;
         const int b = cc & 1;
         const uint32_t stg = stg0 + b * kStagingBytes;
         const int cl0 = j * kChunkC;            // first channel of this chunk within the N tile
         const int ch0 = chbase + cl0;           // ... and within the layer
         const int ncol = min(kChunkC, p.block_n - cl0);   // valid accumulator columns in this chunk (16 or 32)
-        if ((!RES || j >= 2) && issuer_warp && elect_one()) {
-          tma_wait_read<1>();                    // the store that last read staging[b] has drained
-          if (RES) {
-            mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
-            tma_load_4d(stg, &tmR, res_bar(2 * g + b), ch0, it.x0, it.y0, it.img);
+        if (!direct) {
+          if ((!RES || j >= 2) && issuer_warp && elect_one()) {
+            tma_wait_read<1>();                    // the store that last read staging[b] has drained
+            if (RES) {
+              mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
+              tma_load_4d(stg, &tmR, res_bar(2 * g + b), ch0, it.x0, it.y0, it.img);
+            }
           }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         uint32_t v[kChunkC];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)cl0;
         if (ncol > 16) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
@@ -375,9 +578,9 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (j == nchunks - 1) {                  // accumulator fully read -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(g));
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (RES) mbar_wait(res_bar(2 * g + b), (cc >> 1) & 1);
+        if (RES && !direct) mbar_wait(res_bar(2 * g + b), (cc >> 1) & 1);
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
 #pragma unroll
         for (int i = 0; i < kChunkC / 8; ++i) {
@@ -386,7 +589,13 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ ((te >> 1) & 3)) << 4));   // SWIZZLE_64B
             float r[8];
             if (RES) {
-              const uint4 rv = *cell;
+              uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+              if (!direct) rv = *cell;
+              else if (inb && c + 8 <= p.cout) rv = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_cs + c));
+              else if (inb) {
+                __half* rh1 = reinterpret_cast<__half*>(&rv);
+                for (int e = 0; e < 8; ++e) if (c + e < p.cout) rh1[e] = p.res[pix * p.res_cs + c + e];
+              }
               const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(rh[e]); r[2 * e] = f.x; r[2 * e + 1] = f.y; }
@@ -416,11 +625,16 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               __half2 o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
-              *cell = *reinterpret_cast<uint4*>(o);
+              if (!direct) *cell = *reinterpret_cast<uint4*>(o);
+              else if (inb && c + 8 <= p.cout) *reinterpret_cast<uint4*>(p.out + pix * p.out_cs + c) = *reinterpret_cast<uint4*>(o);
+              else if (inb) {
+                const __half* oh = reinterpret_cast<const __half*>(o);
+                for (int e = 0; e < 8; ++e) if (c + e < p.cout) p.out[pix * p.out_cs + c + e] = oh[e];
+              }
             }
           }
         }
-        if (store_main) {
+        if (store_main && !direct) {
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           if (issuer_warp && elect_one()) {
@@ -428,6 +642,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tma_commit();
           }
         }
+        if (!direct) ++cc;
       }
       if (TAIL) {
         if (py < p.H && px < p.W) {
@@ -438,6 +653,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (p.tail_c > 1) dst[(long long)p.H * p.W] = o1;
         }
       }
+      acc += 2;
+      if (acc >= n_acc) { acc = g; acc_phase ^= 1; }
     }
     if (issuer_warp && elect_one()) tma_wait_all();
   }
@@ -453,33 +670,41 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 typedef void (*ConvGemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                                const CUtensorMap, const CUtensorMap, const ConvGemmParams);
 
-template <int BK, int ACTC>
+template <int BK, int ACTC, bool HALO>
 ConvGemmKernel pick_res(int res) {
-  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0, EPI_PLAIN> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1, EPI_PLAIN>
-                                                                            : conv_gemm_sm100_kernel<BK, ACTC, 2, EPI_PLAIN>;
+  return res == 0 ? conv_gemm_sm100_kernel<BK, ACTC, 0, EPI_PLAIN, HALO> : res == 1 ? conv_gemm_sm100_kernel<BK, ACTC, 1, EPI_PLAIN, HALO>
+                                                                                  : conv_gemm_sm100_kernel<BK, ACTC, 2, EPI_PLAIN, HALO>;
 }
-template <int BK>
+template <int BK, bool HALO>
 ConvGemmKernel pick_act(int actc, int res) {
-  return actc == 0 ? pick_res<BK, 0>(res) : actc == 1 ? pick_res<BK, 1>(res) : pick_res<BK, 2>(res);
+  return actc == 0 ? pick_res<BK, 0, HALO>(res) : actc == 1 ? pick_res<BK, 1, HALO>(res) : pick_res<BK, 2, HALO>(res);
 }
-ConvGemmKernel pick_kernel(int bk, int actc, int res) {
-  return bk == 64 ? pick_act<64>(actc, res) : bk == 32 ? pick_act<32>(actc, res) : pick_act<16>(actc, res);
+template <bool HALO>
+ConvGemmKernel pick_bk_kernel(int bk, int actc, int res) {
+  return bk == 64 ? pick_act<64, HALO>(actc, res) : bk == 32 ? pick_act<32, HALO>(actc, res) : pick_act<16, HALO>(actc, res);
+}
+ConvGemmKernel pick_kernel(int bk, int actc, int res, bool halo) {
+  return halo ? pick_bk_kernel<true>(bk, actc, res) : pick_bk_kernel<false>(bk, actc, res);
 }
 // fused-tail variants exist for the shapes that need them: clamp activations (none/relu), no residual or residual-add
-ConvGemmKernel pick_tail_kernel(int bk, int res) {
-  if (bk == 64) return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, EPI_TAIL> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, EPI_TAIL>;
-  if (bk == 32) return res == 0 ? conv_gemm_sm100_kernel<32, ACTC_CLAMP, 0, EPI_TAIL> : conv_gemm_sm100_kernel<32, ACTC_CLAMP, 1, EPI_TAIL>;
-  return res == 0 ? conv_gemm_sm100_kernel<16, ACTC_CLAMP, 0, EPI_TAIL> : conv_gemm_sm100_kernel<16, ACTC_CLAMP, 1, EPI_TAIL>;
+template <bool HALO>
+ConvGemmKernel pick_tail_h(int bk, int res) {
+  if (bk == 64) return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, EPI_TAIL, HALO> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, EPI_TAIL, HALO>;
+  if (bk == 32) return res == 0 ? conv_gemm_sm100_kernel<32, ACTC_CLAMP, 0, EPI_TAIL, HALO> : conv_gemm_sm100_kernel<32, ACTC_CLAMP, 1, EPI_TAIL, HALO>;
+  return res == 0 ? conv_gemm_sm100_kernel<16, ACTC_CLAMP, 0, EPI_TAIL, HALO> : conv_gemm_sm100_kernel<16, ACTC_CLAMP, 1, EPI_TAIL, HALO>;
 }
+ConvGemmKernel pick_tail_kernel(int bk, int res, bool halo) { return halo ? pick_tail_h<true>(bk, res) : pick_tail_h<false>(bk, res); }
 // fp32 NCHW export variants: BK = 64 layers only (the 256-channel trunk / gate layers whose outputs the reference returns)
-template <int ACTC>
+template <int ACTC, bool HALO>
 ConvGemmKernel pick_aux_res(int res) {
-  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_AUX> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_AUX>
-                                                                           : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_AUX>;
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_AUX, HALO> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_AUX, HALO>
+                                                                                 : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_AUX, HALO>;
 }
-ConvGemmKernel pick_aux_kernel(int actc, int res) {
-  return actc == 0 ? pick_aux_res<0>(res) : actc == 1 ? pick_aux_res<1>(res) : pick_aux_res<2>(res);
+template <bool HALO>
+ConvGemmKernel pick_aux_h(int actc, int res) {
+  return actc == 0 ? pick_aux_res<0, HALO>(res) : actc == 1 ? pick_aux_res<1, HALO>(res) : pick_aux_res<2, HALO>(res);
 }
+ConvGemmKernel pick_aux_kernel(int actc, int res, bool halo) { return halo ? pick_aux_h<true>(actc, res) : pick_aux_h<false>(actc, res); }
 int smem_for(int bk) { return bk == 64 ? KCfg<64>::kSmemBytes : bk == 32 ? KCfg<32>::kSmemBytes : KCfg<16>::kSmemBytes; }
 
 // ------------------------------------------------------------------------------------ host side
@@ -545,7 +770,7 @@ int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, i
 struct ConvGemmPlan {
   CUtensorMap tmA, tmB, tmO[4], tmR;
   ConvGemmParams p;
-  int grid, bk, smem, actc, res_mode, transposed, cin_pad;
+  int grid, bk, smem, actc, res_mode, transposed, cin_pad, halo;
   ConvGemmKernel kernel;
 };
 
@@ -592,34 +817,47 @@ int his_conv_gemm_create(void** out_plan,
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return his_set_error(HIS_ERR_NO_DEVICE, "no CUDA device");
     if (prop.major != 10) return his_set_error(HIS_ERR_UNSUPPORTED, "conv_gemm_sm100 needs a compute-capability 10.x device (B200)");
-    for (int bk = 16; bk <= 64; bk *= 2)
+    for (int h = 0; h < 2; ++h) {
+      for (int bk = 16; bk <= 64; bk *= 2)
+        for (int a = 0; a < 3; ++a)
+          for (int r = 0; r < 3; ++r)
+            if (cudaFuncSetAttribute(pick_kernel(bk, a, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
+              return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
+      for (int bk = 16; bk <= 64; bk *= 2)
+        for (int r = 0; r < 2; ++r)
+          if (cudaFuncSetAttribute(pick_tail_kernel(bk, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
+            return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
       for (int a = 0; a < 3; ++a)
         for (int r = 0; r < 3; ++r)
-          if (cudaFuncSetAttribute(pick_kernel(bk, a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
+          if (cudaFuncSetAttribute(pick_aux_kernel(a, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess)
             return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
-    for (int bk = 16; bk <= 64; bk *= 2)
-      for (int r = 0; r < 2; ++r)
-        if (cudaFuncSetAttribute(pick_tail_kernel(bk, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(bk)) != cudaSuccess)
-          return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
-    for (int a = 0; a < 3; ++a)
-      for (int r = 0; r < 3; ++r)
-        if (cudaFuncSetAttribute(pick_aux_kernel(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess)
-          return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
+    }
     g_num_sms = prop.multiProcessorCount;
   }
   ConvGemmPlan* pl = new ConvGemmPlan();
   memset(pl, 0, sizeof(*pl));
   ConvGemmParams& p = pl->p;
   p.n_img = n_img; p.H = H; p.W = W; p.ksize = ksize;
+  // halo mode: every 3x3 conv whose input slice is 16-byte addressable per 8-channel group (HIS_GEMM_HALO=0 disables it,
+  // HIS_GEMM_HALO_MAXN=n keeps the per-tap TMA path for wider N tiles)
+  int tn_tiles = 0, tblock_n = 0;
+  his_conv_gemm_tile_n(cout, &tn_tiles, &tblock_n);
+  int halo = ksize == 3 && !transposed && (cin % 8) == 0;
+  if (const char* e = getenv("HIS_GEMM_HALO")) halo = halo && atoi(e) != 0;
+  int halo_maxn = 128;   // measured: the per-tap TMA path is ahead again from N = 160 up (one tap per weight stage there)
+  if (const char* e = getenv("HIS_GEMM_HALO_MAXN")) halo_maxn = atoi(e);
+  halo = halo && tblock_n <= halo_maxn;
+  pl->halo = halo;
   // pick the 128-pixel rectangle with the least padded area
   long long best = -1;
-  for (int bw = 1; bw <= 128; bw <<= 1) {
+  if (halo) { p.bw = kHaloBw; p.bh = kHaloBh; best = 0; }
+  for (int bw = 1; bw <= 128 && !halo; bw <<= 1) {
     int bh = 128 / bw;
     long long area = (long long)his_div_up(W, bw) * bw * his_div_up(H, bh) * bh;
     if (best < 0 || area < best || (area == best && bw >= 8 && bw <= 32)) { best = area; p.bw = bw; p.bh = bh; }
   }
   p.tiles_x = his_div_up(W, p.bw); p.tiles_y = his_div_up(H, p.bh);
-  const int bk = pick_bk(cin);
+  const int bk = halo ? (cin > 32 ? 64 : cin > 16 ? 32 : 16) : pick_bk(cin);   // halo mode skips the MMAs of an all-padding K=16 step
   pl->bk = bk;
   p.kblocks_per_tap = his_div_up(cin, bk);
   his_conv_gemm_tile_n(cout, &p.n_tiles, &p.block_n);
@@ -638,19 +876,64 @@ int his_conv_gemm_create(void** out_plan,
     default: delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown activation code");
   }
   if (res_mode < 0 || res_mode > 2) { delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown res_mode"); }
-  pl->kernel = pick_kernel(bk, actc, res_mode);
+  pl->kernel = pick_kernel(bk, actc, res_mode, halo);
   pl->smem = smem_for(bk);
-  p.stage_bytes = (kBlockM * bk * 2 + p.block_n * bk * 2 + 1023) / 1024 * 1024;
-  p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
-  if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
+  p.in = (const __half*)in; p.in_sn = (long long)H * W * in_cs; p.in_cs = in_cs; p.cin = cin;
+  p.a_stages = 0; p.a_stage_bytes = 0; p.taps_per_b = 1; p.taps_per_box = 1;
+  p.out = (__half*)out; p.out_cs = out_cs; p.res = (const __half*)res; p.res_cs = res_cs; p.direct_ok = transposed ? 0 : 1;
+  if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok && atoi(e) != 0;
+  p.debug = 0;
+  if (const char* e = getenv("HIS_GEMM_DEBUG")) p.debug = atoi(e);
+  // TMEM accumulator ring: as many buffers as the 512 columns hold (even, <= 8) so that short tiles are not paced by
+  // the MMA -> epilogue -> MMA hand-shake latency
+  p.acc_stride = (p.block_n + 31) / 32 * 32;
+  p.n_acc = kTmemCols / p.acc_stride;
+  if (p.n_acc > 8) p.n_acc = 8;
+  p.n_acc &= ~1;
+  if (const char* e = getenv("HIS_GEMM_NACC")) { int v = atoi(e) & ~1; if (v >= 2 && v <= p.n_acc) p.n_acc = v; }
+  p.fast_decode = (p.n_tiles == 1 && p.groups == 1 && p.num_work < (1 << 21)) ? 1 : 0;
+  p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
+  if (halo) {
+    // B ring stage = taps_per_b weight tiles (block_n x BK); A ring stage = BK/8 planes of the 10 x 18 window
+    // every barrier round trip of a B stage costs the issuing thread ~300 ns, so a stage carries as many taps as 48 KB hold
+    const int tap_bytes = p.block_n * bk * 2;
+    p.taps_per_b = 9 * tap_bytes <= 48 * 1024 ? 9 : 3 * tap_bytes <= 48 * 1024 ? 3 : 1;
+    if (const char* e = getenv("HIS_GEMM_TAPS")) { int v = atoi(e); if (v == 1 || v == 3 || v == 9) p.taps_per_b = v; }
+    p.taps_per_box = (p.n_tiles == 1 && p.taps_per_b * p.block_n <= 256) ? p.taps_per_b : 1;
+    p.stage_bytes = (p.taps_per_b * tap_bytes + 1023) / 1024 * 1024;
+    p.a_stage_bytes = (bk / 8) * kPlaneBytes;
+    const int budget = KCfg<64>::kRingBytes;
+    int a_st = p.a_stage_bytes >= 16 * 1024 ? 2 : (budget / 3) / p.a_stage_bytes;
+    if (a_st > kMaxAStages) a_st = kMaxAStages;
+    if (a_st < 2) a_st = 2;
+    if (const char* e = getenv("HIS_GEMM_ASTAGES")) { int v = atoi(e); if (v >= 1 && v <= kMaxAStages) a_st = v; }
+    int b_st = (budget - a_st * p.a_stage_bytes) / p.stage_bytes;
+    if (b_st > kMaxBStages) b_st = kMaxBStages;
+    if (b_st < 2) { delete pl; return his_set_error(HIS_ERR_UNSUPPORTED, "conv_gemm halo mode: shared memory budget"); }
+    p.a_stages = a_st; p.stages = b_st;
+    // weight-resident mode: the whole [K block][tap] weight set fits next to a deep halo ring -> loaded once per CTA
+    p.b_resident = 0;
+    const int res_bytes = (p.kblocks_per_tap * 9 * p.block_n * bk * 2 + 1023) / 1024 * 1024;
+    int want_res = p.n_tiles == 1 && res_bytes <= 96 * 1024;
+    if (const char* e = getenv("HIS_GEMM_BRES")) want_res = want_res && atoi(e) != 0;
+    if (want_res) {
+      int a2 = (budget - res_bytes) / p.a_stage_bytes;
+      if (a2 > kMaxAStages) a2 = kMaxAStages;
+      if (a2 >= 2) { p.b_resident = 1; p.stages = 1; p.stage_bytes = res_bytes; p.a_stages = a2; p.taps_per_b = 9; }
+    }
+  } else {
+    p.stage_bytes = (kBlockM * bk * 2 + p.block_n * bk * 2 + 1023) / 1024 * 1024;
+    p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
+  }
   pl->actc = actc; pl->res_mode = res_mode; pl->transposed = transposed; pl->cin_pad = cin_pad;
   p.tail_c = 0; p.store_main = 1; p.aux_out = nullptr; p.cout = cout;
   p.shift = shift;
   int taps = ksize * ksize;
   int rc;
   if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, bk, p.bw, p.bh))) { delete pl; return rc; }
-  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, p.block_n, bk))) { delete pl; return rc; }
+  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, (halo ? p.taps_per_box : 1) * p.block_n, bk))) { delete pl; return rc; }
   if (!transposed) {
     if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, kChunkC, p.bw, p.bh))) { delete pl; return rc; }
     pl->tmO[1] = pl->tmO[2] = pl->tmO[3] = pl->tmO[0];
@@ -680,7 +963,7 @@ int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_tail: needs a single N tile, none/relu activation, no MUL operand, not transposed");
   pl->p.tail_w = tail_w; pl->p.tail_b0 = tail_b0; pl->p.tail_b1 = tail_b1; pl->p.tail_c = tail_c; pl->p.tail_sigmoid = tail_sigmoid;
   pl->p.tail_out = tail_out; pl->p.store_main = store_main;
-  pl->kernel = pick_tail_kernel(pl->bk, pl->res_mode);
+  pl->kernel = pick_tail_kernel(pl->bk, pl->res_mode, pl->halo);
   return HIS_OK;
 }
 
@@ -688,6 +971,7 @@ int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image) 
   if (!plan || !w_packed_per_image) return his_set_error(HIS_ERR_INVALID_ARG, "set_image_weights: null pointer");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
   ConvGemmParams& p = pl->p;
+  if (pl->halo) return his_set_error(HIS_ERR_UNSUPPORTED, "set_image_weights: 1x1 / transposed layers only");
   const long long rows = (long long)p.groups * p.ksize * p.ksize * p.cout_slab;
   if (rows * p.n_img >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "set_image_weights: too many weight rows");
   int rc = encode_weight_map(&pl->tmB, w_packed_per_image, pl->cin_pad, rows * p.n_img, p.block_n, pl->bk);
@@ -702,7 +986,7 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   if (pl->bk != 64 || pl->transposed || pl->p.tail_c)
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_aux: needs a 64-wide K block (Cin >= 64), not transposed, no fused tail");
   pl->p.aux_out = aux_out;
-  pl->kernel = pick_aux_kernel(pl->actc, pl->res_mode);
+  pl->kernel = pick_aux_kernel(pl->actc, pl->res_mode, pl->halo);
   return HIS_OK;
 }
 

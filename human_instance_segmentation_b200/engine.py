@@ -248,16 +248,18 @@ def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False, 
         w = w * (sc.view(1, -1, 1, 1) if transposed else sc.view(-1, 1, 1, 1))
         if float(w.abs().max()) > 6.0e4:
             raise _lib.HisError("folded conv*BatchNorm weight exceeds the fp16 range (|w*gamma/sqrt(var+eps)| > 6e4)")
+    # K is zero-padded to a multiple of 64 so that every weight TMA box lies inside the tensor (a clipped box takes a far
+    # slower path through the TMA unit)
     if transposed:
         cin, cout = w.shape[0], w.shape[1]
-        cin_pad = round_up(cin, 8)
+        cin_pad = round_up(cin, 64)
         out = torch.zeros(4, 1, cout_slab, cin_pad, dtype=torch.float16)
         for dy in range(2):
             for dx in range(2):
                 out[dy * 2 + dx, 0, :cout, :cin] = w[:, :, dy, dx].t().half()
         return out.contiguous(), cin_pad
     cout, cin, kh, kw = w.shape
-    cin_pad = round_up(cin, 8)
+    cin_pad = round_up(cin, 64)
     out = torch.zeros(1, kh * kw, cout_slab, cin_pad, dtype=torch.float16)
     out[0, :, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).half()
     return out.contiguous(), cin_pad

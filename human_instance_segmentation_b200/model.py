@@ -553,7 +553,7 @@ class _BuiltPlan:
                 proj = blk.conv_pwl if blk.kind == "ir" else blk.conv_pw
                 nt, bn = ctypes.c_int(), ctypes.c_int()
                 L.his_conv_gemm_tile_n(proj.weight.shape[0], ctypes.byref(nt), ctypes.byref(bn))
-                need = max(need, B * nt.value * bn.value * round_up(blk.mid, 8))
+                need = max(need, B * nt.value * bn.value * round_up(blk.mid, 64))
         self._gated_w = torch.empty(max(need, 8), dtype=torch.float16, device=self.dev)
         p.keep.append(self._gated_w)
         for si, stage in enumerate(enc.blocks):

@@ -95,6 +95,12 @@ CASES = [
     dict(n=2, h=15, w=20, cin=40, cout=240, k=1, act=2),                     # BK=16, 3 K blocks
     dict(n=1, h=60, w=80, cin=96, cout=32, k=3, out_slice=(64, 32)),         # BK=32, 3 blocks per tap
     dict(n=2, h=30, w=40, cin=144, cout=24, k=1, act=0, res_mode=RES_ADD),   # MBConv project + skip, N=32 tile with 24 valid
+    # halo mode (3x3): window loaded once per K block by cp.async, nine taps = nine descriptor offsets
+    dict(n=3, h=80, w=60, cin=72, cout=72, k=3, res_mode=RES_ADD, out_slice=(144, 72)),   # clipped tiles + channel tail -> direct epilogue
+    dict(n=2, h=33, w=21, cin=24, cout=40, k=3, act=2),                      # BK=32 with one half-empty K=16 step; ragged image
+    dict(n=2, h=16, w=8, cin=320, cout=16, k=3, in_slice=(384, 64)),         # 5 K blocks, nine taps per weight stage, input slice
+    dict(n=1, h=128, w=96, cin=128, cout=128, k=3, res_mode=RES_MUL, act=3),  # mask-resolution layer, gate operand
+    dict(n=1, h=17, w=9, cin=8, cout=304, k=3),                               # Cin = 8 (one real plane), 2 N tiles
 ]
 
 

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_conv_gemm.py -x -q > gpurun_out/s4_gemm_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s4_gemm_tests.log
+tail -15 gpurun_out/s4_gemm_tests.log
+grep -q "rc=0" gpurun_out/s4_gemm_tests.log || exit 1
+echo "--- halo on"; timeout 120 python tools/exp_cin72.py 2>&1 | tee gpurun_out/s4_exp_halo1.log
+echo "--- halo on"; timeout 200 python tools/bench_gemm.py 2>&1 | tee gpurun_out/s4_sweep_halo1.log
+echo "--- halo off"; HIS_GEMM_HALO=0 timeout 200 python tools/bench_gemm.py 2>&1 | tee gpurun_out/s4_sweep_halo0.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s4_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s4_tests.log
+tail -5 gpurun_out/s4_tests.log
