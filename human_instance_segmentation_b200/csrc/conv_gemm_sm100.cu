@@ -434,32 +434,35 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // ================================ halo mode: cp.async producers of the input window ================================
       constexpr int CL = BK / 8;                           // chunk lanes: the 16-byte pieces of one pixel in this K block
       constexpr int PL = kAProducerThreads / CL;           // pixels in flight per pass
-      constexpr int QY = PL / kHaloW, QX = PL % kHaloW;    // window-coordinate step of one pass
+      constexpr int NIT = (kHaloPix + PL - 1) / PL;        // passes per stage (6 / 12 / 23)
       const int ptid = threadIdx.x - 64;
       const int c = ptid % CL, pl = ptid / CL;
-      const int hy_first = pl / kHaloW, hx_first = pl - hy_first * kHaloW;
-      const int row_elems = p.W * p.in_cs;
+      // per-thread tables, tile independent: window coordinates of the thread's pixels and their element offsets; the loop
+      // below is fully unrolled so they live in registers and the passes are independent instructions streams
+      int rel[NIT], hyx[NIT];
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const int px = pl + k * PL;
+        const int hy = px / kHaloW, hx = px - hy * kHaloW;
+        rel[k] = hy * p.W * p.in_cs + hx * p.in_cs;
+        hyx[k] = px < kHaloPix ? ((hy << 16) | hx) : (0x4000 << 16);     // beyond the window: never valid
+      }
       int astage = 0; uint32_t aphase = 0;
       for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
         const WorkItem it = decode_work(p, w);
-        const __half* img = p.in + (long long)it.img * p.in_sn;
         const int gy0 = it.y0 - 1, gx0 = it.x0 - 1;
+        const __half* org = p.in + (long long)it.img * p.in_sn + ((long long)gy0 * p.W + gx0) * p.in_cs;   // window origin (may lie outside)
         for (int cb = 0; cb < nblk; ++cb) {
           mbar_wait(aempty_bar(astage), aphase ^ 1);
           const int ch = cb * BK + c * 8;
           const bool chok = ch < p.cin && !(p.debug & 2);
-          uint32_t dst = a_base + astage * p.a_stage_bytes + (uint32_t)c * kPlaneBytes + (uint32_t)pl * 16u;
-          // the address walks the window incrementally: no division, 32-bit element offsets inside the image
-          int hy = hy_first, hx = hx_first;
-          int off = (gy0 + hy) * row_elems + gx0 * p.in_cs + ch;       // element offset of window pixel (hy, 0)
-#pragma unroll 4
-          for (int px = pl; px < kHaloPix; px += PL) {
-            const bool ok = chok && (unsigned)(gy0 + hy) < (unsigned)p.H && (unsigned)(gx0 + hx) < (unsigned)p.W;
-            const __half* src = ok ? img + (off + hx * p.in_cs) : p.in;
-            cp_async16(dst, src, ok ? 16u : 0u);
-            dst += PL * 16u;
-            hx += QX; hy += QY; off += QY * row_elems;
-            if (hx >= kHaloW) { hx -= kHaloW; ++hy; off += row_elems; }
+          const uint32_t dst = a_base + astage * p.a_stage_bytes + (uint32_t)c * kPlaneBytes + (uint32_t)pl * 16u;
+          const __half* orgc = org + ch;
+#pragma unroll
+          for (int k = 0; k < NIT; ++k) {
+            const bool ok = chok && (unsigned)(gy0 + (hyx[k] >> 16)) < (unsigned)p.H && (unsigned)(gx0 + (hyx[k] & 0xffff)) < (unsigned)p.W;
+            if (k * PL + PL <= kHaloPix || pl + k * PL < kHaloPix)
+              cp_async16(dst + (uint32_t)(k * PL) * 16u, ok ? orgc + rel[k] : p.in, ok ? 16u : 0u);
           }
           cp_async_arrive_noinc(afull_bar(astage));
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
@@ -535,7 +538,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // Clipped boxes (channel tail, image edge) take a far slower path inside the TMA unit (measured: a half-clipped store box
       // costs ~20 full ones), so those chunks are read / written straight from registers, 16 bytes per 8 channels.
       const bool tile_full = it.y0 + p.bh <= p.H && it.x0 + p.bw <= p.W;
-      const int ntma = !p.direct_ok ? nchunks : !tile_full ? 0 : min(nchunks, max(0, (p.cout - chbase) / kChunkC));
+      const int ntma = !p.direct_ok ? nchunks : (!tile_full && p.direct_ok > 1) ? 0 : min(nchunks, max(0, (p.cout - chbase) / kChunkC));
       if (RES && issuer_warp && elect_one()) {  // prefetch the first two residual chunks while the MMAs run
         tma_wait_read<0>();
         for (int j = 0; j < 2 && j < ntma; ++j) {
@@ -881,7 +884,7 @@ int his_conv_gemm_create(void** out_plan,
   p.in = (const __half*)in; p.in_sn = (long long)H * W * in_cs; p.in_cs = in_cs; p.cin = cin;
   p.a_stages = 0; p.a_stage_bytes = 0; p.taps_per_b = 1; p.taps_per_box = 1;
   p.out = (__half*)out; p.out_cs = out_cs; p.res = (const __half*)res; p.res_cs = res_cs; p.direct_ok = transposed ? 0 : 1;
-  if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok && atoi(e) != 0;
+  if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok ? atoi(e) : 0;   // 0 never, 1 channel-clipped chunks, 2 + clipped tiles
   p.debug = 0;
   if (const char* e = getenv("HIS_GEMM_DEBUG")) p.debug = atoi(e);
   // TMEM accumulator ring: as many buffers as the 512 columns hold (even, <= 8) so that short tiles are not paced by
