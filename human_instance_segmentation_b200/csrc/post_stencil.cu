@@ -1,0 +1,547 @@
+// Shared-memory stencil kernels of the post-processing family (SURVEY §8 a16/a17 + BASELINE config 5).
+//
+// One CTA = one 32 x 32 output tile of one [H,W] plane: the tile plus its halo is staged in shared memory once
+// (coalesced rows, zero / reflect padding resolved while loading), every tap is then a shared-memory read.  Multi-stage
+// operators (separable blurs, the two bilateral iterations, the fused clean-up chain) keep their intermediates in a second
+// shared plane with a shrinking halo, so a mask is read from HBM once and written once.  Intermediates that the reference
+// zero-pads are forced to 0 outside the image, which reproduces F.conv2d(padding=...) stage by stage.
+// Float arithmetic keeps the reference's operation order (fmaf accumulation in tap order, no fast-math): the final
+// thresholds can sit within a few ulp of a tie.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 32, TH = 32, kThreads = 256;
+constexpr int kMaxR = 8;                                   // largest total halo (fused chain: 1 + 3 + 3 = 7)
+constexpr int kPlane = (TW + 2 * kMaxR) * (TH + 2 * kMaxR);   // floats per shared plane (48 x 48)
+
+enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
+
+struct Tile {
+  int x0, y0;      // image coordinates of the tile's first output pixel
+  int H, W;
+};
+
+__device__ __forceinline__ Tile tile_of(int H, int W) {
+  Tile t; t.x0 = blockIdx.x * TW; t.y0 = blockIdx.y * TH; t.H = H; t.W = W; return t;
+}
+
+// Stages the (TW + 2R) x (TH + 2R) window around the tile into `s` (row pitch TW + 2R).
+template <int PAD, bool CLAMP01>
+__device__ __forceinline__ void load_window(const float* __restrict__ img, const Tile& t, int R, float* __restrict__ s) {
+  const int w = TW + 2 * R, h = TH + 2 * R;
+  for (int i = threadIdx.x; i < w * h; i += kThreads) {
+    const int ly = i / w, lx = i - ly * w;
+    int y = t.y0 - R + ly, x = t.x0 - R + lx;
+    float v = 0.0f;
+    if (PAD == PAD_REFLECT) {
+      // F.pad(mode='reflect'): -1 -> 1, H -> H-2; positions right/below the padded image (partial tiles) are never used
+      if (y < 0) y = -y; if (y >= t.H) y = 2 * t.H - 2 - y;
+      if (x < 0) x = -x; if (x >= t.W) x = 2 * t.W - 2 - x;
+      if (y >= 0 && y < t.H && x >= 0 && x < t.W) v = img[(long long)y * t.W + x];
+    } else if (y >= 0 && y < t.H && x >= 0 && x < t.W) {
+      v = img[(long long)y * t.W + x];
+    }
+    if (CLAMP01) v = fminf(fmaxf(v, 0.0f), 1.0f);
+    s[i] = v;
+  }
+}
+
+__device__ __forceinline__ bool inside(const Tile& t, int y, int x) { return y >= 0 && y < t.H && x >= 0 && x < t.W; }
+
+// ---------------------------------------------------------------------------------------------- edge smoothing family
+// BinaryMaskEdgeSmoothing (hed/edge_smoothing.py:10-90) on a window: value at local (ly, lx) of a plane with pitch `w`
+__device__ __forceinline__ float edge_smooth_at(const float* __restrict__ s, int w, int ly, int lx, float strength) {
+  float lap = 0.0f, g = 0.0f;
+  const float gk[9] = {1.f / 16, 2.f / 16, 1.f / 16, 2.f / 16, 4.f / 16, 2.f / 16, 1.f / 16, 2.f / 16, 1.f / 16};
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float v = s[(ly + t / 3 - 1) * w + lx + t % 3 - 1];
+    lap = fmaf(v, t == 4 ? 8.0f : -1.0f, lap);
+    g = fmaf(v, gk[t], g);
+  }
+  const float e = fabsf(lap) * strength;
+  const float wgt = 1.0f / (1.0f + expf(-e));
+  return __fadd_rn(__fmul_rn(s[ly * w + lx], __fsub_rn(1.0f, wgt)), __fmul_rn(g, wgt));
+}
+
+__global__ void __launch_bounds__(kThreads) edge_smooth_smem_kernel(const float* __restrict__ in, int H, int W, float thr, float strength,
+                                                                    float* __restrict__ out) {
+  __shared__ float s[(TW + 2) * (TH + 2)];
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(in + plane, t, 1, s);
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y < H && x < W) out[plane + (long long)y * W + x] = edge_smooth_at(s, TW + 2, ly + 1, lx + 1, strength) > thr ? 1.0f : 0.0f;
+  }
+}
+
+// DirectionalEdgeSmoothing, export_edge_smoothing_onnx.py:63-154: Sobel direction -> cos^2 weights over four directional blurs
+__global__ void __launch_bounds__(kThreads) edge_directional_kernel(const float* __restrict__ in, int H, int W, float* __restrict__ out) {
+  __shared__ float s[(TW + 4) * (TH + 4)];
+  constexpr int w = TW + 4;
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(in + plane, t, 2, s);
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    const float* c = s + (ly + 2) * w + lx + 2;
+    auto at = [&](int dy, int dx) { return c[dy * w + dx]; };
+    // cross-correlation in tap order (row-major), zero-weight taps skipped like a dense conv would add 0
+    float ex = 0.0f, ey = 0.0f;
+    ex = fmaf(at(-1, -1), -1.0f, ex); ex = fmaf(at(-1, 1), 1.0f, ex); ex = fmaf(at(0, -1), -2.0f, ex); ex = fmaf(at(0, 1), 2.0f, ex);
+    ex = fmaf(at(1, -1), -1.0f, ex); ex = fmaf(at(1, 1), 1.0f, ex);
+    ey = fmaf(at(-1, -1), -1.0f, ey); ey = fmaf(at(-1, 0), -2.0f, ey); ey = fmaf(at(-1, 1), -1.0f, ey); ey = fmaf(at(1, -1), 1.0f, ey);
+    ey = fmaf(at(1, 0), 2.0f, ey); ey = fmaf(at(1, 1), 1.0f, ey);
+    const float mag = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), 1e-8f));
+    const float ang = atan2f(ey, ex);
+    float bh = 0.0f, bv = 0.0f, b1 = 0.0f, b2 = 0.0f;
+    const float k5[5] = {0.1f, 0.2f, 0.4f, 0.2f, 0.1f};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { bh = fmaf(at(0, j - 2), k5[j], bh); bv = fmaf(at(j - 2, 0), k5[j], bv); }
+    b1 = fmaf(at(-1, -1), 0.1f, b1); b1 = fmaf(at(0, 0), 0.8f, b1); b1 = fmaf(at(1, 1), 0.1f, b1);
+    b2 = fmaf(at(-1, 1), 0.1f, b2); b2 = fmaf(at(0, 0), 0.8f, b2); b2 = fmaf(at(1, -1), 0.1f, b2);
+    const float ch = cosf(ang), sh = sinf(ang);
+    const float c1 = cosf(__fsub_rn(ang, 0.78539816339744830962f)), c2 = cosf(__fadd_rn(ang, 0.78539816339744830962f));
+    float wh = __fmul_rn(ch, ch), wv = __fmul_rn(sh, sh), w1 = __fmul_rn(__fmul_rn(c1, c1), 0.5f), w2 = __fmul_rn(__fmul_rn(c2, c2), 0.5f);
+    const float ws = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(wh, wv), w1), w2), 1e-8f);
+    wh = __fdiv_rn(wh, ws); wv = __fdiv_rn(wv, ws); w1 = __fdiv_rn(w1, ws); w2 = __fdiv_rn(w2, ws);
+    const float blurred = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bh, wh), __fmul_rn(bv, wv)), __fmul_rn(b1, w1)), __fmul_rn(b2, w2));
+    const float em = 1.0f / (1.0f + expf(-__fmul_rn(mag, 3.0f)));
+    const float sm = __fadd_rn(__fmul_rn(at(0, 0), __fsub_rn(1.0f, em)), __fmul_rn(blurred, em));
+    out[plane + (long long)y * W + x] = sm > 0.5f ? 1.0f : 0.0f;
+  }
+}
+
+// AdaptiveEdgeSmoothing, export_edge_smoothing_onnx.py:157-218; per-plane runtime parameters
+__global__ void __launch_bounds__(kThreads) edge_adaptive_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ blur_strength,
+                                                                 const float* __restrict__ edge_sens, const float* __restrict__ final_thr,
+                                                                 float* __restrict__ out) {
+  __shared__ float s[(TW + 4) * (TH + 4)];
+  constexpr int w = TW + 4;
+  const Tile t = tile_of(H, W);
+  const int n = blockIdx.z;
+  const long long plane = (long long)n * H * W;
+  load_window<PAD_ZERO, false>(in + plane, t, 2, s);
+  __syncthreads();
+  const float ethr = __fmul_rn(0.5f, edge_sens[n]), bf = __fdiv_rn(blur_strength[n], 3.0f), fthr = final_thr[n];
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    const float* c = s + (ly + 2) * w + lx + 2;
+    float lap = 0.0f, avg = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) lap = fmaf(c[(k / 3 - 1) * w + k % 3 - 1], k == 4 ? 8.0f : -1.0f, lap);
+#pragma unroll
+    for (int k = 0; k < 25; ++k) avg = fmaf(c[(k / 5 - 2) * w + k % 5 - 2], 1.0f / 25.0f, avg);
+    const float m = c[0];
+    const float em = fabsf(lap) > ethr ? 1.0f : 0.0f;
+    const float sm = __fadd_rn(__fmul_rn(m, __fsub_rn(1.0f, bf)), __fmul_rn(avg, bf));
+    const float r = __fadd_rn(__fmul_rn(m, __fsub_rn(1.0f, em)), __fmul_rn(sm, em));
+    out[plane + (long long)y * W + x] = r > fthr ? 1.0f : 0.0f;
+  }
+}
+
+__device__ __forceinline__ float rh(float v, bool fp16) { return fp16 ? __half2float(__float2half_rn(v)) : v; }
+
+// OptimizedEdgeSmoothing, export_edge_smoothing_onnx.py:221-318: separable 5-tap binomial blur (two stages), clamp "sigmoid".
+// fp16 != 0 rounds every operator output to half like the exported FP16 graph does.
+__global__ void __launch_bounds__(kThreads) edge_optimized_kernel(const float* __restrict__ in, int H, int W, int fp16, float* __restrict__ out) {
+  __shared__ float s[(TW + 4) * (TH + 4)];
+  __shared__ float hb[TW * (TH + 4)];         // horizontal blur, rows y0-2 .. y0+TH+1
+  constexpr int w = TW + 4;
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(in + plane, t, 2, s);
+  __syncthreads();
+  const float g5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  const bool f16 = fp16 != 0;
+  for (int i = threadIdx.x; i < TW * (TH + 4); i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW;
+    const int y = t.y0 - 2 + ly;
+    float v = 0.0f;
+    if (y >= 0 && y < H) {           // the vertical pass zero-pads the horizontal result outside the image
+#pragma unroll
+      for (int j = 0; j < 5; ++j) v = fmaf(s[ly * w + lx + j], g5[j], v);
+      v = rh(v, f16);
+    }
+    hb[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    const float* c = s + (ly + 2) * w + lx + 2;
+    float lap = 0.0f, bl = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) lap = fmaf(c[(k / 3 - 1) * w + k % 3 - 1], k == 4 ? 8.0f : -1.0f, lap);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) bl = fmaf(hb[(ly + j) * TW + lx], g5[j], bl);
+    lap = rh(lap, f16); bl = rh(bl, f16);
+    const float e = rh(__fmul_rn(rh(fabsf(lap), f16), 3.0f), f16);
+    float em = rh(__fmul_rn(rh(__fadd_rn(e, 0.5f), f16), 0.5f), f16);
+    em = fminf(fmaxf(em, 0.0f), 1.0f);
+    const float m = c[0];
+    const float a = rh(__fmul_rn(m, rh(__fsub_rn(1.0f, em), f16)), f16), b = rh(__fmul_rn(bl, em), f16);
+    out[plane + (long long)y * W + x] = rh(__fadd_rn(a, b), f16) > 0.5f ? 1.0f : 0.0f;
+  }
+}
+
+// MultiClassEdgeSmoothing front end (hed/edge_smoothing.py:136-143): per-class binary masks of [B,C,H,W] predictions
+__global__ void class_masks_kernel(const float* __restrict__ pred, int B, int C, long long HW, int use_argmax, int softmax_first,
+                                   float* __restrict__ out) {
+  const long long total = (long long)B * HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long b = idx / HW, p = idx - b * HW;
+    const float* src = pred + b * C * HW + p;
+    if (use_argmax) {                  // torch.argmax: first maximum
+      int best = 0; float bv = src[0];
+      for (int c = 1; c < C; ++c) { const float v = src[c * HW]; if (v > bv) { bv = v; best = c; } }
+      for (int c = 0; c < C; ++c) out[(b * C + c) * HW + p] = c == best ? 1.0f : 0.0f;
+    } else {
+      float mx = -INFINITY, sum = 0.0f;
+      if (softmax_first) {
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, src[c * HW]);
+        for (int c = 0; c < C; ++c) sum += expf(src[c * HW] - mx);
+      }
+      for (int c = 0; c < C; ++c) {
+        const float v = softmax_first ? expf(src[c * HW] - mx) / sum : src[c * HW];
+        out[(b * C + c) * HW + p] = v > 0.5f ? 1.0f : 0.0f;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bilateral family
+// BilateralFilter (hed/bilateral_filter.py:9-113): reflect padding, spatial x range Gaussian weights, normalised
+__global__ void __launch_bounds__(kThreads) bilateral_exact_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ spatial, int k,
+                                                                   float inv_2sr2, float* __restrict__ out) {
+  __shared__ float s[kPlane];
+  __shared__ float sk[81];
+  const int R = k / 2, w = TW + 2 * R;
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_REFLECT, false>(in + plane, t, R, s);
+  for (int i = threadIdx.x; i < k * k; i += kThreads) sk[i] = spatial[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    const float* c = s + (ly + R) * w + lx + R;
+    const float cv = c[0];
+    float wsum = 0.0f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const float d = c[(ky - R) * w + kx - R] - cv;
+        wsum += sk[ky * k + kx] * expf(-(d * d) * inv_2sr2);
+      }
+    const float den = wsum + 1e-8f;
+    float acc = 0.0f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const float v = c[(ky - R) * w + kx - R], d = v - cv;
+        acc += v * ((sk[ky * k + kx] * expf(-(d * d) * inv_2sr2)) / den);
+      }
+    out[plane + (long long)y * W + x] = acc;
+  }
+}
+
+// one iteration of FastBilateralFilter (hed/bilateral_filter.py:116-216): separable Gaussian of x and x^2 (zero padded stage
+// by stage), variance -> exp weight -> blend with the input
+__global__ void __launch_bounds__(kThreads) bilateral_fast_iter_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ k1, int k,
+                                                                       float inv_2sr2, float* __restrict__ out) {
+  __shared__ float s[kPlane];
+  __shared__ float h1[TW * (TH + 2 * kMaxR)], h2[TW * (TH + 2 * kMaxR)];
+  __shared__ float sk[16];
+  const int R = k / 2, w = TW + 2 * R, hh = TH + 2 * R;
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(in + plane, t, R, s);
+  if ((int)threadIdx.x < k) sk[threadIdx.x] = k1[threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * hh; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 - R + ly;
+    float a = 0.0f, b = 0.0f;
+    if (y >= 0 && y < H)
+      for (int j = 0; j < k; ++j) { const float v = s[ly * w + lx + j]; a = fmaf(v, sk[j], a); b = fmaf(__fmul_rn(v, v), sk[j], b); }
+    h1[i] = a; h2[i] = b;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    float f = 0.0f, q = 0.0f;
+    for (int j = 0; j < k; ++j) { f = fmaf(h1[(ly + j) * TW + lx], sk[j], f); q = fmaf(h2[(ly + j) * TW + lx], sk[j], q); }
+    const float var = fmaxf(__fsub_rn(q, __fmul_rn(f, f)), 0.0f);
+    const float ew = expf(-var * inv_2sr2);
+    const float c = s[(ly + R) * w + lx + R];
+    out[plane + (long long)y * W + x] = __fadd_rn(__fmul_rn(ew, f), __fmul_rn(__fsub_rn(1.0f, ew), c));
+  }
+}
+
+// EdgePreservingFilter (guided filter, hed/bilateral_filter.py:219-296), stage 1: box statistics -> a, b
+__global__ void __launch_bounds__(kThreads) guided_ab_kernel(const float* __restrict__ x, const float* __restrict__ g, int H, int W, int r, float eps,
+                                                             float* __restrict__ a_out, float* __restrict__ b_out) {
+  __shared__ float sx[kPlane], sg[kPlane];
+  const int w = TW + 2 * r, k = 2 * r + 1;
+  const float wk = 1.0f / (float)(k * k);
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(x + plane, t, r, sx);
+  load_window<PAD_ZERO, false>(g + plane, t, r, sg);
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, xx = t.x0 + lx;
+    if (y >= H || xx >= W) continue;
+    float mx = 0.0f, mg = 0.0f, cxg = 0.0f, cgg = 0.0f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        const float vx = sx[(ly + ky) * w + lx + kx], vg = sg[(ly + ky) * w + lx + kx];
+        mx = fmaf(vx, wk, mx); mg = fmaf(vg, wk, mg); cxg = fmaf(__fmul_rn(vx, vg), wk, cxg); cgg = fmaf(__fmul_rn(vg, vg), wk, cgg);
+      }
+    const float cov = __fsub_rn(cxg, __fmul_rn(mx, mg)), var = __fsub_rn(cgg, __fmul_rn(mg, mg));
+    const float a = __fdiv_rn(cov, __fadd_rn(var, eps));
+    a_out[plane + (long long)y * W + xx] = a;
+    b_out[plane + (long long)y * W + xx] = __fsub_rn(mx, __fmul_rn(a, mg));
+  }
+}
+
+// stage 2: out = box(a) * guide + box(b)
+__global__ void __launch_bounds__(kThreads) guided_out_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g, int H,
+                                                              int W, int r, float* __restrict__ out) {
+  __shared__ float sa[kPlane], sb[kPlane];
+  const int w = TW + 2 * r, k = 2 * r + 1;
+  const float wk = 1.0f / (float)(k * k);
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(a + plane, t, r, sa);
+  load_window<PAD_ZERO, false>(b + plane, t, r, sb);
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i - ly * TW, y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    float ma = 0.0f, mb = 0.0f;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) { ma = fmaf(sa[(ly + ky) * w + lx + kx], wk, ma); mb = fmaf(sb[(ly + ky) * w + lx + kx], wk, mb); }
+    const long long o = plane + (long long)y * W + x;
+    out[o] = __fadd_rn(__fmul_rn(ma, g[o]), mb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fused clean-up chain
+// BASELINE config 5 on full-image masks: BinaryMaskEdgeSmoothing -> BinaryMaskBilateralFilter (n iterations, k x k) in ONE
+// pass: the mask is read once and written once.  Every stage is computed on the region the next stage needs (halo shrinking
+// from 1 + n*R to 0) and zeroed outside the image, which is exactly the stage-by-stage zero padding of the reference chain.
+__device__ __forceinline__ float bilateral_at(const float* __restrict__ s, int w, int ly, int lx, const float* __restrict__ gk, int k) {
+  const int R = k / 2;
+  float f = 0.0f, f2 = 0.0f;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      const float v = s[(ly + ky - R) * w + lx + kx - R], wgt = gk[ky * k + kx];
+      f = fmaf(v, wgt, f);
+      f2 = fmaf(__fmul_rn(v, v), wgt, f2);
+    }
+  const float c = s[ly * w + lx];
+  const float var = fmaxf(__fsub_rn(f2, __fmul_rn(f, f)), 0.0f);
+  const float ew = expf(__fmul_rn(-var, 10.0f));
+  return __fadd_rn(__fmul_rn(ew, f), __fmul_rn(__fsub_rn(1.0f, ew), c));
+}
+
+__global__ void __launch_bounds__(kThreads) mask_cleanup_fused_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
+                                                                      const float* __restrict__ gauss, int k, int iterations, float thr,
+                                                                      float* __restrict__ out) {
+  __shared__ float pa[kPlane], pb[kPlane];
+  __shared__ float gk[81];
+  const int R = k / 2;
+  const int halo = 1 + iterations * R;                 // <= kMaxR (host checks)
+  const int w = TW + 2 * halo;
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, false>(in + plane, t, halo, pa);
+  for (int i = threadIdx.x; i < k * k; i += kThreads) gk[i] = gauss[i];
+  __syncthreads();
+  // stage 0: edge smoothing on the window shrunk by 1 (the bilateral filter clamps its input to [0,1]: a no-op on {0,1})
+  float* src = pa; float* dst = pb;
+  int m = halo - 1;                                    // margin still needed around the tile after this stage
+  for (int i = threadIdx.x; i < (TW + 2 * m) * (TH + 2 * m); i += kThreads) {
+    const int ry = i / (TW + 2 * m), rx = i - ry * (TW + 2 * m);
+    const int ly = ry + halo - m, lx = rx + halo - m;
+    const int y = t.y0 - halo + ly, x = t.x0 - halo + lx;
+    dst[ly * w + lx] = inside(t, y, x) ? (edge_smooth_at(src, w, ly, lx, es_strength) > es_thr ? 1.0f : 0.0f) : 0.0f;
+  }
+  __syncthreads();
+  for (int it = 0; it < iterations; ++it) {
+    float* tmp = src; src = dst; dst = tmp;
+    m -= R;
+    const bool last = it == iterations - 1;
+    for (int i = threadIdx.x; i < (TW + 2 * m) * (TH + 2 * m); i += kThreads) {
+      const int ry = i / (TW + 2 * m), rx = i - ry * (TW + 2 * m);
+      const int ly = ry + halo - m, lx = rx + halo - m;
+      const int y = t.y0 - halo + ly, x = t.x0 - halo + lx;
+      const bool in_img = inside(t, y, x);
+      const float v = in_img ? bilateral_at(src, w, ly, lx, gk, k) : 0.0f;
+      if (!last) dst[ly * w + lx] = v;
+      else if (in_img) out[plane + (long long)y * W + x] = v > thr ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+  }
+}
+
+// BinaryMaskBilateralFilter alone (hed/bilateral_filter.py:299-406), all iterations in one pass over shared memory
+__global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const float* __restrict__ in, int H, int W, const float* __restrict__ gauss, int k,
+                                                                         int iterations, float thr, float* __restrict__ out) {
+  __shared__ float pa[kPlane], pb[kPlane];
+  __shared__ float gk[81];
+  const int R = k / 2;
+  const int halo = iterations * R;
+  const int w = TW + 2 * halo;
+  const Tile t = tile_of(H, W);
+  const long long plane = (long long)blockIdx.z * H * W;
+  load_window<PAD_ZERO, true>(in + plane, t, halo, pa);
+  for (int i = threadIdx.x; i < k * k; i += kThreads) gk[i] = gauss[i];
+  __syncthreads();
+  float* src = pa; float* dst = pb;
+  int m = halo;
+  for (int it = 0; it < iterations; ++it) {
+    m -= R;
+    const bool last = it == iterations - 1;
+    for (int i = threadIdx.x; i < (TW + 2 * m) * (TH + 2 * m); i += kThreads) {
+      const int ry = i / (TW + 2 * m), rx = i - ry * (TW + 2 * m);
+      const int ly = ry + halo - m, lx = rx + halo - m;
+      const int y = t.y0 - halo + ly, x = t.x0 - halo + lx;
+      const bool in_img = inside(t, y, x);
+      const float v = in_img ? bilateral_at(src, w, ly, lx, gk, k) : 0.0f;
+      if (!last) dst[ly * w + lx] = v;
+      else if (in_img) out[plane + (long long)y * W + x] = v > thr ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    float* tmp = src; src = dst; dst = tmp;
+  }
+}
+
+inline dim3 tile_grid(int N, int H, int W) { return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, N); }
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+#define CHECK_PLANES(name)                                                                                              \
+  if (N == 0 || H == 0 || W == 0) return HIS_OK;                                                                        \
+  if (N > 65535) return his_set_error(HIS_ERR_UNSUPPORTED, name ": at most 65535 planes per call (chunk the batch)")
+
+extern "C" {
+
+int his_post_edge_smooth_tiled(const float* mask, int N, int H, int W, float threshold, float blur_strength, float* out, void* stream) {
+  if (!mask || !out) return his_set_error(HIS_ERR_INVALID_ARG, "edge_smooth_tiled: null pointer");
+  CHECK_PLANES("edge_smooth_tiled");
+  edge_smooth_smem_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, threshold, blur_strength, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_edge_directional(const float* mask, int N, int H, int W, float* out, void* stream) {
+  if (!mask || !out) return his_set_error(HIS_ERR_INVALID_ARG, "edge_directional: null pointer");
+  CHECK_PLANES("edge_directional");
+  edge_directional_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_edge_adaptive(const float* mask, int N, int H, int W, const float* blur_strength, const float* edge_sensitivity,
+                           const float* final_threshold, float* out, void* stream) {
+  if (!mask || !out || !blur_strength || !edge_sensitivity || !final_threshold) return his_set_error(HIS_ERR_INVALID_ARG, "edge_adaptive: null pointer");
+  CHECK_PLANES("edge_adaptive");
+  edge_adaptive_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, blur_strength, edge_sensitivity, final_threshold, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_edge_optimized(const float* mask, int N, int H, int W, int fp16, float* out, void* stream) {
+  if (!mask || !out) return his_set_error(HIS_ERR_INVALID_ARG, "edge_optimized: null pointer");
+  CHECK_PLANES("edge_optimized");
+  edge_optimized_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, fp16, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_class_masks(const float* pred, int B, int C, int H, int W, int use_argmax, int softmax_first, float* out, void* stream) {
+  if (!pred || !out) return his_set_error(HIS_ERR_INVALID_ARG, "class_masks: null pointer");
+  const long long total = (long long)B * H * W;
+  if (total == 0 || C == 0) return HIS_OK;
+  long long g = (total + 255) / 256; if (g > 148LL * 64) g = 148LL * 64;
+  class_masks_kernel<<<(int)g, 256, 0, ST>>>(pred, B, C, (long long)H * W, use_argmax, softmax_first, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_bilateral_exact(const float* in, int N, int H, int W, const float* spatial_kernel, int k, float sigma_range, float* out, void* stream) {
+  if (!in || !out || !spatial_kernel) return his_set_error(HIS_ERR_INVALID_ARG, "bilateral_exact: null pointer");
+  if (k < 1 || !(k & 1) || k / 2 > kMaxR) return his_set_error(HIS_ERR_UNSUPPORTED, "bilateral_exact: odd kernel size <= 17");
+  if (k > 9) return his_set_error(HIS_ERR_UNSUPPORTED, "bilateral_exact: kernel size <= 9");
+  if (H <= k / 2 || W <= k / 2) return his_set_error(HIS_ERR_INVALID_ARG, "bilateral_exact: reflect padding needs H, W > kernel_size/2");
+  CHECK_PLANES("bilateral_exact");
+  bilateral_exact_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(in, H, W, spatial_kernel, k, 1.0f / (2.0f * sigma_range * sigma_range), out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_bilateral_fast(const float* in, int N, int H, int W, const float* kernel1d, int k, float sigma_range, int iterations, float* ws,
+                            float* out, void* stream) {
+  if (!in || !out || !kernel1d || (iterations > 1 && !ws)) return his_set_error(HIS_ERR_INVALID_ARG, "bilateral_fast: null pointer");
+  if (k < 1 || !(k & 1) || k > 15 || iterations < 1) return his_set_error(HIS_ERR_UNSUPPORTED, "bilateral_fast: odd kernel size <= 15, iterations >= 1");
+  CHECK_PLANES("bilateral_fast");
+  const float inv = 1.0f / (2.0f * sigma_range * sigma_range);
+  const float* src = in;
+  for (int it = 0; it < iterations; ++it) {
+    // ping-pong so that the last iteration lands in `out`
+    float* dst = ((iterations - 1 - it) & 1) ? ws : out;
+    bilateral_fast_iter_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(src, H, W, kernel1d, k, inv, dst);
+    HIS_CHECK_LAUNCH();
+    src = dst;
+  }
+  return HIS_OK;
+}
+
+int his_post_guided_filter(const float* x, const float* guide, int N, int H, int W, int radius, float eps, float* ws_a, float* ws_b, float* out,
+                           void* stream) {
+  if (!x || !guide || !ws_a || !ws_b || !out) return his_set_error(HIS_ERR_INVALID_ARG, "guided_filter: null pointer");
+  if (radius < 0 || radius > kMaxR) return his_set_error(HIS_ERR_UNSUPPORTED, "guided_filter: radius <= 8");
+  CHECK_PLANES("guided_filter");
+  guided_ab_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(x, guide, H, W, radius, eps, ws_a, ws_b);
+  HIS_CHECK_LAUNCH();
+  guided_out_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(ws_a, ws_b, guide, H, W, radius, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_binary_bilateral_tiled(const float* mask, int N, int H, int W, const float* gauss, int k, int iterations, float threshold, float* out,
+                                    void* stream) {
+  if (!mask || !gauss || !out) return his_set_error(HIS_ERR_INVALID_ARG, "binary_bilateral_tiled: null pointer");
+  if (k < 1 || !(k & 1) || k > 9 || iterations < 1 || iterations * (k / 2) > kMaxR)
+    return his_set_error(HIS_ERR_UNSUPPORTED, "binary_bilateral_tiled: odd kernel size <= 9 and iterations*(k/2) <= 8");
+  CHECK_PLANES("binary_bilateral_tiled");
+  binary_bilateral_smem_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, gauss, k, iterations, threshold, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es_threshold, float es_strength, const float* gauss, int k,
+                                int iterations, float threshold, float* out, void* stream) {
+  if (!mask || !gauss || !out) return his_set_error(HIS_ERR_INVALID_ARG, "mask_cleanup_fused: null pointer");
+  if (k < 1 || !(k & 1) || k > 9 || iterations < 1 || 1 + iterations * (k / 2) > kMaxR)
+    return his_set_error(HIS_ERR_UNSUPPORTED, "mask_cleanup_fused: odd kernel size <= 9 and 1 + iterations*(k/2) <= 8");
+  CHECK_PLANES("mask_cleanup_fused");
+  mask_cleanup_fused_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, k, iterations, threshold, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+}  // extern "C"

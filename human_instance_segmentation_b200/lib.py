@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_uint, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhis_b200.so")
-SOURCES = ["kernels.cu", "conv_gemm_sm100.cu", "post.cu"]
+SOURCES = ["kernels.cu", "conv_gemm_sm100.cu", "post.cu", "post_stencil.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -115,6 +115,17 @@ SIGNATURES = {
     "his_post_binary_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P],
     "his_post_morph_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P],
     "his_post_paste": [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
+    # shared-memory tiled stencils (csrc/post_stencil.cu)
+    "his_post_edge_smooth_tiled": [_P, c_int, c_int, c_int, c_float, c_float, _P, _P],
+    "his_post_edge_directional": [_P, c_int, c_int, c_int, _P, _P],
+    "his_post_edge_adaptive": [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P],
+    "his_post_edge_optimized": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "his_post_class_masks": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
+    "his_post_bilateral_exact": [_P, c_int, c_int, c_int, _P, c_int, c_float, _P, _P],
+    "his_post_bilateral_fast": [_P, c_int, c_int, c_int, _P, c_int, c_float, c_int, _P, _P, _P],
+    "his_post_guided_filter": [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
+    "his_post_binary_bilateral_tiled": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P, _P],
+    "his_post_mask_cleanup_fused": [_P, c_int, c_int, c_int, c_float, c_float, _P, c_int, c_int, c_float, _P, _P],
 }
 _RESTYPES = {"his_last_error": c_char_p, "his_conv_gemm_issued_macs": _LL}
 

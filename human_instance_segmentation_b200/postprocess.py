@@ -1,9 +1,12 @@
 """Post-processing modules with the reference's interfaces, on the B200 stencil kernels (csrc/post.cu).
 
 Mirrors: ``RGBHierarchicalWrapper._to_instance_masks`` (hed/export_onnx_advanced.py:360-364),
-``MaskDilationModule`` (export_hierarchical_instance_peopleseg_onnx.py:85-141), ``BinaryMaskEdgeSmoothing``
-(hed/edge_smoothing.py:10-90), ``BinaryMaskBilateralFilter`` / ``MorphologicalBilateralFilter``
-(hed/bilateral_filter.py:299-501) and the NEAREST paste-back of test_hierarchical_instance_peopleseg_onnx.py.
+``MaskDilationModule`` (export_hierarchical_instance_peopleseg_onnx.py:85-141), ``BinaryMaskEdgeSmoothing`` /
+``MultiClassEdgeSmoothing`` (hed/edge_smoothing.py:10-170), ``DirectionalEdgeSmoothing`` / ``AdaptiveEdgeSmoothing`` /
+``OptimizedEdgeSmoothing`` (export_edge_smoothing_onnx.py:63-318), ``BilateralFilter`` / ``FastBilateralFilter`` /
+``EdgePreservingFilter`` / ``BinaryMaskBilateralFilter`` / ``MorphologicalBilateralFilter`` (hed/bilateral_filter.py:9-501),
+the NEAREST paste-back of test_hierarchical_instance_peopleseg_onnx.py, and ``MaskCleanup`` -- edge smoothing + binary
+bilateral filter fused into one shared-memory pass (BASELINE config 5).
 All take/return CUDA tensors; there is no CPU path.
 """
 from __future__ import annotations
@@ -96,9 +99,98 @@ class BinaryMaskEdgeSmoothing(nn.Module):
         x = _cuda_f32(x4, "BinaryMaskEdgeSmoothing")
         b, c, h, w = x.shape
         out = torch.empty_like(x)
-        _lib.check(_lib.load().his_post_edge_smooth(x.data_ptr(), b * c, h, w, float(self.threshold), float(self.blur_strength),
-                                                    out.data_ptr(), _stream(x)))
+        _run_planes(_lib.load().his_post_edge_smooth_tiled, x, out, float(self.threshold), float(self.blur_strength))
         return out.to(mask.dtype).reshape(shape)
+
+
+def _run_planes(fn, x: torch.Tensor, out: torch.Tensor, *args, extra_in=(), extra_out=()):
+    """Calls a tiled stencil entry point over the [B*C] planes of ``x`` in chunks of 65535 planes."""
+    b, c, h, w = x.shape
+    n, hw = b * c, h * w * 4
+    for s0 in range(0, n, 65535):
+        cnt = min(65535, n - s0)
+        ins = [t.data_ptr() + s0 * hw for t in extra_in]
+        outs = [t.data_ptr() + s0 * hw for t in extra_out]
+        _lib.check(fn(x.data_ptr() + s0 * hw, *ins, cnt, h, w, *args, *outs, out.data_ptr() + s0 * hw, _stream(x)))
+
+
+class DirectionalEdgeSmoothing(nn.Module):
+    """export_edge_smoothing_onnx.py:63-154."""
+
+    def __init__(self, num_directions: int = 4):
+        super().__init__()
+        self.num_directions = num_directions
+
+    @torch.no_grad()
+    def forward(self, mask: torch.Tensor) -> torch.Tensor:
+        x = _cuda_f32(mask, "DirectionalEdgeSmoothing")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise RuntimeError("DirectionalEdgeSmoothing expects [B,1,H,W] (the reference's conv kernels have one input channel)")
+        out = torch.empty_like(x)
+        _run_planes(_lib.load().his_post_edge_directional, x, out)
+        return out
+
+
+class AdaptiveEdgeSmoothing(nn.Module):
+    """export_edge_smoothing_onnx.py:157-218; the three parameters are per-image tensors [B,1]."""
+
+    @torch.no_grad()
+    def forward(self, mask, blur_strength, edge_sensitivity, final_threshold) -> torch.Tensor:
+        x = _cuda_f32(mask, "AdaptiveEdgeSmoothing")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise RuntimeError("AdaptiveEdgeSmoothing expects [B,1,H,W]")
+        b, _, h, w = x.shape
+        if b > 65535:
+            raise _lib.HisError("AdaptiveEdgeSmoothing: at most 65535 images per call")
+        prm = [t.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous() for t in (blur_strength, edge_sensitivity, final_threshold)]
+        if any(t.numel() != b for t in prm):
+            raise RuntimeError("AdaptiveEdgeSmoothing: parameters must hold one value per image ([B,1])")
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().his_post_edge_adaptive(x.data_ptr(), b, h, w, prm[0].data_ptr(), prm[1].data_ptr(), prm[2].data_ptr(),
+                                                      out.data_ptr(), _stream(x)))
+        return out
+
+
+class OptimizedEdgeSmoothing(nn.Module):
+    """export_edge_smoothing_onnx.py:221-318.  ``use_fp16`` reproduces the exported FP16 graph (every operator output rounded to
+    half) and returns a half tensor, like the reference."""
+
+    def __init__(self, use_fp16: bool = True):
+        super().__init__()
+        self.use_fp16 = use_fp16
+
+    @torch.no_grad()
+    def forward(self, mask: torch.Tensor) -> torch.Tensor:
+        x = _cuda_f32(mask, "OptimizedEdgeSmoothing")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise RuntimeError("OptimizedEdgeSmoothing expects [B,1,H,W]")
+        out = torch.empty_like(x)
+        _run_planes(_lib.load().his_post_edge_optimized, x, out, 1 if self.use_fp16 else 0)
+        return out.half() if self.use_fp16 else out
+
+
+class MultiClassEdgeSmoothing:
+    """hed/edge_smoothing.py:93-170 (``device`` is accepted for signature parity; tensors must already be CUDA tensors)."""
+
+    def __init__(self, threshold: float = 0.5, blur_strength: float = 3.0, iterations: int = 1, device: str = "cuda"):
+        self.smoother = BinaryMaskEdgeSmoothing(threshold, blur_strength)
+        self.iterations = iterations
+        self.device = device
+
+    @torch.no_grad()
+    def smooth_predictions(self, predictions: torch.Tensor, apply_softmax: bool = False) -> torch.Tensor:
+        x = _cuda_f32(predictions, "MultiClassEdgeSmoothing")
+        squeeze = x.dim() == 3
+        if squeeze:
+            x = x[None]
+        b, c, h, w = x.shape
+        L = _lib.load()
+        masks = torch.empty_like(x)
+        # argmax is invariant under softmax, so the softmax only matters for the thresholded (C != 3) flavour
+        _lib.check(L.his_post_class_masks(x.data_ptr(), b, c, h, w, 1 if c == 3 else 0, 1 if apply_softmax else 0, masks.data_ptr(), _stream(x)))
+        for _ in range(self.iterations):
+            masks = self.smoother(masks)
+        return masks[0] if (squeeze or b == 1) else masks
 
 
 def _gauss2d(k: int, sigma: float, outer: bool) -> torch.Tensor:
@@ -115,6 +207,95 @@ def _gauss2d(k: int, sigma: float, outer: bool) -> torch.Tensor:
     return (g / g.sum()).contiguous()
 
 
+class BilateralFilter(nn.Module):
+    """hed/bilateral_filter.py:9-113 (the reference walks every pixel in Python; here one tiled kernel)."""
+
+    def __init__(self, kernel_size: int = 5, sigma_spatial: float = 1.0, sigma_range: float = 0.1):
+        super().__init__()
+        if kernel_size % 2 == 0:
+            raise ValueError("Kernel size must be odd")
+        self.kernel_size, self.sigma_spatial, self.sigma_range, self.padding = kernel_size, sigma_spatial, sigma_range, kernel_size // 2
+        coords = torch.arange(kernel_size, dtype=torch.float32) - (kernel_size - 1) / 2
+        y, x = coords.view(-1, 1).expand(kernel_size, kernel_size), coords.view(1, -1).expand(kernel_size, kernel_size)
+        self.register_buffer("spatial_kernel", torch.exp(-(x ** 2 + y ** 2) / (2 * sigma_spatial ** 2)))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = _cuda_f32(x, "BilateralFilter")
+        out = torch.empty_like(x)
+        sk = self.spatial_kernel.to(x.device).contiguous()
+        _run_planes(_lib.load().his_post_bilateral_exact, x, out, sk.data_ptr(), self.kernel_size, float(self.sigma_range))
+        return out
+
+
+class FastBilateralFilter(nn.Module):
+    """hed/bilateral_filter.py:116-216."""
+
+    def __init__(self, kernel_size: int = 5, sigma_spatial: float = 1.0, sigma_range: float = 0.1, num_iterations: int = 2):
+        super().__init__()
+        if kernel_size % 2 == 0:
+            raise ValueError("Kernel size must be odd")
+        self.kernel_size, self.sigma_spatial, self.sigma_range, self.num_iterations = kernel_size, sigma_spatial, sigma_range, num_iterations
+        self.padding = kernel_size // 2
+        coords = torch.arange(kernel_size, dtype=torch.float32) - (kernel_size - 1) / 2
+        k1 = torch.exp(-coords ** 2 / (2 * sigma_spatial ** 2))
+        k1 = k1 / k1.sum()
+        self.register_buffer("kernel_h", k1.view(1, 1, 1, kernel_size))
+        self.register_buffer("kernel_v", k1.view(1, 1, kernel_size, 1))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = _cuda_f32(x, "FastBilateralFilter")
+        if self.num_iterations < 1:
+            return x.clone()
+        out, ws = torch.empty_like(x), torch.empty_like(x)
+        k1 = self.kernel_h.to(x.device).reshape(-1).contiguous()
+        _run_planes(_lib.load().his_post_bilateral_fast, x, out, k1.data_ptr(), self.kernel_size, float(self.sigma_range), int(self.num_iterations),
+                    extra_out=(ws,))
+        return out
+
+
+class EdgePreservingFilter(nn.Module):
+    """Guided filter, hed/bilateral_filter.py:219-296."""
+
+    def __init__(self, radius: int = 2, eps: float = 0.01):
+        super().__init__()
+        self.radius, self.eps, self.kernel_size = radius, eps, 2 * radius + 1
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, guide: torch.Tensor = None) -> torch.Tensor:
+        x = _cuda_f32(x, "EdgePreservingFilter")
+        g = x if guide is None else _cuda_f32(guide, "EdgePreservingFilter")
+        if g.shape != x.shape:
+            raise RuntimeError("EdgePreservingFilter: guide must have the input's shape")
+        out, a, b = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        _run_planes(_lib.load().his_post_guided_filter, x, out, int(self.radius), float(self.eps), extra_in=(g,), extra_out=(a, b))
+        return out
+
+
+class MaskCleanup(nn.Module):
+    """``BinaryMaskBilateralFilter(BinaryMaskEdgeSmoothing(mask))`` in one kernel: the post-processing chain of BASELINE
+    config 5 on full-image masks, read once and written once (bit-identical to running the two modules back to back)."""
+
+    def __init__(self, es_threshold: float = 0.5, blur_strength: float = 3.0, kernel_size: int = 7, sigma_spatial: float = 1.5,
+                 threshold: float = 0.5, num_iterations: int = 2):
+        super().__init__()
+        if kernel_size % 2 == 0:
+            raise ValueError("Kernel size must be odd")
+        self.es_threshold, self.blur_strength = es_threshold, blur_strength
+        self.kernel_size, self.threshold, self.num_iterations = kernel_size, threshold, num_iterations
+        self.register_buffer("gaussian_kernel", _gauss2d(kernel_size, sigma_spatial, False).view(1, 1, kernel_size, kernel_size))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        x = _cuda_f32(x, "MaskCleanup")
+        out = torch.empty_like(x) if out is None else out
+        g = self.gaussian_kernel.to(x.device).contiguous()
+        _run_planes(_lib.load().his_post_mask_cleanup_fused, x, out, float(self.es_threshold), float(self.blur_strength), g.data_ptr(),
+                    self.kernel_size, int(self.num_iterations), float(self.threshold))
+        return out
+
+
 class BinaryMaskBilateralFilter(nn.Module):
     def __init__(self, kernel_size: int = 7, sigma_spatial: float = 1.5, threshold: float = 0.5, num_iterations: int = 2):
         super().__init__()
@@ -129,6 +310,11 @@ class BinaryMaskBilateralFilter(nn.Module):
         b, c, h, w = x.shape
         g = self.gaussian_kernel.to(x.device).contiguous()
         out = torch.empty_like(x)
+        if self.kernel_size <= 9 and 1 <= self.num_iterations and self.num_iterations * (self.kernel_size // 2) <= 8:
+            # all iterations in one shared-memory pass
+            _run_planes(_lib.load().his_post_binary_bilateral_tiled, x, out, g.data_ptr(), self.kernel_size, int(self.num_iterations),
+                        float(self.threshold))
+            return out
         ws0, ws1 = torch.empty_like(x), torch.empty_like(x)
         _lib.check(_lib.load().his_post_binary_bilateral(x.data_ptr(), b * c, h, w, g.data_ptr(), self.kernel_size, int(self.num_iterations),
                                                          float(self.threshold), ws0.data_ptr(), ws1.data_ptr(), out.data_ptr(), _stream(x)))

@@ -187,6 +187,37 @@ int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float
 int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W,
                    void* stream);
 
+/* ---- shared-memory tiled stencils (csrc/post_stencil.cu): one 32x32 tile + halo per CTA, the plane is read once.
+ * All take N planes [N,H,W] fp32 (a [B,C,H,W] tensor is B*C planes), N <= 65535 per call.
+ * his_post_edge_smooth_tiled: BinaryMaskEdgeSmoothing, hed/edge_smoothing.py:10-90 (same result as his_post_edge_smooth).
+ * his_post_edge_directional / _adaptive / _optimized: DirectionalEdgeSmoothing, AdaptiveEdgeSmoothing (per-plane runtime
+ *   parameters, device arrays [N]) and OptimizedEdgeSmoothing (fp16 != 0: every operator output rounded to half, the
+ *   exported FP16 graph), export_edge_smoothing_onnx.py:63-318.
+ * his_post_class_masks: per-class binary masks of [B,C,H,W] predictions -- argmax==c (C == 3) or (softmax?)p > 0.5 --
+ *   the front end of MultiClassEdgeSmoothing.smooth_predictions, hed/edge_smoothing.py:93-170.
+ * his_post_bilateral_exact: BilateralFilter (reflect padding, spatial x range weights), hed/bilateral_filter.py:9-113;
+ *   spatial_kernel: device [k*k] (un-normalised exp(-d^2/2s^2), as the reference builds it).
+ * his_post_bilateral_fast: FastBilateralFilter, hed/bilateral_filter.py:116-216; kernel1d: device [k] normalised; ws: [N,H,W].
+ * his_post_guided_filter: EdgePreservingFilter, hed/bilateral_filter.py:219-296 (guide == x when the caller has no guide).
+ * his_post_binary_bilateral_tiled: BinaryMaskBilateralFilter, all iterations in one pass (needs iterations*(k/2) <= 8).
+ * his_post_mask_cleanup_fused: BinaryMaskEdgeSmoothing -> BinaryMaskBilateralFilter in one kernel (BASELINE config 5 chain). */
+int his_post_edge_smooth_tiled(const float* mask, int N, int H, int W, float threshold, float blur_strength, float* out, void* stream);
+int his_post_edge_directional(const float* mask, int N, int H, int W, float* out, void* stream);
+int his_post_edge_adaptive(const float* mask, int N, int H, int W, const float* blur_strength, const float* edge_sensitivity,
+                           const float* final_threshold, float* out, void* stream);
+int his_post_edge_optimized(const float* mask, int N, int H, int W, int fp16, float* out, void* stream);
+int his_post_class_masks(const float* pred, int B, int C, int H, int W, int use_argmax, int softmax_first, float* out, void* stream);
+int his_post_bilateral_exact(const float* in, int N, int H, int W, const float* spatial_kernel, int k, float sigma_range, float* out,
+                             void* stream);
+int his_post_bilateral_fast(const float* in, int N, int H, int W, const float* kernel1d, int k, float sigma_range, int iterations,
+                            float* ws, float* out, void* stream);
+int his_post_guided_filter(const float* x, const float* guide, int N, int H, int W, int radius, float eps, float* ws_a, float* ws_b,
+                           float* out, void* stream);
+int his_post_binary_bilateral_tiled(const float* mask, int N, int H, int W, const float* gauss, int k, int iterations, float threshold,
+                                    float* out, void* stream);
+int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es_threshold, float es_strength, const float* gauss, int k,
+                                int iterations, float threshold, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

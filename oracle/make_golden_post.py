@@ -30,6 +30,45 @@ def all_3x3_patterns() -> torch.Tensor:
     return img
 
 
+def make_post_variant_goldens(golden_dir: str):
+    """a16/a17 variants: outputs of the reference's own classes (export_edge_smoothing_onnx.py, hed/edge_smoothing.py,
+    hed/bilateral_filter.py) on seeded inputs -> tests/golden/post_variants.npz."""
+    es = refload.ref_import("edge_smoothing")
+    bf = refload.ref_import("bilateral_filter")
+    cls = {n: refload.ref_class_from_script("export_edge_smoothing_onnx.py", n)
+           for n in ("DirectionalEdgeSmoothing", "AdaptiveEdgeSmoothing", "OptimizedEdgeSmoothing")}
+    out = {}
+    masks = blob_masks(7, 3, 96, 128)
+    g = torch.Generator().manual_seed(8)
+    gray = torch.rand(2, 2, 40, 56, generator=g)                       # float images for the value filters
+    guide = (gray + 0.1 * torch.randn(gray.shape, generator=g)).contiguous()
+    logits = torch.randn(2, 3, 48, 64, generator=g) * 2
+    logits = F.avg_pool2d(F.pad(logits, (3, 3, 3, 3), mode="replicate"), 7, 1).contiguous()      # blob-like argmax regions
+    probs5 = torch.rand(2, 5, 48, 64, generator=g)
+    bs, sens, thr = torch.tensor([[1.0], [3.0], [5.0]]), torch.tensor([[0.5], [1.0], [2.0]]), torch.tensor([[0.3], [0.5], [0.7]])
+    out.update(masks=masks.numpy(), gray=gray.numpy(), guide=guide.numpy(), logits=logits.numpy(), probs5=probs5.numpy(),
+               ad_bs=bs.numpy(), ad_sens=sens.numpy(), ad_thr=thr.numpy(), patterns=all_3x3_patterns().numpy())
+    with torch.no_grad():
+        out["directional"] = cls["DirectionalEdgeSmoothing"]()(masks).numpy()
+        out["adaptive"] = cls["AdaptiveEdgeSmoothing"]()(masks, bs, sens, thr).numpy()
+        out["optimized_fp32"] = cls["OptimizedEdgeSmoothing"](use_fp16=False)(masks).numpy()
+        out["optimized_fp32_patterns"] = cls["OptimizedEdgeSmoothing"](use_fp16=False)(all_3x3_patterns()).numpy()
+        # use_fp16=True needs half weights (the exporter converts the module: export_edge_smoothing_onnx.py model.half())
+        out["optimized_fp16"] = cls["OptimizedEdgeSmoothing"](use_fp16=True).half()(masks).float().numpy()
+        mc = es.MultiClassEdgeSmoothing(device="cpu")
+        out["multiclass3"] = mc.smooth_predictions(logits).numpy()
+        out["multiclass3_softmax_it2"] = es.MultiClassEdgeSmoothing(0.5, 3.0, 2, device="cpu").smooth_predictions(logits, apply_softmax=True).numpy()
+        out["multiclass5"] = mc.smooth_predictions(probs5).numpy()
+        out["bilateral_exact"] = bf.BilateralFilter()(gray[:, :, :12, :16].contiguous()).numpy()       # Python triple loop: tiny crop
+        out["bilateral_exact_k3"] = bf.BilateralFilter(3, 0.8, 0.3)(gray[:1, :, :10, :12].contiguous()).numpy()
+        out["bilateral_fast"] = bf.FastBilateralFilter()(gray).numpy()
+        out["bilateral_fast_k7_it3"] = bf.FastBilateralFilter(7, 1.5, 0.2, 3)(gray).numpy()
+        out["edge_preserving"] = bf.EdgePreservingFilter()(gray).numpy()
+        out["edge_preserving_guided_r3"] = bf.EdgePreservingFilter(3, 0.05)(gray, guide).numpy()
+    np.savez_compressed(os.path.join(golden_dir, "post_variants.npz"), **out)
+    print("post variant goldens:", {k: v.shape for k, v in out.items()})
+
+
 def make_post_goldens(golden_dir: str):
     es = refload.ref_import("edge_smoothing")
     bf = refload.ref_import("bilateral_filter")

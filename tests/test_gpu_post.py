@@ -83,3 +83,68 @@ def test_mask_dilation_matches_reference_golden():
         margin = ((torch.nn.functional.max_pool2d(torch.softmax(g["logits"], 1)[:, 1:2], 2 * d + 1, 1, d) - torch.softmax(g["logits"], 1)[:, 1:2]) - 0.1).abs()
         assert bad == 0 or float(margin.min()) < 1e-6, bad
     assert torch.equal(pp.MaskDilationModule(0)(logits), logits)
+
+
+def _frac_bad(got, want):
+    return float((got.float().cpu() != want).float().mean())
+
+
+def test_edge_smoothing_variants_match_reference():
+    """a16 variants (export_edge_smoothing_onnx.py:63-318, hed/edge_smoothing.py:93-170) against the reference's outputs."""
+    g = common.golden("post_variants")
+    m = g["masks"].cuda()
+    # linear-arithmetic variants: bit-exact, including every binary 3x3 neighbourhood
+    assert _mismatch(pp.AdaptiveEdgeSmoothing()(m, g["ad_bs"].cuda(), g["ad_sens"].cuda(), g["ad_thr"].cuda()), g["adaptive"]) == 0
+    assert _mismatch(pp.OptimizedEdgeSmoothing(use_fp16=False)(m), g["optimized_fp32"]) == 0
+    assert _mismatch(pp.OptimizedEdgeSmoothing(use_fp16=False)(g["patterns"].cuda()), g["optimized_fp32_patterns"]) == 0
+    # atan2/cos/sin (directional) and half-precision rounding order (fp16 graph) differ from the CPU libraries by ulps:
+    # only pixels within a hair of the 0.5 threshold may flip
+    bad = _frac_bad(pp.DirectionalEdgeSmoothing()(m), g["directional"])
+    print(f"DirectionalEdgeSmoothing: {bad:.2e} of pixels differ")
+    assert bad <= 2e-4
+    out16 = pp.OptimizedEdgeSmoothing(use_fp16=True)(m)
+    assert out16.dtype == torch.float16
+    bad = _frac_bad(out16, g["optimized_fp16"])
+    print(f"OptimizedEdgeSmoothing(fp16): {bad:.2e} of pixels differ")
+    assert bad <= 1e-3
+    mc = pp.MultiClassEdgeSmoothing()
+    assert _mismatch(mc.smooth_predictions(g["logits"].cuda()), g["multiclass3"]) == 0
+    assert _mismatch(pp.MultiClassEdgeSmoothing(0.5, 3.0, 2).smooth_predictions(g["logits"].cuda(), apply_softmax=True), g["multiclass3_softmax_it2"]) == 0
+    assert _mismatch(mc.smooth_predictions(g["probs5"].cuda()), g["multiclass5"]) == 0
+    assert mc.smooth_predictions(g["logits"][0].cuda()).shape == (3, 48, 64)
+
+
+def test_value_filters_match_reference():
+    """a17: BilateralFilter / FastBilateralFilter / EdgePreservingFilter return float images -> absolute tolerance 2e-5
+    (expf and summation order differ from the CPU by a few ulp)."""
+    g = common.golden("post_variants")
+    gray, guide = g["gray"].cuda(), g["guide"].cuda()
+    tol = 2e-5
+    assert (pp.BilateralFilter()(gray[:, :, :12, :16].contiguous()).cpu() - g["bilateral_exact"]).abs().max() < tol
+    assert (pp.BilateralFilter(3, 0.8, 0.3)(gray[:1, :, :10, :12].contiguous()).cpu() - g["bilateral_exact_k3"]).abs().max() < tol
+    assert (pp.FastBilateralFilter()(gray).cpu() - g["bilateral_fast"]).abs().max() < tol
+    assert (pp.FastBilateralFilter(7, 1.5, 0.2, 3)(gray).cpu() - g["bilateral_fast_k7_it3"]).abs().max() < tol
+    assert (pp.EdgePreservingFilter()(gray).cpu() - g["edge_preserving"]).abs().max() < 1e-4
+    assert (pp.EdgePreservingFilter(3, 0.05)(gray, guide).cpu() - g["edge_preserving_guided_r3"]).abs().max() < 1e-4
+    # full-size image against the oracle (the reference's Python triple loop cannot run at this size)
+    big = torch.rand(1, 1, 120, 160, generator=torch.Generator().manual_seed(4))
+    assert (pp.BilateralFilter(7, 1.5, 0.2)(big.cuda()).cpu() - postport.exact_bilateral(big, 7, 1.5, 0.2)).abs().max() < tol
+    with pytest.raises(ValueError):
+        pp.BilateralFilter(4)
+
+
+def test_fused_mask_cleanup_equals_the_two_modules_and_the_oracle():
+    """BASELINE config 5 chain on 480x640 masks: one fused shared-memory pass == edge smoothing then bilateral filter."""
+    from oracle.make_golden_post import blob_masks
+    masks = blob_masks(5, 6, 480, 640)
+    fused = pp.MaskCleanup()(masks.cuda())
+    two = pp.BinaryMaskBilateralFilter()(pp.BinaryMaskEdgeSmoothing()(masks.cuda()))
+    assert torch.equal(fused, two)
+    want_soft = postport.binary_bilateral(postport.edge_smooth(masks), return_soft=True)
+    _check_soft(fused, (want_soft > 0.5).float(), want_soft, 0.5, "MaskCleanup 480x640", max_bad=4)
+    # ragged sizes (partial tiles on both axes), several planes per image
+    odd = blob_masks(9, 2, 70, 45).repeat(1, 3, 1, 1).contiguous()
+    assert torch.equal(pp.MaskCleanup(num_iterations=1, kernel_size=5)(odd.cuda()),
+                       pp.BinaryMaskBilateralFilter(5, 1.5, 0.5, 1)(pp.BinaryMaskEdgeSmoothing()(odd.cuda())))
+    want = postport.binary_bilateral(postport.edge_smooth(odd), 5, 1.5, 0.5, 1)
+    assert _frac_bad(pp.MaskCleanup(num_iterations=1, kernel_size=5)(odd.cuda()), want) <= 1e-4

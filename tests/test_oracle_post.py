@@ -34,3 +34,25 @@ def test_nearest_index_is_cv2_rule():
             ramp = np.arange(src, dtype=np.uint8)[None, :].repeat(2, 0)
             ref = cv2.resize(ramp, (dst, 2), interpolation=cv2.INTER_NEAREST)[0]
             assert np.array_equal(ref, postport.nearest_index(dst, src).astype(np.uint8)), (src, dst)
+
+
+def test_post_variant_ports_match_reference_goldens():
+    """a16/a17 variants (export_edge_smoothing_onnx.py:63-318, hed/edge_smoothing.py:93-170, hed/bilateral_filter.py:9-296)."""
+    g = common.golden("post_variants")
+    m = g["masks"]
+    assert torch.equal(postport.directional_edge_smooth(m), g["directional"])
+    assert torch.equal(postport.adaptive_edge_smooth(m, g["ad_bs"], g["ad_sens"], g["ad_thr"]), g["adaptive"])
+    assert torch.equal(postport.optimized_edge_smooth(m), g["optimized_fp32"])
+    assert torch.equal(postport.optimized_edge_smooth(g["patterns"]), g["optimized_fp32_patterns"])
+    assert torch.equal(postport.multiclass_edge_smooth(g["logits"]), g["multiclass3"])
+    assert torch.equal(postport.multiclass_edge_smooth(g["logits"], iterations=2, apply_softmax=True), g["multiclass3_softmax_it2"])
+    assert torch.equal(postport.multiclass_edge_smooth(g["probs5"]), g["multiclass5"])
+    gray, guide = g["gray"], g["guide"]
+    assert (postport.exact_bilateral(gray[:, :, :12, :16]) - g["bilateral_exact"]).abs().max() < 1e-6
+    assert (postport.exact_bilateral(gray[:1, :, :10, :12], 3, 0.8, 0.3) - g["bilateral_exact_k3"]).abs().max() < 1e-6
+    assert (postport.fast_bilateral(gray) - g["bilateral_fast"]).abs().max() < 1e-6
+    assert (postport.fast_bilateral(gray, 7, 1.5, 0.2, 3) - g["bilateral_fast_k7_it3"]).abs().max() < 1e-6
+    assert (postport.edge_preserving(gray) - g["edge_preserving"]).abs().max() < 1e-5
+    assert (postport.edge_preserving(gray, guide, 3, 0.05) - g["edge_preserving_guided_r3"]).abs().max() < 1e-5
+    # the fp16 flavour of OptimizedEdgeSmoothing only differs from the fp32 one on near-tie pixels
+    assert float((g["optimized_fp16"] != g["optimized_fp32"]).float().mean()) < 2e-3
