@@ -18,7 +18,7 @@ namespace {
 
 constexpr int TW = 32, TH = 32, kThreads = 256;
 constexpr int kMaxR = 8;                                   // largest total halo (fused chain: 1 + 3 + 3 = 7)
-constexpr int kPlane = (TW + 2 * kMaxR) * (TH + 2 * kMaxR);   // floats per shared plane (48 x 48)
+constexpr int kPlane = (TW + 2 * kMaxR) * (TH + 2 * kMaxR) + 16;   // floats per shared plane (48 x 48) + slack for 4-wide strips
 
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
@@ -356,6 +356,78 @@ __device__ __forceinline__ float bilateral_at(const float* __restrict__ s, int w
   return __fadd_rn(__fmul_rn(ew, f), __fmul_rn(__fsub_rn(1.0f, ew), c));
 }
 
+// Four horizontally adjacent outputs per thread: a window row is loaded once (K + 3 values) and feeds all four accumulators,
+// so the kernel leaves the shared-memory-load bound of the one-output form (K*K loads per output -> K*(K+3)/4).  The
+// accumulation order per output is unchanged (ky major, kx minor) -> bit-identical to bilateral_at.  BIN: the input is
+// binary, v*v == v exactly, so the second moment equals the first.
+template <int K, bool BIN>
+__device__ __forceinline__ void bilateral4(const float* __restrict__ s, int w, int ly, int lx, const float* __restrict__ gk, float* __restrict__ o) {
+  constexpr int R = K / 2;
+  float f[4] = {0.0f, 0.0f, 0.0f, 0.0f}, f2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    const float* row = s + (ly + ky - R) * w + lx - R;
+    float v[K + 3], v2[K + 3];
+#pragma unroll
+    for (int i = 0; i < K + 3; ++i) { v[i] = row[i]; if (!BIN) v2[i] = __fmul_rn(v[i], v[i]); }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float wgt = gk[ky * K + kx];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[j] = fmaf(v[kx + j], wgt, f[j]);
+        if (!BIN) f2[j] = fmaf(v2[kx + j], wgt, f2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float c = s[ly * w + lx + j];
+    const float q = BIN ? f[j] : f2[j];
+    const float var = fmaxf(__fsub_rn(q, __fmul_rn(f[j], f[j])), 0.0f);
+    const float ew = expf(__fmul_rn(-var, 10.0f));
+    o[j] = __fadd_rn(__fmul_rn(ew, f[j]), __fmul_rn(__fsub_rn(1.0f, ew), c));
+  }
+}
+
+template <bool BIN>
+__device__ __forceinline__ void bilateral4_k(const float* s, int w, int ly, int lx, const float* gk, int k, float* o) {
+  switch (k) {
+    case 3: bilateral4<3, BIN>(s, w, ly, lx, gk, o); break;
+    case 5: bilateral4<5, BIN>(s, w, ly, lx, gk, o); break;
+    case 7: bilateral4<7, BIN>(s, w, ly, lx, gk, o); break;
+    case 9: bilateral4<9, BIN>(s, w, ly, lx, gk, o); break;
+    default:
+      for (int j = 0; j < 4; ++j) o[j] = bilateral_at(s, w, ly, lx + j, gk, k);
+  }
+}
+
+// one bilateral iteration over the region with margin m around the tile (window halo `halo`, pitch w)
+template <bool BIN>
+__device__ __forceinline__ void bilateral_stage(const float* __restrict__ src, float* __restrict__ dst, const Tile& t, int halo, int m, int w,
+                                                const float* __restrict__ gk, int k, bool last, float thr, float* __restrict__ out_plane) {
+  const int rw = TW + 2 * m, rh = TH + 2 * m, strips = (rw + 3) / 4;
+  for (int i = threadIdx.x; i < strips * rh; i += kThreads) {
+    const int ry = i / strips, rx = (i - ry * strips) * 4;
+    const int ly = ry + halo - m, lx = rx + halo - m;
+    const int y = t.y0 - halo + ly;
+    if (y < 0 || y >= t.H) {                       // whole strip outside the image: zero padding of the next stage
+      if (!last) for (int j = 0; j < 4 && rx + j < rw; ++j) dst[ly * w + lx + j] = 0.0f;
+      continue;
+    }
+    float o[4];
+    bilateral4_k<BIN>(src, w, ly, lx, gk, k, o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (rx + j >= rw) break;
+      const int x = t.x0 - halo + lx + j;
+      const bool in_img = x >= 0 && x < t.W;
+      if (!last) dst[ly * w + lx + j] = in_img ? o[j] : 0.0f;
+      else if (in_img) out_plane[(long long)y * t.W + x] = o[j] > thr ? 1.0f : 0.0f;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) mask_cleanup_fused_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
                                                                       const float* __restrict__ gauss, int k, int iterations, float thr,
                                                                       float* __restrict__ out) {
@@ -383,15 +455,8 @@ __global__ void __launch_bounds__(kThreads) mask_cleanup_fused_kernel(const floa
     float* tmp = src; src = dst; dst = tmp;
     m -= R;
     const bool last = it == iterations - 1;
-    for (int i = threadIdx.x; i < (TW + 2 * m) * (TH + 2 * m); i += kThreads) {
-      const int ry = i / (TW + 2 * m), rx = i - ry * (TW + 2 * m);
-      const int ly = ry + halo - m, lx = rx + halo - m;
-      const int y = t.y0 - halo + ly, x = t.x0 - halo + lx;
-      const bool in_img = inside(t, y, x);
-      const float v = in_img ? bilateral_at(src, w, ly, lx, gk, k) : 0.0f;
-      if (!last) dst[ly * w + lx] = v;
-      else if (in_img) out[plane + (long long)y * W + x] = v > thr ? 1.0f : 0.0f;
-    }
+    if (it == 0) bilateral_stage<true>(src, dst, t, halo, m, w, gk, k, last, thr, out + plane);     // input of iteration 0 is {0,1}
+    else bilateral_stage<false>(src, dst, t, halo, m, w, gk, k, last, thr, out + plane);
     __syncthreads();
   }
 }
@@ -414,15 +479,7 @@ __global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const f
   for (int it = 0; it < iterations; ++it) {
     m -= R;
     const bool last = it == iterations - 1;
-    for (int i = threadIdx.x; i < (TW + 2 * m) * (TH + 2 * m); i += kThreads) {
-      const int ry = i / (TW + 2 * m), rx = i - ry * (TW + 2 * m);
-      const int ly = ry + halo - m, lx = rx + halo - m;
-      const int y = t.y0 - halo + ly, x = t.x0 - halo + lx;
-      const bool in_img = inside(t, y, x);
-      const float v = in_img ? bilateral_at(src, w, ly, lx, gk, k) : 0.0f;
-      if (!last) dst[ly * w + lx] = v;
-      else if (in_img) out[plane + (long long)y * W + x] = v > thr ? 1.0f : 0.0f;
-    }
+    bilateral_stage<false>(src, dst, t, halo, m, w, gk, k, last, thr, out + plane);
     __syncthreads();
     float* tmp = src; src = dst; dst = tmp;
   }

@@ -55,5 +55,9 @@ gemm(640, 64, 48, 128, 256, 1, RES_MUL, aux=True, act=3)
 gemm(640, 64, 48, 256, 256, 3, RES_ADD, aux=True)
 gemm(640, 64, 48, 256, 256, 3, RES_ADD)
 p.replay()
+# post-processing: the fused clean-up chain on 64 full-image masks (BASELINE config 5)
+from human_instance_segmentation_b200 import postprocess as pp  # noqa: E402
+masks = (torch.rand(64, 1, 480, 640, device=dev) > 0.5).float()
+pp.MaskCleanup().to(dev)(masks)
 torch.cuda.synchronize()
 print("ok")
