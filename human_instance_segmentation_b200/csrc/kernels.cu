@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -405,6 +406,124 @@ __global__ void __launch_bounds__(kDwThreads, 3) depthwise_kernel(const DwParams
       float s = 0.0f;
       for (int t = (g2 - first + cgs) % cgs; t < (int)blockDim.x; t += cgs) s += s_pool[t * VEC + e];
       dst[c] = s;
+    }
+  }
+}
+
+// ---- shared-memory tiled depthwise conv (the one the path runs).  CTA = 8 output rows x (8 strips of XPT columns) x 32 channels:
+// the input window of the tile is staged once in shared memory (80-byte pixel pitch: the four 16-byte channel vectors of a pixel
+// plus 16 B of padding, so the strips of a quarter-warp fall in distinct banks), the K*K x 32 filter taps sit next to it, and a
+// thread produces XPT adjacent outputs of one 8-channel vector: a window row is read once (NX vectors) for all XPT outputs.
+// 256 threads, <= 64 registers of state -> 2-3 CTAs per SM instead of the 12 warps of the register-resident form above.
+// Per-(image, tile) channel sums of the fp16-rounded outputs go to pool[n][tile][c] in a fixed order (deterministic SE pooling).
+constexpr int kDw2Threads = 256, kDw2Rows = 8, kDw2Strips = 8, kDw2Cb = 32, kDw2Pitch = 80;
+
+template <int K, int S, int XPT>
+struct Dw2Cfg {
+  static constexpr int TOW = kDw2Strips * XPT, TOH = kDw2Rows;
+  static constexpr int IW = (TOW - 1) * S + K, IH = (TOH - 1) * S + K;
+  static constexpr int NX = (XPT - 1) * S + K;                       // window vectors a thread reads per filter row
+  static constexpr int kInBytes = IW * IH * kDw2Pitch;
+  static constexpr int kWBytes = K * K * kDw2Cb * 2;
+  static constexpr int kSmem = kInBytes + kWBytes + kDw2Threads * 8 * 4;   // + pooling scratch
+};
+
+template <int K, int S, int XPT, int ACT>
+__global__ void __launch_bounds__(kDw2Threads) depthwise_tiled_kernel(const DwParams p, int tiles_x) {
+  using Cfg = Dw2Cfg<K, S, XPT>;
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  unsigned char* s_in = dw_smem;
+  __half* s_w = reinterpret_cast<__half*>(dw_smem + Cfg::kInBytes);
+  float* s_pool = reinterpret_cast<float*>(dw_smem + Cfg::kInBytes + Cfg::kWBytes);
+  const int n = blockIdx.z, cb0 = blockIdx.y * kDw2Cb;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int oy0 = ty * Cfg::TOH, ox0 = tx * Cfg::TOW;
+  const int iy0 = oy0 * S - p.pad, ix0 = ox0 * S - p.pad;
+  const int nvec = min(4, (p.C - cb0) >> 3);                          // valid 8-channel vectors of this channel block
+  // ---- stage the window (zero padding resolved here) and the filter taps
+  const __half* inb = p.in + (long long)n * p.H * p.W * p.in_cs + cb0;
+  // cp.async (zero-filling form): every load of the window is in flight at once, no register round trip
+  const uint32_t s_in_addr = (uint32_t)__cvta_generic_to_shared(s_in);
+  for (int i = threadIdx.x; i < Cfg::IW * Cfg::IH * 4; i += kDw2Threads) {
+    const int v = i & 3, px = i >> 2;
+    const int ly = px / Cfg::IW, lx = px - ly * Cfg::IW;
+    const int iy = iy0 + ly, ix = ix0 + lx;
+    const bool ok = v < nvec && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+    const __half* src = ok ? inb + ((long long)iy * p.W + ix) * p.in_cs + v * 8 : p.in;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_in_addr + (uint32_t)(px * kDw2Pitch + v * 16)), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+  }
+  for (int i = threadIdx.x; i < K * K * 4; i += kDw2Threads) {
+    const int v = i & 3, t = i >> 2;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (v < nvec) val = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)t * p.C + cb0 + v * 8));
+    *reinterpret_cast<uint4*>(s_w + t * kDw2Cb + v * 8) = val;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // ---- compute: lane -> (vector v, strip), warp -> output row
+  const int v = threadIdx.x & 3, strip = (threadIdx.x >> 2) & 7, row = threadIdx.x >> 5;
+  const int c0 = cb0 + v * 8;
+  float acc[XPT][8];
+#pragma unroll
+  for (int j = 0; j < XPT; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.0f;
+  const unsigned char* base = s_in + ((row * S) * Cfg::IW + strip * XPT * S) * kDw2Pitch + v * 16;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    float xf[Cfg::NX][8];
+#pragma unroll
+    for (int i = 0; i < Cfg::NX; ++i) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(base + (ky * Cfg::IW + i) * kDw2Pitch);
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); xf[i][2 * e] = f.x; xf[i][2 * e + 1] = f.y; }
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(s_w + (ky * K + kx) * kDw2Cb + v * 8);
+      const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+      float wf[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(wh[e]); wf[2 * e] = f.x; wf[2 * e + 1] = f.y; }
+#pragma unroll
+      for (int j = 0; j < XPT; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(xf[j * S + kx][e], wf[e], acc[j][e]);
+    }
+  }
+  // ---- BN + activation, store, per-thread channel sums of what the next layer will read
+  float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int oy = oy0 + row;
+  if (v < nvec && oy < p.Ho) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+#pragma unroll
+    for (int j = 0; j < XPT; ++j) {
+      const int ox = ox0 + strip * XPT + j;
+      if (ox < p.Wo) {
+        uint4 ov;
+        __half2* o = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          o[e >> 1] = __floats2half2_rn(act_ct<ACT>(acc[j][e] * sc[e] + sh[e]), act_ct<ACT>(acc[j][e + 1] * sc[e + 1] + sh[e + 1]));
+          const float2 rf = __half22float2(o[e >> 1]);
+          psum[e] += rf.x; psum[e + 1] += rf.y;
+        }
+        *reinterpret_cast<uint4*>(p.out + ((long long)(n * p.Ho + oy) * p.Wo + ox) * p.out_cs + c0) = ov;
+      }
+    }
+  }
+  if (p.pool) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = psum[e];
+    __syncthreads();
+    if (threadIdx.x < kDw2Cb && cb0 + (int)threadIdx.x < p.C) {          // one thread per channel, fixed summation order
+      const int vv = threadIdx.x >> 3, e = threadIdx.x & 7;
+      float t = 0.0f;
+      for (int q = 0; q < kDw2Threads / 4; ++q) t += s_pool[(q * 4 + vv) * 8 + e];
+      p.pool[((long long)n * gridDim.x + blockIdx.x) * p.C + cb0 + threadIdx.x] = t;
     }
   }
 }
@@ -970,10 +1089,18 @@ static int dw_grid_x(int N, int Ho, int Wo, int C, int k) {
   return pool_grid_x(per_img, kDwThreads, N, 12, cgs);        // ~12 blocks (4 waves of 3 resident) per SM over the whole batch
 }
 
+// tiled kernel geometry: 4 output columns per thread (32-wide tiles) for stride 1 on wide images, 2 otherwise
+static inline int dw2_xpt(int Wo, int stride) { return (stride == 1 && Wo >= 64) ? 4 : 2; }
+static inline bool dw_use_tiled() { const char* e = getenv("HIS_DW_TILED"); return !e || atoi(e) != 0; }
+
 int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride) {
   const int pad = ((stride - 1) + (k - 1)) / 2;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   if (C <= 0 || C % 8) return 0;
+  if (dw_use_tiled()) {
+    const int tow = kDw2Strips * dw2_xpt(Wo, stride);
+    return ((Wo + tow - 1) / tow) * ((Ho + kDw2Rows - 1) / kDw2Rows);
+  }
   return dw_grid_x(N, Ho, Wo, C, k);
 }
 
@@ -996,6 +1123,33 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   p.k = k; p.stride = stride; p.pad = ((stride - 1) + (k - 1)) / 2; p.Ho = (H + 2 * p.pad - k) / stride + 1; p.Wo = (W + 2 * p.pad - k) / stride + 1;
   p.act = act; p.out = (__half*)out; p.out_cs = out_cs; p.pool = pool_sums;
   if ((long long)p.Ho * p.Wo * (C / 4) >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: image too large");
+  if (dw_use_tiled() && N <= 65535) {
+    const int xpt = dw2_xpt(p.Wo, stride), tow = kDw2Strips * xpt;
+    const int tiles_x = (p.Wo + tow - 1) / tow, tiles_y = (p.Ho + kDw2Rows - 1) / kDw2Rows;
+    dim3 g2(tiles_x * tiles_y, (C + kDw2Cb - 1) / kDw2Cb, N);
+#define DW2_LAUNCH(K_, S_, X_)                                                                                                   \
+  do {                                                                                                                           \
+    constexpr int smem = Dw2Cfg<K_, S_, X_>::kSmem;                                                                              \
+    if (act == HIS_ACT_SILU) {                                                                                                   \
+      static bool attr_a = false;                                                                                                \
+      if (!attr_a) { cudaFuncSetAttribute(depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_a = true; } \
+      depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_SILU><<<g2, kDw2Threads, smem, ST>>>(p, tiles_x);                               \
+    } else {                                                                                                                     \
+      static bool attr_b = false;                                                                                                \
+      if (!attr_b) { cudaFuncSetAttribute(depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_b = true; } \
+      depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_NONE><<<g2, kDw2Threads, smem, ST>>>(p, tiles_x);                               \
+    }                                                                                                                            \
+  } while (0)
+    if (k == 3 && stride == 1 && xpt == 4) DW2_LAUNCH(3, 1, 4);
+    else if (k == 3 && stride == 1) DW2_LAUNCH(3, 1, 2);
+    else if (k == 5 && stride == 1 && xpt == 4) DW2_LAUNCH(5, 1, 4);
+    else if (k == 5 && stride == 1) DW2_LAUNCH(5, 1, 2);
+    else if (k == 3) DW2_LAUNCH(3, 2, 2);
+    else DW2_LAUNCH(5, 2, 2);
+#undef DW2_LAUNCH
+    HIS_CHECK_LAUNCH();
+    return HIS_OK;
+  }
   dim3 grid(dw_grid_x(N, p.Ho, p.Wo, C, k), N);
   const size_t sm = pool_sums ? kDwThreads * dw_vec(k) * sizeof(float) : 0;
 #define DW_LAUNCH(K_, S_, V_)                                                                                        \
