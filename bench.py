@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op time table of one instrumented step to stderr")
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--no-graph", action="store_true", help="replay the launch plan kernel by kernel instead of as one CUDA graph")
     args = ap.parse_args()
     if args.workload == "post":
         return run_post(args)
@@ -314,6 +315,7 @@ def main():
     for ra in (model.roi_align_mask, model.roi_align_rgb):       # exporter convention spatial_scale=(H,W)
         ra.spatial_scale = (float(h), float(w)); ra.spatial_scale_h, ra.spatial_scale_w = float(h), float(w)
     model.copy_outputs = False
+    model.use_cuda_graph = not args.no_graph          # launch-bound tail of ~200 small kernels -> one graph submission per step
     images_h, rois_h = synth_batch(100 + rank, n_img, h, w, per_image)
     images_h, rois_h = images_h.pin_memory(), rois_h.pin_memory()
     images_d, rois_d = images_h.to(dev), rois_h.to(dev)
