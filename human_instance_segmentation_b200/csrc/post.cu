@@ -201,6 +201,38 @@ __global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int
   }
 }
 
+// evaluate_model's metric core (hed/train_utils.py:262-292): per-ROI 3x3 confusion counts of (ground-truth class, argmax
+// class).  The reference moves predictions to the CPU and runs Python double loops per sample; everything it reports --
+// the three confusion matrices, per-class IoUs, detection rates -- is a function of these nine integers per ROI.
+// One CTA per (ROI, slice): warp-shuffle + shared-memory integer reduction, then one atomicAdd per counter (integers:
+// order independent, deterministic).  gt: class labels 0..2 as uint8 or int64.
+template <typename T>
+__global__ void eval_confusion_kernel(const float* __restrict__ logits, const T* __restrict__ gt, long long HW, int* __restrict__ counts) {
+  __shared__ int s_cnt[9];
+  const int n = blockIdx.y;
+  if (threadIdx.x < 9) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const float* l = logits + (long long)n * 3 * HW;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const float l0 = l[p], l1 = l[HW + p], l2 = l[2 * HW + p];
+    const int pred = (l1 > l0) ? ((l2 > l1) ? 2 : 1) : ((l2 > l0) ? 2 : 0);      // torch.argmax: first maximum
+    const int t = (int)gt[(long long)n * HW + p];
+    if (t >= 0 && t < 3) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c[k] += (k == t * 3 + pred) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    int v = c[k];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9 && s_cnt[threadIdx.x]) atomicAdd(counts + n * 9 + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -269,6 +301,21 @@ int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float
   minmax_kernel<<<g, kThreads, 0, ST>>>(ws0, N, H, W, morph, 1, 0, ws1);         // close: dilate
   minmax_kernel<<<g, kThreads, 0, ST>>>(ws1, N, H, W, morph, 0, 0, ws0);         //        erode
   threshold_kernel<<<g, kThreads, 0, ST>>>(ws0, total, 0.5f, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_eval_confusion(const float* logits, const void* gt, int gt_is_int64, int N, int H, int W, int* counts, void* stream) {
+  if (!logits || !gt || !counts) return his_set_error(HIS_ERR_INVALID_ARG, "eval_confusion: null pointer");
+  if (N == 0) return HIS_OK;
+  if (N > 65535) return his_set_error(HIS_ERR_UNSUPPORTED, "eval_confusion: at most 65535 ROIs per call (chunk the batch)");
+  if (cudaMemsetAsync(counts, 0, (size_t)N * 9 * sizeof(int), ST) != cudaSuccess) return his_set_error(HIS_ERR_LAUNCH, "memset failed");
+  const long long HW = (long long)H * W;
+  int gx = (int)((HW + kThreads * 8 - 1) / (kThreads * 8));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, N);
+  if (gt_is_int64) eval_confusion_kernel<long long><<<grid, kThreads, 0, ST>>>(logits, (const long long*)gt, HW, counts);
+  else eval_confusion_kernel<unsigned char><<<grid, kThreads, 0, ST>>>(logits, (const unsigned char*)gt, HW, counts);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

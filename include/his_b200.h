@@ -187,6 +187,11 @@ int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float
 int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W,
                    void* stream);
 
+/* ---- evaluate_model's metric core, hed/train_utils.py:262-292 (argmax, calculate_confusion_matrix :25-47, the per-sample
+ * Python loops of the 2x2 matrices and calculate_iou :14-22): per-ROI 3x3 confusion counts counts[n][gt*3+pred] (int32,
+ * zeroed by the call) of 3-class logits [N,3,H,W] against labels [N,H,W] (uint8, or int64 when gt_is_int64). */
+int his_eval_confusion(const float* logits, const void* gt, int gt_is_int64, int N, int H, int W, int* counts, void* stream);
+
 /* ---- shared-memory tiled stencils (csrc/post_stencil.cu): one 32x32 tile + halo per CTA, the plane is read once.
  * All take N planes [N,H,W] fp32 (a [B,C,H,W] tensor is B*C planes), N <= 65535 per call.
  * his_post_edge_smooth_tiled: BinaryMaskEdgeSmoothing, hed/edge_smoothing.py:10-90 (same result as his_post_edge_smooth).

@@ -195,6 +195,9 @@ def main():
     if args.only in ("all", "post"):
         from . import make_golden_post
         make_golden_post.make_post_goldens(GOLDEN)
+    if args.only in ("all", "post", "eval"):
+        from . import make_golden_post
+        make_golden_post.make_eval_goldens(GOLDEN)
     if args.only in ("all", "post", "post_variants"):
         from . import make_golden_post
         make_golden_post.make_post_variant_goldens(GOLDEN)

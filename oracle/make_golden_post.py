@@ -109,3 +109,14 @@ def make_post_goldens(golden_dir: str):
     out["paste_logits"], out["paste_rois"], out["paste_canvas"], out["paste_target"] = logits.numpy(), rois.numpy(), canvas, target
     np.savez_compressed(os.path.join(golden_dir, "post.npz"), **out)
     print("post goldens:", {k: v.shape for k, v in out.items()})
+
+
+def make_eval_goldens(golden_dir: str):
+    """evaluate_model's prediction metrics with the REFERENCE's helper functions (hed/train_utils.py:14-47,85-106) driving
+    the restated loop of oracle/evalport.py -> tests/golden/eval_metrics.npz."""
+    from . import evalport
+    fns = refload.ref_functions_from_script("src/human_edge_detection/train_utils.py",
+                                            ["calculate_iou", "calculate_confusion_matrix", "calculate_detection_metrics"])
+    m = evalport.evaluate(evalport.synth_eval_batches(), helpers=fns)
+    np.savez_compressed(os.path.join(golden_dir, "eval_metrics.npz"), **{k: np.asarray(v) for k, v in m.items()})
+    print("eval goldens:", {k: (v if np.ndim(v) == 0 else np.asarray(v).tolist()) for k, v in m.items()})
