@@ -93,6 +93,9 @@ struct ConvGemmParams {
   int b_resident;       // halo mode: the whole weight set stays in shared memory (loaded once per CTA)
   float inv_tiles_x, inv_tiles_y;   // fast work decode (num_work < 2^21, single N tile, no groups)
   int fast_decode;
+  // per-pixel (GEMM row) extras: y = act(row_scale[pix]*acc + shift ...) and per-pixel channel mean / max of y -> stats[pix][2]
+  // (SpatialAttentionModule, attention_modules.py:67-113: the gate multiplies the next conv's input, the statistics feed it)
+  const float* row_scale; float* stats_out;
   int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
@@ -557,6 +560,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const long long pix = ((long long)it.img * p.H + py) * p.W + px;
       float* aux_px = nullptr;
       if (EPI == EPI_AUX && inb) aux_px = p.aux_out + ((long long)it.img * p.cout * p.H + py) * p.W + px;
+      const float rs = (p.row_scale && inb) ? __ldg(p.row_scale + pix) : 1.0f;
+      float st_sum = 0.0f, st_max = -INFINITY;
       for (int j = 0; j < nchunks; ++j) {
         const bool direct = j >= ntma;
         const int b = cc & 1;
@@ -608,12 +613,16 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float t = __uint_as_float(v[i * 8 + e]) + sh[e];
+              float t = __uint_as_float(v[i * 8 + e]) * rs + sh[e];
               if (RES == HIS_RES_ADD) t += r[e];
               t = epi_act<ACTC>(t, p);
               if (EPI == EPI_AUX) { if (aux_px && c + e < p.cout) aux_px[(long long)(c + e) * p.H * p.W] = t; }
               if (RES == HIS_RES_MUL) t *= r[e];
               y[e] = t;
+            }
+            if (p.stats_out) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (c + e < p.cout) { st_sum += y[e]; st_max = fmaxf(st_max, y[e]); }
             }
             if (TAIL) {
               const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.tail_w + c)), w1 = __ldg(reinterpret_cast<const float4*>(p.tail_w + c + 4));
@@ -646,6 +655,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
         if (!direct) ++cc;
+      }
+      if (p.stats_out && inb) {
+        p.stats_out[pix * 2] = st_sum / (float)p.cout;
+        p.stats_out[pix * 2 + 1] = st_max;
       }
       if (TAIL) {
         if (py < p.H && px < p.W) {
@@ -980,6 +993,14 @@ int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image) 
   int rc = encode_weight_map(&pl->tmB, w_packed_per_image, pl->cin_pad, rows * p.n_img, p.block_n, pl->bk);
   if (rc) return rc;
   p.b_img_rows = (int)rows;
+  return HIS_OK;
+}
+
+int his_conv_gemm_set_row_ops(void* plan, const float* row_scale, float* stats_out) {
+  if (!plan) return his_set_error(HIS_ERR_INVALID_ARG, "set_row_ops: null plan");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  if (stats_out && (pl->p.n_tiles != 1 || pl->transposed)) return his_set_error(HIS_ERR_UNSUPPORTED, "set_row_ops: statistics need a single N tile, not transposed");
+  pl->p.row_scale = row_scale; pl->p.stats_out = stats_out;
   return HIS_OK;
 }
 

@@ -840,6 +840,29 @@ __global__ void spatial_attention_apply_kernel(const __half* __restrict__ in, in
   }
 }
 
+// sigmoid(conv_kxk([mean,max])) alone: the statistics come from the producing GEMM's epilogue and the gate is applied as a
+// row scale inside the consuming GEMM (his_conv_gemm_set_row_ops), so the 256-channel tensor is not touched here
+__global__ void spatial_gate_kernel(const float* __restrict__ stats, int N, int H, int W, const float* __restrict__ w, int k, float* __restrict__ gate) {
+  const long long total = (long long)N * H * W;
+  const int pad = k / 2;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W), y = (int)((pix / W) % H);
+    const long long img0 = pix - ((long long)y * W + x);
+    float s = 0.0f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = y + ky - pad;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = x + kx - pad;
+        if (ix < 0 || ix >= W) continue;
+        const float2 st = __ldg(reinterpret_cast<const float2*>(stats + (img0 + (long long)iy * W + ix) * 2));
+        s = fmaf(st.x, __ldg(w + ky * k + kx), s); s = fmaf(st.y, __ldg(w + k * k + ky * k + kx), s);
+      }
+    }
+    gate[pix] = his_sigmoid(s);
+  }
+}
+
 // ------------------------------------------------------------------------------------ head tails
 // upsample_bg_fg (..._refinement.py:501-506): ConvT(2->32,k2,s2) + norm(BN folded) + act + 1x1(32->2), NCHW fp32 in/out.
 //   wt: [2][32][2][2] (PyTorch ConvTranspose2d weight), s/t: folded scale/shift [32] (bias folded in), w1: [2][32], b1: [2]
@@ -1289,6 +1312,15 @@ int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs,
   HIS_CHECK_LAUNCH();
   spatial_attention_apply_kernel<<<grid_for(pixels * 32), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, stats_ws, w, k,
                                                                             (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_spatial_gate(const float* stats, int N, int H, int W, const float* w, int k, float* gate, void* stream) {
+  if (!stats || !w || !gate) return his_set_error(HIS_ERR_INVALID_ARG, "spatial_gate: null pointer");
+  const long long total = (long long)N * H * W;
+  if (total == 0) return HIS_OK;
+  spatial_gate_kernel<<<grid_for(total), kThreads, 0, ST>>>(stats, N, H, W, w, k, gate);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

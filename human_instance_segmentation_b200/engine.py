@@ -26,13 +26,14 @@ def round_up(x: int, m: int) -> int:
 class Act:
     """A channel slice [c_off, c_off+C) of an NHWC fp16 buffer [N,H,W,cs]."""
 
-    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off")
+    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off", "zero_tail")
 
     def __init__(self, buf: torch.Tensor, C: int, c_off: int = 0):
         assert buf.dtype == torch.float16 and buf.dim() == 4 and buf.is_contiguous()
         self.buf = buf
         self.N, self.H, self.W, self.cs = buf.shape
         self.C, self.c_off = C, c_off
+        self.zero_tail = False          # True: channels [C, cs) are zero and nobody ever writes them (see Plan.act_zeroed)
         assert c_off % 8 == 0 and self.cs % 8 == 0 and c_off + C <= self.cs
 
     @property
@@ -53,6 +54,7 @@ class NullAct(Act):
     def __init__(self, buf: torch.Tensor, N: int, H: int, W: int, C: int):
         self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
         self.cs, self.c_off = round_up(C, 8), 0
+        self.zero_tail = False
 
 
 class Plan:
@@ -78,6 +80,14 @@ class Plan:
         buf = torch.empty((N, H, W, cs), dtype=torch.float16, device=self.device)
         self.keep.append(buf)
         return Act(buf, C)
+
+    def act_zeroed(self, N, H, W, C) -> Act:
+        """Activation whose channel tail [C, cs) is zero for the plan's lifetime: producers write exactly C channels."""
+        buf = torch.zeros((N, H, W, round_up(C, 8)), dtype=torch.float16, device=self.device)
+        self.keep.append(buf)
+        a = Act(buf, C)
+        a.zero_tail = True
+        return a
 
     def null_act(self, N, H, W, C) -> NullAct:
         buf = torch.zeros(64, dtype=torch.float16, device=self.device)
@@ -112,7 +122,8 @@ class Plan:
     # -------------------------------------------------------------- ops
     def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, shift: torch.Tensor, out: Act,
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
-                  transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None):
+                  transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None,
+                  row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None):
         """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
         channels into the epilogue (his_conv_gemm_set_tail).  aux_f32: fp32 NCHW copy of the output written from the
         epilogue (his_conv_gemm_set_aux).  in_gate = (gate fp32 [N, Cin], fp16 scratch >= N*rows*cin_pad): per-image
@@ -141,6 +152,10 @@ class Plan:
         if aux_f32 is not None:
             _lib.check(L.his_conv_gemm_set_aux(h, aux_f32.data_ptr()), "his_conv_gemm_set_aux")
             self.keep.append(aux_f32)
+        if row_scale is not None or stats_out is not None:
+            _lib.check(L.his_conv_gemm_set_row_ops(h, row_scale.data_ptr() if row_scale is not None else None,
+                                                   stats_out.data_ptr() if stats_out is not None else None), "his_conv_gemm_set_row_ops")
+            self.keep += [t for t in (row_scale, stats_out) if t is not None]
         if in_gate is not None:
             gate, wimg = in_gate
             rows = w_packed.numel() // cin_pad

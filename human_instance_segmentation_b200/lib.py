@@ -78,6 +78,7 @@ SIGNATURES = {
                              _P, c_int, c_int, c_int, c_float, c_int],
     "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
     "his_conv_gemm_set_aux": [_P, _P],
+    "his_conv_gemm_set_row_ops": [_P, _P, _P],
     "his_conv_gemm_set_image_weights": [_P, _P],
     "his_conv_gemm_run": [_P, _P],
     "his_conv_gemm_destroy": [_P],
@@ -95,6 +96,7 @@ SIGNATURES = {
     "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],
     "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P],
     "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P],
+    "his_spatial_gate": [_P, c_int, c_int, c_int, _P, c_int, _P, _P],
     "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_resize_nearest": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_resize_bilinear_f32": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],

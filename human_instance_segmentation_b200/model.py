@@ -416,7 +416,7 @@ class _BuiltPlan:
 
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
-             in_gate=None) -> Optional[Act]:
+             in_gate=None, row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> Optional[Act]:
         """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
         tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
         epilogue; the wide activation itself is then not written (its only consumer is the tail).
@@ -425,8 +425,8 @@ class _BuiltPlan:
         if norm is not None and not self._is_bn(norm):
             # LayerNorm2d (hed/model.py:18-38): per-sample statistics over (C,H,W) cannot fold into the conv ->
             # conv(+bias) to fp16, then the two-launch LayerNorm kernel applies norm + residual + activation.
-            assert tail is None and out_f32 is None and aux_f32 is None
-            raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate)
+            assert tail is None and out_f32 is None and aux_f32 is None and stats_out is None
+            raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate, row_scale=row_scale)
             return self.layernorm(raw, norm, act, res, res_mode, out)
         transposed = isinstance(conv, nn.ConvTranspose2d)
         w = conv.weight
@@ -437,6 +437,13 @@ class _BuiltPlan:
         scale, shift = fold_bn(conv.bias, norm, cout)
         oh, ow = (2 * x.H, 2 * x.W) if transposed else (x.H, x.W)
         use_gemm = cin >= 16 and cout >= 16 and (transposed or k in (1, 3)) and out_f32 is None
+        if (not use_gemm and not transposed and k == 3 and cin < 8 and cout >= 16 and out_f32 is None and res is None
+                and getattr(x, "zero_tail", False) and x.cs >= 8 and x.c_off == 0):
+            # Cin = 3 (RGB patches): the buffer's channel tail is zero by construction, so the layer runs on the tensor cores as a
+            # Cin = 8 halo-mode GEMM with zero-padded weights (K = 16 per tap) instead of the CUDA-core direct kernel
+            w = torch.cat([w.detach().float().cpu(), torch.zeros(cout, 8 - cin, k, k)], 1)
+            x = Act(x.buf, 8)
+            cin, use_gemm = 8, True
         if out is None and out_f32 is None:
             out = p.null_act(x.N, oh, ow, cout) if (tail is not None and use_gemm) else p.act(x.N, oh, ow, cout)
         if use_gemm:
@@ -453,11 +460,12 @@ class _BuiltPlan:
                 tb = tconv.bias.detach().float().cpu().tolist() + [0.0]
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(shift, slab)), out,
-                        k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate)
+                        k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate,
+                        row_scale=row_scale, stats_out=stats_out)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
-            assert tail is None and aux_f32 is None and in_gate is None
+            assert tail is None and aux_f32 is None and in_gate is None and row_scale is None and stats_out is None
             p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, p.const(pack_direct_weight(w), torch.float16), p.const(scale), p.const(shift),
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
@@ -475,9 +483,10 @@ class _BuiltPlan:
               res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs)
         return out
 
-    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None, aux_f32=None) -> Act:
+    def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None, aux_f32=None,
+                       stats_out=None) -> Act:
         t = self.conv(x, rb.conv1, rb.norm1, act)
-        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail, aux_f32=aux_f32)
+        return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail, aux_f32=aux_f32, stats_out=stats_out)
 
     def _aux_fusable(self, cin: int) -> bool:
         """The epilogue export exists for BatchNorm-folded layers whose K block is 64 wide (Cin >= 52)."""
@@ -624,7 +633,7 @@ class _BuiltPlan:
         # --- Dynamic RoI Align (rgb.py:751-755): UNet logits -> channels 256..257 of the combiner input, RGB -> patches
         # (guided head: channel 256 of its 257-channel input_adjust input holds sigmoid(fg logit) instead)
         comb_in = p.act(N, rh, rw, 258 if m.use_refinement else 257)
-        patches = p.act(N, rh, rw, 3)
+        patches = p.act_zeroed(N, rh, rw, 3)
         roi_feat = p.f32(N, 2, rh, rw)
         roi_patch = p.f32(N, 3, rh, rw) if aux_level != "none" else None
         ram, rar = m.roi_align_mask, m.roi_align_rgb
@@ -659,7 +668,7 @@ class _BuiltPlan:
         N, B, H, W = self.Nc, self.B, self.H, self.W
         rh, rw = m.roi_size
         A = ACT["relu"]
-        patches = p.act(N, rh, rw, 3)
+        patches = p.act_zeroed(N, rh, rw, 3)
         roi_patch = p.f32(N, 3, rh, rw) if m.aux_outputs != "none" else None
         ra = m.roi_align
         p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
@@ -736,14 +745,23 @@ class _BuiltPlan:
         gated = self.conv(g2, fg[5], None, ACT["sigmoid"], res=shared, res_mode=RES_MUL, aux_f32=gate_nchw)
         # --- target vs non-target branch
         tb = bh.target_vs_nontarget_branch
-        x = self.residual_block(gated, tb[0], A_ref)
+        fuse_sa = m.use_attention_module and self._is_bn_mode()
+        stats = p.f32(N, rh, rw, 2) if m.use_attention_module else None
+        x = self.residual_block(gated, tb[0], A_ref, stats_out=stats if fuse_sa else None)
         if m.use_attention_module:
-            sa = p.act(N, rh, rw, 256)
-            stats = p.f32(N, rh, rw, 2)
             kk = tb[1].conv.weight.shape[-1]
-            p.add("spatial_attention", L.his_spatial_attention, x.ptr, N, rh, rw, 256, x.cs, p.const(tb[1].conv.weight.reshape(2, kk, kk)).data_ptr(),
-                  kk, stats.data_ptr(), sa.ptr, sa.cs)
-            x = self.conv(sa, tb[3], tb[4], A_ref)                       # ConvT 256->128 k2s2 + norm + act
+            wsa = p.const(tb[1].conv.weight.reshape(2, kk, kk))
+            if fuse_sa:
+                # SpatialAttentionModule without a pass over the 256-channel tensor: channel mean / max come from the residual
+                # block's epilogue, the gate sigmoid(conv7x7(stats)) scales the rows of the ConvT that consumes x
+                # (conv(g*x) = g*conv(x) for a per-pixel g and a 1x1-per-pixel transposed conv)
+                sgate = p.f32(N, rh, rw)
+                p.add("spatial_gate", L.his_spatial_gate, stats.data_ptr(), N, rh, rw, wsa.data_ptr(), kk, sgate.data_ptr())
+                x = self.conv(x, tb[3], tb[4], A_ref, row_scale=sgate)       # ConvT 256->128 k2s2 + norm + act
+            else:
+                sa = p.act(N, rh, rw, 256)
+                p.add("spatial_attention", L.his_spatial_attention, x.ptr, N, rh, rw, 256, x.cs, wsa.data_ptr(), kk, stats.data_ptr(), sa.ptr, sa.cs)
+                x = self.conv(sa, tb[3], tb[4], A_ref)                       # ConvT 256->128 k2s2 + norm + act
             ca = tb[6]
             r = ca.fc1.weight.shape[0]
             parts = L.his_pool_sum_parts(N, x.H * x.W, 128)

@@ -73,6 +73,10 @@ int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float
  * returns in its aux dict: shared_features ..._refinement.py:557, fg_attention :570); with res_mode MUL the copy is the
  * activated value before the product (the gate).  Layers with Cin >= 64 only. */
 int his_conv_gemm_set_aux(void* plan, float* aux_out);
+/* Per-pixel (GEMM row) extras of the SpatialAttentionModule fusion (hed/advanced/attention_modules.py:67-113):
+ * row_scale [n_img*H*W] fp32 (may be NULL): y = act(row_scale[pix]*conv(x) + shift ...), i.e. the conv of the gated input;
+ * stats_out [n_img*H*W][2] fp32 (may be NULL): channel mean and max of this layer's output per pixel. */
+int his_conv_gemm_set_row_ops(void* plan, const float* row_scale, float* stats_out);
 /* Per-image weights: image n reads slab n of w_packed_per_image ([n_img] x the his_conv_gemm_create layout).  Used to fold
  * the squeeze-excite gate of timm's MBConv into the projection conv (his_scale_weights). */
 int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image);
@@ -127,6 +131,8 @@ int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const floa
  * w: fp32 [2][k][k]; stats_ws: fp32 workspace [N*H*W*2]. */
 int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs, const float* w, int k, float* stats_ws,
                           void* out, int out_cs, void* stream);
+/* gate = sigmoid(conv_kxk([mean,max])) from per-pixel statistics [N,H,W,2] (no pass over the feature tensor). */
+int his_spatial_gate(const float* stats, int N, int H, int W, const float* w, int k, float* gate, void* stream);
 
 /* ---- nn.MaxPool2d(2) (..._unet.py:332), nearest resize (smp UnetDecoderBlock), bilinear align_corners=False
  * (F.interpolate at ..._refinement.py:561-566,581-586,772-802) */
