@@ -96,6 +96,9 @@ struct ConvGemmParams {
   // per-pixel (GEMM row) extras: y = act(row_scale[pix]*acc + shift ...) and per-pixel channel mean / max of y -> stats[pix][2]
   // (SpatialAttentionModule, attention_modules.py:67-113: the gate multiplies the next conv's input, the statistics feed it)
   const float* row_scale; float* stats_out;
+  // halo mode, fused nearest 2x upsample (smp UnetDecoderBlock: F.interpolate(x, nearest) then cat with the skip): channels
+  // [0, up_split) are gathered from the low-resolution tensor `up_in` [n, H/2, W/2, up_cs] at (y>>1, x>>1), the rest from `in`
+  const __half* up_in; long long up_sn; int up_cs, up_split;
   int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
@@ -442,12 +445,15 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int c = ptid % CL, pl = ptid / CL;
       // per-thread tables, tile independent: window coordinates of the thread's pixels and their element offsets; the loop
       // below is fully unrolled so they live in registers and the passes are independent instructions streams
-      int rel[NIT], hyx[NIT];
+      int rel[NIT], hyx[NIT], rel_up[NIT];
+      const int W2 = p.W >> 1;
 #pragma unroll
       for (int k = 0; k < NIT; ++k) {
         const int px = pl + k * PL;
         const int hy = px / kHaloW, hx = px - hy * kHaloW;
         rel[k] = hy * p.W * p.in_cs + hx * p.in_cs;
+        // low-resolution source: window origin (y0-1, x0-1) with y0, x0 even -> source pixel (y0/2 + ((hy-1)>>1), x0/2 + ((hx-1)>>1))
+        rel_up[k] = ((hy - 1) >> 1) * W2 * p.up_cs + ((hx - 1) >> 1) * p.up_cs;
         hyx[k] = px < kHaloPix ? ((hy << 16) | hx) : (0x4000 << 16);     // beyond the window: never valid
       }
       int astage = 0; uint32_t aphase = 0;
@@ -455,17 +461,19 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const WorkItem it = decode_work(p, w);
         const int gy0 = it.y0 - 1, gx0 = it.x0 - 1;
         const __half* org = p.in + (long long)it.img * p.in_sn + ((long long)gy0 * p.W + gx0) * p.in_cs;   // window origin (may lie outside)
+        const __half* org_up = p.up_in + (long long)it.img * p.up_sn + ((long long)(it.y0 >> 1) * W2 + (it.x0 >> 1)) * p.up_cs;
         for (int cb = 0; cb < nblk; ++cb) {
           mbar_wait(aempty_bar(astage), aphase ^ 1);
           const int ch = cb * BK + c * 8;
           const bool chok = ch < p.cin && !(p.debug & 2);
           const uint32_t dst = a_base + astage * p.a_stage_bytes + (uint32_t)c * kPlaneBytes + (uint32_t)pl * 16u;
-          const __half* orgc = org + ch;
+          const bool from_up = ch < p.up_split;                       // block uniform: up_split is a multiple of BK
+          const __half* orgc = (from_up ? org_up : org) + ch;
 #pragma unroll
           for (int k = 0; k < NIT; ++k) {
             const bool ok = chok && (unsigned)(gy0 + (hyx[k] >> 16)) < (unsigned)p.H && (unsigned)(gx0 + (hyx[k] & 0xffff)) < (unsigned)p.W;
             if (k * PL + PL <= kHaloPix || pl + k * PL < kHaloPix)
-              cp_async16(dst + (uint32_t)(k * PL) * 16u, ok ? orgc + rel[k] : p.in, ok ? 16u : 0u);
+              cp_async16(dst + (uint32_t)(k * PL) * 16u, ok ? orgc + (from_up ? rel_up[k] : rel[k]) : p.in, ok ? 16u : 0u);
           }
           cp_async_arrive_noinc(afull_bar(astage));
           if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
@@ -900,6 +908,7 @@ int his_conv_gemm_create(void** out_plan,
   if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok ? atoi(e) : 0;   // 0 never, 1 channel-clipped chunks, 2 + clipped tiles
   p.debug = 0;
   if (const char* e = getenv("HIS_GEMM_DEBUG")) p.debug = atoi(e);
+  p.up_in = (const __half*)in; p.up_sn = 0; p.up_cs = 8; p.up_split = 0;      // no fused upsample
   // TMEM accumulator ring: as many buffers as the 512 columns hold (even, <= 8) so that short tiles are not paced by
   // the MMA -> epilogue -> MMA hand-shake latency
   p.acc_stride = (p.block_n + 31) / 32 * 32;
@@ -1002,6 +1011,29 @@ int his_conv_gemm_set_row_ops(void* plan, const float* row_scale, float* stats_o
   if (stats_out && (pl->p.n_tiles != 1 || pl->transposed)) return his_set_error(HIS_ERR_UNSUPPORTED, "set_row_ops: statistics need a single N tile, not transposed");
   pl->p.row_scale = row_scale; pl->p.stats_out = stats_out;
   return HIS_OK;
+}
+
+int his_conv_gemm_set_upsampled_input(void* plan, const void* low, int low_c, int low_cs) {
+  if (!plan || !low) return his_set_error(HIS_ERR_INVALID_ARG, "set_upsampled_input: null pointer");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  ConvGemmParams& p = pl->p;
+  if (!pl->halo || (p.H & 1) || (p.W & 1) || low_c <= 0 || low_c > p.cin || (low_c % pl->bk) || (low_cs % 8) || low_c > low_cs)
+    return his_set_error(HIS_ERR_UNSUPPORTED, "set_upsampled_input: needs a halo-mode 3x3 layer, even H and W, low_c a multiple of the K block");
+  p.up_in = (const __half*)low; p.up_cs = low_cs; p.up_sn = (long long)(p.H >> 1) * (p.W >> 1) * low_cs; p.up_split = low_c;
+  return HIS_OK;
+}
+
+// 1 when his_conv_gemm_set_upsampled_input would accept this layer (same policy as his_conv_gemm_create)
+int his_conv_gemm_can_fuse_upsample(int H, int W, int cin, int cout, int low_c) {
+  int nt = 0, bn = 0;
+  if (his_conv_gemm_tile_n(cout, &nt, &bn) != HIS_OK) return 0;
+  int halo_maxn = 128;
+  if (const char* e = getenv("HIS_GEMM_HALO_MAXN")) halo_maxn = atoi(e);
+  if (const char* e = getenv("HIS_GEMM_HALO")) if (atoi(e) == 0) return 0;
+  if (const char* e = getenv("HIS_GEMM_FUSE_UP")) if (atoi(e) == 0) return 0;
+  if ((cin % 8) || bn > halo_maxn || (H & 1) || (W & 1)) return 0;
+  const int bk = cin > 32 ? 64 : cin > 16 ? 32 : 16;
+  return (low_c > 0 && low_c <= cin && low_c % bk == 0) ? 1 : 0;
 }
 
 int his_conv_gemm_set_aux(void* plan, float* aux_out) {

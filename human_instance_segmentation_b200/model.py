@@ -416,7 +416,8 @@ class _BuiltPlan:
 
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
-             in_gate=None, row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> Optional[Act]:
+             in_gate=None, row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
+             up_input: Optional[Act] = None) -> Optional[Act]:
         """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
         tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
         epilogue; the wide activation itself is then not written (its only consumer is the tail).
@@ -461,7 +462,7 @@ class _BuiltPlan:
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(shift, slab)), out,
                         k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate,
-                        row_scale=row_scale, stats_out=stats_out)
+                        row_scale=row_scale, stats_out=stats_out, up_input=up_input)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
@@ -574,9 +575,14 @@ class _BuiltPlan:
         for i, blk in enumerate(dec.blocks):
             cat = cats[i]
             up = cat.slice(0, blk.cin)
-            p.add("resize_nearest", L.his_resize_nearest, x.ptr, B, x.H, x.W, x.C, x.cs, cat.H, cat.W, up.ptr, up.cs)
             full = Act(cat.buf, blk.cin + blk.cskip)
-            y = self.conv(full, blk.conv1[0], blk.conv1[1], ACT["relu"])
+            fuse_up = (cat.H, cat.W) == (2 * x.H, 2 * x.W) and x.C == blk.cin and \
+                L.his_conv_gemm_can_fuse_upsample(cat.H, cat.W, blk.cin + blk.cskip, blk.conv1[0].weight.shape[0], blk.cin) == 1
+            if fuse_up:   # nearest 2x + concat happen inside the conv's window loads: the upsampled tensor is never materialised
+                y = self.conv(full, blk.conv1[0], blk.conv1[1], ACT["relu"], up_input=x)
+            else:
+                p.add("resize_nearest", L.his_resize_nearest, x.ptr, B, x.H, x.W, x.C, x.cs, cat.H, cat.W, up.ptr, up.cs)
+                y = self.conv(full, blk.conv1[0], blk.conv1[1], ACT["relu"])
             x = self.conv(y, blk.conv2[0], blk.conv2[1], ACT["relu"])
         # segmentation head conv3x3 16->1 (+bias) -> fp32 logits; output_conv 1->2; export-wrapper binary mask
         head = net.segmentation_head[0]

@@ -77,6 +77,12 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out);
  * row_scale [n_img*H*W] fp32 (may be NULL): y = act(row_scale[pix]*conv(x) + shift ...), i.e. the conv of the gated input;
  * stats_out [n_img*H*W][2] fp32 (may be NULL): channel mean and max of this layer's output per pixel. */
 int his_conv_gemm_set_row_ops(void* plan, const float* row_scale, float* stats_out);
+/* Fused nearest 2x upsample + concat of the smp UnetDecoderBlock (F.interpolate(x, mode="nearest") then torch.cat with the
+ * skip): channels [0, low_c) of this 3x3 halo-mode layer's input are gathered from `low` [n_img, H/2, W/2, low_cs] at
+ * (y>>1, x>>1); the remaining channels come from the `in` buffer given at creation (same channel indices).
+ * his_conv_gemm_can_fuse_upsample tells whether a layer qualifies (halo mode, even H and W, low_c % K-block == 0). */
+int his_conv_gemm_set_upsampled_input(void* plan, const void* low, int low_c, int low_cs);
+int his_conv_gemm_can_fuse_upsample(int H, int W, int cin, int cout, int low_c);
 /* Per-image weights: image n reads slab n of w_packed_per_image ([n_img] x the his_conv_gemm_create layout).  Used to fold
  * the squeeze-excite gate of timm's MBConv into the projection conv (his_scale_weights). */
 int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image);
