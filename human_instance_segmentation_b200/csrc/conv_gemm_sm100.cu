@@ -401,7 +401,26 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (p.b_resident) b_units = b_units0 + (uint32_t)(cb * 9) * b_tap_units;
           for (int tg = 0; tg < tgroups; ++tg) {
             if (!p.b_resident) { mbar_wait(full_bar(stage), phase); tc_fence_after(); }
-            if (elect_one()) {
+            if (T == 9) {
+              // all nine taps in one stage (weight-resident / narrow layers): fully unrolled, descriptor offsets are constants
+              if (elect_one()) {
+                const uint64_t ad0 = adesc_hi | a_units, bd0 = bdesc_hi | b_units;
+                if (!(p.debug & 8)) {
+#pragma unroll
+                  for (int t = 0; t < 9; ++t) {
+                    const uint64_t ad = ad0 + (uint64_t)((t / 3) * kHaloW + (t % 3)), bd = bd0 + (uint64_t)t * b_tap_units;
+                    if (t == 0) umma_f16(d_tmem, ad, bd, idesc, cb ? 1u : 0u);
+                    else umma_f16_acc(d_tmem, ad, bd, idesc);
+#pragma unroll
+                    for (int kk = 1; kk < BK / 16; ++kk)
+                      if (kk < nk16) umma_f16_acc(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
+                  }
+                }
+                if (!p.b_resident) umma_commit(empty_bar(stage));
+                umma_commit(aempty_bar(astage));
+                if (cb == nblk - 1) umma_commit(tfull_bar(acc));
+              }
+            } else if (elect_one()) {
               const int tap0 = tg * T;
               const int dy0 = (tap0 * 11) >> 5;                       // tap0 / 3 for 0..8
               uint32_t au = a_units + (uint32_t)(dy0 * kHaloW + (tap0 - dy0 * 3)), bu = b_units;
