@@ -34,6 +34,16 @@ HEAD_GFLOP_PER_ROI = {"b0": 57.84, "b1_enhanced": 93.01, "b7_ultra": 278.44}    
 UNET_GFLOP_PER_IMG = {"b0": 27.72, "b1_enhanced": 29.97, "b7_ultra": 90.21}
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json: dram__bytes_read.sum
+    + dram__bytes_write.sum summed over the kernel's launches of one step / number of launches).  None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -253,7 +263,8 @@ def run_post(args):
                    "api": "postprocess.MaskDilationModule / instance_masks / paste_masks / MaskCleanup on pinned host tensors"},
            "gpu_launches": 5 * args.steps, "launches_per_step": 5,
            "roofline": {"bound": "hbm", "kernel": "mask_cleanup_fused_kernel", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"], "avg_launch_ms": ms_fused,
+                        "frac": achieved / pk["hbm_gbs"], "traffic": measured_traffic("mask_cleanup_fused_kernel:post"), "peak_source": pk["source"],
+                        "avg_launch_ms": ms_fused,
                         "algorithmic_bytes_per_launch": alg_bytes, "share_of_step": ms_fused / ms,
                         "how": "2*H*W*4 bytes per mask (read once + write once) x masks per launch / CUDA-event time of the launch"}}
     if not args.no_cpu_baseline and world == 1:
@@ -401,7 +412,9 @@ def main():
         "gpu_launches": plan.launches * args.steps,
         "launches_per_step": plan.launches,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_sm100_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                     "frac": achieved / pk["tflops"], "traffic": measured_traffic("conv_gemm_sm100_kernel:" + args.workload),
+                     "traffic_note": "DRAM bytes per launch (read+write), averaged over the kernel's launches of one step, ncu capture in profiles/",
+                     "peak_source": pk["source"] + ", sustained bf16",
                      "launches_per_step": len(gemm), "avg_launch_ms": gemm_ms / max(len(gemm), 1),
                      "algorithmic_flop_per_launch": gemm_flops / max(len(gemm), 1), "share_of_step": gemm_ms / step_ms_instr,
                      "how": "sum of algorithmic FLOPs of all conv_gemm launches of one step / sum of their CUDA-event durations "
