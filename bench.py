@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-op time table of one instrumented step to stderr")
     ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e through the blocking model.infer instead of infer_pipelined")
     ap.add_argument("--no-graph", action="store_true", help="replay the launch plan kernel by kernel instead of as one CUDA graph")
     args = ap.parse_args()
     if args.workload == "post":
@@ -359,20 +360,43 @@ def main():
     inst_h = torch.empty((n_rois, 1) + tuple(cfg["mask_size"]), dtype=torch.float32).pin_memory()
     bin_h = torch.empty((n_img, 1, h, w), dtype=torch.float32).pin_memory()
 
+    # two sets of host output buffers: the pipelined API downloads batch i-1 while batch i computes
+    inst_h2, bin_h2 = torch.empty_like(inst_h).pin_memory(), torch.empty_like(bin_h).pin_memory()
+    host_out = [(inst_h, bin_h), (inst_h2, bin_h2)]
+    e2e_i = [0]
+
     def e2e_step():
-        inst, binary = model.infer(images_h, rois_h)
-        inst_h.copy_(inst, non_blocking=True)
-        bin_h.copy_(binary, non_blocking=True)
+        if args.no_pipeline:
+            inst, binary = model.infer(images_h, rois_h)
+            inst_h.copy_(inst, non_blocking=True)
+            bin_h.copy_(binary, non_blocking=True)
+        else:
+            o = host_out[e2e_i[0] & 1]; e2e_i[0] += 1
+            model.infer_pipelined(images_h, rois_h, o[0], o[1])
 
     for _ in range(2):
         e2e_step()
+    model.pipeline_sync()
     barrier()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    model.pipeline_sync()          # every batch of the timed region has landed in host memory (current stream waits for the downloads)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
+    # the same through the blocking call (upload, forward, download strictly one after the other), for comparison
+    ms_e2e_blocking = None
+    if not args.no_pipeline:
+        args.no_pipeline = True
+        e2e_step(); barrier()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e_blocking = e0.elapsed_time(e1) / args.steps
+        args.no_pipeline = False
 
     # ---------------- per-kernel timing for the roofline (instrumented replay right after the timed region)
     timed = plan.run_timed()
@@ -407,8 +431,11 @@ def main():
         "dtype": "f16 operands, f32 accumulate", "data": "synthetic", "config": workload_config(args.workload),
         "clocks": clocks,
         "e2e": {"value": world * n_rois / (ms_e2e * 1e-3), "unit": "ROI-masks/s", "ms_per_step": ms_e2e,
+                "blocking_value": (world * n_rois / (ms_e2e_blocking * 1e-3)) if ms_e2e_blocking else None,
                 "h2d_bytes_per_step": images_h.numel() * 4 + rois_h.numel() * 4, "d2h_bytes_per_step": inst_h.numel() * 4 + bin_h.numel() * 4,
-                "api": "model.infer(images_host_pinned, rois_host) -> (instance_masks, binary_masks) copied to pinned host"},
+                "api": ("model.infer(images_host_pinned, rois_host) -> (instance_masks, binary_masks) copied to pinned host" if args.no_pipeline else
+                        "model.infer_pipelined(images_host_pinned, rois_host, instance_masks_host, binary_masks_host): upload / forward / "
+                        "download of consecutive batches overlap on three streams, two launch plans; every step's H2D and D2H are inside the timed region")},
         "gpu_launches": plan.launches * args.steps,
         "launches_per_step": plan.launches,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_sm100_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",

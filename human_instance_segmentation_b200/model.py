@@ -106,6 +106,9 @@ class _PlannedModel(nn.Module):
     def invalidate(self):
         """Drop packed weights / plans (call after mutating parameters in place)."""
         self._plans.clear()
+        if getattr(self, "_pipe", None) is not None:
+            torch.cuda.synchronize()
+            self._pipe = None
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
@@ -122,7 +125,7 @@ class _PlannedModel(nn.Module):
     def _aligners(self):
         return [self.roi_align_mask, self.roi_align_rgb] if hasattr(self, "roi_align_mask") else [self.roi_align]
 
-    def _get_plan(self, images: torch.Tensor, rois: torch.Tensor) -> "_BuiltPlan":
+    def _get_plan(self, images: torch.Tensor, rois: torch.Tensor, slot: int = 0) -> "_BuiltPlan":
         if not images.is_cuda and not torch.cuda.is_available():
             raise _lib.HisError("human_instance_segmentation_b200 needs a CUDA (B200) device; there is no CPU fallback")
         if images.dim() != 4 or images.shape[1] != 3:
@@ -134,7 +137,7 @@ class _PlannedModel(nn.Module):
             raise _lib.HisError("move the model to a CUDA device first (model.to('cuda')); there is no CPU fallback")
         B, _, H, W = images.shape
         key = (B, H, W, rois.shape[0], self.aux_outputs, self.max_rois_per_pass, self.max_images_per_pass,
-               tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index)
+               tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index, slot)
         bp = self._plans.get(key)
         if bp is None:
             bp = _BuiltPlan(self, dev, B, H, W, rois.shape[0])
@@ -205,6 +208,64 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
             return (logits.clone(), binary.clone()) if self.copy_outputs else (logits, binary)
         inst = postprocess.instance_masks(logits)
         return inst, (binary.clone() if self.copy_outputs else binary)
+
+    @torch.no_grad()
+    def infer_pipelined(self, images: torch.Tensor, rois: torch.Tensor, out_instance_masks: torch.Tensor, out_binary_masks: torch.Tensor):
+        """``infer`` for a stream of batches held in (pinned) HOST memory: the call enqueues H2D -> forward -> argmax -> D2H into
+        the caller's host tensors on three streams and returns at once; consecutive calls alternate between two launch plans,
+        so batch i+1 is uploaded while batch i computes and batch i-1 is downloaded.  Results are valid after
+        ``pipeline_sync()`` (or an event wait).  Same arithmetic as ``infer`` (bit-identical outputs)."""
+        from . import lib as L_
+        dev = next(self.parameters()).device
+        st = getattr(self, "_pipe", None)
+        if st is None:
+            st = self._pipe = {"h2d": torch.cuda.Stream(dev), "compute": torch.cuda.Stream(dev), "d2h": torch.cuda.Stream(dev), "i": 0,
+                               "done": [None, None], "fetched": [None, None], "inst": [None, None]}
+        slot = st["i"] & 1
+        st["i"] += 1
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st["compute"]):
+            bp = self._get_plan(images, rois, slot=slot)            # built (and graph-captured) on first use of the slot
+        mh, mw = self.mask_size
+        if st["inst"][slot] is None or st["inst"][slot].shape[0] != rois.shape[0]:
+            st["inst"][slot] = torch.empty((rois.shape[0], 1, mh, mw), dtype=torch.float32, device=dev)
+        inst = st["inst"][slot]
+        # upload: the slot's input buffers are free once the forward that last read them has finished
+        st["h2d"].wait_stream(cur)
+        if st["done"][slot] is not None:
+            st["h2d"].wait_event(st["done"][slot])
+        with torch.cuda.stream(st["h2d"]):
+            bp.load_inputs(images, rois)
+            up = torch.cuda.Event(); up.record()
+        # forward + argmax: the slot's output buffers are free once their last download has finished
+        st["compute"].wait_event(up)
+        if st["fetched"][slot] is not None:
+            st["compute"].wait_event(st["fetched"][slot])
+        with torch.cuda.stream(st["compute"]):
+            bp.plan.replay()
+            n = rois.shape[0]
+            if n:
+                L_.check(L_.load().his_post_instance_mask(bp.logits.data_ptr(), n, mh, mw, 0.0, inst.data_ptr(), None,
+                                                          ctypes.c_void_p(st["compute"].cuda_stream)), "his_post_instance_mask")
+            done = torch.cuda.Event(); done.record()
+        st["done"][slot] = done
+        # download
+        st["d2h"].wait_event(done)
+        with torch.cuda.stream(st["d2h"]):
+            out_instance_masks.copy_(inst, non_blocking=True)
+            out_binary_masks.copy_(bp.binary, non_blocking=True)
+            fetched = torch.cuda.Event(); fetched.record()
+        st["fetched"][slot] = fetched
+        return fetched
+
+    def pipeline_sync(self):
+        """Waits until every batch enqueued by ``infer_pipelined`` has landed in its host tensors."""
+        st = getattr(self, "_pipe", None)
+        if st is not None:
+            for ev in st["fetched"]:
+                if ev is not None:
+                    ev.synchronize()
+            torch.cuda.current_stream(next(self.parameters()).device).wait_stream(st["d2h"])
 
     def _run_unet_only(self, images: torch.Tensor) -> torch.Tensor:
         rois = torch.zeros((0, 5), dtype=torch.float32, device=images.device)

@@ -199,3 +199,22 @@ def test_cuda_graph_replay_is_bit_identical():
     c, _ = m(images.cuda(), rois.cuda())
     # no atomics anywhere on the path (fixed-order reductions): eager launches and graph replays agree bitwise
     assert torch.equal(a, b) and torch.equal(b, c)
+
+
+def test_pipelined_infer_matches_blocking_infer():
+    """infer_pipelined (three streams, two alternating launch plans, host tensors in / out) returns what infer returns, batch
+    after batch, including when consecutive batches differ."""
+    cfg, images, rois = common.small_case_inputs("small_b0_bn_relu")
+    m = build(cfg, common.shapes_for_case("small_b0_bn_relu"))
+    m.use_cuda_graph = True
+    batches = [(images, rois), (images.flip(0).contiguous(), rois.clone()), (images * 0.5, rois.flip(0).contiguous()), (images, rois)]
+    want = []
+    for im, r in batches:
+        inst, binary = m.infer(im.cuda(), r.cuda())
+        want.append((inst.cpu(), binary.cpu()))
+    outs = [(torch.empty_like(want[0][0]).pin_memory(), torch.empty_like(want[0][1]).pin_memory()) for _ in batches]
+    for (im, r), (oi, ob) in zip(batches, outs):
+        m.infer_pipelined(im.pin_memory(), r.pin_memory(), oi, ob)
+    m.pipeline_sync()
+    for (wi, wb), (oi, ob) in zip(want, outs):
+        assert torch.equal(oi, wi) and torch.equal(ob, wb)
