@@ -12,8 +12,8 @@ from .lib import HisError, build, load  # noqa: F401
 from .model import (HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet,  # noqa: F401
                     PreTrainedPeopleSegmentationUNet, PreTrainedPeopleSegmentationUNetWrapper, create_rgb_hierarchical_model)
 from .roi_align import DynamicRoIAlign  # noqa: F401
-from . import metrics, postprocess  # noqa: F401
+from . import metrics, postprocess, preprocess  # noqa: F401
 
 __all__ = ["create_rgb_hierarchical_model", "HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet",
-           "PreTrainedPeopleSegmentationUNetWrapper", "PreTrainedPeopleSegmentationUNet", "DynamicRoIAlign", "postprocess", "metrics",
+           "PreTrainedPeopleSegmentationUNetWrapper", "PreTrainedPeopleSegmentationUNet", "DynamicRoIAlign", "postprocess", "metrics", "preprocess",
            "HisError", "build", "load"]

@@ -201,6 +201,33 @@ __global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int
   }
 }
 
+// Input path (test_hierarchical_instance_peopleseg_onnx.py:170-196, after the file decode): BGR->RGB, cv2.resize(uint8,
+// INTER_LINEAR), /255, HWC -> CHW, fused.  OpenCV's 8-bit bilinear arithmetic is kept bit for bit: 11-bit fixed-point weights
+// (tables built by the caller exactly like cv2 builds them), horizontal pass in int32, vertical pass
+// (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2.  One thread = one output pixel, three channels.
+__global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, int N, int Hs, int Ws, int Hd, int Wd, const int* __restrict__ xtab,
+                                     const int* __restrict__ ytab, int swap_rb, float* __restrict__ out) {
+  const long long total = (long long)N * Hd * Wd;
+  GRID_STRIDE(idx, total) {
+    const int x = (int)(idx % Wd), y = (int)((idx / Wd) % Hd);
+    const long long n = idx / ((long long)Wd * Hd);
+    const int x0 = xtab[x], x1 = xtab[Wd + x], ax0 = xtab[2 * Wd + x], ax1 = xtab[3 * Wd + x];
+    const int y0 = ytab[y], y1 = ytab[Hd + y], ay0 = ytab[2 * Hd + y], ay1 = ytab[3 * Hd + y];
+    const unsigned char* img = src + n * (long long)Hs * Ws * 3;
+    const unsigned char* r0 = img + (long long)y0 * Ws * 3;
+    const unsigned char* r1 = img + (long long)y1 * Ws * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int sc = swap_rb ? 2 - c : c;
+      const int h0 = (int)r0[x0 * 3 + sc] * ax0 + (int)r0[x1 * 3 + sc] * ax1;
+      const int h1 = (int)r1[x0 * 3 + sc] * ax0 + (int)r1[x1 * 3 + sc] * ax1;
+      const int v = (((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      const int u = min(max(v, 0), 255);
+      out[((n * 3 + c) * Hd + y) * (long long)Wd + x] = __fdiv_rn((float)u, 255.0f);
+    }
+  }
+}
+
 // evaluate_model's metric core (hed/train_utils.py:262-292): per-ROI 3x3 confusion counts of (ground-truth class, argmax
 // class).  The reference moves predictions to the CPU and runs Python double loops per sample; everything it reports --
 // the three confusion matrices, per-class IoUs, detection rates -- is a function of these nine integers per ROI.
@@ -301,6 +328,17 @@ int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float
   minmax_kernel<<<g, kThreads, 0, ST>>>(ws0, N, H, W, morph, 1, 0, ws1);         // close: dilate
   minmax_kernel<<<g, kThreads, 0, ST>>>(ws1, N, H, W, morph, 0, 0, ws0);         //        erode
   threshold_kernel<<<g, kThreads, 0, ST>>>(ws0, total, 0.5f, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_preprocess_u8(const unsigned char* src, int N, int Hs, int Ws, int Hd, int Wd, const int* xtab, const int* ytab, int swap_rb, float* out,
+                      void* stream) {
+  if (!src || !xtab || !ytab || !out) return his_set_error(HIS_ERR_INVALID_ARG, "preprocess_u8: null pointer");
+  const long long total = (long long)N * Hd * Wd;
+  if (total == 0) return HIS_OK;
+  if (Hs <= 0 || Ws <= 0) return his_set_error(HIS_ERR_INVALID_ARG, "preprocess_u8: empty source image");
+  preprocess_u8_kernel<<<grid_for(total), kThreads, 0, ST>>>(src, N, Hs, Ws, Hd, Wd, xtab, ytab, swap_rb, out);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -119,6 +119,7 @@ SIGNATURES = {
     "his_post_binary_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P],
     "his_post_morph_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P],
     "his_post_paste": [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
+    "his_preprocess_u8": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P],
     "his_eval_confusion": [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
     # shared-memory tiled stencils (csrc/post_stencil.cu)
     "his_post_edge_smooth_tiled": [_P, c_int, c_int, c_int, c_float, c_float, _P, _P],

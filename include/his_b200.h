@@ -199,6 +199,13 @@ int his_post_morph_bilateral(const float* mask, int N, int H, int W, const float
 int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W,
                    void* stream);
 
+/* ---- prepare_image after the file decode, test_hierarchical_instance_peopleseg_onnx.py:170-196 (cv2.cvtColor BGR2RGB,
+ * cv2.resize uint8 INTER_LINEAR, /255, HWC->CHW) fused, bit-exact with OpenCV's 8-bit bilinear arithmetic.
+ * src: device uint8 [N,Hs,Ws,3]; out: fp32 [N,3,Hd,Wd]; xtab / ytab: device int32 [4][Wd] / [4][Hd] = {index0, index1,
+ * weight0, weight1} (11-bit fixed point), built like cv2 builds them (human_instance_segmentation_b200/preprocess.py). */
+int his_preprocess_u8(const unsigned char* src, int N, int Hs, int Ws, int Hd, int Wd, const int* xtab, const int* ytab, int swap_rb,
+                      float* out, void* stream);
+
 /* ---- evaluate_model's metric core, hed/train_utils.py:262-292 (argmax, calculate_confusion_matrix :25-47, the per-sample
  * Python loops of the 2x2 matrices and calculate_iou :14-22): per-ROI 3x3 confusion counts counts[n][gt*3+pred] (int32,
  * zeroed by the call) of 3-class logits [N,3,H,W] against labels [N,H,W] (uint8, or int64 when gt_is_int64). */
