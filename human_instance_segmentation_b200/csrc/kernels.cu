@@ -788,6 +788,38 @@ __global__ void resize_bilinear_f32_kernel(const float* __restrict__ in, int NC,
   }
 }
 
+// bilinear resize (align_corners=False) of an NHWC fp16 slice into another slice (MultiScaleRGBSegmentationModel resizes every
+// scale's features to 28x28, rgb.py:887-893); 8 channels per thread, fp32 interpolation
+__global__ void resize_bilinear_half_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, int Ho, int Wo,
+                                            __half* __restrict__ out, int out_cs) {
+  const int cgs = C / 8;
+  const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const long long total = (long long)N * Ho * Wo * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    const float fy = fmaxf(((float)oy + 0.5f) * sy - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sx - 0.5f, 0.0f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const __half* b = in + (long long)n * H * W * in_cs + cg * 8;
+    const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x0) * in_cs)), v01 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x1) * in_cs));
+    const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x0) * in_cs)), v11 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x1) * in_cs));
+    const __half2 *a = reinterpret_cast<const __half2*>(&v00), *bb = reinterpret_cast<const __half2*>(&v01);
+    const __half2 *c = reinterpret_cast<const __half2*>(&v10), *d = reinterpret_cast<const __half2*>(&v11);
+    uint4 ov; __half2* o = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 p00 = __half22float2(a[e]), p01 = __half22float2(bb[e]), p10 = __half22float2(c[e]), p11 = __half22float2(d[e]);
+      const float r0 = (1.0f - ly) * ((1.0f - lx) * p00.x + lx * p01.x) + ly * ((1.0f - lx) * p10.x + lx * p11.x);
+      const float r1 = (1.0f - ly) * ((1.0f - lx) * p00.y + lx * p01.y) + ly * ((1.0f - lx) * p10.y + lx * p11.y);
+      o[e] = __floats2half2_rn(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = ov;
+  }
+}
+
 // ------------------------------------------------------------------------------------ attention glue
 // SpatialAttentionModule (attention_modules.py:67-113): per-pixel channel mean & max -> [N,H,W,2] fp32
 __global__ void channel_stats_kernel(const __half* __restrict__ in, long long pixels, int C, int cs, float* __restrict__ stats) {
@@ -1289,6 +1321,16 @@ int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, in
   const long long total = (long long)N * Ho * Wo * (C / 8);
   if (total == 0) return HIS_OK;
   resize_nearest_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_resize_bilinear_half(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "resize_bilinear_half: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "resize_bilinear_half: channels must be multiples of 8");
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  if (total == 0) return HIS_OK;
+  resize_bilinear_half_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -101,6 +101,7 @@ SIGNATURES = {
     "his_spatial_gate": [_P, c_int, c_int, c_int, _P, c_int, _P, _P],
     "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_resize_nearest": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "his_resize_bilinear_half": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_resize_bilinear_f32": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "his_upsample_bgfg": [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P],
     "his_head_combine": [_P, _P, c_int, c_int, c_int, _P, _P],

@@ -123,6 +123,8 @@ class _PlannedModel(nn.Module):
         return bp.outputs(self.copy_outputs)
 
     def _aligners(self):
+        if hasattr(self, "roi_aligns"):
+            return list(self.roi_aligns.values())
         return [self.roi_align_mask, self.roi_align_rgb] if hasattr(self, "roi_align_mask") else [self.roi_align]
 
     def _get_plan(self, images: torch.Tensor, rois: torch.Tensor, slot: int = 0) -> "_BuiltPlan":
@@ -311,6 +313,42 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
         self.roi_align = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=False)      # rgb.py:404-408
         self._init_exec_state()
 
+class MultiScaleRGBSegmentationModel(_PlannedModel):
+    """rgb.py:777-922: one RGBFeatureExtractor per ROI scale (DynamicRoIAlign aligned=False), features resized to 28x28, fused
+    ('concat' | 'sum' | 'adaptive'), projected 1x1 to 256 channels, HierarchicalSegmentationHeadUNetV2 (LayerNorm2d + ReLU)."""
+
+    def __init__(self, roi_sizes=None, mask_size: Union[int, Tuple[int, int]] = 56, feature_channels: int = 256, fusion_method: str = "concat",
+                 num_classes: int = 3, use_attention_module: bool = False, normalization_type: str = "layernorm2d", normalization_groups: int = 8,
+                 activation_function: str = "relu", activation_beta: float = 1.0):
+        super().__init__()
+        if num_classes != 3:
+            raise AssertionError("Hierarchical model designed for 3 classes")
+        if feature_channels != 256:
+            raise NotImplementedError("feature_channels != 256 is not implemented on B200 (the factory never passes it)")
+        roi_sizes = dict(roi_sizes) if roi_sizes is not None else {"scale1": 56, "scale2": 42, "scale3": 28}
+        self.roi_sizes, self.fusion_method, self.scales = roi_sizes, fusion_method, list(roi_sizes.keys())
+        if fusion_method not in ("concat", "sum", "adaptive"):
+            self._bad_fusion = fusion_method          # the reference raises at forward time (rgb.py:905-906)
+        self.mask_size = _pair(mask_size)
+        big = max(int(v) for v in roi_sizes.values())
+        self.roi_size = (big, big)                    # bounds the per-pass footprint
+        self.feature_size = (28, 28)                  # rgb.py:887: every scale is resized to 28x28
+        self.activation_function = pt.check_activation(activation_function)
+        self.activation_beta = float(activation_beta)
+        self.extractor_normalization_type = normalization_type
+        self.normalization_type = "layernorm2d"       # the V2 head hard-codes LayerNorm2d
+        self.use_attention_module = bool(use_attention_module)
+        self.use_contour_detection = self.use_distance_transform = self.use_refinement = False
+        self.rgb_extractors = nn.ModuleDict({s_: pt.RGBFeatureExtractorParams(normalization_type) for s_ in self.scales})
+        self.roi_aligns = nn.ModuleDict({s_: DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=False) for s_ in self.scales})
+        if fusion_method == "adaptive":
+            self.fusion_weights = nn.Parameter(torch.ones(len(roi_sizes)))
+        fused = 256 * len(roi_sizes) if fusion_method == "concat" else 256
+        self.fusion_proj = pt.FusionProjParams(fused, 256, normalization_type)
+        self.segmentation_head = pt.BaseHeadParams(256, 256, "layernorm2d", self.use_attention_module, 96, 3)
+        self._init_exec_state()
+
+
 def _scale_hw(ra: DynamicRoIAlign):
     return float(ra.spatial_scale_h), float(ra.spatial_scale_w)
 
@@ -422,6 +460,8 @@ class _BuiltPlan:
             self.h_logits = self.plan.f32(self.Nc, 3, mh, mw) if self.chunked_head else self.logits
             if self.has_unet:
                 self._build_head()
+            elif hasattr(m, "roi_aligns"):
+                self._build_head_multiscale()
             else:
                 self._build_head_standard()
             for k, v in self.h_aux.items():
@@ -742,22 +782,83 @@ class _BuiltPlan:
               float(ra.spatial_scale_h), float(ra.spatial_scale_w), 1 if ra.aligned else 0, patches.ptr, patches.cs,
               roi_patch.data_ptr() if roi_patch is not None else None)
         # RGBFeatureExtractor (rgb.py:221-295): [conv3x3, norm, ReLU] (+ ResidualBlock after every stage but the first)
-        saved = m.normalization_type
-        m.normalization_type = m.extractor_normalization_type        # _tail_ok/_aux_fusable look at the current norm kind
-        x = patches
-        for mod in m.rgb_extractor.features:
-            if isinstance(mod, nn.Conv2d):
-                conv = mod
-            elif isinstance(mod, (nn.BatchNorm2d, pt.LayerNorm2dParams)):
-                x = self.conv(x, conv, mod, A)
-            elif isinstance(mod, pt.ResidualBlockParams):
-                x = self.residual_block(x, mod, A)
-        m.normalization_type = saved
+        x = self._rgb_extractor(patches, m.rgb_extractor.features, m.extractor_normalization_type, A, A)
         if m.use_refinement:
             self._hier_head(x, m.segmentation_head.base_head, m.segmentation_head)
         else:
             self._hier_head(x, m.segmentation_head, None)
             self.h_aux.pop("shared_features", None)                  # the V2 head returns 4 aux tensors (..._unet.py:836-841)
+        if m.aux_outputs != "none":
+            self.h_aux["roi_patches"] = roi_patch
+
+    def _rgb_extractor(self, x: Act, features, norm_kind: str, act_stage: int, act_rb: int) -> Act:
+        """RGBFeatureExtractor (rgb.py:221-295): [conv3x3, norm, act] per stage, a ResidualBlock after every stage but the first."""
+        m = self.m
+        saved = m.normalization_type
+        m.normalization_type = norm_kind             # _tail_ok/_aux_fusable look at the current norm kind
+        conv = None
+        for mod in features:
+            if isinstance(mod, nn.Conv2d):
+                conv = mod
+            elif isinstance(mod, (nn.BatchNorm2d, pt.LayerNorm2dParams)):
+                x = self.conv(x, conv, mod, act_stage)
+            elif isinstance(mod, pt.ResidualBlockParams):
+                x = self.residual_block(x, mod, act_rb)
+        m.normalization_type = saved
+        return x
+
+    def _build_head_multiscale(self):
+        """MultiScaleRGBSegmentationModel.forward (rgb.py:866-922)."""
+        m, p, L = self.m, self.plan, self.plan.lib
+        if hasattr(m, "_bad_fusion"):
+            raise ValueError(f"Unknown fusion method: {m._bad_fusion}")
+        N, B, H, W = self.Nc, self.B, self.H, self.W
+        fh, fw = m.feature_size
+        A_stage = self.act_rgb
+        bn = m.extractor_normalization_type.lower() in ("batch", "batchnorm", "batchnorm2d")
+        A_rb = self.act_rgb if bn else ACT["relu"]       # rgb.py:267-276: only the batchnorm branch forwards the activation
+        concat = m.fusion_method == "concat"
+        ns = len(m.scales)
+        fused_in = p.act(N, fh, fw, 256 * ns)
+        roi_patch = None
+        for i, sc in enumerate(m.scales):
+            rs = int(m.roi_sizes[sc])
+            ra = m.roi_aligns[sc]
+            patches = p.act_zeroed(N, rs, rs, 3)
+            want_patch = i == 0 and m.aux_outputs != "none"
+            if want_patch:
+                roi_patch = p.f32(N, 3, rs, rs)
+            p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rs, rs,
+                  float(ra.spatial_scale_h), float(ra.spatial_scale_w), 1 if ra.aligned else 0, patches.ptr, patches.cs,
+                  roi_patch.data_ptr() if want_patch else None)
+            slot = fused_in.slice(256 * i, 256)
+            f = self._rgb_extractor(patches, m.rgb_extractors[sc].features, m.extractor_normalization_type, A_stage, A_rb)
+            # F.interpolate to 28x28 (identity when the scale already is 28) straight into the scale's concat slot
+            p.add("resize_bilinear_half", L.his_resize_bilinear_half, f.ptr, N, rs, rs, 256, f.cs, fh, fw, slot.ptr, slot.cs)
+        # fusion + projection: 'sum' / 'adaptive' are the 1x1 projection applied to the weighted sum of the scales, i.e. a 1x1 conv
+        # over the concat buffer whose weight is [w_0*W | w_1*W | ...] -- no extra pass over the features
+        proj = m.fusion_proj[0]
+        if concat:
+            conv_mod = proj
+        else:
+            w = torch.ones(ns) if m.fusion_method == "sum" else torch.softmax(m.fusion_weights.detach().float().cpu(), 0)
+            conv_mod = nn.Conv2d(256 * ns, 256, 1)
+            with torch.no_grad():
+                conv_mod.weight.copy_(torch.cat([proj.weight.detach().float().cpu() * w[i] for i in range(ns)], 1))
+                conv_mod.bias.copy_(proj.bias.detach().float().cpu())
+        saved = m.normalization_type
+        m.normalization_type = m.extractor_normalization_type
+        x = self.conv(Act(fused_in.buf, 256 * ns), conv_mod, m.fusion_proj[1], A_stage)
+        m.normalization_type = saved
+        # the head works at 28x28 whatever the ROI scales are, and with ReLU whatever the extractors use (the reference builds
+        # HierarchicalSegmentationHeadUNetV2 without forwarding the activation, rgb.py:854-860)
+        saved_roi, saved_acts = m.roi_size, (self.act_rgb, self.act_ref)
+        m.roi_size = m.feature_size
+        self.act_rgb = self.act_ref = ACT["relu"]
+        self._hier_head(x, m.segmentation_head, None)
+        m.roi_size = saved_roi
+        self.act_rgb, self.act_ref = saved_acts
+        self.h_aux.pop("shared_features", None)
         if m.aux_outputs != "none":
             self.h_aux["roi_patches"] = roi_patch
 
@@ -992,10 +1093,14 @@ def create_rgb_hierarchical_model(roi_size: Union[int, Tuple[int, int]] = 28, ma
     pretrained_weights_path = kwargs.pop("pretrained_weights_path", "")
     freeze_pretrained_weights = kwargs.pop("freeze_pretrained_weights", False)
     use_full_image_unet = kwargs.pop("use_full_image_unet", False)
+    if multi_scale:          # rgb.py:961-975
+        return MultiScaleRGBSegmentationModel(
+            roi_sizes=kwargs.get("roi_sizes", {"scale1": 56, "scale2": 42, "scale3": 28}), mask_size=mask_size,
+            fusion_method=kwargs.get("fusion_method", "concat"), use_attention_module=use_attention_module,
+            normalization_type=normalization_type, normalization_groups=normalization_groups,
+            activation_function=activation_function, activation_beta=activation_beta)
     kwargs.pop("roi_sizes", None)
     kwargs.pop("fusion_method", None)
-    if multi_scale:
-        raise NotImplementedError("MultiScaleRGBSegmentationModel (rgb.py:777-922) is outside the B200 hot path (SURVEY §8f rank 4)")
     if use_pretrained_unet and not use_full_image_unet:
         # rgb.py:442-561: the reference's own constructor dies on an undefined name (`kwargs`, :497) -> nothing to mirror
         raise NotImplementedError("HierarchicalRGBSegmentationModelWithPretrainedUNet (ROI-level UNet) cannot be constructed in the "

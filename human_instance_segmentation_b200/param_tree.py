@@ -176,6 +176,13 @@ class RGBFeatureExtractorParams(nn.Module):
         self.features = nn.Sequential(*layers)
 
 
+class FusionProjParams(nn.Sequential):
+    """MultiScaleRGBSegmentationModel.fusion_proj, rgb.py:846-851."""
+
+    def __init__(self, cin: int, cout: int, norm: str):
+        super().__init__(nn.Conv2d(cin, cout, 1), norm_params(norm, cout), Slot())
+
+
 class GuidedHeadParams(nn.Module):
     """PretrainedUNetGuidedSegmentationHead, rgb.py:43-123 (the head built when no refinement flag is set, :715-727)."""
 

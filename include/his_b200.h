@@ -145,6 +145,8 @@ int his_spatial_gate(const float* stats, int N, int H, int W, const float* w, in
 int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, void* stream);
 int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream);
 int his_resize_bilinear_f32(const float* in, int NC, int H, int W, int Ho, int Wo, float* out, void* stream);
+/* F.interpolate(bilinear, align_corners=False) of an NHWC half slice (MultiScaleRGBSegmentationModel, rgb.py:887-893). */
+int his_resize_bilinear_half(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream);
 
 /* ---- head tails: upsample_bg_fg (..._refinement.py:501-506) fused ConvT(2->32,k2,s2)+BN+act+1x1(32->2), NCHW fp32;
  * hierarchical combine (:588-596); elementwise sigmoid / sigmoid((x-*param)*10) (:294,:341). */

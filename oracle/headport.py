@@ -48,8 +48,16 @@ class PathConfig:
     spatial_scale: Tuple[float, float] = (640.0, 640.0)
     # False -> HierarchicalRGBSegmentationModel (rgb.py:298-439): no UNet branch, one RoIAlign with aligned=False
     use_pretrained_unet: bool = True
+    # True -> MultiScaleRGBSegmentationModel (rgb.py:777-922)
+    multi_scale: bool = False
+    roi_sizes: tuple = (("scale1", 56), ("scale2", 42), ("scale3", 28))
+    fusion_method: str = "concat"
 
     def factory_kwargs(self) -> dict:
+        if self.multi_scale:
+            return dict(mask_size=self.mask_size, multi_scale=True, roi_sizes=dict(self.roi_sizes), fusion_method=self.fusion_method,
+                        use_attention_module=self.use_attention_module, normalization_type=self.normalization_type, normalization_groups=8,
+                        activation_function=self.activation_function, activation_beta=self.activation_beta)
         if not self.use_pretrained_unet:
             return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
                         use_attention_module=self.use_attention_module, use_contour_detection=self.use_contour_detection,
@@ -425,9 +433,54 @@ def forward_standard(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig):
     return logits, aux
 
 
+def _rgb_feature_extractor_std(sd: SD, p: str, x: Tensor, cfg: PathConfig, rb_cfg: PathConfig) -> Tensor:
+    """RGBFeatureExtractor.features (rgb.py:221-295): stages use ``cfg`` (norm + rgb-factory activation); the residual blocks
+    use ``rb_cfg`` (only the batchnorm branch forwards norm/activation, every other norm gets the default LayerNorm2d+ReLU block)."""
+    for i, base in enumerate((0, 3, 7, 11)):
+        x = act_rgb(norm(sd, f"{p}{base + 1}.", conv(sd, f"{p}{base}.", x, 1), cfg), cfg)
+        if i >= 1:
+            x = residual_block(sd, f"{p}{base + 3}.", x, rb_cfg, act_rgb)
+    return x
+
+
+@torch.no_grad()
+def forward_multiscale(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig):
+    """MultiScaleRGBSegmentationModel.forward (rgb.py:866-922; ctor :780-864)."""
+    from dataclasses import replace
+    sh, sw = cfg.spatial_scale
+    bn = cfg.normalization_type.lower() in ("batch", "batchnorm", "batchnorm2d")
+    rb_cfg = cfg if bn else replace(cfg, normalization_type="layernorm2d", activation_function="relu")
+    feats, first = [], None
+    for name, rs in cfg.roi_sizes:
+        reg = roi_align(images, rois, rs, rs, sh, sw, False)
+        if first is None:
+            first = reg
+        f = _rgb_feature_extractor_std(sd, f"rgb_extractors.{name}.features.", reg, cfg, rb_cfg)
+        if f.shape[-1] != 28:
+            f = F.interpolate(f, size=(28, 28), mode="bilinear", align_corners=False)
+        feats.append(f)
+    if cfg.fusion_method == "concat":
+        fused = torch.cat(feats, 1)
+    elif cfg.fusion_method == "sum":
+        fused = sum(feats)
+    elif cfg.fusion_method == "adaptive":
+        w = F.softmax(sd["fusion_weights"], 0)
+        fused = sum(wi * fi for wi, fi in zip(w, feats))
+    else:
+        raise ValueError(f"Unknown fusion method: {cfg.fusion_method}")
+    x = act_rgb(norm(sd, "fusion_proj.1.", conv(sd, "fusion_proj.0.", fused, 0), cfg), cfg)
+    head_cfg = replace(cfg, normalization_type="layernorm2d", activation_function="relu", hierarchical_base_channels=96, hierarchical_depth=3)
+    logits, aux = base_head(sd, "segmentation_head.", x, head_cfg)
+    aux.pop("shared_features")
+    aux["roi_patches"] = first
+    return logits, aux
+
+
 @torch.no_grad()
 def forward(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig, full_image_logits: Tensor = None):
     """HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet.forward (rgb.py:729-774)."""
+    if cfg.multi_scale:
+        return forward_multiscale(sd, images, rois, cfg)
     if not cfg.use_pretrained_unet:
         return forward_standard(sd, images, rois, cfg)
     if full_image_logits is None:

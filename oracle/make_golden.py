@@ -59,7 +59,17 @@ STANDARD_CASES = {
     "small_std_refined_bn_att": (headport.PathConfig(roi_size=(16, 12), mask_size=(40, 28), normalization_type="batchnorm",
                                                      use_attention_module=True, use_pretrained_unet=False), (96, 128)),
 }
-SMALL_CASES_ALL = {**SMALL_CASES, **GUIDED_CASES, **STANDARD_CASES}
+# a1 multi_scale=True -> MultiScaleRGBSegmentationModel (rgb.py:777-922): default fusion/normalisation, and batchnorm + SiLU +
+# adaptive fusion + attention with two scales
+MULTISCALE_CASES = {
+    "small_ms_concat_ln": (headport.PathConfig(mask_size=(56, 56), multi_scale=True, normalization_type="layernorm2d", use_attention_module=False,
+                                               use_contour_detection=False, use_distance_transform=False, use_pretrained_unet=False), (96, 128)),
+    "small_ms_adaptive_bn_silu_att": (headport.PathConfig(mask_size=(56, 56), multi_scale=True, roi_sizes=(("a", 28), ("b", 36)),
+                                                          fusion_method="adaptive", normalization_type="batchnorm", activation_function="silu",
+                                                          use_attention_module=True, use_contour_detection=False, use_distance_transform=False,
+                                                          use_pretrained_unet=False), (96, 128)),
+}
+SMALL_CASES_ALL = {**SMALL_CASES, **GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES}
 
 _FULL_KEYS = ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_mask",
               "distance_map", "roi_features", "roi_patches")
@@ -73,7 +83,8 @@ def _run_reference(cfg: headport.PathConfig, images, rois, seed=0, mode="stress"
     model = refload.build_reference_model(**cfg.factory_kwargs())
     sd = paramfill.fill_state_dict(model.state_dict(), seed=seed, mode=mode)
     model.load_state_dict(sd)
-    aligners = (model.roi_align_mask, model.roi_align_rgb) if hasattr(model, "roi_align_mask") else (model.roi_align,)
+    aligners = (model.roi_align_mask, model.roi_align_rgb) if hasattr(model, "roi_align_mask") else \
+        tuple(model.roi_aligns.values()) if hasattr(model, "roi_aligns") else (model.roi_align,)
     for ra in aligners:      # export_onnx_advanced.py:80-98 mutates these
         ra.spatial_scale = cfg.spatial_scale
         ra.spatial_scale_h, ra.spatial_scale_w = cfg.spatial_scale
@@ -129,7 +140,7 @@ def make_guided_goldens():
     """The guided-head variant; adds its key/shape tables to state_dict_keys.json without touching the other entries."""
     path = os.path.join(GOLDEN, "state_dict_keys.json")
     keys_json = json.load(open(path))
-    for name, (cfg, (h, w)) in {**GUIDED_CASES, **STANDARD_CASES}.items():
+    for name, (cfg, (h, w)) in {**GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES}.items():
         images = synth_images(11, 2, h, w)
         rois = torch.cat([synth_rois(11, 2, 2), edge_rois(2)], 0)
         model, sd, logits, aux = _run_reference(cfg, images, rois)

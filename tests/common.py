@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from oracle import headport, paramfill
-from oracle.make_golden import GUIDED_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
+from oracle.make_golden import GUIDED_CASES, MULTISCALE_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -110,6 +110,26 @@ def test_standard_model_variant_matches_reference_golden(name):
     assert set(aux) == set(keys) | {"fg_attention"} | ({"shared_features"} if headport.uses_refined_head(cfg) else set())
 
 
+@pytest.mark.parametrize("name", list(common.MULTISCALE_CASES))
+def test_multiscale_model_matches_reference_golden(name):
+    """a1 multi_scale=True -> MultiScaleRGBSegmentationModel (rgb.py:777-922): per-scale extractors, bilinear resize to 28x28,
+    concat / adaptive fusion folded into the 1x1 projection, V2 head."""
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    m = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    assert type(m).__name__ == "MultiScaleRGBSegmentationModel"
+    m.load_state_dict(common.procedural_state(common.shapes_for_case(name)))
+    m = m.to("cuda")
+    logits, aux = m(images.cuda(), rois.cuda())
+    check(logits, g["logits"], "logits")
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= 0.998
+    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention")
+    keys = [k for k in g if k not in ("logits", "fg_attention_sub")]
+    for k in keys:
+        check(aux[k], g[k], k)
+    assert set(aux) == set(keys) | {"fg_attention"}
+
+
 def test_model_matches_reference_golden_config1():
     """BASELINE.json configs[0]: B0 std, 2x3x480x640, 8 ROIs, 64x48 -> 128x96."""
     cfg, images, rois = common.cfg1_inputs()

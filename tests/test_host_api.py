@@ -34,6 +34,16 @@ def test_guided_variant_state_dict_matches_reference(name):
     assert not hasattr(model, "feature_combiner")
 
 
+@pytest.mark.parametrize("name", list(common.MULTISCALE_CASES))
+def test_multiscale_state_dict_matches_reference(name):
+    cfg = common.MULTISCALE_CASES[name][0]
+    model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    want = common.golden_keys()[name]
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert got == want and list(got) == list(want)
+    assert model.scales == [n for n, _ in cfg.roi_sizes] and all(not ra.aligned for ra in model.roi_aligns.values())     # rgb.py:826-833
+
+
 @pytest.mark.parametrize("name", list(common.STANDARD_CASES))
 def test_standard_variant_state_dict_matches_reference(name):
     cfg = common.STANDARD_CASES[name][0]
@@ -73,8 +83,8 @@ def test_factory_errors_match_reference_behaviour():
         his.create_rgb_hierarchical_model(**{**kw, "activation_function": "tanh"})
     with pytest.raises(ValueError):     # normalization_comparison.py:206
         his.create_rgb_hierarchical_model(**{**kw, "normalization_type": "nonsense"})
-    with pytest.raises(NotImplementedError):
-        his.create_rgb_hierarchical_model(**{**kw, "multi_scale": True})
+    with pytest.raises(NotImplementedError):       # sub-pixel / progressive decoders are not part of any preset
+        his.create_rgb_hierarchical_model(**{**kw, "use_subpixel_conv": True})
 
 
 def test_no_cpu_fallback():

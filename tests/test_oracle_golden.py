@@ -43,7 +43,7 @@ def test_guided_head_port_matches_reference(name):
         assert aux["attention"] is None and "attention" not in g
 
 
-@pytest.mark.parametrize("name", list(common.STANDARD_CASES))
+@pytest.mark.parametrize("name", list(common.STANDARD_CASES) + list(common.MULTISCALE_CASES))
 def test_standard_model_port_matches_reference(name):
     """a13: HierarchicalRGBSegmentationModel (rgb.py:298-439) + HierarchicalSegmentationHeadUNetV2 (..._unet.py:670-845)."""
     cfg, images, rois = common.small_case_inputs(name)
