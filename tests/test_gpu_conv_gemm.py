@@ -108,3 +108,68 @@ CASES = [
 def test_conv_gemm_matches_torch_fp32(case):
     err, ref = run_case(**case)
     assert err <= 2e-3 * max(ref, 1.0), (err, ref)   # fp16 output rounding: 2^-11 relative
+
+
+def test_fused_nearest_upsample_concat_matches_torch():
+    """his_conv_gemm_set_upsampled_input: channels [0, low_c) gathered from the half-resolution tensor at (y>>1, x>>1), the rest
+    from the concat buffer == F.interpolate(nearest) + cat + conv3x3 (smp UnetDecoderBlock)."""
+    import ctypes
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(7)
+    for (n, h, w, low_c, skip_c, cout) in [(2, 24, 32, 64, 24, 64), (1, 34, 18, 32, 0, 16), (3, 16, 48, 128, 40, 128)]:
+        plan = engine.Plan(dev)
+        low = plan.act(n, h // 2, w // 2, low_c)
+        low.buf.copy_(torch.randn(low.buf.shape, generator=g).half())
+        cat = plan.act(n, h, w, low_c + skip_c)
+        cat.buf.copy_(torch.randn(cat.buf.shape, generator=g).half())           # the first low_c channels are never read
+        cin = low_c + skip_c
+        wt = torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (cin * 9)) ** 0.5
+        shift = torch.randn(cout, generator=g) * 0.1
+        assert plan.lib.his_conv_gemm_can_fuse_upsample(h, w, cin, cout, low_c) == 1
+        nt, bn = ctypes.c_int(), ctypes.c_int()
+        plan.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
+        slab = nt.value * bn.value
+        wp, cin_pad = engine.pack_gemm_weight(wt, slab, False)
+        out = plan.act(n, h, w, cout)
+        plan.conv_gemm(cat, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(shift, slab)), out, 3, ACT["relu"], up_input=low)
+        plan.replay()
+        torch.cuda.synchronize()
+        x = torch.cat([F.interpolate(low.torch_nchw().cpu(), scale_factor=2, mode="nearest"), cat.torch_nchw().cpu()[:, low_c:]], 1)
+        want = F.relu(F.conv2d(x, wt.half().float(), padding=1) + shift.view(1, -1, 1, 1))
+        err = (out.torch_nchw().cpu() - want).abs().max().item()
+        assert err <= 2e-3 * max(want.abs().max().item(), 1.0), (n, h, w, low_c, skip_c, cout, err)
+
+
+def test_row_scale_and_channel_statistics_epilogue():
+    """his_conv_gemm_set_row_ops: y = act(row_scale[pix]*conv(x) + shift (+res)); stats[pix] = (mean_c y, max_c y) -- the two halves
+    of the SpatialAttentionModule fusion (attention_modules.py:67-113)."""
+    import ctypes
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11)
+    n, h, w, cin, cout = 3, 16, 12, 256, 256
+    plan = engine.Plan(dev)
+    x = plan.act(n, h, w, cin); x.buf.copy_(torch.randn(x.buf.shape, generator=g).half())
+    res = plan.act(n, h, w, cout); res.buf.copy_(torch.randn(res.buf.shape, generator=g).half())
+    wt = torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (cin * 9)) ** 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    nt, bn = ctypes.c_int(), ctypes.c_int()
+    plan.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
+    wp, cin_pad = engine.pack_gemm_weight(wt, nt.value * bn.value, False)
+    out = plan.act(n, h, w, cout)
+    stats = plan.f32(n, h, w, 2)
+    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(shift, cout)), out, 3, ACT["relu"], 1.0, res, RES_ADD, stats_out=stats)
+    # consumer: ConvT k2s2 of the gated tensor == row scale inside the transposed conv
+    gate = torch.rand(n, h, w, generator=g)
+    wT = torch.randn(cout, 128, 2, 2, generator=g) * (1.0 / cout) ** 0.5
+    shiftT = torch.randn(128, generator=g) * 0.1
+    wpT, cin_padT = engine.pack_gemm_weight(wT, 128, True)
+    outT = plan.act(n, 2 * h, 2 * w, 128)
+    plan.conv_gemm(out, plan.const(wpT, torch.float16), cin_padT, plan.const(shiftT), outT, 1, ACT["relu"], transposed=True, row_scale=plan.const(gate))
+    plan.replay()
+    torch.cuda.synchronize()
+    y = F.relu(F.conv2d(x.torch_nchw().cpu(), wt.half().float(), padding=1) + shift.view(1, -1, 1, 1) + res.torch_nchw().cpu())
+    assert (stats.cpu()[..., 0] - y.mean(1)).abs().max() < 2e-3 and (stats.cpu()[..., 1] - y.max(1)[0]).abs().max() < 5e-3
+    yh = out.torch_nchw().cpu()
+    wantT = F.relu(F.conv_transpose2d(yh * gate[:, None], wT.half().float(), stride=2) + shiftT.view(1, -1, 1, 1))
+    errT = (outT.torch_nchw().cpu() - wantT).abs().max().item()
+    assert errT <= 3e-3 * max(wantT.abs().max().item(), 1.0), errT
