@@ -356,6 +356,13 @@ def main():
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---------------- per-kernel timing for the roofline (instrumented replay right after the timed region)
+    timed = plan.run_timed()
+    timed = plan.run_timed()
+    n_launches, step_flops, op_desc = plan.launches, plan.flops, list(plan.op_desc)
+    del plan, bp
+    model.release_plans()          # the e2e arm builds its own (masks-only) plans; keep the HBM footprint to two of them
+
     # ---------------- e2e: host (pinned) buffers in, instance/binary masks back to host, through model.infer()
     inst_h = torch.empty((n_rois, 1) + tuple(cfg["mask_size"]), dtype=torch.float32).pin_memory()
     bin_h = torch.empty((n_img, 1, h, w), dtype=torch.float32).pin_memory()
@@ -398,9 +405,6 @@ def main():
         ms_e2e_blocking = e0.elapsed_time(e1) / args.steps
         args.no_pipeline = False
 
-    # ---------------- per-kernel timing for the roofline (instrumented replay right after the timed region)
-    timed = plan.run_timed()
-    timed = plan.run_timed()
     gemm = [(t, f) for name, t, f in timed if name == "conv_gemm"]
     gemm_ms, gemm_flops = sum(t for t, _ in gemm), sum(f for _, f in gemm)
     step_ms_instr = sum(t for _, t, _ in timed)
@@ -410,7 +414,7 @@ def main():
     if args.breakdown and rank == 0:
         for name, (cnt, t) in sorted(by_name.items(), key=lambda kv: -kv[1][1]):
             print(f"  {name:22s} x{cnt:4d} {t:9.3f} ms {100 * t / step_ms_instr:5.1f}%", file=sys.stderr)
-        rows = sorted(((t, plan.op_desc[i], f) for i, (n_, t, f) in enumerate(timed)), reverse=True)
+        rows = sorted(((t, op_desc[i], f) for i, (n_, t, f) in enumerate(timed)), reverse=True)
         for t, desc, f in rows[:args.top]:
             print(f"  {t:7.3f} ms {f / t / 1e9 if f else 0:8.1f} TFLOP/s  {desc}", file=sys.stderr)
 
@@ -435,9 +439,10 @@ def main():
                 "h2d_bytes_per_step": images_h.numel() * 4 + rois_h.numel() * 4, "d2h_bytes_per_step": inst_h.numel() * 4 + bin_h.numel() * 4,
                 "api": ("model.infer(images_host_pinned, rois_host) -> (instance_masks, binary_masks) copied to pinned host" if args.no_pipeline else
                         "model.infer_pipelined(images_host_pinned, rois_host, instance_masks_host, binary_masks_host): upload / forward / "
-                        "download of consecutive batches overlap on three streams, two launch plans; every step's H2D and D2H are inside the timed region")},
-        "gpu_launches": plan.launches * args.steps,
-        "launches_per_step": plan.launches,
+                        "download of consecutive batches overlap on three streams, two launch plans; every step's H2D and D2H are inside the timed region; "
+                        "exported-ONNX contract (masks + binary masks only: aux-only contour / distance branches are not computed, as in the exported graph)")},
+        "gpu_launches": n_launches * args.steps,
+        "launches_per_step": n_launches,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_sm100_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tflops"], "traffic": measured_traffic("conv_gemm_sm100_kernel:" + args.workload),
                      "traffic_note": "DRAM bytes per launch (read+write), averaged over the kernel's launches of one step, ncu capture in profiles/",
@@ -446,8 +451,8 @@ def main():
                      "algorithmic_flop_per_launch": gemm_flops / max(len(gemm), 1), "share_of_step": gemm_ms / step_ms_instr,
                      "how": "sum of algorithmic FLOPs of all conv_gemm launches of one step / sum of their CUDA-event durations "
                             "(instrumented replay immediately after the timed region)"},
-        "step_algorithmic_tflop": plan.flops / 1e12,
-        "step_tflops": plan.flops / (ms * 1e-3) / 1e12,
+        "step_algorithmic_tflop": step_flops / 1e12,
+        "step_tflops": step_flops / (ms * 1e-3) / 1e12,
         "time_share_by_op": {k: round(v[1] / step_ms_instr, 4) for k, v in sorted(by_name.items(), key=lambda kv: -kv[1][1])},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -557,6 +557,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int nchunks = (p.block_n + kChunkC - 1) / kChunkC;
     const uint32_t stg0 = staging_base + g * 2 * kStagingBytes;
     uint32_t cc = 0;
+    uint32_t res_phase = 0;                       // bit b: parity of the next residual load into staging buffer b
     int acc = g; uint32_t acc_phase = 0;          // group g drains the accumulators of parity g (n_acc is even)
     for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += 2 * gridDim.x) {
       const WorkItem it = decode_work(p, w);
@@ -569,7 +570,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // costs ~20 full ones), so those chunks are read / written straight from registers, 16 bytes per 8 channels.
       const bool tile_full = it.y0 + p.bh <= p.H && it.x0 + p.bw <= p.W;
       const int ntma = !p.direct_ok ? nchunks : (!tile_full && p.direct_ok > 1) ? 0 : min(nchunks, max(0, (p.cout - chbase) / kChunkC));
-      if (RES && issuer_warp && elect_one()) {  // prefetch the first two residual chunks while the MMAs run
+      // direct_ok == 3: the residual of an edge-clipped tile is read straight from global memory (a clipped residual TMA box
+      // is served far slower than a full one), the output still leaves through the staging buffer + TMA store
+      const bool res_glob = RES && !tile_full && p.direct_ok == 3;
+      if (RES && !res_glob && issuer_warp && elect_one()) {  // prefetch the first two residual chunks while the MMAs run
         tma_wait_read<0>();
         for (int j = 0; j < 2 && j < ntma; ++j) {
           const int b = (cc + j) & 1;
@@ -597,9 +601,9 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int ch0 = chbase + cl0;           // ... and within the layer
         const int ncol = min(kChunkC, p.block_n - cl0);   // valid accumulator columns in this chunk (16 or 32)
         if (!direct) {
-          if ((!RES || j >= 2) && issuer_warp && elect_one()) {
+          if ((!RES || res_glob || j >= 2) && issuer_warp && elect_one()) {
             tma_wait_read<1>();                    // the store that last read staging[b] has drained
-            if (RES) {
+            if (RES && !res_glob) {
               mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
               tma_load_4d(stg, &tmR, res_bar(2 * g + b), ch0, it.x0, it.y0, it.img);
             }
@@ -615,7 +619,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (RES && !direct) mbar_wait(res_bar(2 * g + b), (cc >> 1) & 1);
+        if (RES && !direct && !res_glob) { mbar_wait(res_bar(2 * g + b), (res_phase >> b) & 1u); res_phase ^= 1u << b; }
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
 #pragma unroll
         for (int i = 0; i < kChunkC / 8; ++i) {
@@ -625,7 +629,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             float r[8];
             if (RES) {
               uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-              if (!direct) rv = *cell;
+              if (!direct && !res_glob) rv = *cell;
               else if (inb && c + 8 <= p.cout) rv = __ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_cs + c));
               else if (inb) {
                 __half* rh1 = reinterpret_cast<__half*>(&rv);
@@ -924,7 +928,7 @@ int his_conv_gemm_create(void** out_plan,
   p.in = (const __half*)in; p.in_sn = (long long)H * W * in_cs; p.in_cs = in_cs; p.cin = cin;
   p.a_stages = 0; p.a_stage_bytes = 0; p.taps_per_b = 1; p.taps_per_box = 1;
   p.out = (__half*)out; p.out_cs = out_cs; p.res = (const __half*)res; p.res_cs = res_cs; p.direct_ok = transposed ? 0 : 1;
-  if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok ? atoi(e) : 0;   // 0 never, 1 channel-clipped chunks, 2 + clipped tiles
+  if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok ? atoi(e) : 0;   // 0 never, 1 channel-clipped chunks, 2 + clipped tiles, 3 = 1 + residual of clipped tiles
   p.debug = 0;
   if (const char* e = getenv("HIS_GEMM_DEBUG")) p.debug = atoi(e);
   p.up_in = (const __half*)in; p.up_sn = 0; p.up_cs = 8; p.up_split = 0;      // no fused upsample

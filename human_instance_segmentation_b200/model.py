@@ -202,7 +202,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         ``(instance_masks [N,1,mh,mw] in {0,1}, binary_masks [B,1,H,W])``; ``raw_logits=True`` gives the older
         released flavour ``(masks [N,3,mh,mw], binary_masks)`` (README.md:537)."""
         from . import postprocess
-        bp = self._get_plan(images, rois)
+        bp = self._masks_only_plan(images, rois)
         bp.load_inputs(images, rois)
         bp.plan.replay()
         logits, binary = bp.logits, bp.binary
@@ -210,6 +210,21 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
             return (logits.clone(), binary.clone()) if self.copy_outputs else (logits, binary)
         inst = postprocess.instance_masks(logits)
         return inst, (binary.clone() if self.copy_outputs else binary)
+
+    def _masks_only_plan(self, images, rois, slot: int = 0):
+        """Launch plan of the exported-ONNX contract: only what `masks` / `binary_masks` depend on (no aux tensors, no contour /
+        distance branches -- the ONNX export prunes them as dead code, export_onnx_advanced.py:353-457)."""
+        saved = self.aux_outputs
+        self.aux_outputs = "none"
+        try:
+            return self._get_plan(images, rois, slot=slot)
+        finally:
+            self.aux_outputs = saved
+
+    def release_plans(self):
+        """Frees every launch plan (and its HBM buffers); the next call rebuilds what it needs."""
+        self.invalidate()
+        torch.cuda.empty_cache()
 
     @torch.no_grad()
     def infer_pipelined(self, images: torch.Tensor, rois: torch.Tensor, out_instance_masks: torch.Tensor, out_binary_masks: torch.Tensor):
@@ -227,7 +242,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         st["i"] += 1
         cur = torch.cuda.current_stream(dev)
         with torch.cuda.stream(st["compute"]):
-            bp = self._get_plan(images, rois, slot=slot)            # built (and graph-captured) on first use of the slot
+            bp = self._masks_only_plan(images, rois, slot=slot)     # built (and graph-captured) on first use of the slot
         mh, mw = self.mask_size
         if st["inst"][slot] is None or st["inst"][slot].shape[0] != rois.shape[0]:
             st["inst"][slot] = torch.empty((rois.shape[0], 1, mh, mw), dtype=torch.float32, device=dev)
@@ -956,8 +971,9 @@ class _BuiltPlan:
             if aux_level == "full":
                 self.h_aux["shared_features"] = shared_nchw if shared_nchw is not None else self.export_nchw(shared)
         # --- auxiliary branches (..._refinement.py:772-802); computed like the reference forward does
-        if head is None:
-            return
+        if head is None or aux_level == "none":
+            return          # contour / distance branches only feed aux outputs: dead code when none is returned (the exported ONNX
+                            # graph, whose outputs are the masks alone, prunes them the same way)
         if m.use_contour_detection:
             cb = head.contour_branch.contour_branch
             c = self.conv(shared, cb[0], cb[1], A_ref)
