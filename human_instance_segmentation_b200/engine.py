@@ -123,7 +123,8 @@ class Plan:
     def conv_gemm(self, x: Act, w_packed: torch.Tensor, cin_pad: int, shift: torch.Tensor, out: Act,
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
                   transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None,
-                  row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None, up_input: Optional[Act] = None):
+                  row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None, up_input: Optional[Act] = None,
+                  res_scale: Optional[torch.Tensor] = None):
         """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
         channels into the epilogue (his_conv_gemm_set_tail).  aux_f32: fp32 NCHW copy of the output written from the
         epilogue (his_conv_gemm_set_aux).  in_gate = (gate fp32 [N, Cin], fp16 scratch >= N*rows*cin_pad): per-image
@@ -156,6 +157,9 @@ class Plan:
             _lib.check(L.his_conv_gemm_set_row_ops(h, row_scale.data_ptr() if row_scale is not None else None,
                                                    stats_out.data_ptr() if stats_out is not None else None), "his_conv_gemm_set_row_ops")
             self.keep += [t for t in (row_scale, stats_out) if t is not None]
+        if res_scale is not None:
+            _lib.check(L.his_conv_gemm_set_res_scale(h, res_scale.data_ptr()), "his_conv_gemm_set_res_scale")
+            self.keep.append(res_scale)
         if up_input is not None:          # channels [0, up_input.C) gathered from the half-resolution tensor (nearest 2x)
             assert (2 * up_input.H, 2 * up_input.W) == (x.H, x.W) and up_input.N == x.N
             _lib.check(L.his_conv_gemm_set_upsampled_input(h, up_input.ptr, up_input.C, up_input.cs), "his_conv_gemm_set_upsampled_input")

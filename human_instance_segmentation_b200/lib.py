@@ -79,6 +79,7 @@ SIGNATURES = {
     "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
     "his_conv_gemm_set_aux": [_P, _P],
     "his_conv_gemm_set_row_ops": [_P, _P, _P],
+    "his_conv_gemm_set_res_scale": [_P, _P],
     "his_conv_gemm_set_upsampled_input": [_P, _P, c_int, c_int],
     "his_conv_gemm_can_fuse_upsample": [c_int, c_int, c_int, c_int, c_int],
     "his_conv_gemm_set_image_weights": [_P, _P],

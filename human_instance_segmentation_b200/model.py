@@ -533,7 +533,7 @@ class _BuiltPlan:
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
              in_gate=None, row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
-             up_input: Optional[Act] = None) -> Optional[Act]:
+             up_input: Optional[Act] = None, res_scale: Optional[torch.Tensor] = None) -> Optional[Act]:
         """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
         tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
         epilogue; the wide activation itself is then not written (its only consumer is the tail).
@@ -578,11 +578,11 @@ class _BuiltPlan:
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(shift, slab)), out,
                         k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate,
-                        row_scale=row_scale, stats_out=stats_out, up_input=up_input)
+                        row_scale=row_scale, stats_out=stats_out, up_input=up_input, res_scale=res_scale)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
-            assert tail is None and aux_f32 is None and in_gate is None and row_scale is None and stats_out is None
+            assert tail is None and aux_f32 is None and in_gate is None and row_scale is None and stats_out is None and res_scale is None
             p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, p.const(pack_direct_weight(w), torch.float16), p.const(scale), p.const(shift),
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
@@ -930,6 +930,7 @@ class _BuiltPlan:
         tb = bh.target_vs_nontarget_branch
         fuse_sa = m.use_attention_module and self._is_bn_mode()
         stats = p.f32(N, rh, rw, 2) if m.use_attention_module else None
+        tn_nat = p.f32(N, 2, 2 * rh, 2 * rw)
         x = self.residual_block(gated, tb[0], A_ref, stats_out=stats if fuse_sa else None)
         if m.use_attention_module:
             kk = tb[1].conv.weight.shape[-1]
@@ -952,13 +953,28 @@ class _BuiltPlan:
             p.add("pool_sum", L.his_pool_sum, x.ptr, N, x.H * x.W, 128, x.cs, pool.data_ptr())
             p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
                   p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, p.f32(N, r).data_ptr(), gate_c.data_ptr())
-            p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
             last_rb, tail = tb[8], tb[9]
+            if self._is_bn_mode() and self._tail_ok(A_ref):
+                # ChannelAttention without a pass over the mask-resolution tensor: x*g feeds the residual block twice -- as conv1's
+                # input (gate folded into per-ROI weights: conv(x*g) = conv_{w*g}(x)) and as the residual (scaled when it is read)
+                c_mid = last_rb.conv1.weight.shape[0]
+                nt, bnn = ctypes.c_int(), ctypes.c_int()
+                L.his_conv_gemm_tile_n(c_mid, ctypes.byref(nt), ctypes.byref(bnn))
+                wscr = torch.empty(N * 9 * nt.value * bnn.value * round_up(c_mid, 64), dtype=torch.float16, device=self.dev)
+                p.keep.append(wscr)
+                t = self.conv(x, last_rb.conv1, last_rb.norm1, A_ref, in_gate=(gate_c, wscr))
+                self.conv(t, last_rb.conv2, last_rb.norm2, A_ref, res=x, res_mode=RES_ADD, res_scale=gate_c, tail=(tail, False, tn_nat))
+                ca_fused = True
+            else:
+                p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
+                ca_fused = False
         else:
             x = self.conv(x, tb[2], tb[3], A_ref)
             last_rb, tail = tb[6], tb[7]
-        tn_nat = p.f32(N, 2, 2 * rh, 2 * rw)
-        if self._tail_ok(A_ref):
+            ca_fused = False
+        if ca_fused:
+            pass
+        elif self._tail_ok(A_ref):
             self.residual_block(x, last_rb, A_ref, tail=(tail, False, tn_nat))
         else:
             x = self.residual_block(x, last_rb, A_ref)

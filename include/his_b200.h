@@ -77,6 +77,9 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out);
  * row_scale [n_img*H*W] fp32 (may be NULL): y = act(row_scale[pix]*conv(x) + shift ...), i.e. the conv of the gated input;
  * stats_out [n_img*H*W][2] fp32 (may be NULL): channel mean and max of this layer's output per pixel. */
 int his_conv_gemm_set_row_ops(void* plan, const float* row_scale, float* stats_out);
+/* res_scale [n_img][cout] fp32: the residual / multiplicand operand is multiplied by res_scale[image][channel] when it is read
+ * (ChannelAttentionModule folded into the following residual block: y = act(conv(.) + shift + g*x)). */
+int his_conv_gemm_set_res_scale(void* plan, const float* res_scale);
 /* Fused nearest 2x upsample + concat of the smp UnetDecoderBlock (F.interpolate(x, mode="nearest") then torch.cat with the
  * skip): channels [0, low_c) of this 3x3 halo-mode layer's input are gathered from `low` [n_img, H/2, W/2, low_cs] at
  * (y>>1, x>>1); the remaining channels come from the `in` buffer given at creation (same channel indices).
