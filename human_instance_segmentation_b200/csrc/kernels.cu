@@ -1030,6 +1030,33 @@ __global__ void input_affine_kernel(const unsigned int* __restrict__ flag, float
   for (int c = 0; c < 3; ++c) { affine[c] = 1.0f / (d * s[c]); affine[3 + c] = -m[c] / s[c]; }
 }
 
+// Stem input for the tensor cores: normalise (x*a[c]+b[c]) and space-to-depth the NCHW fp32 image into NHWC fp16
+// [N, H/2, W/2, 16] with channel (sy*2+sx)*3 + c (12 used, 4 zero).  A 3x3 stride-2 pad-1 conv over the image is then a 2x2
+// stride-1 conv over this tensor (taps (-1,-1),(-1,0),(0,-1),(0,0)), which the halo-mode GEMM runs as a 3x3 with five zero taps.
+__global__ void s2d_input_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ affine, __half* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo;
+  const float a0 = affine[0], a1 = affine[1], a2 = affine[2], b0 = affine[3], b1 = affine[4], b2 = affine[5];
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
+    const long long n = idx / ((long long)Wo * Ho);
+    const float* p0 = img + (n * 3) * (long long)H * W + (long long)(2 * oy) * W + 2 * ox;
+    __half v[16];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float* q = p0 + (s >> 1) * W + (s & 1);
+      v[s * 3 + 0] = __float2half_rn(fmaf(__ldg(q), a0, b0));
+      v[s * 3 + 1] = __float2half_rn(fmaf(__ldg(q + (long long)H * W), a1, b1));
+      v[s * 3 + 2] = __float2half_rn(fmaf(__ldg(q + 2LL * H * W), a2, b2));
+    }
+#pragma unroll
+    for (int e = 12; e < 16; ++e) v[e] = __float2half_rn(0.0f);
+    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&v[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&v[8]);
+  }
+}
+
 // output_conv 1x1 (1->2) + export-wrapper binary mask: two = [w0*x+b0, w1*x+b1]; binary = softmax(two)[:,0]
 __global__ void unet_outputs_kernel(const float* __restrict__ one, int B, long long HW, float w0, float w1, float b0, float b1,
                                     float* __restrict__ two, float* __restrict__ binary) {
@@ -1441,6 +1468,16 @@ int his_unet_input_affine(const float* images, long long count, const float* mea
   fill_u32_kernel<<<1, 32, 0, ST>>>(flag_ws, 1, 0u);
   if (count > 0) max_reduce_kernel<<<grid_for(count), kThreads, 0, ST>>>(images, count, flag_ws);
   input_affine_kernel<<<1, 1, 0, ST>>>(flag_ws, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], affine6);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_s2d_input(const float* images, int N, int H, int W, const float* affine6, void* out_half, void* stream) {
+  if (!images || !affine6 || !out_half) return his_set_error(HIS_ERR_INVALID_ARG, "s2d_input: null pointer");
+  if ((H & 1) || (W & 1)) return his_set_error(HIS_ERR_UNSUPPORTED, "s2d_input: H and W must be even");
+  const long long total = (long long)N * (H >> 1) * (W >> 1);
+  if (total == 0) return HIS_OK;
+  s2d_input_kernel<<<grid_for(total), kThreads, 0, ST>>>(images, N, H, W, affine6, (__half*)out_half);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

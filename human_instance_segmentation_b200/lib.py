@@ -112,6 +112,7 @@ SIGNATURES = {
     "his_scale_pixels": [_P, c_int, _P, _P, _LL, c_int, _P, c_int, _P],
     "his_guided_aux": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "his_unet_input_affine": [_P, _LL, _F, _F, _P, _P, _P],
+    "his_s2d_input": [_P, c_int, c_int, c_int, _P, _P, _P],
     "his_unet_outputs": [_P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, _P, _P, _P],
     "his_memset_async": [_P, c_int, _LL, _P],
     # post-processing (csrc/post.cu)

@@ -669,8 +669,30 @@ class _BuiltPlan:
         stem_c = oc[1]
         x = skip_slot[1]
         scale, shift = fold_bn(None, enc.bn1, stem_c)
-        p.conv_direct(self.u_images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
-                      p.const(shift), stem_c, 3, 2, 1, ACT["silu"], 1.0, in_affine=affine, out=x)
+        if H % 2 == 0 and W % 2 == 0 and stem_c >= 16:
+            # stem on the tensor cores: normalise + space-to-depth the image (one pass), then the 3x3 s2 conv is a 2x2 s1 conv over
+            # [B, H/2, W/2, 16], run by the halo-mode GEMM as a 3x3 whose other five taps are zero
+            s2d = p.act(B, H // 2, W // 2, 16)
+            p.add("s2d_input", L.his_s2d_input, self.u_images.data_ptr(), B, H, W, affine.data_ptr(), s2d.ptr)
+            w = enc.conv_stem.weight.detach().float().cpu()                       # [stem_c, 3, 3, 3]
+            w2 = torch.zeros(stem_c, 16, 3, 3)
+            for a in (-1, 0):                   # s2d row offset
+                for sy in (0, 1):
+                    ky = 2 * a + sy + 1
+                    if not 0 <= ky <= 2:
+                        continue
+                    for b_ in (-1, 0):
+                        for sx in (0, 1):
+                            kx = 2 * b_ + sx + 1
+                            if 0 <= kx <= 2:
+                                w2[:, (sy * 2 + sx) * 3:(sy * 2 + sx) * 3 + 3, a + 1, b_ + 1] = w[:, :, ky, kx]
+            stem = nn.Conv2d(16, stem_c, 3, padding=1, bias=False)
+            with torch.no_grad():
+                stem.weight.copy_(w2)
+            self.conv(s2d, stem, enc.bn1, ACT["silu"], out=x)
+        else:
+            p.conv_direct(self.u_images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
+                          p.const(shift), stem_c, 3, 2, 1, ACT["silu"], 1.0, in_affine=affine, out=x)
         level_of_stage = {1: 2, 2: 3, 4: 4}
         # scratch for the per-image gated projection weights, sized for the widest block (the blocks run back to back)
         need = 0

@@ -178,6 +178,9 @@ int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, i
  * softmax(two)[:,0] (hed/export_onnx_advanced.py:374-387). */
 int his_unet_input_affine(const float* images, long long count, const float* mean3, const float* std3,
                           unsigned int* flag_ws, float* affine6, void* stream);
+/* Normalised, space-to-depth copy of the NCHW fp32 images for the stem conv (timm conv_stem 3x3 s2 p1): NHWC half
+ * [N, H/2, W/2, 16], channel (sy*2+sx)*3 + c; the stride-2 conv becomes a 2x2 stride-1 conv the tensor-core GEMM can run. */
+int his_s2d_input(const float* images, int N, int H, int W, const float* affine6, void* out_half, void* stream);
 int his_unet_outputs(const float* one, int B, int H, int W, float w0, float w1, float b0, float b1, float* two,
                      float* binary, void* stream);
 
