@@ -999,6 +999,71 @@ __global__ void guided_aux_kernel(const float* __restrict__ in, int C, int c, in
   }
 }
 
+// ---- refinement flags of the refined head (hierarchical_segmentation_refinement.py)
+// PixelShuffle(2) of NCHW fp32 (SubPixelDecoder :218-252): out[n][c][2y+i][2x+j] = in[n][c*4 + i*2 + j][y][x]; the input holds
+// in_ch >= 4*C channels per image (the producing GEMM pads 12 to 16)
+__global__ void pixel_shuffle2_kernel(const float* __restrict__ in, int N, int C, int in_ch, int h, int w, float* __restrict__ out) {
+  const int Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)N * C * Ho * Wo;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
+    const long long nc = idx / ((long long)Wo * Ho);
+    const long long n = nc / C; const int c = (int)(nc - n * C);
+    out[idx] = in[((n * in_ch + c * 4 + (oy & 1) * 2 + (ox & 1)) * h + (oy >> 1)) * (long long)w + (ox >> 1)];
+  }
+}
+
+__device__ __forceinline__ void softmax3(const float* __restrict__ l, long long HW, long long p, float* pr) {
+  const float a = l[p], b = l[HW + p], c = l[2 * HW + p];
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+  const float s = (ea + eb) + ec;
+  pr[0] = ea / s; pr[1] = eb / s; pr[2] = ec / s;
+}
+
+// BoundaryRefinementModule.detect_edges (:94-129) before the normalisation: mean_c sqrt(dy^2 + dx^2) of the softmax gradients
+// (forward differences, last row / column replicated), and the min / max over the WHOLE batch tensor (non-negative floats order
+// like their bit patterns -> integer atomics, order independent).
+__global__ void boundary_edges_kernel(const float* __restrict__ logits, int N, int H, int W, float* __restrict__ edges, unsigned int* __restrict__ minmax) {
+  const long long HW = (long long)H * W, total = (long long)N * HW;
+  float lo = INFINITY, hi = 0.0f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / HW, p = idx - n * HW;
+    const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+    const float* l = logits + n * 3 * HW;
+    // replicate padding of the difference maps: the last row uses rows (H-2, H-1), the last column columns (W-2, W-1)
+    const int yy = H > 1 ? min(y, H - 2) : 0, xx = W > 1 ? min(x, W - 2) : 0;
+    float e = 0.0f;
+    float a0[3], a1[3], b0[3], b1[3];
+    softmax3(l, HW, (long long)yy * W + x, a0); softmax3(l, HW, (long long)min(yy + 1, H - 1) * W + x, a1);
+    softmax3(l, HW, (long long)y * W + xx, b0); softmax3(l, HW, (long long)y * W + min(xx + 1, W - 1), b1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float dy = fabsf(a1[c] - a0[c]), dx = fabsf(b1[c] - b0[c]);
+      e += sqrtf(dy * dy + dx * dx);
+    }
+    e /= 3.0f;
+    edges[idx] = e;
+    lo = fminf(lo, e); hi = fmaxf(hi, e);
+  }
+  for (int o = 16; o; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(minmax, __float_as_uint(lo)); atomicMax(minmax + 1, __float_as_uint(hi)); }
+}
+
+// refined = logits + blend * edge_conv(logits) * normalised_edges   (:131-149)
+__global__ void boundary_blend_kernel(const float* __restrict__ logits, const float* __restrict__ corr, const float* __restrict__ edges,
+                                      const unsigned int* __restrict__ minmax, const float* __restrict__ blend, int N, long long HW, float* __restrict__ out) {
+  const float lo = __uint_as_float(minmax[0]), hi = __uint_as_float(minmax[1]);
+  const bool flat = (hi - lo) < 1e-6f;
+  const float inv = 1.0f / ((hi - lo) + 1e-6f), bw = *blend;
+  const long long total = (long long)N * 3 * HW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / (3 * HW), p = idx % HW;
+    const float e = flat ? 0.0f : (edges[n * HW + p] - lo) * inv;
+    out[idx] = logits[idx] + bw * corr[idx] * e;
+  }
+}
+
 // NHWC fp16 slice -> NCHW fp32 (aux outputs: shared_features, fg_attention)
 __global__ void nhwc_half_to_nchw_float_kernel(const __half* __restrict__ in, int N, int HW, int C, int cs, float* __restrict__ out) {
   __shared__ float tile[32][33];
@@ -1449,6 +1514,36 @@ int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, i
   const long long total = (long long)N * Ho * Wo;
   if (total == 0) return HIS_OK;
   guided_aux_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, C, c, H, W, Ho, Wo, total, mask_out, fg_out, bgfg_out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_pixel_shuffle2_f32(const float* in, int N, int C, int in_channels, int h, int w, float* out, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "pixel_shuffle2: null pointer");
+  if (in_channels < 4 * C) return his_set_error(HIS_ERR_INVALID_ARG, "pixel_shuffle2: in_channels < 4*C");
+  const long long total = (long long)N * C * 4 * h * w;
+  if (total == 0) return HIS_OK;
+  pixel_shuffle2_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, N, C, in_channels, h, w, out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_boundary_edges(const float* logits, int N, int H, int W, float* edges, unsigned int* minmax_ws, void* stream) {
+  if (!logits || !edges || !minmax_ws) return his_set_error(HIS_ERR_INVALID_ARG, "boundary_edges: null pointer");
+  fill_u32_kernel<<<1, 32, 0, ST>>>(minmax_ws, 1, 0x7f800000u);      // +inf
+  fill_u32_kernel<<<1, 32, 0, ST>>>(minmax_ws + 1, 1, 0u);
+  const long long total = (long long)N * H * W;
+  if (total > 0) boundary_edges_kernel<<<grid_for(total), kThreads, 0, ST>>>(logits, N, H, W, edges, minmax_ws);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_boundary_blend(const float* logits, const float* correction, const float* edges, const unsigned int* minmax_ws, const float* blend_weight,
+                       int N, int H, int W, float* out, void* stream) {
+  if (!logits || !correction || !edges || !minmax_ws || !blend_weight || !out) return his_set_error(HIS_ERR_INVALID_ARG, "boundary_blend: null pointer");
+  const long long total = (long long)N * 3 * H * W;
+  if (total == 0) return HIS_OK;
+  boundary_blend_kernel<<<grid_for(total), kThreads, 0, ST>>>(logits, correction, edges, minmax_ws, blend_weight, N, (long long)H * W, out);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

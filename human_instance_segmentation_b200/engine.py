@@ -111,7 +111,7 @@ class Plan:
             self.tensor_flops += f
 
     # kernels launched per op (cudaMemsetAsync is not one of ours)
-    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0, "se_gate": 3}
+    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0, "se_gate": 3, "boundary_edges": 3}
 
     def add(self, name: str, fn, *args, flops: int = 0, desc: str = ""):
         self.ops.append((name, fn, args))

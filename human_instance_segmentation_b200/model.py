@@ -169,10 +169,12 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         self.use_attention_module = bool(use_attention_module)
         self.use_contour_detection = bool(use_contour_detection)
         self.use_distance_transform = bool(use_distance_transform)
-        if use_boundary_refinement or use_progressive_upsampling or use_subpixel_conv:
-            raise NotImplementedError("boundary refinement / progressive upsampling / sub-pixel decoders are not part of the "
-                                      "preset path (all three presets disable them) and are not implemented on B200")
-        self.use_refinement = bool(use_contour_detection or use_distance_transform)      # rgb.py:683-689
+        if use_progressive_upsampling:
+            raise NotImplementedError("ProgressiveUpsamplingDecoder (ConvTranspose2d k4 s2 stages, disabled in every preset) is not "
+                                      "implemented on B200")
+        self.use_boundary_refinement = bool(use_boundary_refinement)
+        self.use_subpixel_conv = bool(use_subpixel_conv)
+        self.use_refinement = bool(use_contour_detection or use_distance_transform or use_boundary_refinement or use_subpixel_conv)   # rgb.py:683-689
         self.pretrained_unet = PreTrainedPeopleSegmentationUNetWrapper(
             in_channels=3, pretrained_weights_path=pretrained_weights_path, freeze_weights=freeze_pretrained_weights,
             encoder_name=kwargs.get("encoder_name", "timm-efficientnet-b3"))
@@ -189,7 +191,8 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         if self.use_refinement:
             self.feature_combiner = nn.Conv2d(258, 256, 1)
             self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
-                                                          self.use_distance_transform, base, depth)
+                                                          self.use_distance_transform, base, depth, self.use_boundary_refinement,
+                                                          self.use_subpixel_conv)
         else:                                  # rgb.py:715-727: the UNet-guided head takes (features, roi masks) directly
             self.segmentation_head = pt.GuidedHeadParams(256, 256, n, self.use_attention_module)
         self.hierarchical_depth = depth
@@ -306,15 +309,17 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
             raise AssertionError("Hierarchical model designed for 3 classes")           # ..._unet.py:703
         if feature_channels != 256:
             raise NotImplementedError("feature_channels != 256 is not implemented on B200 (the factory never passes it)")
-        if use_boundary_refinement or use_progressive_upsampling or use_subpixel_conv:
-            raise NotImplementedError("boundary refinement / progressive upsampling / sub-pixel decoders are not implemented on B200")
+        if use_progressive_upsampling:
+            raise NotImplementedError("ProgressiveUpsamplingDecoder is not implemented on B200")
+        self.use_boundary_refinement = bool(use_boundary_refinement)
+        self.use_subpixel_conv = bool(use_subpixel_conv)
         self.roi_size = _pair(roi_size)
         self.mask_size = _pair(mask_size)
         n = kwargs.get("normalization_type", "layernorm2d")
         self.use_attention_module = bool(use_attention_module)
         self.use_contour_detection = bool(use_contour_detection)
         self.use_distance_transform = bool(use_distance_transform)
-        self.use_refinement = bool(use_contour_detection or use_distance_transform)
+        self.use_refinement = bool(use_contour_detection or use_distance_transform or use_boundary_refinement or use_subpixel_conv)
         # the reference passes no activation to any sub-module here: everything is ReLU
         self.activation_function, self.activation_beta = "relu", 1.0
         self.normalization_type = n if self.use_refinement else "layernorm2d"       # head norm (V2 head: LayerNorm2d hard-coded)
@@ -322,7 +327,7 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
         self.rgb_extractor = pt.RGBFeatureExtractorParams(n)
         if self.use_refinement:
             self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
-                                                          self.use_distance_transform, 96, 3)
+                                                          self.use_distance_transform, 96, 3, self.use_boundary_refinement, self.use_subpixel_conv)
         else:
             self.segmentation_head = pt.BaseHeadParams(256, 256, "layernorm2d", self.use_attention_module, 96, 3)
         self.roi_align = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=False)      # rgb.py:404-408
@@ -381,6 +386,8 @@ class _CompositePlan:
         parts = [(bp.unet_plan, bp.n_unet_chunks)]
         if bp.head_plan is not None:
             parts.append((bp.head_plan, bp.n_head_chunks))
+        if bp.post_plan is not None:
+            parts.append((bp.post_plan, 1))
         return parts
 
     @property
@@ -481,6 +488,12 @@ class _BuiltPlan:
                 self._build_head_standard()
             for k, v in self.h_aux.items():
                 self.aux[k] = (self.plan.f32(N, *v.shape[1:]) if self.chunked_head else v) if v is not None else None
+        # ---- post sub-plan over ALL ROIs (the boundary refiner normalises its edge map over the whole batch tensor)
+        self.post_plan = None
+        if N and getattr(m, "use_boundary_refinement", False):
+            self.post_plan = self.plan = Plan(dev)
+            self.plan.tag = "post"
+            self._build_boundary_refiner()
         self.plan = _CompositePlan(self)
 
     # -------------------------------------------------------------- I/O + schedule
@@ -524,6 +537,11 @@ class _BuiltPlan:
                 for k, v in self.h_aux.items():
                     if v is not None:
                         self.aux[k][j0:j0 + n].copy_(v[:n])
+        if self.post_plan is not None:
+            if timed:
+                out += self.post_plan.run_timed()
+            else:
+                self.post_plan.replay()
         return out
 
     # -------------------------------------------------------------- helpers
@@ -828,6 +846,35 @@ class _BuiltPlan:
         if m.aux_outputs != "none":
             self.h_aux["roi_patches"] = roi_patch
 
+    def _build_boundary_refiner(self):
+        """BoundaryRefinementModule (..._refinement.py:58-149) on the full [N,3,mh,mw] logits, in place."""
+        m, p, L = self.m, self.plan, self.plan.lib
+        N = self.N
+        mh, mw = m.mask_size
+        br = m.segmentation_head.boundary_refiner
+        A = self.act_ref
+        edges = p.f32(N, mh, mw)
+        minmax = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        p.keep.append(minmax)
+        p.add("boundary_edges", L.his_boundary_edges, self.logits.data_ptr(), N, mh, mw, edges.data_ptr(), minmax.data_ptr())
+        ec = br.edge_conv
+        c = ec[0].weight.shape[0]
+        x = p.act(N, mh, mw, c)
+        if self._is_bn(ec[1]):
+            sc, sh = fold_bn(ec[0].bias, ec[1], c)
+            p.conv_direct(self.logits, 1, N, mh, mw, 3, 0, p.const(pack_direct_weight(ec[0].weight), torch.float16), p.const(sc), p.const(sh), c, 3, 1, 1,
+                          A, self.beta, out=x)
+        else:
+            sc, sh = fold_bn(ec[0].bias, None, c)
+            p.conv_direct(self.logits, 1, N, mh, mw, 3, 0, p.const(pack_direct_weight(ec[0].weight), torch.float16), p.const(sc), p.const(sh), c, 3, 1, 1,
+                          ACT["none"], self.beta, out=x)
+            x = self.layernorm(x, ec[1], A)
+        x = self.conv(x, ec[3], ec[4], A)
+        corr = p.f32(N, 3, mh, mw)
+        self.conv(x, ec[6], None, ACT["none"], out_f32=corr)
+        p.add("boundary_blend", L.his_boundary_blend, self.logits.data_ptr(), corr.data_ptr(), edges.data_ptr(), minmax.data_ptr(),
+              p.const(br.blend_weight.detach().reshape(1)).data_ptr(), N, mh, mw, self.logits.data_ptr())
+
     def _rgb_extractor(self, x: Act, features, norm_kind: str, act_stage: int, act_rb: int) -> Act:
         """RGBFeatureExtractor (rgb.py:221-295): [conv3x3, norm, act] per stage, a ResidualBlock after every stage but the first."""
         m = self.m
@@ -1003,6 +1050,20 @@ class _BuiltPlan:
             self.conv(x, tail, None, ACT["none"], out_f32=tn_nat)
         tn = self.to_mask_size(tn_nat)
         p.add("head_combine", L.his_head_combine, bgfg.data_ptr(), tn.data_ptr(), N, mh, mw, self.h_logits.data_ptr())
+        if head is not None and getattr(m, "use_subpixel_conv", False):
+            # SubPixelDecoder (..._refinement.py:218-252) re-decodes the shared features and REPLACES the hierarchical logits (:753-763):
+            # conv3x3 256 -> 12 with the fp32 NCHW copy written by the GEMM epilogue, PixelShuffle(2), bilinear to the mask size
+            sp = head.subpixel_decoder
+            conv16 = nn.Conv2d(256, 16, 3, padding=1)              # 12 real output channels, padded to the GEMM's minimum N tile
+            with torch.no_grad():
+                conv16.weight.zero_(); conv16.bias.zero_()
+                conv16.weight[:12].copy_(sp.conv.weight.detach().float().cpu()); conv16.bias[:12].copy_(sp.conv.bias.detach().float().cpu())
+            sub16 = p.f32(N, 16, rh, rw)
+            self.conv(shared, conv16, None, ACT["none"], aux_f32=sub16)
+            shuf = self.h_logits if (2 * rh, 2 * rw) == (mh, mw) else p.f32(N, 3, 2 * rh, 2 * rw)
+            p.add("pixel_shuffle", L.his_pixel_shuffle2_f32, sub16.data_ptr(), N, 3, 16, rh, rw, shuf.data_ptr())
+            if shuf is not self.h_logits:
+                p.add("resize_bilinear", L.his_resize_bilinear_f32, shuf.data_ptr(), N * 3, 2 * rh, 2 * rw, mh, mw, self.h_logits.data_ptr())
 
         if aux_level != "none":
             self.h_aux.update({"bg_fg_logits": bgfg, "bg_fg_logits_low": low, "target_nontarget_logits": tn})

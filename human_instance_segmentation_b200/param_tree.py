@@ -150,12 +150,34 @@ class DistanceDecoderParams(nn.Module):
         self.threshold = nn.Parameter(torch.tensor(0.3))
 
 
-class RefinedHeadParams(nn.Module):
-    """RefinedHierarchicalSegmentationHead, ..._refinement.py:609-732 (preset flags)."""
+class BoundaryRefinerParams(nn.Module):
+    """BoundaryRefinementModule, ..._refinement.py:58-92."""
 
-    def __init__(self, cin, mid, norm, attention, contour, distance, base, depth):
+    def __init__(self, norm: str, c: int = 32):
+        super().__init__()
+        self.edge_conv = nn.Sequential(nn.Conv2d(3, c, 3, padding=1), norm_params(norm, c), Slot(), nn.Conv2d(c, c, 3, padding=1),
+                                       norm_params(norm, c), Slot(), nn.Conv2d(c, 3, 1))
+        self.blend_weight = nn.Parameter(torch.tensor(0.01))
+
+
+class SubPixelDecoderParams(nn.Module):
+    """SubPixelDecoder, ..._refinement.py:218-240."""
+
+    def __init__(self, cin: int, num_classes: int = 3, upscale: int = 2):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, num_classes * upscale ** 2, 3, padding=1)
+
+
+class RefinedHeadParams(nn.Module):
+    """RefinedHierarchicalSegmentationHead, ..._refinement.py:609-732 (module order = the reference constructor's)."""
+
+    def __init__(self, cin, mid, norm, attention, contour, distance, base, depth, boundary=False, subpixel=False):
         super().__init__()
         self.base_head = BaseHeadParams(cin, mid, norm, attention, base, depth)
+        if boundary:
+            self.boundary_refiner = BoundaryRefinerParams(norm)
+        if subpixel:
+            self.subpixel_decoder = SubPixelDecoderParams(mid)
         if contour:
             self.contour_branch = ContourBranchParams(mid, 64, norm)
         if distance:

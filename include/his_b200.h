@@ -159,6 +159,16 @@ int his_head_combine(const float* bgfg, const float* tn, int N, int H, int W, fl
 int his_map_f32(const float* in, long long total, int op, const float* param, float* out, void* stream);
 int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, void* stream);
 
+/* ---- refinement flags of RefinedHierarchicalSegmentationHead (hed/advanced/hierarchical_segmentation_refinement.py):
+ * his_pixel_shuffle2_f32: nn.PixelShuffle(2) of SubPixelDecoder (:218-252), NCHW fp32 [N,in_channels>=4C,h,w] -> [N,C,2h,2w];
+ * his_boundary_edges: BoundaryRefinementModule.detect_edges (:94-129) up to the normalisation -- raw edge map [N,H,W] and the
+ *   min / max over the whole tensor in minmax_ws[2] (bit patterns); his_boundary_blend: logits + blend * correction * normalised
+ *   edges (:131-149), blend_weight is the device scalar parameter. */
+int his_pixel_shuffle2_f32(const float* in, int N, int C, int in_channels, int h, int w, float* out, void* stream);
+int his_boundary_edges(const float* logits, int N, int H, int W, float* edges, unsigned int* minmax_ws, void* stream);
+int his_boundary_blend(const float* logits, const float* correction, const float* edges, const unsigned int* minmax_ws,
+                       const float* blend_weight, int N, int H, int W, float* out, void* stream);
+
 /* ---- PretrainedUNetGuidedSegmentationHead glue, hed/advanced/hierarchical_segmentation_rgb.py:125-218 (the head the
  * factory builds when no refinement flag is set, :715-727).
  * his_sigmoid_channel: fg_prob = sigmoid(in[:,c]) of NCHW fp32 [N,C,HW] (:146) -> channel 0 of an NHWC half slice

@@ -49,6 +49,8 @@ class PathConfig:
     # False -> HierarchicalRGBSegmentationModel (rgb.py:298-439): no UNet branch, one RoIAlign with aligned=False
     use_pretrained_unet: bool = True
     # True -> MultiScaleRGBSegmentationModel (rgb.py:777-922)
+    use_boundary_refinement: bool = False      # BoundaryRefinementModule on the final logits (..._refinement.py:58-149)
+    use_subpixel_conv: bool = False            # SubPixelDecoder re-decode of the shared features (:218-252)
     multi_scale: bool = False
     roi_sizes: tuple = (("scale1", 56), ("scale2", 42), ("scale3", 28))
     fusion_method: str = "concat"
@@ -65,6 +67,7 @@ class PathConfig:
                         normalization_groups=8)
         return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
                     use_attention_module=self.use_attention_module,
+                    use_boundary_refinement=self.use_boundary_refinement, use_subpixel_conv=self.use_subpixel_conv,
                     use_contour_detection=self.use_contour_detection,
                     use_distance_transform=self.use_distance_transform,
                     normalization_type=self.normalization_type, normalization_groups=8,
@@ -349,11 +352,31 @@ def base_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig):
     return logits, aux
 
 
+def boundary_refine(sd: SD, p: str, logits: Tensor, cfg: PathConfig) -> Tensor:
+    """BoundaryRefinementModule.forward (..._refinement.py:131-149): edge map from softmax gradients, normalised by the min / max
+    over the WHOLE batch tensor (:118-128), gates a small conv net's correction."""
+    probs = torch.softmax(logits, 1)
+    dy = F.pad((probs[:, :, 1:] - probs[:, :, :-1]).abs(), (0, 0, 0, 1), mode="replicate")
+    dx = F.pad((probs[:, :, :, 1:] - probs[:, :, :, :-1]).abs(), (0, 1, 0, 0), mode="replicate")
+    edges = torch.sqrt(dy ** 2 + dx ** 2).mean(1, keepdim=True)
+    emin, emax = edges.min(), edges.max()
+    edges = torch.zeros_like(edges) if emax - emin < 1e-6 else (edges - emin) / (emax - emin + 1e-6)
+    e = p + "edge_conv."
+    x = act_ref(norm(sd, e + "1.", conv(sd, e + "0.", logits, 1), cfg), cfg)
+    x = act_ref(norm(sd, e + "4.", conv(sd, e + "3.", x, 1), cfg), cfg)
+    x = conv(sd, e + "6.", x, 0)
+    return logits + sd[p + "blend_weight"] * x * edges
+
+
 def refined_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig):
     """RefinedHierarchicalSegmentationHead.forward (..._refinement.py:734-804), preset flags only
     (no boundary refiner / progressive / sub-pixel decoders)."""
     logits, aux = base_head(sd, p + "base_head.", feats, cfg)
     shared = aux["shared_features"]
+    if cfg.use_subpixel_conv:         # SubPixelDecoder :218-252 replaces the hierarchical logits (:753-763)
+        logits = _to_mask_size(F.pixel_shuffle(conv(sd, p + "subpixel_decoder.conv.", shared, 1), 2), cfg)
+    if cfg.use_boundary_refinement:   # BoundaryRefinementModule :58-149
+        logits = boundary_refine(sd, p + "boundary_refiner.", logits, cfg)
     if cfg.use_contour_detection:     # ContourDetectionBranch :255-295
         c = p + "contour_branch.contour_branch."
         x = act_ref(norm(sd, c + "1.", conv(sd, c + "0.", shared, 1), cfg), cfg)
@@ -404,7 +427,7 @@ def guided_head(sd: SD, p: str, feats: Tensor, bg_fg_mask: Tensor, cfg: PathConf
 
 def uses_refined_head(cfg: PathConfig) -> bool:
     """rgb.py:683-689: any refinement flag selects RefinedHierarchicalSegmentationHead (+ feature_combiner)."""
-    return bool(cfg.use_contour_detection or cfg.use_distance_transform)
+    return bool(cfg.use_contour_detection or cfg.use_distance_transform or cfg.use_boundary_refinement or cfg.use_subpixel_conv)
 
 
 @torch.no_grad()

@@ -59,6 +59,14 @@ STANDARD_CASES = {
     "small_std_refined_bn_att": (headport.PathConfig(roi_size=(16, 12), mask_size=(40, 28), normalization_type="batchnorm",
                                                      use_attention_module=True, use_pretrained_unet=False), (96, 128)),
 }
+# a7 flags that no headline preset enables: boundary refiner and sub-pixel re-decode (..._refinement.py:58-149, 218-252, 734-770)
+REFINE_CASES = {
+    "small_b0_boundary": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), use_boundary_refinement=True), (96, 128)),
+    "small_b0_subpixel_boundary_ln": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28), use_boundary_refinement=True,
+                                              use_subpixel_conv=True, use_contour_detection=False, use_distance_transform=False,
+                                              normalization_type="layernorm2d", use_attention_module=False), (96, 128)),
+}
+
 # a1 multi_scale=True -> MultiScaleRGBSegmentationModel (rgb.py:777-922): default fusion/normalisation, and batchnorm + SiLU +
 # adaptive fusion + attention with two scales
 MULTISCALE_CASES = {
@@ -69,7 +77,7 @@ MULTISCALE_CASES = {
                                                           use_attention_module=True, use_contour_detection=False, use_distance_transform=False,
                                                           use_pretrained_unet=False), (96, 128)),
 }
-SMALL_CASES_ALL = {**SMALL_CASES, **GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES}
+SMALL_CASES_ALL = {**SMALL_CASES, **GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES, **REFINE_CASES}
 
 _FULL_KEYS = ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_mask",
               "distance_map", "roi_features", "roi_patches")
@@ -140,7 +148,7 @@ def make_guided_goldens():
     """The guided-head variant; adds its key/shape tables to state_dict_keys.json without touching the other entries."""
     path = os.path.join(GOLDEN, "state_dict_keys.json")
     keys_json = json.load(open(path))
-    for name, (cfg, (h, w)) in {**GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES}.items():
+    for name, (cfg, (h, w)) in {**GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES, **REFINE_CASES}.items():
         images = synth_images(11, 2, h, w)
         rois = torch.cat([synth_rois(11, 2, 2), edge_rois(2)], 0)
         model, sd, logits, aux = _run_reference(cfg, images, rois)

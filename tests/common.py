@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from oracle import headport, paramfill
-from oracle.make_golden import GUIDED_CASES, MULTISCALE_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
+from oracle.make_golden import GUIDED_CASES, MULTISCALE_CASES, REFINE_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -47,6 +47,8 @@ def procedural_state(shapes: dict, seed=0, weights_path="ext_extractor/best_mode
     for k in sd:
         if k.endswith("distance_decoder.threshold"):
             sd[k] = torch.tensor(0.3)
+        if k.endswith("boundary_refiner.blend_weight"):
+            sd[k] = torch.tensor(0.01)           # ..._refinement.py:90 (scalars keep their constructor value)
     return paramfill.fill_state_dict(sd, seed=seed, mode=mode)
 
 

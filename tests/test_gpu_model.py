@@ -130,6 +130,24 @@ def test_multiscale_model_matches_reference_golden(name):
     assert set(aux) == set(keys) | {"fg_attention"}
 
 
+@pytest.mark.parametrize("name", list(common.REFINE_CASES))
+def test_refinement_flags_match_reference_golden(name):
+    """a7 flags no headline preset enables: BoundaryRefinementModule (edge map normalised over the WHOLE batch tensor -> its own
+    sub-plan after the ROI chunks) and SubPixelDecoder (..._refinement.py:58-149, 218-252, 734-770)."""
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    m = build(cfg, common.shapes_for_case(name))
+    logits, aux = m(images.cuda(), rois.cuda())
+    check(logits, g["logits"], "logits")
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= 0.998
+    for k in ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "roi_features", "roi_patches"):
+        check(aux[k], g[k], k)
+    # chunked ROI schedule: the refiner still sees all ROIs at once
+    m.max_rois_per_pass = 4
+    logits2, _ = m(images.cuda(), rois.cuda())
+    check(logits2, g["logits"], "logits(chunked)")
+
+
 def test_model_matches_reference_golden_config1():
     """BASELINE.json configs[0]: B0 std, 2x3x480x640, 8 ROIs, 64x48 -> 128x96."""
     cfg, images, rois = common.cfg1_inputs()

@@ -34,6 +34,16 @@ def test_guided_variant_state_dict_matches_reference(name):
     assert not hasattr(model, "feature_combiner")
 
 
+@pytest.mark.parametrize("name", list(common.REFINE_CASES))
+def test_refinement_flag_state_dict_matches_reference(name):
+    cfg = common.REFINE_CASES[name][0]
+    model = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    want = common.golden_keys()[name]
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert got == want and list(got) == list(want)
+    assert float(model.segmentation_head.boundary_refiner.blend_weight) == pytest.approx(0.01)
+
+
 @pytest.mark.parametrize("name", list(common.MULTISCALE_CASES))
 def test_multiscale_state_dict_matches_reference(name):
     cfg = common.MULTISCALE_CASES[name][0]
@@ -84,7 +94,7 @@ def test_factory_errors_match_reference_behaviour():
     with pytest.raises(ValueError):     # normalization_comparison.py:206
         his.create_rgb_hierarchical_model(**{**kw, "normalization_type": "nonsense"})
     with pytest.raises(NotImplementedError):       # sub-pixel / progressive decoders are not part of any preset
-        his.create_rgb_hierarchical_model(**{**kw, "use_subpixel_conv": True})
+        his.create_rgb_hierarchical_model(**{**kw, "use_progressive_upsampling": True})
 
 
 def test_no_cpu_fallback():

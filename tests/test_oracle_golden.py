@@ -57,6 +57,15 @@ def test_standard_model_port_matches_reference(name):
         assert common.rel_err(aux[k], g[k]) < 5e-5, k
 
 
+@pytest.mark.parametrize("name", list(common.REFINE_CASES))
+def test_refinement_flags_port_matches_reference(name):
+    cfg, images, rois = common.small_case_inputs(name)
+    g = common.golden(name)
+    logits, aux = headport.forward(_state(name), images, rois, cfg)
+    assert common.rel_err(logits, g["logits"]) < 2e-5
+    assert common.rel_err(aux["bg_fg_logits"], g["bg_fg_logits"]) < 5e-5
+
+
 def test_port_matches_reference_cfg1():
     cfg, images, rois = common.cfg1_inputs()
     g = common.golden("cfg1_b0")
