@@ -41,7 +41,7 @@ def test_refinement_flag_state_dict_matches_reference(name):
     want = common.golden_keys()[name]
     got = {k: list(v.shape) for k, v in model.state_dict().items()}
     assert got == want and list(got) == list(want)
-    assert float(model.segmentation_head.boundary_refiner.blend_weight) == pytest.approx(0.01)
+    assert float(model.segmentation_head.boundary_refiner.blend_weight.detach()) == pytest.approx(0.01)
 
 
 @pytest.mark.parametrize("name", list(common.MULTISCALE_CASES))
