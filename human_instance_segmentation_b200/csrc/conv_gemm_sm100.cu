@@ -846,6 +846,13 @@ int pick_bk(int cin) {
 
 int g_num_sms = 0;
 
+// Widest N tile that runs in halo mode.  Measured on the full B0 step: N <= 96 layers gain 2-3.5x from the halo mode, N = 128
+// layers are ahead again in per-tap TMA mode (12.7k vs 12.35k ROI-masks/s), N = 256 is tensor bound in either.
+int halo_max_n() {
+  if (const char* e = getenv("HIS_GEMM_HALO_MAXN")) return atoi(e);
+  return 96;
+}
+
 }  // namespace
 
 extern "C" {
@@ -906,9 +913,7 @@ int his_conv_gemm_create(void** out_plan,
   his_conv_gemm_tile_n(cout, &tn_tiles, &tblock_n);
   int halo = ksize == 3 && !transposed && (cin % 8) == 0;
   if (const char* e = getenv("HIS_GEMM_HALO")) halo = halo && atoi(e) != 0;
-  int halo_maxn = 128;   // measured: the per-tap TMA path is ahead again from N = 160 up (one tap per weight stage there)
-  if (const char* e = getenv("HIS_GEMM_HALO_MAXN")) halo_maxn = atoi(e);
-  halo = halo && tblock_n <= halo_maxn;
+  halo = halo && tblock_n <= halo_max_n();
   pl->halo = halo;
   // pick the 128-pixel rectangle with the least padded area
   long long best = -1;
@@ -1073,8 +1078,7 @@ int his_conv_gemm_set_upsampled_input(void* plan, const void* low, int low_c, in
 int his_conv_gemm_can_fuse_upsample(int H, int W, int cin, int cout, int low_c) {
   int nt = 0, bn = 0;
   if (his_conv_gemm_tile_n(cout, &nt, &bn) != HIS_OK) return 0;
-  int halo_maxn = 128;
-  if (const char* e = getenv("HIS_GEMM_HALO_MAXN")) halo_maxn = atoi(e);
+  const int halo_maxn = halo_max_n();
   if (const char* e = getenv("HIS_GEMM_HALO")) if (atoi(e) == 0) return 0;
   if (const char* e = getenv("HIS_GEMM_FUSE_UP")) if (atoi(e) == 0) return 0;
   if ((cin % 8) || bn > halo_maxn || (H & 1) || (W & 1)) return 0;
