@@ -999,6 +999,22 @@ __global__ void guided_aux_kernel(const float* __restrict__ in, int C, int c, in
   }
 }
 
+// depth-to-space of an NHWC fp16 slice: out[n][2y+py][2x+px][c] = in[n][y][x][(py*2+px)*C + c].  ConvTranspose2d(k4, s2, p1)
+// of ProgressiveUpsamplingDecoder (..._refinement.py:152-215) is four 2x2 phase convolutions of the input; they run as ONE 3x3
+// conv with 4*C output channels (phase-major, the taps a phase does not use are zero) and this kernel interleaves the phases.
+__global__ void depth_to_space2_half_kernel(const __half* __restrict__ in, int N, int h, int w, int C, int in_cs, __half* __restrict__ out, int out_cs) {
+  const int cgs = C / 8, Ho = 2 * h, Wo = 2 * w;
+  const long long total = (long long)N * Ho * Wo * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = idx / cgs;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    const int ph = (oy & 1) * 2 + (ox & 1);
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) =
+        __ldg(reinterpret_cast<const uint4*>(in + ((long long)(n * h + (oy >> 1)) * w + (ox >> 1)) * in_cs + ph * C + cg * 8));
+  }
+}
+
 // ---- refinement flags of the refined head (hierarchical_segmentation_refinement.py)
 // PixelShuffle(2) of NCHW fp32 (SubPixelDecoder :218-252): out[n][c][2y+i][2x+j] = in[n][c*4 + i*2 + j][y][x]; the input holds
 // in_ch >= 4*C channels per image (the producing GEMM pads 12 to 16)
@@ -1514,6 +1530,16 @@ int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, i
   const long long total = (long long)N * Ho * Wo;
   if (total == 0) return HIS_OK;
   guided_aux_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, C, c, H, W, Ho, Wo, total, mask_out, fg_out, bgfg_out);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_depth_to_space2_half(const void* in, int N, int h, int w, int C, int in_cs, void* out, int out_cs, void* stream) {
+  if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "depth_to_space2: null pointer");
+  if (C % 8 || in_cs % 8 || out_cs % 8 || in_cs < 4 * C) return his_set_error(HIS_ERR_UNSUPPORTED, "depth_to_space2: channels must be multiples of 8, in_cs >= 4*C");
+  const long long total = (long long)N * 4 * h * w * (C / 8);
+  if (total == 0) return HIS_OK;
+  depth_to_space2_half_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, h, w, C, in_cs, (__half*)out, out_cs);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

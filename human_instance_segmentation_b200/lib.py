@@ -107,6 +107,7 @@ SIGNATURES = {
     "his_upsample_bgfg": [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P],
     "his_head_combine": [_P, _P, c_int, c_int, c_int, _P, _P],
     "his_map_f32": [_P, _LL, c_int, _P, _P, _P],
+    "his_depth_to_space2_half": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_pixel_shuffle2_f32": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "his_boundary_edges": [_P, c_int, c_int, c_int, _P, _P, _P],
     "his_boundary_blend": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P],

@@ -169,12 +169,11 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         self.use_attention_module = bool(use_attention_module)
         self.use_contour_detection = bool(use_contour_detection)
         self.use_distance_transform = bool(use_distance_transform)
-        if use_progressive_upsampling:
-            raise NotImplementedError("ProgressiveUpsamplingDecoder (ConvTranspose2d k4 s2 stages, disabled in every preset) is not "
-                                      "implemented on B200")
+        self.use_progressive_upsampling = bool(use_progressive_upsampling)
         self.use_boundary_refinement = bool(use_boundary_refinement)
         self.use_subpixel_conv = bool(use_subpixel_conv)
-        self.use_refinement = bool(use_contour_detection or use_distance_transform or use_boundary_refinement or use_subpixel_conv)   # rgb.py:683-689
+        self.use_refinement = bool(use_contour_detection or use_distance_transform or use_boundary_refinement or use_subpixel_conv
+                                   or use_progressive_upsampling)   # rgb.py:683-689
         self.pretrained_unet = PreTrainedPeopleSegmentationUNetWrapper(
             in_channels=3, pretrained_weights_path=pretrained_weights_path, freeze_weights=freeze_pretrained_weights,
             encoder_name=kwargs.get("encoder_name", "timm-efficientnet-b3"))
@@ -192,7 +191,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
             self.feature_combiner = nn.Conv2d(258, 256, 1)
             self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
                                                           self.use_distance_transform, base, depth, self.use_boundary_refinement,
-                                                          self.use_subpixel_conv)
+                                                          self.use_subpixel_conv, self.use_progressive_upsampling)
         else:                                  # rgb.py:715-727: the UNet-guided head takes (features, roi masks) directly
             self.segmentation_head = pt.GuidedHeadParams(256, 256, n, self.use_attention_module)
         self.hierarchical_depth = depth
@@ -309,8 +308,7 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
             raise AssertionError("Hierarchical model designed for 3 classes")           # ..._unet.py:703
         if feature_channels != 256:
             raise NotImplementedError("feature_channels != 256 is not implemented on B200 (the factory never passes it)")
-        if use_progressive_upsampling:
-            raise NotImplementedError("ProgressiveUpsamplingDecoder is not implemented on B200")
+        self.use_progressive_upsampling = bool(use_progressive_upsampling)
         self.use_boundary_refinement = bool(use_boundary_refinement)
         self.use_subpixel_conv = bool(use_subpixel_conv)
         self.roi_size = _pair(roi_size)
@@ -319,7 +317,8 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
         self.use_attention_module = bool(use_attention_module)
         self.use_contour_detection = bool(use_contour_detection)
         self.use_distance_transform = bool(use_distance_transform)
-        self.use_refinement = bool(use_contour_detection or use_distance_transform or use_boundary_refinement or use_subpixel_conv)
+        self.use_refinement = bool(use_contour_detection or use_distance_transform or use_boundary_refinement or use_subpixel_conv
+                                   or use_progressive_upsampling)
         # the reference passes no activation to any sub-module here: everything is ReLU
         self.activation_function, self.activation_beta = "relu", 1.0
         self.normalization_type = n if self.use_refinement else "layernorm2d"       # head norm (V2 head: LayerNorm2d hard-coded)
@@ -327,7 +326,8 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
         self.rgb_extractor = pt.RGBFeatureExtractorParams(n)
         if self.use_refinement:
             self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
-                                                          self.use_distance_transform, 96, 3, self.use_boundary_refinement, self.use_subpixel_conv)
+                                                          self.use_distance_transform, 96, 3, self.use_boundary_refinement, self.use_subpixel_conv,
+                                                          self.use_progressive_upsampling)
         else:
             self.segmentation_head = pt.BaseHeadParams(256, 256, "layernorm2d", self.use_attention_module, 96, 3)
         self.roi_align = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=False)      # rgb.py:404-408
@@ -622,6 +622,35 @@ class _BuiltPlan:
                        stats_out=None) -> Act:
         t = self.conv(x, rb.conv1, rb.norm1, act)
         return self.conv(t, rb.conv2, rb.norm2, act, res=x, res_mode=RES_ADD, out=out, tail=tail, aux_f32=aux_f32, stats_out=stats_out)
+
+    def conv_transpose4(self, x: Act, convt: nn.ConvTranspose2d, norm, act: int) -> Act:
+        """ConvTranspose2d(k4, s2, p1) + norm + activation (ProgressiveUpsamplingDecoder, ..._refinement.py:161-181).  Output pixel
+        (2y+py, 2x+px) sees a 2x2 input neighbourhood through the kernel taps ky = py+1-2dy, kx = px+1-2dx: the four phases run as ONE
+        3x3 tensor-core conv with 4*Cout phase-major output channels (unused taps zero), then depth-to-space interleaves them."""
+        p, L = self.plan, self.plan.lib
+        wt = convt.weight.detach().float().cpu()                 # [cin, cout, 4, 4]
+        cin, cout = wt.shape[:2]
+        conv4 = nn.Conv2d(cin, 4 * cout, 3, padding=1)
+        tap = {(0, -1): 3, (0, 0): 1, (1, 0): 2, (1, 1): 0}      # (phase, input offset) -> kernel index
+        with torch.no_grad():
+            conv4.weight.zero_()
+            for (py, dy), ky in tap.items():
+                for (px, dx), kx in tap.items():
+                    ph = py * 2 + px
+                    conv4.weight[ph * cout:(ph + 1) * cout, :, dy + 1, dx + 1] = wt[:, :, ky, kx].t()
+            conv4.bias.copy_(convt.bias.detach().float().cpu().repeat(4))
+        bn4 = None
+        if self._is_bn(norm):
+            bn4 = nn.BatchNorm2d(4 * cout, eps=norm.eps)
+            with torch.no_grad():
+                for name in ("weight", "bias", "running_mean", "running_var"):
+                    getattr(bn4, name).copy_(getattr(norm, name).detach().float().cpu().repeat(4))
+        wide = self.conv(x, conv4, bn4, act if bn4 is not None else ACT["none"])
+        out = p.act(x.N, 2 * x.H, 2 * x.W, cout)
+        p.add("depth_to_space", L.his_depth_to_space2_half, wide.ptr, x.N, x.H, x.W, cout, wide.cs, out.ptr, out.cs)
+        if bn4 is None:
+            out = self.layernorm(out, norm, act)
+        return out
 
     def _aux_fusable(self, cin: int) -> bool:
         """The epilogue export exists for BatchNorm-folded layers whose K block is 64 wide (Cin >= 52)."""
@@ -1050,7 +1079,19 @@ class _BuiltPlan:
             self.conv(x, tail, None, ACT["none"], out_f32=tn_nat)
         tn = self.to_mask_size(tn_nat)
         p.add("head_combine", L.his_head_combine, bgfg.data_ptr(), tn.data_ptr(), N, mh, mw, self.h_logits.data_ptr())
-        if head is not None and getattr(m, "use_subpixel_conv", False):
+        if head is not None and getattr(m, "use_progressive_upsampling", False):
+            # ProgressiveUpsamplingDecoder (..._refinement.py:152-215) re-decodes the shared features at 4x the ROI resolution and
+            # REPLACES the hierarchical logits (:753-756; it wins over the sub-pixel decoder)
+            st = head.progressive_decoder.stages
+            x = shared
+            for i in (0, 1):
+                x = self.conv_transpose4(x, st[i][0], st[i][1], A_ref)
+                x = self.residual_block(x, st[i][3], A_ref)
+            nat = self.h_logits if (4 * rh, 4 * rw) == (mh, mw) else p.f32(N, 3, 4 * rh, 4 * rw)
+            self.conv(x, st[2], None, ACT["none"], out_f32=nat)
+            if nat is not self.h_logits:
+                p.add("resize_bilinear", L.his_resize_bilinear_f32, nat.data_ptr(), N * 3, 4 * rh, 4 * rw, mh, mw, self.h_logits.data_ptr())
+        elif head is not None and getattr(m, "use_subpixel_conv", False):
             # SubPixelDecoder (..._refinement.py:218-252) re-decodes the shared features and REPLACES the hierarchical logits (:753-763):
             # conv3x3 256 -> 12 with the fp32 NCHW copy written by the GEMM epilogue, PixelShuffle(2), bilinear to the mask size
             sp = head.subpixel_decoder

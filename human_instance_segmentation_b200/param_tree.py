@@ -160,6 +160,17 @@ class BoundaryRefinerParams(nn.Module):
         self.blend_weight = nn.Parameter(torch.tensor(0.01))
 
 
+class ProgressiveDecoderParams(nn.Module):
+    """ProgressiveUpsamplingDecoder, ..._refinement.py:152-190."""
+
+    def __init__(self, cin: int, norm: str, num_classes: int = 3):
+        super().__init__()
+        self.stages = nn.ModuleList([
+            nn.Sequential(nn.ConvTranspose2d(cin, cin // 2, 4, stride=2, padding=1), norm_params(norm, cin // 2), Slot(), ResidualBlockParams(cin // 2, norm)),
+            nn.Sequential(nn.ConvTranspose2d(cin // 2, cin // 4, 4, stride=2, padding=1), norm_params(norm, cin // 4), Slot(), ResidualBlockParams(cin // 4, norm)),
+            nn.Conv2d(cin // 4, num_classes, 1)])
+
+
 class SubPixelDecoderParams(nn.Module):
     """SubPixelDecoder, ..._refinement.py:218-240."""
 
@@ -171,11 +182,13 @@ class SubPixelDecoderParams(nn.Module):
 class RefinedHeadParams(nn.Module):
     """RefinedHierarchicalSegmentationHead, ..._refinement.py:609-732 (module order = the reference constructor's)."""
 
-    def __init__(self, cin, mid, norm, attention, contour, distance, base, depth, boundary=False, subpixel=False):
+    def __init__(self, cin, mid, norm, attention, contour, distance, base, depth, boundary=False, subpixel=False, progressive=False):
         super().__init__()
         self.base_head = BaseHeadParams(cin, mid, norm, attention, base, depth)
         if boundary:
             self.boundary_refiner = BoundaryRefinerParams(norm)
+        if progressive:
+            self.progressive_decoder = ProgressiveDecoderParams(mid, norm)
         if subpixel:
             self.subpixel_decoder = SubPixelDecoderParams(mid)
         if contour:

@@ -165,6 +165,9 @@ int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, fl
  *   min / max over the whole tensor in minmax_ws[2] (bit patterns); his_boundary_blend: logits + blend * correction * normalised
  *   edges (:131-149), blend_weight is the device scalar parameter. */
 int his_pixel_shuffle2_f32(const float* in, int N, int C, int in_channels, int h, int w, float* out, void* stream);
+/* NHWC half depth-to-space: out[n][2y+py][2x+px][c] = in[n][y][x][(py*2+px)*C + c] -- interleaves the four phase convolutions that
+ * make up ConvTranspose2d(k4, s2, p1) of ProgressiveUpsamplingDecoder (:152-215), which run as one 3x3 conv with 4*C channels. */
+int his_depth_to_space2_half(const void* in, int N, int h, int w, int C, int in_cs, void* out, int out_cs, void* stream);
 int his_boundary_edges(const float* logits, int N, int H, int W, float* edges, unsigned int* minmax_ws, void* stream);
 int his_boundary_blend(const float* logits, const float* correction, const float* edges, const unsigned int* minmax_ws,
                        const float* blend_weight, int N, int H, int W, float* out, void* stream);

@@ -51,6 +51,7 @@ class PathConfig:
     # True -> MultiScaleRGBSegmentationModel (rgb.py:777-922)
     use_boundary_refinement: bool = False      # BoundaryRefinementModule on the final logits (..._refinement.py:58-149)
     use_subpixel_conv: bool = False            # SubPixelDecoder re-decode of the shared features (:218-252)
+    use_progressive_upsampling: bool = False   # ProgressiveUpsamplingDecoder re-decode (:152-215); wins over sub-pixel (:753-756)
     multi_scale: bool = False
     roi_sizes: tuple = (("scale1", 56), ("scale2", 42), ("scale3", 28))
     fusion_method: str = "concat"
@@ -68,6 +69,7 @@ class PathConfig:
         return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
                     use_attention_module=self.use_attention_module,
                     use_boundary_refinement=self.use_boundary_refinement, use_subpixel_conv=self.use_subpixel_conv,
+                    use_progressive_upsampling=self.use_progressive_upsampling,
                     use_contour_detection=self.use_contour_detection,
                     use_distance_transform=self.use_distance_transform,
                     normalization_type=self.normalization_type, normalization_groups=8,
@@ -373,7 +375,15 @@ def refined_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig):
     (no boundary refiner / progressive / sub-pixel decoders)."""
     logits, aux = base_head(sd, p + "base_head.", feats, cfg)
     shared = aux["shared_features"]
-    if cfg.use_subpixel_conv:         # SubPixelDecoder :218-252 replaces the hierarchical logits (:753-763)
+    if cfg.use_progressive_upsampling:    # ProgressiveUpsamplingDecoder :152-215 replaces the hierarchical logits (:753-756)
+        d = p + "progressive_decoder.stages."
+        x = shared
+        for i in (0, 1):
+            x = F.conv_transpose2d(x, sd[f"{d}{i}.0.weight"], sd[f"{d}{i}.0.bias"], stride=2, padding=1)
+            x = act_ref(norm(sd, f"{d}{i}.1.", x, cfg), cfg)
+            x = residual_block(sd, f"{d}{i}.3.", x, cfg, act_ref)
+        logits = _to_mask_size(conv(sd, d + "2.", x, 0), cfg)
+    elif cfg.use_subpixel_conv:       # SubPixelDecoder :218-252 replaces the hierarchical logits (:757-763)
         logits = _to_mask_size(F.pixel_shuffle(conv(sd, p + "subpixel_decoder.conv.", shared, 1), 2), cfg)
     if cfg.use_boundary_refinement:   # BoundaryRefinementModule :58-149
         logits = boundary_refine(sd, p + "boundary_refiner.", logits, cfg)
@@ -427,7 +437,8 @@ def guided_head(sd: SD, p: str, feats: Tensor, bg_fg_mask: Tensor, cfg: PathConf
 
 def uses_refined_head(cfg: PathConfig) -> bool:
     """rgb.py:683-689: any refinement flag selects RefinedHierarchicalSegmentationHead (+ feature_combiner)."""
-    return bool(cfg.use_contour_detection or cfg.use_distance_transform or cfg.use_boundary_refinement or cfg.use_subpixel_conv)
+    return bool(cfg.use_contour_detection or cfg.use_distance_transform or cfg.use_boundary_refinement or cfg.use_subpixel_conv
+                or cfg.use_progressive_upsampling)
 
 
 @torch.no_grad()

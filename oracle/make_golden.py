@@ -65,6 +65,11 @@ REFINE_CASES = {
     "small_b0_subpixel_boundary_ln": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28), use_boundary_refinement=True,
                                               use_subpixel_conv=True, use_contour_detection=False, use_distance_transform=False,
                                               normalization_type="layernorm2d", use_attention_module=False), (96, 128)),
+    "small_b0_progressive": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), use_progressive_upsampling=True,
+                                     use_contour_detection=False, use_distance_transform=False), (96, 128)),
+    "small_b0_progressive_ln_silu": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28), use_progressive_upsampling=True,
+                                             use_boundary_refinement=True, normalization_type="layernorm2d", activation_function="silu",
+                                             use_attention_module=False), (96, 128)),
 }
 
 # a1 multi_scale=True -> MultiScaleRGBSegmentationModel (rgb.py:777-922): default fusion/normalisation, and batchnorm + SiLU +

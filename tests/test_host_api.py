@@ -41,7 +41,8 @@ def test_refinement_flag_state_dict_matches_reference(name):
     want = common.golden_keys()[name]
     got = {k: list(v.shape) for k, v in model.state_dict().items()}
     assert got == want and list(got) == list(want)
-    assert float(model.segmentation_head.boundary_refiner.blend_weight.detach()) == pytest.approx(0.01)
+    if cfg.use_boundary_refinement:
+        assert float(model.segmentation_head.boundary_refiner.blend_weight.detach()) == pytest.approx(0.01)
 
 
 @pytest.mark.parametrize("name", list(common.MULTISCALE_CASES))
@@ -93,8 +94,6 @@ def test_factory_errors_match_reference_behaviour():
         his.create_rgb_hierarchical_model(**{**kw, "activation_function": "tanh"})
     with pytest.raises(ValueError):     # normalization_comparison.py:206
         his.create_rgb_hierarchical_model(**{**kw, "normalization_type": "nonsense"})
-    with pytest.raises(NotImplementedError):       # sub-pixel / progressive decoders are not part of any preset
-        his.create_rgb_hierarchical_model(**{**kw, "use_progressive_upsampling": True})
 
 
 def test_no_cpu_fallback():
