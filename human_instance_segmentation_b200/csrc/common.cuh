@@ -28,6 +28,14 @@ int his_set_error(int code, const char* msg);
 
 __device__ __forceinline__ float his_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// One MUFU each, no range fix-up code around them (`__expf` / `__fdividef` add an FSETP and two predicated FMULs per value for
+// denormal results): 1/(1+2^(nb2*x)) with nb2 = -beta*log2(e).  Flush-to-zero is exact enough here: 2^t < 2^-126 -> s = 1,
+// 2^t = inf -> s = 0, and x*s of a finite x stays finite.
+__device__ __forceinline__ float his_ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float his_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float his_sigmoid_fast(float x, float nb2) { return his_rcp_approx(1.0f + his_ex2_approx(nb2 * x)); }
+#define HIS_NEG_LOG2E (-1.4426950408889634f)
+
 __device__ __forceinline__ float his_act(float v, int act, float beta) {
   switch (act) {
     case HIS_ACT_RELU: return fmaxf(v, 0.0f);

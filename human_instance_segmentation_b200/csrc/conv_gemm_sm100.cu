@@ -105,7 +105,7 @@ struct ConvGemmParams {
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
   //   SIGMOID: s = 1/(1+exp(-act_beta*y)); y = act_mul_x ? y*s : s   (sigmoid / silu / swish(beta))
   //   GELU:    exact erf form
-  float act_lo, act_beta;
+  float act_lo, act_beta, act_nb2;
   int act_mul_x;
   const float* shift;   // [cout_slab]  (conv bias + folded-BatchNorm shift; the BN scale lives in the weights)
   // fused 1x1 tail to <= 2 channels (TAIL kernels): tail[o] = sum_c y[c]*tail_w[o][c] + tail_b[o], NCHW fp32 out
@@ -255,7 +255,7 @@ template <int ACTC>
 __device__ __forceinline__ float epi_act(float y, const ConvGemmParams& p) {
   if (ACTC == ACTC_CLAMP) return fmaxf(y, p.act_lo);
   if (ACTC == ACTC_SIGMOID) {
-    const float s = __fdividef(1.0f, 1.0f + __expf(-p.act_beta * y));
+    const float s = his_sigmoid_fast(y, p.act_nb2);       // act_nb2 = -act_beta * log2(e)
     return p.act_mul_x ? y * s : s;
   }
   return 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
@@ -942,6 +942,7 @@ int his_conv_gemm_create(void** out_plan,
     case HIS_ACT_GELU: actc = ACTC_GELU; break;
     default: delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown activation code");
   }
+  p.act_nb2 = p.act_beta * HIS_NEG_LOG2E;
   if (res_mode < 0 || res_mode > 2) { delete pl; return his_set_error(HIS_ERR_INVALID_ARG, "unknown res_mode"); }
   pl->kernel = pick_kernel(bk, actc, res_mode, halo);
   pl->smem = smem_for(bk);

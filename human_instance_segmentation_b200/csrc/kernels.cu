@@ -276,6 +276,69 @@ __global__ void small_cout_conv_kernel(const DirectConvParams p) {
   }
 }
 
+// 3x3 stride-1 pad-1 conv to ONE output channel (the smp segmentation head 16->1 at full image resolution).  A warp walks down a
+// 30-column strip: lane L owns input column x0-1+L and loads every input pixel exactly once (32 lanes x 32 B = one contiguous
+// 1 KB row segment); per loaded row it adds that pixel's dot products with the nine taps into the three output rows the row
+// touches, and a finished output row is assembled from the neighbours' partial sums with two shuffles:
+//   out[y][x] = sum_ky ( x[y+ky-1][x-1].w[ky][0] + x[y+ky-1][x].w[ky][1] + x[y+ky-1][x+1].w[ky][2] ).
+// fp32 weights as broadcast reads from shared memory, fp32 NCHW output (coalesced over the lanes).
+constexpr int kHeadStripCols = 30, kHeadStripRows = 32;
+template <int CIN>
+__global__ void __launch_bounds__(kThreads) head3x3_c1_kernel(const DirectConvParams p) {
+  __shared__ __align__(16) float s_w[9 * CIN];
+  for (int i = threadIdx.x; i < 9 * CIN; i += blockDim.x) s_w[i] = __half2float(p.w[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int ncol = (p.W + kHeadStripCols - 1) / kHeadStripCols, nstrip = (p.H + kHeadStripRows - 1) / kHeadStripRows;
+  const long long total = (long long)p.N * nstrip * ncol;
+  const float sc = __ldg(p.scale), sh = __ldg(p.shift);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long item = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); item < total; item += nwarps) {
+    const int cgp = (int)(item % ncol), strip = (int)((item / ncol) % nstrip), n = (int)(item / ((long long)ncol * nstrip));
+    const int x = cgp * kHeadStripCols - 1 + lane;
+    const bool xin_ok = x >= 0 && x < p.W;
+    const int y0 = strip * kHeadStripRows, y1 = min(y0 + kHeadStripRows, p.H);
+    float P[3], Q[3] = {0.0f, 0.0f, 0.0f}, R[3] = {0.0f, 0.0f, 0.0f};    // partial sums of output rows r+1, r, r-1
+    for (int r = y0 - 1; r <= y1; ++r) {
+      float xin[CIN];
+      if (xin_ok && r >= 0 && r < p.H) {
+        const __half* px = (const __half*)p.in + ((long long)(n * p.H + r) * p.W + x) * p.in_cs;
+#pragma unroll
+        for (int c8 = 0; c8 < CIN; c8 += 8) {
+          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(px + c8));
+          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); xin[c8 + 2 * e] = f.x; xin[c8 + 2 * e + 1] = f.y; }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) xin[c] = 0.0f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+        for (int c4 = 0; c4 < CIN; c4 += 4) {
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w + (0 * 3 + kx) * CIN + c4);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_w + (1 * 3 + kx) * CIN + c4);
+          const float4 w2 = *reinterpret_cast<const float4*>(s_w + (2 * 3 + kx) * CIN + c4);
+          a0 = fmaf(xin[c4], w0.x, a0); a0 = fmaf(xin[c4 + 1], w0.y, a0); a0 = fmaf(xin[c4 + 2], w0.z, a0); a0 = fmaf(xin[c4 + 3], w0.w, a0);
+          a1 = fmaf(xin[c4], w1.x, a1); a1 = fmaf(xin[c4 + 1], w1.y, a1); a1 = fmaf(xin[c4 + 2], w1.z, a1); a1 = fmaf(xin[c4 + 3], w1.w, a1);
+          a2 = fmaf(xin[c4], w2.x, a2); a2 = fmaf(xin[c4 + 1], w2.y, a2); a2 = fmaf(xin[c4 + 2], w2.z, a2); a2 = fmaf(xin[c4 + 3], w2.w, a2);
+        }
+        P[kx] = a0; Q[kx] += a1; R[kx] += a2;        // input row r is tap ky = 0 / 1 / 2 of output rows r+1 / r / r-1
+      }
+      // output row r-1 is complete: the kx = 0 term comes from the left neighbour's column, the kx = 2 term from the right one
+      const float left = __shfl_up_sync(0xffffffffu, R[0], 1), right = __shfl_down_sync(0xffffffffu, R[2], 1);
+      const int o = r - 1;
+      if (o >= y0 && lane >= 1 && lane <= kHeadStripCols && xin_ok)
+        p.out_f[((long long)n * p.H + o) * p.W + x] = his_act((left + R[1] + right) * sc + sh, p.act, p.act_beta);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) { R[kx] = Q[kx]; Q[kx] = P[kx]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ depthwise conv
 // NHWC fp16, 8 channels (16 B) per thread, fused BN scale/shift + activation, optional per-(n,c)
 // sums for the squeeze-excite pooling that follows (fp32 atomics, one per thread per channel after
@@ -293,8 +356,8 @@ struct DwParams {
 template <int ACT>
 __device__ __forceinline__ float act_ct(float v) {
   if (ACT == HIS_ACT_RELU) return fmaxf(v, 0.0f);
-  if (ACT == HIS_ACT_SILU) return v * __fdividef(1.0f, 1.0f + __expf(-v));
-  if (ACT == HIS_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+  if (ACT == HIS_ACT_SILU) return v * his_sigmoid_fast(v, HIS_NEG_LOG2E);
+  if (ACT == HIS_ACT_SIGMOID) return his_sigmoid_fast(v, HIS_NEG_LOG2E);
   return v;
 }
 
@@ -535,14 +598,20 @@ __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, in
   const int n = blockIdx.y, cgs = C / 8;
   const long long per_img = (long long)HW * cgs;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(idx % cgs);
-    const long long pix = idx / cgs;
-    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
+  const long long step = (long long)gridDim.x * blockDim.x;
+  const __half* img = in + (long long)n * HW * cs;
+  auto addr = [&](long long i) { return reinterpret_cast<const uint4*>(img + (i / cgs) * cs + (int)(i % cgs) * 8); };
+  auto add = [&](const uint4& xv) {
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+  };
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; idx + 3 * step < per_img; idx += 4 * step) {      // four loads in flight; the per-thread summation order is unchanged
+    const uint4 v0 = __ldg(addr(idx)), v1 = __ldg(addr(idx + step)), v2 = __ldg(addr(idx + 2 * step)), v3 = __ldg(addr(idx + 3 * step));
+    add(v0); add(v1); add(v2); add(v3);
   }
+  for (; idx < per_img; idx += step) add(__ldg(addr(idx)));
 #pragma unroll
   for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = acc[e];
   __syncthreads();
@@ -1216,6 +1285,12 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
       (size_t)kh * kw * cin * cout * sizeof(float) <= 48 * 1024) {
     const long long total = (long long)N * p.Ho * p.Wo;
     const size_t sm = (size_t)kh * kw * cin * cout * sizeof(float);
+    if (cout == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && cin == 16) {
+      const long long warps = (long long)N * ((H + kHeadStripRows - 1) / kHeadStripRows) * ((W + kHeadStripCols - 1) / kHeadStripCols);
+      head3x3_c1_kernel<16><<<grid_for(warps * 32), kThreads, 0, ST>>>(p);
+      HIS_CHECK_LAUNCH();
+      return HIS_OK;
+    }
     if (cout == 1) small_cout_conv_kernel<1><<<grid_for(total), kThreads, sm, ST>>>(p);
     else if (cout == 3) small_cout_conv_kernel<3><<<grid_for(total), kThreads, sm, ST>>>(p);
     else small_cout_conv_kernel<2><<<grid_for(total), kThreads, sm, ST>>>(p);

@@ -1114,9 +1114,23 @@ class _BuiltPlan:
         if head is None or aux_level == "none":
             return          # contour / distance branches only feed aux outputs: dead code when none is returned (the exported ONNX
                             # graph, whose outputs are the masks alone, prunes them the same way)
+        merged = None
+        if m.use_contour_detection and m.use_distance_transform and self._is_bn_mode():
+            # both aux branches open with a 3x3 conv + BatchNorm + activation of the shared features (256->64 and 256->128): one
+            # N = 192 GEMM reads `shared` once and runs in the tensor-bound per-tap mode instead of two narrow layers
+            c0, d0 = head.contour_branch.contour_branch, head.distance_decoder.distance_head
+            both = nn.Conv2d(256, 192, 3, padding=1)
+            bn = nn.BatchNorm2d(192, eps=c0[1].eps)
+            with torch.no_grad():
+                both.weight.copy_(torch.cat([c0[0].weight.detach().float().cpu(), d0[0].weight.detach().float().cpu()]))
+                both.bias.copy_(torch.cat([c0[0].bias.detach().float().cpu(), d0[0].bias.detach().float().cpu()]))
+                for name in ("weight", "bias", "running_mean", "running_var"):
+                    getattr(bn, name).copy_(torch.cat([getattr(c0[1], name).detach().float().cpu(), getattr(d0[1], name).detach().float().cpu()]))
+            if c0[1].eps == d0[1].eps:
+                merged = self.conv(shared, both, bn, A_ref)
         if m.use_contour_detection:
             cb = head.contour_branch.contour_branch
-            c = self.conv(shared, cb[0], cb[1], A_ref)
+            c = merged.slice(0, 64) if merged is not None else self.conv(shared, cb[0], cb[1], A_ref)
             c_low = p.f32(N, 1, rh, rw)
             if self._tail_ok(A_ref):
                 self.conv(c, cb[3], cb[4], A_ref, tail=(cb[6], True, c_low))
@@ -1129,7 +1143,7 @@ class _BuiltPlan:
         if m.use_distance_transform:
             dd = head.distance_decoder
             dh = dd.distance_head
-            d = self.conv(shared, dh[0], dh[1], A_ref)
+            d = merged.slice(64, 128) if merged is not None else self.conv(shared, dh[0], dh[1], A_ref)
             d_low = p.f32(N, 1, rh, rw)
             if self._tail_ok(A_ref):
                 self.residual_block(d, dh[3], A_ref, tail=(dh[4], False, d_low))

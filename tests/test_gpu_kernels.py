@@ -83,7 +83,20 @@ def test_direct_conv_variants_match_torch():
     tail = p.f32(n, 2, 9, 11)
     p.conv_direct(x, 0, n, 9, 11, 128, x.cs, p.const(engine.pack_direct_weight(w2), torch.float16), p.const(torch.ones(2)), p.const(torch.tensor([0.1, -0.2])),
                   2, 1, 1, 0, 0, out_f32=tail)
+    # (c) 3x3 16 -> 1 segmentation head (four output pixels per thread), widths that are / are not multiples of four, input slice
+    heads = []
+    for hw in ((13, 24), (7, 10), (5, 3)):
+        xb = p.act(n, hw[0], hw[1], 24); xb.buf.copy_(torch.randn(n, hw[0], hw[1], 24, generator=g).half())
+        xs = xb.slice(8, 16)
+        w3 = torch.randn(1, 16, 3, 3, generator=g) * 0.1
+        o3 = p.f32(n, 1, hw[0], hw[1])
+        p.conv_direct(xs, 0, n, hw[0], hw[1], 16, xs.cs, p.const(engine.pack_direct_weight(w3), torch.float16), p.const(torch.tensor([1.5])),
+                      p.const(torch.tensor([-0.3])), 1, 3, 1, 1, 3, out_f32=o3)
+        heads.append((xs, w3, o3))
     p.replay(); torch.cuda.synchronize()
+    for xs, w3, o3 in heads:
+        ref3 = torch.sigmoid(F.conv2d(xs.torch_nchw().cpu(), w3.half().float(), None, 1, 1) * 1.5 - 0.3)
+        assert (o3.cpu() - ref3).abs().max() <= 1e-5
     xin = img * aff[:3].view(1, 3, 1, 1) + aff[3:].view(1, 3, 1, 1)
     ref = F.silu(F.conv2d(xin, wt.half().float(), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     assert (out.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * float(ref.abs().max())

@@ -36,7 +36,7 @@ SHAPES = [
 ]
 
 
-def bench(shape, reps):
+def bench(shape, reps, act=1):
     label, n, h, w, cin, cout, k, res_mode, transposed = shape
     dev = torch.device("cuda")
     plan = engine.Plan(dev)
@@ -53,7 +53,7 @@ def bench(shape, reps):
     if res_mode != RES_NONE:
         res = plan.act(n, oh, ow, cout)
         res.buf.normal_()
-    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(torch.zeros(slab)), out, k, 1, 1.0, res,
+    plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(torch.zeros(slab)), out, k, act, 1.0, res,
                    res_mode, transposed)
     for _ in range(2):
         plan.replay()
@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--stages", default="0")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--act", type=int, default=1, help="0 none, 1 relu, 2 silu, 3 sigmoid")
     args = ap.parse_args()
     sweeps = [int(v) for v in args.stages.split(",")]
     for shape in SHAPES:
@@ -85,7 +86,7 @@ def main():
                 os.environ["HIS_GEMM_STAGES"] = str(st)
             else:
                 os.environ.pop("HIS_GEMM_STAGES", None)
-            ms, tf, gbs = bench(shape, args.reps)
+            ms, tf, gbs = bench(shape, args.reps, args.act)
             cells.append(f"st{st}: {ms:7.3f} ms {tf:7.1f} TF {gbs:6.0f} GB/s")
         print(f"{shape[0]:38s} " + " | ".join(cells), flush=True)
 
