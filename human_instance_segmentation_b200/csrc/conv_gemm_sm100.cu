@@ -100,6 +100,7 @@ struct ConvGemmParams {
   // halo mode, fused nearest 2x upsample (smp UnetDecoderBlock: F.interpolate(x, nearest) then cat with the skip): channels
   // [0, up_split) are gathered from the low-resolution tensor `up_in` [n, H/2, W/2, up_cs] at (y>>1, x>>1), the rest from `in`
   const __half* up_in; long long up_sn; int up_cs, up_split;
+  int pair;             // 1: CTA pairs (cluster of 2) run cta_group::2 MMAs, M = 256 pixels x block_n, each CTA stages half of the weight tile
   int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
@@ -161,6 +162,40 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: TMA loads of both CTAs complete on the LEADER's barrier, the leader's MMA thread issues one
+// M = 256 instruction that reads A (own 128 rows) and half of B from each CTA's shared memory and accumulates into each CTA's TMEM;
+// its commit arrives on the same-offset barrier of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -203,13 +238,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 }
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n.
-__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, int m = kBlockM) {
   uint32_t d = 0;
   d |= 1u << 4;                       // c_format = F32
   d |= 0u << 7;                       // a_format = F16
   d |= 0u << 10;                      // b_format = F16
   d |= (uint32_t)(n >> 3) << 17;      // n_dim
-  d |= (uint32_t)(kBlockM >> 4) << 24;  // m_dim
+  d |= (uint32_t)(m >> 4) << 24;        // m_dim (256 = CTA pair)
   return d;
 }
 
@@ -283,7 +318,7 @@ __device__ __forceinline__ WorkItem decode_work(const ConvGemmParams& p, int w) 
 // ------------------------------------------------------------------------------------ kernel
 enum { EPI_PLAIN = 0, EPI_TAIL = 1, EPI_AUX = 2 };
 
-template <int BK, int ACTC, int RES, int EPI, bool HALO>
+template <int BK, int ACTC, int RES, int EPI, bool HALO, bool PAIR = false>
 __global__ void __launch_bounds__(kThreadsGemm, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
@@ -314,7 +349,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.ksize * p.ksize;
   const int kiters = taps * p.kblocks_per_tap;
-  const uint32_t b_bytes = (uint32_t)p.block_n * BK * 2;
+  // PAIR kernels hold cta_group::2 instructions and can only be launched as clusters of two CTAs
+  constexpr bool pair = PAIR && !HALO;
+  const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
+  // bytes of the weight tile this CTA stages (a pair member holds half of the N rows)
+  const uint32_t b_bytes = (uint32_t)(pair ? p.block_n >> 1 : p.block_n) * BK * 2;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO0);
@@ -322,15 +361,20 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 8; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 8; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
     for (int a = 0; a < 4; ++a) mbar_init(res_bar(a), 1);
     if (HALO)
       for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kAProducerThreads); mbar_init(aempty_bar(s), 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (pair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   // single N tile: the per-channel shift stays in shared memory for the whole kernel
   float* s_shift = reinterpret_cast<float*>(smem_gen + (shift_base - smem_base));
@@ -338,6 +382,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = threadIdx.x; i < p.block_n; i += kThreadsGemm) s_shift[i] = __ldg(p.shift + i);
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();        // the peer's barriers are initialised and its TMEM is allocated before anything remote happens
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -514,9 +559,17 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (elect_one()) {
           const uint32_t sa = stage_base + stage * p.stage_bytes, sb = sa + Cfg::kABytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kABytes + b_bytes);
-          tma_load_4d(sa, &tmA, full_bar(stage), cb * BK, it.x0 + dx, it.y0 + dy, it.img);
-          tma_load_2d(sb, &tmB, full_bar(stage), cb * BK, brow);
+          if (pair) {
+            // both CTAs' boxes complete on the leader's barrier; the leader expects the bytes of both
+            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * (Cfg::kABytes + b_bytes));
+            tma_load_4d_2sm(sa, &tmA, lead_full, cb * BK, it.x0 + dx, it.y0 + dy, it.img);
+            tma_load_2d_2sm(sb, &tmB, lead_full, cb * BK, brow + (int)cta_rank * (p.block_n >> 1));
+          } else {
+            mbar_expect_tx(full_bar(stage), Cfg::kABytes + b_bytes);
+            tma_load_4d(sa, &tmA, full_bar(stage), cb * BK, it.x0 + dx, it.y0 + dy, it.img);
+            tma_load_2d(sb, &tmB, full_bar(stage), cb * BK, brow);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -525,10 +578,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (!HALO && warp == 1) {
     // ================================ MMA issuer (whole warp converged, one elected lane issues) ================================
-    const uint32_t idesc = make_idesc_f16(p.block_n);
+    const uint32_t idesc = make_idesc_f16(p.block_n, pair ? 2 * kBlockM : kBlockM);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+    // pair: the leader issues for both CTAs (its work items and the peer's advance in lock step); the peer's MMA warp idles
+    for (int w = blockIdx.x; w < p.num_work && cta_rank == 0; w += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
@@ -538,11 +592,19 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (elect_one()) {
           const uint32_t sa = stage_base + stage * p.stage_bytes, sb = sa + Cfg::kABytes;
           const uint64_t adesc = make_kmajor_desc<BK>(sa), bdesc = make_kmajor_desc<BK>(sb);
+          if (pair) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)
-            umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-          umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
-          if (k == kiters - 1) umma_commit(tfull_bar(acc));
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_f16_2sm(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+            umma_commit_2sm(empty_bar(stage));   // same-offset barriers of both CTAs
+            if (k == kiters - 1) umma_commit_2sm(tfull_bar(acc));
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+            umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
+            if (k == kiters - 1) umma_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -628,7 +690,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (j == nchunks - 1) {                  // accumulator fully read -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (pair) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));   // the leader's MMA thread waits for both CTAs
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         if (RES && !direct && !res_glob) { mbar_wait(res_bar(2 * g + b), (res_phase >> b) & 1u); res_phase ^= 1u << b; }
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
@@ -723,9 +788,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();        // no CTA leaves (or frees TMEM) while its peer can still signal it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -767,6 +834,24 @@ ConvGemmKernel pick_aux_h(int actc, int res) {
   return actc == 0 ? pick_aux_res<0, HALO>(res) : actc == 1 ? pick_aux_res<1, HALO>(res) : pick_aux_res<2, HALO>(res);
 }
 ConvGemmKernel pick_aux_kernel(int actc, int res, bool halo) { return halo ? pick_aux_h<true>(actc, res) : pick_aux_h<false>(actc, res); }
+// CTA-pair variants (BK = 64, per-tap TMA mode): launched as clusters of two
+template <int ACTC>
+ConvGemmKernel pick_pair_res(int res) {
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_PLAIN, false, true> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_PLAIN, false, true>
+                                                                                       : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_PLAIN, false, true>;
+}
+ConvGemmKernel pick_pair_kernel(int actc, int res) { return actc == 0 ? pick_pair_res<0>(res) : actc == 1 ? pick_pair_res<1>(res) : pick_pair_res<2>(res); }
+ConvGemmKernel pick_pair_tail_kernel(int res) {
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, EPI_TAIL, false, true> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, EPI_TAIL, false, true>;
+}
+template <int ACTC>
+ConvGemmKernel pick_pair_aux_res(int res) {
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_AUX, false, true> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_AUX, false, true>
+                                                                                     : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_AUX, false, true>;
+}
+ConvGemmKernel pick_pair_aux_kernel(int actc, int res) {
+  return actc == 0 ? pick_pair_aux_res<0>(res) : actc == 1 ? pick_pair_aux_res<1>(res) : pick_pair_aux_res<2>(res);
+}
 int smem_for(int bk) { return bk == 64 ? KCfg<64>::kSmemBytes : bk == 32 ? KCfg<32>::kSmemBytes : KCfg<16>::kSmemBytes; }
 
 // ------------------------------------------------------------------------------------ host side
@@ -832,7 +917,7 @@ int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, i
 struct ConvGemmPlan {
   CUtensorMap tmA, tmB, tmO[4], tmR;
   ConvGemmParams p;
-  int grid, bk, smem, actc, res_mode, transposed, cin_pad, halo;
+  int grid, bk, smem, actc, res_mode, transposed, cin_pad, halo, b_box_rows, pair_grid_checked;
   ConvGemmKernel kernel;
 };
 
@@ -901,6 +986,12 @@ int his_conv_gemm_create(void** out_plan,
           if (cudaFuncSetAttribute(pick_aux_kernel(a, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess)
             return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     }
+    for (int a = 0; a < 3; ++a)
+      for (int r = 0; r < 3; ++r)
+        if (cudaFuncSetAttribute(pick_pair_kernel(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess ||
+            cudaFuncSetAttribute(pick_pair_aux_kernel(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess ||
+            (r < 2 && cudaFuncSetAttribute(pick_pair_tail_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess))
+          return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     g_num_sms = prop.multiProcessorCount;
   }
   ConvGemmPlan* pl = new ConvGemmPlan();
@@ -991,7 +1082,14 @@ int his_conv_gemm_create(void** out_plan,
       if (a2 >= 2) { p.b_resident = 1; p.stages = 1; p.stage_bytes = res_bytes; p.a_stages = a2; p.taps_per_b = 9; }
     }
   } else {
-    p.stage_bytes = (kBlockM * bk * 2 + p.block_n * bk * 2 + 1023) / 1024 * 1024;
+    // CTA pairs (cta_group::2): two adjacent pixel tiles of one image share the weight tile, each CTA stages half of it -> half
+    // the shared-memory operand traffic per MMA for B and half the weight L2 traffic.  Needs a single N tile (adjacent work
+    // items = adjacent pixel tiles), an even number of tiles per image and block_n a multiple of 32.
+    int pair_min_n = 128;
+    if (const char* e = getenv("HIS_GEMM_PAIR")) pair_min_n = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    p.pair = (!transposed && p.n_tiles == 1 && bk == 64 && p.block_n >= pair_min_n && (p.block_n % 32) == 0 &&
+              ((p.tiles_x * p.tiles_y) % 2) == 0 && p.num_work >= 2) ? 1 : 0;
+    p.stage_bytes = (kBlockM * bk * 2 + (p.pair ? p.block_n / 2 : p.block_n) * bk * 2 + 1023) / 1024 * 1024;
     p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
@@ -1002,7 +1100,8 @@ int his_conv_gemm_create(void** out_plan,
   int taps = ksize * ksize;
   int rc;
   if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, bk, p.bw, p.bh))) { delete pl; return rc; }
-  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, (halo ? p.taps_per_box : 1) * p.block_n, bk))) { delete pl; return rc; }
+  pl->b_box_rows = halo ? p.taps_per_box * p.block_n : p.pair ? p.block_n / 2 : p.block_n;
+  if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, pl->b_box_rows, bk))) { delete pl; return rc; }
   if (!transposed) {
     if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, kChunkC, p.bw, p.bh))) { delete pl; return rc; }
     pl->tmO[1] = pl->tmO[2] = pl->tmO[3] = pl->tmO[0];
@@ -1019,6 +1118,7 @@ int his_conv_gemm_create(void** out_plan,
     pl->tmR = pl->tmO[0];
   }
   pl->grid = p.num_work < g_num_sms ? p.num_work : g_num_sms;
+  if (p.pair) { pl->grid &= ~1; pl->kernel = pick_pair_kernel(actc, res_mode); }
   *out_plan = pl;
   return HIS_OK;
 }
@@ -1032,7 +1132,7 @@ int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_tail: needs a single N tile, none/relu activation, no MUL operand, not transposed");
   pl->p.tail_w = tail_w; pl->p.tail_b0 = tail_b0; pl->p.tail_b1 = tail_b1; pl->p.tail_c = tail_c; pl->p.tail_sigmoid = tail_sigmoid;
   pl->p.tail_out = tail_out; pl->p.store_main = store_main;
-  pl->kernel = pick_tail_kernel(pl->bk, pl->res_mode, pl->halo);
+  pl->kernel = pl->p.pair ? pick_pair_tail_kernel(pl->res_mode) : pick_tail_kernel(pl->bk, pl->res_mode, pl->halo);
   return HIS_OK;
 }
 
@@ -1043,7 +1143,7 @@ int his_conv_gemm_set_image_weights(void* plan, const void* w_packed_per_image) 
   if (pl->halo && p.b_resident) return his_set_error(HIS_ERR_UNSUPPORTED, "set_image_weights: not for weight-resident halo layers");
   const long long rows = (long long)p.groups * p.ksize * p.ksize * p.cout_slab;
   if (rows * p.n_img >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "set_image_weights: too many weight rows");
-  int rc = encode_weight_map(&pl->tmB, w_packed_per_image, pl->cin_pad, rows * p.n_img, (pl->halo ? p.taps_per_box : 1) * p.block_n, pl->bk);
+  int rc = encode_weight_map(&pl->tmB, w_packed_per_image, pl->cin_pad, rows * p.n_img, pl->b_box_rows, pl->bk);
   if (rc) return rc;
   p.b_img_rows = (int)rows;
   return HIS_OK;
@@ -1093,7 +1193,7 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   if (pl->bk != 64 || pl->transposed || pl->p.tail_c)
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_aux: needs a 64-wide K block (Cin >= 64), not transposed, no fused tail");
   pl->p.aux_out = aux_out;
-  pl->kernel = pick_aux_kernel(pl->actc, pl->res_mode, pl->halo);
+  pl->kernel = pl->p.pair ? pick_pair_aux_kernel(pl->actc, pl->res_mode) : pick_aux_kernel(pl->actc, pl->res_mode, pl->halo);
   return HIS_OK;
 }
 
@@ -1101,6 +1201,25 @@ int his_conv_gemm_run(void* plan, void* stream) {
   if (!plan) return his_set_error(HIS_ERR_INVALID_ARG, "null plan");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
   if (pl->p.num_work == 0) return HIS_OK;
+  if (pl->p.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kThreadsGemm); cfg.dynamicSmemBytes = pl->smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    if (!pl->pair_grid_checked) {      // persistent kernel: never more clusters than can be co-resident (a TPC with one SM hosts none)
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, pl->kernel, &cfg) == cudaSuccess && ncl > 0 && 2 * ncl < pl->grid) pl->grid = 2 * ncl;
+      (void)cudaGetLastError();
+      cfg.gridDim = dim3(pl->grid);
+      pl->pair_grid_checked = 1;
+    }
+    if (cudaLaunchKernelEx(&cfg, pl->kernel, pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR, pl->p) != cudaSuccess)
+      return his_set_error(HIS_ERR_LAUNCH, cudaGetErrorString(cudaGetLastError()));
+    return HIS_OK;
+  }
   pl->kernel<<<pl->grid, kThreadsGemm, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
                                                                pl->p);
   HIS_CHECK_LAUNCH();

@@ -1,5 +1,12 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_conv_gemm.py -x -q > gpurun_out/s24_t1.log 2>&1; echo "rc=$?" >> gpurun_out/s24_t1.log; tail -2 gpurun_out/s24_t1.log
-HIS_GEMM_DIRECT=3 timeout 300 python -m pytest tests/test_gpu_conv_gemm.py -x -q > gpurun_out/s24_t3.log 2>&1; echo "rc=$?" >> gpurun_out/s24_t3.log; tail -2 gpurun_out/s24_t3.log
-for d in 1 3; do echo "=== DIRECT=$d"; HIS_GEMM_DIRECT=$d python bench.py --steps 3 --warmup 3 --breakdown --no-cpu-baseline --workload b1 2> gpurun_out/s24_b1_d$d.err | cut -c1-150; grep -E "cin256 cout256 k3" gpurun_out/s24_b1_d$d.err | head -3; done
+cd /root/repo
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+echo "--- pair on (default)"
+timeout 120 python tools/bench_gemm.py --only "head 1" 2>&1 | tail -4
+timeout 120 python tools/bench_gemm.py --only "head 256->" 2>&1 | tail -5
+echo "--- pair off"
+HIS_GEMM_PAIR=0 timeout 120 python tools/bench_gemm.py --only "head 1" 2>&1 | tail -4
+HIS_GEMM_PAIR=0 timeout 120 python tools/bench_gemm.py --only "head 256->" 2>&1 | tail -5
+timeout 280 python bench.py --steps 5 --warmup 3 --breakdown --top 30 --no-cpu-baseline > gpurun_out/b0_pair.log 2>&1
+tail -1 gpurun_out/b0_pair.log | cut -c1-300
+HIS_GEMM_PAIR=0 timeout 280 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-300
