@@ -196,6 +196,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_acc_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -263,6 +269,19 @@ __device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t adesc, ui
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool P>
+__device__ __forceinline__ void umma_x(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (P) umma_f16_2sm(tmem_d, adesc, bdesc, idesc, accumulate); else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+template <bool P>
+__device__ __forceinline__ void umma_acc_x(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if (P) umma_f16_acc_2sm(tmem_d, adesc, bdesc, idesc); else umma_f16_acc(tmem_d, adesc, bdesc, idesc);
+}
+template <bool P>
+__device__ __forceinline__ void umma_commit_x(uint32_t bar) {
+  if (P) umma_commit_2sm(bar); else umma_commit(bar);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
@@ -342,6 +361,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 20);
   auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + s); };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + p.a_stages + s); };
+  auto apeer_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + 2 * p.a_stages + s); };   // pair: the peer's window is complete
   const int n_acc = p.n_acc;
   const uint32_t a_base = bar_base + kBarrierBytes;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to the aligned base
@@ -350,7 +370,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int taps = p.ksize * p.ksize;
   const int kiters = taps * p.kblocks_per_tap;
   // PAIR kernels hold cta_group::2 instructions and can only be launched as clusters of two CTAs
-  constexpr bool pair = PAIR && !HALO;
+  constexpr bool pair = PAIR;
   const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
   // bytes of the weight tile this CTA stages (a pair member holds half of the N rows)
   const uint32_t b_bytes = (uint32_t)(pair ? p.block_n >> 1 : p.block_n) * BK * 2;
@@ -364,7 +384,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int a = 0; a < 8; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
     for (int a = 0; a < 4; ++a) mbar_init(res_bar(a), 1);
     if (HALO)
-      for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kAProducerThreads); mbar_init(aempty_bar(s), 1); }
+      for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kAProducerThreads); mbar_init(aempty_bar(s), 1); mbar_init(apeer_bar(s), 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -408,7 +428,16 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int cb = 0; cb < nblk; ++cb)
           for (int tg = 0; tg < tgroups; ++tg) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            if (elect_one()) {
+            if (pair) {
+              if (elect_one()) {       // both CTAs stage their half of every tap's weight rows; completion on the leader's barrier
+                const uint32_t sb = stage_base + stage * p.stage_bytes;
+                const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_tx);
+                for (int t = 0; t < p.taps_per_b; ++t)
+                  tma_load_2d_2sm(sb + (uint32_t)t * b_bytes, &tmB, lead_full, cb * BK,
+                                  brow0 + (tg * p.taps_per_b + t) * p.cout_slab + (int)cta_rank * (p.block_n >> 1));
+              }
+            } else if (elect_one()) {
               const uint32_t sb = stage_base + stage * p.stage_bytes;
               if (p.debug & 4) mbar_arrive(full_bar(stage));
               else {
@@ -426,8 +455,20 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // ================================ halo mode: MMA issuer ================================
       // One thread feeds the tensor pipe, so the loop is kept short: descriptors are a constant high word plus a 14-bit
       // address that advances by adds, the K=16 steps of a block are unrolled, and a B stage carries up to nine taps.
-      const uint32_t idesc = make_idesc_f16(p.block_n);
+      const uint32_t idesc = make_idesc_f16(p.block_n, pair ? 2 * kBlockM : kBlockM);
       const uint64_t adesc_hi = make_halo_desc(0), bdesc_hi = make_kmajor_desc<BK>(0);
+      if (pair && cta_rank != 0) {
+        // peer of a pair: this warp only relays "my window of stage s is complete" to the leader's MMA thread
+        int astage = 0; uint32_t aphase = 0;
+        for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
+          for (int cb = 0; cb < nblk; ++cb) {
+            mbar_wait(afull_bar(astage), aphase);
+            fence_proxy_async();
+            if (elect_one()) mbar_arrive_cluster(mapa_shared(apeer_bar(astage), 0));
+            __syncwarp();
+            if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+          }
+      }
       const int T = p.taps_per_b, cin = p.cin, a_stages = p.a_stages;
       const uint32_t b_tap_units = b_bytes >> 4, b_stage_units = (uint32_t)p.stage_bytes >> 4, a_stage_units = (uint32_t)p.a_stage_bytes >> 4;
       const uint32_t a_units0 = a_base >> 4, b_units0 = stage_base >> 4;
@@ -435,12 +476,13 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int acc = 0; uint32_t acc_phase = 0;
       uint32_t a_units = a_units0, b_units = b_units0;
       if (p.b_resident) { mbar_wait(full_bar(0), 0); tc_fence_after(); }      // weights: loaded once, never released
-      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+      for (int w = blockIdx.x; w < p.num_work && cta_rank == 0; w += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         for (int cb = 0; cb < nblk; ++cb) {
           mbar_wait(afull_bar(astage), aphase);
+          if (pair) mbar_wait(apeer_bar(astage), aphase);
           fence_proxy_async();                 // cp.async (generic proxy) writes -> tcgen05 (async proxy) reads
           tc_fence_after();
           const int nk16 = min(BK / 16, (cin - cb * BK + 15) >> 4);
@@ -455,16 +497,16 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
                   for (int t = 0; t < 9; ++t) {
                     const uint64_t ad = ad0 + (uint64_t)((t / 3) * kHaloW + (t % 3)), bd = bd0 + (uint64_t)t * b_tap_units;
-                    if (t == 0) umma_f16(d_tmem, ad, bd, idesc, cb ? 1u : 0u);
-                    else umma_f16_acc(d_tmem, ad, bd, idesc);
+                    if (t == 0) umma_x<pair>(d_tmem, ad, bd, idesc, cb ? 1u : 0u);
+                    else umma_acc_x<pair>(d_tmem, ad, bd, idesc);
 #pragma unroll
                     for (int kk = 1; kk < BK / 16; ++kk)
-                      if (kk < nk16) umma_f16_acc(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
+                      if (kk < nk16) umma_acc_x<pair>(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
                   }
                 }
-                if (!p.b_resident) umma_commit(empty_bar(stage));
-                umma_commit(aempty_bar(astage));
-                if (cb == nblk - 1) umma_commit(tfull_bar(acc));
+                if (!p.b_resident) umma_commit_x<pair>(empty_bar(stage));
+                umma_commit_x<pair>(aempty_bar(astage));
+                if (cb == nblk - 1) umma_commit_x<pair>(tfull_bar(acc));
               }
             } else if (elect_one()) {
               const int tap0 = tg * T;
@@ -474,18 +516,18 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               for (int t = 0; t < T; ++t) {
                 const uint64_t ad = adesc_hi | au, bd = bdesc_hi | bu;
                 if (!(p.debug & 8)) {
-                  umma_f16(d_tmem, ad, bd, idesc, (cb | tg | t) ? 1u : 0u);
+                  umma_x<pair>(d_tmem, ad, bd, idesc, (cb | tg | t) ? 1u : 0u);
 #pragma unroll
                   for (int kk = 1; kk < BK / 16; ++kk)
-                    if (kk < nk16) umma_f16_acc(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
+                    if (kk < nk16) umma_acc_x<pair>(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
                 }
                 bu += b_tap_units; ++au;
                 if (++dx == 3) { dx = 0; au += kHaloW - 3; }
               }
-              if (!p.b_resident) umma_commit(empty_bar(stage));
+              if (!p.b_resident) umma_commit_x<pair>(empty_bar(stage));
               if (tg == tgroups - 1) {
-                umma_commit(aempty_bar(astage));
-                if (cb == nblk - 1) umma_commit(tfull_bar(acc));
+                umma_commit_x<pair>(aempty_bar(astage));
+                if (cb == nblk - 1) umma_commit_x<pair>(tfull_bar(acc));
               }
             }
             __syncwarp();
@@ -834,24 +876,31 @@ ConvGemmKernel pick_aux_h(int actc, int res) {
   return actc == 0 ? pick_aux_res<0, HALO>(res) : actc == 1 ? pick_aux_res<1, HALO>(res) : pick_aux_res<2, HALO>(res);
 }
 ConvGemmKernel pick_aux_kernel(int actc, int res, bool halo) { return halo ? pick_aux_h<true>(actc, res) : pick_aux_h<false>(actc, res); }
-// CTA-pair variants (BK = 64, per-tap TMA mode): launched as clusters of two
-template <int ACTC>
+// CTA-pair variants (BK = 64; per-tap TMA mode or halo mode): launched as clusters of two
+template <int ACTC, bool HALO>
 ConvGemmKernel pick_pair_res(int res) {
-  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_PLAIN, false, true> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_PLAIN, false, true>
-                                                                                       : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_PLAIN, false, true>;
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_PLAIN, HALO, true> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_PLAIN, HALO, true>
+                                                                                      : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_PLAIN, HALO, true>;
 }
-ConvGemmKernel pick_pair_kernel(int actc, int res) { return actc == 0 ? pick_pair_res<0>(res) : actc == 1 ? pick_pair_res<1>(res) : pick_pair_res<2>(res); }
-ConvGemmKernel pick_pair_tail_kernel(int res) {
+template <bool HALO>
+ConvGemmKernel pick_pair_h(int actc, int res) {
+  return actc == 0 ? pick_pair_res<0, HALO>(res) : actc == 1 ? pick_pair_res<1, HALO>(res) : pick_pair_res<2, HALO>(res);
+}
+ConvGemmKernel pick_pair_kernel(int actc, int res, bool halo) { return halo ? pick_pair_h<true>(actc, res) : pick_pair_h<false>(actc, res); }
+ConvGemmKernel pick_pair_tail_kernel(int res, bool halo) {
+  if (halo) return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, EPI_TAIL, true, true> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, EPI_TAIL, true, true>;
   return res == 0 ? conv_gemm_sm100_kernel<64, ACTC_CLAMP, 0, EPI_TAIL, false, true> : conv_gemm_sm100_kernel<64, ACTC_CLAMP, 1, EPI_TAIL, false, true>;
 }
-template <int ACTC>
+template <int ACTC, bool HALO>
 ConvGemmKernel pick_pair_aux_res(int res) {
-  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_AUX, false, true> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_AUX, false, true>
-                                                                                     : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_AUX, false, true>;
+  return res == 0 ? conv_gemm_sm100_kernel<64, ACTC, 0, EPI_AUX, HALO, true> : res == 1 ? conv_gemm_sm100_kernel<64, ACTC, 1, EPI_AUX, HALO, true>
+                                                                                    : conv_gemm_sm100_kernel<64, ACTC, 2, EPI_AUX, HALO, true>;
 }
-ConvGemmKernel pick_pair_aux_kernel(int actc, int res) {
-  return actc == 0 ? pick_pair_aux_res<0>(res) : actc == 1 ? pick_pair_aux_res<1>(res) : pick_pair_aux_res<2>(res);
+template <bool HALO>
+ConvGemmKernel pick_pair_aux_h(int actc, int res) {
+  return actc == 0 ? pick_pair_aux_res<0, HALO>(res) : actc == 1 ? pick_pair_aux_res<1, HALO>(res) : pick_pair_aux_res<2, HALO>(res);
 }
+ConvGemmKernel pick_pair_aux_kernel(int actc, int res, bool halo) { return halo ? pick_pair_aux_h<true>(actc, res) : pick_pair_aux_h<false>(actc, res); }
 int smem_for(int bk) { return bk == 64 ? KCfg<64>::kSmemBytes : bk == 32 ? KCfg<32>::kSmemBytes : KCfg<16>::kSmemBytes; }
 
 // ------------------------------------------------------------------------------------ host side
@@ -986,12 +1035,13 @@ int his_conv_gemm_create(void** out_plan,
           if (cudaFuncSetAttribute(pick_aux_kernel(a, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess)
             return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     }
-    for (int a = 0; a < 3; ++a)
-      for (int r = 0; r < 3; ++r)
-        if (cudaFuncSetAttribute(pick_pair_kernel(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess ||
-            cudaFuncSetAttribute(pick_pair_aux_kernel(a, r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess ||
-            (r < 2 && cudaFuncSetAttribute(pick_pair_tail_kernel(r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess))
-          return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
+    for (int h = 0; h < 2; ++h)
+      for (int a = 0; a < 3; ++a)
+        for (int r = 0; r < 3; ++r)
+          if (cudaFuncSetAttribute(pick_pair_kernel(a, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess ||
+              cudaFuncSetAttribute(pick_pair_aux_kernel(a, r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess ||
+              (r < 2 && cudaFuncSetAttribute(pick_pair_tail_kernel(r, h), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(64)) != cudaSuccess))
+            return his_set_error(HIS_ERR_LAUNCH, "cannot raise dynamic shared memory limit");
     g_num_sms = prop.multiProcessorCount;
   }
   ConvGemmPlan* pl = new ConvGemmPlan();
@@ -1004,7 +1054,16 @@ int his_conv_gemm_create(void** out_plan,
   his_conv_gemm_tile_n(cout, &tn_tiles, &tblock_n);
   int halo = ksize == 3 && !transposed && (cin % 8) == 0;
   if (const char* e = getenv("HIS_GEMM_HALO")) halo = halo && atoi(e) != 0;
-  halo = halo && tblock_n <= halo_max_n();
+  // wide single-N-tile layers run as CTA pairs (cta_group::2) in the per-tap TMA mode; with HIS_GEMM_PAIR_HALO=n those with
+  // Cout >= n use the halo window as well (A read once instead of nine times through L2, each CTA streaming half of every tap's
+  // weight tile).  Measured equal or slightly slower (128->128 @128x96: 0.985 vs 0.979 ms, 256->256: 1.565 vs 1.519 ms): with the
+  // weight traffic halved the pair is no longer L2 bound, so the default keeps the simpler per-tap pair.
+  int pair_halo_min_n = 1 << 30;
+  if (const char* e = getenv("HIS_GEMM_PAIR_HALO")) pair_halo_min_n = atoi(e) > 0 ? atoi(e) : (1 << 30);
+  if (const char* e = getenv("HIS_GEMM_PAIR")) if (atoi(e) <= 0) pair_halo_min_n = 1 << 30;
+  const bool pair_halo = halo && tn_tiles == 1 && cin > 32 && tblock_n >= pair_halo_min_n && (tblock_n % 32) == 0 &&
+                         ((his_div_up(W, kHaloBw) * his_div_up(H, kHaloBh)) % 2) == 0 && n_img * his_div_up(W, kHaloBw) * his_div_up(H, kHaloBh) >= 2;
+  halo = halo && (tblock_n <= halo_max_n() || pair_halo);
   pl->halo = halo;
   // pick the 128-pixel rectangle with the least padded area
   long long best = -1;
@@ -1056,14 +1115,16 @@ int his_conv_gemm_create(void** out_plan,
   if (halo) {
     // B ring stage = taps_per_b weight tiles (block_n x BK); A ring stage = BK/8 planes of the 10 x 18 window
     // every barrier round trip of a B stage costs the issuing thread ~300 ns, so a stage carries as many taps as 48 KB hold
-    const int tap_bytes = p.block_n * bk * 2;
+    p.pair = pair_halo ? 1 : 0;
+    const int tap_bytes = (p.pair ? p.block_n / 2 : p.block_n) * bk * 2;      // the weight rows THIS CTA stages per tap
     p.taps_per_b = 9 * tap_bytes <= 48 * 1024 ? 9 : 3 * tap_bytes <= 48 * 1024 ? 3 : 1;
     if (const char* e = getenv("HIS_GEMM_TAPS")) { int v = atoi(e); if (v == 1 || v == 3 || v == 9) p.taps_per_b = v; }
     p.taps_per_box = (p.n_tiles == 1 && p.taps_per_b * p.block_n <= 256) ? p.taps_per_b : 1;
+    if (p.pair) p.taps_per_box = 1;      // a CTA's half of a tap's rows is not contiguous with the next tap's
     p.stage_bytes = (p.taps_per_b * tap_bytes + 1023) / 1024 * 1024;
     p.a_stage_bytes = (bk / 8) * kPlaneBytes;
     const int budget = KCfg<64>::kRingBytes;
-    int a_st = p.a_stage_bytes >= 16 * 1024 ? 2 : (budget / 3) / p.a_stage_bytes;
+    int a_st = p.a_stage_bytes >= 16 * 1024 ? (p.pair ? 3 : 2) : (budget / 3) / p.a_stage_bytes;
     if (a_st > kMaxAStages) a_st = kMaxAStages;
     if (a_st < 2) a_st = 2;
     if (const char* e = getenv("HIS_GEMM_ASTAGES")) { int v = atoi(e); if (v >= 1 && v <= kMaxAStages) a_st = v; }
@@ -1074,7 +1135,7 @@ int his_conv_gemm_create(void** out_plan,
     // weight-resident mode: the whole [K block][tap] weight set fits next to a deep halo ring -> loaded once per CTA
     p.b_resident = 0;
     const int res_bytes = (p.kblocks_per_tap * 9 * p.block_n * bk * 2 + 1023) / 1024 * 1024;
-    int want_res = p.n_tiles == 1 && res_bytes <= 96 * 1024;
+    int want_res = p.n_tiles == 1 && res_bytes <= 96 * 1024 && !p.pair;
     if (const char* e = getenv("HIS_GEMM_BRES")) want_res = want_res && atoi(e) != 0;
     if (want_res) {
       int a2 = (budget - res_bytes) / p.a_stage_bytes;
@@ -1087,7 +1148,8 @@ int his_conv_gemm_create(void** out_plan,
     // items = adjacent pixel tiles), an even number of tiles per image and block_n a multiple of 32.
     int pair_min_n = 128;
     if (const char* e = getenv("HIS_GEMM_PAIR")) pair_min_n = atoi(e) > 0 ? atoi(e) : (1 << 30);
-    p.pair = (!transposed && p.n_tiles == 1 && bk == 64 && p.block_n >= pair_min_n && (p.block_n % 32) == 0 &&
+    // (1x1 layers are HBM / L2 bound, the pair's lock step only costs there: measured 0.50 -> 0.55 ms on 256->256 k1)
+    p.pair = (!transposed && ksize == 3 && p.n_tiles == 1 && bk == 64 && p.block_n >= pair_min_n && (p.block_n % 32) == 0 &&
               ((p.tiles_x * p.tiles_y) % 2) == 0 && p.num_work >= 2) ? 1 : 0;
     p.stage_bytes = (kBlockM * bk * 2 + (p.pair ? p.block_n / 2 : p.block_n) * bk * 2 + 1023) / 1024 * 1024;
     p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
@@ -1100,7 +1162,7 @@ int his_conv_gemm_create(void** out_plan,
   int taps = ksize * ksize;
   int rc;
   if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, bk, p.bw, p.bh))) { delete pl; return rc; }
-  pl->b_box_rows = halo ? p.taps_per_box * p.block_n : p.pair ? p.block_n / 2 : p.block_n;
+  pl->b_box_rows = p.pair ? p.block_n / 2 : halo ? p.taps_per_box * p.block_n : p.block_n;
   if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, pl->b_box_rows, bk))) { delete pl; return rc; }
   if (!transposed) {
     if ((rc = encode_act_map(&pl->tmO[0], out, cout, W, H, n_img, out_cs, (long long)W * out_cs, (long long)H * W * out_cs, kChunkC, p.bw, p.bh))) { delete pl; return rc; }
@@ -1118,7 +1180,7 @@ int his_conv_gemm_create(void** out_plan,
     pl->tmR = pl->tmO[0];
   }
   pl->grid = p.num_work < g_num_sms ? p.num_work : g_num_sms;
-  if (p.pair) { pl->grid &= ~1; pl->kernel = pick_pair_kernel(actc, res_mode); }
+  if (p.pair) { pl->grid &= ~1; pl->kernel = pick_pair_kernel(actc, res_mode, halo); }
   *out_plan = pl;
   return HIS_OK;
 }
@@ -1132,7 +1194,7 @@ int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_tail: needs a single N tile, none/relu activation, no MUL operand, not transposed");
   pl->p.tail_w = tail_w; pl->p.tail_b0 = tail_b0; pl->p.tail_b1 = tail_b1; pl->p.tail_c = tail_c; pl->p.tail_sigmoid = tail_sigmoid;
   pl->p.tail_out = tail_out; pl->p.store_main = store_main;
-  pl->kernel = pl->p.pair ? pick_pair_tail_kernel(pl->res_mode) : pick_tail_kernel(pl->bk, pl->res_mode, pl->halo);
+  pl->kernel = pl->p.pair ? pick_pair_tail_kernel(pl->res_mode, pl->halo) : pick_tail_kernel(pl->bk, pl->res_mode, pl->halo);
   return HIS_OK;
 }
 
@@ -1193,7 +1255,7 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   if (pl->bk != 64 || pl->transposed || pl->p.tail_c)
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_aux: needs a 64-wide K block (Cin >= 64), not transposed, no fused tail");
   pl->p.aux_out = aux_out;
-  pl->kernel = pl->p.pair ? pick_pair_aux_kernel(pl->actc, pl->res_mode) : pick_aux_kernel(pl->actc, pl->res_mode, pl->halo);
+  pl->kernel = pl->p.pair ? pick_pair_aux_kernel(pl->actc, pl->res_mode, pl->halo) : pick_aux_kernel(pl->actc, pl->res_mode, pl->halo);
   return HIS_OK;
 }
 

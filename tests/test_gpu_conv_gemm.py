@@ -110,6 +110,18 @@ def test_conv_gemm_matches_torch_fp32(case):
     assert err <= 2e-3 * max(ref, 1.0), (err, ref)   # fp16 output rounding: 2^-11 relative
 
 
+@pytest.mark.parametrize("case", [dict(n=3, h=64, w=48, cin=128, cout=128, k=3, res_mode=RES_ADD),
+                                  dict(n=2, h=30, w=40, cin=200, cout=256, k=3, act=2),
+                                  dict(n=1, h=16, w=12, cin=64, cout=160, k=3)],
+                         ids=["n128-res", "n256-silu-clipped", "n160-small"])
+def test_cta_pair_halo_variant_matches_torch_fp32(case, monkeypatch):
+    """HIS_GEMM_PAIR_HALO: the cta_group::2 kernels fed by the halo window (off by default, kept as a tuning variant); the per-tap
+    pair kernels are what CASES with Cout >= 128 and an even tile count run through by default."""
+    monkeypatch.setenv("HIS_GEMM_PAIR_HALO", "128")
+    err, ref = run_case(**case)
+    assert err <= 2e-3 * max(ref, 1.0), (err, ref)
+
+
 def test_fused_nearest_upsample_concat_matches_torch():
     """his_conv_gemm_set_upsampled_input: channels [0, low_c) gathered from the half-resolution tensor at (y>>1, x>>1), the rest
     from the concat buffer == F.interpolate(nearest) + cat + conv3x3 (smp UnetDecoderBlock)."""

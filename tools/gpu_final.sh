@@ -17,4 +17,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 python tools/prof_set.py > gpurun_out/r1f_prof_set_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"depthwise|conv_gemm|mask_cleanup" -c 16 -o gpurun_out/r1f_prof_set python tools/prof_set.py > gpurun_out/r1f_prof_set_ncu.log 2>&1
 tail -2 gpurun_out/r1f_prof_set_ncu.log
+# the report itself can exceed what gpurun copies back (64 MiB for the whole directory): keep its raw page as CSV, drop the file when large
+ncu -i gpurun_out/r1f_prof_set.ncu-rep --page raw --csv > gpurun_out/r1f_prof_set_raw.csv 2> /dev/null
+if [ $(stat -c %s gpurun_out/r1f_prof_set.ncu-rep) -gt 40000000 ]; then rm -f gpurun_out/r1f_prof_set.ncu-rep; fi
 ls -la gpurun_out/r1f_*
