@@ -790,6 +790,100 @@ __global__ void ln_apply_kernel(const __half* __restrict__ in, int HW, int C, in
   }
 }
 
+// ------------------------------------------------------------------------------------ GroupNorm family
+// nn.GroupNorm / nn.InstanceNorm2d(affine) / AdaptiveInstanceNorm2d / SpatialGroupNorm of get_normalization_layer
+// (hed/advanced/normalization_comparison.py:12-74,159-206): statistics per (sample, group of C/G channels) over (C/G, H, W), biased
+// variance, affine [C].  Three launches, fixed summation order (bit-reproducible):
+//   1. per-channel partial (sum, sum of squares) of a pixel range: thread = (8-channel vector, pixel lane), fp32 per thread,
+//      pixel lanes merged in order through shared memory            -> ws[n][part][c][2]
+//   2. per (n, group): parts and channels summed in double          -> ws[n][parts][c] = (mean, rstd) of the channel's group
+//   3. normalise + affine (+ residual) + activation, 16-byte vectors
+constexpr int kGnMaxC = 2048;
+__global__ void gn_stats_kernel(const __half* __restrict__ in, int HW, int C, int cs, int pix_per_part, int nslots, float* __restrict__ ws) {
+  extern __shared__ float s_gn[];                       // [pixel lanes][C][2]
+  const int n = blockIdx.y, part = blockIdx.x, cgs = C / 8;
+  const int PL = blockDim.x / cgs;                      // pixel lanes (>= 1: C <= 2048)
+  const int cg = threadIdx.x % cgs, pl = threadIdx.x / cgs;
+  const int p0 = part * pix_per_part, p1 = min(p0 + pix_per_part, HW);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sum[e] = 0.0f; sq[e] = 0.0f; }
+  if (pl < PL) {
+    for (int pix = p0 + pl; pix < p1; pix += PL) {
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(xh[e]);
+        sum[2 * e] += f.x; sum[2 * e + 1] += f.y;
+        sq[2 * e] = fmaf(f.x, f.x, sq[2 * e]); sq[2 * e + 1] = fmaf(f.y, f.y, sq[2 * e + 1]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s_gn[((size_t)pl * C + cg * 8 + e) * 2] = sum[e]; s_gn[((size_t)pl * C + cg * 8 + e) * 2 + 1] = sq[e]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.0f, b = 0.0f;
+    for (int l = 0; l < PL; ++l) { a += s_gn[((size_t)l * C + c) * 2]; b += s_gn[((size_t)l * C + c) * 2 + 1]; }
+    float* dst = ws + (((long long)n * nslots + part) * C + c) * 2;
+    dst[0] = a; dst[1] = b;
+  }
+}
+
+__global__ void gn_finalize_kernel(float* __restrict__ ws, int HW, int C, int G, int nparts, float eps) {
+  const int n = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int gs = C / G;
+  double s = 0.0, q = 0.0;
+  for (int part = 0; part < nparts; ++part) {
+    const float* src = ws + (((long long)n * (nparts + 1) + part) * C + g * gs) * 2;
+    for (int c = 0; c < gs; ++c) { s += (double)src[2 * c]; q += (double)src[2 * c + 1]; }
+  }
+  const double cnt = (double)HW * (double)gs;
+  const double mu = s / cnt;
+  double var = q / cnt - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float muf = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  float* dst = ws + (((long long)n * (nparts + 1) + nparts) * C + g * gs) * 2;
+  for (int c = 0; c < gs; ++c) { dst[2 * c] = muf; dst[2 * c + 1] = rstd; }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ in, int HW, int C, int cs, const float* __restrict__ ws, int nparts,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int act, float act_beta,
+                                int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs) {
+  extern __shared__ float s_ab[];                       // per channel: y = x*a + b with a = rstd*gamma, b = beta - mean*a
+  const int n = blockIdx.y, cgs = C / 8;
+  const float* st = ws + ((long long)n * (nparts + 1) + nparts) * C * 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = st[2 * c + 1] * __ldg(gamma + c);
+    s_ab[2 * c] = a; s_ab[2 * c + 1] = __ldg(beta + c) - st[2 * c] * a;
+  }
+  __syncthreads();
+  const long long per_img_vec = (long long)HW * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = (long long)n * HW + idx / cgs;
+    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * cs + cg * 8));
+    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (res_mode) rv = __ldg(reinterpret_cast<const uint4*>(res + pix * res_cs + cg * 8));
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(xh[e]), r = __half22float2(rh[e]);
+      const int c = cg * 8 + 2 * e;
+      float y0 = fmaf(f.x, s_ab[2 * c], s_ab[2 * c + 1]);
+      float y1 = fmaf(f.y, s_ab[2 * c + 2], s_ab[2 * c + 3]);
+      if (res_mode == HIS_RES_ADD) { y0 += r.x; y1 += r.y; }
+      y0 = his_act(y0, act, act_beta); y1 = his_act(y1, act, act_beta);
+      if (res_mode == HIS_RES_MUL) { y0 *= r.x; y1 *= r.y; }
+      xh[e] = __floats2half2_rn(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+  }
+}
+
 // ConvTranspose2d(k2,s2) for tiny Cin (upsample_bg_fg.0 in LayerNorm mode: 2 -> 32): NCHW fp32 in, NHWC fp16 out (+bias)
 __global__ void convT2x2_small_kernel(const float* __restrict__ in, int N, int Cin, int h, int w, const float* __restrict__ wt,
                                       const float* __restrict__ bias, int Cout, __half* __restrict__ out, int out_cs) {
@@ -1474,6 +1568,42 @@ int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const f
   dim3 g2((int)(gx < 1 ? 1 : gx), N);
   ln_apply_kernel<<<g2, kThreads, 0, ST>>>((const __half*)in, HW, C, in_cs, partials_ws, parts, gamma, beta, eps, act, act_beta, res_mode,
                                           (const __half*)res, res_cs, (__half*)out, out_cs);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_groupnorm_parts(int N, int HW, int C) {
+  long long parts = (HW + 255) / 256;                       // >= 256 pixels per block
+  const long long cap = (148LL * 8 + N - 1) / (N > 0 ? N : 1);
+  if (parts > cap) parts = cap;
+  return (int)(parts < 1 ? 1 : parts);
+}
+
+int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int groups, const float* gamma, const float* beta, float eps, int act,
+                      float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, void* stream) {
+  if (!in || !gamma || !beta || !ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "groupnorm: null pointer");
+  if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "groupnorm: res_mode without residual");
+  if (C % 8 || in_cs % 8 || out_cs % 8 || (res_mode && res_cs % 8)) return his_set_error(HIS_ERR_UNSUPPORTED, "groupnorm: channels must be multiples of 8");
+  if (groups < 1 || C % groups) return his_set_error(HIS_ERR_INVALID_ARG, "groupnorm: channels must be divisible by the group count");
+  if (C > kGnMaxC) return his_set_error(HIS_ERR_UNSUPPORTED, "groupnorm: more than 2048 channels");
+  if (N == 0) return HIS_OK;
+  const int parts = his_groupnorm_parts(N, HW, C);
+  const int ppp = (HW + parts - 1) / parts;
+  const int cgs = C / 8, PL = kThreads / cgs;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_done = true;
+  }
+  const size_t sm1 = (size_t)PL * C * 2 * sizeof(float);      // <= 256/cgs * 8*cgs * 8 B = 16 KB
+  gn_stats_kernel<<<dim3(parts, N), kThreads, sm1, ST>>>((const __half*)in, HW, C, in_cs, ppp, parts + 1, ws);
+  gn_finalize_kernel<<<dim3((groups + 127) / 128, N), 128, 0, ST>>>(ws, HW, C, groups, parts, eps);
+  const long long per_img_vec = (long long)HW * cgs;
+  long long gx = (per_img_vec + kThreads - 1) / kThreads;
+  const long long cap = (148LL * 16 + N - 1) / N;
+  if (gx > cap) gx = cap;
+  gn_apply_kernel<<<dim3((int)(gx < 1 ? 1 : gx), N), kThreads, (size_t)C * 2 * sizeof(float), ST>>>(
+      (const __half*)in, HW, C, in_cs, ws, parts, gamma, beta, act, act_beta, res_mode, (const __half*)res, res_cs, (__half*)out, out_cs);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

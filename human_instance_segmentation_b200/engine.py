@@ -111,7 +111,8 @@ class Plan:
             self.tensor_flops += f
 
     # kernels launched per op (cudaMemsetAsync is not one of ours)
-    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0, "se_gate": 3, "boundary_edges": 3}
+    KERNELS_PER_OP = {"spatial_attention": 2, "input_affine": 3, "memset": 0, "se_gate": 3, "boundary_edges": 3, "layernorm2d": 2,
+                      "groupnorm": 3}
 
     def add(self, name: str, fn, *args, flops: int = 0, desc: str = ""):
         self.ops.append((name, fn, args))
@@ -247,6 +248,7 @@ class Plan:
 def fold_bn(conv_bias: Optional[torch.Tensor], bn, cout: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """y = conv(x)*scale + shift  ==  BN_eval(conv(x) + bias)   (BatchNorm2d eps from the module)."""
     bias = conv_bias.detach().float().cpu() if conv_bias is not None else torch.zeros(cout)
+    bn = getattr(bn, "batch_norm", bn)          # MixedNormalization in eval mode is its BatchNorm2d
     if bn is None:
         return torch.ones(cout), bias
     g, b = bn.weight.detach().float().cpu(), bn.bias.detach().float().cpu()

@@ -97,6 +97,8 @@ SIGNATURES = {
     "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
     "his_layernorm2d_parts": [c_int, c_int, c_int],
     "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],
+    "his_groupnorm_parts": [c_int, c_int, c_int],
+    "his_groupnorm_act": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],
     "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P],
     "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P],
     "his_spatial_gate": [_P, c_int, c_int, c_int, _P, c_int, _P, _P],

@@ -181,7 +181,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         object.__setattr__(self.pretrained_unet, "_owner", weakref.ref(self))
         self.roi_align_mask = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=True)
         self.roi_align_rgb = DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=True)
-        n = normalization_type
+        n = pt.norm_spec(normalization_type, normalization_groups)
         self.rgb_feature_extractor = nn.Sequential(
             nn.Conv2d(3, 64, 3, padding=1), pt.norm_params(n, 64), pt.Slot(), pt.ResidualBlockParams(64, n),
             nn.Conv2d(64, 128, 3, padding=1), pt.norm_params(n, 128), pt.Slot(), pt.ResidualBlockParams(128, n),
@@ -323,6 +323,7 @@ class HierarchicalRGBSegmentationModel(_PlannedModel):
         self.activation_function, self.activation_beta = "relu", 1.0
         self.normalization_type = n if self.use_refinement else "layernorm2d"       # head norm (V2 head: LayerNorm2d hard-coded)
         self.extractor_normalization_type = n
+        n = pt.norm_spec(n, kwargs.get("normalization_groups", 8))
         self.rgb_extractor = pt.RGBFeatureExtractorParams(n)
         if self.use_refinement:
             self.segmentation_head = pt.RefinedHeadParams(256, 256, n, self.use_attention_module, self.use_contour_detection,
@@ -359,12 +360,13 @@ class MultiScaleRGBSegmentationModel(_PlannedModel):
         self.normalization_type = "layernorm2d"       # the V2 head hard-codes LayerNorm2d
         self.use_attention_module = bool(use_attention_module)
         self.use_contour_detection = self.use_distance_transform = self.use_refinement = False
-        self.rgb_extractors = nn.ModuleDict({s_: pt.RGBFeatureExtractorParams(normalization_type) for s_ in self.scales})
+        nspec = pt.norm_spec(normalization_type, normalization_groups)
+        self.rgb_extractors = nn.ModuleDict({s_: pt.RGBFeatureExtractorParams(nspec) for s_ in self.scales})
         self.roi_aligns = nn.ModuleDict({s_: DynamicRoIAlign(spatial_scale=640.0, sampling_ratio=2, aligned=False) for s_ in self.scales})
         if fusion_method == "adaptive":
             self.fusion_weights = nn.Parameter(torch.ones(len(roi_sizes)))
         fused = 256 * len(roi_sizes) if fusion_method == "concat" else 256
-        self.fusion_proj = pt.FusionProjParams(fused, 256, normalization_type)
+        self.fusion_proj = pt.FusionProjParams(fused, 256, nspec)
         self.segmentation_head = pt.BaseHeadParams(256, 256, "layernorm2d", self.use_attention_module, 96, 3)
         self._init_exec_state()
 
@@ -546,7 +548,8 @@ class _BuiltPlan:
 
     # -------------------------------------------------------------- helpers
     def _is_bn(self, norm) -> bool:
-        return isinstance(norm, nn.BatchNorm2d)
+        """BatchNorm2d, or MixedNormalization whose eval forward is its batch_norm alone (normalization_comparison.py:143-147)."""
+        return isinstance(norm, (nn.BatchNorm2d, pt.MixedNormParams))
 
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
@@ -557,9 +560,11 @@ class _BuiltPlan:
         epilogue; the wide activation itself is then not written (its only consumer is the tail).
         aux_f32: fp32 NCHW copy of the output from the epilogue; in_gate: see Plan.conv_gemm (GEMM shapes only)."""
         p = self.plan
+        if isinstance(norm, pt.MixedNormParams):
+            norm = norm.batch_norm
         if norm is not None and not self._is_bn(norm):
-            # LayerNorm2d (hed/model.py:18-38): per-sample statistics over (C,H,W) cannot fold into the conv ->
-            # conv(+bias) to fp16, then the two-launch LayerNorm kernel applies norm + residual + activation.
+            # LayerNorm2d (hed/model.py:18-38) and the group / instance family: per-sample statistics cannot fold into the conv ->
+            # conv(+bias) to fp16, then the statistics + normalise kernels apply norm + residual + activation.
             assert tail is None and out_f32 is None and aux_f32 is None and stats_out is None
             raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate, row_scale=row_scale)
             return self.layernorm(raw, norm, act, res, res_mode, out)
@@ -605,11 +610,23 @@ class _BuiltPlan:
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
 
-    def layernorm(self, x: Act, norm: pt.LayerNorm2dParams, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
+    def layernorm(self, x: Act, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
                   out: Optional[Act] = None) -> Act:
+        """Per-sample statistic norms: LayerNorm2d (one group over C,H,W) or GroupNorm / SpatialGroupNorm (G groups) + affine
+        (+ residual) + activation."""
         p, L = self.plan, self.plan.lib
         if out is None:
             out = p.act(x.N, x.H, x.W, x.C)
+        gn = pt.group_norm_args(norm)
+        if gn is not None:
+            groups, gamma, beta, eps = gn
+            parts = L.his_groupnorm_parts(x.N, x.H * x.W, x.C)
+            ws = torch.empty((x.N, parts + 1, x.C, 2), dtype=torch.float32, device=self.dev)
+            p.keep.append(ws)
+            p.add("groupnorm", L.his_groupnorm_act, x.ptr, x.N, x.H * x.W, x.C, x.cs, int(groups), p.const(gamma.reshape(-1)).data_ptr(),
+                  p.const(beta.reshape(-1)).data_ptr(), float(eps), act, self.beta, res_mode, res.ptr if res is not None else None,
+                  res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs)
+            return out
         parts = L.his_layernorm2d_parts(x.N, x.H * x.W, x.C)
         ws = torch.empty((x.N, parts, 2), dtype=torch.float64, device=self.dev)
         p.keep.append(ws)
@@ -628,6 +645,7 @@ class _BuiltPlan:
         (2y+py, 2x+px) sees a 2x2 input neighbourhood through the kernel taps ky = py+1-2dy, kx = px+1-2dx: the four phases run as ONE
         3x3 tensor-core conv with 4*Cout phase-major output channels (unused taps zero), then depth-to-space interleaves them."""
         p, L = self.plan, self.plan.lib
+        norm = getattr(norm, "batch_norm", norm)                 # MixedNormalization: eval = its BatchNorm
         wt = convt.weight.detach().float().cpu()                 # [cin, cout, 4, 4]
         cin, cout = wt.shape[:2]
         conv4 = nn.Conv2d(cin, 4 * cout, 3, padding=1)
@@ -913,7 +931,7 @@ class _BuiltPlan:
         for mod in features:
             if isinstance(mod, nn.Conv2d):
                 conv = mod
-            elif isinstance(mod, (nn.BatchNorm2d, pt.LayerNorm2dParams)):
+            elif isinstance(mod, pt.NORM_MODULES):
                 x = self.conv(x, conv, mod, act_stage)
             elif isinstance(mod, pt.ResidualBlockParams):
                 x = self.residual_block(x, mod, act_rb)

@@ -133,6 +133,12 @@ int his_layernorm2d_parts(int N, int HW, int C);
 int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps,
                         int act, float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws,
                         void* out, int out_cs, void* stream);
+/* nn.GroupNorm / nn.InstanceNorm2d(affine=True) / AdaptiveInstanceNorm2d / SpatialGroupNorm of get_normalization_layer
+ * (hed/advanced/normalization_comparison.py:12-74,159-206) + residual + activation on an NHWC half slice: statistics per
+ * (sample, group of C/groups channels) over (C/groups, H, W), biased variance.  ws: float [N][his_groupnorm_parts()+1][C][2]. */
+int his_groupnorm_parts(int N, int HW, int C);
+int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int groups, const float* gamma, const float* beta, float eps, int act,
+                      float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, void* stream);
 int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const float* wt, const float* bias, int cout,
                        void* out, int out_cs, void* stream);
 

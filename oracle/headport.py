@@ -39,6 +39,7 @@ class PathConfig:
     use_contour_detection: bool = True
     use_distance_transform: bool = True
     normalization_type: str = "batchnorm"
+    normalization_groups: int = 8
     activation_function: str = "relu"
     activation_beta: float = 1.0
     hierarchical_base_channels: int = 64
@@ -59,20 +60,20 @@ class PathConfig:
     def factory_kwargs(self) -> dict:
         if self.multi_scale:
             return dict(mask_size=self.mask_size, multi_scale=True, roi_sizes=dict(self.roi_sizes), fusion_method=self.fusion_method,
-                        use_attention_module=self.use_attention_module, normalization_type=self.normalization_type, normalization_groups=8,
+                        use_attention_module=self.use_attention_module, normalization_type=self.normalization_type, normalization_groups=self.normalization_groups,
                         activation_function=self.activation_function, activation_beta=self.activation_beta)
         if not self.use_pretrained_unet:
             return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
                         use_attention_module=self.use_attention_module, use_contour_detection=self.use_contour_detection,
                         use_distance_transform=self.use_distance_transform, normalization_type=self.normalization_type,
-                        normalization_groups=8)
+                        normalization_groups=self.normalization_groups)
         return dict(roi_size=self.roi_size, mask_size=self.mask_size, multi_scale=False,
                     use_attention_module=self.use_attention_module,
                     use_boundary_refinement=self.use_boundary_refinement, use_subpixel_conv=self.use_subpixel_conv,
                     use_progressive_upsampling=self.use_progressive_upsampling,
                     use_contour_detection=self.use_contour_detection,
                     use_distance_transform=self.use_distance_transform,
-                    normalization_type=self.normalization_type, normalization_groups=8,
+                    normalization_type=self.normalization_type, normalization_groups=self.normalization_groups,
                     activation_function=self.activation_function, activation_beta=self.activation_beta,
                     use_pretrained_unet=True, pretrained_weights_path=self.pretrained_weights_path,
                     freeze_pretrained_weights=True, use_full_image_unet=True,
@@ -134,6 +135,30 @@ def norm(sd: SD, p: str, x: Tensor, cfg: PathConfig) -> Tensor:
         mean = x.mean(dim=(1, 2, 3), keepdim=True)
         var = x.var(dim=(1, 2, 3), keepdim=True, unbiased=False)
         return (x - mean) / torch.sqrt(var + 1e-5) * sd[p + "weight"] + sd[p + "bias"]
+    if t in ("instance", "instancenorm", "instancenorm2d"):
+        # nn.InstanceNorm2d(affine=True) (:185-186): per (sample, channel) statistics over (H,W), biased variance, eps 1e-5
+        return F.instance_norm(x, None, None, sd[p + "weight"], sd[p + "bias"], True, 0.0, 1e-5)
+    if t == "adaptive_instance":
+        # AdaptiveInstanceNorm2d.forward (:31-51), written out like the reference (mean / var of the flattened map, divide by
+        # sqrt(var + eps)): same mathematics as instance norm, but the operation order matters at fp32 for near-constant
+        # channels (F.instance_norm moves the small-ROI golden by 1.4e-3); the running statistics are never read
+        b, c, h, w = x.shape
+        xr = x.reshape(b, c, -1)
+        mean = xr.mean(dim=2, keepdim=True)
+        var = xr.var(dim=2, keepdim=True, unbiased=False)
+        xn = ((xr - mean) / torch.sqrt(var + 1e-5)).view(b, c, h, w)
+        return xn * sd[p + "weight"].view(1, c, 1, 1) + sd[p + "bias"].view(1, c, 1, 1)
+    if t in ("group", "groupnorm", "spatial_group"):
+        # nn.GroupNorm (:187-194; SpatialGroupNorm :54-74 wraps one under .norm); group count as the factory resolves it for
+        # group counts that do not exceed the channel count
+        q = p + "norm." if t == "spatial_group" else p
+        c, g = x.shape[1], min(cfg.normalization_groups, x.shape[1])
+        if c % g and t != "spatial_group":
+            g = next(d for d in (8, 4, 2, 1) if c % d == 0)
+        return F.group_norm(x, g, sd[q + "weight"], sd[q + "bias"], 1e-5)
+    if t == "mixed":     # MixedNormalization.forward in eval mode (:143-147) = its BatchNorm2d
+        q = p + "batch_norm."
+        return F.batch_norm(x, sd[q + "running_mean"], sd[q + "running_var"], sd[q + "weight"], sd[q + "bias"], False, 0.0, 1e-5)
     raise ValueError(f"oracle does not restate normalization type {t!r}")
 
 

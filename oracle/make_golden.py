@@ -65,6 +65,13 @@ REFINE_CASES = {
     "small_b0_subpixel_boundary_ln": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28), use_boundary_refinement=True,
                                               use_subpixel_conv=True, use_contour_detection=False, use_distance_transform=False,
                                               normalization_type="layernorm2d", use_attention_module=False), (96, 128)),
+    # a10: the other kinds of get_normalization_layer (normalization_comparison.py:159-206) through the full model
+    "small_b0_groupnorm": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="groupnorm",
+                                   normalization_groups=4, use_attention_module=True), (96, 128)),
+    "small_b0_spatial_group": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="spatial_group",
+                                       use_distance_transform=False, use_attention_module=False), (96, 128)),
+    "small_b0_mixed": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="mixed",
+                               use_progressive_upsampling=True), (96, 128)),
     "small_b0_progressive": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), use_progressive_upsampling=True,
                                      use_contour_detection=False, use_distance_transform=False), (96, 128)),
     "small_b0_progressive_ln_silu": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(40, 28), use_progressive_upsampling=True,

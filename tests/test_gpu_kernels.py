@@ -104,6 +104,34 @@ def test_direct_conv_variants_match_torch():
     assert (tail.cpu() - ref2).abs().max() <= 1e-4 * max(1.0, float(ref2.abs().max()))
 
 
+@pytest.mark.parametrize("c,groups", [(72, 1), (72, 9), (64, 4), (256, 256), (32, 8)])
+def test_groupnorm_matches_torch(c, groups):
+    """his_groupnorm_act (GroupNorm / SpatialGroupNorm of get_normalization_layer; one group per channel = instance norm) against
+    F.group_norm on the same fp16-rounded input, with residual add + ReLU and with a plain SiLU epilogue."""
+    p = _plan()
+    L = p.lib
+    g = torch.Generator().manual_seed(c + groups)
+    n, h, w = 3, 13, 11
+    x = p.act(n, h, w, c); x.buf.copy_((torch.randn(n, h, w, c, generator=g) * 1.5 + 0.7).half())
+    r = p.act(n, h, w, c); r.buf.copy_(torch.randn(n, h, w, c, generator=g).half())
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    outs = []
+    for act, res in ((1, r), (2, None)):
+        out = p.act(n, h, w, c)
+        parts = L.his_groupnorm_parts(n, h * w, c)
+        ws = torch.empty((n, parts + 1, c, 2), dtype=torch.float32, device="cuda")
+        p.keep.append(ws)
+        p.add("groupnorm", L.his_groupnorm_act, x.ptr, n, h * w, c, x.cs, groups, p.const(gamma).data_ptr(), p.const(beta).data_ptr(), 1e-5, act,
+              1.0, 1 if res is not None else 0, res.ptr if res is not None else None, res.cs if res is not None else 0, ws.data_ptr(), out.ptr,
+              out.cs)
+        outs.append(out)
+    p.replay(); torch.cuda.synchronize()
+    xin, rin = x.torch_nchw().cpu(), r.torch_nchw().cpu()
+    y = F.group_norm(xin, groups, gamma, beta, 1e-5)
+    for out, ref in zip(outs, (F.relu(y + rin), F.silu(y))):
+        assert (out.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
 def test_glue_kernels_match_torch():
     p = _plan(); lib = p.lib
     st = torch.cuda.current_stream().cuda_stream
