@@ -623,6 +623,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t idesc = make_idesc_f16(p.block_n, pair ? 2 * kBlockM : kBlockM);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    // descriptors = a constant high word | the 14-bit (address >> 4) that advances by adds (no per-iteration multiply / shift / mask)
+    const uint64_t desc_hi = make_kmajor_desc<BK>(0);
+    const uint32_t a_units0 = stage_base >> 4, stage_units = (uint32_t)p.stage_bytes >> 4;
+    constexpr uint32_t kBOffUnits = Cfg::kABytes >> 4;
+    uint32_t a_units = a_units0;
     // pair: the leader issues for both CTAs (its work items and the peer's advance in lock step); the peer's MMA warp idles
     for (int w = blockIdx.x; w < p.num_work && cta_rank == 0; w += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -632,24 +637,16 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = stage_base + stage * p.stage_bytes, sb = sa + Cfg::kABytes;
-          const uint64_t adesc = make_kmajor_desc<BK>(sa), bdesc = make_kmajor_desc<BK>(sb);
-          if (pair) {
+          const uint64_t adesc = desc_hi | a_units, bdesc = desc_hi | (a_units + kBOffUnits);
+          umma_x<pair>(d_tmem, adesc, bdesc, idesc, k ? 1u : 0u);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)
-              umma_f16_2sm(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-            umma_commit_2sm(empty_bar(stage));   // same-offset barriers of both CTAs
-            if (k == kiters - 1) umma_commit_2sm(tfull_bar(acc));
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)
-              umma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-            umma_commit(empty_bar(stage));      // frees the smem slot when these MMAs retire
-            if (k == kiters - 1) umma_commit(tfull_bar(acc));
-          }
+          for (int kk = 1; kk < BK / 16; ++kk) umma_acc_x<pair>(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc);
+          umma_commit_x<pair>(empty_bar(stage));      // frees the smem slot (of both CTAs of a pair) when these MMAs retire
+          if (k == kiters - 1) umma_commit_x<pair>(tfull_bar(acc));
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        a_units += stage_units;
+        if (++stage == kStages) { stage = 0; phase ^= 1; a_units = a_units0; }
       }
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
     }
