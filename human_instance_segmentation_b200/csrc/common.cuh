@@ -35,6 +35,13 @@ __device__ __forceinline__ float his_ex2_approx(float x) { float y; asm("ex2.app
 __device__ __forceinline__ float his_rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float his_sigmoid_fast(float x, float nb2) { return his_rcp_approx(1.0f + his_ex2_approx(nb2 * x)); }
 #define HIS_NEG_LOG2E (-1.4426950408889634f)
+// packed fp32 FMA of sm_100 (FFMA2): two IEEE fma.rn in one issue slot
+__device__ __forceinline__ float2 his_ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
 
 __device__ __forceinline__ float his_act(float v, int act, float beta) {
   switch (act) {

@@ -487,7 +487,7 @@ struct Dw2Cfg {
   static constexpr int IW = (TOW - 1) * S + K, IH = (TOH - 1) * S + K;
   static constexpr int NX = (XPT - 1) * S + K;                       // window vectors a thread reads per filter row
   static constexpr int kInBytes = IW * IH * kDw2Pitch;
-  static constexpr int kWBytes = K * K * kDw2Cb * 2;
+  static constexpr int kWBytes = K * K * kDw2Cb * 4;                  // filter taps as fp32 (converted once per CTA)
   static constexpr int kSmem = kInBytes + kWBytes + kDw2Threads * 8 * 4;   // + pooling scratch
 };
 
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kDw2Threads) depthwise_tiled_kernel(const DwPa
   using Cfg = Dw2Cfg<K, S, XPT>;
   extern __shared__ __align__(16) unsigned char dw_smem[];
   unsigned char* s_in = dw_smem;
-  __half* s_w = reinterpret_cast<__half*>(dw_smem + Cfg::kInBytes);
+  float* s_w = reinterpret_cast<float*>(dw_smem + Cfg::kInBytes);
   float* s_pool = reinterpret_cast<float*>(dw_smem + Cfg::kInBytes + Cfg::kWBytes);
   const int n = blockIdx.z, cb0 = blockIdx.y * kDw2Cb;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
@@ -519,42 +519,50 @@ __global__ void __launch_bounds__(kDw2Threads) depthwise_tiled_kernel(const DwPa
     const int v = i & 3, t = i >> 2;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (v < nvec) val = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)t * p.C + cb0 + v * 8));
-    *reinterpret_cast<uint4*>(s_w + t * kDw2Cb + v * 8) = val;
+    const __half2* wh = reinterpret_cast<const __half2*>(&val);
+    float2* dst = reinterpret_cast<float2*>(s_w + t * kDw2Cb + v * 8);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dst[e] = __half22float2(wh[e]);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   // ---- compute: lane -> (vector v, strip), warp -> output row
   const int v = threadIdx.x & 3, strip = (threadIdx.x >> 2) & 7, row = threadIdx.x >> 5;
   const int c0 = cb0 + v * 8;
-  float acc[XPT][8];
+  // accumulators, inputs and taps as fp32 PAIRS: one FFMA2 (fma.rn.f32x2, same rounding as two FFMAs) per two channels halves the
+  // FMA issue slots of this issue-bound kernel
+  float2 acc2[XPT][4];
 #pragma unroll
   for (int j = 0; j < XPT; ++j)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[j][e] = 0.0f;
+    for (int e = 0; e < 4; ++e) acc2[j][e] = make_float2(0.0f, 0.0f);
   const unsigned char* base = s_in + ((row * S) * Cfg::IW + strip * XPT * S) * kDw2Pitch + v * 16;
 #pragma unroll
   for (int ky = 0; ky < K; ++ky) {
-    float xf[Cfg::NX][8];
+    float2 xf[Cfg::NX][4];
 #pragma unroll
     for (int i = 0; i < Cfg::NX; ++i) {
       const uint4 xv = *reinterpret_cast<const uint4*>(base + (ky * Cfg::IW + i) * kDw2Pitch);
       const __half2* xh = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); xf[i][2 * e] = f.x; xf[i][2 * e + 1] = f.y; }
+      for (int e = 0; e < 4; ++e) xf[i][e] = __half22float2(xh[e]);
     }
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) {
-      const uint4 wv = *reinterpret_cast<const uint4*>(s_w + (ky * K + kx) * kDw2Cb + v * 8);
-      const __half2* wh = reinterpret_cast<const __half2*>(&wv);
-      float wf[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(wh[e]); wf[2 * e] = f.x; wf[2 * e + 1] = f.y; }
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * kDw2Cb + v * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * kDw2Cb + v * 8 + 4);
+      const float2 wf[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
       for (int j = 0; j < XPT; ++j)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(xf[j * S + kx][e], wf[e], acc[j][e]);
+        for (int e = 0; e < 4; ++e) acc2[j][e] = his_ffma2(xf[j * S + kx][e], wf[e], acc2[j][e]);
     }
   }
+  float acc[XPT][8];
+#pragma unroll
+  for (int j = 0; j < XPT; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc[j][2 * e] = acc2[j][e].x; acc[j][2 * e + 1] = acc2[j][e].y; }
   // ---- BN + activation, store, per-thread channel sums of what the next layer will read
   float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int oy = oy0 + row;

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd /root/repo
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 280 python bench.py --steps 5 --warmup 3 --breakdown --top 60 --no-cpu-baseline > gpurun_out/b0_dw.log 2>&1
+tail -1 gpurun_out/b0_dw.log | cut -c1-260
+head -4 gpurun_out/b0_dw.log | cut -c1-90
+grep depthwise gpurun_out/b0_dw.log | head -20
