@@ -55,3 +55,46 @@ __device__ __forceinline__ float his_act(float v, int act, float beta) {
 }
 
 static inline int his_div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- split-fp16 activations ("strict" precision mode): a value is a pair of fp16 numbers x = hi + lo with hi = fp16(x) and
+// lo = fp16(x - hi) (~21 significant bits); the lo plane of a pixel lies `lo` elements after its hi plane inside the same NHWC
+// buffer ([hi channels | lo channels], lo = pixel stride / 2).  lo == 0 means plain fp16.  The C entry points take `int split`
+// and derive lo = cs / 2 per tensor.
+#ifdef __CUDACC__
+__device__ __forceinline__ void his_ld8(const __half* p, int lo, float* f) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+  if (lo) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p + lo));
+    const __half2* l = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(l[e]); f[2 * e] += t.x; f[2 * e + 1] += t.y; }
+  }
+}
+__device__ __forceinline__ void his_st8(__half* p, int lo, const float* f) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+  if (lo) {
+    uint4 w;
+    __half2* l = reinterpret_cast<__half2*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); l[e] = __floats2half2_rn(f[2 * e] - t.x, f[2 * e + 1] - t.y); }
+    *reinterpret_cast<uint4*>(p + lo) = w;
+  }
+}
+__device__ __forceinline__ float his_ld1(const __half* p, int lo) {
+  float v = __half2float(__ldg(p));
+  if (lo) v += __half2float(__ldg(p + lo));
+  return v;
+}
+__device__ __forceinline__ void his_st1(__half* p, int lo, float v) {
+  const __half h = __float2half_rn(v);
+  *p = h;
+  if (lo) p[lo] = __float2half_rn(v - __half2float(h));
+}
+#endif

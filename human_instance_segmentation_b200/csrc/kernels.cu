@@ -60,7 +60,7 @@ template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p
 template <typename T>
 __global__ void roi_align_kernel(const T* __restrict__ feat, long long sN, long long sC, long long sH, long long sW, int B, int C,
                                  int H, int W, const float* __restrict__ rois, int n_rois, int oh, int ow, float scale_h,
-                                 float scale_w, int aligned, __half* __restrict__ out_h, int out_cs, float* __restrict__ out_f) {
+                                 float scale_w, int aligned, __half* __restrict__ out_h, int out_cs, int out_lo, float* __restrict__ out_f) {
   const long long total = (long long)n_rois * oh * ow;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(idx % ow);
@@ -86,7 +86,7 @@ __global__ void roi_align_kernel(const T* __restrict__ feat, long long sN, long 
       if (x1ok && y0ok) v += ld_as_float(base + iy * sH + (ix + 1) * sW) * (wx1 * wy0);
       if (x0ok && y1ok) v += ld_as_float(base + (iy + 1) * sH + ix * sW) * (wx0 * wy1);
       if (x1ok && y1ok) v += ld_as_float(base + (iy + 1) * sH + (ix + 1) * sW) * (wx1 * wy1);
-      if (out_h) out_h[idx * out_cs + c] = __float2half_rn(v);
+      if (out_h) his_st1(out_h + idx * out_cs + c, out_lo, v);
       if (out_f) out_f[(((long long)k * C + c) * oh + oy) * ow + ox] = v;
     }
   }
@@ -97,14 +97,18 @@ struct DirectConvParams {
   const void* in; int in_fmt;          // 0: NHWC fp16 (stride in_cs), 1: NCHW fp32
   const float* in_affine;              // optional [2*Cin]: x*a[c]+b[c] on in-bounds samples (input normalisation)
   int N, H, W, Cin, in_cs;
-  const __half* w;                     // [kh][kw][Cin][Cout]
+  const void* w;                       // [kh][kw][Cin][Cout], fp16 (fp32 when w_f32: the split-fp16 "strict" mode)
   const float* scale; const float* shift;
   int Cout, kh, kw, stride, pad, Ho, Wo;
   int act; float act_beta; int res_mode;
   const __half* res; int res_cs;
   __half* out_h; int out_cs;           // NHWC fp16 slice (may be null)
   float* out_f;                        // NCHW fp32 (may be null)
+  int w_f32, in_lo, res_lo, out_lo;    // split-fp16 activations: offset of the lo plane (0: plain fp16)
 };
+__device__ __forceinline__ float dc_w(const DirectConvParams& p, long long i) {
+  return p.w_f32 ? __ldg((const float*)p.w + i) : __half2float(__ldg((const __half*)p.w + i));
+}
 
 template <int COT>
 __global__ void direct_conv_kernel(const DirectConvParams p) {
@@ -124,23 +128,23 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
       for (int kx = 0; kx < p.kw; ++kx) {
         const int ix = ox * p.stride - p.pad + kx;
         if (ix < 0 || ix >= p.W) continue;
-        const __half* wrow = p.w + ((long long)(ky * p.kw + kx) * p.Cin) * p.Cout + co;
+        const long long wrow = ((long long)(ky * p.kw + kx) * p.Cin) * p.Cout + co;
         if (p.in_fmt == 0) {
           const __half* ip = (const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs;
           for (int ci = 0; ci < p.Cin; ++ci) {
-            const float x = __half2float(__ldg(ip + ci));
-            const __half* wp = wrow + (long long)ci * p.Cout;
+            const float x = his_ld1(ip + ci, p.in_lo);
+            const long long wp = wrow + (long long)ci * p.Cout;
 #pragma unroll
-            for (int t = 0; t < COT; ++t) acc[t] = fmaf(x, __half2float(__ldg(wp + t)), acc[t]);
+            for (int t = 0; t < COT; ++t) acc[t] = fmaf(x, dc_w(p, wp + t), acc[t]);
           }
         } else {
           const float* ip = (const float*)p.in + (long long)n * p.Cin * p.H * p.W + (long long)iy * p.W + ix;
           for (int ci = 0; ci < p.Cin; ++ci) {
             float x = __ldg(ip + (long long)ci * p.H * p.W);
             if (p.in_affine) x = fmaf(x, __ldg(p.in_affine + ci), __ldg(p.in_affine + p.Cin + ci));
-            const __half* wp = wrow + (long long)ci * p.Cout;
+            const long long wp = wrow + (long long)ci * p.Cout;
 #pragma unroll
-            for (int t = 0; t < COT; ++t) acc[t] = fmaf(x, __half2float(__ldg(wp + t)), acc[t]);
+            for (int t = 0; t < COT; ++t) acc[t] = fmaf(x, dc_w(p, wp + t), acc[t]);
           }
         }
       }
@@ -149,7 +153,7 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
     for (int t = 0; t < COT; ++t) {
       float y = acc[t] * __ldg(p.scale + co + t) + __ldg(p.shift + co + t);
       float r = 0.0f;
-      if (p.res_mode) r = __half2float(p.res[pix * p.res_cs + co + t]);
+      if (p.res_mode) r = his_ld1(p.res + pix * p.res_cs + co + t, p.res_lo);
       if (p.res_mode == HIS_RES_ADD) y += r;
       y = his_act(y, p.act, p.act_beta);
       if (p.res_mode == HIS_RES_MUL) y *= r;
@@ -158,7 +162,7 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
     if (p.out_h) {
       __half* op = p.out_h + pix * p.out_cs + co;
 #pragma unroll
-      for (int t = 0; t < COT; ++t) op[t] = __float2half_rn(acc[t]);
+      for (int t = 0; t < COT; ++t) his_st1(op + t, p.out_lo, acc[t]);
     }
     if (p.out_f) {
 #pragma unroll
@@ -174,7 +178,7 @@ template <int KK /*k*k*/, int CIN>
 __global__ void small_cin_conv_kernel(const DirectConvParams p) {
   extern __shared__ float s_w[];            // [KK*CIN][Cout]
   const int nw = KK * CIN * p.Cout;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = __half2float(p.w[i]);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = dc_w(p, i);
   __syncthreads();
   const int groups = p.Cout / 32;
   const long long total = (long long)p.N * p.Ho * p.Wo * groups;
@@ -192,7 +196,7 @@ __global__ void small_cin_conv_kernel(const DirectConvParams p) {
       for (int ci = 0; ci < CIN; ++ci) {
         float v = 0.0f;
         if (ok) {
-          if (p.in_fmt == 0) v = __half2float(__ldg((const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs + ci));
+          if (p.in_fmt == 0) v = his_ld1((const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs + ci, p.in_lo);
           else {
             v = __ldg((const float*)p.in + ((long long)(n * CIN + ci) * p.H + iy) * p.W + ix);
             if (p.in_affine) v = fmaf(v, __ldg(p.in_affine + ci), __ldg(p.in_affine + CIN + ci));
@@ -218,15 +222,13 @@ __global__ void small_cin_conv_kernel(const DirectConvParams p) {
     __half* op = p.out_h + pix * p.out_cs + co;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      __half2 o[4];
+      float y8[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = q * 8 + 2 * e;
-        const float y0 = his_act(acc[c] * __ldg(p.scale + co + c) + __ldg(p.shift + co + c), p.act, p.act_beta);
-        const float y1 = his_act(acc[c + 1] * __ldg(p.scale + co + c + 1) + __ldg(p.shift + co + c + 1), p.act, p.act_beta);
-        o[e] = __floats2half2_rn(y0, y1);
+      for (int e = 0; e < 8; ++e) {
+        const int c = q * 8 + e;
+        y8[e] = his_act(acc[c] * __ldg(p.scale + co + c) + __ldg(p.shift + co + c), p.act, p.act_beta);
       }
-      *reinterpret_cast<uint4*>(op + q * 8) = *reinterpret_cast<uint4*>(o);
+      his_st8(op + q * 8, p.out_lo, y8);
     }
   }
 }
@@ -237,7 +239,7 @@ template <int COUT>
 __global__ void small_cout_conv_kernel(const DirectConvParams p) {
   extern __shared__ float s_w[];            // [kh*kw][Cin][COUT]
   const int nw = p.kh * p.kw * p.Cin * COUT;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = __half2float(p.w[i]);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = dc_w(p, i);
   __syncthreads();
   const long long total = (long long)p.N * p.Ho * p.Wo;
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
@@ -254,16 +256,12 @@ __global__ void small_cout_conv_kernel(const DirectConvParams p) {
         const __half* ip = (const __half*)p.in + ((long long)(n * p.H + iy) * p.W + ix) * p.in_cs;
         const float* wr = s_w + (long long)(ky * p.kw + kx) * p.Cin * COUT;
         for (int c8 = 0; c8 < p.Cin; c8 += 8) {
-          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(ip + c8));
-          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+          float xf[8];
+          his_ld8(ip + c8, p.in_lo, xf);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(xh[e]);
+          for (int e = 0; e < 8; ++e) {
 #pragma unroll
-            for (int t = 0; t < COUT; ++t) {
-              acc[t] = fmaf(f.x, wr[(c8 + 2 * e) * COUT + t], acc[t]);
-              acc[t] = fmaf(f.y, wr[(c8 + 2 * e + 1) * COUT + t], acc[t]);
-            }
+            for (int t = 0; t < COUT; ++t) acc[t] = fmaf(xf[e], wr[(c8 + e) * COUT + t], acc[t]);
           }
         }
       }
@@ -286,7 +284,7 @@ constexpr int kHeadStripCols = 30, kHeadStripRows = 32;
 template <int CIN>
 __global__ void __launch_bounds__(kThreads) head3x3_c1_kernel(const DirectConvParams p) {
   __shared__ __align__(16) float s_w[9 * CIN];
-  for (int i = threadIdx.x; i < 9 * CIN; i += blockDim.x) s_w[i] = __half2float(p.w[i]);
+  for (int i = threadIdx.x; i < 9 * CIN; i += blockDim.x) s_w[i] = dc_w(p, i);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int ncol = (p.W + kHeadStripCols - 1) / kHeadStripCols, nstrip = (p.H + kHeadStripRows - 1) / kHeadStripRows;
@@ -304,12 +302,7 @@ __global__ void __launch_bounds__(kThreads) head3x3_c1_kernel(const DirectConvPa
       if (xin_ok && r >= 0 && r < p.H) {
         const __half* px = (const __half*)p.in + ((long long)(n * p.H + r) * p.W + x) * p.in_cs;
 #pragma unroll
-        for (int c8 = 0; c8 < CIN; c8 += 8) {
-          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(px + c8));
-          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); xin[c8 + 2 * e] = f.x; xin[c8 + 2 * e + 1] = f.y; }
-        }
+        for (int c8 = 0; c8 < CIN; c8 += 8) his_ld8(px + c8, p.in_lo, xin + c8);
       } else {
 #pragma unroll
         for (int c = 0; c < CIN; ++c) xin[c] = 0.0f;
@@ -599,9 +592,66 @@ __global__ void __launch_bounds__(kDw2Threads) depthwise_tiled_kernel(const DwPa
   }
 }
 
+// Split-fp16 ("strict" precision) depthwise conv: same CTA geometry and pooling-partial layout as the tiled kernel above, operands read
+// straight from global memory as hi + lo pairs, fp32 filter taps, fp32 pooling of the exact (unrounded) outputs.  Precision first:
+// this path is 2-3x slower than the staged kernel and only runs when the model is in strict mode.
+template <int K, int S, int XPT, int ACT>
+__global__ void __launch_bounds__(kDw2Threads) depthwise_split_kernel(const DwParams p, int tiles_x, const float* __restrict__ w32, int in_lo, int out_lo) {
+  using Cfg = Dw2Cfg<K, S, XPT>;
+  __shared__ float s_pool[kDw2Threads * 8];
+  const int n = blockIdx.z, cb0 = blockIdx.y * kDw2Cb;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int oy0 = ty * Cfg::TOH, ox0 = tx * Cfg::TOW;
+  const int nvec = min(4, (p.C - cb0) >> 3);
+  const int v = threadIdx.x & 3, strip = (threadIdx.x >> 2) & 7, row = threadIdx.x >> 5;
+  const int c0 = cb0 + v * 8;
+  const int oy = oy0 + row;
+  float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (v < nvec && oy < p.Ho) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+    const __half* inb = p.in + (long long)n * p.H * p.W * p.in_cs + c0;
+    for (int j = 0; j < XPT; ++j) {
+      const int ox = ox0 + strip * XPT + j;
+      if (ox >= p.Wo) continue;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S - p.pad + ky;
+        if (iy < 0 || iy >= p.H) continue;
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox * S - p.pad + kx;
+          if (ix < 0 || ix >= p.W) continue;
+          float xf[8];
+          his_ld8(inb + ((long long)iy * p.W + ix) * p.in_cs, in_lo, xf);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w32 + (long long)(ky * K + kx) * p.C + c0));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w32 + (long long)(ky * K + kx) * p.C + c0 + 4));
+          acc[0] = fmaf(xf[0], w0.x, acc[0]); acc[1] = fmaf(xf[1], w0.y, acc[1]); acc[2] = fmaf(xf[2], w0.z, acc[2]); acc[3] = fmaf(xf[3], w0.w, acc[3]);
+          acc[4] = fmaf(xf[4], w1.x, acc[4]); acc[5] = fmaf(xf[5], w1.y, acc[5]); acc[6] = fmaf(xf[6], w1.z, acc[6]); acc[7] = fmaf(xf[7], w1.w, acc[7]);
+        }
+      }
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { y[e] = act_ct<ACT>(acc[e] * sc[e] + sh[e]); psum[e] += y[e]; }
+      his_st8(p.out + ((long long)(n * p.Ho + oy) * p.Wo + ox) * p.out_cs + c0, out_lo, y);
+    }
+  }
+  if (p.pool) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = psum[e];
+    __syncthreads();
+    if (threadIdx.x < kDw2Cb && cb0 + (int)threadIdx.x < p.C) {
+      const int vv = threadIdx.x >> 3, e = threadIdx.x & 7;
+      float t = 0.0f;
+      for (int q = 0; q < kDw2Threads / 4; ++q) t += s_pool[(q * 4 + vv) * 8 + e];
+      p.pool[((long long)n * gridDim.x + blockIdx.x) * p.C + cb0 + threadIdx.x] = t;
+    }
+  }
+}
+
 // per-(n,c) sums of an NHWC fp16 tensor (ChannelAttentionModule's adaptive_avg_pool2d): per-block partials
 // [N][gridDim.x][C], reduced in a fixed order (deterministic); blockDim.x is a multiple of C/8.
-__global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, int cs, float* __restrict__ pool) {
+__global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, int cs, int lo, float* __restrict__ pool) {
   extern __shared__ float s_pool[];
   const int n = blockIdx.y, cgs = C / 8;
   const long long per_img = (long long)HW * cgs;
@@ -620,6 +670,8 @@ __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, in
     add(v0); add(v1); add(v2); add(v3);
   }
   for (; idx < per_img; idx += step) add(__ldg(addr(idx)));
+  if (lo)      // split-fp16 input: the lo planes of the same pixels (their sum is ~2^-11 of the total: order is immaterial)
+    for (idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += step) add(__ldg(addr(idx) + (lo >> 3)));
 #pragma unroll
   for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = acc[e];
   __syncthreads();
@@ -711,40 +763,54 @@ __global__ void scale_weights_kernel(const __half* __restrict__ w, const float* 
   }
 }
 
+// split-fp16 form: rows are [W_hi | W_lo] (K1 elements each); out = split((W_hi + W_lo) * gate)
+__global__ void scale_weights_split_kernel(const __half* __restrict__ w, const float* __restrict__ gate, long long rows, int K1, int C,
+                                           long long total, __half* __restrict__ out) {
+  const int kgs = K1 / 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kg = (int)(idx % kgs);
+    const long long row = (idx / kgs) % rows;
+    const long long n = idx / (kgs * rows);
+    float f[8];
+    his_ld8(w + row * 2 * K1 + kg * 8, K1, f);
+    const float* g = gate + n * C + kg * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (kg * 8 + e < C) ? f[e] * __ldg(g + e) : 0.0f;
+    his_st8(out + (n * rows + row) * 2 * K1 + kg * 8, K1, f);
+  }
+}
+
 // x[n,p,c] *= gate[n,c]  (in place or to another slice)
 __global__ void scale_channels_kernel(const __half* __restrict__ in, int in_cs, const float* __restrict__ gate, long long HW, int C,
-                                      long long total, __half* __restrict__ out, int out_cs) {
+                                      long long total, __half* __restrict__ out, int out_cs, int in_lo, int out_lo) {
   const int cgs = C / 8;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = idx / cgs;
     const long long n = pix / HW;
-    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * in_cs + cg * 8));
-    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    float f[8];
+    his_ld8(in + pix * in_cs + cg * 8, in_lo, f);
     const float* g = gate + n * C + cg * 8;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(xh[e]);
-      xh[e] = __floats2half2_rn(f.x * __ldg(g + 2 * e), f.y * __ldg(g + 2 * e + 1));
-    }
-    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+    for (int e = 0; e < 8; ++e) f[e] *= __ldg(g + e);
+    his_st8(out + pix * out_cs + cg * 8, out_lo, f);
   }
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm2d (hed/model.py:18-38)
 // Statistics over (C,H,W) per sample (biased variance, eps 1e-5), affine [C].  Two launches: fixed-order partial sums
 // (fp32 per thread, double per block -> bit-reproducible), then normalise + affine (+residual) + activation.
-__global__ void ln_stats_kernel(const __half* __restrict__ in, long long per_img_vec, int HW, int C, int cs, double* __restrict__ partials) {
+__global__ void ln_stats_kernel(const __half* __restrict__ in, long long per_img_vec, int HW, int C, int cs, int lo, double* __restrict__ partials) {
   __shared__ double s_sum[kThreads], s_sq[kThreads];
   const int n = blockIdx.y, cgs = C / 8;
   float a = 0.0f, b = 0.0f;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = idx / cgs;
-    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
-    const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+    float f[8];
+    his_ld8(in + ((long long)n * HW + pix) * cs + cg * 8, lo, f);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); a += f.x + f.y; b = fmaf(f.x, f.x, fmaf(f.y, f.y, b)); }
+    for (int e = 0; e < 4; ++e) { a += f[2 * e] + f[2 * e + 1]; b = fmaf(f[2 * e], f[2 * e], fmaf(f[2 * e + 1], f[2 * e + 1], b)); }
   }
   s_sum[threadIdx.x] = (double)a; s_sq[threadIdx.x] = (double)b;
   __syncthreads();
@@ -760,7 +826,8 @@ __global__ void ln_stats_kernel(const __half* __restrict__ in, long long per_img
 
 __global__ void ln_apply_kernel(const __half* __restrict__ in, int HW, int C, int cs, const double* __restrict__ partials, int nparts,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int act, float act_beta,
-                                int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs) {
+                                int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs,
+                                int in_lo, int res_lo, int out_lo) {
   __shared__ float s_mu, s_rstd;
   const int n = blockIdx.y, cgs = C / 8;
   if (threadIdx.x == 0) {
@@ -778,23 +845,19 @@ __global__ void ln_apply_kernel(const __half* __restrict__ in, int HW, int C, in
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = (long long)n * HW + idx / cgs;
-    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * cs + cg * 8));
-    __half2* xh = reinterpret_cast<__half2*>(&xv);
-    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-    if (res_mode) rv = __ldg(reinterpret_cast<const uint4*>(res + pix * res_cs + cg * 8));
-    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+    float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    his_ld8(in + pix * cs + cg * 8, in_lo, f);
+    if (res_mode) his_ld8(res + pix * res_cs + cg * 8, res_lo, r);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(xh[e]), r = __half22float2(rh[e]);
-      const int c = cg * 8 + 2 * e;
-      float y0 = (f.x - mu) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-      float y1 = (f.y - mu) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-      if (res_mode == HIS_RES_ADD) { y0 += r.x; y1 += r.y; }
-      y0 = his_act(y0, act, act_beta); y1 = his_act(y1, act, act_beta);
-      if (res_mode == HIS_RES_MUL) { y0 *= r.x; y1 *= r.y; }
-      xh[e] = __floats2half2_rn(y0, y1);
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      float y = (f[e] - mu) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      if (res_mode == HIS_RES_ADD) y += r[e];
+      y = his_act(y, act, act_beta);
+      if (res_mode == HIS_RES_MUL) y *= r[e];
+      f[e] = y;
     }
-    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+    his_st8(out + pix * out_cs + cg * 8, out_lo, f);
   }
 }
 
@@ -807,7 +870,7 @@ __global__ void ln_apply_kernel(const __half* __restrict__ in, int HW, int C, in
 //   2. per (n, group): parts and channels summed in double          -> ws[n][parts][c] = (mean, rstd) of the channel's group
 //   3. normalise + affine (+ residual) + activation, 16-byte vectors
 constexpr int kGnMaxC = 2048;
-__global__ void gn_stats_kernel(const __half* __restrict__ in, int HW, int C, int cs, int pix_per_part, int nslots, float* __restrict__ ws) {
+__global__ void gn_stats_kernel(const __half* __restrict__ in, int HW, int C, int cs, int lo, int pix_per_part, int nslots, float* __restrict__ ws) {
   extern __shared__ float s_gn[];                       // [pixel lanes][C][2]
   const int n = blockIdx.y, part = blockIdx.x, cgs = C / 8;
   const int PL = blockDim.x / cgs;                      // pixel lanes (>= 1: C <= 2048)
@@ -818,14 +881,10 @@ __global__ void gn_stats_kernel(const __half* __restrict__ in, int HW, int C, in
   for (int e = 0; e < 8; ++e) { sum[e] = 0.0f; sq[e] = 0.0f; }
   if (pl < PL) {
     for (int pix = p0 + pl; pix < p1; pix += PL) {
-      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + ((long long)n * HW + pix) * cs + cg * 8));
-      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+      float f[8];
+      his_ld8(in + ((long long)n * HW + pix) * cs + cg * 8, lo, f);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(xh[e]);
-        sum[2 * e] += f.x; sum[2 * e + 1] += f.y;
-        sq[2 * e] = fmaf(f.x, f.x, sq[2 * e]); sq[2 * e + 1] = fmaf(f.y, f.y, sq[2 * e + 1]);
-      }
+      for (int e = 0; e < 8; ++e) { sum[e] += f[e]; sq[e] = fmaf(f[e], f[e], sq[e]); }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s_gn[((size_t)pl * C + cg * 8 + e) * 2] = sum[e]; s_gn[((size_t)pl * C + cg * 8 + e) * 2 + 1] = sq[e]; }
@@ -859,7 +918,8 @@ __global__ void gn_finalize_kernel(float* __restrict__ ws, int HW, int C, int G,
 
 __global__ void gn_apply_kernel(const __half* __restrict__ in, int HW, int C, int cs, const float* __restrict__ ws, int nparts,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int act, float act_beta,
-                                int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs) {
+                                int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs,
+                                int in_lo, int res_lo, int out_lo) {
   extern __shared__ float s_ab[];                       // per channel: y = x*a + b with a = rstd*gamma, b = beta - mean*a
   const int n = blockIdx.y, cgs = C / 8;
   const float* st = ws + ((long long)n * (nparts + 1) + nparts) * C * 2;
@@ -872,29 +932,25 @@ __global__ void gn_apply_kernel(const __half* __restrict__ in, int HW, int C, in
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = (long long)n * HW + idx / cgs;
-    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * cs + cg * 8));
-    __half2* xh = reinterpret_cast<__half2*>(&xv);
-    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-    if (res_mode) rv = __ldg(reinterpret_cast<const uint4*>(res + pix * res_cs + cg * 8));
-    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+    float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    his_ld8(in + pix * cs + cg * 8, in_lo, f);
+    if (res_mode) his_ld8(res + pix * res_cs + cg * 8, res_lo, r);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(xh[e]), r = __half22float2(rh[e]);
-      const int c = cg * 8 + 2 * e;
-      float y0 = fmaf(f.x, s_ab[2 * c], s_ab[2 * c + 1]);
-      float y1 = fmaf(f.y, s_ab[2 * c + 2], s_ab[2 * c + 3]);
-      if (res_mode == HIS_RES_ADD) { y0 += r.x; y1 += r.y; }
-      y0 = his_act(y0, act, act_beta); y1 = his_act(y1, act, act_beta);
-      if (res_mode == HIS_RES_MUL) { y0 *= r.x; y1 *= r.y; }
-      xh[e] = __floats2half2_rn(y0, y1);
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      float y = fmaf(f[e], s_ab[2 * c], s_ab[2 * c + 1]);
+      if (res_mode == HIS_RES_ADD) y += r[e];
+      y = his_act(y, act, act_beta);
+      if (res_mode == HIS_RES_MUL) y *= r[e];
+      f[e] = y;
     }
-    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+    his_st8(out + pix * out_cs + cg * 8, out_lo, f);
   }
 }
 
 // ConvTranspose2d(k2,s2) for tiny Cin (upsample_bg_fg.0 in LayerNorm mode: 2 -> 32): NCHW fp32 in, NHWC fp16 out (+bias)
 __global__ void convT2x2_small_kernel(const float* __restrict__ in, int N, int Cin, int h, int w, const float* __restrict__ wt,
-                                      const float* __restrict__ bias, int Cout, __half* __restrict__ out, int out_cs) {
+                                      const float* __restrict__ bias, int Cout, __half* __restrict__ out, int out_cs, int out_lo) {
   const int Ho = 2 * h, Wo = 2 * w;
   const long long total = (long long)N * Ho * Wo * Cout;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -904,12 +960,13 @@ __global__ void convT2x2_small_kernel(const float* __restrict__ in, int N, int C
     float v = bias ? bias[c] : 0.0f;
     for (int ci = 0; ci < Cin; ++ci)
       v = fmaf(in[((long long)(n * Cin + ci) * h + (oy >> 1)) * w + (ox >> 1)], wt[((ci * Cout + c) * 2 + (oy & 1)) * 2 + (ox & 1)], v);
-    out[pix * out_cs + c] = __float2half_rn(v);
+    his_st1(out + pix * out_cs + c, out_lo, v);
   }
 }
 
 // ------------------------------------------------------------------------------------ pooling / resize
-__global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, __half* __restrict__ out, int out_cs) {
+__global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, __half* __restrict__ out, int out_cs,
+                                int in_lo, int out_lo) {
   const int Ho = H / 2, Wo = W / 2, cgs = C / 8;
   const long long total = (long long)N * Ho * Wo * cgs;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -917,6 +974,15 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int
     const long long pix = idx / cgs;
     const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
     const __half* base = in + ((long long)(n * H + 2 * oy) * W + 2 * ox) * in_cs + cg * 8;
+    if (in_lo) {       // split-fp16: the maximum of the hi + lo sums, re-split (exact: the winner's own pair)
+      float fa[8], fb[8], fc[8], fd[8];
+      his_ld8(base, in_lo, fa); his_ld8(base + in_cs, in_lo, fb);
+      his_ld8(base + (long long)W * in_cs, in_lo, fc); his_ld8(base + (long long)(W + 1) * in_cs, in_lo, fd);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fa[e] = fmaxf(fmaxf(fa[e], fb[e]), fmaxf(fc[e], fd[e]));
+      his_st8(out + pix * out_cs + cg * 8, out_lo, fa);
+      continue;
+    }
     uint4 a = __ldg(reinterpret_cast<const uint4*>(base)), b = __ldg(reinterpret_cast<const uint4*>(base + in_cs));
     uint4 c = __ldg(reinterpret_cast<const uint4*>(base + (long long)W * in_cs)), d = __ldg(reinterpret_cast<const uint4*>(base + (long long)(W + 1) * in_cs));
     __half2* ah = reinterpret_cast<__half2*>(&a); const __half2* bh = reinterpret_cast<const __half2*>(&b);
@@ -929,7 +995,7 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, int N, int H, int
 
 // nearest resize of an NHWC fp16 tensor into a channel slice (smp UnetDecoderBlock F.interpolate(mode="nearest"))
 __global__ void resize_nearest_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, int Ho, int Wo,
-                                      __half* __restrict__ out, int out_cs) {
+                                      __half* __restrict__ out, int out_cs, int in_lo, int out_lo) {
   const int cgs = C / 8;
   const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
   const long long total = (long long)N * Ho * Wo * cgs;
@@ -940,6 +1006,9 @@ __global__ void resize_nearest_kernel(const __half* __restrict__ in, int N, int 
     const int iy = min((int)floorf(oy * sy), H - 1), ix = min((int)floorf(ox * sx), W - 1);
     *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) =
         __ldg(reinterpret_cast<const uint4*>(in + ((long long)(n * H + iy) * W + ix) * in_cs + cg * 8));
+    if (in_lo)
+      *reinterpret_cast<uint4*>(out + pix * out_cs + out_lo + cg * 8) =
+          __ldg(reinterpret_cast<const uint4*>(in + ((long long)(n * H + iy) * W + ix) * in_cs + in_lo + cg * 8));
   }
 }
 
@@ -962,7 +1031,7 @@ __global__ void resize_bilinear_f32_kernel(const float* __restrict__ in, int NC,
 // bilinear resize (align_corners=False) of an NHWC fp16 slice into another slice (MultiScaleRGBSegmentationModel resizes every
 // scale's features to 28x28, rgb.py:887-893); 8 channels per thread, fp32 interpolation
 __global__ void resize_bilinear_half_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs, int Ho, int Wo,
-                                            __half* __restrict__ out, int out_cs) {
+                                            __half* __restrict__ out, int out_cs, int in_lo, int out_lo) {
   const int cgs = C / 8;
   const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
   const long long total = (long long)N * Ho * Wo * cgs;
@@ -975,25 +1044,18 @@ __global__ void resize_bilinear_half_kernel(const __half* __restrict__ in, int N
     const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
     const float ly = fy - (float)y0, lx = fx - (float)x0;
     const __half* b = in + (long long)n * H * W * in_cs + cg * 8;
-    const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x0) * in_cs)), v01 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y0 * W + x1) * in_cs));
-    const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x0) * in_cs)), v11 = __ldg(reinterpret_cast<const uint4*>(b + ((long long)y1 * W + x1) * in_cs));
-    const __half2 *a = reinterpret_cast<const __half2*>(&v00), *bb = reinterpret_cast<const __half2*>(&v01);
-    const __half2 *c = reinterpret_cast<const __half2*>(&v10), *d = reinterpret_cast<const __half2*>(&v11);
-    uint4 ov; __half2* o = reinterpret_cast<__half2*>(&ov);
+    float p00[8], p01[8], p10[8], p11[8], r[8];
+    his_ld8(b + ((long long)y0 * W + x0) * in_cs, in_lo, p00); his_ld8(b + ((long long)y0 * W + x1) * in_cs, in_lo, p01);
+    his_ld8(b + ((long long)y1 * W + x0) * in_cs, in_lo, p10); his_ld8(b + ((long long)y1 * W + x1) * in_cs, in_lo, p11);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 p00 = __half22float2(a[e]), p01 = __half22float2(bb[e]), p10 = __half22float2(c[e]), p11 = __half22float2(d[e]);
-      const float r0 = (1.0f - ly) * ((1.0f - lx) * p00.x + lx * p01.x) + ly * ((1.0f - lx) * p10.x + lx * p11.x);
-      const float r1 = (1.0f - ly) * ((1.0f - lx) * p00.y + lx * p01.y) + ly * ((1.0f - lx) * p10.y + lx * p11.y);
-      o[e] = __floats2half2_rn(r0, r1);
-    }
-    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = ov;
+    for (int e = 0; e < 8; ++e) r[e] = (1.0f - ly) * ((1.0f - lx) * p00[e] + lx * p01[e]) + ly * ((1.0f - lx) * p10[e] + lx * p11[e]);
+    his_st8(out + pix * out_cs + cg * 8, out_lo, r);
   }
 }
 
 // ------------------------------------------------------------------------------------ attention glue
 // SpatialAttentionModule (attention_modules.py:67-113): per-pixel channel mean & max -> [N,H,W,2] fp32
-__global__ void channel_stats_kernel(const __half* __restrict__ in, long long pixels, int C, int cs, float* __restrict__ stats) {
+__global__ void channel_stats_kernel(const __half* __restrict__ in, long long pixels, int C, int cs, int lo, float* __restrict__ stats) {
   // one warp per pixel: lanes stride the channel vector in 16-byte pieces
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -1001,10 +1063,10 @@ __global__ void channel_stats_kernel(const __half* __restrict__ in, long long pi
   for (long long pix = warp_global; pix < pixels; pix += nwarps) {
     float s = 0.0f, m = -INFINITY;
     for (int c = lane * 8; c < C; c += 256) {
-      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * cs + c));
-      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+      float f[8];
+      his_ld8(in + pix * cs + c, lo, f);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); s += f.x + f.y; m = fmaxf(m, fmaxf(f.x, f.y)); }
+      for (int e = 0; e < 4; ++e) { s += f[2 * e] + f[2 * e + 1]; m = fmaxf(m, fmaxf(f[2 * e], f[2 * e + 1])); }
     }
     for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
     if (lane == 0) { stats[pix * 2] = s / (float)C; stats[pix * 2 + 1] = m; }
@@ -1014,7 +1076,7 @@ __global__ void channel_stats_kernel(const __half* __restrict__ in, long long pi
 // x * sigmoid(conv_kxk([mean,max])) ; w is [2][k][k] fp32 (PyTorch [1,2,k,k])
 __global__ void spatial_attention_apply_kernel(const __half* __restrict__ in, int N, int H, int W, int C, int in_cs,
                                                const float* __restrict__ stats, const float* __restrict__ w, int k,
-                                               __half* __restrict__ out, int out_cs) {
+                                               __half* __restrict__ out, int out_cs, int in_lo, int out_lo) {
   const int lane = threadIdx.x & 31;
   const long long pixels = (long long)N * H * W;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -1034,11 +1096,11 @@ __global__ void spatial_attention_apply_kernel(const __half* __restrict__ in, in
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float g = his_sigmoid(s);
     for (int c = lane * 8; c < C; c += 256) {
-      uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * in_cs + c));
-      __half2* xh = reinterpret_cast<__half2*>(&xv);
+      float f[8];
+      his_ld8(in + pix * in_cs + c, in_lo, f);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); xh[e] = __floats2half2_rn(f.x * g, f.y * g); }
-      *reinterpret_cast<uint4*>(out + pix * out_cs + c) = xv;
+      for (int e = 0; e < 8; ++e) f[e] *= g;
+      his_st8(out + pix * out_cs + c, out_lo, f);
     }
   }
 }
@@ -1134,28 +1196,28 @@ __global__ void map_f32_kernel(const float* __restrict__ in, long long total, in
 // ---- PretrainedUNetGuidedSegmentationHead glue (rgb.py:125-218)
 // fg_prob = sigmoid(channel c of an NCHW fp32 tensor) -> channel 0 of an NHWC fp16 slice (the concat slot) and/or fp32 [N,HW]
 __global__ void sigmoid_channel_kernel(const float* __restrict__ in, int C, long long HW, int c, long long total, __half* __restrict__ out_h,
-                                       int out_cs, float* __restrict__ out_f) {
+                                       int out_cs, int out_lo, float* __restrict__ out_f) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const long long n = idx / HW, p = idx - n * HW;
     const float v = 1.0f / (1.0f + expf(-in[(n * C + c) * HW + p]));
-    if (out_h) out_h[idx * out_cs] = __float2half_rn(v);
+    if (out_h) his_st1(out_h + idx * out_cs, out_lo, v);
     if (out_f) out_f[idx] = v;
   }
 }
 
 // processed * (attention * (0.5 + 0.5 * fg_prob))  (rgb.py:169-173); a, f: fp32 per pixel
 __global__ void scale_pixels_kernel(const __half* __restrict__ in, int in_cs, const float* __restrict__ a, const float* __restrict__ f, int C,
-                                    long long total, __half* __restrict__ out, int out_cs) {
+                                    long long total, __half* __restrict__ out, int out_cs, int in_lo, int out_lo) {
   const int cgs = C / 8;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = idx / cgs;
     const float g = __ldg(a + pix) * (0.5f + 0.5f * __ldg(f + pix));
-    uint4 xv = __ldg(reinterpret_cast<const uint4*>(in + pix * in_cs + cg * 8));
-    __half2* xh = reinterpret_cast<__half2*>(&xv);
+    float v[8];
+    his_ld8(in + pix * in_cs + cg * 8, in_lo, v);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const float2 v = __half22float2(xh[e]); xh[e] = __floats2half2_rn(v.x * g, v.y * g); }
-    *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) = xv;
+    for (int e = 0; e < 8; ++e) v[e] *= g;
+    his_st8(out + pix * out_cs + cg * 8, out_lo, v);
   }
 }
 
@@ -1190,7 +1252,8 @@ __global__ void guided_aux_kernel(const float* __restrict__ in, int C, int c, in
 // depth-to-space of an NHWC fp16 slice: out[n][2y+py][2x+px][c] = in[n][y][x][(py*2+px)*C + c].  ConvTranspose2d(k4, s2, p1)
 // of ProgressiveUpsamplingDecoder (..._refinement.py:152-215) is four 2x2 phase convolutions of the input; they run as ONE 3x3
 // conv with 4*C output channels (phase-major, the taps a phase does not use are zero) and this kernel interleaves the phases.
-__global__ void depth_to_space2_half_kernel(const __half* __restrict__ in, int N, int h, int w, int C, int in_cs, __half* __restrict__ out, int out_cs) {
+__global__ void depth_to_space2_half_kernel(const __half* __restrict__ in, int N, int h, int w, int C, int in_cs, __half* __restrict__ out, int out_cs,
+                                            int in_lo, int out_lo) {
   const int cgs = C / 8, Ho = 2 * h, Wo = 2 * w;
   const long long total = (long long)N * Ho * Wo * cgs;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -1200,6 +1263,9 @@ __global__ void depth_to_space2_half_kernel(const __half* __restrict__ in, int N
     const int ph = (oy & 1) * 2 + (ox & 1);
     *reinterpret_cast<uint4*>(out + pix * out_cs + cg * 8) =
         __ldg(reinterpret_cast<const uint4*>(in + ((long long)(n * h + (oy >> 1)) * w + (ox >> 1)) * in_cs + ph * C + cg * 8));
+    if (in_lo)
+      *reinterpret_cast<uint4*>(out + pix * out_cs + out_lo + cg * 8) =
+          __ldg(reinterpret_cast<const uint4*>(in + ((long long)(n * h + (oy >> 1)) * w + (ox >> 1)) * in_cs + in_lo + ph * C + cg * 8));
   }
 }
 
@@ -1269,12 +1335,12 @@ __global__ void boundary_blend_kernel(const float* __restrict__ logits, const fl
 }
 
 // NHWC fp16 slice -> NCHW fp32 (aux outputs: shared_features, fg_attention)
-__global__ void nhwc_half_to_nchw_float_kernel(const __half* __restrict__ in, int N, int HW, int C, int cs, float* __restrict__ out) {
+__global__ void nhwc_half_to_nchw_float_kernel(const __half* __restrict__ in, int N, int HW, int C, int cs, int lo, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (p < HW && c < C) ? __half2float(in[((long long)n * HW + p) * cs + c]) : 0.0f;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? his_ld1(in + ((long long)n * HW + p) * cs + c, lo) : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -1302,7 +1368,7 @@ __global__ void input_affine_kernel(const unsigned int* __restrict__ flag, float
 // Stem input for the tensor cores: normalise (x*a[c]+b[c]) and space-to-depth the NCHW fp32 image into NHWC fp16
 // [N, H/2, W/2, 16] with channel (sy*2+sx)*3 + c (12 used, 4 zero).  A 3x3 stride-2 pad-1 conv over the image is then a 2x2
 // stride-1 conv over this tensor (taps (-1,-1),(-1,0),(0,-1),(0,0)), which the halo-mode GEMM runs as a 3x3 with five zero taps.
-__global__ void s2d_input_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ affine, __half* __restrict__ out) {
+__global__ void s2d_input_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ affine, __half* __restrict__ out, int split) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo;
   const float a0 = affine[0], a1 = affine[1], a2 = affine[2], b0 = affine[3], b1 = affine[4], b2 = affine[5];
@@ -1310,19 +1376,20 @@ __global__ void s2d_input_kernel(const float* __restrict__ img, int N, int H, in
     const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho);
     const long long n = idx / ((long long)Wo * Ho);
     const float* p0 = img + (n * 3) * (long long)H * W + (long long)(2 * oy) * W + 2 * ox;
-    __half v[16];
+    float v[16];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const float* q = p0 + (s >> 1) * W + (s & 1);
-      v[s * 3 + 0] = __float2half_rn(fmaf(__ldg(q), a0, b0));
-      v[s * 3 + 1] = __float2half_rn(fmaf(__ldg(q + (long long)H * W), a1, b1));
-      v[s * 3 + 2] = __float2half_rn(fmaf(__ldg(q + 2LL * H * W), a2, b2));
+      v[s * 3 + 0] = fmaf(__ldg(q), a0, b0);
+      v[s * 3 + 1] = fmaf(__ldg(q + (long long)H * W), a1, b1);
+      v[s * 3 + 2] = fmaf(__ldg(q + 2LL * H * W), a2, b2);
     }
 #pragma unroll
-    for (int e = 12; e < 16; ++e) v[e] = __float2half_rn(0.0f);
-    uint4* dst = reinterpret_cast<uint4*>(out + idx * 16);
-    dst[0] = *reinterpret_cast<const uint4*>(&v[0]);
-    dst[1] = *reinterpret_cast<const uint4*>(&v[8]);
+    for (int e = 12; e < 16; ++e) v[e] = 0.0f;
+    // split: pixel = [16 hi | 16 lo]
+    __half* dst = out + idx * (split ? 32 : 16);
+    his_st8(dst, split ? 16 : 0, v);
+    his_st8(dst + 8, split ? 16 : 0, v + 8);
   }
 }
 
@@ -1352,37 +1419,50 @@ int his_set_error(int code, const char* msg) {
 
 #define ST ((cudaStream_t)stream)
 
+// One-time work per (call site, device): function attributes such as the dynamic shared memory opt-in are per device.
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 extern "C" {
 
 const char* his_last_error(void) { return g_err; }
 
-int his_version(void) { return 100; }
+int his_version(void) { return 200; }
 
 int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC, long long sH, long long sW, int B, int C, int H, int W,
                   const float* rois, int n_rois, int oh, int ow, float scale_h, float scale_w, int aligned, void* out_half, int out_cs,
-                  float* out_f32, void* stream) {
+                  float* out_f32, int split, void* stream) {
   if (n_rois == 0) return HIS_OK;
   if (!feat || (!out_half && !out_f32) || !rois) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: null pointer");
   if (oh <= 0 || ow <= 0 || C <= 0) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align: bad shape");
   const long long total = (long long)n_rois * oh * ow;
   if (feat_is_half)
     roi_align_kernel<__half><<<grid_for(total), kThreads, 0, ST>>>((const __half*)feat, sN, sC, sH, sW, B, C, H, W, rois, n_rois, oh, ow,
-                                                                  scale_h, scale_w, aligned, (__half*)out_half, out_cs, out_f32);
+                                                                  scale_h, scale_w, aligned, (__half*)out_half, out_cs, split ? out_cs / 2 : 0, out_f32);
   else
     roi_align_kernel<float><<<grid_for(total), kThreads, 0, ST>>>((const float*)feat, sN, sC, sH, sW, B, C, H, W, rois, n_rois, oh, ow,
-                                                                 scale_h, scale_w, aligned, (__half*)out_half, out_cs, out_f32);
+                                                                 scale_h, scale_w, aligned, (__half*)out_half, out_cs, split ? out_cs / 2 : 0, out_f32);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
 int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, int H, int W, int cin, int in_cs, const void* w,
                     const float* scale, const float* shift, int cout, int kh, int kw, int stride, int pad, int act, float act_beta,
-                    int res_mode, const void* res, int res_cs, void* out_half, int out_cs, float* out_f32, void* stream) {
+                    int res_mode, const void* res, int res_cs, void* out_half, int out_cs, float* out_f32, int split, void* stream) {
   if (!in || !w || !scale || !shift || (!out_half && !out_f32)) return his_set_error(HIS_ERR_INVALID_ARG, "conv_direct: null pointer");
   if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "conv_direct: res_mode without residual");
   DirectConvParams p;
   p.in = in; p.in_fmt = in_fmt; p.in_affine = in_affine; p.N = N; p.H = H; p.W = W; p.Cin = cin; p.in_cs = in_cs;
-  p.w = (const __half*)w; p.scale = scale; p.shift = shift; p.Cout = cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
+  p.w = w; p.w_f32 = split ? 1 : 0; p.in_lo = (split && in_fmt == 0) ? in_cs / 2 : 0; p.res_lo = split ? res_cs / 2 : 0;
+  p.out_lo = split ? out_cs / 2 : 0; p.scale = scale; p.shift = shift; p.Cout = cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
   p.Ho = (H + 2 * pad - kh) / stride + 1; p.Wo = (W + 2 * pad - kw) / stride + 1;
   p.act = act; p.act_beta = act_beta; p.res_mode = res_mode; p.res = (const __half*)res; p.res_cs = res_cs;
   p.out_h = (__half*)out_half; p.out_cs = out_cs; p.out_f = out_f32;
@@ -1468,7 +1548,7 @@ int his_pool_sum_parts(int N, int HW, int C) {
 }
 
 int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale, const float* shift, int k,
-                       int stride, int act, void* out, int out_cs, float* pool_sums, void* stream) {
+                       int stride, int act, void* out, int out_cs, float* pool_sums, int split, void* stream) {
   if (!in || !w || !scale || !shift || !out) return his_set_error(HIS_ERR_INVALID_ARG, "depthwise: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: channels must be multiples of 8");
   if (N == 0) return HIS_OK;
@@ -1480,6 +1560,28 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   p.k = k; p.stride = stride; p.pad = ((stride - 1) + (k - 1)) / 2; p.Ho = (H + 2 * p.pad - k) / stride + 1; p.Wo = (W + 2 * p.pad - k) / stride + 1;
   p.act = act; p.out = (__half*)out; p.out_cs = out_cs; p.pool = pool_sums;
   if ((long long)p.Ho * p.Wo * (C / 4) >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise: image too large");
+  if (split) {      // split-fp16 activations, fp32 taps (w = [k*k][C] float): the tiled kernel's geometry, operands from global memory
+    if (!dw_use_tiled() || N > 65535 || (in_cs % 16) || (out_cs % 16)) return his_set_error(HIS_ERR_UNSUPPORTED, "depthwise (split): unsupported configuration");
+    const int xpt = dw2_xpt(p.Wo, stride), tow = kDw2Strips * xpt;
+    const int tiles_x = (p.Wo + tow - 1) / tow, tiles_y = (p.Ho + kDw2Rows - 1) / kDw2Rows;
+    dim3 g2(tiles_x * tiles_y, (C + kDw2Cb - 1) / kDw2Cb, N);
+    const float* w32 = (const float*)w;
+    const int il = in_cs / 2, ol = out_cs / 2;
+#define DWS_LAUNCH(K_, S_, X_)                                                                                            \
+  do {                                                                                                                    \
+    if (act == HIS_ACT_SILU) depthwise_split_kernel<K_, S_, X_, HIS_ACT_SILU><<<g2, kDw2Threads, 0, ST>>>(p, tiles_x, w32, il, ol); \
+    else depthwise_split_kernel<K_, S_, X_, HIS_ACT_NONE><<<g2, kDw2Threads, 0, ST>>>(p, tiles_x, w32, il, ol);             \
+  } while (0)
+    if (k == 3 && stride == 1 && xpt == 4) DWS_LAUNCH(3, 1, 4);
+    else if (k == 3 && stride == 1) DWS_LAUNCH(3, 1, 2);
+    else if (k == 5 && stride == 1 && xpt == 4) DWS_LAUNCH(5, 1, 4);
+    else if (k == 5 && stride == 1) DWS_LAUNCH(5, 1, 2);
+    else if (k == 3) DWS_LAUNCH(3, 2, 2);
+    else DWS_LAUNCH(5, 2, 2);
+#undef DWS_LAUNCH
+    HIS_CHECK_LAUNCH();
+    return HIS_OK;
+  }
   if (dw_use_tiled() && N <= 65535) {
     const int xpt = dw2_xpt(p.Wo, stride), tow = kDw2Strips * xpt;
     const int tiles_x = (p.Wo + tow - 1) / tow, tiles_y = (p.Ho + kDw2Rows - 1) / kDw2Rows;
@@ -1488,12 +1590,12 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   do {                                                                                                                           \
     constexpr int smem = Dw2Cfg<K_, S_, X_>::kSmem;                                                                              \
     if (act == HIS_ACT_SILU) {                                                                                                   \
-      static bool attr_a = false;                                                                                                \
-      if (!attr_a) { cudaFuncSetAttribute(depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_a = true; } \
+      static PerDeviceOnce attr_a;                                                                                               \
+      if (attr_a.first()) cudaFuncSetAttribute(depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
       depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_SILU><<<g2, kDw2Threads, smem, ST>>>(p, tiles_x);                               \
     } else {                                                                                                                     \
-      static bool attr_b = false;                                                                                                \
-      if (!attr_b) { cudaFuncSetAttribute(depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_b = true; } \
+      static PerDeviceOnce attr_b;                                                                                               \
+      if (attr_b.first()) cudaFuncSetAttribute(depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
       depthwise_tiled_kernel<K_, S_, X_, HIS_ACT_NONE><<<g2, kDw2Threads, smem, ST>>>(p, tiles_x);                               \
     }                                                                                                                            \
   } while (0)
@@ -1523,7 +1625,7 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
   return HIS_OK;
 }
 
-int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, void* stream) {
+int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, int split, void* stream) {
   if (!in || !pool_sums) return his_set_error(HIS_ERR_INVALID_ARG, "pool_sum: null pointer");
   if (C % 8 || cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: channels must be multiples of 8");
   if (N == 0) return HIS_OK;
@@ -1532,7 +1634,7 @@ int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums,
   if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: more than 8192 channels");
   const int gx = pool_grid_x((per_img + 7) / 8, threads, N, 8, C / 8);
   dim3 grid(gx, N);
-  pool_sum_kernel<<<grid, threads, threads * 8 * sizeof(float), ST>>>((const __half*)in, HW, C, cs, pool_sums);
+  pool_sum_kernel<<<grid, threads, threads * 8 * sizeof(float), ST>>>((const __half*)in, HW, C, cs, split ? cs / 2 : 0, pool_sums);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1550,9 +1652,17 @@ int his_se_gate(float* pool_sums, int nparts, int N, int HW, int C, int R, const
   return HIS_OK;
 }
 
-int his_scale_weights(const void* w_packed, const float* gate, int N, long long rows, int K, int C, void* out, void* stream) {
+int his_scale_weights(const void* w_packed, const float* gate, int N, long long rows, int K, int C, void* out, int split, void* stream) {
   if (!w_packed || !gate || !out) return his_set_error(HIS_ERR_INVALID_ARG, "scale_weights: null pointer");
   if (K % 8 || C > K) return his_set_error(HIS_ERR_INVALID_ARG, "scale_weights: K must be a multiple of 8 and >= C");
+  if (split) {      // rows are [W_hi | W_lo], K/2 elements each
+    if (K % 16 || C > K / 2) return his_set_error(HIS_ERR_INVALID_ARG, "scale_weights (split): K must be a multiple of 16 and >= 2*C");
+    const long long tot = (long long)N * rows * (K / 16);
+    if (tot == 0) return HIS_OK;
+    scale_weights_split_kernel<<<grid_for(tot), kThreads, 0, ST>>>((const __half*)w_packed, gate, rows, K / 2, C, tot, (__half*)out);
+    HIS_CHECK_LAUNCH();
+    return HIS_OK;
+  }
   const long long total = (long long)N * rows * (K / 8);
   if (total == 0) return HIS_OK;
   scale_weights_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)w_packed, gate, rows, K, C, total, (__half*)out);
@@ -1560,12 +1670,13 @@ int his_scale_weights(const void* w_packed, const float* gate, int N, long long 
   return HIS_OK;
 }
 
-int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream) {
+int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, int split, void* stream) {
   if (!in || !gate || !out) return his_set_error(HIS_ERR_INVALID_ARG, "scale_channels: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "scale_channels: channels must be multiples of 8");
   const long long total = (long long)N * HW * (C / 8);
   if (total == 0) return HIS_OK;
-  scale_channels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, gate, HW, C, total, (__half*)out, out_cs);
+  scale_channels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, gate, HW, C, total, (__half*)out, out_cs,
+                                                              split ? in_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1578,7 +1689,8 @@ int his_layernorm2d_parts(int N, int HW, int C) {
 }
 
 int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps, int act,
-                        float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws, void* out, int out_cs, void* stream) {
+                        float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws, void* out, int out_cs, int split,
+                        void* stream) {
   if (!in || !gamma || !beta || !partials_ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "layernorm2d: null pointer");
   if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "layernorm2d: res_mode without residual");
   if (C % 8 || in_cs % 8 || out_cs % 8 || (res_mode && res_cs % 8)) return his_set_error(HIS_ERR_UNSUPPORTED, "layernorm2d: channels must be multiples of 8");
@@ -1586,13 +1698,14 @@ int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const f
   const int parts = his_layernorm2d_parts(N, HW, C);
   const long long per_img_vec = (long long)HW * (C / 8);
   dim3 g1(parts, N);
-  ln_stats_kernel<<<g1, kThreads, 0, ST>>>((const __half*)in, per_img_vec, HW, C, in_cs, partials_ws);
+  ln_stats_kernel<<<g1, kThreads, 0, ST>>>((const __half*)in, per_img_vec, HW, C, in_cs, split ? in_cs / 2 : 0, partials_ws);
   long long gx = (per_img_vec + kThreads - 1) / kThreads;
   const long long cap = (148LL * 16 + N - 1) / N;
   if (gx > cap) gx = cap;
   dim3 g2((int)(gx < 1 ? 1 : gx), N);
   ln_apply_kernel<<<g2, kThreads, 0, ST>>>((const __half*)in, HW, C, in_cs, partials_ws, parts, gamma, beta, eps, act, act_beta, res_mode,
-                                          (const __half*)res, res_cs, (__half*)out, out_cs);
+                                          (const __half*)res, res_cs, (__half*)out, out_cs, split ? in_cs / 2 : 0, split ? res_cs / 2 : 0,
+                                          split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1605,7 +1718,7 @@ int his_groupnorm_parts(int N, int HW, int C) {
 }
 
 int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int groups, const float* gamma, const float* beta, float eps, int act,
-                      float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, void* stream) {
+                      float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, int split, void* stream) {
   if (!in || !gamma || !beta || !ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "groupnorm: null pointer");
   if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "groupnorm: res_mode without residual");
   if (C % 8 || in_cs % 8 || out_cs % 8 || (res_mode && res_cs % 8)) return his_set_error(HIS_ERR_UNSUPPORTED, "groupnorm: channels must be multiples of 8");
@@ -1615,60 +1728,62 @@ int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int group
   const int parts = his_groupnorm_parts(N, HW, C);
   const int ppp = (HW + parts - 1) / parts;
   const int cgs = C / 8, PL = kThreads / cgs;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_done = true;
-  }
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const size_t sm1 = (size_t)PL * C * 2 * sizeof(float);      // <= 256/cgs * 8*cgs * 8 B = 16 KB
-  gn_stats_kernel<<<dim3(parts, N), kThreads, sm1, ST>>>((const __half*)in, HW, C, in_cs, ppp, parts + 1, ws);
+  gn_stats_kernel<<<dim3(parts, N), kThreads, sm1, ST>>>((const __half*)in, HW, C, in_cs, split ? in_cs / 2 : 0, ppp, parts + 1, ws);
   gn_finalize_kernel<<<dim3((groups + 127) / 128, N), 128, 0, ST>>>(ws, HW, C, groups, parts, eps);
   const long long per_img_vec = (long long)HW * cgs;
   long long gx = (per_img_vec + kThreads - 1) / kThreads;
   const long long cap = (148LL * 16 + N - 1) / N;
   if (gx > cap) gx = cap;
   gn_apply_kernel<<<dim3((int)(gx < 1 ? 1 : gx), N), kThreads, (size_t)C * 2 * sizeof(float), ST>>>(
-      (const __half*)in, HW, C, in_cs, ws, parts, gamma, beta, act, act_beta, res_mode, (const __half*)res, res_cs, (__half*)out, out_cs);
+      (const __half*)in, HW, C, in_cs, ws, parts, gamma, beta, act, act_beta, res_mode, (const __half*)res, res_cs, (__half*)out, out_cs,
+      split ? in_cs / 2 : 0, split ? res_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
 int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const float* wt, const float* bias, int cout, void* out, int out_cs,
-                       void* stream) {
+                       int split, void* stream) {
   if (!in || !wt || !out) return his_set_error(HIS_ERR_INVALID_ARG, "convT2x2_small: null pointer");
   const long long total = (long long)N * 4 * h * w * cout;
   if (total == 0) return HIS_OK;
-  convT2x2_small_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, N, cin, h, w, wt, bias, cout, (__half*)out, out_cs);
+  convT2x2_small_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, N, cin, h, w, wt, bias, cout, (__half*)out, out_cs, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
-int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, void* stream) {
+int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, int split, void* stream) {
   if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "maxpool2: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "maxpool2: channels must be multiples of 8");
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
   if (total == 0) return HIS_OK;
-  maxpool2_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, (__half*)out, out_cs);
+  maxpool2_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, (__half*)out, out_cs, split ? in_cs / 2 : 0,
+                                                        split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
-int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream) {
+int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, int split, void* stream) {
   if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "resize_nearest: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "resize_nearest: channels must be multiples of 8");
   const long long total = (long long)N * Ho * Wo * (C / 8);
   if (total == 0) return HIS_OK;
-  resize_nearest_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs);
+  resize_nearest_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs,
+                                                              split ? in_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
-int his_resize_bilinear_half(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream) {
+int his_resize_bilinear_half(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, int split,
+                             void* stream) {
   if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "resize_bilinear_half: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "resize_bilinear_half: channels must be multiples of 8");
   const long long total = (long long)N * Ho * Wo * (C / 8);
   if (total == 0) return HIS_OK;
-  resize_bilinear_half_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs);
+  resize_bilinear_half_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, Ho, Wo, (__half*)out, out_cs,
+                                                                    split ? in_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1683,15 +1798,16 @@ int his_resize_bilinear_f32(const float* in, int NC, int H, int W, int Ho, int W
 }
 
 int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs, const float* w, int k, float* stats_ws, void* out,
-                          int out_cs, void* stream) {
+                          int out_cs, int split, void* stream) {
   if (!in || !w || !stats_ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "spatial_attention: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "spatial_attention: channels must be multiples of 8");
   const long long pixels = (long long)N * H * W;
   if (pixels == 0) return HIS_OK;
-  channel_stats_kernel<<<grid_for(pixels * 32), kThreads, 0, ST>>>((const __half*)in, pixels, C, in_cs, stats_ws);
+  channel_stats_kernel<<<grid_for(pixels * 32), kThreads, 0, ST>>>((const __half*)in, pixels, C, in_cs, split ? in_cs / 2 : 0, stats_ws);
   HIS_CHECK_LAUNCH();
   spatial_attention_apply_kernel<<<grid_for(pixels * 32), kThreads, 0, ST>>>((const __half*)in, N, H, W, C, in_cs, stats_ws, w, k,
-                                                                            (__half*)out, out_cs);
+                                                                            (__half*)out, out_cs, split ? in_cs / 2 : 0,
+                                                                            split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1732,23 +1848,24 @@ int his_map_f32(const float* in, long long total, int op, const float* param, fl
   return HIS_OK;
 }
 
-int his_sigmoid_channel(const float* in, int N, int C, int HW, int c, void* out_half, int out_cs, float* out_f32, void* stream) {
+int his_sigmoid_channel(const float* in, int N, int C, int HW, int c, void* out_half, int out_cs, float* out_f32, int split, void* stream) {
   if (!in || (!out_half && !out_f32)) return his_set_error(HIS_ERR_INVALID_ARG, "sigmoid_channel: null pointer");
   if (c < 0 || c >= C) return his_set_error(HIS_ERR_INVALID_ARG, "sigmoid_channel: channel out of range");
   const long long total = (long long)N * HW;
   if (total == 0) return HIS_OK;
-  sigmoid_channel_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, C, HW, c, total, (__half*)out_half, out_cs, out_f32);
+  sigmoid_channel_kernel<<<grid_for(total), kThreads, 0, ST>>>(in, C, HW, c, total, (__half*)out_half, out_cs, split ? out_cs / 2 : 0, out_f32);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
 
 int his_scale_pixels(const void* in, int in_cs, const float* attention, const float* fg_prob, long long pixels, int C, void* out, int out_cs,
-                     void* stream) {
+                     int split, void* stream) {
   if (!in || !attention || !fg_prob || !out) return his_set_error(HIS_ERR_INVALID_ARG, "scale_pixels: null pointer");
   if (C % 8 || in_cs % 8 || out_cs % 8) return his_set_error(HIS_ERR_UNSUPPORTED, "scale_pixels: channels must be multiples of 8");
   const long long total = pixels * (C / 8);
   if (total == 0) return HIS_OK;
-  scale_pixels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, attention, fg_prob, C, total, (__half*)out, out_cs);
+  scale_pixels_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, in_cs, attention, fg_prob, C, total, (__half*)out, out_cs,
+                                                            split ? in_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1764,12 +1881,13 @@ int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, i
   return HIS_OK;
 }
 
-int his_depth_to_space2_half(const void* in, int N, int h, int w, int C, int in_cs, void* out, int out_cs, void* stream) {
+int his_depth_to_space2_half(const void* in, int N, int h, int w, int C, int in_cs, void* out, int out_cs, int split, void* stream) {
   if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "depth_to_space2: null pointer");
-  if (C % 8 || in_cs % 8 || out_cs % 8 || in_cs < 4 * C) return his_set_error(HIS_ERR_UNSUPPORTED, "depth_to_space2: channels must be multiples of 8, in_cs >= 4*C");
+  if (C % 8 || in_cs % 8 || out_cs % 8 || (split ? in_cs / 2 : in_cs) < 4 * C) return his_set_error(HIS_ERR_UNSUPPORTED, "depth_to_space2: channels must be multiples of 8, in_cs >= 4*C");
   const long long total = (long long)N * 4 * h * w * (C / 8);
   if (total == 0) return HIS_OK;
-  depth_to_space2_half_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, h, w, C, in_cs, (__half*)out, out_cs);
+  depth_to_space2_half_kernel<<<grid_for(total), kThreads, 0, ST>>>((const __half*)in, N, h, w, C, in_cs, (__half*)out, out_cs,
+                                                                    split ? in_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1804,11 +1922,11 @@ int his_boundary_blend(const float* logits, const float* correction, const float
   return HIS_OK;
 }
 
-int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, void* stream) {
+int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, int split, void* stream) {
   if (!in || !out) return his_set_error(HIS_ERR_INVALID_ARG, "layout: null pointer");
   if (N == 0) return HIS_OK;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  nhwc_half_to_nchw_float_kernel<<<grid, block, 0, ST>>>((const __half*)in, N, HW, C, cs, out);
+  nhwc_half_to_nchw_float_kernel<<<grid, block, 0, ST>>>((const __half*)in, N, HW, C, cs, split ? cs / 2 : 0, out);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -1823,12 +1941,12 @@ int his_unet_input_affine(const float* images, long long count, const float* mea
   return HIS_OK;
 }
 
-int his_s2d_input(const float* images, int N, int H, int W, const float* affine6, void* out_half, void* stream) {
+int his_s2d_input(const float* images, int N, int H, int W, const float* affine6, void* out_half, int split, void* stream) {
   if (!images || !affine6 || !out_half) return his_set_error(HIS_ERR_INVALID_ARG, "s2d_input: null pointer");
   if ((H & 1) || (W & 1)) return his_set_error(HIS_ERR_UNSUPPORTED, "s2d_input: H and W must be even");
   const long long total = (long long)N * (H >> 1) * (W >> 1);
   if (total == 0) return HIS_OK;
-  s2d_input_kernel<<<grid_for(total), kThreads, 0, ST>>>(images, N, H, W, affine6, (__half*)out_half);
+  s2d_input_kernel<<<grid_for(total), kThreads, 0, ST>>>(images, N, H, W, affine6, (__half*)out_half, split ? 1 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -24,28 +24,55 @@ def round_up(x: int, m: int) -> int:
 
 
 class Act:
-    """A channel slice [c_off, c_off+C) of an NHWC fp16 buffer [N,H,W,cs]."""
+    """A channel slice [c_off, c_off+C) of an NHWC fp16 buffer [N,H,W,cs].
 
-    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off", "zero_tail")
+    ``split`` (the "strict" precision mode): every value is a pair of fp16 numbers x = hi + lo stored [hi channels | lo channels]
+    inside one pixel -- the buffer is [N,H,W,cs] with the hi planes in [0, cs/2) and the lo plane of a channel cs/2 elements
+    after its hi plane; ``cs`` stays the pixel stride the kernels are given."""
 
-    def __init__(self, buf: torch.Tensor, C: int, c_off: int = 0):
+    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off", "zero_tail", "split")
+
+    def __init__(self, buf: torch.Tensor, C: int, c_off: int = 0, split: bool = False):
         assert buf.dtype == torch.float16 and buf.dim() == 4 and buf.is_contiguous()
         self.buf = buf
         self.N, self.H, self.W, self.cs = buf.shape
         self.C, self.c_off = C, c_off
+        self.split = bool(split)
         self.zero_tail = False          # True: channels [C, cs) are zero and nobody ever writes them (see Plan.act_zeroed)
-        assert c_off % 8 == 0 and self.cs % 8 == 0 and c_off + C <= self.cs
+        assert c_off % 8 == 0 and self.cs % (16 if split else 8) == 0 and c_off + C <= self.width
+
+    @property
+    def width(self) -> int:
+        """Channel capacity of the buffer (per plane)."""
+        return self.cs // 2 if self.split else self.cs
 
     @property
     def ptr(self) -> int:
         return self.buf.data_ptr() + 2 * self.c_off
 
     def slice(self, c_off: int, C: int) -> "Act":
-        return Act(self.buf, C, self.c_off + c_off)
+        return Act(self.buf, C, self.c_off + c_off, self.split)
+
+    def widen(self, C: int) -> "Act":
+        """The first C channels of the underlying buffer (a concat buffer read as one tensor)."""
+        return Act(self.buf, C, 0, self.split)
+
+    def fill_nhwc(self, t: torch.Tensor):
+        """Debug / test helper: writes fp32 values [N,H,W,C] into the slice (hi = fp16(t), lo = fp16(t - hi) when split)."""
+        t = t.to(self.buf.device, torch.float32)
+        hi = t.half()
+        self.buf[..., self.c_off:self.c_off + self.C] = hi
+        if self.split:
+            lo = self.cs // 2
+            self.buf[..., lo + self.c_off:lo + self.c_off + self.C] = (t - hi.float()).half()
 
     def torch_nchw(self) -> torch.Tensor:
         """Debug view (fp32 NCHW copy through torch) -- tests only."""
-        return self.buf[..., self.c_off:self.c_off + self.C].permute(0, 3, 1, 2).float().contiguous()
+        v = self.buf[..., self.c_off:self.c_off + self.C].float()
+        if self.split:
+            lo = self.cs // 2
+            v = v + self.buf[..., lo + self.c_off:lo + self.c_off + self.C].float()
+        return v.permute(0, 3, 1, 2).contiguous()
 
 
 class NullAct(Act):
@@ -53,13 +80,15 @@ class NullAct(Act):
 
     def __init__(self, buf: torch.Tensor, N: int, H: int, W: int, C: int):
         self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
-        self.cs, self.c_off = round_up(C, 8), 0
+        self.cs, self.c_off = round_up(C, 16), 0
         self.zero_tail = False
+        self.split = False
 
 
 class Plan:
-    def __init__(self, device: torch.device):
+    def __init__(self, device: torch.device, split: bool = False):
         self.device = device
+        self.split = bool(split)            # split-fp16 ("strict" precision) activations and weights
         self.lib = _lib.load()
         self.ops: List[Tuple] = []          # (name, cfunc, args-without-stream)
         self.keep: List[object] = []        # tensors / gemm plans the ops point into
@@ -77,15 +106,15 @@ class Plan:
     # -------------------------------------------------------------- allocation
     def act(self, N, H, W, C, cs=None) -> Act:
         cs = cs or round_up(C, 8)
-        buf = torch.empty((N, H, W, cs), dtype=torch.float16, device=self.device)
+        buf = torch.empty((N, H, W, cs * (2 if self.split else 1)), dtype=torch.float16, device=self.device)
         self.keep.append(buf)
-        return Act(buf, C)
+        return Act(buf, C, 0, self.split)
 
     def act_zeroed(self, N, H, W, C) -> Act:
         """Activation whose channel tail [C, cs) is zero for the plan's lifetime: producers write exactly C channels."""
-        buf = torch.zeros((N, H, W, round_up(C, 8)), dtype=torch.float16, device=self.device)
+        buf = torch.zeros((N, H, W, round_up(C, 8) * (2 if self.split else 1)), dtype=torch.float16, device=self.device)
         self.keep.append(buf)
-        a = Act(buf, C)
+        a = Act(buf, C, 0, self.split)
         a.zero_tail = True
         return a
 
@@ -140,7 +169,7 @@ class Plan:
         _lib.check(L.his_conv_gemm_create(ctypes.byref(h), x.ptr, x.N, x.H, x.W, x.C, x.cs, w_packed.data_ptr(), cin_pad,
                                           out.ptr, out.C, out.cs, res.ptr if res is not None else None,
                                           res.cs if res is not None else 0, shift.data_ptr(), ksize,
-                                          1 if transposed else 0, act, beta, res_mode), "his_conv_gemm_create")
+                                          1 if transposed else 0, act, beta, res_mode, 1 if self.split else 0), "his_conv_gemm_create")
         self.gemm_plans.append(h)
         self.keep += [w_packed, shift]
         taps = 4 if transposed else ksize * ksize
@@ -170,7 +199,8 @@ class Plan:
             rows = w_packed.numel() // cin_pad
             assert wimg.dtype == torch.float16 and wimg.numel() >= x.N * rows * cin_pad
             _lib.check(L.his_conv_gemm_set_image_weights(h, wimg.data_ptr()), "his_conv_gemm_set_image_weights")
-            self.add("scale_weights", L.his_scale_weights, w_packed.data_ptr(), gate.data_ptr(), x.N, rows, cin_pad, x.C, wimg.data_ptr())
+            self.add("scale_weights", L.his_scale_weights, w_packed.data_ptr(), gate.data_ptr(), x.N, rows, cin_pad, x.C, wimg.data_ptr(),
+                     1 if self.split else 0)
             self.keep += [gate, wimg]
         self._add_flops(f, True)
         self.add("conv_gemm", L.his_conv_gemm_run, h, flops=f,
@@ -191,7 +221,7 @@ class Plan:
                  cin, in_cs, w.data_ptr(), scale.data_ptr(), shift.data_ptr(), cout, k, k, stride, pad, act, beta, res_mode,
                  res.ptr if res is not None else None, res.cs if res is not None else 0,
                  out.ptr if out is not None else None, out.cs if out is not None else 0,
-                 out_f32.data_ptr() if out_f32 is not None else None, flops=fd,
+                 out_f32.data_ptr() if out_f32 is not None else None, 1 if self.split else 0, flops=fd,
                  desc=f"N{N} {H}x{W} cin{cin} cout{cout} k{k} s{stride} fmt{in_fmt}")
 
     # -------------------------------------------------------------- execution
@@ -263,10 +293,17 @@ def pad_vec(v: torch.Tensor, n: int) -> torch.Tensor:
     return out
 
 
-def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False, scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, int]:
+def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False, scale: Optional[torch.Tensor] = None,
+                     split: bool = False) -> Tuple[torch.Tensor, int]:
     """Conv2d weight [Cout,Cin,kh,kw] -> fp16 [1][taps][cout_slab][cin_pad];
     ConvTranspose2d(k2,s2) weight [Cin,Cout,2,2] -> fp16 [4 groups (dy,dx)][1][cout_slab][cin_pad].
-    ``scale`` [Cout] (the folded BatchNorm scale) multiplies the fp32 weights per output channel before the fp16 rounding."""
+    ``scale`` [Cout] (the folded BatchNorm scale) multiplies the fp32 weights per output channel before the fp16 rounding.
+    ``split``: rows become [W_hi | W_lo] (W_hi = fp16(w), W_lo = fp16(w - W_hi)); the returned cin_pad counts both halves."""
+    if split:
+        hi, k1 = pack_gemm_weight(w, cout_slab, transposed, scale)
+        full = _packed_f32(w, cout_slab, transposed, scale, k1)
+        lo = (full - hi.float()).half()
+        return torch.cat([hi, lo], dim=-1).contiguous(), 2 * k1
     w = w.detach().float().cpu()
     if scale is not None:
         sc = scale.detach().float().cpu()
@@ -290,6 +327,26 @@ def pack_gemm_weight(w: torch.Tensor, cout_slab: int, transposed: bool = False, 
     return out.contiguous(), cin_pad
 
 
-def pack_direct_weight(w: torch.Tensor) -> torch.Tensor:
-    """[Cout,Cin,kh,kw] -> fp16 [kh][kw][Cin][Cout]."""
-    return w.detach().float().cpu().permute(2, 3, 1, 0).contiguous().half()
+def _packed_f32(w: torch.Tensor, cout_slab: int, transposed: bool, scale: Optional[torch.Tensor], cin_pad: int) -> torch.Tensor:
+    """The packed layout of ``pack_gemm_weight`` in fp32 (before any rounding)."""
+    w = w.detach().float().cpu()
+    if scale is not None:
+        sc = scale.detach().float().cpu()
+        w = w * (sc.view(1, -1, 1, 1) if transposed else sc.view(-1, 1, 1, 1))
+    if transposed:
+        cin, cout = w.shape[0], w.shape[1]
+        out = torch.zeros(4, 1, cout_slab, cin_pad)
+        for dy in range(2):
+            for dx in range(2):
+                out[dy * 2 + dx, 0, :cout, :cin] = w[:, :, dy, dx].t()
+        return out
+    cout, cin, kh, kw = w.shape
+    out = torch.zeros(1, kh * kw, cout_slab, cin_pad)
+    out[0, :, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    return out
+
+
+def pack_direct_weight(w: torch.Tensor, f32: bool = False) -> torch.Tensor:
+    """[Cout,Cin,kh,kw] -> [kh][kw][Cin][Cout], fp16 (fp32 for the split-fp16 "strict" mode)."""
+    t = w.detach().float().cpu().permute(2, 3, 1, 0).contiguous()
+    return t if f32 else t.half()

@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_uint, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhis_b200.so")
-SOURCES = ["kernels.cu", "conv_gemm_sm100.cu", "post.cu", "post_stencil.cu"]
+SOURCES = ["kernels.cu", "conv_gemm_sm100.cu", "conv_gemm_sm100_split.cu", "post.cu", "post_stencil.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -22,14 +22,33 @@ class HisError(RuntimeError):
     pass
 
 
+ABI_VERSION = 200          # his_version() of the library this binding was written against (csrc/kernels.cu)
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "his_b200.h")
+
+
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive a snapshot copy to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    if os.path.exists(HEADER):
+        srcs.append(HEADER)
+    for f in srcs:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    for f in os.listdir(CSRC):
-        if f.endswith((".cu", ".cuh", ".h")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
-            return True
-    return False
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -60,6 +79,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise HisError(f"link failed:\n{r.stdout.decode(errors='replace')}")
+    with open(HASH_PATH, "w") as fh:
+        fh.write(_source_hash())
     return LIB_PATH
 
 
@@ -72,10 +93,10 @@ SIGNATURES = {
     "his_last_error": [],
     "his_version": [],
     "his_roi_align": [_P, c_int, _LL, _LL, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_float, c_float,
-                      c_int, _P, c_int, _P, _P],
+                      c_int, _P, c_int, _P, c_int, _P],
     "his_conv_gemm_tile_n": [c_int, POINTER(c_int), POINTER(c_int)],
     "his_conv_gemm_create": [POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int,
-                             _P, c_int, c_int, c_int, c_float, c_int],
+                             _P, c_int, c_int, c_int, c_float, c_int, c_int],
     "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
     "his_conv_gemm_set_aux": [_P, _P],
     "his_conv_gemm_set_row_ops": [_P, _P, _P],
@@ -87,38 +108,38 @@ SIGNATURES = {
     "his_conv_gemm_destroy": [_P],
     "his_conv_gemm_issued_macs": [_P],
     "his_conv_direct": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
-                        c_float, c_int, _P, c_int, _P, c_int, _P, _P],
-    "his_depthwise_conv": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, _P],
-    "his_pool_sum": [_P, c_int, c_int, c_int, c_int, _P, _P],
+                        c_float, c_int, _P, c_int, _P, c_int, _P, c_int, _P],
+    "his_depthwise_conv": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, _P, c_int, _P, c_int, _P],
+    "his_pool_sum": [_P, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "his_se_gate": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P, _P],
     "his_depthwise_pool_parts": [c_int, c_int, c_int, c_int, c_int, c_int],
     "his_pool_sum_parts": [c_int, c_int, c_int],
-    "his_scale_weights": [_P, _P, c_int, _LL, c_int, c_int, _P, _P],
-    "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P],
+    "his_scale_weights": [_P, _P, c_int, _LL, c_int, c_int, _P, c_int, _P],
+    "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "his_layernorm2d_parts": [c_int, c_int, c_int],
-    "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],
+    "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
     "his_groupnorm_parts": [c_int, c_int, c_int],
-    "his_groupnorm_act": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, _P],
-    "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P],
-    "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P],
+    "his_groupnorm_act": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
+    "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P],
+    "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
     "his_spatial_gate": [_P, c_int, c_int, c_int, _P, c_int, _P, _P],
-    "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
-    "his_resize_nearest": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
-    "his_resize_bilinear_half": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "his_maxpool2": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
+    "his_resize_nearest": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
+    "his_resize_bilinear_half": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "his_resize_bilinear_f32": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "his_upsample_bgfg": [_P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_float, _P, _P],
     "his_head_combine": [_P, _P, c_int, c_int, c_int, _P, _P],
     "his_map_f32": [_P, _LL, c_int, _P, _P, _P],
-    "his_depth_to_space2_half": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "his_depth_to_space2_half": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "his_pixel_shuffle2_f32": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "his_boundary_edges": [_P, c_int, c_int, c_int, _P, _P, _P],
     "his_boundary_blend": [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P],
-    "his_nhwc_half_to_nchw_float": [_P, c_int, c_int, c_int, c_int, _P, _P],
-    "his_sigmoid_channel": [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P],
-    "his_scale_pixels": [_P, c_int, _P, _P, _LL, c_int, _P, c_int, _P],
+    "his_nhwc_half_to_nchw_float": [_P, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "his_sigmoid_channel": [_P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P],
+    "his_scale_pixels": [_P, c_int, _P, _P, _LL, c_int, _P, c_int, c_int, _P],
     "his_guided_aux": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "his_unet_input_affine": [_P, _LL, _F, _F, _P, _P, _P],
-    "his_s2d_input": [_P, c_int, c_int, c_int, _P, _P, _P],
+    "his_s2d_input": [_P, c_int, c_int, c_int, _P, _P, c_int, _P],
     "his_unet_outputs": [_P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, _P, _P, _P],
     "his_memset_async": [_P, c_int, _LL, _P],
     # post-processing (csrc/post.cu)
@@ -155,14 +176,22 @@ def load():
     try:
         path = build()
     except HisError:
-        if os.path.exists(LIB_PATH):
-            path = LIB_PATH   # e.g. GPU box without a writable tree: use the shipped build
+        # A failed rebuild may only be papered over when the tree cannot be written at all (a read-only deployment that ships
+        # the built library); a stale library next to newer sources would be called with the wrong ABI.
+        if os.path.exists(LIB_PATH) and not os.access(_HERE, os.W_OK):
+            path = LIB_PATH
         else:
             raise
     try:
         lib = ctypes.CDLL(path)
     except OSError as e:
         raise HisError(f"cannot load {path}: {e}") from e
+    try:
+        ver = int(lib.his_version())
+    except AttributeError as e:
+        raise HisError(f"{path} does not export his_version") from e
+    if ver != ABI_VERSION:
+        raise HisError(f"{path} reports ABI version {ver}, this binding needs {ABI_VERSION}: rebuild (human_instance_segmentation_b200.build(force=True))")
     for name, argtypes in SIGNATURES.items():
         try:
             fn = getattr(lib, name)

@@ -86,6 +86,10 @@ class _PlannedModel(nn.Module):
 
     def _init_exec_state(self):
         self.aux_outputs = "full"        # "full" (reference dict) | "light" (no 256-channel tensors) | "none"
+        # "fast": fp16 operands / activations (11 significant bits, the tensor-core operand precision), documented bounds in
+        # DESIGN section 4.  "strict": split-fp16 operands (hi + lo planes, three MMA passes, ~21 bits) -- meets north_star's
+        # <= 1e-3 / >= 99.9 % against the reference's fp32 evaluation on any weights, at ~2.5x the time.
+        self.precision = "fast"
         self.copy_outputs = True         # return fresh tensors (False: views of the plan's static buffers)
         self.use_cuda_graph = False
         self.max_rois_per_pass = None    # None: derived from the ROI size (bounds the activation footprint)
@@ -138,7 +142,9 @@ class _PlannedModel(nn.Module):
         if dev.type != "cuda":
             raise _lib.HisError("move the model to a CUDA device first (model.to('cuda')); there is no CPU fallback")
         B, _, H, W = images.shape
-        key = (B, H, W, rois.shape[0], self.aux_outputs, self.max_rois_per_pass, self.max_images_per_pass,
+        if self.precision not in ("fast", "strict"):
+            raise ValueError(f"precision must be 'fast' or 'strict', got {self.precision!r}")
+        key = (B, H, W, rois.shape[0], self.aux_outputs, self.precision, self.max_rois_per_pass, self.max_images_per_pass,
                tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index, slot)
         bp = self._plans.get(key)
         if bp is None:
@@ -448,6 +454,8 @@ class _BuiltPlan:
 
     def __init__(self, m: HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet, dev, B, H, W, N):
         self.m, self.dev, self.B, self.H, self.W, self.N = m, dev, B, H, W, N
+        self.split = getattr(m, "precision", "fast") == "strict"
+        self.S = 1 if self.split else 0          # the `split` argument of the C entry points
         self.act_rgb = {"relu": ACT["relu"], "swish": ACT["silu"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
         self.act_ref = {"relu": ACT["relu"], "swish": ACT["swish"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
         self.beta = m.activation_beta
@@ -459,7 +467,7 @@ class _BuiltPlan:
         self.n_unet_chunks = (B + self.Bc - 1) // self.Bc if self.has_unet else 0
         self.n_head_chunks = (N + self.Nc - 1) // self.Nc if N else 0
         # ---- UNet sub-plan
-        self.unet_plan = self.plan = Plan(dev)
+        self.unet_plan = self.plan = Plan(dev, self.split)
         p = self.plan
         p.tag = "unet"
         self.images = p.f32(B, 3, H, W)
@@ -478,7 +486,7 @@ class _BuiltPlan:
         if m.aux_outputs != "none" and self.has_unet:
             self.aux["full_image_logits"] = self.two
         if N:
-            self.head_plan = self.plan = Plan(dev)
+            self.head_plan = self.plan = Plan(dev, self.split)
             self.plan.tag = "head"
             self.h_rois = self.plan.f32(self.Nc, 5, zero=True) if self.chunked_head else self.rois
             self.h_logits = self.plan.f32(self.Nc, 3, mh, mw) if self.chunked_head else self.logits
@@ -493,7 +501,7 @@ class _BuiltPlan:
         # ---- post sub-plan over ALL ROIs (the boundary refiner normalises its edge map over the whole batch tensor)
         self.post_plan = None
         if N and getattr(m, "use_boundary_refinement", False):
-            self.post_plan = self.plan = Plan(dev)
+            self.post_plan = self.plan = Plan(dev, self.split)
             self.plan.tag = "post"
             self._build_boundary_refiner()
         self.plan = _CompositePlan(self)
@@ -582,7 +590,7 @@ class _BuiltPlan:
             # Cin = 3 (RGB patches): the buffer's channel tail is zero by construction, so the layer runs on the tensor cores as a
             # Cin = 8 halo-mode GEMM with zero-padded weights (K = 16 per tap) instead of the CUDA-core direct kernel
             w = torch.cat([w.detach().float().cpu(), torch.zeros(cout, 8 - cin, k, k)], 1)
-            x = Act(x.buf, 8)
+            x = x.widen(8)
             cin, use_gemm = 8, True
         if out is None and out_f32 is None:
             out = p.null_act(x.N, oh, ow, cout) if (tail is not None and use_gemm) else p.act(x.N, oh, ow, cout)
@@ -590,7 +598,7 @@ class _BuiltPlan:
             nt, bn = ctypes.c_int(), ctypes.c_int()
             p.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
             slab = nt.value * bn.value
-            wp, cin_pad = pack_gemm_weight(w, slab, transposed, scale)
+            wp, cin_pad = pack_gemm_weight(w, slab, transposed, scale, split=self.split)
             tl = None
             if tail is not None:
                 tconv, tsig, tout = tail
@@ -606,9 +614,13 @@ class _BuiltPlan:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
             assert tail is None and aux_f32 is None and in_gate is None and row_scale is None and stats_out is None and res_scale is None
-            p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, p.const(pack_direct_weight(w), torch.float16), p.const(scale), p.const(shift),
+            p.conv_direct(x, 0, x.N, x.H, x.W, cin, x.cs, self.direct_w(w), p.const(scale), p.const(shift),
                           cout, k, 1, k // 2, act, self.beta, None, res, res_mode, out, out_f32)
         return out
+
+    def direct_w(self, w: torch.Tensor) -> torch.Tensor:
+        """Weights of the CUDA-core convolutions: fp16 [kh][kw][Cin][Cout], fp32 in strict mode."""
+        return self.plan.const(pack_direct_weight(w, f32=self.split), torch.float32 if self.split else torch.float16)
 
     def layernorm(self, x: Act, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
                   out: Optional[Act] = None) -> Act:
@@ -625,14 +637,14 @@ class _BuiltPlan:
             p.keep.append(ws)
             p.add("groupnorm", L.his_groupnorm_act, x.ptr, x.N, x.H * x.W, x.C, x.cs, int(groups), p.const(gamma.reshape(-1)).data_ptr(),
                   p.const(beta.reshape(-1)).data_ptr(), float(eps), act, self.beta, res_mode, res.ptr if res is not None else None,
-                  res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs)
+                  res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs, self.S)
             return out
         parts = L.his_layernorm2d_parts(x.N, x.H * x.W, x.C)
         ws = torch.empty((x.N, parts, 2), dtype=torch.float64, device=self.dev)
         p.keep.append(ws)
         p.add("layernorm2d", L.his_layernorm2d_act, x.ptr, x.N, x.H * x.W, x.C, x.cs, p.const(norm.weight.reshape(-1)).data_ptr(),
               p.const(norm.bias.reshape(-1)).data_ptr(), float(norm.eps), act, self.beta, res_mode, res.ptr if res is not None else None,
-              res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs)
+              res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs, self.S)
         return out
 
     def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None, aux_f32=None,
@@ -665,7 +677,7 @@ class _BuiltPlan:
                     getattr(bn4, name).copy_(getattr(norm, name).detach().float().cpu().repeat(4))
         wide = self.conv(x, conv4, bn4, act if bn4 is not None else ACT["none"])
         out = p.act(x.N, 2 * x.H, 2 * x.W, cout)
-        p.add("depth_to_space", L.his_depth_to_space2_half, wide.ptr, x.N, x.H, x.W, cout, wide.cs, out.ptr, out.cs)
+        p.add("depth_to_space", L.his_depth_to_space2_half, wide.ptr, x.N, x.H, x.W, cout, wide.cs, out.ptr, out.cs, self.S)
         if bn4 is None:
             out = self.layernorm(out, norm, act)
         return out
@@ -693,7 +705,7 @@ class _BuiltPlan:
 
     def export_nchw(self, x: Act) -> torch.Tensor:
         out = self.plan.f32(x.N, x.C, x.H, x.W)
-        self.plan.add("nhwc2nchw", self.plan.lib.his_nhwc_half_to_nchw_float, x.ptr, x.N, x.H * x.W, x.C, x.cs, out.data_ptr())
+        self.plan.add("nhwc2nchw", self.plan.lib.his_nhwc_half_to_nchw_float, x.ptr, x.N, x.H * x.W, x.C, x.cs, out.data_ptr(), self.S)
         return out
 
     # -------------------------------------------------------------- EfficientNet-UNet (full image)
@@ -738,7 +750,7 @@ class _BuiltPlan:
             # stem on the tensor cores: normalise + space-to-depth the image (one pass), then the 3x3 s2 conv is a 2x2 s1 conv over
             # [B, H/2, W/2, 16], run by the halo-mode GEMM as a 3x3 whose other five taps are zero
             s2d = p.act(B, H // 2, W // 2, 16)
-            p.add("s2d_input", L.his_s2d_input, self.u_images.data_ptr(), B, H, W, affine.data_ptr(), s2d.ptr)
+            p.add("s2d_input", L.his_s2d_input, self.u_images.data_ptr(), B, H, W, affine.data_ptr(), s2d.ptr, self.S)
             w = enc.conv_stem.weight.detach().float().cpu()                       # [stem_c, 3, 3, 3]
             w2 = torch.zeros(stem_c, 16, 3, 3)
             for a in (-1, 0):                   # s2d row offset
@@ -756,7 +768,7 @@ class _BuiltPlan:
                 stem.weight.copy_(w2)
             self.conv(s2d, stem, enc.bn1, ACT["silu"], out=x)
         else:
-            p.conv_direct(self.u_images, 1, B, H, W, 3, 0, p.const(pack_direct_weight(enc.conv_stem.weight), torch.float16), p.const(scale),
+            p.conv_direct(self.u_images, 1, B, H, W, 3, 0, self.direct_w(enc.conv_stem.weight), p.const(scale),
                           p.const(shift), stem_c, 3, 2, 1, ACT["silu"], 1.0, in_affine=affine, out=x)
         level_of_stage = {1: 2, 2: 3, 4: 4}
         # scratch for the per-image gated projection weights, sized for the widest block (the blocks run back to back)
@@ -766,7 +778,7 @@ class _BuiltPlan:
                 proj = blk.conv_pwl if blk.kind == "ir" else blk.conv_pw
                 nt, bn = ctypes.c_int(), ctypes.c_int()
                 L.his_conv_gemm_tile_n(proj.weight.shape[0], ctypes.byref(nt), ctypes.byref(bn))
-                need = max(need, B * nt.value * bn.value * round_up(blk.mid, 64))
+                need = max(need, B * nt.value * bn.value * round_up(blk.mid, 64) * (2 if self.split else 1))
         self._gated_w = torch.empty(max(need, 8), dtype=torch.float16, device=self.dev)
         p.keep.append(self._gated_w)
         for si, stage in enumerate(enc.blocks):
@@ -778,19 +790,19 @@ class _BuiltPlan:
         for i, blk in enumerate(dec.blocks):
             cat = cats[i]
             up = cat.slice(0, blk.cin)
-            full = Act(cat.buf, blk.cin + blk.cskip)
+            full = cat.widen(blk.cin + blk.cskip)
             fuse_up = (cat.H, cat.W) == (2 * x.H, 2 * x.W) and x.C == blk.cin and \
                 L.his_conv_gemm_can_fuse_upsample(cat.H, cat.W, blk.cin + blk.cskip, blk.conv1[0].weight.shape[0], blk.cin) == 1
             if fuse_up:   # nearest 2x + concat happen inside the conv's window loads: the upsampled tensor is never materialised
                 y = self.conv(full, blk.conv1[0], blk.conv1[1], ACT["relu"], up_input=x)
             else:
-                p.add("resize_nearest", L.his_resize_nearest, x.ptr, B, x.H, x.W, x.C, x.cs, cat.H, cat.W, up.ptr, up.cs)
+                p.add("resize_nearest", L.his_resize_nearest, x.ptr, B, x.H, x.W, x.C, x.cs, cat.H, cat.W, up.ptr, up.cs, self.S)
                 y = self.conv(full, blk.conv1[0], blk.conv1[1], ACT["relu"])
             x = self.conv(y, blk.conv2[0], blk.conv2[1], ACT["relu"])
         # segmentation head conv3x3 16->1 (+bias) -> fp32 logits; output_conv 1->2; export-wrapper binary mask
         head = net.segmentation_head[0]
         self.u_one = p.f32(B, 1, H, W)
-        p.conv_direct(x, 0, B, H, W, x.C, x.cs, p.const(pack_direct_weight(head.weight), torch.float16), p.const(torch.ones(1)),
+        p.conv_direct(x, 0, B, H, W, x.C, x.cs, self.direct_w(head.weight), p.const(torch.ones(1)),
                       p.const(head.bias.detach().float()), 1, 3, 1, 1, ACT["none"], out_f32=self.u_one)
         oc_w = m.pretrained_unet.output_conv.weight.detach().float().flatten().tolist()
         oc_b = m.pretrained_unet.output_conv.bias.detach().float().flatten().tolist()
@@ -813,10 +825,11 @@ class _BuiltPlan:
         d = p.act(B, ho, wo, blk.mid)
         parts = L.his_depthwise_pool_parts(B, t.H, t.W, blk.mid, blk.k, blk.s)
         pool = p.f32(B, parts, blk.mid)
-        wdw = blk.conv_dw.weight.detach().float().cpu().reshape(blk.mid, blk.k * blk.k).t().contiguous().half()
+        wdw = blk.conv_dw.weight.detach().float().cpu().reshape(blk.mid, blk.k * blk.k).t().contiguous()
         scale, shift = fold_bn(None, dw_bn, blk.mid)
-        p.add("depthwise", L.his_depthwise_conv, t.ptr, B, t.H, t.W, blk.mid, t.cs, p.const(wdw, torch.float16).data_ptr(),
-              p.const(scale).data_ptr(), p.const(shift).data_ptr(), blk.k, blk.s, ACT["silu"], d.ptr, d.cs, pool.data_ptr(),
+        p.add("depthwise", L.his_depthwise_conv, t.ptr, B, t.H, t.W, blk.mid, t.cs,
+              p.const(wdw, torch.float32 if self.split else torch.float16).data_ptr(),          # strict mode: fp32 taps
+              p.const(scale).data_ptr(), p.const(shift).data_ptr(), blk.k, blk.s, ACT["silu"], d.ptr, d.cs, pool.data_ptr(), self.S,
               desc=f"N{B} {t.H}x{t.W} C{blk.mid} k{blk.k} s{blk.s}")
         p._add_flops(2 * B * ho * wo * blk.mid * blk.k * blk.k, False)
         se = blk.se
@@ -849,10 +862,10 @@ class _BuiltPlan:
         msk = comb_in.slice(256, 2) if m.use_refinement else None
         p.add("roi_align_mask", L.his_roi_align, self.two.data_ptr(), 0, 2 * H * W, H * W, W, 1, B, 2, H, W, self.h_rois.data_ptr(), N, rh, rw,
               float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0, msk.ptr if msk else None, msk.cs if msk else 0,
-              roi_feat.data_ptr())
+              roi_feat.data_ptr(), self.S)
         p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
               float(rar.spatial_scale_h), float(rar.spatial_scale_w), 1 if rar.aligned else 0, patches.ptr, patches.cs,
-              roi_patch.data_ptr() if roi_patch is not None else None)
+              roi_patch.data_ptr() if roi_patch is not None else None, self.S)
 
         # --- rgb_feature_extractor (rgb.py:657-673)
         fe = m.rgb_feature_extractor
@@ -865,7 +878,7 @@ class _BuiltPlan:
             self._build_guided_head(comb_in, roi_feat, roi_patch)
             return
         # --- feature_combiner 1x1 258->256 (rgb.py:695,758-762); the concat is the buffer layout itself
-        feats = self.conv(Act(comb_in.buf, 258), m.feature_combiner, None, ACT["none"])
+        feats = self.conv(comb_in.widen(258), m.feature_combiner, None, ACT["none"])
         self._hier_head(feats, m.segmentation_head.base_head, m.segmentation_head)
         if aux_level != "none":
             self.h_aux["roi_features"] = roi_feat
@@ -882,7 +895,7 @@ class _BuiltPlan:
         ra = m.roi_align
         p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
               float(ra.spatial_scale_h), float(ra.spatial_scale_w), 1 if ra.aligned else 0, patches.ptr, patches.cs,
-              roi_patch.data_ptr() if roi_patch is not None else None)
+              roi_patch.data_ptr() if roi_patch is not None else None, self.S)
         # RGBFeatureExtractor (rgb.py:221-295): [conv3x3, norm, ReLU] (+ ResidualBlock after every stage but the first)
         x = self._rgb_extractor(patches, m.rgb_extractor.features, m.extractor_normalization_type, A, A)
         if m.use_refinement:
@@ -909,11 +922,11 @@ class _BuiltPlan:
         x = p.act(N, mh, mw, c)
         if self._is_bn(ec[1]):
             sc, sh = fold_bn(ec[0].bias, ec[1], c)
-            p.conv_direct(self.logits, 1, N, mh, mw, 3, 0, p.const(pack_direct_weight(ec[0].weight), torch.float16), p.const(sc), p.const(sh), c, 3, 1, 1,
+            p.conv_direct(self.logits, 1, N, mh, mw, 3, 0, self.direct_w(ec[0].weight), p.const(sc), p.const(sh), c, 3, 1, 1,
                           A, self.beta, out=x)
         else:
             sc, sh = fold_bn(ec[0].bias, None, c)
-            p.conv_direct(self.logits, 1, N, mh, mw, 3, 0, p.const(pack_direct_weight(ec[0].weight), torch.float16), p.const(sc), p.const(sh), c, 3, 1, 1,
+            p.conv_direct(self.logits, 1, N, mh, mw, 3, 0, self.direct_w(ec[0].weight), p.const(sc), p.const(sh), c, 3, 1, 1,
                           ACT["none"], self.beta, out=x)
             x = self.layernorm(x, ec[1], A)
         x = self.conv(x, ec[3], ec[4], A)
@@ -961,11 +974,11 @@ class _BuiltPlan:
                 roi_patch = p.f32(N, 3, rs, rs)
             p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rs, rs,
                   float(ra.spatial_scale_h), float(ra.spatial_scale_w), 1 if ra.aligned else 0, patches.ptr, patches.cs,
-                  roi_patch.data_ptr() if want_patch else None)
+                  roi_patch.data_ptr() if want_patch else None, self.S)
             slot = fused_in.slice(256 * i, 256)
             f = self._rgb_extractor(patches, m.rgb_extractors[sc].features, m.extractor_normalization_type, A_stage, A_rb)
             # F.interpolate to 28x28 (identity when the scale already is 28) straight into the scale's concat slot
-            p.add("resize_bilinear_half", L.his_resize_bilinear_half, f.ptr, N, rs, rs, 256, f.cs, fh, fw, slot.ptr, slot.cs)
+            p.add("resize_bilinear_half", L.his_resize_bilinear_half, f.ptr, N, rs, rs, 256, f.cs, fh, fw, slot.ptr, slot.cs, self.S)
         # fusion + projection: 'sum' / 'adaptive' are the 1x1 projection applied to the weighted sum of the scales, i.e. a 1x1 conv
         # over the concat buffer whose weight is [w_0*W | w_1*W | ...] -- no extra pass over the features
         proj = m.fusion_proj[0]
@@ -979,7 +992,7 @@ class _BuiltPlan:
                 conv_mod.bias.copy_(proj.bias.detach().float().cpu())
         saved = m.normalization_type
         m.normalization_type = m.extractor_normalization_type
-        x = self.conv(Act(fused_in.buf, 256 * ns), conv_mod, m.fusion_proj[1], A_stage)
+        x = self.conv(fused_in.widen(256 * ns), conv_mod, m.fusion_proj[1], A_stage)
         m.normalization_type = saved
         # the head works at 28x28 whatever the ROI scales are, and with ReLU whatever the extractors use (the reference builds
         # HierarchicalSegmentationHeadUNetV2 without forwarding the activation, rgb.py:854-860)
@@ -1022,7 +1035,7 @@ class _BuiltPlan:
         else:   # LayerNorm2d over (32, 2rh, 2rw) needs the whole sample: ConvT -> LN+act -> 1x1
             u = p.act(N, 2 * rh, 2 * rw, 32)
             p.add("convT2x2_small", L.his_convT2x2_small, low.data_ptr(), N, 2, rh, rw, p.const(up[0].weight).data_ptr(),
-                  p.const(up[0].bias).data_ptr(), 32, u.ptr, u.cs)
+                  p.const(up[0].bias).data_ptr(), 32, u.ptr, u.cs, self.S)
             u = self.layernorm(u, up[1], A_ref)
             self.conv(u, up[3], None, ACT["none"], out_f32=bgfg_nat)
         bgfg = self.to_mask_size(bgfg_nat)
@@ -1030,7 +1043,7 @@ class _BuiltPlan:
         fg = bh.fg_gate
         g1 = p.act(N, rh, rw, 64)
         sc, sh = fold_bn(fg[0].bias, None, 64)
-        p.conv_direct(low, 1, N, rh, rw, 2, 0, p.const(pack_direct_weight(fg[0].weight), torch.float16), p.const(sc), p.const(sh), 64, 1, 1, 0,
+        p.conv_direct(low, 1, N, rh, rw, 2, 0, self.direct_w(fg[0].weight), p.const(sc), p.const(sh), 64, 1, 1, 0,
                       A_ref, self.beta, out=g1)
         g2 = self.conv(g1, fg[3], None, A_ref)
         gate_nchw = None
@@ -1060,13 +1073,13 @@ class _BuiltPlan:
                 x = self.conv(x, tb[3], tb[4], A_ref, row_scale=sgate)       # ConvT 256->128 k2s2 + norm + act
             else:
                 sa = p.act(N, rh, rw, 256)
-                p.add("spatial_attention", L.his_spatial_attention, x.ptr, N, rh, rw, 256, x.cs, wsa.data_ptr(), kk, stats.data_ptr(), sa.ptr, sa.cs)
+                p.add("spatial_attention", L.his_spatial_attention, x.ptr, N, rh, rw, 256, x.cs, wsa.data_ptr(), kk, stats.data_ptr(), sa.ptr, sa.cs, self.S)
                 x = self.conv(sa, tb[3], tb[4], A_ref)                       # ConvT 256->128 k2s2 + norm + act
             ca = tb[6]
             r = ca.fc1.weight.shape[0]
             parts = L.his_pool_sum_parts(N, x.H * x.W, 128)
             pool = p.f32(N, parts, 128); gate_c = p.f32(N, 128)
-            p.add("pool_sum", L.his_pool_sum, x.ptr, N, x.H * x.W, 128, x.cs, pool.data_ptr())
+            p.add("pool_sum", L.his_pool_sum, x.ptr, N, x.H * x.W, 128, x.cs, pool.data_ptr(), self.S)
             p.add("se_gate", L.his_se_gate, pool.data_ptr(), parts, N, x.H * x.W, 128, r, p.const(ca.fc1.weight.reshape(r, 128)).data_ptr(), None,
                   p.const(ca.fc2.weight.reshape(128, r)).data_ptr(), None, A_ref, self.beta, p.f32(N, r).data_ptr(), gate_c.data_ptr())
             last_rb, tail = tb[8], tb[9]
@@ -1076,13 +1089,13 @@ class _BuiltPlan:
                 c_mid = last_rb.conv1.weight.shape[0]
                 nt, bnn = ctypes.c_int(), ctypes.c_int()
                 L.his_conv_gemm_tile_n(c_mid, ctypes.byref(nt), ctypes.byref(bnn))
-                wscr = torch.empty(N * 9 * nt.value * bnn.value * round_up(c_mid, 64), dtype=torch.float16, device=self.dev)
+                wscr = torch.empty(N * 9 * nt.value * bnn.value * round_up(c_mid, 64) * (2 if self.split else 1), dtype=torch.float16, device=self.dev)
                 p.keep.append(wscr)
                 t = self.conv(x, last_rb.conv1, last_rb.norm1, A_ref, in_gate=(gate_c, wscr))
                 self.conv(t, last_rb.conv2, last_rb.norm2, A_ref, res=x, res_mode=RES_ADD, res_scale=gate_c, tail=(tail, False, tn_nat))
                 ca_fused = True
             else:
-                p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs)
+                p.add("scale_channels", L.his_scale_channels, x.ptr, x.cs, gate_c.data_ptr(), N, x.H * x.W, 128, x.ptr, x.cs, self.S)
                 ca_fused = False
         else:
             x = self.conv(x, tb[2], tb[3], A_ref)
@@ -1186,8 +1199,8 @@ class _BuiltPlan:
         hd = m.segmentation_head
         fg_slot = comb_in.slice(256, 1)
         fg_low = p.f32(N, 1, rh, rw)
-        p.add("sigmoid_channel", L.his_sigmoid_channel, roi_feat.data_ptr(), N, 2, rh * rw, 1, fg_slot.ptr, fg_slot.cs, fg_low.data_ptr())
-        x = self.conv(Act(comb_in.buf, 257), hd.input_adjust, None, ACT["none"])
+        p.add("sigmoid_channel", L.his_sigmoid_channel, roi_feat.data_ptr(), N, 2, rh * rw, 1, fg_slot.ptr, fg_slot.cs, fg_low.data_ptr(), self.S)
+        x = self.conv(comb_in.widen(257), hd.input_adjust, None, ACT["none"])
         fp = hd.feature_processor
         x = self.conv(x, fp[0], fp[1], A_rgb)
         x = self.residual_block(x, fp[4], A_ref)
@@ -1198,7 +1211,7 @@ class _BuiltPlan:
             a = self.conv(x, am[0], None, A_rgb)
             attention = p.f32(N, 1, rh, rw)
             self.conv(a, am[2], None, ACT["sigmoid"], out_f32=attention)
-            p.add("scale_pixels", L.his_scale_pixels, x.ptr, x.cs, attention.data_ptr(), fg_low.data_ptr(), N * rh * rw, 256, x.ptr, x.cs)
+            p.add("scale_pixels", L.his_scale_pixels, x.ptr, x.cs, attention.data_ptr(), fg_low.data_ptr(), N * rh * rw, 256, x.ptr, x.cs, self.S)
         fc = hd.final_classifier
         y = self.conv(x, fc[0], fc[1], A_rgb)
         same = (rh, rw) == (mh, mw)
@@ -1242,7 +1255,7 @@ class _BuiltPlan:
                 x = self.conv(x, e[2], e[3], A, out=dst)
             if i < d - 1:
                 pooled = p.act(N, hw[i + 1][0], hw[i + 1][1], ch[i + 1])
-                p.add("maxpool2", L.his_maxpool2, x.ptr, N, x.H, x.W, x.C, x.cs, pooled.ptr, pooled.cs)
+                p.add("maxpool2", L.his_maxpool2, x.ptr, N, x.H, x.W, x.C, x.cs, pooled.ptr, pooled.cs, self.S)
                 x = pooled
         b = u.bottleneck
         a = self.residual_block(x, b[0], A)
@@ -1255,7 +1268,7 @@ class _BuiltPlan:
             c = ch[lvl + 1]
             self.conv(x, u.upconvs[i], None, ACT["none"], out=cats[lvl].slice(0, c))
             dec = u.decoders[i]
-            x = self.conv(Act(cats[lvl].buf, 2 * c), dec[0], dec[1], A)
+            x = self.conv(cats[lvl].widen(2 * c), dec[0], dec[1], A)
             x = self.residual_block(x, dec[3], A)
             x = self.residual_block(x, dec[4], A)
         f = u.final

@@ -45,5 +45,5 @@ class DynamicRoIAlign(nn.Module):
         stream = torch.cuda.current_stream(feat.device).cuda_stream
         _lib.check(L.his_roi_align(feat.data_ptr(), 1 if feat.dtype == torch.float16 else 0, sN, sC, sH, sW, B, C, H, W,
                                    rois.data_ptr(), K, oh, ow, float(self.spatial_scale_h), float(self.spatial_scale_w),
-                                   1 if self.aligned else 0, None, 0, out.data_ptr(), stream), "his_roi_align")
+                                   1 if self.aligned else 0, None, 0, out.data_ptr(), 0, stream), "his_roi_align")
         return out

@@ -48,7 +48,7 @@ int his_version(void);
  * Writes an NHWC half slice [n_rois,oh,ow,C] and/or NCHW fp32 [n_rois,C,oh,ow] (either may be NULL). */
 int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC, long long sH, long long sW,
                   int B, int C, int H, int W, const float* rois, int n_rois, int oh, int ow,
-                  float scale_h, float scale_w, int aligned, void* out_half, int out_cs, float* out_f32, void* stream);
+                  float scale_h, float scale_w, int aligned, void* out_half, int out_cs, float* out_f32, int split, void* stream);
 
 /* ---- dense conv2d 3x3(pad 1)/1x1, stride 1, and conv_transpose2d k2 s2, as tcgen05 implicit GEMM
  * (hed/advanced/hierarchical_segmentation_rgb.py:657-673,695; ..._refinement.py:37-39,479-523,537-545;
@@ -63,7 +63,22 @@ int his_conv_gemm_tile_n(int cout, int* n_tiles, int* block_n);
 int his_conv_gemm_create(void** plan, const void* in, int n_img, int H, int W, int cin, int in_cs,
                          const void* w_packed, int cin_pad, void* out, int cout, int out_cs,
                          const void* res, int res_cs, const float* shift,
-                         int ksize, int transposed, int act, float act_beta, int res_mode);
+                         int ksize, int transposed, int act, float act_beta, int res_mode, int split);
+/* `split` = 1 selects the split-fp16 ("strict" precision) form, which matches the reference's fp32 evaluation
+ * (hed/train_utils.py:162-180, no autocast) to ~1e-5 instead of ~1.5e-3: every NHWC half slice of the call is then a PAIR of
+ * fp16 planes x = hi + lo, hi = fp16(x), lo = fp16(x - hi), stored [hi channels | lo channels] inside one pixel (the lo plane
+ * cs/2 elements after the hi plane; cs % 16 == 0); w_packed holds [W_hi | W_lo] along K (cin_pad = 2 x the padded Cin) and the
+ * kernel runs three MMA passes per K block (A_hi.W_hi + A_lo.W_hi + A_hi.W_lo, exact products, fp32 accumulation).  The same
+ * `split` flag on the other entry points below means the same layout for their NHWC half operands (and fp32 instead of fp16
+ * weights for his_conv_direct / his_depthwise_conv).
+ *
+ * Tuning knobs read from the environment at plan creation (experiments only; defaults are the measured optimum, profiles/):
+ *   HIS_GEMM_HALO=0 (disable the halo-window A path), HIS_GEMM_HALO_MAXN=n (widest N tile in halo mode, default 96),
+ *   HIS_GEMM_PAIR=n (minimum N for cta_group::2 CTA pairs, default 128; <=0 disables), HIS_GEMM_PAIR_HALO=n (pairs fed by the halo
+ *   window), HIS_GEMM_TAPS=1|3|9 (taps per weight stage), HIS_GEMM_ASTAGES / HIS_GEMM_STAGES (ring depths), HIS_GEMM_BRES=0
+ *   (no resident weights), HIS_GEMM_NACC (TMEM accumulator ring), HIS_GEMM_DIRECT=0..3 (register->global epilogue policy),
+ *   HIS_GEMM_FUSE_UP=0 (no fused nearest upsample), HIS_GEMM_DEBUG (bit mask: skip stores / A loads / B loads / MMAs),
+ *   HIS_DW_TILED=0 (register-resident depthwise kernel). */
 /* Optional fused 1x1 tail to 1-2 channels computed in the epilogue from the fp32 activations (the Cout<=2 convs at
  * ..._refinement.py:293,335,523 and ..._unet.py:371): tail_out[n,o,y,x] = (sigmoid)(sum_c y[c]*tail_w[o][c] + tail_b[o]),
  * NCHW fp32; tail_w: device fp32 [tail_c][cout_slab]; store_main=0 skips writing the wide activation altogether. */
@@ -101,7 +116,7 @@ long long his_conv_gemm_issued_macs(void* plan);
 int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, int H, int W, int cin, int in_cs,
                     const void* w, const float* scale, const float* shift, int cout, int kh, int kw, int stride, int pad,
                     int act, float act_beta, int res_mode, const void* res, int res_cs,
-                    void* out_half, int out_cs, float* out_f32, void* stream);
+                    void* out_half, int out_cs, float* out_f32, int split, void* stream);
 
 /* ---- timm DepthwiseSeparableConv / InvertedResidual depthwise conv + BN + act (oracle/effunet.py _DS/_IR);
  * symmetric padding ((s-1)+(k-1))/2; w: fp16 [k*k][C]; optionally writes per-block partial sums of the output,
@@ -109,7 +124,7 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
  * (fixed-order reduction: bit-reproducible run to run, no atomics). */
 int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride);
 int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale,
-                       const float* shift, int k, int stride, int act, void* out, int out_cs, float* pool_sums, void* stream);
+                       const float* shift, int k, int stride, int act, void* out, int out_cs, float* pool_sums, int split, void* stream);
 
 /* ---- squeeze-excite (timm SqueezeExcite) and ChannelAttentionModule (hed/advanced/attention_modules.py:10-64):
  * pool_sum: per-block partial sums fp32 [N][parts][C], parts = his_pool_sum_parts(...); se_gate: mean = sum of the
@@ -117,13 +132,13 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
  * gate = sigmoid(W2*act(W1*mean+b1)+b2), fp32 weights w1 [R,C], w2 [C,R], biases may be NULL;
  * scale_channels: out = in * gate[n,c]. */
 int his_pool_sum_parts(int N, int HW, int C);
-int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, void* stream);
+int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums, int split, void* stream);
 int his_se_gate(float* pool_sums, int nparts, int N, int HW, int C, int R, const float* w1, const float* b1,
                 const float* w2, const float* b2, int act, float act_beta, float* hidden_ws /* [N][R] */, float* gate,
                 void* stream);
 /* out[n][row][k] = w_packed[row][k] * gate[n][k] (k < C, else 0): folds an input-channel gate into packed GEMM weights. */
-int his_scale_weights(const void* w_packed, const float* gate, int N, long long rows, int K, int C, void* out, void* stream);
-int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, void* stream);
+int his_scale_weights(const void* w_packed, const float* gate, int N, long long rows, int K, int C, void* out, int split, void* stream);
+int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int HW, int C, void* out, int out_cs, int split, void* stream);
 
 /* ---- LayerNorm2d, hed/model.py:18-38 (statistics over C,H,W per sample, biased variance) + optional residual +
  * activation, on an NHWC half slice.  partials_ws: device double [N][his_layernorm2d_parts(...)][2].
@@ -132,30 +147,30 @@ int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int 
 int his_layernorm2d_parts(int N, int HW, int C);
 int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps,
                         int act, float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws,
-                        void* out, int out_cs, void* stream);
+                        void* out, int out_cs, int split, void* stream);
 /* nn.GroupNorm / nn.InstanceNorm2d(affine=True) / AdaptiveInstanceNorm2d / SpatialGroupNorm of get_normalization_layer
  * (hed/advanced/normalization_comparison.py:12-74,159-206) + residual + activation on an NHWC half slice: statistics per
  * (sample, group of C/groups channels) over (C/groups, H, W), biased variance.  ws: float [N][his_groupnorm_parts()+1][C][2]. */
 int his_groupnorm_parts(int N, int HW, int C);
 int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int groups, const float* gamma, const float* beta, float eps, int act,
-                      float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, void* stream);
+                      float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, int split, void* stream);
 int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const float* wt, const float* bias, int cout,
-                       void* out, int out_cs, void* stream);
+                       void* out, int out_cs, int split, void* stream);
 
 /* ---- SpatialAttentionModule, hed/advanced/attention_modules.py:67-113: out = x*sigmoid(conv_kxk([mean_c,max_c])).
  * w: fp32 [2][k][k]; stats_ws: fp32 workspace [N*H*W*2]. */
 int his_spatial_attention(const void* in, int N, int H, int W, int C, int in_cs, const float* w, int k, float* stats_ws,
-                          void* out, int out_cs, void* stream);
+                          void* out, int out_cs, int split, void* stream);
 /* gate = sigmoid(conv_kxk([mean,max])) from per-pixel statistics [N,H,W,2] (no pass over the feature tensor). */
 int his_spatial_gate(const float* stats, int N, int H, int W, const float* w, int k, float* gate, void* stream);
 
 /* ---- nn.MaxPool2d(2) (..._unet.py:332), nearest resize (smp UnetDecoderBlock), bilinear align_corners=False
  * (F.interpolate at ..._refinement.py:561-566,581-586,772-802) */
-int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, void* stream);
-int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream);
+int his_maxpool2(const void* in, int N, int H, int W, int C, int in_cs, void* out, int out_cs, int split, void* stream);
+int his_resize_nearest(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, int split, void* stream);
 int his_resize_bilinear_f32(const float* in, int NC, int H, int W, int Ho, int Wo, float* out, void* stream);
 /* F.interpolate(bilinear, align_corners=False) of an NHWC half slice (MultiScaleRGBSegmentationModel, rgb.py:887-893). */
-int his_resize_bilinear_half(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, void* stream);
+int his_resize_bilinear_half(const void* in, int N, int H, int W, int C, int in_cs, int Ho, int Wo, void* out, int out_cs, int split, void* stream);
 
 /* ---- head tails: upsample_bg_fg (..._refinement.py:501-506) fused ConvT(2->32,k2,s2)+BN+act+1x1(32->2), NCHW fp32;
  * hierarchical combine (:588-596); elementwise sigmoid / sigmoid((x-*param)*10) (:294,:341). */
@@ -163,7 +178,7 @@ int his_upsample_bgfg(const float* low, int N, int h, int w, const float* wt, co
                       const float* w1, const float* b1, int act, float act_beta, float* out, void* stream);
 int his_head_combine(const float* bgfg, const float* tn, int N, int H, int W, float* logits, void* stream);
 int his_map_f32(const float* in, long long total, int op, const float* param, float* out, void* stream);
-int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, void* stream);
+int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, float* out, int split, void* stream);
 
 /* ---- refinement flags of RefinedHierarchicalSegmentationHead (hed/advanced/hierarchical_segmentation_refinement.py):
  * his_pixel_shuffle2_f32: nn.PixelShuffle(2) of SubPixelDecoder (:218-252), NCHW fp32 [N,in_channels>=4C,h,w] -> [N,C,2h,2w];
@@ -173,7 +188,7 @@ int his_nhwc_half_to_nchw_float(const void* in, int N, int HW, int C, int cs, fl
 int his_pixel_shuffle2_f32(const float* in, int N, int C, int in_channels, int h, int w, float* out, void* stream);
 /* NHWC half depth-to-space: out[n][2y+py][2x+px][c] = in[n][y][x][(py*2+px)*C + c] -- interleaves the four phase convolutions that
  * make up ConvTranspose2d(k4, s2, p1) of ProgressiveUpsamplingDecoder (:152-215), which run as one 3x3 conv with 4*C channels. */
-int his_depth_to_space2_half(const void* in, int N, int h, int w, int C, int in_cs, void* out, int out_cs, void* stream);
+int his_depth_to_space2_half(const void* in, int N, int h, int w, int C, int in_cs, void* out, int out_cs, int split, void* stream);
 int his_boundary_edges(const float* logits, int N, int H, int W, float* edges, unsigned int* minmax_ws, void* stream);
 int his_boundary_blend(const float* logits, const float* correction, const float* edges, const unsigned int* minmax_ws,
                        const float* blend_weight, int N, int H, int W, float* out, void* stream);
@@ -185,9 +200,9 @@ int his_boundary_blend(const float* logits, const float* correction, const float
  * his_scale_pixels: out = x * (attention * (0.5 + 0.5*fg_prob)) per pixel (:169-173); attention, fg_prob fp32 [pixels].
  * his_guided_aux: m = bilinear(in[:,c] -> (Ho,Wo), align_corners=False) (identity when sizes match), fg = sigmoid(m),
  *   bgfg = [log(1-fg+1e-7), log(fg+1e-7)] (:187-205); outputs NCHW fp32 [N,1,Ho,Wo] x2 and [N,2,Ho,Wo]. */
-int his_sigmoid_channel(const float* in, int N, int C, int HW, int c, void* out_half, int out_cs, float* out_f32, void* stream);
+int his_sigmoid_channel(const float* in, int N, int C, int HW, int c, void* out_half, int out_cs, float* out_f32, int split, void* stream);
 int his_scale_pixels(const void* in, int in_cs, const float* attention, const float* fg_prob, long long pixels, int C, void* out,
-                     int out_cs, void* stream);
+                     int out_cs, int split, void* stream);
 int his_guided_aux(const float* in, int N, int C, int c, int H, int W, int Ho, int Wo, float* mask_out, float* fg_out, float* bgfg_out,
                    void* stream);
 
@@ -199,7 +214,7 @@ int his_unet_input_affine(const float* images, long long count, const float* mea
                           unsigned int* flag_ws, float* affine6, void* stream);
 /* Normalised, space-to-depth copy of the NCHW fp32 images for the stem conv (timm conv_stem 3x3 s2 p1): NHWC half
  * [N, H/2, W/2, 16], channel (sy*2+sx)*3 + c; the stride-2 conv becomes a 2x2 stride-1 conv the tensor-core GEMM can run. */
-int his_s2d_input(const float* images, int N, int H, int W, const float* affine6, void* out_half, void* stream);
+int his_s2d_input(const float* images, int N, int H, int W, const float* affine6, void* out_half, int split, void* stream);
 int his_unet_outputs(const float* one, int B, int H, int W, float w0, float w1, float b0, float b1, float* two,
                      float* binary, void* stream);
 

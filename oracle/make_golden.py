@@ -194,6 +194,36 @@ def make_default_init_golden():
           "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
 
 
+REAL_CASES = {
+    # BASELINE configs[1] / [2] at their true ROI geometry ("no golden at 80x60->160x120 or 128x96->256x192"):
+    # one 480x640 image, 4 ROIs, stress weights (seed 0), data seed 2 / 3 like SURVEY 8d
+    "real_b1_enhanced": ("b1_enhanced", 2),
+    "real_b7_ultra": ("b7_ultra", 3),
+}
+
+
+def real_case_inputs(name):
+    preset, seed = REAL_CASES[name]
+    return headport.PRESETS[preset], synth_images(seed, 1, 480, 640), synth_rois(seed, 1, 4)
+
+
+def make_real_goldens():
+    """B1 enhanced / B7 ultra presets end to end through the real reference modules at full ROI / mask resolution.  The stored
+    tensors are sub-sampled where they are large (the file stays a few MB); the logits are stored whole."""
+    for name in REAL_CASES:
+        cfg, images, rois = real_case_inputs(name)
+        model, sd, logits, aux = _run_reference(cfg, images, rois)
+        out = {"logits": _np(logits), "full_image_logits_ch0_s4": _np(aux["full_image_logits"][:, 0, ::4, ::4]),
+               "shared_features_sub": _np(aux["shared_features"][:, ::16, ::4, ::4]),
+               "fg_attention_sub": _np(aux["fg_attention"][:, ::16, ::4, ::4]),
+               "bg_fg_logits_low": _np(aux["bg_fg_logits_low"]), "roi_features": _np(aux["roi_features"]),
+               "target_nontarget_logits_s2": _np(aux["target_nontarget_logits"][:, :, ::2, ::2]),
+               "contours_s2": _np(aux["contours"][:, :, ::2, ::2]), "distance_map_s2": _np(aux["distance_map"][:, :, ::2, ::2])}
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **{k: v.astype(np.float32) for k, v in out.items()})
+        print(name, "logits", tuple(logits.shape), "absmax", float(logits.abs().max()),
+              "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
+
+
 def make_roi_goldens():
     """DynamicRoIAlign itself (hed/dynamic_roi_align.py) on random feature maps, all conventions."""
     mod = refload.ref_import("dynamic_roi_align")
@@ -223,6 +253,8 @@ def main():
         make_default_init_golden()
     if args.only in ("all", "guided"):
         make_guided_goldens()
+    if args.only in ("all", "real"):
+        make_real_goldens()
     if args.only in ("all", "post"):
         from . import make_golden_post
         make_golden_post.make_post_goldens(GOLDEN)

@@ -6,7 +6,8 @@ import numpy as np
 import torch
 
 from oracle import headport, paramfill
-from oracle.make_golden import GUIDED_CASES, MULTISCALE_CASES, REFINE_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES, edge_rois, synth_images, synth_rois  # noqa: F401
+from oracle.make_golden import (GUIDED_CASES, MULTISCALE_CASES, REAL_CASES, REFINE_CASES, SMALL_CASES, SMALL_CASES_ALL, STANDARD_CASES,  # noqa: F401
+                                edge_rois, real_case_inputs, synth_images, synth_rois)
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 

@@ -14,16 +14,19 @@ def _act(y, code, beta):
     return {0: lambda v: v, 1: F.relu, 2: F.silu, 3: torch.sigmoid, 4: lambda v: v * torch.sigmoid(beta * v), 5: F.gelu}[code](y)
 
 
-def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, in_slice=None, out_slice=None, beta=1.0, seed=0):
+def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, in_slice=None, out_slice=None, beta=1.0, seed=0, split=False):
+    """split=True: the split-fp16 ("strict") kernels -- operands hi + lo, reference on the UNROUNDED fp32 operands."""
     import ctypes
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(seed)
-    plan = engine.Plan(dev)
+    plan = engine.Plan(dev, split)
     # input as a slice of a wider buffer when requested
     in_total, in_off = in_slice or (cin, 0)
     xbuf = plan.act(n, h, w, in_total)
-    xbuf.buf.copy_((torch.randn(n, h, w, xbuf.cs, generator=g)).half())
+    xbuf.buf.copy_((torch.randn(n, h, w, xbuf.cs, generator=g)).half())       # neighbours of the slice (and, split, its lo planes)
     x = xbuf.slice(in_off, cin)
+    if split:
+        x.fill_nhwc(torch.randn(n, h, w, cin, generator=g))
     if transposed:
         wt = torch.randn(cin, cout, 2, 2, generator=g) * (1.0 / cin) ** 0.5
     else:
@@ -33,7 +36,7 @@ def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, 
     nt, bn = ctypes.c_int(), ctypes.c_int()
     plan.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
     slab = nt.value * bn.value
-    wp, cin_pad = engine.pack_gemm_weight(wt, slab, transposed, scale)   # BatchNorm scale folded into the weights
+    wp, cin_pad = engine.pack_gemm_weight(wt, slab, transposed, scale, split=split)   # BatchNorm scale folded into the weights
     oh, ow = (2 * h, 2 * w) if transposed else (h, w)
     out_total, out_off = out_slice or (cout, 0)
     obuf = plan.act(n, oh, ow, out_total)
@@ -42,7 +45,7 @@ def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, 
     res = None
     if res_mode != RES_NONE:
         res = plan.act(n, oh, ow, cout)
-        res.buf.copy_(torch.randn(n, oh, ow, res.cs, generator=g).half())
+        res.fill_nhwc(torch.randn(n, oh, ow, cout, generator=g))
     plan.conv_gemm(x, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(shift, slab)),
                    out, k, act, beta, res, res_mode, transposed)
     plan.replay()
@@ -51,7 +54,11 @@ def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, 
     # reference
     xin = x.torch_nchw().cpu()
     # the kernel's operand: weights with the scale folded in, rounded to fp16
-    wh = (wt * (scale.view(1, -1, 1, 1) if transposed else scale.view(-1, 1, 1, 1))).half().float()
+    wh = wt * (scale.view(1, -1, 1, 1) if transposed else scale.view(-1, 1, 1, 1))
+    if not split:
+        wh = wh.half().float()
+    else:       # what the hi + lo pair can represent
+        wh = wh.half().float() + (wh - wh.half().float()).half().float()
     if transposed:
         y = F.conv_transpose2d(xin, wh, stride=2)
     else:
@@ -69,6 +76,8 @@ def run_case(n, h, w, cin, cout, k, act=1, res_mode=RES_NONE, transposed=False, 
         full = obuf.buf.float().cpu()
         mask = torch.ones(full.shape[-1], dtype=torch.bool)
         mask[out_off:out_off + cout] = False
+        if split:
+            mask[obuf.cs // 2 + out_off:obuf.cs // 2 + out_off + cout] = False
         assert (full[..., mask] == 7.0).all(), "store spilled outside the output channel slice"
     return err, ref
 
@@ -110,6 +119,14 @@ def test_conv_gemm_matches_torch_fp32(case):
     assert err <= 2e-3 * max(ref, 1.0), (err, ref)   # fp16 output rounding: 2^-11 relative
 
 
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items() if k in ("h", "w", "cin", "cout", "k")))
+def test_conv_gemm_split_fp16_matches_torch_fp32(case):
+    """The strict-precision kernels (three MMA passes over hi / lo operand planes): against torch fp32 on the operands the pairs
+    represent -- the error left is the fp32 accumulation order, the approximate sigmoid (2 ulp) and the lo plane's own rounding."""
+    err, ref = run_case(**case, split=True)
+    assert err <= 2e-5 * max(ref, 1.0), (err, ref)
+
+
 @pytest.mark.parametrize("case", [dict(n=3, h=64, w=48, cin=128, cout=128, k=3, res_mode=RES_ADD),
                                   dict(n=2, h=30, w=40, cin=200, cout=256, k=3, act=2),
                                   dict(n=1, h=16, w=12, cin=64, cout=160, k=3)],
@@ -122,18 +139,19 @@ def test_cta_pair_halo_variant_matches_torch_fp32(case, monkeypatch):
     assert err <= 2e-3 * max(ref, 1.0), (err, ref)
 
 
-def test_fused_nearest_upsample_concat_matches_torch():
+@pytest.mark.parametrize("split", [False, True], ids=["fp16", "split"])
+def test_fused_nearest_upsample_concat_matches_torch(split):
     """his_conv_gemm_set_upsampled_input: channels [0, low_c) gathered from the half-resolution tensor at (y>>1, x>>1), the rest
     from the concat buffer == F.interpolate(nearest) + cat + conv3x3 (smp UnetDecoderBlock)."""
     import ctypes
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(7)
     for (n, h, w, low_c, skip_c, cout) in [(2, 24, 32, 64, 24, 64), (1, 34, 18, 32, 0, 16), (3, 16, 48, 128, 40, 96)]:
-        plan = engine.Plan(dev)
+        plan = engine.Plan(dev, split)
         low = plan.act(n, h // 2, w // 2, low_c)
-        low.buf.copy_(torch.randn(low.buf.shape, generator=g).half())
+        low.fill_nhwc(torch.randn(n, h // 2, w // 2, low_c, generator=g))
         cat = plan.act(n, h, w, low_c + skip_c)
-        cat.buf.copy_(torch.randn(cat.buf.shape, generator=g).half())           # the first low_c channels are never read
+        cat.fill_nhwc(torch.randn(n, h, w, low_c + skip_c, generator=g))        # the first low_c channels are never read
         cin = low_c + skip_c
         wt = torch.randn(cout, cin, 3, 3, generator=g) * (1.0 / (cin * 9)) ** 0.5
         shift = torch.randn(cout, generator=g) * 0.1
@@ -141,15 +159,16 @@ def test_fused_nearest_upsample_concat_matches_torch():
         nt, bn = ctypes.c_int(), ctypes.c_int()
         plan.lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn))
         slab = nt.value * bn.value
-        wp, cin_pad = engine.pack_gemm_weight(wt, slab, False)
+        wp, cin_pad = engine.pack_gemm_weight(wt, slab, False, split=split)
         out = plan.act(n, h, w, cout)
         plan.conv_gemm(cat, plan.const(wp, torch.float16), cin_pad, plan.const(engine.pad_vec(shift, slab)), out, 3, ACT["relu"], up_input=low)
         plan.replay()
         torch.cuda.synchronize()
         x = torch.cat([F.interpolate(low.torch_nchw().cpu(), scale_factor=2, mode="nearest"), cat.torch_nchw().cpu()[:, low_c:]], 1)
-        want = F.relu(F.conv2d(x, wt.half().float(), padding=1) + shift.view(1, -1, 1, 1))
+        wref = wt.half().float() + ((wt - wt.half().float()).half().float() if split else 0.0)
+        want = F.relu(F.conv2d(x, wref, padding=1) + shift.view(1, -1, 1, 1))
         err = (out.torch_nchw().cpu() - want).abs().max().item()
-        assert err <= 2e-3 * max(want.abs().max().item(), 1.0), (n, h, w, low_c, skip_c, cout, err)
+        assert err <= (2e-5 if split else 2e-3) * max(want.abs().max().item(), 1.0), (n, h, w, low_c, skip_c, cout, err)
 
 
 def test_row_scale_and_channel_statistics_epilogue():

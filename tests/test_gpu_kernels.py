@@ -24,17 +24,23 @@ def test_dynamic_roi_align_matches_reference_golden():
     assert (out - g["ahw"]).abs().max() < 2e-5
 
 
-def _plan():
-    return engine.Plan(torch.device("cuda"))
+def _plan(split=False):
+    return engine.Plan(torch.device("cuda"), split)
 
 
+SPLIT = pytest.mark.parametrize("split", [False, True], ids=["fp16", "split"])
+
+
+@SPLIT
 @pytest.mark.parametrize("k,s,c", [(3, 1, 32), (3, 2, 96), (5, 2, 144), (5, 1, 672), (3, 1, 1152)])
-def test_depthwise_se_matches_torch(k, s, c):
-    p = _plan()
+def test_depthwise_se_matches_torch(k, s, c, split):
+    p = _plan(split)
     lib = p.lib
+    S = 1 if split else 0
+    tol = 2e-5 if split else 2e-3
     g = torch.Generator().manual_seed(k * 100 + c)
     n, h, w = 2, 23, 31
-    x = p.act(n, h, w, c); x.buf.copy_(torch.randn(n, h, w, x.cs, generator=g).half())
+    x = p.act(n, h, w, c); x.fill_nhwc(torch.randn(n, h, w, c, generator=g))
     wt = torch.randn(c, 1, k, k, generator=g) * 0.3
     scale, shift = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
     pad = ((s - 1) + (k - 1)) // 2
@@ -42,10 +48,10 @@ def test_depthwise_se_matches_torch(k, s, c):
     out = p.act(n, ho, wo, c)
     parts = lib.his_depthwise_pool_parts(n, h, w, c, k, s)
     pool = p.f32(n, parts, c)
-    wdw = p.const(wt.reshape(c, k * k).t().contiguous(), torch.float16)
+    wdw = p.const(wt.reshape(c, k * k).t().contiguous(), torch.float32 if split else torch.float16)      # strict mode: fp32 taps
     st = torch.cuda.current_stream().cuda_stream
     L.check(lib.his_depthwise_conv(x.ptr, n, h, w, c, x.cs, wdw.data_ptr(), p.const(scale).data_ptr(), p.const(shift).data_ptr(), k, s, 2,
-                                   out.ptr, out.cs, pool.data_ptr(), st))
+                                   out.ptr, out.cs, pool.data_ptr(), S, st))
     r = max(c // 4, 1)
     w1, b1 = torch.randn(r, c, generator=g) * 0.2, torch.randn(r, generator=g) * 0.1
     w2, b2 = torch.randn(c, r, generator=g) * 0.2, torch.randn(c, generator=g) * 0.1
@@ -53,19 +59,23 @@ def test_depthwise_se_matches_torch(k, s, c):
     L.check(lib.his_se_gate(pool.data_ptr(), parts, n, ho * wo, c, r, p.const(w1).data_ptr(), p.const(b1).data_ptr(), p.const(w2).data_ptr(),
                             p.const(b2).data_ptr(), 2, 1.0, p.f32(n, r).data_ptr(), gate.data_ptr(), st))
     scaled = p.act(n, ho, wo, c)
-    L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), n, ho * wo, c, scaled.ptr, scaled.cs, st))
+    L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), n, ho * wo, c, scaled.ptr, scaled.cs, S, st))
     torch.cuda.synchronize()
-    ref = F.silu(F.conv2d(x.torch_nchw().cpu(), wt.half().float(), None, s, pad, 1, c) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    ref = F.silu(F.conv2d(x.torch_nchw().cpu(), wt if split else wt.half().float(), None, s, pad, 1, c) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     got = out.torch_nchw().cpu()
-    assert (got - ref).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+    assert (got - ref).abs().max() <= tol * max(1.0, float(ref.abs().max()))
     mean = got.mean((2, 3))
     gref = torch.sigmoid(F.silu(mean @ w1.t() + b1) @ w2.t() + b2)
     assert (gate.cpu() - gref).abs().max() < 1e-4
-    assert (scaled.torch_nchw().cpu() - got * gref[:, :, None, None]).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+    assert (scaled.torch_nchw().cpu() - got * gref[:, :, None, None]).abs().max() <= max(tol, 1e-4) * max(1.0, float(ref.abs().max()))
 
 
-def test_direct_conv_variants_match_torch():
-    p = _plan()
+@SPLIT
+def test_direct_conv_variants_match_torch(split):
+    p = _plan(split)
+    wdt = torch.float32 if split else torch.float16
+    rnd = (lambda t: t) if split else (lambda t: t.half().float())
+    tol = 2e-5 if split else 2e-3
     g = torch.Generator().manual_seed(4)
     # (a) NCHW fp32 input + input affine + stride 2 (the UNet stem)
     n, h, w = 2, 37, 50
@@ -75,45 +85,46 @@ def test_direct_conv_variants_match_torch():
     scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
     ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
     out = p.act(n, ho, wo, 32)
-    p.conv_direct(p.const(img), 1, n, h, w, 3, 0, p.const(engine.pack_direct_weight(wt), torch.float16), p.const(scale), p.const(shift), 32, 3, 2, 1,
+    p.conv_direct(p.const(img), 1, n, h, w, 3, 0, p.const(engine.pack_direct_weight(wt, f32=split), wdt), p.const(scale), p.const(shift), 32, 3, 2, 1,
                   2, 1.0, in_affine=p.const(aff), out=out)
     # (b) NHWC half input, tail 1x1 to 2 channels, fp32 NCHW output
-    x = p.act(n, 9, 11, 128); x.buf.copy_(torch.randn(n, 9, 11, 128, generator=g).half())
+    x = p.act(n, 9, 11, 128); x.fill_nhwc(torch.randn(n, 9, 11, 128, generator=g))
     w2 = torch.randn(2, 128, 1, 1, generator=g) * 0.1
     tail = p.f32(n, 2, 9, 11)
-    p.conv_direct(x, 0, n, 9, 11, 128, x.cs, p.const(engine.pack_direct_weight(w2), torch.float16), p.const(torch.ones(2)), p.const(torch.tensor([0.1, -0.2])),
+    p.conv_direct(x, 0, n, 9, 11, 128, x.cs, p.const(engine.pack_direct_weight(w2, f32=split), wdt), p.const(torch.ones(2)), p.const(torch.tensor([0.1, -0.2])),
                   2, 1, 1, 0, 0, out_f32=tail)
     # (c) 3x3 16 -> 1 segmentation head (four output pixels per thread), widths that are / are not multiples of four, input slice
     heads = []
     for hw in ((13, 24), (7, 10), (5, 3)):
-        xb = p.act(n, hw[0], hw[1], 24); xb.buf.copy_(torch.randn(n, hw[0], hw[1], 24, generator=g).half())
+        xb = p.act(n, hw[0], hw[1], 24); xb.fill_nhwc(torch.randn(n, hw[0], hw[1], 24, generator=g))
         xs = xb.slice(8, 16)
         w3 = torch.randn(1, 16, 3, 3, generator=g) * 0.1
         o3 = p.f32(n, 1, hw[0], hw[1])
-        p.conv_direct(xs, 0, n, hw[0], hw[1], 16, xs.cs, p.const(engine.pack_direct_weight(w3), torch.float16), p.const(torch.tensor([1.5])),
+        p.conv_direct(xs, 0, n, hw[0], hw[1], 16, xs.cs, p.const(engine.pack_direct_weight(w3, f32=split), wdt), p.const(torch.tensor([1.5])),
                       p.const(torch.tensor([-0.3])), 1, 3, 1, 1, 3, out_f32=o3)
         heads.append((xs, w3, o3))
     p.replay(); torch.cuda.synchronize()
     for xs, w3, o3 in heads:
-        ref3 = torch.sigmoid(F.conv2d(xs.torch_nchw().cpu(), w3.half().float(), None, 1, 1) * 1.5 - 0.3)
+        ref3 = torch.sigmoid(F.conv2d(xs.torch_nchw().cpu(), rnd(w3), None, 1, 1) * 1.5 - 0.3)
         assert (o3.cpu() - ref3).abs().max() <= 1e-5
     xin = img * aff[:3].view(1, 3, 1, 1) + aff[3:].view(1, 3, 1, 1)
-    ref = F.silu(F.conv2d(xin, wt.half().float(), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
-    assert (out.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * float(ref.abs().max())
-    ref2 = F.conv2d(x.torch_nchw().cpu(), w2.half().float(), torch.tensor([0.1, -0.2]))
+    ref = F.silu(F.conv2d(xin, rnd(wt), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert (out.torch_nchw().cpu() - ref).abs().max() <= tol * float(ref.abs().max())
+    ref2 = F.conv2d(x.torch_nchw().cpu(), rnd(w2), torch.tensor([0.1, -0.2]))
     assert (tail.cpu() - ref2).abs().max() <= 1e-4 * max(1.0, float(ref2.abs().max()))
 
 
+@SPLIT
 @pytest.mark.parametrize("c,groups", [(72, 1), (72, 9), (64, 4), (256, 256), (32, 8)])
-def test_groupnorm_matches_torch(c, groups):
+def test_groupnorm_matches_torch(c, groups, split):
     """his_groupnorm_act (GroupNorm / SpatialGroupNorm of get_normalization_layer; one group per channel = instance norm) against
     F.group_norm on the same fp16-rounded input, with residual add + ReLU and with a plain SiLU epilogue."""
-    p = _plan()
+    p = _plan(split)
     L = p.lib
     g = torch.Generator().manual_seed(c + groups)
     n, h, w = 3, 13, 11
-    x = p.act(n, h, w, c); x.buf.copy_((torch.randn(n, h, w, c, generator=g) * 1.5 + 0.7).half())
-    r = p.act(n, h, w, c); r.buf.copy_(torch.randn(n, h, w, c, generator=g).half())
+    x = p.act(n, h, w, c); x.fill_nhwc(torch.randn(n, h, w, c, generator=g) * 1.5 + 0.7)
+    r = p.act(n, h, w, c); r.fill_nhwc(torch.randn(n, h, w, c, generator=g))
     gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
     outs = []
     for act, res in ((1, r), (2, None)):
@@ -123,42 +134,44 @@ def test_groupnorm_matches_torch(c, groups):
         p.keep.append(ws)
         p.add("groupnorm", L.his_groupnorm_act, x.ptr, n, h * w, c, x.cs, groups, p.const(gamma).data_ptr(), p.const(beta).data_ptr(), 1e-5, act,
               1.0, 1 if res is not None else 0, res.ptr if res is not None else None, res.cs if res is not None else 0, ws.data_ptr(), out.ptr,
-              out.cs)
+              out.cs, 1 if split else 0)
         outs.append(out)
     p.replay(); torch.cuda.synchronize()
     xin, rin = x.torch_nchw().cpu(), r.torch_nchw().cpu()
     y = F.group_norm(xin, groups, gamma, beta, 1e-5)
     for out, ref in zip(outs, (F.relu(y + rin), F.silu(y))):
-        assert (out.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+        assert (out.torch_nchw().cpu() - ref).abs().max() <= (2e-5 if split else 2e-3) * max(1.0, float(ref.abs().max()))
 
 
-def test_glue_kernels_match_torch():
-    p = _plan(); lib = p.lib
+@SPLIT
+def test_glue_kernels_match_torch(split):
+    p = _plan(split); lib = p.lib
+    S = 1 if split else 0
     st = torch.cuda.current_stream().cuda_stream
     g = torch.Generator().manual_seed(9)
     n, h, w, c = 3, 16, 12, 256
-    x = p.act(n, h, w, c); x.buf.copy_(torch.randn(n, h, w, c, generator=g).half())
+    x = p.act(n, h, w, c); x.fill_nhwc(torch.randn(n, h, w, c, generator=g))
     xr = x.torch_nchw().cpu()
     # maxpool
     mp = p.act(n, h // 2, w // 2, c)
-    L.check(lib.his_maxpool2(x.ptr, n, h, w, c, x.cs, mp.ptr, mp.cs, st))
+    L.check(lib.his_maxpool2(x.ptr, n, h, w, c, x.cs, mp.ptr, mp.cs, S, st))
     # spatial attention 7x7
     wsa = torch.randn(1, 2, 7, 7, generator=g) * 0.2
     sa = p.act(n, h, w, c); stats = p.f32(n, h, w, 2)
-    L.check(lib.his_spatial_attention(x.ptr, n, h, w, c, x.cs, p.const(wsa.reshape(2, 7, 7)).data_ptr(), 7, stats.data_ptr(), sa.ptr, sa.cs, st))
+    L.check(lib.his_spatial_attention(x.ptr, n, h, w, c, x.cs, p.const(wsa.reshape(2, 7, 7)).data_ptr(), 7, stats.data_ptr(), sa.ptr, sa.cs, S, st))
     # nearest resize into a slice, bilinear fp32, NHWC->NCHW
     cat = p.act(n, 31, 25, c + 8)
-    L.check(lib.his_resize_nearest(x.ptr, n, h, w, c, x.cs, 31, 25, cat.slice(8, c).ptr, cat.cs, st))
+    L.check(lib.his_resize_nearest(x.ptr, n, h, w, c, x.cs, 31, 25, cat.slice(8, c).ptr, cat.cs, S, st))
     t = torch.randn(n, 2, 10, 14, generator=g)
     bl = p.f32(n, 2, 23, 17)
     L.check(lib.his_resize_bilinear_f32(p.const(t).data_ptr(), n * 2, 10, 14, 23, 17, bl.data_ptr(), st))
     nchw = p.f32(n, c, h, w)
-    L.check(lib.his_nhwc_half_to_nchw_float(x.ptr, n, h * w, c, x.cs, nchw.data_ptr(), st))
+    L.check(lib.his_nhwc_half_to_nchw_float(x.ptr, n, h * w, c, x.cs, nchw.data_ptr(), S, st))
     torch.cuda.synchronize()
     assert torch.equal(mp.torch_nchw().cpu(), F.max_pool2d(xr, 2))
     s = torch.cat([xr.mean(1, keepdim=True), xr.max(1, keepdim=True)[0]], 1)
     ref = xr * torch.sigmoid(F.conv2d(s, wsa, padding=3))
-    assert (sa.torch_nchw().cpu() - ref).abs().max() <= 2e-3 * float(ref.abs().max())
+    assert (sa.torch_nchw().cpu() - ref).abs().max() <= (2e-5 if split else 2e-3) * float(ref.abs().max())
     assert torch.equal(cat.slice(8, c).torch_nchw().cpu(), F.interpolate(xr, size=(31, 25), mode="nearest"))
     assert (bl.cpu() - F.interpolate(t, size=(23, 17), mode="bilinear", align_corners=False)).abs().max() < 1e-5
     assert torch.equal(nchw.cpu(), xr)

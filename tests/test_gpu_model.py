@@ -10,6 +10,9 @@ significant bits -- the same operand precision as TF32 tensor cores) and fp32 ac
     strength through ~40 layers): ||a-b||_2/||b||_2 <= 2.5e-3, max|a-b|/max|b| <= 6e-3 -- i.e. sqrt(#layers) *
     2^-11 operand roundings, the floor of any 11-bit-operand tensor-core path (measured 1.2-1.8e-3 / 1.6-3.4e-3) --
     and argmax agreement >= 99.9 % on the BASELINE config, >= 99.8 % on the tiny golden cases (7-20 k pixels).
+  * ``model.precision = "strict"`` (split-fp16 operands: hi + lo planes, three MMA passes, fp32 accumulate):
+    north_star's bar on EVERY case and weight set -- max|a-b|/max|b| <= 1e-3 (and L2 <= 5e-4), argmax agreement >= 99.9 %.
+    Every golden test below runs in both modes.
 """
 import pytest
 import torch
@@ -21,16 +24,20 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 L2_TOL, MAX_TOL = 2.5e-3, 6e-3
+# (L2 bound, max bound, argmax agreement) per precision mode; "strict" is north_star's stated tolerance
+TOL = {"fast": (L2_TOL, MAX_TOL, 0.998), "strict": (5e-4, 1e-3, 0.999)}
+PRECISION = pytest.mark.parametrize("precision", ["fast", "strict"])
 
 
 def l2_rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-12))
 
 
-def build(cfg, shapes):
+def build(cfg, shapes, precision="fast"):
     m = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
     m.load_state_dict(common.procedural_state(shapes, weights_path=cfg.pretrained_weights_path))
     m = m.to("cuda")
+    m.precision = precision
     for ra in (m.roi_align_mask, m.roi_align_rgb):      # what export_onnx_advanced.py:80-98 does
         ra.spatial_scale = cfg.spatial_scale
         ra.spatial_scale_h, ra.spatial_scale_w = cfg.spatial_scale
@@ -48,37 +55,42 @@ def check(got, want, name, l2=L2_TOL, mx=MAX_TOL):
 SMALL = list(common.SMALL_CASES)
 
 
+@PRECISION
 @pytest.mark.parametrize("name", SMALL)
-def test_model_matches_reference_golden_small(name):
+def test_model_matches_reference_golden_small(name, precision):
     cfg, images, rois = common.small_case_inputs(name)
     g = common.golden(name)
-    m = build(cfg, common.shapes_for_case(name))
+    l2, mx, amin = TOL[precision]
+    m = build(cfg, common.shapes_for_case(name), precision)
     logits, aux = m(images.cuda(), rois.cuda())
-    check(logits, g["logits"], "logits")
-    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= 0.998
-    check(aux["full_image_logits"][:, 0], g["full_image_logits_ch0"], "full_image_logits")
-    check(aux["shared_features"][:, ::8], g["shared_features_sub"], "shared_features")
-    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention")
+    check(logits, g["logits"], "logits", l2, mx)
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= amin
+    check(aux["full_image_logits"][:, 0], g["full_image_logits_ch0"], "full_image_logits", l2, mx)
+    check(aux["shared_features"][:, ::8], g["shared_features_sub"], "shared_features", l2, mx)
+    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention", l2, mx)
     for k in ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_map", "roi_features", "roi_patches"):
-        check(aux[k], g[k], k)
-    check(aux["distance_mask"], g["distance_mask"], "distance_mask", l2=1e-2, mx=3e-2)   # sigmoid(10*(d-thr)): 10x gain on d's error
+        check(aux[k], g[k], k, l2, mx)
+    # sigmoid(10*(d-thr)): 10x gain on d's error
+    check(aux["distance_mask"], g["distance_mask"], "distance_mask", *((1e-2, 3e-2) if precision == "fast" else (1e-3, 3e-3)))
     assert set(aux) == {"bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "fg_attention", "shared_features", "contours",
                         "distance_mask", "distance_map", "full_image_logits", "roi_features", "roi_patches"}   # rgb.py:767-772
 
 
+@PRECISION
 @pytest.mark.parametrize("name", list(common.GUIDED_CASES))
-def test_guided_head_variant_matches_reference_golden(name):
+def test_guided_head_variant_matches_reference_golden(name, precision):
     """a13: no refinement flag -> PretrainedUNetGuidedSegmentationHead (rgb.py:43-218, :715-727), incl. the factory-default
     LayerNorm2d normalisation."""
     cfg, images, rois = common.small_case_inputs(name)
     g = common.golden(name)
-    m = build(cfg, common.shapes_for_case(name))
+    l2, mx, amin = TOL[precision]
+    m = build(cfg, common.shapes_for_case(name), precision)
     logits, aux = m(images.cuda(), rois.cuda())
-    check(logits, g["logits"], "logits")
+    check(logits, g["logits"], "logits", l2, mx)
     for k in ("bg_fg_logits", "target_nontarget_logits", "fg_prob", "pretrained_bg_fg_mask", "roi_features", "roi_patches"):
-        check(aux[k], g[k], k)
+        check(aux[k], g[k], k, l2, mx)
     if cfg.use_attention_module:
-        check(aux["attention"], g["attention"], "attention")
+        check(aux["attention"], g["attention"], "attention", l2, mx)
     else:
         assert aux["attention"] is None
     assert set(aux) == {"bg_fg_logits", "target_nontarget_logits", "fg_prob", "pretrained_bg_fg_mask", "attention", "full_image_logits",
@@ -89,8 +101,9 @@ def test_guided_head_variant_matches_reference_golden(name):
     assert l2_rel(logits2.cpu(), logits.cpu()) < 2e-3 and aux2["target_nontarget_logits"].shape == aux["target_nontarget_logits"].shape
 
 
+@PRECISION
 @pytest.mark.parametrize("name", list(common.STANDARD_CASES))
-def test_standard_model_variant_matches_reference_golden(name):
+def test_standard_model_variant_matches_reference_golden(name, precision):
     """a13: use_pretrained_unet=False -> HierarchicalRGBSegmentationModel (rgb.py:298-439): RoIAlign(aligned=False),
     RGBFeatureExtractor, HierarchicalSegmentationHeadUNetV2 (LayerNorm2d hard-coded) or the refined head."""
     cfg, images, rois = common.small_case_inputs(name)
@@ -99,19 +112,22 @@ def test_standard_model_variant_matches_reference_golden(name):
     assert type(m).__name__ == "HierarchicalRGBSegmentationModel" and m.roi_align.aligned is False
     m.load_state_dict(common.procedural_state(common.shapes_for_case(name)))
     m = m.to("cuda")
+    m.precision = precision
+    l2, mx, amin = TOL[precision]
     logits, aux = m(images.cuda(), rois.cuda())
-    check(logits, g["logits"], "logits")
-    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= 0.998
-    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention")
+    check(logits, g["logits"], "logits", l2, mx)
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= amin
+    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention", l2, mx)
     keys = [k for k in g if k not in ("logits", "fg_attention_sub")]
     for k in keys:
-        tol = dict(l2=1e-2, mx=3e-2) if k == "distance_mask" else {}
-        check(aux[k], g[k], k, **tol)
+        tol = ((1e-2, 3e-2) if precision == "fast" else (1e-3, 3e-3)) if k == "distance_mask" else (l2, mx)
+        check(aux[k], g[k], k, *tol)
     assert set(aux) == set(keys) | {"fg_attention"} | ({"shared_features"} if headport.uses_refined_head(cfg) else set())
 
 
+@PRECISION
 @pytest.mark.parametrize("name", list(common.MULTISCALE_CASES))
-def test_multiscale_model_matches_reference_golden(name):
+def test_multiscale_model_matches_reference_golden(name, precision):
     """a1 multi_scale=True -> MultiScaleRGBSegmentationModel (rgb.py:777-922): per-scale extractors, bilinear resize to 28x28,
     concat / adaptive fusion folded into the 1x1 projection, V2 head."""
     cfg, images, rois = common.small_case_inputs(name)
@@ -120,30 +136,36 @@ def test_multiscale_model_matches_reference_golden(name):
     assert type(m).__name__ == "MultiScaleRGBSegmentationModel"
     m.load_state_dict(common.procedural_state(common.shapes_for_case(name)))
     m = m.to("cuda")
+    m.precision = precision
+    l2, mx, amin = TOL[precision]
     logits, aux = m(images.cuda(), rois.cuda())
-    check(logits, g["logits"], "logits")
-    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= 0.998
-    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention")
+    check(logits, g["logits"], "logits", l2, mx)
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= amin
+    check(aux["fg_attention"][:, ::8], g["fg_attention_sub"], "fg_attention", l2, mx)
     keys = [k for k in g if k not in ("logits", "fg_attention_sub")]
     for k in keys:
-        check(aux[k], g[k], k)
+        check(aux[k], g[k], k, l2, mx)
     assert set(aux) == set(keys) | {"fg_attention"}
 
 
+@PRECISION
 @pytest.mark.parametrize("name", list(common.REFINE_CASES))
-def test_refinement_flags_match_reference_golden(name):
+def test_refinement_flags_match_reference_golden(name, precision):
     """a7 flags no headline preset enables: BoundaryRefinementModule (edge map normalised over the WHOLE batch tensor -> its own
     sub-plan after the ROI chunks) and SubPixelDecoder (..._refinement.py:58-149, 218-252, 734-770)."""
     cfg, images, rois = common.small_case_inputs(name)
     g = common.golden(name)
-    m = build(cfg, common.shapes_for_case(name))
+    m = build(cfg, common.shapes_for_case(name), precision)
     logits, aux = m(images.cuda(), rois.cuda())
     # group / instance statistics divide by a per-group deviation that is itself computed from fp16-rounded activations: the
     # stress weights' rounding noise (DESIGN section 4) grows from 1.4e-3 to ~2.5-3e-3 through the ~40 normalised layers
+    # (fast mode only: strict mode holds north_star's bound here too)
     stat_norm = cfg.normalization_type.lower() in ("group", "groupnorm", "spatial_group")
-    l2, mx = (6e-3, 1.2e-2) if stat_norm else (L2_TOL, MAX_TOL)      # measured: 2.5e-3 (4 groups), 4.4e-3 (8 groups of 2-4 channels)
+    l2, mx, amin = TOL[precision]
+    if stat_norm and precision == "fast":
+        l2, mx, amin = 6e-3, 1.2e-2, 0.997      # measured: 2.5e-3 (4 groups), 4.4e-3 (8 groups of 2-4 channels)
     check(logits, g["logits"], "logits", l2, mx)
-    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= (0.997 if stat_norm else 0.998)
+    assert common.argmax_agreement(logits.cpu(), g["logits"]) >= amin
     for k in ("bg_fg_logits", "bg_fg_logits_low", "target_nontarget_logits", "roi_features", "roi_patches"):
         check(aux[k], g[k], k, l2, mx)
     # chunked ROI schedule: the refiner still sees all ROIs at once
@@ -152,19 +174,21 @@ def test_refinement_flags_match_reference_golden(name):
     check(logits2, g["logits"], "logits(chunked)", l2, mx)
 
 
-def test_model_matches_reference_golden_config1():
-    """BASELINE.json configs[0]: B0 std, 2x3x480x640, 8 ROIs, 64x48 -> 128x96."""
+@PRECISION
+def test_model_matches_reference_golden_config1(precision):
+    """BASELINE.json configs[0]: B0 std, 2x3x480x640, 8 ROIs, 64x48 -> 128x96 (stress weights)."""
     cfg, images, rois = common.cfg1_inputs()
     g = common.golden("cfg1_b0")
-    m = build(cfg, common.golden_keys()["preset_b0"])
+    l2, mx, _ = TOL[precision]
+    m = build(cfg, common.golden_keys()["preset_b0"], precision)
     logits, aux = m(images.cuda(), rois.cuda())
-    e2, em = check(logits, g["logits"], "logits")
+    e2, em = check(logits, g["logits"], "logits", l2, mx)
     agree = common.argmax_agreement(logits.cpu(), g["logits"])
-    print(f"config1: l2_rel={e2:.3e} max_rel={em:.3e} argmax={agree:.5f}")
+    print(f"config1[{precision}]: l2_rel={e2:.3e} max_rel={em:.3e} argmax={agree:.5f}")
     assert agree >= 0.999
-    check(aux["full_image_logits"][:, 0, ::2, ::2], g["full_image_logits_ch0_s2"], "full_image_logits")
+    check(aux["full_image_logits"][:, 0, ::2, ::2], g["full_image_logits_ch0_s2"], "full_image_logits", l2, mx)
     for k in ("bg_fg_logits_low", "target_nontarget_logits", "contours", "distance_map", "roi_features"):
-        check(aux[k], g[k], k)
+        check(aux[k], g[k], k, l2, mx)
     # export contract (hed/export_onnx_advanced.py:353-457)
     inst, binary = m.infer(images.cuda(), rois.cuda())
     want_inst, want_bin = headport.export_outputs(g["logits"], torch.stack([g["full_image_logits_ch0_s2"], -g["full_image_logits_ch0_s2"]], 1))
@@ -187,6 +211,30 @@ def test_model_matches_reference_golden_config1_default_init():
     assert agree >= 0.999
     check(aux["bg_fg_logits_low"], g["bg_fg_logits_low"], "bg_fg_logits_low", l2=1e-3, mx=1e-3)
     check(aux["full_image_logits"][:, 0, ::4, ::4], g["full_image_logits_ch0_s4"], "full_image_logits", l2=1e-3, mx=2e-3)
+
+
+@PRECISION
+@pytest.mark.parametrize("name", list(common.REAL_CASES))
+def test_model_matches_reference_golden_real_geometry(name, precision):
+    """BASELINE.json configs[1] / [2] at their true geometry: B1 enhanced 80x60 -> 160x120 and B7 ultra 128x96 -> 256x192 on a
+    480x640 image, 4 ROIs, stress weights; goldens from the real reference modules (oracle/make_golden.py --only real)."""
+    cfg, images, rois = common.real_case_inputs(name)
+    g = common.golden(name)
+    l2, mx, _ = TOL[precision]
+    m = build(cfg, common.golden_keys()["preset_" + common.REAL_CASES[name][0]], precision)
+    logits, aux = m(images.cuda(), rois.cuda())
+    e2, em = check(logits, g["logits"], "logits", l2, mx)
+    agree = common.argmax_agreement(logits.cpu(), g["logits"])
+    print(f"{name}[{precision}]: l2_rel={e2:.3e} max_rel={em:.3e} argmax={agree:.5f}")
+    assert agree >= 0.999
+    check(aux["full_image_logits"][:, 0, ::4, ::4], g["full_image_logits_ch0_s4"], "full_image_logits", l2, mx)
+    check(aux["shared_features"][:, ::16, ::4, ::4], g["shared_features_sub"], "shared_features", l2, mx)
+    check(aux["fg_attention"][:, ::16, ::4, ::4], g["fg_attention_sub"], "fg_attention", l2, mx)
+    check(aux["bg_fg_logits_low"], g["bg_fg_logits_low"], "bg_fg_logits_low", l2, mx)
+    check(aux["roi_features"], g["roi_features"], "roi_features", l2, mx)
+    check(aux["target_nontarget_logits"][:, :, ::2, ::2], g["target_nontarget_logits_s2"], "target_nontarget_logits", l2, mx)
+    check(aux["contours"][:, :, ::2, ::2], g["contours_s2"], "contours", l2, mx)
+    check(aux["distance_map"][:, :, ::2, ::2], g["distance_map_s2"], "distance_map", l2, mx)
 
 
 def test_model_matches_oracle_fresh_inputs_edge_cases():

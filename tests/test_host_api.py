@@ -116,7 +116,7 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/his_b200.h but not exported"
     from human_instance_segmentation_b200 import lib as L
     assert set(L.SIGNATURES) == set(names)
-    assert lib.his_version() == 100
+    assert lib.his_version() == his.lib.ABI_VERSION
 
 
 def test_tile_n_policy():

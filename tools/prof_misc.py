@@ -17,9 +17,9 @@ def dw(h, w, c, k, s):
     pool = p.f32(N, parts, c)
     wdw = p.const(torch.randn(k * k, c), torch.float16)
     sc, sh = p.const(torch.ones(c)), p.const(torch.zeros(c))
-    L.check(lib.his_depthwise_conv(x.ptr, N, h, w, c, x.cs, wdw.data_ptr(), sc.data_ptr(), sh.data_ptr(), k, s, 2, out.ptr, out.cs, pool.data_ptr(), st))
+    L.check(lib.his_depthwise_conv(x.ptr, N, h, w, c, x.cs, wdw.data_ptr(), sc.data_ptr(), sh.data_ptr(), k, s, 2, out.ptr, out.cs, pool.data_ptr(), 0, st))
     gate = p.f32(N, c); gate.fill_(0.5)
-    L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), N, ho * wo, c, out.ptr, out.cs, st))
+    L.check(lib.his_scale_channels(out.ptr, out.cs, gate.data_ptr(), N, ho * wo, c, out.ptr, out.cs, 0, st))
 dw(240, 320, 96, 3, 2)
 dw(120, 160, 144, 3, 1)
 dw(60, 80, 240, 5, 1)
@@ -27,8 +27,8 @@ dw(60, 80, 240, 5, 1)
 n = 160
 x = p.act(n, 64, 48, 256); x.buf.normal_()
 sa = p.act(n, 64, 48, 256); stats = p.f32(n, 64, 48, 2)
-L.check(lib.his_spatial_attention(x.ptr, n, 64, 48, 256, x.cs, p.const(torch.randn(2, 7, 7)).data_ptr(), 7, stats.data_ptr(), sa.ptr, sa.cs, st))
+L.check(lib.his_spatial_attention(x.ptr, n, 64, 48, 256, x.cs, p.const(torch.randn(2, 7, 7)).data_ptr(), 7, stats.data_ptr(), sa.ptr, sa.cs, 0, st))
 nchw = p.f32(n, 256, 64, 48)
-L.check(lib.his_nhwc_half_to_nchw_float(x.ptr, n, 64 * 48, 256, x.cs, nchw.data_ptr(), st))
+L.check(lib.his_nhwc_half_to_nchw_float(x.ptr, n, 64 * 48, 256, x.cs, nchw.data_ptr(), 0, st))
 torch.cuda.synchronize()
 print("ok")

@@ -24,7 +24,7 @@ def dw(N, h, w, c, k, s):
     pool = p.f32(N, parts, c)
     wdw = p.const(torch.randn(k * k, c), torch.float16)
     sc, sh = p.const(torch.ones(c)), p.const(torch.zeros(c))
-    L.check(lib.his_depthwise_conv(x.ptr, N, h, w, c, x.cs, wdw.data_ptr(), sc.data_ptr(), sh.data_ptr(), k, s, 2, out.ptr, out.cs, pool.data_ptr(), st))
+    L.check(lib.his_depthwise_conv(x.ptr, N, h, w, c, x.cs, wdw.data_ptr(), sc.data_ptr(), sh.data_ptr(), k, s, 2, out.ptr, out.cs, pool.data_ptr(), 0, st))
 
 
 def gemm(n, h, w, cin, cout, k, res_mode=RES_NONE, aux=False, act=1):
