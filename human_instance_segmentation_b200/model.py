@@ -15,6 +15,8 @@ There is no torch-op fallback: without a CUDA device or the built library the ca
 from __future__ import annotations
 
 import ctypes
+import os
+import warnings
 from typing import Dict, Optional, Tuple, Union
 
 import torch
@@ -51,12 +53,41 @@ class PreTrainedPeopleSegmentationUNet(nn.Module):
         else:
             self.mean, self.std = [0.5, 0.5, 0.5], [0.5, 0.5, 0.5]
         self.model = pt.SmpUnetParams(encoder_name)
+        self.load_report = None
+        if pretrained_weights_path and os.path.exists(pretrained_weights_path):
+            self.load_report = self._load_pretrained(pretrained_weights_path)
+        else:       # the reference prints the same warning and keeps its random initialisation (..._unet.py:1866)
+            warnings.warn(f"Pre-trained weights not found at {pretrained_weights_path!r}: the full-image UNet keeps its initial "
+                          "parameters until a checkpoint is loaded with load_state_dict", stacklevel=3)
         self._freeze_bn = bool(freeze_weights)
         if freeze_weights:
             for p in self.model.parameters():
                 p.requires_grad = False
         self.register_buffer("norm_mean", torch.tensor(self.mean).view(1, 3, 1, 1))
         self.register_buffer("norm_std", torch.tensor(self.std).view(1, 3, 1, 1))
+
+
+    def _load_pretrained(self, path: str):
+        """The reference constructor's weight loading (..._unet.py:1776-1864): a plain state dict or a checkpoint holding it under
+        'state_dict' / 'model_state_dict'; a leading 'model.' or 'unet.' prefix (decided from the first key) is dropped; loaded
+        with strict=False.  Returns (missing_keys, unexpected_keys)."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        sd = ckpt
+        if isinstance(ckpt, dict):
+            sd = ckpt.get("state_dict", ckpt.get("model_state_dict", ckpt))
+        first = next(iter(sd), "")
+        prefix = "model." if first.startswith("model.") else "unet." if first.startswith("unet.") else ""
+        sd = {(k[len(prefix):] if prefix and k.startswith(prefix) else k): v for k, v in sd.items()}
+        n_enc = sum("encoder" in k for k in sd)           # B0 ~358, B1 ~506, B3 ~572, B7 ~1198 (..._unet.py:1815-1828)
+        detected = "b0" if n_enc < 400 else "b1" if n_enc < 540 else "b3" if n_enc < 700 else "b7"
+        expected = next((v for v in ("b0", "b1", "b3", "b7") if v in self.encoder_name.lower()), None)
+        if expected is not None and detected != expected:
+            warnings.warn(f"{path}: {n_enc} encoder keys look like EfficientNet-{detected.upper()} weights, the encoder is {self.encoder_name}")
+        res = self.model.load_state_dict(sd, strict=False)
+        if res.missing_keys or res.unexpected_keys:
+            warnings.warn(f"{path}: loaded with {len(res.missing_keys)} missing and {len(res.unexpected_keys)} unexpected keys "
+                          f"(first missing: {res.missing_keys[:5]}, first unexpected: {res.unexpected_keys[:5]})")
+        return list(res.missing_keys), list(res.unexpected_keys)
 
 
 class PreTrainedPeopleSegmentationUNetWrapper(nn.Module):

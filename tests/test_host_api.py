@@ -125,3 +125,38 @@ def test_tile_n_policy():
     for cout, want in [(256, (1, 256)), (128, (1, 128)), (72, (1, 80)), (36, (1, 48)), (288, (2, 160)), (384, (2, 192)), (768, (3, 256)), (16, (1, 16))]:
         assert lib.his_conv_gemm_tile_n(cout, ctypes.byref(nt), ctypes.byref(bn)) == 0
         assert (nt.value, bn.value) == want, cout
+
+
+def test_pretrained_unet_weights_are_loaded_from_the_path(tmp_path):
+    """..._unet.py:1776-1864: the constructor loads `pretrained_weights_path` when the file exists (plain or wrapped state
+    dict, optional 'model.' / 'unet.' prefix, strict=False) and warns when it does not."""
+    import warnings
+    from human_instance_segmentation_b200 import param_tree as pt
+    donor = pt.SmpUnetParams("timm-efficientnet-b0")
+    g = torch.Generator().manual_seed(5)
+    sd = {k: (torch.randn(v.shape, generator=g) if v.dtype.is_floating_point else v.clone()) for k, v in donor.state_dict().items()}
+    for wrap, prefix in (("state_dict", "model."), ("model_state_dict", "unet."), (None, "")):
+        f = tmp_path / f"best_model_b0_{wrap}.pth"
+        payload = {prefix + k: v for k, v in sd.items()}
+        torch.save({wrap: payload, "epoch": 3} if wrap else payload, f)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")          # a complete file loads silently
+            m = his.create_rgb_hierarchical_model(roi_size=(16, 12), mask_size=(32, 24), use_pretrained_unet=True, use_full_image_unet=True,
+                                                  pretrained_weights_path=str(f), encoder_name="timm-efficientnet-b0", use_contour_detection=True,
+                                                  normalization_type="batchnorm")
+        inner = m.pretrained_unet.model
+        assert inner.load_report == ([], [])
+        for k, v in inner.model.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+        assert inner.mean == [0.485, 0.456, 0.406]                     # "b0" in the path string (:1744-1758)
+    with pytest.warns(UserWarning, match="not found"):
+        his.create_rgb_hierarchical_model(use_pretrained_unet=True, use_full_image_unet=True, pretrained_weights_path=str(tmp_path / "absent.pth"),
+                                          encoder_name="timm-efficientnet-b0")
+    # a partial file: strict=False semantics, reported
+    part = {k: v for i, (k, v) in enumerate(sd.items()) if i % 2 == 0}
+    torch.save(part, tmp_path / "half_b0.pth")
+    with pytest.warns(UserWarning, match="missing"):
+        m = his.create_rgb_hierarchical_model(use_pretrained_unet=True, use_full_image_unet=True, pretrained_weights_path=str(tmp_path / "half_b0.pth"),
+                                              encoder_name="timm-efficientnet-b0")
+    # (torch does not report BatchNorm's num_batches_tracked as missing for a state dict without version metadata)
+    assert set(m.pretrained_unet.model.load_report[0]) == {k for k in sd if k not in part and not k.endswith("num_batches_tracked")}
