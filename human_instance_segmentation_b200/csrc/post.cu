@@ -182,7 +182,7 @@ __global__ void threshold_kernel(const float* __restrict__ in, long long total, 
 // full[y1:y2, x1:x2] = mask; later instances win.  canvas[b,y,x] = 1 + index of the last ROI whose pasted mask is 1.
 __global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int mh, int mw, const float* __restrict__ rois, int* __restrict__ canvas,
                              int B, int H, int W) {
-  const int roi = blockIdx.y;
+  const int roi = blockIdx.x;          // ROIs on gridDim.x (2^31-1 blocks): one call handles any ROI count
   const float* r = rois + 5 * roi;
   const int b = (int)r[0];
   if (b < 0 || b >= B) return;
@@ -192,7 +192,7 @@ __global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int
   if (bw <= 0 || bh <= 0) return;
   const double sx = 1.0 / ((double)bw / (double)mw), sy = 1.0 / ((double)bh / (double)mh);
   const long long total = (long long)bw * bh;
-  GRID_STRIDE(idx, total) {
+  for (long long idx = blockIdx.y * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.y * blockDim.x) {
     const int dx = (int)(idx % bw), dy = (int)(idx / bw);
     const int X = x1 + dx, Y = y1 + dy;
     if (X < 0 || X >= W || Y < 0 || Y >= H) continue;
@@ -236,12 +236,12 @@ __global__ void preprocess_u8_kernel(const unsigned char* __restrict__ src, int 
 template <typename T>
 __global__ void eval_confusion_kernel(const float* __restrict__ logits, const T* __restrict__ gt, long long HW, int* __restrict__ counts) {
   __shared__ int s_cnt[9];
-  const int n = blockIdx.y;
+  const int n = blockIdx.x;            // ROIs on gridDim.x
   if (threadIdx.x < 9) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   const float* l = logits + (long long)n * 3 * HW;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+  for (long long p = blockIdx.y * (long long)blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.y * blockDim.x) {
     const float l0 = l[p], l1 = l[HW + p], l2 = l[2 * HW + p];
     const int pred = (l1 > l0) ? ((l2 > l1) ? 2 : 1) : ((l2 > l0) ? 2 : 0);      // torch.argmax: first maximum
     const int t = (int)gt[(long long)n * HW + p];
@@ -346,12 +346,12 @@ int his_preprocess_u8(const unsigned char* src, int N, int Hs, int Ws, int Hd, i
 int his_eval_confusion(const float* logits, const void* gt, int gt_is_int64, int N, int H, int W, int* counts, void* stream) {
   if (!logits || !gt || !counts) return his_set_error(HIS_ERR_INVALID_ARG, "eval_confusion: null pointer");
   if (N == 0) return HIS_OK;
-  if (N > 65535) return his_set_error(HIS_ERR_UNSUPPORTED, "eval_confusion: at most 65535 ROIs per call (chunk the batch)");
   if (cudaMemsetAsync(counts, 0, (size_t)N * 9 * sizeof(int), ST) != cudaSuccess) return his_set_error(HIS_ERR_LAUNCH, "memset failed");
   const long long HW = (long long)H * W;
   int gx = (int)((HW + kThreads * 8 - 1) / (kThreads * 8));
   if (gx < 1) gx = 1;
-  dim3 grid(gx, N);
+  if (gx > 65535) gx = 65535;
+  dim3 grid(N, gx);
   if (gt_is_int64) eval_confusion_kernel<long long><<<grid, kThreads, 0, ST>>>(logits, (const long long*)gt, HW, counts);
   else eval_confusion_kernel<unsigned char><<<grid, kThreads, 0, ST>>>(logits, (const unsigned char*)gt, HW, counts);
   HIS_CHECK_LAUNCH();
@@ -361,8 +361,7 @@ int his_eval_confusion(const float* logits, const void* gt, int gt_is_int64, int
 int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W, void* stream) {
   if (!masks || !rois || !canvas) return his_set_error(HIS_ERR_INVALID_ARG, "paste: null pointer");
   if (N == 0) return HIS_OK;
-  if (N > 65535) return his_set_error(HIS_ERR_UNSUPPORTED, "paste: at most 65535 ROIs per call (chunk the batch)");
-  dim3 grid(32, N);
+  dim3 grid(N, 32);
   paste_kernel<<<grid, kThreads, 0, ST>>>(masks, N, mh, mw, rois, canvas, B, H, W);
   HIS_CHECK_LAUNCH();
   return HIS_OK;

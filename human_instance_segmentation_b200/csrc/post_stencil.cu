@@ -27,8 +27,12 @@ struct Tile {
   int H, W;
 };
 
+// grid = (planes * tiles_x, tiles_y): the plane index rides on gridDim.x (2^31-1 blocks), so one call handles any number of
+// planes (BASELINE configs[4] streams 1 M masks; gridDim.z would cap a call at 65 535)
+__device__ __forceinline__ int tiles_x_of(int W) { return (W + TW - 1) / TW; }
+__device__ __forceinline__ int plane_of(int W) { return blockIdx.x / tiles_x_of(W); }
 __device__ __forceinline__ Tile tile_of(int H, int W) {
-  Tile t; t.x0 = blockIdx.x * TW; t.y0 = blockIdx.y * TH; t.H = H; t.W = W; return t;
+  Tile t; t.x0 = (blockIdx.x % tiles_x_of(W)) * TW; t.y0 = blockIdx.y * TH; t.H = H; t.W = W; return t;
 }
 
 // Stages the (TW + 2R) x (TH + 2R) window around the tile into `s` (row pitch TW + 2R).
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(kThreads) edge_smooth_smem_kernel(const float*
                                                                     float* __restrict__ out) {
   __shared__ float s[(TW + 2) * (TH + 2)];
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(in + plane, t, 1, s);
   __syncthreads();
   for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) edge_directional_kernel(const float*
   __shared__ float s[(TW + 4) * (TH + 4)];
   constexpr int w = TW + 4;
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(in + plane, t, 2, s);
   __syncthreads();
   for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) edge_adaptive_kernel(const float* __
   __shared__ float s[(TW + 4) * (TH + 4)];
   constexpr int w = TW + 4;
   const Tile t = tile_of(H, W);
-  const int n = blockIdx.z;
+  const int n = plane_of(W);
   const long long plane = (long long)n * H * W;
   load_window<PAD_ZERO, false>(in + plane, t, 2, s);
   __syncthreads();
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) edge_optimized_kernel(const float* _
   __shared__ float hb[TW * (TH + 4)];         // horizontal blur, rows y0-2 .. y0+TH+1
   constexpr int w = TW + 4;
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(in + plane, t, 2, s);
   __syncthreads();
   const float g5[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) bilateral_exact_kernel(const float* 
   __shared__ float sk[81];
   const int R = k / 2, w = TW + 2 * R;
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_REFLECT, false>(in + plane, t, R, s);
   for (int i = threadIdx.x; i < k * k; i += kThreads) sk[i] = spatial[i];
   __syncthreads();
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) bilateral_fast_iter_kernel(const flo
   __shared__ float sk[16];
   const int R = k / 2, w = TW + 2 * R, hh = TH + 2 * R;
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(in + plane, t, R, s);
   if ((int)threadIdx.x < k) sk[threadIdx.x] = k1[threadIdx.x];
   __syncthreads();
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) guided_ab_kernel(const float* __rest
   const int w = TW + 2 * r, k = 2 * r + 1;
   const float wk = 1.0f / (float)(k * k);
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(x + plane, t, r, sx);
   load_window<PAD_ZERO, false>(g + plane, t, r, sg);
   __syncthreads();
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) guided_out_kernel(const float* __res
   const int w = TW + 2 * r, k = 2 * r + 1;
   const float wk = 1.0f / (float)(k * k);
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(a + plane, t, r, sa);
   load_window<PAD_ZERO, false>(b + plane, t, r, sb);
   __syncthreads();
@@ -437,7 +441,7 @@ __global__ void __launch_bounds__(kThreads) mask_cleanup_fused_kernel(const floa
   const int halo = 1 + iterations * R;                 // <= kMaxR (host checks)
   const int w = TW + 2 * halo;
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, false>(in + plane, t, halo, pa);
   for (int i = threadIdx.x; i < k * k; i += kThreads) gk[i] = gauss[i];
   __syncthreads();
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const f
   const int halo = iterations * R;
   const int w = TW + 2 * halo;
   const Tile t = tile_of(H, W);
-  const long long plane = (long long)blockIdx.z * H * W;
+  const long long plane = (long long)plane_of(W) * H * W;
   load_window<PAD_ZERO, true>(in + plane, t, halo, pa);
   for (int i = threadIdx.x; i < k * k; i += kThreads) gk[i] = gauss[i];
   __syncthreads();
@@ -485,14 +489,14 @@ __global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const f
   }
 }
 
-inline dim3 tile_grid(int N, int H, int W) { return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, N); }
+inline dim3 tile_grid(int N, int H, int W) { return dim3((unsigned)((long long)N * ((W + TW - 1) / TW)), (H + TH - 1) / TH, 1); }
 
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
 #define CHECK_PLANES(name)                                                                                              \
   if (N == 0 || H == 0 || W == 0) return HIS_OK;                                                                        \
-  if (N > 65535) return his_set_error(HIS_ERR_UNSUPPORTED, name ": at most 65535 planes per call (chunk the batch)")
+  if ((long long)N * ((W + TW - 1) / TW) >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, name ": too many planes per call")
 
 extern "C" {
 

@@ -203,6 +203,25 @@ def load():
     return lib
 
 
+def on_tensor_device(fn):
+    """Runs ``fn`` with the CUDA *current device* set to the device of its first CUDA tensor argument.  Kernel launches go to
+    the stream the caller passes, but function attributes, occupancy queries and stream handles are resolved against the current
+    device: a tensor on cuda:1 while the current device is 0 would fail with "invalid resource handle"."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        import torch
+        for a in list(args) + list(kw.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kw)
+        return fn(*args, **kw)
+    return wrapped
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().his_last_error()

@@ -18,6 +18,9 @@ from . import lib as _lib
 
 
 @torch.no_grad()
+
+
+@_lib.on_tensor_device
 def roi_confusion_counts(logits: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
     """[N,3,H,W] logits, [N,H,W] labels in {0,1,2} (uint8 or int64) -> int32 [N,3,3] counts[n, gt, pred]."""
     if not logits.is_cuda:

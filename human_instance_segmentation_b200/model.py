@@ -14,6 +14,7 @@ There is no torch-op fallback: without a CUDA device or the built library the ca
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 import warnings
@@ -26,6 +27,36 @@ from . import lib as _lib
 from . import param_tree as pt
 from .engine import ACT, RES_ADD, RES_MUL, RES_NONE, Act, Plan, fold_bn, pack_direct_weight, pack_gemm_weight, pad_vec, round_up
 from .roi_align import DynamicRoIAlign
+
+
+def _on_model_device(fn):
+    """Runs a model method with the CUDA current device set to the model's device (function attributes, occupancy queries,
+    graph capture and stream handles are resolved against the current device; a model on cuda:1 is otherwise unusable while
+    the current device is 0)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        dev = next(self.parameters()).device
+        if dev.type == "cuda" and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return fn(self, *a, **k)
+        return fn(self, *a, **k)
+    return wrapped
+
+
+def _bucket_rois(n: int) -> int:
+    """ROI capacity of the launch plan that serves n ROIs (exported contract: dynamic `num_rois`, export_onnx_advanced.py:427-457):
+    exact up to 16, then steps of 8 / 32 / 64 -- at most ~12-25 % padded head work, a handful of plans for any stream of counts."""
+    if n <= 16:
+        return n
+    step = 8 if n <= 64 else 32 if n <= 256 else 64
+    return (n + step - 1) // step * step
+
+
+def _bucket_images(b: int) -> int:
+    """Image capacity (dynamic `batch_size`): exact up to 16, then multiples of 8."""
+    return b if b <= 16 else (b + 7) // 8 * 8
 
 
 def _pair(v) -> Tuple[int, int]:
@@ -125,7 +156,12 @@ class _PlannedModel(nn.Module):
         self.use_cuda_graph = False
         self.max_rois_per_pass = None    # None: derived from the ROI size (bounds the activation footprint)
         self.max_images_per_pass = None  # None: derived from the image size / encoder width
-        self._plans: Dict[tuple, "_BuiltPlan"] = {}
+        # Launch plans are keyed on CAPACITY buckets of (batch, ROI count): a request with fewer images / ROIs runs on the bucket's
+        # plan with a masked tail (zero images, zero-area ROIs; outputs sliced), bit-identical to an exact-size plan because no
+        # kernel mixes data across images or ROIs.  Plans are evicted least-recently-used once their buffers exceed the budget.
+        self.plan_buckets = True
+        self.max_plan_bytes = 64 << 30
+        self._plans: "collections.OrderedDict[tuple, _BuiltPlan]" = collections.OrderedDict()
         self.eval()
 
     def train(self, mode: bool = True):
@@ -148,14 +184,22 @@ class _PlannedModel(nn.Module):
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         self._plans.clear()
+        if getattr(self, "_pipe", None) is not None:        # streams / events of the pipelined API belong to the old device
+            torch.cuda.synchronize()
+            self._pipe = None
         return r
 
     @torch.no_grad()
+    @_on_model_device
     def forward(self, images: torch.Tensor, rois: torch.Tensor):
         bp = self._get_plan(images, rois)
         bp.load_inputs(images, rois)
         bp.plan.replay()
         return bp.outputs(self.copy_outputs)
+
+    def plan_bytes(self) -> int:
+        """HBM held by the cached launch plans."""
+        return sum(bp.nbytes for bp in self._plans.values())
 
     def _aligners(self):
         if hasattr(self, "roi_aligns"):
@@ -175,15 +219,35 @@ class _PlannedModel(nn.Module):
         B, _, H, W = images.shape
         if self.precision not in ("fast", "strict"):
             raise ValueError(f"precision must be 'fast' or 'strict', got {self.precision!r}")
-        key = (B, H, W, rois.shape[0], self.aux_outputs, self.precision, self.max_rois_per_pass, self.max_images_per_pass,
-               tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index, slot)
+        N = rois.shape[0]
+        # the boundary refiner normalises its edge map over the WHOLE [N,3,mh,mw] tensor (..._refinement.py:94-129): padded ROIs would
+        # take part in that min / max, so such models keep exact-size plans
+        bucket = self.plan_buckets and not getattr(self, "use_boundary_refinement", False)
+        Bc, Nc = (_bucket_images(B), _bucket_rois(N)) if bucket else (B, N)
+        key = (Bc, H, W, Nc, self.aux_outputs, self.precision, self.max_rois_per_pass, self.max_images_per_pass,
+               tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index, slot, self.use_cuda_graph)
         bp = self._plans.get(key)
         if bp is None:
-            bp = _BuiltPlan(self, dev, B, H, W, rois.shape[0])
+            self._evict(self.max_plan_bytes)
+            bp = _BuiltPlan(self, dev, Bc, H, W, Nc)
             if self.use_cuda_graph:
                 bp.plan.capture()
             self._plans[key] = bp
+            self._evict(self.max_plan_bytes, protect=key)
+        else:
+            self._plans.move_to_end(key)
+        bp.set_active(B, N)
         return bp
+
+    def _evict(self, keep_bytes: int, protect=None):
+        """Drops least-recently-used plans until the cache fits the byte budget (the plan in use is never dropped; plans still
+        referenced by the pipelined API's in-flight batches are kept alive by those references until they finish)."""
+        while self._plans and self.plan_bytes() > keep_bytes:
+            victim = next((k for k in self._plans if k != protect), None)
+            if victim is None:
+                break
+            torch.cuda.synchronize()           # its kernels may still be running
+            del self._plans[victim]
 
 
 class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel):
@@ -236,6 +300,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
+    @_on_model_device
     def infer(self, images: torch.Tensor, rois: torch.Tensor, raw_logits: bool = False):
         """Exported-ONNX contract (hed/export_onnx_advanced.py:353-457): returns
         ``(instance_masks [N,1,mh,mw] in {0,1}, binary_masks [B,1,H,W])``; ``raw_logits=True`` gives the older
@@ -244,7 +309,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         bp = self._masks_only_plan(images, rois)
         bp.load_inputs(images, rois)
         bp.plan.replay()
-        logits, binary = bp.logits, bp.binary
+        logits, binary = bp.out_logits, bp.out_binary
         if raw_logits:
             return (logits.clone(), binary.clone()) if self.copy_outputs else (logits, binary)
         inst = postprocess.instance_masks(logits)
@@ -266,6 +331,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         torch.cuda.empty_cache()
 
     @torch.no_grad()
+    @_on_model_device
     def infer_pipelined(self, images: torch.Tensor, rois: torch.Tensor, out_instance_masks: torch.Tensor, out_binary_masks: torch.Tensor):
         """``infer`` for a stream of batches held in (pinned) HOST memory: the call enqueues H2D -> forward -> argmax -> D2H into
         the caller's host tensors on three streams and returns at once; consecutive calls alternate between two launch plans,
@@ -283,9 +349,12 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         with torch.cuda.stream(st["compute"]):
             bp = self._masks_only_plan(images, rois, slot=slot)     # built (and graph-captured) on first use of the slot
         mh, mw = self.mask_size
-        if st["inst"][slot] is None or st["inst"][slot].shape[0] != rois.shape[0]:
-            st["inst"][slot] = torch.empty((rois.shape[0], 1, mh, mw), dtype=torch.float32, device=dev)
-        inst = st["inst"][slot]
+        if st["inst"][slot] is None or st["inst"][slot].shape[0] < rois.shape[0]:
+            old = st["inst"][slot]
+            if old is not None:      # still read by the slot's last download / written by its last argmax on the side streams
+                old.record_stream(st["compute"]); old.record_stream(st["d2h"])
+            st["inst"][slot] = torch.empty((_bucket_rois(rois.shape[0]), 1, mh, mw), dtype=torch.float32, device=dev)
+        inst = st["inst"][slot][: rois.shape[0]]
         # upload: the slot's input buffers are free once the forward that last read them has finished
         st["h2d"].wait_stream(cur)
         if st["done"][slot] is not None:
@@ -301,7 +370,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
             bp.plan.replay()
             n = rois.shape[0]
             if n:
-                L_.check(L_.load().his_post_instance_mask(bp.logits.data_ptr(), n, mh, mw, 0.0, inst.data_ptr(), None,
+                L_.check(L_.load().his_post_instance_mask(bp.out_logits.data_ptr(), n, mh, mw, 0.0, inst.data_ptr(), None,
                                                           ctypes.c_void_p(st["compute"].cuda_stream)), "his_post_instance_mask")
             done = torch.cuda.Event(); done.record()
         st["done"][slot] = done
@@ -309,7 +378,7 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
         st["d2h"].wait_event(done)
         with torch.cuda.stream(st["d2h"]):
             out_instance_masks.copy_(inst, non_blocking=True)
-            out_binary_masks.copy_(bp.binary, non_blocking=True)
+            out_binary_masks.copy_(bp.out_binary, non_blocking=True)
             fetched = torch.cuda.Event(); fetched.record()
         st["fetched"][slot] = fetched
         return fetched
@@ -323,12 +392,13 @@ class HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet(_PlannedModel)
                     ev.synchronize()
             torch.cuda.current_stream(next(self.parameters()).device).wait_stream(st["d2h"])
 
+    @_on_model_device
     def _run_unet_only(self, images: torch.Tensor) -> torch.Tensor:
         rois = torch.zeros((0, 5), dtype=torch.float32, device=images.device)
         bp = self._get_plan(images, rois)
         bp.load_inputs(images, rois)
         bp.plan.replay()
-        return bp.two.clone()
+        return bp.two[: bp.nB].clone()
 
 
 class HierarchicalRGBSegmentationModel(_PlannedModel):
@@ -484,7 +554,9 @@ class _BuiltPlan:
     buffers, so the common case has no extra copies)."""
 
     def __init__(self, m: HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet, dev, B, H, W, N):
-        self.m, self.dev, self.B, self.H, self.W, self.N = m, dev, B, H, W, N
+        self.m, self.dev, self.B, self.H, self.W, self.N = m, dev, B, H, W, N      # B, N: CAPACITY of the plan
+        self.nB, self.nN = B, N                                                    # images / ROIs of the current request
+        self._filled_B, self._filled_N = 0, 0                                      # buffer rows that may hold stale inputs
         self.split = getattr(m, "precision", "fast") == "strict"
         self.S = 1 if self.split else 0          # the `split` argument of the C entry points
         self.act_rgb = {"relu": ACT["relu"], "swish": ACT["silu"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
@@ -538,15 +610,49 @@ class _BuiltPlan:
         self.plan = _CompositePlan(self)
 
     # -------------------------------------------------------------- I/O + schedule
+    def set_active(self, n_images: int, n_rois: int):
+        assert 0 <= n_images <= self.B and 0 <= n_rois <= self.N
+        self.nB, self.nN = n_images, n_rois
+
+    @property
+    def nbytes(self) -> int:
+        if getattr(self, "_nbytes", None) is None:
+            seen, total = set(), 0
+            for pl in (self.unet_plan, self.head_plan, self.post_plan):
+                for t in (pl.keep if pl is not None else ()):
+                    if isinstance(t, torch.Tensor) and t.data_ptr() not in seen:
+                        seen.add(t.data_ptr()); total += t.numel() * t.element_size()
+            self._nbytes = total
+        return self._nbytes
+
     def load_inputs(self, images: torch.Tensor, rois: torch.Tensor):
-        self.images.copy_(images, non_blocking=True)
+        """Copies the request into the plan's static buffers; rows beyond the request (capacity plans) are zeroed when they
+        hold an earlier request: a stale 0..255 image would flip the whole-batch `x.max() > 1` decision, a stale ROI costs nothing
+        but keeps results reproducible."""
+        nb, nn = self.nB, self.nN
+        self.images[:nb].copy_(images, non_blocking=True)
+        if self._filled_B > nb:
+            self.images[nb:self._filled_B].zero_()
+        self._filled_B = nb
         if self.N:
-            self.rois[: self.N].copy_(rois, non_blocking=True)
+            self.rois[:nn].copy_(rois, non_blocking=True)
+            if self._filled_N > nn:
+                self.rois[nn:self._filled_N].zero_()
+            self._filled_N = nn
+
+    @property
+    def out_logits(self) -> torch.Tensor:
+        return self.logits[: self.nN]
+
+    @property
+    def out_binary(self) -> torch.Tensor:
+        return self.binary[: self.nB]
 
     def outputs(self, copy: bool):
         f = (lambda t: t.clone()) if copy else (lambda t: t)
-        aux = {k: (f(v) if v is not None else None) for k, v in self.aux.items()}
-        return f(self.logits), aux
+        image_level = ("full_image_logits",)
+        aux = {k: (f(v[: self.nB] if k in image_level else v[: self.nN]) if v is not None else None) for k, v in self.aux.items()}
+        return f(self.out_logits), aux
 
     def run(self, timed: bool = False):
         L = self.unet_plan.lib

@@ -28,6 +28,9 @@ def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 @torch.no_grad()
+
+
+@_lib.on_tensor_device
 def instance_masks(logits: torch.Tensor, score_threshold: float = 0.0, as_uint8: bool = False) -> torch.Tensor:
     """[N,3,H,W] logits -> [N,1,H,W] fp32 in {0,1} (or [N,H,W] uint8)."""
     x = _cuda_f32(logits, "instance_masks")
@@ -50,11 +53,17 @@ class MaskDilationModule(nn.Module):
         self.dilation_pixels = dilation_pixels
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, masks: torch.Tensor) -> torch.Tensor:
-        if self.dilation_pixels == 0:
+        if self.dilation_pixels <= 0:          # export_hierarchical_instance_peopleseg_onnx.py:97-98 returns the input
             return masks
         x = _cuda_f32(masks, "MaskDilationModule")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"MaskDilationModule expects [N,3,H,W] logits (bg, target, non-target), got {tuple(x.shape)}")
         n, c, h, w = x.shape
+        if n == 0:
+            return x.clone()
         out = torch.empty_like(x)
         _lib.check(_lib.load().his_post_dilate_logits(x.data_ptr(), n, h, w, int(self.dilation_pixels), out.data_ptr(), _stream(x)))
         return out
@@ -94,6 +103,8 @@ class BinaryMaskEdgeSmoothing(nn.Module):
         self.threshold, self.blur_strength = threshold, blur_strength
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, mask: torch.Tensor) -> torch.Tensor:
         x4, shape = _as_planes(mask)
         x = _cuda_f32(x4, "BinaryMaskEdgeSmoothing")
@@ -104,14 +115,12 @@ class BinaryMaskEdgeSmoothing(nn.Module):
 
 
 def _run_planes(fn, x: torch.Tensor, out: torch.Tensor, *args, extra_in=(), extra_out=()):
-    """Calls a tiled stencil entry point over the [B*C] planes of ``x`` in chunks of 65535 planes."""
+    """Calls a tiled stencil entry point over the [B*C] planes of ``x`` (one launch whatever the plane count: the plane index
+    rides on gridDim.x)."""
     b, c, h, w = x.shape
-    n, hw = b * c, h * w * 4
-    for s0 in range(0, n, 65535):
-        cnt = min(65535, n - s0)
-        ins = [t.data_ptr() + s0 * hw for t in extra_in]
-        outs = [t.data_ptr() + s0 * hw for t in extra_out]
-        _lib.check(fn(x.data_ptr() + s0 * hw, *ins, cnt, h, w, *args, *outs, out.data_ptr() + s0 * hw, _stream(x)))
+    if b * c == 0:
+        return
+    _lib.check(fn(x.data_ptr(), *[t.data_ptr() for t in extra_in], b * c, h, w, *args, *[t.data_ptr() for t in extra_out], out.data_ptr(), _stream(x)))
 
 
 class DirectionalEdgeSmoothing(nn.Module):
@@ -122,6 +131,8 @@ class DirectionalEdgeSmoothing(nn.Module):
         self.num_directions = num_directions
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, mask: torch.Tensor) -> torch.Tensor:
         x = _cuda_f32(mask, "DirectionalEdgeSmoothing")
         if x.dim() != 4 or x.shape[1] != 1:
@@ -135,13 +146,13 @@ class AdaptiveEdgeSmoothing(nn.Module):
     """export_edge_smoothing_onnx.py:157-218; the three parameters are per-image tensors [B,1]."""
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, mask, blur_strength, edge_sensitivity, final_threshold) -> torch.Tensor:
         x = _cuda_f32(mask, "AdaptiveEdgeSmoothing")
         if x.dim() != 4 or x.shape[1] != 1:
             raise RuntimeError("AdaptiveEdgeSmoothing expects [B,1,H,W]")
         b, _, h, w = x.shape
-        if b > 65535:
-            raise _lib.HisError("AdaptiveEdgeSmoothing: at most 65535 images per call")
         prm = [t.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous() for t in (blur_strength, edge_sensitivity, final_threshold)]
         if any(t.numel() != b for t in prm):
             raise RuntimeError("AdaptiveEdgeSmoothing: parameters must hold one value per image ([B,1])")
@@ -160,6 +171,8 @@ class OptimizedEdgeSmoothing(nn.Module):
         self.use_fp16 = use_fp16
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, mask: torch.Tensor) -> torch.Tensor:
         x = _cuda_f32(mask, "OptimizedEdgeSmoothing")
         if x.dim() != 4 or x.shape[1] != 1:
@@ -178,7 +191,15 @@ class MultiClassEdgeSmoothing:
         self.device = device
 
     @torch.no_grad()
-    def smooth_predictions(self, predictions: torch.Tensor, apply_softmax: bool = False) -> torch.Tensor:
+
+    @_lib.on_tensor_device
+    def smooth_predictions(self, predictions, apply_softmax: bool = False):
+        """``predictions``: CUDA tensor, or (like the reference, edge_smoothing.py:120-124) a numpy array, which is uploaded to
+        ``self.device`` and returned as a numpy array."""
+        import numpy as np
+        if isinstance(predictions, np.ndarray):
+            out = self.smooth_predictions(torch.from_numpy(predictions).to(self.device), apply_softmax)
+            return out.cpu().numpy()
         x = _cuda_f32(predictions, "MultiClassEdgeSmoothing")
         squeeze = x.dim() == 3
         if squeeze:
@@ -220,6 +241,8 @@ class BilateralFilter(nn.Module):
         self.register_buffer("spatial_kernel", torch.exp(-(x ** 2 + y ** 2) / (2 * sigma_spatial ** 2)))
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = _cuda_f32(x, "BilateralFilter")
         out = torch.empty_like(x)
@@ -244,6 +267,8 @@ class FastBilateralFilter(nn.Module):
         self.register_buffer("kernel_v", k1.view(1, 1, kernel_size, 1))
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = _cuda_f32(x, "FastBilateralFilter")
         if self.num_iterations < 1:
@@ -263,6 +288,8 @@ class EdgePreservingFilter(nn.Module):
         self.radius, self.eps, self.kernel_size = radius, eps, 2 * radius + 1
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, x: torch.Tensor, guide: torch.Tensor = None) -> torch.Tensor:
         x = _cuda_f32(x, "EdgePreservingFilter")
         g = x if guide is None else _cuda_f32(guide, "EdgePreservingFilter")
@@ -287,6 +314,8 @@ class MaskCleanup(nn.Module):
         self.register_buffer("gaussian_kernel", _gauss2d(kernel_size, sigma_spatial, False).view(1, 1, kernel_size, kernel_size))
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         x = _cuda_f32(x, "MaskCleanup")
         out = torch.empty_like(x) if out is None else out
@@ -305,6 +334,8 @@ class BinaryMaskBilateralFilter(nn.Module):
         self.register_buffer("gaussian_kernel", _gauss2d(kernel_size, sigma_spatial, False).view(1, 1, kernel_size, kernel_size))
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = _cuda_f32(x, "BinaryMaskBilateralFilter")
         b, c, h, w = x.shape
@@ -328,6 +359,8 @@ class MorphologicalBilateralFilter(nn.Module):
         self.register_buffer("bilateral_kernel", _gauss2d(kernel_size, sigma, True).view(1, 1, kernel_size, kernel_size))
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = _cuda_f32(x, "MorphologicalBilateralFilter")
         b, c, h, w = x.shape
@@ -340,6 +373,9 @@ class MorphologicalBilateralFilter(nn.Module):
 
 
 @torch.no_grad()
+
+
+@_lib.on_tensor_device
 def paste_masks(masks_u8: torch.Tensor, rois: torch.Tensor, batch_size: int, height: int, width: int) -> torch.Tensor:
     """ROI masks [N,mh,mw] uint8 + rois [N,5] -> int32 label canvas [B,H,W]: 0 = background, i+1 = last ROI i covering
     the pixel (the reference pastes instances in order, later ones overwrite)."""
@@ -351,11 +387,6 @@ def paste_masks(masks_u8: torch.Tensor, rois: torch.Tensor, batch_size: int, hei
     r = rois.to(device=m.device, dtype=torch.float32).contiguous()
     n, mh, mw = m.shape
     canvas = torch.zeros((batch_size, height, width), dtype=torch.int32, device=m.device)
-    L = _lib.load()
-    for s in range(0, n, 65535):
-        e = min(n, s + 65535)
-        if s == 0:
-            _lib.check(L.his_post_paste(m.data_ptr(), e, mh, mw, r.data_ptr(), canvas.data_ptr(), batch_size, height, width, _stream(m)))
-        else:
-            raise _lib.HisError("paste_masks: more than 65535 ROIs per call; chunk the batch")
+    if n:
+        _lib.check(_lib.load().his_post_paste(m.data_ptr(), n, mh, mw, r.data_ptr(), canvas.data_ptr(), batch_size, height, width, _stream(m)))
     return canvas

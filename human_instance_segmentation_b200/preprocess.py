@@ -36,6 +36,9 @@ def _tables(dn: int, sn: int, vertical: bool) -> np.ndarray:
 
 
 @torch.no_grad()
+
+
+@_lib.on_tensor_device
 def prepare_images(bgr_u8: torch.Tensor, target_size: Tuple[int, int] = (640, 640), swap_rb: bool = True) -> torch.Tensor:
     """uint8 [N,Hs,Ws,3] (or [Hs,Ws,3]) CUDA tensor as ``cv2.imread`` lays it out -> float32 [N,3,H,W] in [0,1], RGB;
     ``target_size`` is (width, height) like the reference's."""

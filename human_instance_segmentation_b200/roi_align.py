@@ -25,6 +25,8 @@ class DynamicRoIAlign(nn.Module):
         self.aligned = aligned
 
     @torch.no_grad()
+
+    @_lib.on_tensor_device
     def forward(self, input_feature_map: torch.Tensor, rois: torch.Tensor, output_height, output_width) -> torch.Tensor:
         if isinstance(output_width, (list, tuple)):
             output_width = output_width[0]

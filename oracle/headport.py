@@ -395,9 +395,10 @@ def boundary_refine(sd: SD, p: str, logits: Tensor, cfg: PathConfig) -> Tensor:
     return logits + sd[p + "blend_weight"] * x * edges
 
 
-def refined_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig):
+def refined_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig, aux_branches: bool = True):
     """RefinedHierarchicalSegmentationHead.forward (..._refinement.py:734-804), preset flags only
-    (no boundary refiner / progressive / sub-pixel decoders)."""
+    (no boundary refiner / progressive / sub-pixel decoders).  aux_branches=False skips the contour / distance branches, which
+    feed aux outputs only: the exported ONNX graph (outputs: masks + binary masks, export_onnx_advanced.py:353-457) prunes them."""
     logits, aux = base_head(sd, p + "base_head.", feats, cfg)
     shared = aux["shared_features"]
     if cfg.use_progressive_upsampling:    # ProgressiveUpsamplingDecoder :152-215 replaces the hierarchical logits (:753-756)
@@ -412,6 +413,8 @@ def refined_head(sd: SD, p: str, feats: Tensor, cfg: PathConfig):
         logits = _to_mask_size(F.pixel_shuffle(conv(sd, p + "subpixel_decoder.conv.", shared, 1), 2), cfg)
     if cfg.use_boundary_refinement:   # BoundaryRefinementModule :58-149
         logits = boundary_refine(sd, p + "boundary_refiner.", logits, cfg)
+    if not aux_branches:
+        return logits, aux
     if cfg.use_contour_detection:     # ContourDetectionBranch :255-295
         c = p + "contour_branch.contour_branch."
         x = act_ref(norm(sd, c + "1.", conv(sd, c + "0.", shared, 1), cfg), cfg)
@@ -536,8 +539,9 @@ def forward_multiscale(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig):
 
 
 @torch.no_grad()
-def forward(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig, full_image_logits: Tensor = None):
-    """HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet.forward (rgb.py:729-774)."""
+def forward(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig, full_image_logits: Tensor = None, masks_only: bool = False):
+    """HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet.forward (rgb.py:729-774).  masks_only: the work of the exported
+    ONNX contract (no aux-only contour / distance branches), see refined_head."""
     if cfg.multi_scale:
         return forward_multiscale(sd, images, rois, cfg)
     if not cfg.use_pretrained_unet:
@@ -551,7 +555,7 @@ def forward(sd: SD, images: Tensor, rois: Tensor, cfg: PathConfig, full_image_lo
     feats = rgb_feature_extractor(sd, roi_rgb, cfg)
     if uses_refined_head(cfg):
         comb = conv(sd, "feature_combiner.", torch.cat([feats, roi_masks], 1), 0)
-        logits, aux = refined_head(sd, "segmentation_head.", comb, cfg)
+        logits, aux = refined_head(sd, "segmentation_head.", comb, cfg, aux_branches=not masks_only)
     else:
         logits, aux = guided_head(sd, "segmentation_head.", feats, roi_masks, cfg)
     aux["full_image_logits"] = full_image_logits

@@ -308,3 +308,79 @@ def test_pipelined_infer_matches_blocking_infer():
     m.pipeline_sync()
     for (wi, wb), (oi, ob) in zip(want, outs):
         assert torch.equal(oi, wi) and torch.equal(ob, wb)
+
+
+def test_plan_cache_buckets_random_shapes_under_a_byte_budget():
+    """Dynamic `batch_size` / `num_rois` of the exported contract (export_onnx_advanced.py:427-457): requests of any (B, N) run on
+    capacity-bucketed launch plans (masked tail), least-recently-used plans are evicted under a byte budget, and the results are
+    bit-identical to exact-size plans."""
+    cfg = common.SMALL_CASES["small_b0_bn_relu"][0]
+    shapes = common.shapes_for_case("small_b0_bn_relu")
+    m = build(cfg, shapes)
+    exact = build(cfg, shapes)
+    exact.plan_buckets = False
+    g = torch.Generator().manual_seed(17)
+    # budget: about three plans of the largest geometry
+    probe_im, probe_r = common.synth_images(1, 20, 64, 96), common.synth_rois(1, 20, 4)
+    m(probe_im.cuda(), probe_r.cuda())
+    one = m.plan_bytes()
+    m.release_plans()
+    m.max_plan_bytes = 3 * one
+    seen_keys, built = set(), 0
+    for it in range(50):
+        b = int(torch.randint(1, 21, (1,), generator=g))
+        per = int(torch.randint(0, 5, (1,), generator=g))
+        images = common.synth_images(100 + it, b, 64, 96)
+        if it % 7 == 3:
+            images = images * 255.0                      # the whole-batch x.max() > 1 branch must not see stale tail images
+        rois = common.synth_rois(100 + it, b, per)[: int(torch.randint(0, b * per + 1, (1,), generator=g))] if per else torch.zeros(0, 5)
+        before = set(m._plans)
+        got, aux = m(images.cuda(), rois.cuda())
+        built += len(set(m._plans) - before)
+        seen_keys.add((b, rois.shape[0]))
+        want, want_aux = exact(images.cuda(), rois.cuda())
+        assert got.shape == want.shape == (rois.shape[0], 3, 32, 24)
+        assert torch.equal(got, want), (it, b, rois.shape[0])
+        assert torch.equal(aux["full_image_logits"], want_aux["full_image_logits"])
+        if rois.shape[0]:
+            assert torch.equal(aux["bg_fg_logits_low"], want_aux["bg_fg_logits_low"])
+        assert m.plan_bytes() <= m.max_plan_bytes or len(m._plans) == 1
+        if it % 10 == 9:
+            exact.release_plans()
+    assert built < len(seen_keys), (built, len(seen_keys))        # buckets are shared between request shapes
+    # the pipelined host API serves changing ROI counts from the same buckets
+    m.use_cuda_graph = True
+    outs = []
+    for n in (5, 3, 6):
+        images, rois = common.synth_images(7, 2, 64, 96), common.synth_rois(7, 2, 3)[:n]
+        oi, ob = torch.empty(n, 1, 32, 24).pin_memory(), torch.empty(2, 1, 64, 96).pin_memory()
+        m.infer_pipelined(images.pin_memory(), rois.pin_memory(), oi, ob)
+        outs.append((images, rois, oi, ob))
+    m.pipeline_sync()
+    for images, rois, oi, ob in outs:
+        wi, wb = exact.infer(images.cuda(), rois.cuda())
+        assert torch.equal(oi, wi.cpu()) and torch.equal(ob, wb.cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_model_on_second_gpu_while_current_device_is_first():
+    """One process driving several GPUs: per-device kernel attributes / SM counts, launches on the tensor's device."""
+    cfg, images, rois = common.small_case_inputs("small_b0_bn_relu")
+    g = common.golden("small_b0_bn_relu")
+    torch.cuda.set_device(0)
+    m0 = build(cfg, common.shapes_for_case("small_b0_bn_relu"))
+    a, _ = m0(images.cuda(0), rois.cuda(0))
+    m1 = his.create_rgb_hierarchical_model(**cfg.factory_kwargs())
+    m1.load_state_dict(common.procedural_state(common.shapes_for_case("small_b0_bn_relu"), weights_path=cfg.pretrained_weights_path))
+    m1 = m1.to("cuda:1")
+    for ra in (m1.roi_align_mask, m1.roi_align_rgb):
+        ra.spatial_scale = cfg.spatial_scale
+        ra.spatial_scale_h, ra.spatial_scale_w = cfg.spatial_scale
+    m1.use_cuda_graph = True
+    assert torch.cuda.current_device() == 0
+    b, _ = m1(images.cuda(1), rois.cuda(1))
+    inst, _ = m1.infer(images.cuda(1), rois.cuda(1))
+    assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
+    check(b, g["logits"], "logits(cuda:1)")
+    dil = his.postprocess.MaskDilationModule(1)(b)
+    assert dil.device.index == 1 and torch.cuda.current_device() == 0
