@@ -160,7 +160,7 @@ class _PlannedModel(nn.Module):
         # plan with a masked tail (zero images, zero-area ROIs; outputs sliced), bit-identical to an exact-size plan because no
         # kernel mixes data across images or ROIs.  Plans are evicted least-recently-used once their buffers exceed the budget.
         self.plan_buckets = True
-        self.max_plan_bytes = 64 << 30
+        self.max_plan_bytes = None       # None: 70 % of the device's memory
         self._plans: "collections.OrderedDict[tuple, _BuiltPlan]" = collections.OrderedDict()
         self.eval()
 
@@ -228,12 +228,13 @@ class _PlannedModel(nn.Module):
                tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index, slot, self.use_cuda_graph)
         bp = self._plans.get(key)
         if bp is None:
-            self._evict(self.max_plan_bytes)
+            budget = self.max_plan_bytes if self.max_plan_bytes is not None else int(0.7 * torch.cuda.get_device_properties(dev).total_memory)
+            self._evict(budget)
             bp = _BuiltPlan(self, dev, Bc, H, W, Nc)
             if self.use_cuda_graph:
                 bp.plan.capture()
             self._plans[key] = bp
-            self._evict(self.max_plan_bytes, protect=key)
+            self._evict(budget, protect=key)
         else:
             self._plans.move_to_end(key)
         bp.set_active(B, N)
@@ -487,8 +488,16 @@ class _CompositePlan:
     """bench/graph-facing view of the (UNet sub-plan x image chunks) + (head sub-plan x ROI chunks) schedule."""
 
     def __init__(self, bp: "_BuiltPlan"):
-        self.bp = bp
+        import weakref
+        self._bp = weakref.ref(bp)           # the built plan owns this object: no reference cycle, buffers are freed on eviction
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    @property
+    def bp(self) -> "_BuiltPlan":
+        bp = self._bp()
+        if bp is None:
+            raise _lib.HisError("launch plan used after it was released")
+        return bp
 
     def _parts(self):
         bp = self.bp
