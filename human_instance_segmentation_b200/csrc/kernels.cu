@@ -1509,9 +1509,12 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
   return HIS_OK;
 }
 
-static int pool_grid_x(long long per_img, int threads, int N, int per_sm, int cgs) {
+// Blocks per image of the pixel reductions.  `fixed_cap` > 0: the count depends on the per-image size only, never on the batch --
+// the partial sums of an image (and with them every bit of its result) are then the same whatever batch the image arrives in
+// (capacity-bucketed launch plans, sharded batches).  fixed_cap == 0: the register-resident depthwise fallback, sized to the batch.
+static int pool_grid_x(long long per_img, int threads, int N, int per_sm, int cgs, int fixed_cap = 0) {
   long long gx = (per_img + threads - 1) / threads;
-  const long long cap = (148LL * per_sm + N - 1) / (N > 0 ? N : 1);
+  const long long cap = fixed_cap > 0 ? fixed_cap : (148LL * per_sm + N - 1) / (N > 0 ? N : 1);
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   const int m = grid_multiple(cgs, threads);
@@ -1544,7 +1547,7 @@ int his_depthwise_pool_parts(int N, int H, int W, int C, int k, int stride) {
 int his_pool_sum_parts(int N, int HW, int C) {
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return 0;
-  return pool_grid_x(((long long)HW * (C / 8) + 7) / 8, threads, N, 8, C / 8);
+  return pool_grid_x(((long long)HW * (C / 8) + 31) / 32, threads, N, 8, C / 8, 64);
 }
 
 int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, const void* w, const float* scale, const float* shift, int k,
@@ -1632,7 +1635,7 @@ int his_pool_sum(const void* in, int N, int HW, int C, int cs, float* pool_sums,
   const long long per_img = (long long)HW * (C / 8);
   const int threads = threads_multiple_of(C / 8);
   if (threads == 0) return his_set_error(HIS_ERR_UNSUPPORTED, "pool_sum: more than 8192 channels");
-  const int gx = pool_grid_x((per_img + 7) / 8, threads, N, 8, C / 8);
+  const int gx = pool_grid_x((per_img + 31) / 32, threads, N, 8, C / 8, 64);
   dim3 grid(gx, N);
   pool_sum_kernel<<<grid, threads, threads * 8 * sizeof(float), ST>>>((const __half*)in, HW, C, cs, split ? cs / 2 : 0, pool_sums);
   HIS_CHECK_LAUNCH();
@@ -1682,9 +1685,9 @@ int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int 
 }
 
 int his_layernorm2d_parts(int N, int HW, int C) {
-  long long gx = ((long long)HW * (C / 8) + kThreads * 4 - 1) / (kThreads * 4);
-  const long long cap = (148LL * 8 + N - 1) / (N > 0 ? N : 1);
-  if (gx > cap) gx = cap;
+  (void)N;      // independent of the batch: an image's statistics are summed in the same order whatever batch it arrives in
+  long long gx = ((long long)HW * (C / 8) + kThreads * 16 - 1) / (kThreads * 16);
+  if (gx > 64) gx = 64;
   return (int)(gx < 1 ? 1 : gx);
 }
 
@@ -1711,9 +1714,9 @@ int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const f
 }
 
 int his_groupnorm_parts(int N, int HW, int C) {
+  (void)N; (void)C;                                         // independent of the batch (see his_layernorm2d_parts)
   long long parts = (HW + 255) / 256;                       // >= 256 pixels per block
-  const long long cap = (148LL * 8 + N - 1) / (N > 0 ? N : 1);
-  if (parts > cap) parts = cap;
+  if (parts > 64) parts = 64;
   return (int)(parts < 1 ? 1 : parts);
 }
 

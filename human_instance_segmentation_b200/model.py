@@ -228,6 +228,7 @@ class _PlannedModel(nn.Module):
                tuple((_scale_hw(ra), ra.aligned) for ra in self._aligners()), dev.index, slot, self.use_cuda_graph)
         bp = self._plans.get(key)
         if bp is None:
+            self.plans_built = getattr(self, "plans_built", 0) + 1
             budget = self.max_plan_bytes if self.max_plan_bytes is not None else int(0.7 * torch.cuda.get_device_properties(dev).total_memory)
             self._evict(budget)
             bp = _BuiltPlan(self, dev, Bc, H, W, Nc)

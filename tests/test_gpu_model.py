@@ -229,7 +229,9 @@ def test_model_matches_reference_golden_real_geometry(name, precision):
     assert agree >= amin          # fast mode on B7 ultra: 99.88 % measured (2.0e-3 L2), strict: >= 99.9 %
     check(aux["full_image_logits"][:, 0, ::4, ::4], g["full_image_logits_ch0_s4"], "full_image_logits", l2, mx)
     check(aux["shared_features"][:, ::16, ::4, ::4], g["shared_features_sub"], "shared_features", l2, mx)
-    check(aux["fg_attention"][:, ::16, ::4, ::4], g["fg_attention_sub"], "fg_attention", l2, mx)
+    # the gate is a sigmoid of a 3-layer 1x1 stack on the low-resolution logits: single-fp16 operands leave up to 9e-3 at isolated
+    # pixels on B7 ultra (L2 1.5e-3); strict mode holds the common bound
+    check(aux["fg_attention"][:, ::16, ::4, ::4], g["fg_attention_sub"], "fg_attention", l2, mx if precision == "strict" else 1.5e-2)
     check(aux["bg_fg_logits_low"], g["bg_fg_logits_low"], "bg_fg_logits_low", l2, mx)
     check(aux["roi_features"], g["roi_features"], "roi_features", l2, mx)
     check(aux["target_nontarget_logits"][:, :, ::2, ::2], g["target_nontarget_logits_s2"], "target_nontarget_logits", l2, mx)
