@@ -437,7 +437,7 @@ def measure_model(ctx, workload, steps, warmup, precision="fast", e2e="pipelined
         e1.record()
         ctx.barrier()
         ms_e2e_full = e0.elapsed_time(e1) / steps
-    plans_built, plan_gb = getattr(model, "plans_built", 0), model.plan_bytes() / 1e9
+    plans_built, plan_gb, plan_log = getattr(model, "plans_built", 0), model.plan_bytes() / 1e9, list(getattr(model, "plan_log", []))
     model.release_plans()
 
     gemm = [(t, f) for name, t, f in timed if name == "conv_gemm"]
@@ -490,7 +490,7 @@ def measure_model(ctx, workload, steps, warmup, precision="fast", e2e="pipelined
             "blocking_value": (world * n_rois / (ms_e2e_blocking * 1e-3)) if ms_e2e_blocking else None,
             "full_forward_value": (world * n_rois / (ms_e2e_full * 1e-3)) if ms_e2e_full else None,
             "h2d_bytes_per_step": images_h.numel() * 4 + rois_h.numel() * 4, "d2h_bytes_per_step": inst_h.numel() * 4 + bin_h.numel() * 4,
-            "launch_plans_built_in_run": plans_built, "launch_plan_gb_at_end": round(plan_gb, 2),
+            "launch_plans_built_in_run": plans_built, "launch_plan_gb_at_end": round(plan_gb, 2), "launch_plan_log": plan_log,
             "api": ("model.infer_pipelined(images_host_pinned, rois_host, instance_masks_host, binary_masks_host): upload / forward / download of "
                     "consecutive batches overlap on three streams, two launch plans; every step's H2D and D2H are inside the timed region" if "pipelined" in e2e
                     else "model.infer(images_host_pinned, rois_host) -> (instance_masks, binary_masks) copied to pinned host") +

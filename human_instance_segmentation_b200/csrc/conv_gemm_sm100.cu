@@ -142,7 +142,7 @@ int encode_weight_map(CUtensorMap* m, const void* base, int K, long long rows, i
 }
 
 struct ConvGemmPlan {
-  CUtensorMap tmA, tmB, tmO[4], tmR;
+  CUtensorMap tmA, tmB, tmO[4], tmR, tmAux;
   ConvGemmParams p;
   int grid, bk, smem, actc, res_mode, transposed, cin_pad, halo, b_box_rows, pair_grid_checked, split;
   ConvGemmKernel kernel;
@@ -283,6 +283,16 @@ int his_conv_gemm_create(void** out_plan,
   his_conv_gemm_tile_n(cout, &p.n_tiles, &p.block_n);
   p.groups = transposed ? 4 : 1;
   p.cout_slab = p.n_tiles * p.block_n;
+  p.phase_merge = 1; p.phase_slab = p.block_n;
+  if (transposed && p.n_tiles == 1 && (p.block_n % 32) == 0) {
+    // ConvTranspose k2s2 = four 1x1 phase GEMMs over the same A: merge as many phases as fit a 256-wide N tile (the packed
+    // weight rows of the phases are contiguous, so the slab layout does not change).  HIS_GEMM_CONVT_MERGE=0 keeps four groups.
+    int merge = 256 / p.block_n >= 4 ? 4 : 256 / p.block_n >= 2 ? 2 : 1;
+    if (const char* e = getenv("HIS_GEMM_CONVT_MERGE")) if (atoi(e) == 0) merge = 1;
+    if (merge > 1) {
+      p.phase_merge = merge; p.block_n *= merge; p.groups = 4 / merge; p.cout_slab = p.block_n;
+    }
+  }
   p.num_work = n_img * p.tiles_y * p.tiles_x * p.n_tiles * p.groups;
   int actc = ACTC_CLAMP;
   p.act_lo = -INFINITY; p.act_beta = 1.0f; p.act_mul_x = 0;
@@ -382,6 +392,7 @@ int his_conv_gemm_create(void** out_plan,
   } else {
     pl->tmR = pl->tmO[0];
   }
+  pl->tmAux = pl->tmO[0];
   pl->grid = p.num_work < num_sms ? p.num_work : num_sms;
   if (p.pair) { pl->grid &= ~1; pl->kernel = pick_pair_kernel(actc, res_mode, halo); }
   *out_plan = pl;
@@ -460,6 +471,36 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   if (pl->bk != 64 || pl->transposed || pl->p.tail_c)
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_aux: needs a 64-wide K block (Cin >= 64), not transposed, no fused tail");
   pl->p.aux_out = aux_out;
+  // export through a [32 ch][128 px] fp32 staging tile + one TMA store per chunk when the rows are 16-byte addressable and the
+  // 32 KB of staging can be taken from the operand rings (HIS_GEMM_AUX_TMA=0: per-thread strided stores)
+  ConvGemmParams& p = pl->p;
+  int want = (p.W % 4) == 0;
+  if (const char* e = getenv("HIS_GEMM_AUX_TMA")) want = want && atoi(e) != 0;
+  p.aux_tma = 0;
+  if (want) {
+    const int need = 2 * kAuxStagingBytes;
+    bool ok = true;
+    if (!pl->halo) {
+      const int st = (KCfg<64>::kRingBytes - need) / p.stage_bytes;
+      if (st >= 2) { if (st < p.stages) p.stages = st; } else ok = false;
+    } else {
+      const int budget = KCfg<64>::kRingBytes - need;
+      while (p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes > budget && p.a_stages > 2) --p.a_stages;
+      while (p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes > budget && p.stages > 2 && !p.b_resident) --p.stages;
+      ok = p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes <= budget;
+    }
+    if (ok) {
+      PFN_encodeTiled enc = get_encode();
+      cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.cout, (cuuint64_t)p.n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H * p.W * 4, (cuuint64_t)p.cout * p.H * p.W * 4};
+      cuuint32_t box[4] = {(cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)kChunkC, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      if (enc && !((uintptr_t)aux_out & 15) &&
+          enc(&pl->tmAux, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, aux_out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        p.aux_tma = 1;
+    }
+  }
   pl->kernel = pl->split ? (ConvGemmKernel)his_gemm_pick_split_kernel(64, pl->actc, pl->res_mode, EPI_AUX, pl->halo)
                : pl->p.pair ? pick_pair_aux_kernel(pl->actc, pl->res_mode, pl->halo) : pick_aux_kernel(pl->actc, pl->res_mode, pl->halo);
   return HIS_OK;
@@ -484,12 +525,12 @@ int his_conv_gemm_run(void* plan, void* stream) {
       cfg.gridDim = dim3(pl->grid);
       pl->pair_grid_checked = 1;
     }
-    if (cudaLaunchKernelEx(&cfg, pl->kernel, pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR, pl->p) != cudaSuccess)
+    if (cudaLaunchKernelEx(&cfg, pl->kernel, pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR, pl->tmAux, pl->p) != cudaSuccess)
       return his_set_error(HIS_ERR_LAUNCH, cudaGetErrorString(cudaGetLastError()));
     return HIS_OK;
   }
   pl->kernel<<<pl->grid, kThreadsGemm, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
-                                                               pl->p);
+                                                               pl->tmAux, pl->p);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -56,6 +56,7 @@ constexpr int kHaloBw = 8, kHaloBh = 16;               // tile = 8 x 16 output p
 constexpr int kHaloW = kHaloBw + 2, kHaloH = kHaloBh + 2, kHaloPix = kHaloW * kHaloH;
 constexpr int kPlaneBytes = (kHaloPix + 1) * 16;       // 2896: +16 B so the planes of one pixel fall in distinct 16-byte bank groups
 constexpr int kAProducerThreads = 64;                  // warps 2 and 3
+constexpr int kAuxStagingBytes = kChunkC * kBlockM * 4; // EPI_AUX: one [32 channels][128 pixels] fp32 tile per epilogue group
 constexpr int kMaxAStages = 24, kMaxBStages = 16;
 
 // K-block width BK (fp16 elements) selects the shared-memory swizzle: one row of the operand tile is BK*2 bytes.
@@ -117,6 +118,8 @@ struct ConvGemmParams {
   int tail_c, tail_sigmoid, store_main;
   // fp32 NCHW copy of the layer output (EPI_AUX kernels): aux[n][c][y][x] = y, or the gate itself (before the product) for RES_MUL
   float* aux_out;
+  int aux_tma;          // 1: the export leaves through a [32 ch][128 px] fp32 staging tile and ONE TMA store per chunk (coalesced
+                        // 64-byte rows per channel) instead of 32 strided 4-byte stores per thread; needs W % 4 == 0
   int cout;             // true output channel count
   // split-fp16 ("strict" precision) operands, SPLIT kernels only: every activation is a pair of fp16 planes x = hi + lo that live
   // lo elements apart inside one pixel ([hi channels | lo channels], lo = pixel stride / 2), the packed weights are [W_hi | W_lo]
@@ -124,6 +127,10 @@ struct ConvGemmParams {
   // lo.lo term is below 2^-22 relative); products of fp16 pairs are exact in the fp32 accumulator, so the result carries ~21
   // significant bits.  The epilogue emits hi = fp16(y), lo = fp16(y - hi).  kblocks_per_tap holds the VIRTUAL count (3x).
   int nblk_phys, cin_pad1, in_lo, up_lo, out_lo, res_lo;
+  // conv_transpose k2s2 with merged phases: one N tile holds phase_merge (2 or 4) of the four (dy,dx) phase GEMMs, phase_slab
+  // columns each, so the A tile is read 4 / phase_merge times instead of four and the MMAs run at N = 256; every 32-channel
+  // epilogue chunk goes to its phase's strided output map.  phase_merge == 1: one group per phase (or not transposed).
+  int phase_merge, phase_slab;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1)
 conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                        const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
-                       const __grid_constant__ CUtensorMap tmR, const ConvGemmParams p) {
+                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmAux, const ConvGemmParams p) {
   using Cfg = KCfg<BK>;
   const int kStages = p.stages;
   extern __shared__ uint8_t smem_raw[];
@@ -381,6 +388,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   auto apeer_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + 2 * p.a_stages + s); };   // pair: the peer's window is complete
   const int n_acc = p.n_acc;
   const uint32_t a_base = bar_base + kBarrierBytes;
+  // EPI_AUX: fp32 export staging (one tile per epilogue group) behind the halo ring
+  const uint32_t aux_base = a_base + (uint32_t)(HALO ? p.a_stages * p.a_stage_bytes : 0);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to the aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -416,7 +425,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   // single N tile: the per-channel shift stays in shared memory for the whole kernel
   float* s_shift = reinterpret_cast<float*>(smem_gen + (shift_base - smem_base));
   if (p.n_tiles == 1)
-    for (int i = threadIdx.x; i < p.block_n; i += kThreadsGemm) s_shift[i] = __ldg(p.shift + i);
+    for (int i = threadIdx.x; i < p.block_n; i += kThreadsGemm) s_shift[i] = __ldg(p.shift + (p.phase_merge > 1 ? i % p.phase_slab : i));
   tc_fence_before();
   __syncthreads();
   if (pair) cluster_sync_all();        // the peer's barriers are initialised and its TMEM is allocated before anything remote happens
@@ -698,7 +707,6 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += 2 * gridDim.x) {
       const WorkItem it = decode_work(p, w);
       const uint32_t acc_col = (uint32_t)(acc * p.acc_stride);
-      const CUtensorMap* tmO = it.group == 0 ? &tmO0 : it.group == 1 ? &tmO1 : it.group == 2 ? &tmO2 : &tmO3;
       const int chbase = it.n_tile * p.block_n;
       const float* shp = p.n_tiles == 1 ? s_shift : p.shift + chbase;
       // A chunk goes through the swizzled staging buffer + TMA when its 32-channel x 128-pixel box lies fully inside the tensor.
@@ -754,6 +762,9 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int cl0 = j * kChunkC;            // first channel of this chunk within the N tile
         const int ch0 = chbase + cl0;           // ... and within the layer
         const int ncol = min(kChunkC, p.block_n - cl0);   // valid accumulator columns in this chunk (16 or 32)
+        const bool aux_tma = EPI == EPI_AUX && p.aux_tma;
+        if (aux_tma && issuer_warp && elect_one()) tma_wait_read<0>();     // the (single) export tile and staging[b] are free again
+        if (direct && aux_tma) asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (!direct) {
           if (SPLIT) {
             if ((!RES || res_glob || j >= 1) && issuer_warp && elect_one()) {
@@ -787,6 +798,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         if (RES && !direct && !res_glob) { mbar_wait(res_bar(2 * g + b), (res_phase >> b) & 1u); res_phase ^= 1u << b; }
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
+        float* aux_row = reinterpret_cast<float*>(smem_gen + (aux_base - smem_base) + g * kAuxStagingBytes) + te;
 #pragma unroll
         for (int i = 0; i < kChunkC / 8; ++i) {
           if (i * 8 < ncol) {
@@ -830,7 +842,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               float t = __uint_as_float(v[i * 8 + e]) * rs + sh[e];
               if (RES == HIS_RES_ADD) t += r[e];
               t = epi_act<ACTC>(t, p);
-              if (EPI == EPI_AUX) { if (aux_px && c + e < p.cout) aux_px[(long long)(c + e) * p.H * p.W] = t; }
+              if (EPI == EPI_AUX) {
+                if (aux_tma) aux_row[(i * 8 + e) * kBlockM] = t;      // [channel][pixel]: lanes write consecutive words
+                else if (aux_px && c + e < p.cout) aux_px[(long long)(c + e) * p.H * p.W] = t;
+              }
               if (RES == HIS_RES_MUL) t *= r[e];
               y[e] = t;
             }
@@ -874,16 +889,25 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
         }
-        if (store_main && !direct) {
+        if ((store_main && !direct) || aux_tma) {
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           if (issuer_warp && elect_one()) {
-            if (SPLIT) {
-              tma_store_5d(tmO, stg0, ch0, 0, it.x0, it.y0, it.img);
-              tma_store_5d(tmO, stg0 + kStagingBytes, ch0, 1, it.x0, it.y0, it.img);
-            } else {
-              tma_store_4d(tmO, stg, ch0, it.x0, it.y0, it.img);
+            if (store_main && !direct) {
+              // merged ConvT phases: the chunk belongs to phase (group * merge + cl0 / phase_slab) and to its output map
+              const int ph = p.phase_merge > 1 ? cl0 / p.phase_slab : 0;
+              const int ch_st = p.phase_merge > 1 ? cl0 - ph * p.phase_slab : ch0;
+              const int gsel = p.phase_merge > 1 ? it.group * p.phase_merge + ph : it.group;
+              const CUtensorMap* tmOj = gsel == 0 ? &tmO0 : gsel == 1 ? &tmO1 : gsel == 2 ? &tmO2 : &tmO3;
+              if (SPLIT) {
+                tma_store_5d(tmOj, stg0, ch_st, 0, it.x0, it.y0, it.img);
+                tma_store_5d(tmOj, stg0 + kStagingBytes, ch_st, 1, it.x0, it.y0, it.img);
+              } else {
+                tma_store_4d(tmOj, stg, ch_st, it.x0, it.y0, it.img);
+              }
             }
+            // fp32 NCHW export: box {bw, bh, 32 channels, 1} of the map {W, H, C, N}; the TMA unit clips image edges / channel tail
+            if (aux_tma) tma_store_4d(&tmAux, aux_base + g * kAuxStagingBytes, it.x0, it.y0, ch0, it.img);
             tma_commit();
           }
         }
@@ -919,5 +943,5 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 typedef void (*ConvGemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                               const CUtensorMap, const CUtensorMap, const ConvGemmParams);
+                               const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvGemmParams);
 }  // namespace

@@ -235,6 +235,7 @@ class _PlannedModel(nn.Module):
             if self.use_cuda_graph:
                 bp.plan.capture()
             self._plans[key] = bp
+            self.plan_log = getattr(self, "plan_log", [])[-63:] + [("build", Bc, Nc, self.aux_outputs, self.precision, slot, round(bp.nbytes / 1e9, 2))]
             self._evict(budget, protect=key)
         else:
             self._plans.move_to_end(key)
@@ -249,6 +250,7 @@ class _PlannedModel(nn.Module):
             if victim is None:
                 break
             torch.cuda.synchronize()           # its kernels may still be running
+            self.plan_log = getattr(self, "plan_log", [])[-63:] + [("evict", victim[0], victim[3], round(self._plans[victim].nbytes / 1e9, 2))]
             del self._plans[victim]
 
 
@@ -566,7 +568,7 @@ class _BuiltPlan:
     def __init__(self, m: HierarchicalRGBSegmentationModelWithFullImagePretrainedUNet, dev, B, H, W, N):
         self.m, self.dev, self.B, self.H, self.W, self.N = m, dev, B, H, W, N      # B, N: CAPACITY of the plan
         self.nB, self.nN = B, N                                                    # images / ROIs of the current request
-        self._filled_B, self._filled_N = 0, 0                                      # buffer rows that may hold stale inputs
+        self._filled_B, self._filled_N = B, 0          # buffer rows that may hold stale inputs (images: allocated uninitialised)
         self.split = getattr(m, "precision", "fast") == "strict"
         self.S = 1 if self.split else 0          # the `split` argument of the C entry points
         self.act_rgb = {"relu": ACT["relu"], "swish": ACT["silu"], "silu": ACT["silu"], "gelu": ACT["gelu"]}[m.activation_function]
@@ -574,8 +576,10 @@ class _BuiltPlan:
         self.beta = m.activation_beta
         self.has_unet = hasattr(m, "pretrained_unet")
         stem_c = m.pretrained_unet.model.model.encoder.out_channels[1] if self.has_unet else 32
-        self.Bc = min(B, m.max_images_per_pass or _images_per_pass(H, W, stem_c)) if self.has_unet else B
-        self.Nc = min(N, m.max_rois_per_pass or _rois_per_pass(m.roi_size))
+        # strict mode stores two fp16 planes per activation: half the images / ROIs per pass keep the footprint of a plan
+        div = 2 if self.split else 1
+        self.Bc = min(B, m.max_images_per_pass or max(1, _images_per_pass(H, W, stem_c) // div)) if self.has_unet else B
+        self.Nc = min(N, m.max_rois_per_pass or max(1, _rois_per_pass(m.roi_size) // div))
         self.chunked_unet, self.chunked_head = self.Bc < B, self.Nc < N
         self.n_unet_chunks = (B + self.Bc - 1) // self.Bc if self.has_unet else 0
         self.n_head_chunks = (N + self.Nc - 1) // self.Nc if N else 0
