@@ -92,6 +92,94 @@ __global__ void roi_align_kernel(const T* __restrict__ feat, long long sN, long 
   }
 }
 
+// Both aligners of the model in ONE launch (rgb.py:751-755: roi_align_mask on the 2-channel UNet logits, roi_align_rgb on the
+// image), one WARP per (ROI, output row): an output row samples two source rows (iy, iy+1) over the ROI's x extent, so the warp
+// stages exactly that segment of every channel in shared memory with coalesced 128-byte row reads (each source pixel is read
+// once, instead of up to two 4-byte sector-sized gathers per output tap) and then every lane interpolates its output pixels
+// from the staged rows, in the same operation order as roi_align_kernel (identical results).  Outputs go straight into the
+// consumers' layouts: the NHWC fp16 slices (mask logits -> channels 256..257 of the feature_combiner input, RGB patches -> the
+// 3->64 conv's input) and the NCHW fp32 aux tensors.  Segments longer than kRoiSeg pixels fall back to direct gathers.
+constexpr int kRoiSeg = 296, kRoiWarps = 4, kRoiMaxC = 5;
+struct RoiSrc {
+  const float* feat; int C;            // [B,C,H,W] fp32 contiguous
+  float scale_h, scale_w; int aligned;
+  __half* out_h; int out_cs, out_lo;   // NHWC fp16 slice (may be null)
+  float* out_f;                        // NCHW fp32 [n_rois,C,oh,ow] (may be null)
+};
+__global__ void __launch_bounds__(kRoiWarps * 32) roi_align_rows_kernel(RoiSrc s0, RoiSrc s1, int B, int H, int W, const float* __restrict__ rois,
+                                                                        int n_rois, int oh, int ow) {
+  __shared__ float s_seg[kRoiWarps][kRoiMaxC][2][kRoiSeg];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row_id = (long long)blockIdx.x * kRoiWarps + warp;
+  if (row_id >= (long long)n_rois * oh) return;
+  const int k = (int)(row_id / oh), oy = (int)(row_id - (long long)k * oh);
+  const float* r = rois + 5 * k;
+  const int b = (int)r[0];
+  int ch_base = 0;
+#pragma unroll
+  for (int si = 0; si < 2; ++si) {
+    const RoiSrc& s = si == 0 ? s0 : s1;
+    if (s.C == 0) continue;
+    const float x1 = __fmul_rn(r[1], s.scale_w), y1 = __fmul_rn(r[2], s.scale_h);
+    const float x2 = __fmul_rn(r[3], s.scale_w), y2 = __fmul_rn(r[4], s.scale_h);
+    const float py = roi_px(y1, y2, linspace01(oy, oh), H, s.aligned);
+    const float fy0 = floorf(py);
+    const int iy = (int)fy0;
+    const float wy1 = py - fy0, wy0 = (fy0 + 1.0f) - py;
+    const bool okb = (b >= 0 && b < B) && isfinite(py);
+    const bool y0ok = okb && iy >= 0 && iy < H, y1ok = okb && iy + 1 >= 0 && iy + 1 < H;
+    // x extent of the row's samples (the grid is monotonic in ox; either direction)
+    const float pxa = roi_px(x1, x2, linspace01(0, ow), W, s.aligned), pxb = roi_px(x1, x2, linspace01(ow - 1, ow), W, s.aligned);
+    const bool finite_x = isfinite(pxa) && isfinite(pxb);
+    int lo = 0, hi = -1;
+    if (finite_x) {
+      lo = max((int)floorf(fminf(pxa, pxb)), 0);
+      hi = min((int)floorf(fmaxf(pxa, pxb)) + 1, W - 1);
+    }
+    const bool staged = finite_x && (hi - lo + 1) <= kRoiSeg;
+    const float* img = s.feat + (long long)(okb ? b : 0) * s.C * H * W;
+    if (staged) {
+      for (int c = 0; c < s.C; ++c)
+        for (int rr = 0; rr < 2; ++rr) {
+          const bool rok = rr == 0 ? y0ok : y1ok;
+          const float* src = img + ((long long)c * H + (iy + rr)) * W + lo;
+          for (int i = lane; i <= hi - lo; i += 32) s_seg[warp][ch_base + c][rr][i] = rok ? __ldg(src + i) : 0.0f;
+        }
+    }
+    __syncwarp();
+    for (int ox = lane; ox < ow; ox += 32) {
+      const float px = roi_px(x1, x2, linspace01(ox, ow), W, s.aligned);
+      const float fx0 = floorf(px);
+      const int ix = (int)fx0;
+      const float wx1 = px - fx0, wx0 = (fx0 + 1.0f) - px;
+      const bool okx = isfinite(px);
+      const bool x0ok = okx && ix >= 0 && ix < W, x1ok = okx && ix + 1 >= 0 && ix + 1 < W;
+      const long long opix = ((long long)k * oh + oy) * ow + ox;
+      for (int c = 0; c < s.C; ++c) {
+        float v = 0.0f;
+        if (staged) {
+          const float* t0 = s_seg[warp][ch_base + c][0];
+          const float* t1 = s_seg[warp][ch_base + c][1];
+          if (x0ok && y0ok) v += t0[ix - lo] * (wx0 * wy0);
+          if (x1ok && y0ok) v += t0[ix + 1 - lo] * (wx1 * wy0);
+          if (x0ok && y1ok) v += t1[ix - lo] * (wx0 * wy1);
+          if (x1ok && y1ok) v += t1[ix + 1 - lo] * (wx1 * wy1);
+        } else {
+          const float* base = img + (long long)c * H * W;
+          if (x0ok && y0ok) v += __ldg(base + (long long)iy * W + ix) * (wx0 * wy0);
+          if (x1ok && y0ok) v += __ldg(base + (long long)iy * W + ix + 1) * (wx1 * wy0);
+          if (x0ok && y1ok) v += __ldg(base + (long long)(iy + 1) * W + ix) * (wx0 * wy1);
+          if (x1ok && y1ok) v += __ldg(base + (long long)(iy + 1) * W + ix + 1) * (wx1 * wy1);
+        }
+        if (s.out_h) his_st1(s.out_h + opix * s.out_cs + c, s.out_lo, v);
+        if (s.out_f) s.out_f[(((long long)k * s.C + c) * oh + oy) * ow + ox] = v;
+      }
+    }
+    ch_base += s.C;
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------ direct conv
 struct DirectConvParams {
   const void* in; int in_fmt;          // 0: NHWC fp16 (stride in_cs), 1: NCHW fp32
@@ -1450,6 +1538,20 @@ int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC
   else
     roi_align_kernel<float><<<grid_for(total), kThreads, 0, ST>>>((const float*)feat, sN, sC, sH, sW, B, C, H, W, rois, n_rois, oh, ow,
                                                                  scale_h, scale_w, aligned, (__half*)out_half, out_cs, split ? out_cs / 2 : 0, out_f32);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_roi_align_fused(const float* feat0, int C0, float scale_h0, float scale_w0, int aligned0, void* out_half0, int out_cs0, float* out_f0,
+                        const float* feat1, int C1, float scale_h1, float scale_w1, int aligned1, void* out_half1, int out_cs1, float* out_f1,
+                        int B, int H, int W, const float* rois, int n_rois, int oh, int ow, int split, void* stream) {
+  if (n_rois == 0) return HIS_OK;
+  if (!feat0 || !rois || C0 <= 0 || C1 < 0 || C0 + C1 > kRoiMaxC || (C1 > 0 && !feat1)) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align_fused: bad arguments (at most 5 channels over the two sources)");
+  if (oh <= 0 || ow <= 0) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align_fused: bad shape");
+  RoiSrc s0{feat0, C0, scale_h0, scale_w0, aligned0, (__half*)out_half0, out_cs0, split ? out_cs0 / 2 : 0, out_f0};
+  RoiSrc s1{feat1, C1, scale_h1, scale_w1, aligned1, (__half*)out_half1, out_cs1, split ? out_cs1 / 2 : 0, out_f1};
+  const long long rows = (long long)n_rois * oh;
+  roi_align_rows_kernel<<<(unsigned)((rows + kRoiWarps - 1) / kRoiWarps), kRoiWarps * 32, 0, ST>>>(s0, s1, B, H, W, rois, n_rois, oh, ow);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -94,6 +94,8 @@ SIGNATURES = {
     "his_version": [],
     "his_roi_align": [_P, c_int, _LL, _LL, _LL, _LL, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_float, c_float,
                       c_int, _P, c_int, _P, c_int, _P],
+    "his_roi_align_fused": [_P, c_int, c_float, c_float, c_int, _P, c_int, _P, _P, c_int, c_float, c_float, c_int, _P, c_int, _P,
+                            c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P],
     "his_conv_gemm_tile_n": [c_int, POINTER(c_int), POINTER(c_int)],
     "his_conv_gemm_create": [POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, _P, c_int,
                              _P, c_int, c_int, c_int, c_float, c_int, c_int],

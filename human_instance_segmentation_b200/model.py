@@ -780,6 +780,9 @@ class _BuiltPlan:
         p, L = self.plan, self.plan.lib
         if out is None:
             out = p.act(x.N, x.H, x.W, x.C)
+        if isinstance(norm, pt.INSTANCE_NORMS) and not self.split:
+            raise NotImplementedError("normalization_type 'instance' / 'adaptive_instance' needs model.precision = 'strict': per-channel statistics "
+                                      "of a single-fp16 pre-normalisation tensor are 1.5e-2 .. 4e-2 off the reference (DESIGN section 4)")
         gn = pt.group_norm_args(norm)
         if gn is not None:
             groups, gamma, beta, eps = gn
@@ -1011,12 +1014,14 @@ class _BuiltPlan:
         roi_patch = p.f32(N, 3, rh, rw) if aux_level != "none" else None
         ram, rar = m.roi_align_mask, m.roi_align_rgb
         msk = comb_in.slice(256, 2) if m.use_refinement else None
-        p.add("roi_align_mask", L.his_roi_align, self.two.data_ptr(), 0, 2 * H * W, H * W, W, 1, B, 2, H, W, self.h_rois.data_ptr(), N, rh, rw,
-              float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0, msk.ptr if msk else None, msk.cs if msk else 0,
-              roi_feat.data_ptr(), self.S)
-        p.add("roi_align_rgb", L.his_roi_align, self.images.data_ptr(), 0, 3 * H * W, H * W, W, 1, B, 3, H, W, self.h_rois.data_ptr(), N, rh, rw,
-              float(rar.spatial_scale_h), float(rar.spatial_scale_w), 1 if rar.aligned else 0, patches.ptr, patches.cs,
-              roi_patch.data_ptr() if roi_patch is not None else None, self.S)
+        # one launch for both aligners: warp per (ROI, output row), source rows staged in shared memory, outputs written straight
+        # into the consumers' NHWC slices (+ the fp32 aux tensors)
+        p.add("roi_align", L.his_roi_align_fused,
+              self.two.data_ptr(), 2, float(ram.spatial_scale_h), float(ram.spatial_scale_w), 1 if ram.aligned else 0,
+              msk.ptr if msk else None, msk.cs if msk else 0, roi_feat.data_ptr(),
+              self.images.data_ptr(), 3, float(rar.spatial_scale_h), float(rar.spatial_scale_w), 1 if rar.aligned else 0,
+              patches.ptr, patches.cs, roi_patch.data_ptr() if roi_patch is not None else None,
+              B, H, W, self.h_rois.data_ptr(), N, rh, rw, self.S)
 
         # --- rgb_feature_extractor (rgb.py:657-673)
         fe = m.rgb_feature_extractor

@@ -53,6 +53,19 @@ class MixedNormParams(nn.Module):
         self.instance_norm = nn.InstanceNorm2d(c, affine=True)
 
 
+class AdaptiveInstanceNormParams(nn.Module):
+    """AdaptiveInstanceNorm2d (normalization_comparison.py:12-57): per-(sample, channel) statistics + affine; the running
+    statistics are buffers the forward never reads (they exist in the state dict)."""
+
+    def __init__(self, c: int, eps: float = 1e-5):
+        super().__init__()
+        self.num_features, self.eps = c, eps
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+
+
 def norm_spec(kind: str, groups: int = 8) -> str:
     """Internal spelling of (normalization_type, normalization_groups) handed down the parameter tree: 'group:8'."""
     return f"{kind}:{int(groups)}"
@@ -70,13 +83,13 @@ def norm_params(kind: str, c: int, clamp: bool = True) -> nn.Module:
         return LayerNorm2dParams(c)
     if k in ("batch", "batchnorm", "batchnorm2d"):
         return nn.BatchNorm2d(c)
-    if k in ("instance", "instancenorm", "instancenorm2d", "adaptive_instance"):
-        # the kernels handle one group per channel (his_groupnorm_act, tested against torch), but the B200 path stores the
-        # pre-norm conv output in fp16: a channel whose deviation is small against its mean loses its signal to the 2^-11
-        # rounding before the statistics are taken (measured 1.5e-2 .. 4e-2 against the reference on the small goldens, where
-        # even two fp32 formulations differ by 1.4e-3).  Needs an fp32 pre-norm path -> not offered rather than offered wrong.
-        raise NotImplementedError(f"normalization_type={k!r}: per-channel statistics need an fp32 pre-normalisation path that the "
-                                  "B200 path does not have; use 'batchnorm' (presets), 'layernorm2d', 'groupnorm', 'spatial_group' or 'mixed'")
+    if k in ("instance", "instancenorm", "instancenorm2d"):
+        # one group per channel (his_groupnorm_act).  Runs in the strict precision mode only: with single-fp16 activations a channel
+        # whose deviation is small against its mean loses its signal to the 2^-11 rounding of the pre-norm tensor before the
+        # statistics are taken (measured 1.5e-2 .. 4e-2 against the reference); the split-fp16 pre-norm tensor carries ~21 bits.
+        return nn.InstanceNorm2d(c, affine=True)
+    if k == "adaptive_instance":
+        return AdaptiveInstanceNormParams(c)
     if k in ("group", "groupnorm"):
         if c % groups != 0:                      # :188-193
             for g in (8, 4, 2, 1):
@@ -100,10 +113,13 @@ def group_norm_args(norm: nn.Module):
         norm = norm.norm
     if isinstance(norm, nn.GroupNorm):
         return norm.num_groups, norm.weight, norm.bias, norm.eps
+    if isinstance(norm, (nn.InstanceNorm2d, AdaptiveInstanceNormParams)):       # one group per channel
+        return norm.num_features, norm.weight, norm.bias, norm.eps
     return None
 
 
-NORM_MODULES = (nn.BatchNorm2d, LayerNorm2dParams, nn.GroupNorm, SpatialGroupNormParams, MixedNormParams)
+INSTANCE_NORMS = (nn.InstanceNorm2d, AdaptiveInstanceNormParams)
+NORM_MODULES = (nn.BatchNorm2d, LayerNorm2dParams, nn.GroupNorm, SpatialGroupNormParams, MixedNormParams) + INSTANCE_NORMS
 
 
 def check_activation(name: str) -> str:

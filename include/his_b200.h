@@ -50,6 +50,15 @@ int his_roi_align(const void* feat, int feat_is_half, long long sN, long long sC
                   int B, int C, int H, int W, const float* rois, int n_rois, int oh, int ow,
                   float scale_h, float scale_w, int aligned, void* out_half, int out_cs, float* out_f32, int split, void* stream);
 
+/* Both aligners of the model forward (rgb.py:751-755) in one launch: source 0 (e.g. the 2-channel UNet logits) and the optional
+ * source 1 (the RGB image), fp32 NCHW contiguous [B,C,H,W], C0 + C1 <= 5, same rois / output size, each with its own
+ * spatial scale, `aligned` flag and outputs (NHWC half slice and / or NCHW fp32, either may be NULL).  One warp per (ROI, output
+ * row) stages the two source rows of that output row in shared memory (coalesced reads) and interpolates from there; results are
+ * identical to his_roi_align. */
+int his_roi_align_fused(const float* feat0, int C0, float scale_h0, float scale_w0, int aligned0, void* out_half0, int out_cs0, float* out_f0,
+                        const float* feat1, int C1, float scale_h1, float scale_w1, int aligned1, void* out_half1, int out_cs1, float* out_f1,
+                        int B, int H, int W, const float* rois, int n_rois, int oh, int ow, int split, void* stream);
+
 /* ---- dense conv2d 3x3(pad 1)/1x1, stride 1, and conv_transpose2d k2 s2, as tcgen05 implicit GEMM
  * (hed/advanced/hierarchical_segmentation_rgb.py:657-673,695; ..._refinement.py:37-39,479-523,537-545;
  *  ..._unet.py:44-47,313-372; smp decoder convs / timm 1x1 convs, see oracle/effunet.py).

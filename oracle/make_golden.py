@@ -70,6 +70,11 @@ REFINE_CASES = {
                                    normalization_groups=4, use_attention_module=True), (96, 128)),
     "small_b0_spatial_group": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="spatial_group",
                                        use_distance_transform=False, use_attention_module=False), (96, 128)),
+    # instance / adaptive_instance (normalization_comparison.py:12-57,183,195): strict precision mode only on the B200 path
+    "small_b0_instance": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="instance",
+                                  use_attention_module=True, use_distance_transform=False), (96, 128)),
+    "small_b0_adaptive_instance": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="adaptive_instance",
+                                           use_attention_module=False, use_contour_detection=False), (96, 128)),
     "small_b0_mixed": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="mixed",
                                use_progressive_upsampling=True), (96, 128)),
     "small_b0_progressive": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), use_progressive_upsampling=True,

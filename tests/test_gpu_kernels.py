@@ -199,3 +199,41 @@ def test_head_tail_kernels_match_torch():
     fg = F.softmax(ref, 1)[:, 1]
     want = torch.stack([ref[:, 0], ref[:, 1] + tn[:, 0] * fg, ref[:, 1] + tn[:, 1] * fg], 1)
     assert (logits.cpu() - want).abs().max() < 1e-4
+
+
+@SPLIT
+def test_fused_roi_align_matches_reference_golden_and_plain_kernel(split):
+    """his_roi_align_fused (both aligners in one launch, warp per (ROI, output row), source rows staged in shared memory) against
+    the reference-generated goldens of DynamicRoIAlign (hed/dynamic_roi_align.py:56-171) and, on a wide image whose ROI rows exceed
+    the staging capacity (direct-gather fallback), against the plain kernel -- identical results required."""
+    import ctypes
+    p = _plan(split); lib = p.lib
+    st = torch.cuda.current_stream().cuda_stream
+    g = common.golden("roi_align")
+    feat, rois = g["feat"].cuda(), g["rois"].cuda()
+    f0, f1 = feat[:, :2].contiguous(), feat[:, 2:].contiguous()
+    n = rois.shape[0]
+    for tag, (sh, sw), aligned, (oh, ow) in [("a640", (640.0, 640.0), 1, (16, 12)), ("ahw", (37.0, 53.0), 1, (16, 12)), ("u_hw", (37.0, 53.0), 0, (7, 9)),
+                                            ("a64", (64.0, 64.0), 1, (5, 3))]:
+        o0, o1 = p.f32(n, 2, oh, ow), p.f32(n, 3, oh, ow)
+        h0, h1 = p.act(n, oh, ow, 16).slice(8, 2), p.act_zeroed(n, oh, ow, 3)
+        L.check(lib.his_roi_align_fused(f0.data_ptr(), 2, sh, sw, aligned, h0.ptr, h0.cs, o0.data_ptr(),
+                                        f1.data_ptr(), 3, sh, sw, aligned, h1.ptr, h1.cs, o1.data_ptr(),
+                                        3, 37, 53, rois.data_ptr(), n, oh, ow, 1 if split else 0, st))
+        torch.cuda.synchronize()
+        got = torch.cat([o0, o1], 1).cpu()
+        assert (got - g[tag]).abs().max() < 2e-5, tag
+        tol = 1e-6 if split else 1e-3
+        assert (h0.torch_nchw().cpu() - g[tag][:, :2]).abs().max() <= tol * max(1.0, float(g[tag].abs().max()))
+        assert (h1.torch_nchw().cpu() - g[tag][:, 2:]).abs().max() <= tol * max(1.0, float(g[tag].abs().max()))
+    # wide image: rows of up to 1000 source pixels (> staging capacity) next to narrow ones, one source only
+    gen = torch.Generator().manual_seed(4)
+    wide = torch.randn(2, 3, 20, 1000, generator=gen).cuda()
+    r = torch.tensor([[0, 0.0, 0.1, 1.0, 0.9], [1, 0.2, 0.0, 0.45, 1.0], [1, 0.9, 0.5, 0.1, 0.6], [5, 0.1, 0.1, 0.5, 0.5]], dtype=torch.float32).cuda()
+    a, b = p.f32(4, 3, 6, 40), p.f32(4, 3, 6, 40)
+    L.check(lib.his_roi_align_fused(wide.data_ptr(), 3, 20.0, 1000.0, 1, None, 0, a.data_ptr(), None, 0, 0.0, 0.0, 0, None, 0, None,
+                                    2, 20, 1000, r.data_ptr(), 4, 6, 40, 0, st))
+    L.check(lib.his_roi_align(wide.data_ptr(), 0, 3 * 20 * 1000, 20 * 1000, 1000, 1, 2, 3, 20, 1000, r.data_ptr(), 4, 6, 40, 20.0, 1000.0, 1, None, 0,
+                              b.data_ptr(), 0, st))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)

@@ -156,6 +156,11 @@ def test_refinement_flags_match_reference_golden(name, precision):
     cfg, images, rois = common.small_case_inputs(name)
     g = common.golden(name)
     m = build(cfg, common.shapes_for_case(name), precision)
+    if cfg.normalization_type.lower() in ("instance", "adaptive_instance") and precision == "fast":
+        # per-channel statistics need the ~21-bit pre-normalisation tensor of the strict mode: refused, not computed wrong
+        with pytest.raises(NotImplementedError, match="strict"):
+            m(images.cuda(), rois.cuda())
+        return
     logits, aux = m(images.cuda(), rois.cuda())
     # group / instance statistics divide by a per-group deviation that is itself computed from fp16-rounded activations: the
     # stress weights' rounding noise grows from 1.4e-3 to ~2.5-3e-3 through the ~40 normalised layers
