@@ -223,9 +223,9 @@ def test_fused_roi_align_matches_reference_golden_and_plain_kernel(split):
         torch.cuda.synchronize()
         got = torch.cat([o0, o1], 1).cpu()
         assert (got - g[tag]).abs().max() < 2e-5, tag
-        tol = 1e-6 if split else 1e-3
-        assert (h0.torch_nchw().cpu() - g[tag][:, :2]).abs().max() <= tol * max(1.0, float(g[tag].abs().max()))
-        assert (h1.torch_nchw().cpu() - g[tag][:, 2:]).abs().max() <= tol * max(1.0, float(g[tag].abs().max()))
+        tol = 1e-6 if split else 1e-3          # the NHWC slices hold the same values, rounded to fp16 (or to a hi + lo pair)
+        assert (h0.torch_nchw().cpu() - o0.cpu()).abs().max() <= tol * max(1.0, float(g[tag].abs().max()))
+        assert (h1.torch_nchw().cpu() - o1.cpu()).abs().max() <= tol * max(1.0, float(g[tag].abs().max()))
     # wide image: rows of up to 1000 source pixels (> staging capacity) next to narrow ones, one source only
     gen = torch.Generator().manual_seed(4)
     wide = torch.randn(2, 3, 20, 1000, generator=gen).cuda()
