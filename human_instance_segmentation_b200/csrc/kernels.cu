@@ -964,15 +964,18 @@ __global__ void gn_stats_kernel(const __half* __restrict__ in, int HW, int C, in
   const int PL = blockDim.x / cgs;                      // pixel lanes (>= 1: C <= 2048)
   const int cg = threadIdx.x % cgs, pl = threadIdx.x / cgs;
   const int p0 = part * pix_per_part, p1 = min(p0 + pix_per_part, HW);
-  float sum[8], sq[8];
+  float sum[8], sq[8], pivot[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sum[e] = 0.0f; sq[e] = 0.0f; }
   if (pl < PL) {
+    // sums of (x - pivot) and (x - pivot)^2 with pivot = the channel's value at the image's first pixel: a channel whose deviation
+    // is small against its mean (instance norm on near-constant maps) would lose E[x^2] - E[x]^2 to cancellation in fp32
+    his_ld8(in + (long long)n * HW * cs + cg * 8, lo, pivot);
     for (int pix = p0 + pl; pix < p1; pix += PL) {
       float f[8];
       his_ld8(in + ((long long)n * HW + pix) * cs + cg * 8, lo, f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { sum[e] += f[e]; sq[e] = fmaf(f[e], f[e], sq[e]); }
+      for (int e = 0; e < 8; ++e) { const float d = f[e] - pivot[e]; sum[e] += d; sq[e] = fmaf(d, d, sq[e]); }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s_gn[((size_t)pl * C + cg * 8 + e) * 2] = sum[e]; s_gn[((size_t)pl * C + cg * 8 + e) * 2 + 1] = sq[e]; }
@@ -986,18 +989,31 @@ __global__ void gn_stats_kernel(const __half* __restrict__ in, int HW, int C, in
   }
 }
 
-__global__ void gn_finalize_kernel(float* __restrict__ ws, int HW, int C, int G, int nparts, float eps) {
+__global__ void gn_finalize_kernel(float* __restrict__ ws, const __half* __restrict__ in, int cs, int lo, int HW, int C, int G, int nparts, float eps) {
   const int n = blockIdx.y, g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const int gs = C / G;
-  double s = 0.0, q = 0.0;
-  for (int part = 0; part < nparts; ++part) {
-    const float* src = ws + (((long long)n * (nparts + 1) + part) * C + g * gs) * 2;
-    for (int c = 0; c < gs; ++c) { s += (double)src[2 * c]; q += (double)src[2 * c + 1]; }
+  // per channel: mean_c = pivot_c + S1/HW and the squared deviations about it M2_c = S2 - S1^2/HW (both well conditioned), then the
+  // group: mean_g = avg mean_c, M2_g = sum_c [M2_c + HW (mean_c - mean_g)^2]  (parallel-variance merge, in double)
+  double mean_sum = 0.0;
+  for (int c = 0; c < gs; ++c) {
+    double s1 = 0.0;
+    for (int part = 0; part < nparts; ++part) s1 += (double)ws[(((long long)n * (nparts + 1) + part) * C + g * gs + c) * 2];
+    mean_sum += (double)his_ld1(in + (long long)n * HW * cs + g * gs + c, lo) + s1 / (double)HW;
+  }
+  const double mu = mean_sum / (double)gs;
+  double m2 = 0.0;
+  for (int c = 0; c < gs; ++c) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int part = 0; part < nparts; ++part) {
+      const float* src = ws + (((long long)n * (nparts + 1) + part) * C + g * gs + c) * 2;
+      s1 += (double)src[0]; s2 += (double)src[1];
+    }
+    const double mc = (double)his_ld1(in + (long long)n * HW * cs + g * gs + c, lo) + s1 / (double)HW;
+    m2 += (s2 - s1 * s1 / (double)HW) + (double)HW * (mc - mu) * (mc - mu);
   }
   const double cnt = (double)HW * (double)gs;
-  const double mu = s / cnt;
-  double var = q / cnt - mu * mu;
+  double var = m2 / cnt;
   if (var < 0.0) var = 0.0;
   const float muf = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
   float* dst = ws + (((long long)n * (nparts + 1) + nparts) * C + g * gs) * 2;
@@ -1008,12 +1024,12 @@ __global__ void gn_apply_kernel(const __half* __restrict__ in, int HW, int C, in
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int act, float act_beta,
                                 int res_mode, const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs,
                                 int in_lo, int res_lo, int out_lo) {
-  extern __shared__ float s_ab[];                       // per channel: y = x*a + b with a = rstd*gamma, b = beta - mean*a
+  extern __shared__ float s_ab[];                       // per channel: y = (x - mean)*a + beta with a = rstd*gamma (the subtraction
+                                                        // first: x*a - mean*a would cancel for channels with |mean| >> deviation)
   const int n = blockIdx.y, cgs = C / 8;
   const float* st = ws + ((long long)n * (nparts + 1) + nparts) * C * 2;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float a = st[2 * c + 1] * __ldg(gamma + c);
-    s_ab[2 * c] = a; s_ab[2 * c + 1] = __ldg(beta + c) - st[2 * c] * a;
+    s_ab[3 * c] = st[2 * c]; s_ab[3 * c + 1] = st[2 * c + 1] * __ldg(gamma + c); s_ab[3 * c + 2] = __ldg(beta + c);
   }
   __syncthreads();
   const long long per_img_vec = (long long)HW * cgs;
@@ -1026,7 +1042,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ in, int HW, int C, in
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cg * 8 + e;
-      float y = fmaf(f[e], s_ab[2 * c], s_ab[2 * c + 1]);
+      float y = fmaf(f[e] - s_ab[3 * c], s_ab[3 * c + 1], s_ab[3 * c + 2]);
       if (res_mode == HIS_RES_ADD) y += r[e];
       y = his_act(y, act, act_beta);
       if (res_mode == HIS_RES_MUL) y *= r[e];
@@ -1837,12 +1853,12 @@ int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int group
   if (attr_done.first()) cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const size_t sm1 = (size_t)PL * C * 2 * sizeof(float);      // <= 256/cgs * 8*cgs * 8 B = 16 KB
   gn_stats_kernel<<<dim3(parts, N), kThreads, sm1, ST>>>((const __half*)in, HW, C, in_cs, split ? in_cs / 2 : 0, ppp, parts + 1, ws);
-  gn_finalize_kernel<<<dim3((groups + 127) / 128, N), 128, 0, ST>>>(ws, HW, C, groups, parts, eps);
+  gn_finalize_kernel<<<dim3((groups + 127) / 128, N), 128, 0, ST>>>(ws, (const __half*)in, in_cs, split ? in_cs / 2 : 0, HW, C, groups, parts, eps);
   const long long per_img_vec = (long long)HW * cgs;
   long long gx = (per_img_vec + kThreads - 1) / kThreads;
   const long long cap = (148LL * 16 + N - 1) / N;
   if (gx > cap) gx = cap;
-  gn_apply_kernel<<<dim3((int)(gx < 1 ? 1 : gx), N), kThreads, (size_t)C * 2 * sizeof(float), ST>>>(
+  gn_apply_kernel<<<dim3((int)(gx < 1 ? 1 : gx), N), kThreads, (size_t)C * 3 * sizeof(float), ST>>>(
       (const __half*)in, HW, C, in_cs, ws, parts, gamma, beta, act, act_beta, res_mode, (const __half*)res, res_cs, (__half*)out, out_cs,
       split ? in_cs / 2 : 0, split ? res_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
