@@ -324,6 +324,10 @@ int his_conv_gemm_create(void** out_plan,
   p.n_acc &= ~1;
   if (const char* e = getenv("HIS_GEMM_NACC")) { int v = atoi(e) & ~1; if (v >= 2 && v <= p.n_acc) p.n_acc = v; }
   p.fast_decode = (p.n_tiles == 1 && p.groups == 1 && p.num_work < (1 << 21)) ? 1 : 0;
+  // a third epilogue warpgroup for the layers bound by the epilogue's per-tile latency: narrow N tiles and the 1x1 convs
+  // (HIS_GEMM_EPI=2|3 forces the count; pair kernels keep two)
+  p.epi_groups = (p.block_n <= 96 || (ksize == 1 && cin <= 112)) ? 3 : 2;
+  if (const char* e = getenv("HIS_GEMM_EPI")) { const int v = atoi(e); if (v == 2 || v == 3) p.epi_groups = v; }
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   if (halo) {
     // B ring stage = taps_per_b weight tiles (block_n x BK); A ring stage = BK/8 planes of the 10 x 18 window
@@ -336,7 +340,7 @@ int his_conv_gemm_create(void** out_plan,
     if (p.pair) p.taps_per_box = 1;      // a CTA's half of a tap's rows is not contiguous with the next tap's
     p.stage_bytes = (p.taps_per_b * tap_bytes + 1023) / 1024 * 1024;
     p.a_stage_bytes = (bk / 8) * kPlaneBytes;
-    const int budget = KCfg<64>::kRingBytes;
+    const int budget = KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes;
     int a_st = p.a_stage_bytes >= 16 * 1024 ? (p.pair ? 3 : 2) : (budget / 3) / p.a_stage_bytes;
     if (a_st > kMaxAStages) a_st = kMaxAStages;
     if (a_st < 2) a_st = 2;
@@ -365,7 +369,7 @@ int his_conv_gemm_create(void** out_plan,
     p.pair = (!split && !transposed && ksize == 3 && p.n_tiles == 1 && bk == 64 && p.block_n >= pair_min_n && (p.block_n % 32) == 0 &&
               ((p.tiles_x * p.tiles_y) % 2) == 0 && p.num_work >= 2) ? 1 : 0;
     p.stage_bytes = (kBlockM * bk * 2 + (p.pair ? p.block_n / 2 : p.block_n) * bk * 2 + 1023) / 1024 * 1024;
-    p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
+    p.stages = (KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes) / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
   }
@@ -478,13 +482,13 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   if (const char* e = getenv("HIS_GEMM_AUX_TMA")) want = want && atoi(e) != 0;
   p.aux_tma = 0;
   if (want) {
-    const int need = 2 * kAuxStagingBytes;
+    const int need = p.epi_groups * kAuxStagingBytes;
     bool ok = true;
     if (!pl->halo) {
-      const int st = (KCfg<64>::kRingBytes - need) / p.stage_bytes;
+      const int st = (KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes - need) / p.stage_bytes;
       if (st >= 2) { if (st < p.stages) p.stages = st; } else ok = false;
     } else {
-      const int budget = KCfg<64>::kRingBytes - need;
+      const int budget = KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes - need;
       while (p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes > budget && p.a_stages > 2) --p.a_stages;
       while (p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes > budget && p.stages > 2 && !p.b_resident) --p.stages;
       ok = p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes <= budget;
@@ -513,7 +517,7 @@ int his_conv_gemm_run(void* plan, void* stream) {
   if (pl->p.pair) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kThreadsGemm); cfg.dynamicSmemBytes = pl->smem; cfg.stream = (cudaStream_t)stream;
+    cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(128 + 128 * pl->p.epi_groups); cfg.dynamicSmemBytes = pl->smem; cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
@@ -529,7 +533,7 @@ int his_conv_gemm_run(void* plan, void* stream) {
       return his_set_error(HIS_ERR_LAUNCH, cudaGetErrorString(cudaGetLastError()));
     return HIS_OK;
   }
-  pl->kernel<<<pl->grid, kThreadsGemm, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
+  pl->kernel<<<pl->grid, 128 + 128 * pl->p.epi_groups, pl->smem, (cudaStream_t)stream>>>(pl->tmA, pl->tmB, pl->tmO[0], pl->tmO[1], pl->tmO[2], pl->tmO[3], pl->tmR,
                                                                pl->tmAux, pl->p);
   HIS_CHECK_LAUNCH();
   return HIS_OK;

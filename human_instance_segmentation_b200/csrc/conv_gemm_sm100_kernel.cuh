@@ -41,9 +41,9 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kChunkC = 32;                            // output channels per epilogue chunk
 constexpr int kStagingBytes = kBlockM * kChunkC * 2;   // 8 KB : 128 rows x 32 channels fp16 (SWIZZLE_64B rows)
-constexpr int kNumStaging = 4;                         // two per epilogue group
-constexpr int kShiftBytes = 3 * 256 * 4;               // per-channel shift of the (single) N tile + one residual-scale row per epilogue group
-constexpr int kThreadsGemm = 384;
+constexpr int kMaxEpiGroups = 3;                       // epilogue warpgroups: 2 (384 threads) or 3 (512 threads), see ConvGemmParams::epi_groups
+constexpr int kShiftBytes = (1 + kMaxEpiGroups) * 256 * 4;   // per-channel shift of the (single) N tile + one residual-scale row per epilogue group
+constexpr int kThreadsGemm = 128 + 128 * kMaxEpiGroups;      // launch bound; a plan launches 128 + 128 * epi_groups threads
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 48;
 constexpr int kSmemBudget = 227 * 1024;
@@ -65,7 +65,7 @@ template <int BK> struct KCfg {
   static constexpr int kBBytesMax = 256 * BK * 2;
   // the ring gets whatever the 227 KB leave after the staging buffers, barriers and the 1 KB alignment slack; its depth is a
   // run-time parameter (stage = A + the layer's actual B tile), so narrow layers keep many more loads in flight
-  static constexpr int kRingBytes = kSmemBudget - kNumStaging * kStagingBytes - kShiftBytes - 1024 - kBarrierBytes;
+  static constexpr int kRingBytes = kSmemBudget - 4 * kStagingBytes - kShiftBytes - 1024 - kBarrierBytes;      // two epilogue groups
   static constexpr int kSmemBytes = kSmemBudget;
   static constexpr uint32_t kSbo = 8 * BK * 2;                 // bytes between 8-row groups
   static constexpr uint64_t kLayout = BK == 64 ? 2 : BK == 32 ? 4 : 6;   // SWIZZLE_128B / 64B / 32B
@@ -131,6 +131,10 @@ struct ConvGemmParams {
   // columns each, so the A tile is read 4 / phase_merge times instead of four and the MMAs run at N = 256; every 32-channel
   // epilogue chunk goes to its phase's strided output map.  phase_merge == 1: one group per phase (or not transposed).
   int phase_merge, phase_slab;
+  // epilogue warpgroups (2 or 3), each with two staging buffers; tiles go to the groups round robin.  Narrow layers are bound by
+  // the per-tile latency of one warpgroup's dependent instruction chain (wait, tcgen05.ld, math, stores: ~1 900 clk per tile
+  // and group measured with every memory operation removed), not by any throughput: a third group gives 1.5x there.
+  int epi_groups;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -373,7 +377,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage_base = smem_base;
   const uint32_t staging_base = smem_base + kStages * p.stage_bytes;
-  const uint32_t shift_base = staging_base + kNumStaging * kStagingBytes;
+  const uint32_t shift_base = staging_base + (uint32_t)(2 * p.epi_groups) * kStagingBytes;
   const uint32_t bar_base = shift_base + kShiftBytes;
   // barrier slots (8 B each): full[kStages] empty[kStages] tmem_full[2] tmem_empty[2] res_full[4], the TMEM pointer, then (halo
   // mode) afull[a_stages] aempty[a_stages]; the halo ring itself follows the barrier block
@@ -381,11 +385,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 8 + a); };
-  auto res_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 16 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 20);
-  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + s); };
-  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + p.a_stages + s); };
-  auto apeer_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 21 + 2 * p.a_stages + s); };   // pair: the peer's window is complete
+  auto res_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 16 + b); };          // 2 per epilogue group (<= 6)
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 22);
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 23 + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 23 + p.a_stages + s); };
+  auto apeer_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 23 + 2 * p.a_stages + s); };   // pair: the peer's window is complete
   const int n_acc = p.n_acc;
   const uint32_t a_base = bar_base + kBarrierBytes;
   // EPI_AUX: fp32 export staging (one tile per epilogue group) behind the halo ring
@@ -408,7 +412,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 8; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
-    for (int a = 0; a < 4; ++a) mbar_init(res_bar(a), 1);
+    for (int a = 0; a < 2 * kMaxEpiGroups; ++a) mbar_init(res_bar(a), 1);
     if (HALO)
       for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kAProducerThreads); mbar_init(aempty_bar(s), 1); mbar_init(apeer_bar(s), 1); }
     fence_barrier_init();
@@ -425,7 +429,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   // single N tile: the per-channel shift stays in shared memory for the whole kernel
   float* s_shift = reinterpret_cast<float*>(smem_gen + (shift_base - smem_base));
   if (p.n_tiles == 1)
-    for (int i = threadIdx.x; i < p.block_n; i += kThreadsGemm) s_shift[i] = __ldg(p.shift + (p.phase_merge > 1 ? i % p.phase_slab : i));
+    for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) s_shift[i] = __ldg(p.shift + (p.phase_merge > 1 ? i % p.phase_slab : i));
   tc_fence_before();
   __syncthreads();
   if (pair) cluster_sync_all();        // the peer's barriers are initialised and its TMEM is allocated before anything remote happens
@@ -703,8 +707,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t stg0 = staging_base + g * 2 * kStagingBytes;
     uint32_t cc = 0;
     uint32_t res_phase = 0;                       // bit b: parity of the next residual load into staging buffer b
-    int acc = g; uint32_t acc_phase = 0;          // group g drains the accumulators of parity g (n_acc is even)
-    for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += 2 * gridDim.x) {
+    // the CTA's i-th tile uses accumulator i % n_acc (phase (i / n_acc) & 1) and is drained by group i % epi_groups
+    const int G = p.epi_groups;
+    int ti = g, acc = g % n_acc; uint32_t acc_phase = (uint32_t)(g / n_acc) & 1u;
+    for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += G * gridDim.x) {
       const WorkItem it = decode_work(p, w);
       const uint32_t acc_col = (uint32_t)(acc * p.acc_stride);
       const int chbase = it.n_tile * p.block_n;
@@ -926,8 +932,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (p.tail_c > 1) dst[(long long)p.H * p.W] = o1;
         }
       }
-      acc += 2;
-      if (acc >= n_acc) { acc = g; acc_phase ^= 1; }
+      ti += G;
+      acc = ti % n_acc; acc_phase = (uint32_t)(ti / n_acc) & 1u;
     }
     if (issuer_warp && elect_one()) tma_wait_all();
   }
