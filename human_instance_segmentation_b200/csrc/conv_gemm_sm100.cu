@@ -328,6 +328,12 @@ int his_conv_gemm_create(void** out_plan,
   // (HIS_GEMM_EPI=2|3 forces the count; pair kernels keep two)
   p.epi_groups = (p.block_n <= 96 || (ksize == 1 && cin <= 112)) ? 3 : 2;
   if (const char* e = getenv("HIS_GEMM_EPI")) { const int v = atoi(e); if (v == 2 || v == 3) p.epi_groups = v; }
+  // every accumulator must always be drained by the SAME group (a group that met an accumulator first at its second use would
+  // pass the parity wait of the still untouched barrier): the ring length is a multiple of the group count
+  if (p.epi_groups == 3) {
+    const int fit = kTmemCols / p.acc_stride;
+    if (fit >= 6) p.n_acc = 6; else if (fit >= 3) p.n_acc = 3; else p.epi_groups = 2;
+  }
   p.inv_tiles_x = 1.0f / (float)p.tiles_x; p.inv_tiles_y = 1.0f / (float)p.tiles_y;
   if (halo) {
     // B ring stage = taps_per_b weight tiles (block_n x BK); A ring stage = BK/8 planes of the 10 x 18 window
