@@ -139,12 +139,20 @@ __global__ void __launch_bounds__(kRoiWarps * 32) roi_align_rows_kernel(RoiSrc s
     const bool staged = finite_x && (hi - lo + 1) <= kRoiSeg;
     const float* img = s.feat + (long long)(okb ? b : 0) * s.C * H * W;
     if (staged) {
-      for (int c = 0; c < s.C; ++c)
-        for (int rr = 0; rr < 2; ++rr) {
-          const bool rok = rr == 0 ? y0ok : y1ok;
-          const float* src = img + ((long long)c * H + (iy + rr)) * W + lo;
-          for (int i = lane; i <= hi - lo; i += 32) s_seg[warp][ch_base + c][rr][i] = rok ? __ldg(src + i) : 0.0f;
-        }
+      // all 2*C row segments of one 32-pixel column block are loaded before any is stored: 2*C independent loads in flight per
+      // lane instead of one load -> store round trip per element
+      const float* src0 = img + (long long)iy * W + lo;
+      for (int i = lane; i <= hi - lo; i += 32) {
+        float t[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr)
+            t[c][rr] = (c < s.C && (rr == 0 ? y0ok : y1ok)) ? __ldg(src0 + ((long long)c * H + rr) * W + i) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < s.C) { s_seg[warp][ch_base + c][0][i] = t[c][0]; s_seg[warp][ch_base + c][1][i] = t[c][1]; }
+      }
     }
     __syncwarp();
     for (int ox = lane; ox < ow; ox += 32) {
@@ -1562,7 +1570,8 @@ int his_roi_align_fused(const float* feat0, int C0, float scale_h0, float scale_
                         const float* feat1, int C1, float scale_h1, float scale_w1, int aligned1, void* out_half1, int out_cs1, float* out_f1,
                         int B, int H, int W, const float* rois, int n_rois, int oh, int ow, int split, void* stream) {
   if (n_rois == 0) return HIS_OK;
-  if (!feat0 || !rois || C0 <= 0 || C1 < 0 || C0 + C1 > kRoiMaxC || (C1 > 0 && !feat1)) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align_fused: bad arguments (at most 5 channels over the two sources)");
+  if (!feat0 || !rois || C0 <= 0 || C1 < 0 || C0 > 3 || C1 > 3 || C0 + C1 > kRoiMaxC || (C1 > 0 && !feat1))
+    return his_set_error(HIS_ERR_INVALID_ARG, "roi_align_fused: bad arguments (at most 3 channels per source, 5 over the two)");
   if (oh <= 0 || ow <= 0) return his_set_error(HIS_ERR_INVALID_ARG, "roi_align_fused: bad shape");
   RoiSrc s0{feat0, C0, scale_h0, scale_w0, aligned0, (__half*)out_half0, out_cs0, split ? out_cs0 / 2 : 0, out_f0};
   RoiSrc s1{feat1, C1, scale_h1, scale_w1, aligned1, (__half*)out_half1, out_cs1, split ? out_cs1 / 2 : 0, out_f1};
