@@ -345,7 +345,7 @@ int his_conv_gemm_create(void** out_plan,
     p.taps_per_box = (p.n_tiles == 1 && p.taps_per_b * p.block_n <= 256) ? p.taps_per_b : 1;
     if (p.pair) p.taps_per_box = 1;      // a CTA's half of a tap's rows is not contiguous with the next tap's
     p.stage_bytes = (p.taps_per_b * tap_bytes + 1023) / 1024 * 1024;
-    p.a_stage_bytes = (bk / 8) * kPlaneBytes;
+    p.a_stage_bytes = (bk / 8) * kPlaneBytes;       // stage pitch (the TMA window uses 16 B less per plane of it)
     const int budget = KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes;
     int a_st = p.a_stage_bytes >= 16 * 1024 ? (p.pair ? 3 : 2) : (budget / 3) / p.a_stage_bytes;
     if (a_st > kMaxAStages) a_st = kMaxAStages;
@@ -385,6 +385,23 @@ int his_conv_gemm_create(void** out_plan,
   int taps = ksize * ksize;
   int rc;
   if ((rc = encode_act_map(&pl->tmA, in, cin, W, H, n_img, in_cs, (long long)W * in_cs, (long long)H * W * in_cs, bk, p.bw, p.bh, p.in_lo))) { delete pl; return rc; }
+  // halo window by TMA: one 5-D box {8, 10, 18, BK/8, 1} of the map {8 ch, W, H, C/8, N}.  HIS_GEMM_HALO_TMA=0 keeps the cp.async producers.
+  p.a_tma = 0; p.plane_bytes = kPlaneBytes;
+  if (halo && !split && !p.pair) {
+    int want = 1;
+    if (const char* e = getenv("HIS_GEMM_HALO_TMA")) want = atoi(e) != 0;
+    PFN_encodeTiled enc = get_encode();
+    if (want && enc) {
+      cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(cin / 8), (cuuint64_t)n_img};
+      cuuint64_t strides[4] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, 16, (cuuint64_t)H * W * in_cs * 2};
+      cuuint32_t box[5] = {8, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, (cuuint32_t)(bk / 8), 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      if (enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        p.a_tma = 1; p.plane_bytes = kHaloPix * 16;
+      }
+    }
+  }
   pl->b_box_rows = p.pair ? p.block_n / 2 : halo ? p.taps_per_box * p.block_n : p.block_n;
   if ((rc = encode_weight_map(&pl->tmB, w_packed, cin_pad, (long long)p.groups * taps * p.cout_slab, pl->b_box_rows, bk))) { delete pl; return rc; }
   if (!transposed) {
@@ -460,6 +477,7 @@ int his_conv_gemm_set_upsampled_input(void* plan, const void* low, int low_c, in
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_upsampled_input: needs a halo-mode 3x3 layer, even H and W, low_c a multiple of the K block");
   p.up_in = (const __half*)low; p.up_cs = low_cs; p.up_sn = (long long)(p.H >> 1) * (p.W >> 1) * low_cs; p.up_split = low_c;
   p.up_lo = pl->split ? low_cs / 2 : 0;
+  p.a_tma = 0; p.plane_bytes = kPlaneBytes;      // the gather from two tensors needs the cp.async producers
   return HIS_OK;
 }
 

@@ -135,6 +135,11 @@ struct ConvGemmParams {
   // the per-tile latency of one warpgroup's dependent instruction chain (wait, tcgen05.ld, math, stores: ~1 900 clk per tile
   // and group measured with every memory operation removed), not by any throughput: a third group gives 1.5x there.
   int epi_groups;
+  // halo mode: 1 = the (bh+2) x (bw+2) input window of a K block arrives as ONE 5-D TMA box {8 ch, 10 cols, 18 rows, BK/8 planes, 1}
+  // of the map {8, W, H, C/8, N} (out-of-image coordinates and the channel tail zero-filled by the TMA unit), issued by one
+  // lane of warp 2; 0 = the two cp.async producer warps (needed for the fused nearest upsample and the split-fp16 planes).
+  // plane_bytes = pitch of an 8-channel plane in the window: 180*16 for the TMA box, +16 for the cp.async writes' bank spread.
+  int a_tma, plane_bytes;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -256,10 +261,10 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
 
 // K-major un-swizzled (INTERLEAVE) descriptor of the halo window: core matrix = 8 rows x 16 B, rows 16 B apart;
 // SBO = bytes between 8-row groups (one halo row), LBO = bytes between the two 8-channel planes of one K=16 step.
-__device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr, int plane_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(kPlaneBytes >> 4) << 16;
+  d |= (uint64_t)(plane_bytes >> 4) << 16;
   d |= (uint64_t)((kHaloW * 16) >> 4) << 32;
   d |= (uint64_t)1 << 46;
   return d;
@@ -414,7 +419,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int a = 0; a < 8; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), pair ? 8 : 4); }   // pair: both CTAs' epilogue warps
     for (int a = 0; a < 2 * kMaxEpiGroups; ++a) mbar_init(res_bar(a), 1);
     if (HALO)
-      for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), kAProducerThreads); mbar_init(aempty_bar(s), 1); mbar_init(apeer_bar(s), 1); }
+      for (int s = 0; s < p.a_stages; ++s) { mbar_init(afull_bar(s), p.a_tma ? 1 : kAProducerThreads); mbar_init(aempty_bar(s), 1); mbar_init(apeer_bar(s), 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -492,7 +497,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // One thread feeds the tensor pipe, so the loop is kept short: descriptors are a constant high word plus a 14-bit
       // address that advances by adds, the K=16 steps of a block are unrolled, and a B stage carries up to nine taps.
       const uint32_t idesc = make_idesc_f16(p.block_n, pair ? 2 * kBlockM : kBlockM);
-      const uint64_t adesc_hi = make_halo_desc(0), bdesc_hi = make_kmajor_desc<BK>(0);
+      const uint64_t adesc_hi = make_halo_desc(0, p.plane_bytes), bdesc_hi = make_kmajor_desc<BK>(0);
+      const uint64_t k16_units = (uint64_t)(2 * (p.plane_bytes >> 4));       // two 8-channel planes per K = 16 step
       if (pair && cta_rank != 0) {
         // peer of a pair: this warp only relays "my window of stage s is complete" to the leader's MMA thread
         int astage = 0; uint32_t aphase = 0;
@@ -537,7 +543,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     else umma_acc_x<pair>(d_tmem, ad, bd, idesc);
 #pragma unroll
                     for (int kk = 1; kk < BK / 16; ++kk)
-                      if (kk < nk16) umma_acc_x<pair>(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
+                      if (kk < nk16) umma_acc_x<pair>(d_tmem, ad + (uint64_t)kk * k16_units, bd + (uint64_t)(kk * 2), idesc);
                   }
                 }
                 if (!p.b_resident) umma_commit_x<pair>(empty_bar(stage));
@@ -555,7 +561,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                   umma_x<pair>(d_tmem, ad, bd, idesc, (cb | tg | t) ? 1u : 0u);
 #pragma unroll
                   for (int kk = 1; kk < BK / 16; ++kk)
-                    if (kk < nk16) umma_acc_x<pair>(d_tmem, ad + (uint64_t)(kk * 2 * (kPlaneBytes >> 4)), bd + (uint64_t)(kk * 2), idesc);
+                    if (kk < nk16) umma_acc_x<pair>(d_tmem, ad + (uint64_t)kk * k16_units, bd + (uint64_t)(kk * 2), idesc);
                 }
                 bu += b_tap_units; ++au;
                 if (++dx == 3) { dx = 0; au += kHaloW - 3; }
@@ -578,6 +584,24 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++astage == a_stages) { astage = 0; aphase ^= 1; a_units = a_units0; }
         }
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
+      }
+    } else if (warp < 4 && p.a_tma) {
+      // ================================ halo mode: the input window as one 5-D TMA box per K block ================================
+      if (warp == 2) {
+        int astage = 0; uint32_t aphase = 0;
+        const uint32_t tx = (uint32_t)(BK / 8) * (uint32_t)p.plane_bytes;
+        for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+          const WorkItem it = decode_work(p, w);
+          for (int cb = 0; cb < nblk; ++cb) {
+            mbar_wait(aempty_bar(astage), aphase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(afull_bar(astage), tx);
+              tma_load_5d(a_base + astage * p.a_stage_bytes, &tmA, afull_bar(astage), 0, it.x0 - 1, it.y0 - 1, cb * (BK / 8), it.img);
+            }
+            __syncwarp();
+            if (++astage == p.a_stages) { astage = 0; aphase ^= 1; }
+          }
+        }
       }
     } else if (warp < 4) {
       // ================================ halo mode: cp.async producers of the input window ================================

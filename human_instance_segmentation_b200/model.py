@@ -578,8 +578,10 @@ class _BuiltPlan:
         stem_c = m.pretrained_unet.model.model.encoder.out_channels[1] if self.has_unet else 32
         # strict mode stores two fp16 planes per activation: half the images / ROIs per pass keep the footprint of a plan
         div = 2 if self.split else 1
-        self.Bc = min(B, m.max_images_per_pass or max(1, _images_per_pass(H, W, stem_c) // div)) if self.has_unet else B
+        self.Bc = max(1, min(B, m.max_images_per_pass or max(1, _images_per_pass(H, W, stem_c) // div))) if self.has_unet else B
         self.Nc = min(N, m.max_rois_per_pass or max(1, _rois_per_pass(m.roi_size) // div))
+        if B == 0 and N:
+            raise ValueError("rois given for an empty image batch")
         self.chunked_unet, self.chunked_head = self.Bc < B, self.Nc < N
         self.n_unet_chunks = (B + self.Bc - 1) // self.Bc if self.has_unet else 0
         self.n_head_chunks = (N + self.Nc - 1) // self.Nc if N else 0

@@ -272,6 +272,11 @@ def test_model_matches_oracle_fresh_inputs_edge_cases():
     # N = 0
     got0, aux0 = m(images.cuda(), rois[:0].cuda())
     assert got0.shape == (0, 3, 32, 24) and aux0["full_image_logits"].shape == (3, 2, 64, 96)
+    # B = 0 (an empty shard of sharding.partition_images)
+    gote, auxe = m(images[:0].cuda(), rois[:0].cuda())
+    assert gote.shape == (0, 3, 32, 24) and auxe["full_image_logits"].shape == (0, 2, 64, 96)
+    with pytest.raises(ValueError):
+        m(images[:0].cuda(), rois.cuda())
 
 
 def test_chunked_schedule_matches_single_pass():
