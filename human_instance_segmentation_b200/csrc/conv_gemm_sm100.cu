@@ -345,7 +345,8 @@ int his_conv_gemm_create(void** out_plan,
     p.taps_per_box = (p.n_tiles == 1 && p.taps_per_b * p.block_n <= 256) ? p.taps_per_b : 1;
     if (p.pair) p.taps_per_box = 1;      // a CTA's half of a tap's rows is not contiguous with the next tap's
     p.stage_bytes = (p.taps_per_b * tap_bytes + 1023) / 1024 * 1024;
-    p.a_stage_bytes = (bk / 8) * kPlaneBytes;       // stage pitch (the TMA window uses 16 B less per plane of it)
+    p.a_stage_bytes = ((bk / 8) * kPlaneBytes + 127) / 128 * 128;   // stage pitch: 128-byte aligned (TMA destination); the TMA window
+                                                                    // uses 16 B less per plane of it
     const int budget = KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes;
     int a_st = p.a_stage_bytes >= 16 * 1024 ? (p.pair ? 3 : 2) : (budget / 3) / p.a_stage_bytes;
     if (a_st > kMaxAStages) a_st = kMaxAStages;
