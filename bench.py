@@ -29,7 +29,9 @@ WORKLOADS = {
     "b1": ("b1_enhanced", 64, 480, 640, 10),   # BASELINE.json configs[1]
     "b7": ("b7_ultra", 4, 480, 640, 10),       # configs[2] per-GPU share at 8 GPUs (32 images / 8)
     "b0_160x120": ("b0", 512, 120, 160, 10),   # configs[3] per-GPU share at 8 GPUs (4096 / 8)
+    "b0_ln": ("b0", 64, 480, 640, 10),         # the b0 workload with the factory-default normalisation (LayerNorm2d, hed/model.py:18-38)
 }
+OVERRIDES = {"b0_ln": {"normalization_type": "layernorm2d"}}
 HEAD_GFLOP_PER_ROI = {"b0": 57.84, "b1_enhanced": 93.01, "b7_ultra": 278.44}      # SURVEY §8d / BASELINE.md §2
 UNET_GFLOP_PER_IMG = {"b0": 27.72, "b1_enhanced": 29.97, "b7_ultra": 90.21}
 
@@ -101,11 +103,11 @@ def synth_batch(seed, n_images, h, w, per_image):
     return synth_images(seed, n_images, h, w), synth_rois(seed, n_images, per_image)
 
 
-def build_model(preset):
+def build_model(preset, overrides=None):
     """The product arm: nothing under oracle/ is imported here."""
     import human_instance_segmentation_b200 as his
     from human_instance_segmentation_b200 import presets, synthetic
-    kw = presets.PRESETS[preset]
+    kw = dict(presets.PRESETS[preset], **(overrides or {}))
     model = his.create_rgb_hierarchical_model(**kw)
     # random-init weights of that architecture (no checkpoints exist offline); BatchNorm statistics randomised so that
     # nothing folds to a no-op
@@ -327,9 +329,10 @@ def workload_config(name, n_img=None, per_image=None):
     b = n_img or b
     per_image = per_image or ppi
     from human_instance_segmentation_b200 import presets
-    kw = presets.PRESETS[preset]
+    kw = dict(presets.PRESETS[preset], **OVERRIDES.get(name, {}))
     rs, msz = kw["roi_size"], kw["mask_size"]
-    return {"workload": f"{preset} hierarchical RGB model, {w}x{h} input, batch {b} per GPU, {per_image} ROIs/image, ROI {rs[0]}x{rs[1]} -> mask "
+    extra = "".join(f", {k}={v}" for k, v in OVERRIDES.get(name, {}).items())
+    return {"workload": f"{preset} hierarchical RGB model{extra}, {w}x{h} input, batch {b} per GPU, {per_image} ROIs/image, ROI {rs[0]}x{rs[1]} -> mask "
                         f"{msz[0]}x{msz[1]}, random-init weights", "images_per_gpu": b, "rois_per_gpu": b * per_image,
             "encoder": kw["encoder_name"], "cache": "inputs larger than L2 (images + multi-GB activations per step)"}
 
@@ -348,7 +351,7 @@ def measure_model(ctx, workload, steps, warmup, precision="fast", e2e="pipelined
     preset, b_def, h, w, ppi_def = WORKLOADS[workload]
     n_img, per_image = n_img or b_def, per_image or ppi_def
     if model is None:
-        cfg, model = build_model(preset)
+        cfg, model = build_model(preset, OVERRIDES.get(workload))
         model = model.to(dev)
     else:
         from human_instance_segmentation_b200 import presets
@@ -613,7 +616,7 @@ def main():
                                    "tolerance": "north_star: max-rel <= 1e-3, argmax >= 99.9 % on every golden (tests/test_gpu_model.py)"}}
                 if ctx.world == 1:
                     subs = {"cfg0_b0_batch2_8rois": measure_latency_cfg0(ctx, sub_steps, 3)}
-                    for wl in ("b1", "b7", "b0_160x120"):
+                    for wl in ("b1", "b7", "b0_160x120", "b0_ln"):
                         subs[wl] = measure_model(ctx, wl, sub_steps, 3, "fast", e2e="pipelined")
                     subs["post"] = run_post(ctx, sub_steps, 3, cpu_baseline=False)
                     out["configs"] = subs
