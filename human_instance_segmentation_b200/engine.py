@@ -154,7 +154,7 @@ class Plan:
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
                   transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None,
                   row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None, up_input: Optional[Act] = None,
-                  res_scale: Optional[torch.Tensor] = None):
+                  res_scale: Optional[torch.Tensor] = None, alg_flops: Optional[int] = None):
         """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
         channels into the epilogue (his_conv_gemm_set_tail).  aux_f32: fp32 NCHW copy of the output written from the
         epilogue (his_conv_gemm_set_aux).  in_gate = (gate fp32 [N, Cin], fp16 scratch >= N*rows*cin_pad): per-image
@@ -173,7 +173,9 @@ class Plan:
         self.gemm_plans.append(h)
         self.keep += [w_packed, shift]
         taps = 4 if transposed else ksize * ksize
-        f = 2 * x.N * x.H * x.W * x.C * out.C * taps
+        # algorithmic FLOPs of the REFERENCE convolution this launch computes (alg_flops: a re-formulated layer whose weight
+        # matrix holds structural zeros reports the original conv's count, not the padded one)
+        f = alg_flops if alg_flops is not None else 2 * x.N * x.H * x.W * x.C * out.C * taps
         if tail is not None:
             tw, (b0, b1), tc, sig, tout, store_main = tail
             _lib.check(L.his_conv_gemm_set_tail(h, tw.data_ptr(), float(b0), float(b1), tc, 1 if sig else 0, tout.data_ptr(),

@@ -715,7 +715,7 @@ class _BuiltPlan:
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
              in_gate=None, row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
-             up_input: Optional[Act] = None, res_scale: Optional[torch.Tensor] = None) -> Optional[Act]:
+             up_input: Optional[Act] = None, res_scale: Optional[torch.Tensor] = None, alg_flops: Optional[int] = None) -> Optional[Act]:
         """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
         tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
         epilogue; the wide activation itself is then not written (its only consumer is the tail).
@@ -762,7 +762,7 @@ class _BuiltPlan:
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(shift, slab)), out,
                         k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate,
-                        row_scale=row_scale, stats_out=stats_out, up_input=up_input, res_scale=res_scale)
+                        row_scale=row_scale, stats_out=stats_out, up_input=up_input, res_scale=res_scale, alg_flops=alg_flops)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
@@ -894,7 +894,8 @@ class _BuiltPlan:
         cats = []
         for i, blk in enumerate(dec.blocks):
             th, tw = sizes[4 - i]                 # block i upsamples to feature level (4-i); level 0 = the image
-            cats.append(p.act(B, th, tw, blk.cin + blk.cskip))
+            # (the last block has no skip: its buffer is only needed when the block does not run in phase-packed form, see below)
+            cats.append(p.act(B, th, tw, blk.cin + blk.cskip) if blk.cskip else None)
         skip_slot = {1: cats[3].slice(dec.blocks[3].cin, oc[1]), 2: cats[2].slice(dec.blocks[2].cin, oc[2]),
                      3: cats[1].slice(dec.blocks[1].cin, oc[3]), 4: cats[0].slice(dec.blocks[0].cin, oc[4])}
 
@@ -943,8 +944,21 @@ class _BuiltPlan:
                 dst = skip_slot[level_of_stage[si]] if (last_of_stage and si in level_of_stage) else None
                 x = self._mbconv(x, blk, dst)
         # decoder (smp UnetDecoder, nearest resize + concat + 2x conv3x3-BN-ReLU)
+        head_fmt = 0
         for i, blk in enumerate(dec.blocks):
             cat = cats[i]
+            if self._phase_packed_tail(i, blk, x, sizes[4 - i]):
+                # Last decoder block (no skip): nearest-2x + conv3x3 + conv3x3 at 480x640 with 16 channels = 153 600 pixel tiles per
+                # 64 images whose cost is the per-tile latency of the GEMM pipeline, not their 16-wide MMAs.  The same arithmetic at
+                # the LOW resolution in phase-packed form -- channel block (py*2+px) of low pixel (y, x) = full pixel (2y+py, 2x+px):
+                #   conv1(up(x)) = a 3x3 conv Cin -> 4*C1 on x (taps that land on the same low pixel summed),
+                #   conv2        = a 3x3 conv 4*C1 -> 4*C2 whose weights are conv2's taps scattered by (input phase, low offset)
+                # -- a quarter of the tiles at N = 64; the 16 -> 1 head reads the phase-packed tensor directly.
+                x = self._decoder_tail_phase_packed(x, blk)
+                head_fmt = 2
+                continue
+            if cat is None:
+                cat = p.act(B, sizes[4 - i][0], sizes[4 - i][1], blk.cin + blk.cskip)
             up = cat.slice(0, blk.cin)
             full = cat.widen(blk.cin + blk.cskip)
             fuse_up = (cat.H, cat.W) == (2 * x.H, 2 * x.W) and x.C == blk.cin and \
@@ -958,13 +972,55 @@ class _BuiltPlan:
         # segmentation head conv3x3 16->1 (+bias) -> fp32 logits; output_conv 1->2; export-wrapper binary mask
         head = net.segmentation_head[0]
         self.u_one = p.f32(B, 1, H, W)
-        p.conv_direct(x, 0, B, H, W, x.C, x.cs, self.direct_w(head.weight), p.const(torch.ones(1)),
+        p.conv_direct(x, head_fmt, B, H, W, head.weight.shape[1], x.cs, self.direct_w(head.weight), p.const(torch.ones(1)),
                       p.const(head.bias.detach().float()), 1, 3, 1, 1, ACT["none"], out_f32=self.u_one)
         oc_w = m.pretrained_unet.output_conv.weight.detach().float().flatten().tolist()
         oc_b = m.pretrained_unet.output_conv.bias.detach().float().flatten().tolist()
         self._oc = (oc_w[0], oc_w[1], oc_b[0], oc_b[1])
         if not self.chunked_unet:          # chunked: run() writes each chunk's slice of the full-batch outputs
             p.add("unet_outputs", L.his_unet_outputs, self.u_one.data_ptr(), B, H, W, *self._oc, self.two.data_ptr(), self.binary.data_ptr())
+
+    def _phase_packed_tail(self, i: int, blk, x: Act, out_hw) -> bool:
+        if os.environ.get("HIS_UNET_PHASE_TAIL", "1") == "0":
+            return False
+        dec = self.m.pretrained_unet.model.model.decoder
+        c1, c2 = blk.conv1[0].weight.shape[0], blk.conv2[0].weight.shape[0]
+        return (i == len(dec.blocks) - 1 and blk.cskip == 0 and tuple(out_hw) == (2 * x.H, 2 * x.W) and x.C == blk.cin and x.C % 8 == 0
+                and c1 == 16 and c2 == 16 and self._is_bn(blk.conv1[1]) and self._is_bn(blk.conv2[1]))
+
+    def _decoder_tail_phase_packed(self, x: Act, blk) -> Act:
+        """smp UnetDecoderBlock without skip, at the input's resolution: returns the block's output in phase-packed form
+        [B, h, w, 4*C2] (see _build_unet)."""
+        w1 = blk.conv1[0].weight.detach().float().cpu()           # [C1, Cin, 3, 3]
+        w2 = blk.conv2[0].weight.detach().float().cpu()           # [C2, C1, 3, 3]
+        c1, cin = w1.shape[:2]
+        c2 = w2.shape[0]
+        W1 = torch.zeros(4 * c1, cin, 3, 3)
+        W2 = torch.zeros(4 * c2, 4 * c1, 3, 3)
+        for py in (0, 1):
+            for px in (0, 1):
+                ph = py * 2 + px
+                for dy in (-1, 0, 1):
+                    oy, qy = (py + dy) // 2, (py + dy) % 2      # low-resolution row offset and the input phase of full row 2y+py+dy
+                    for dx in (-1, 0, 1):
+                        ox, qx = (px + dx) // 2, (px + dx) % 2
+                        W1[ph * c1:(ph + 1) * c1, :, oy + 1, ox + 1] += w1[:, :, dy + 1, dx + 1]       # up(x) rows 2y+py+dy share low row y+oy
+                        W2[ph * c2:(ph + 1) * c2, (qy * 2 + qx) * c1:(qy * 2 + qx + 1) * c1, oy + 1, ox + 1] = w2[:, :, dy + 1, dx + 1]
+
+        def packed(conv_w, bn):
+            conv = nn.Conv2d(conv_w.shape[1], conv_w.shape[0], 3, padding=1, bias=False)
+            bn4 = nn.BatchNorm2d(conv_w.shape[0], eps=bn.eps)
+            with torch.no_grad():
+                conv.weight.copy_(conv_w)
+                for name in ("weight", "bias", "running_mean", "running_var"):
+                    getattr(bn4, name).copy_(getattr(bn, name).detach().float().cpu().repeat(4))
+            return conv, bn4
+
+        full_px = x.N * (2 * x.H) * (2 * x.W)
+        cv1, bn1 = packed(W1, blk.conv1[1])
+        cv2, bn2 = packed(W2, blk.conv2[1])
+        y = self.conv(x, cv1, bn1, ACT["relu"], alg_flops=2 * full_px * cin * c1 * 9)
+        return self.conv(y, cv2, bn2, ACT["relu"], alg_flops=2 * full_px * c1 * c2 * 9)
 
     def _mbconv(self, x: Act, blk, dst: Optional[Act]) -> Act:
         """timm DepthwiseSeparableConv / InvertedResidual (oracle/effunet.py _DS/_IR restates them)."""

@@ -120,7 +120,8 @@ long long his_conv_gemm_issued_macs(void* plan);
 /* ---- direct convolution for the shapes that are not GEMM-worthy (Cin = 2/3, Cout <= 2 tails, strided stem,
  * segmentation head): rgb.py:657 (3->64), ..._refinement.py:506,523,537 (tails / 2->64), ..._unet.py:371,
  * timm conv_stem, smp segmentation_head.  in_fmt 0: NHWC half slice; 1: NCHW fp32 with optional per-channel
- * input affine x*a[c]+b[c] (device [2*cin], applied to in-bounds samples only = normalise-then-zero-pad).
+ * input affine x*a[c]+b[c] (device [2*cin], applied to in-bounds samples only = normalise-then-zero-pad); 2: phase-packed NHWC half
+ * [N, H/2, W/2, 4*cin] (pixel (y, x) = channel block (y&1)*2 + (x&1) of low pixel (y>>1, x>>1); 3x3 16->1 head only).
  * w: fp16 [kh][kw][cin][cout]. Writes NHWC half slice and/or NCHW fp32. */
 int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, int H, int W, int cin, int in_cs,
                     const void* w, const float* scale, const float* shift, int cout, int kh, int kw, int stride, int pad,
