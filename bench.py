@@ -158,7 +158,7 @@ def cpu_reference_rate(preset, h, w, n_images, per_image, iters, threads, masks_
     return rois.shape[0] / min(times), min(times)
 
 
-def run_reference(args):
+def run_reference(args, out_stream=None):
     """Reference arm: the reference's CPU implementation of the path (oracle port -- the reference tree and smp/timm cannot travel
     to the GPU box) on all host cores, same contract as the GPU arm's `e2e`: images, rois -> instance_masks, binary_masks (the
     exported-ONNX outputs, export_onnx_advanced.py:353-457; aux-only branches not computed, as in the exported graph)."""
@@ -194,7 +194,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / done
     value = rois.shape[0] / dt
     sample = f"{sample_images} images x {per_image} ROIs of the {args.workload} workload per step, fp32, torch CPU ({threads} threads)"
-    print(json.dumps({
+    (out_stream or sys.stdout).write(json.dumps({
         "impl": "reference", "metric": "roi_masks_per_sec", "value": value, "unit": "ROI-masks/s", "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.workload, sample_images),
@@ -203,7 +203,7 @@ def run_reference(args):
                 "api": "oracle headport.forward(masks_only=True) + export_outputs: images, rois -> instance_masks, binary_masks "
                        "(the exported-ONNX contract, same work as the GPU arm's e2e)"},
         "note": "reference path = oracle port of the reference modules (the reference tree and smp/timm cannot travel to the GPU box); "
-                "per-ROI throughput on a bounded sample of the workload"}))
+                "per-ROI throughput on a bounded sample of the workload"}) + "\n")
 
 
 class Ctx:
@@ -596,6 +596,18 @@ def measure_strong_b7(ctx, steps, warmup):
 
 
 def main():
+    # exactly ONE line on stdout: libraries that print to fd 1 (NCCL's version banner ...) are sent to stderr, the JSON line is
+    # written to the real stdout at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(real_stdout):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -611,7 +623,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="replay the launch plan kernel by kernel instead of as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
     ctx = Ctx()
     try:
         if args.workload == "post":
@@ -654,7 +666,7 @@ def main():
                                                  "oracle port of the reference modules (reference tree cannot travel), exported-ONNX contract "
                                                  "(same work as e2e)"}
         if ctx.rank == 0 and out is not None:
-            print(json.dumps(out))
+            real_stdout.write(json.dumps(out) + "\n")
     finally:
         ctx.close()
 

@@ -578,8 +578,20 @@ class _BuiltPlan:
         stem_c = m.pretrained_unet.model.model.encoder.out_channels[1] if self.has_unet else 32
         # strict mode stores two fp16 planes per activation: half the images / ROIs per pass keep the footprint of a plan
         div = 2 if self.split else 1
-        self.Bc = max(1, min(B, m.max_images_per_pass or max(1, _images_per_pass(H, W, stem_c) // div))) if self.has_unet else B
-        self.Nc = min(N, m.max_rois_per_pass or max(1, _rois_per_pass(m.roi_size) // div))
+        bc_max = max(1, m.max_images_per_pass or max(1, _images_per_pass(H, W, stem_c) // div))
+        nc_max = max(1, m.max_rois_per_pass or max(1, _rois_per_pass(m.roi_size) // div))
+
+        def balanced(total, cap):
+            """Chunk size for `total` items in passes of at most `cap`: every pass runs the full chunk plan, so equal chunks
+            (170 ROIs at cap 160 -> 2 x 88, not 160 + a 160-wide pass holding 10)."""
+            if total <= cap:
+                return total
+            n = (total + cap - 1) // cap
+            c = (total + n - 1) // n
+            return min(cap, (c + 7) // 8 * 8 if c > 16 else c)
+
+        self.Bc = max(1, balanced(B, bc_max)) if self.has_unet else B
+        self.Nc = balanced(N, nc_max)
         if B == 0 and N:
             raise ValueError("rois given for an empty image batch")
         self.chunked_unet, self.chunked_head = self.Bc < B, self.Nc < N
