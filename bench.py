@@ -37,13 +37,16 @@ UNET_GFLOP_PER_IMG = {"b0": 27.72, "b1_enhanced": 29.97, "b7_ultra": 90.21}
 
 
 def measured_traffic(kernel: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json: dram__bytes_read.sum
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r2_traffic.json, else r1: dram__bytes_read.sum
     + dram__bytes_write.sum summed over the kernel's launches of one step / number of launches).  None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        return json.load(open(path)).get(kernel)
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            v = json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 def peaks():
