@@ -494,6 +494,20 @@ int his_conv_gemm_can_fuse_upsample(int H, int W, int cin, int cout, int low_c) 
   return (low_c > 0 && low_c <= cin && low_c % bk == 0) ? 1 : 0;
 }
 
+int his_conv_gemm_set_ln_partials(void* plan, double* partials, int* parts_per_image) {
+  if (!plan || !partials || !parts_per_image) return his_set_error(HIS_ERR_INVALID_ARG, "set_ln_partials: null pointer");
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  ConvGemmParams& p = pl->p;
+  if (p.n_img <= 0 || p.num_work % p.n_img) return his_set_error(HIS_ERR_UNSUPPORTED, "set_ln_partials: work items do not split by image");
+  if (p.tail_c && !p.store_main) return his_set_error(HIS_ERR_UNSUPPORTED, "set_ln_partials: the layer does not store its output");
+  if (p.res_scale) return his_set_error(HIS_ERR_UNSUPPORTED, "set_ln_partials: not together with a residual scale");
+  p.ln_partials = partials;
+  *parts_per_image = p.num_work / p.n_img;
+  return HIS_OK;
+}
+
+int his_conv_gemm_work_items(void* plan) { return plan ? ((ConvGemmPlan*)plan)->p.num_work : 0; }
+
 int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   if (!plan || !aux_out) return his_set_error(HIS_ERR_INVALID_ARG, "set_aux: null pointer");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;

@@ -140,6 +140,10 @@ struct ConvGemmParams {
   // lane of warp 2; 0 = the two cp.async producer warps (needed for the fused nearest upsample and the split-fp16 planes).
   // plane_bytes = pitch of an 8-channel plane in the window: 180*16 for the TMA box, +16 for the cp.async writes' bank spread.
   int a_tma, plane_bytes;
+  // LayerNorm2d statistics from the epilogue (hed/model.py:18-38: mean / variance over (C,H,W) per sample): every work item
+  // writes (sum, sum of squares) of the values it stores -- the fp16-rounded ones, i.e. what the normalise pass will read -- to
+  // ln_partials[work item][2] (double); a sample's work items are contiguous, his_layernorm2d_act adds them in order.
+  double* ln_partials;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -785,6 +789,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
       float st_sum = 0.0f, st_max = -INFINITY;
+      float ln_s = 0.0f, ln_q = 0.0f;
       for (int j = 0; j < nchunks; ++j) {
         const bool direct = j >= ntma;
         const int b = SPLIT ? 0 : (cc & 1);     // SPLIT: staging[0] = hi plane, staging[1] = lo plane of the chunk
@@ -896,6 +901,15 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               __half2 o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
+              if (p.ln_partials && inb) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  // SPLIT stores hi + lo ~ y itself; plain fp16 stores the rounded value
+                  const float2 h = SPLIT ? make_float2(y[2 * e], y[2 * e + 1]) : __half22float2(o[e]);
+                  if (c + 2 * e < p.cout) { ln_s += h.x; ln_q = fmaf(h.x, h.x, ln_q); }
+                  if (c + 2 * e + 1 < p.cout) { ln_s += h.y; ln_q = fmaf(h.y, h.y, ln_q); }
+                }
+              }
               if (!direct) *cell = *reinterpret_cast<uint4*>(o);
               else if (inb && c + 8 <= p.cout) *reinterpret_cast<uint4*>(p.out + pix * p.out_cs + c) = *reinterpret_cast<uint4*>(o);
               else if (inb) {
@@ -946,6 +960,18 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (p.stats_out && inb) {
         p.stats_out[pix * 2] = st_sum / (float)p.cout;
         p.stats_out[pix * 2 + 1] = st_max;
+      }
+      if (p.ln_partials) {      // fixed-order reduction: lanes (shuffle tree), then the group's four warps through shared memory
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { ln_s += __shfl_xor_sync(0xffffffffu, ln_s, o); ln_q += __shfl_xor_sync(0xffffffffu, ln_q, o); }
+        float* red = s_shift + 256 + g * 256;          // the residual-scale row of the group (LayerNorm layers carry none)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (lane == 0) { red[2 * q] = ln_s; red[2 * q + 1] = ln_q; }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (te == 0) {
+          p.ln_partials[2 * (long long)w] = ((double)red[0] + (double)red[2]) + ((double)red[4] + (double)red[6]);
+          p.ln_partials[2 * (long long)w + 1] = ((double)red[1] + (double)red[3]) + ((double)red[5] + (double)red[7]);
+        }
       }
       if (TAIL) {
         if (py < p.H && px < p.W) {

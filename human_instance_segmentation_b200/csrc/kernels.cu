@@ -1823,16 +1823,19 @@ int his_layernorm2d_parts(int N, int HW, int C) {
 }
 
 int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps, int act,
-                        float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws, void* out, int out_cs, int split,
-                        void* stream) {
+                        float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws, int nparts_given, void* out, int out_cs,
+                        int split, void* stream) {
   if (!in || !gamma || !beta || !partials_ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "layernorm2d: null pointer");
   if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "layernorm2d: res_mode without residual");
   if (C % 8 || in_cs % 8 || out_cs % 8 || (res_mode && res_cs % 8)) return his_set_error(HIS_ERR_UNSUPPORTED, "layernorm2d: channels must be multiples of 8");
   if (N == 0) return HIS_OK;
-  const int parts = his_layernorm2d_parts(N, HW, C);
+  // nparts_given > 0: partials_ws already holds that many (sum, sum of squares) pairs per sample, written by the producing GEMM's
+  // epilogue (his_conv_gemm_set_ln_partials): the statistics pass over the tensor is skipped
+  const int parts = nparts_given > 0 ? nparts_given : his_layernorm2d_parts(N, HW, C);
   const long long per_img_vec = (long long)HW * (C / 8);
   dim3 g1(parts, N);
-  ln_stats_kernel<<<g1, kThreads, 0, ST>>>((const __half*)in, per_img_vec, HW, C, in_cs, split ? in_cs / 2 : 0, partials_ws);
+  if (nparts_given <= 0)
+    ln_stats_kernel<<<g1, kThreads, 0, ST>>>((const __half*)in, per_img_vec, HW, C, in_cs, split ? in_cs / 2 : 0, partials_ws);
   long long gx = (per_img_vec + kThreads - 1) / kThreads;
   const long long cap = (148LL * 16 + N - 1) / N;
   if (gx > cap) gx = cap;

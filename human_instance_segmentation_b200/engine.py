@@ -30,7 +30,7 @@ class Act:
     inside one pixel -- the buffer is [N,H,W,cs] with the hi planes in [0, cs/2) and the lo plane of a channel cs/2 elements
     after its hi plane; ``cs`` stays the pixel stride the kernels are given."""
 
-    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off", "zero_tail", "split")
+    __slots__ = ("buf", "N", "H", "W", "C", "cs", "c_off", "zero_tail", "split", "ln_ws")
 
     def __init__(self, buf: torch.Tensor, C: int, c_off: int = 0, split: bool = False):
         assert buf.dtype == torch.float16 and buf.dim() == 4 and buf.is_contiguous()
@@ -39,6 +39,7 @@ class Act:
         self.C, self.c_off = C, c_off
         self.split = bool(split)
         self.zero_tail = False          # True: channels [C, cs) are zero and nobody ever writes them (see Plan.act_zeroed)
+        self.ln_ws = None               # (double [N, parts, 2], parts): LayerNorm2d partial statistics written by the producing GEMM
         assert c_off % 8 == 0 and self.cs % (16 if split else 8) == 0 and c_off + C <= self.width
 
     @property
@@ -83,6 +84,7 @@ class NullAct(Act):
         self.cs, self.c_off = round_up(C, 16), 0
         self.zero_tail = False
         self.split = False
+        self.ln_ws = None
 
 
 class Plan:
@@ -154,7 +156,7 @@ class Plan:
                   ksize: int, act: int, beta: float = 1.0, res: Optional[Act] = None, res_mode: int = RES_NONE,
                   transposed: bool = False, tail=None, aux_f32: Optional[torch.Tensor] = None, in_gate: Optional[torch.Tensor] = None,
                   row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None, up_input: Optional[Act] = None,
-                  res_scale: Optional[torch.Tensor] = None, alg_flops: Optional[int] = None):
+                  res_scale: Optional[torch.Tensor] = None, alg_flops: Optional[int] = None, ln_stats: bool = False):
         """tail = (tail_w fp32 [tc, cout_slab], (b0, b1), tc, sigmoid?, out_f32 NCHW, store_main) fuses a 1x1 conv to <=2
         channels into the epilogue (his_conv_gemm_set_tail).  aux_f32: fp32 NCHW copy of the output written from the
         epilogue (his_conv_gemm_set_aux).  in_gate = (gate fp32 [N, Cin], fp16 scratch >= N*rows*cin_pad): per-image
@@ -192,6 +194,13 @@ class Plan:
         if res_scale is not None:
             _lib.check(L.his_conv_gemm_set_res_scale(h, res_scale.data_ptr()), "his_conv_gemm_set_res_scale")
             self.keep.append(res_scale)
+        if ln_stats:                      # LayerNorm2d statistics of the output from the epilogue (one (sum, sumsq) pair per work item)
+            n_work = L.his_conv_gemm_work_items(h)
+            ws = torch.zeros((max(n_work, 1), 2), dtype=torch.float64, device=self.device)
+            parts = ctypes.c_int()
+            _lib.check(L.his_conv_gemm_set_ln_partials(h, ws.data_ptr(), ctypes.byref(parts)), "his_conv_gemm_set_ln_partials")
+            self.keep.append(ws)
+            out.ln_ws = (ws, parts.value)
         if up_input is not None:          # channels [0, up_input.C) gathered from the half-resolution tensor (nearest 2x)
             assert (2 * up_input.H, 2 * up_input.W) == (x.H, x.W) and up_input.N == x.N
             _lib.check(L.his_conv_gemm_set_upsampled_input(h, up_input.ptr, up_input.C, up_input.cs), "his_conv_gemm_set_upsampled_input")

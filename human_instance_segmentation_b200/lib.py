@@ -101,6 +101,8 @@ SIGNATURES = {
                              _P, c_int, c_int, c_int, c_float, c_int, c_int],
     "his_conv_gemm_set_tail": [_P, _P, c_float, c_float, c_int, c_int, _P, c_int],
     "his_conv_gemm_set_aux": [_P, _P],
+    "his_conv_gemm_set_ln_partials": [_P, _P, POINTER(c_int)],
+    "his_conv_gemm_work_items": [_P],
     "his_conv_gemm_set_row_ops": [_P, _P, _P],
     "his_conv_gemm_set_res_scale": [_P, _P],
     "his_conv_gemm_set_upsampled_input": [_P, _P, c_int, c_int],
@@ -119,7 +121,7 @@ SIGNATURES = {
     "his_scale_weights": [_P, _P, c_int, _LL, c_int, c_int, _P, c_int, _P],
     "his_scale_channels": [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, c_int, _P],
     "his_layernorm2d_parts": [c_int, c_int, c_int],
-    "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
+    "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P],
     "his_groupnorm_parts": [c_int, c_int, c_int],
     "his_groupnorm_act": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
     "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P],

@@ -727,7 +727,8 @@ class _BuiltPlan:
     def conv(self, x: Act, conv: nn.Module, norm, act: int, res: Optional[Act] = None, res_mode: int = RES_NONE,
              out: Optional[Act] = None, out_f32: Optional[torch.Tensor] = None, tail=None, aux_f32: Optional[torch.Tensor] = None,
              in_gate=None, row_scale: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None,
-             up_input: Optional[Act] = None, res_scale: Optional[torch.Tensor] = None, alg_flops: Optional[int] = None) -> Optional[Act]:
+             up_input: Optional[Act] = None, res_scale: Optional[torch.Tensor] = None, alg_flops: Optional[int] = None,
+             ln_stats: bool = False) -> Optional[Act]:
         """conv (+ folded BatchNorm) (+res) + activation.  Dense shapes -> tcgen05 GEMM, odd shapes -> direct kernel.
         tail = (conv1x1 module with <=2 outputs, sigmoid?, out_f32 NCHW): the following 1x1 conv, fused into the GEMM
         epilogue; the wide activation itself is then not written (its only consumer is the tail).
@@ -739,7 +740,9 @@ class _BuiltPlan:
             # LayerNorm2d (hed/model.py:18-38) and the group / instance family: per-sample statistics cannot fold into the conv ->
             # conv(+bias) to fp16, then the statistics + normalise kernels apply norm + residual + activation.
             assert tail is None and out_f32 is None and aux_f32 is None and stats_out is None
-            raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate, row_scale=row_scale)
+            # LayerNorm2d: the statistics of the conv output come from the GEMM epilogue (no separate pass over the tensor)
+            raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate, row_scale=row_scale,
+                            ln_stats=pt.group_norm_args(norm) is None and os.environ.get("HIS_LN_EPILOGUE", "1") != "0")
             return self.layernorm(raw, norm, act, res, res_mode, out)
         transposed = isinstance(conv, nn.ConvTranspose2d)
         w = conv.weight
@@ -774,7 +777,8 @@ class _BuiltPlan:
                 tl = (p.const(tw), (tb[0], tb[1]), tc, tsig, tout, False)
             p.conv_gemm(x, p.const(wp, torch.float16), cin_pad, p.const(pad_vec(shift, slab)), out,
                         k, act, self.beta, res, res_mode, transposed, tail=tl, aux_f32=aux_f32, in_gate=in_gate,
-                        row_scale=row_scale, stats_out=stats_out, up_input=up_input, res_scale=res_scale, alg_flops=alg_flops)
+                        row_scale=row_scale, stats_out=stats_out, up_input=up_input, res_scale=res_scale, alg_flops=alg_flops,
+                        ln_stats=ln_stats)
         else:
             if transposed:
                 raise NotImplementedError("direct transposed convolution")
@@ -807,12 +811,16 @@ class _BuiltPlan:
                   p.const(beta.reshape(-1)).data_ptr(), float(eps), act, self.beta, res_mode, res.ptr if res is not None else None,
                   res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs, self.S)
             return out
-        parts = L.his_layernorm2d_parts(x.N, x.H * x.W, x.C)
-        ws = torch.empty((x.N, parts, 2), dtype=torch.float64, device=self.dev)
-        p.keep.append(ws)
-        p.add("layernorm2d", L.his_layernorm2d_act, x.ptr, x.N, x.H * x.W, x.C, x.cs, p.const(norm.weight.reshape(-1)).data_ptr(),
-              p.const(norm.bias.reshape(-1)).data_ptr(), float(norm.eps), act, self.beta, res_mode, res.ptr if res is not None else None,
-              res.cs if res is not None else 0, ws.data_ptr(), out.ptr, out.cs, self.S)
+        given = 0
+        if getattr(x, "ln_ws", None) is not None:         # partial statistics written by the producing GEMM's epilogue
+            ws, given = x.ln_ws
+        else:
+            parts = L.his_layernorm2d_parts(x.N, x.H * x.W, x.C)
+            ws = torch.empty((x.N, parts, 2), dtype=torch.float64, device=self.dev)
+            p.keep.append(ws)
+        p.add("layernorm2d" if not given else "layernorm2d_apply", L.his_layernorm2d_act, x.ptr, x.N, x.H * x.W, x.C, x.cs,
+              p.const(norm.weight.reshape(-1)).data_ptr(), p.const(norm.bias.reshape(-1)).data_ptr(), float(norm.eps), act, self.beta, res_mode,
+              res.ptr if res is not None else None, res.cs if res is not None else 0, ws.data_ptr(), given, out.ptr, out.cs, self.S)
         return out
 
     def residual_block(self, x: Act, rb: pt.ResidualBlockParams, act: int, out: Optional[Act] = None, tail=None, aux_f32=None,

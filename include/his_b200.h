@@ -97,6 +97,11 @@ int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float
  * returns in its aux dict: shared_features ..._refinement.py:557, fg_attention :570); with res_mode MUL the copy is the
  * activated value before the product (the gate).  Layers with Cin >= 64 only. */
 int his_conv_gemm_set_aux(void* plan, float* aux_out);
+/* LayerNorm2d statistics from the epilogue: every work item of the layer writes (sum, sum of squares) of the values it stores to
+ * partials[work item][2] (double, device); *parts_per_image receives the work items per sample.  his_layernorm2d_act(...,
+ * partials, nparts_given = *parts_per_image, ...) then skips its own pass over the tensor. */
+int his_conv_gemm_set_ln_partials(void* plan, double* partials, int* parts_per_image);
+int his_conv_gemm_work_items(void* plan);
 /* Per-pixel (GEMM row) extras of the SpatialAttentionModule fusion (hed/advanced/attention_modules.py:67-113):
  * row_scale [n_img*H*W] fp32 (may be NULL): y = act(row_scale[pix]*conv(x) + shift ...), i.e. the conv of the gated input;
  * stats_out [n_img*H*W][2] fp32 (may be NULL): channel mean and max of this layer's output per pixel. */
@@ -156,7 +161,7 @@ int his_scale_channels(const void* in, int in_cs, const float* gate, int N, int 
  * NCHW fp32 in, PyTorch weight layout [Cin][Cout][2][2] fp32, NHWC half out. */
 int his_layernorm2d_parts(int N, int HW, int C);
 int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const float* gamma, const float* beta, float eps,
-                        int act, float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws,
+                        int act, float act_beta, int res_mode, const void* res, int res_cs, double* partials_ws, int nparts_given,
                         void* out, int out_cs, int split, void* stream);
 /* nn.GroupNorm / nn.InstanceNorm2d(affine=True) / AdaptiveInstanceNorm2d / SpatialGroupNorm of get_normalization_layer
  * (hed/advanced/normalization_comparison.py:12-74,159-206) + residual + activation on an NHWC half slice: statistics per
