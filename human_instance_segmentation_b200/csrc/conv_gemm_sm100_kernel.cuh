@@ -906,8 +906,9 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int e = 0; e < 4; ++e) {
                   // SPLIT stores hi + lo ~ y itself; plain fp16 stores the rounded value
                   const float2 h = SPLIT ? make_float2(y[2 * e], y[2 * e + 1]) : __half22float2(o[e]);
-                  if (c + 2 * e < p.cout) { ln_s += h.x; ln_q = fmaf(h.x, h.x, ln_q); }
-                  if (c + 2 * e + 1 < p.cout) { ln_s += h.y; ln_q = fmaf(h.y, h.y, ln_q); }
+                  const int cv = (p.phase_merge > 1 ? c % p.phase_slab : c) + 2 * e;      // channel within its ConvT phase
+                  if (cv < p.cout) { ln_s += h.x; ln_q = fmaf(h.x, h.x, ln_q); }
+                  if (cv + 1 < p.cout) { ln_s += h.y; ln_q = fmaf(h.y, h.y, ln_q); }
                 }
               }
               if (!direct) *cell = *reinterpret_cast<uint4*>(o);
