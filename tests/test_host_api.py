@@ -160,3 +160,43 @@ def test_pretrained_unet_weights_are_loaded_from_the_path(tmp_path):
                                               encoder_name="timm-efficientnet-b0")
     # (torch does not report BatchNorm's num_batches_tracked as missing for a state dict without version metadata)
     assert set(m.pretrained_unet.model.load_report[0]) == {k for k in sd if k not in part and not k.endswith("num_batches_tracked")}
+
+
+def test_plan_capacity_buckets_and_split_weight_packing():
+    """Host logic of the serving plan cache (dynamic batch_size / num_rois, export_onnx_advanced.py:427-457) and of the strict
+    precision mode's weight split."""
+    from human_instance_segmentation_b200 import engine, model
+    prev = 0
+    for n in range(0, 3000):
+        b = model._bucket_rois(n)
+        assert b >= n and b >= prev and model._bucket_rois(b) == b          # covers the request, monotonic, idempotent
+        assert b - n < (1 if n <= 16 else 8 if n <= 64 else 32 if n <= 256 else 64)     # bounded padding
+        prev = b
+    assert [model._bucket_images(b) for b in (0, 1, 16, 17, 63, 64)] == [0, 1, 16, 24, 64, 64]
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(40, 24, 3, 3, generator=g) * 0.07
+    scale = torch.rand(40, generator=g) + 0.5
+    hi, k1 = engine.pack_gemm_weight(w, 48, False, scale)
+    both, k2 = engine.pack_gemm_weight(w, 48, False, scale, split=True)
+    assert k2 == 2 * k1 and both.shape[-1] == k2 and torch.equal(both[..., :k1], hi)
+    full = (w * scale.view(-1, 1, 1, 1)).permute(2, 3, 0, 1).reshape(9, 40, 24)
+    rec = both[0, :, :40, :24].float() + both[0, :, :40, k1:k1 + 24].float()
+    assert float((rec - full).abs().max()) <= 2.0 ** -21 * float(full.abs().max())      # hi + lo carries ~21 bits
+    assert float((hi[0, :, :40, :24].float() - full).abs().max()) > 2.0 ** -14 * float(full.abs().max())   # ... a single fp16 does not
+    wt = torch.randn(24, 40, 2, 2, generator=g)
+    bt, kt = engine.pack_gemm_weight(wt, 48, True, None, split=True)
+    assert bt.shape == (4, 1, 48, kt) and kt == 128
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["metric"] == "roi_masks_per_sec" and rec["value"] > 0
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["cpu_baseline"]["kind"] == "port"
