@@ -270,9 +270,13 @@ __global__ void direct_conv_kernel(const DirectConvParams p) {
 // in shared memory as fp32 and read as broadcast float4s.
 template <int KK /*k*k*/, int CIN>
 __global__ void small_cin_conv_kernel(const DirectConvParams p) {
-  extern __shared__ float s_w[];            // [KK*CIN][Cout]
+  extern __shared__ float s_w[];            // [KK*CIN][Cout] weights, then scale[Cout], shift[Cout] (broadcast reads instead of
+                                            // two global loads per output channel per thread)
   const int nw = KK * CIN * p.Cout;
+  float* s_sc = s_w + nw;
+  float* s_sh = s_sc + p.Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = dc_w(p, i);
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { s_sc[i] = __ldg(p.scale + i); s_sh[i] = __ldg(p.shift + i); }
   __syncthreads();
   const int groups = p.Cout / 32;
   const long long total = (long long)p.N * p.Ho * p.Wo * groups;
@@ -320,7 +324,7 @@ __global__ void small_cin_conv_kernel(const DirectConvParams p) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = q * 8 + e;
-        y8[e] = his_act(acc[c] * __ldg(p.scale + co + c) + __ldg(p.shift + co + c), p.act, p.act_beta);
+        y8[e] = his_act(fmaf(acc[c], s_sc[co + c], s_sh[co + c]), p.act, p.act_beta);
       }
       his_st8(op + q * 8, p.out_lo, y8);
     }
@@ -1597,10 +1601,10 @@ int his_conv_direct(const void* in, int in_fmt, const float* in_affine, int N, i
   if (N == 0) return HIS_OK;
   // specialised kernels for the shapes the path actually uses
   if (cin <= 4 && cout % 32 == 0 && out_half && !out_f32 && !res_mode && (out_cs % 8) == 0 && kh == kw && (kh == 1 || kh == 3) &&
-      (size_t)kh * kw * cin * cout * sizeof(float) <= 48 * 1024 && (in_fmt == 1 || in_fmt == 0)) {
+      ((size_t)kh * kw * cin + 2) * cout * sizeof(float) <= 48 * 1024 && (in_fmt == 1 || in_fmt == 0)) {
     const long long total = (long long)N * p.Ho * p.Wo * (cout / 32);
     const int g = grid_for(total, 128);
-    const size_t sm = (size_t)kh * kw * cin * cout * sizeof(float);
+    const size_t sm = ((size_t)kh * kw * cin * cout + 2 * (size_t)cout) * sizeof(float);
     bool done = true;
     if (kh == 3 && cin == 3) small_cin_conv_kernel<9, 3><<<g, 128, sm, ST>>>(p);
     else if (kh == 1 && cin == 2) small_cin_conv_kernel<1, 2><<<g, 128, sm, ST>>>(p);
