@@ -148,3 +148,38 @@ def test_fused_mask_cleanup_equals_the_two_modules_and_the_oracle():
                        pp.BinaryMaskBilateralFilter(5, 1.5, 0.5, 1)(pp.BinaryMaskEdgeSmoothing()(odd.cuda())))
     want = postport.binary_bilateral(postport.edge_smooth(odd), 5, 1.5, 0.5, 1)
     assert _frac_bad(pp.MaskCleanup(num_iterations=1, kernel_size=5)(odd.cuda()), want) <= 1e-4
+
+
+@pytest.mark.parametrize("k,its", [(7, 2), (7, 1), (5, 2), (5, 1), (3, 2), (3, 1)])
+def test_wide_mask_cleanup_is_bit_identical_to_the_unfused_chain(k, its):
+    """The 64x32 / vector-load / table form of the fused clean-up kernel (post_stencil.cu: mask_cleanup_wide_kernel) against
+    the two separate kernels that keep the plain per-pixel arithmetic: noise masks (every (centre, edge, corner) neighbour
+    count of the edge-smoothing table occurs), blob masks, soft masks (the block-wide vote sends them down the general
+    edge-smoothing path), sizes with partial tiles on both axes and W % 4 != 0 (scalar stores)."""
+    from oracle.make_golden_post import blob_masks
+    g = torch.Generator().manual_seed(100 * k + its)
+    fused = pp.MaskCleanup(kernel_size=k, num_iterations=its).cuda()
+    es, bf = pp.BinaryMaskEdgeSmoothing().cuda(), pp.BinaryMaskBilateralFilter(k, 1.5, 0.5, its).cuda()
+    cases = [
+        (torch.rand(3, 1, 96, 128, generator=g) > 0.5).float(),
+        (torch.rand(2, 2, 67, 131, generator=g) > 0.3).float(),          # W % 4 != 0, partial tiles
+        (torch.rand(1, 1, 33, 65, generator=g) > 0.7).float(),
+        (torch.rand(1, 1, 5, 3, generator=g) > 0.5).float(),             # smaller than the halo
+        blob_masks(3, 2, 120, 200),
+        torch.rand(2, 1, 70, 90, generator=g),                           # soft masks
+        torch.cat([(torch.rand(1, 1, 64, 128, generator=g) > 0.5).float(), torch.rand(1, 1, 64, 128, generator=g)]),   # mixed planes
+    ]
+    for m in cases:
+        m = m.cuda().contiguous()
+        want = bf(es(m))
+        got = fused(m)
+        assert torch.equal(got, want), f"k={k} its={its} shape={tuple(m.shape)}: {(got != want).sum().item()} pixels differ"
+    # an output buffer that is not 16-byte aligned (view at an odd element offset): scalar stores
+    m = (torch.rand(2, 1, 64, 128, generator=g) > 0.5).float().cuda()
+    buf = torch.empty(m.numel() + 1, device="cuda")
+    out = buf[1:].view_as(m)
+    assert torch.equal(fused(m, out=out), bf(es(m)))
+    # other thresholds / strength
+    f2 = pp.MaskCleanup(0.4, 2.0, k, 1.2, 0.45, its).cuda()
+    m = blob_masks(4, 2, 90, 150).cuda()
+    assert torch.equal(f2(m), pp.BinaryMaskBilateralFilter(k, 1.2, 0.45, its).cuda()(pp.BinaryMaskEdgeSmoothing(0.4, 2.0).cuda()(m)))
