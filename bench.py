@@ -242,7 +242,7 @@ class Ctx:
 
 def run_post(ctx, steps, warmup, cpu_baseline=True):
     """BASELINE configs[4]: post-processing only.  A step = (a) the ROI chain on 10 ROIs per image -- MaskDilationModule on the
-    [N,3,128,96] logits, argmax -> instance mask (u8), NEAREST paste-back onto the 480x640 label canvases -- and (b) the
+    [N,3,128,96] logits + argmax -> instance mask (u8) in one kernel, NEAREST paste-back onto the 480x640 label canvases -- and (b) the
     full-image mask clean-up -- BinaryMaskEdgeSmoothing + BinaryMaskBilateralFilter fused in one shared-memory pass over
     [B,1,480,640] masks.  value = masks (ROI masks + full-image masks) per second with inputs resident in HBM; the roofline is
     the fused stencil kernel against the measured HBM copy bandwidth (algorithmic bytes: read + write once, 2*H*W*4 per mask)."""
@@ -259,11 +259,11 @@ def run_post(ctx, steps, warmup, cpu_baseline=True):
     logits_h = (torch.randn(N, 3, mh // 8, mw // 8, generator=g) * 2)
     logits_h = torch.nn.functional.interpolate(logits_h, size=(mh, mw), mode="bilinear").contiguous().pin_memory()
     full, rois, logits = full_h.to(dev), rois_h.to(dev), logits_h.to(dev)
-    cleanup, dil = pp.MaskCleanup().to(dev), pp.MaskDilationModule(1)
+    cleanup = pp.MaskCleanup().to(dev)
     out_full = torch.empty_like(full)
 
     def step(f, r, lg):
-        masks = pp.instance_masks(dil(lg), as_uint8=True)
+        masks = pp.instance_masks(lg, as_uint8=True, dilation_pixels=1)       # MaskDilationModule(1) + argmax, one pass
         canvas = pp.paste_masks(masks, r, B, H, W)
         return cleanup(f, out=out_full), canvas
 
@@ -323,7 +323,7 @@ def run_post(ctx, steps, warmup, cpu_baseline=True):
            "e2e": {"value": world * units / (ms_e2e * 1e-3), "unit": "masks/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": full_h.numel() * 4 + logits_h.numel() * 4 + rois_h.numel() * 4,
                    "d2h_bytes_per_step": res_h.numel() * 4 + canvas_h.numel() * 4,
-                   "api": "postprocess.MaskDilationModule / instance_masks / paste_masks / MaskCleanup on pinned host tensors"},
+                   "api": "postprocess.instance_masks(dilation_pixels=1) / paste_masks / MaskCleanup on pinned host tensors"},
            "gpu_launches": 5 * steps, "launches_per_step": 5,
            "roofline": {"bound": "hbm", "kernel": "mask_cleanup_fused_kernel", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / pk["hbm_gbs"], "traffic": measured_traffic("mask_cleanup_fused_kernel:post"), "peak_source": pk["source"],

@@ -40,37 +40,6 @@ __global__ void instance_mask_kernel(const float* __restrict__ logits, int N, lo
   }
 }
 
-__device__ __forceinline__ float softmax_p1(const float* __restrict__ logits, long long n, long long HW, long long p) {
-  const float l0 = logits[(n * 3) * HW + p], l1 = logits[(n * 3 + 1) * HW + p], l2 = logits[(n * 3 + 2) * HW + p];
-  const float m = fmaxf(l0, fmaxf(l1, l2));
-  const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
-  return e1 / ((e0 + e1) + e2);
-}
-
-// MaskDilationModule, export_hierarchical_instance_peopleseg_onnx.py:85-141
-__global__ void dilate_logits_kernel(const float* __restrict__ logits, int N, int H, int W, int k, float* __restrict__ out) {
-  const long long HW = (long long)H * W, total = (long long)N * HW;
-  GRID_STRIDE(idx, total) {
-    const long long n = idx / HW, p = idx % HW;
-    const int y = (int)(p / W), x = (int)(p % W);
-    const float p1 = softmax_p1(logits, n, HW, p);
-    float d = p1;
-    for (int dy = -k; dy <= k; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = -k; dx <= k; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= W || (dx == 0 && dy == 0)) continue;
-        d = fmaxf(d, softmax_p1(logits, n, HW, (long long)yy * W + xx));
-      }
-    }
-    const float l0 = logits[(n * 3) * HW + p], l1 = logits[(n * 3 + 1) * HW + p], l2 = logits[(n * 3 + 2) * HW + p];
-    out[(n * 3) * HW + p] = l0;
-    out[(n * 3 + 1) * HW + p] = ((d - p1) > 0.1f) ? l1 + 2.0f : l1;
-    out[(n * 3 + 2) * HW + p] = l2;
-  }
-}
-
 __device__ __forceinline__ float at0(const float* __restrict__ img, int H, int W, int y, int x) {
   return (y >= 0 && y < H && x >= 0 && x < W) ? img[(long long)y * W + x] : 0.0f;
 }
@@ -180,8 +149,13 @@ __global__ void threshold_kernel(const float* __restrict__ in, long long total, 
 // Paste-back (test_hierarchical_instance_peopleseg_onnx.py:144-161,264-278,369-374): box = int(x1*W) ... (fp32 product,
 // truncation), cv2.resize(..., INTER_NEAREST): src = min(floor(dst * (1/(dst_size/src_size))), src_size-1) in double,
 // full[y1:y2, x1:x2] = mask; later instances win.  canvas[b,y,x] = 1 + index of the last ROI whose pasted mask is 1.
-__global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int mh, int mw, const float* __restrict__ rois, int* __restrict__ canvas,
-                             int B, int H, int W) {
+// One CTA = one ROI x one slice of its rows: the source column of every destination column is tabulated once per CTA (the
+// double-precision floor product of cv2's NEAREST rule), a warp then walks one destination row at a time (source row computed
+// once per row, lanes over columns: coalesced RED.MAX, byte gather along one mask row) -- no 64-bit division per pixel.
+constexpr int kPasteTab = 4096;
+__global__ void __launch_bounds__(kThreads) paste_kernel(const unsigned char* __restrict__ masks, int N, int mh, int mw, const float* __restrict__ rois,
+                                                         int* __restrict__ canvas, int B, int H, int W) {
+  __shared__ unsigned short sxt[kPasteTab];
   const int roi = blockIdx.x;          // ROIs on gridDim.x (2^31-1 blocks): one call handles any ROI count
   const float* r = rois + 5 * roi;
   const int b = (int)r[0];
@@ -191,13 +165,22 @@ __global__ void paste_kernel(const unsigned char* __restrict__ masks, int N, int
   const int bw = x2 - x1, bh = y2 - y1;
   if (bw <= 0 || bh <= 0) return;
   const double sx = 1.0 / ((double)bw / (double)mw), sy = 1.0 / ((double)bh / (double)mh);
-  const long long total = (long long)bw * bh;
-  for (long long idx = blockIdx.y * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.y * blockDim.x) {
-    const int dx = (int)(idx % bw), dy = (int)(idx / bw);
-    const int X = x1 + dx, Y = y1 + dy;
-    if (X < 0 || X >= W || Y < 0 || Y >= H) continue;
-    const int sxi = min((int)floor((double)dx * sx), mw - 1), syi = min((int)floor((double)dy * sy), mh - 1);
-    if (masks[((long long)roi * mh + syi) * mw + sxi]) atomicMax(canvas + ((long long)b * H + Y) * W + X, roi + 1);
+  const bool tab = bw <= kPasteTab && mw <= 65536;
+  if (tab) {
+    for (int dx = threadIdx.x; dx < bw; dx += kThreads) sxt[dx] = (unsigned short)min((int)floor((double)dx * sx), mw - 1);
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = kThreads / 32;
+  // destination rows / columns clipped to the canvas once
+  const int dy_lo = max(0, -y1), dy_hi = min(bh, H - y1), dx_lo = max(0, -x1), dx_hi = min(bw, W - x1);
+  for (int dy = dy_lo + blockIdx.y * wpb + warp; dy < dy_hi; dy += gridDim.y * wpb) {
+    const int syi = min((int)floor((double)dy * sy), mh - 1);
+    const unsigned char* mrow = masks + ((long long)roi * mh + syi) * mw;
+    int* crow = canvas + ((long long)b * H + (y1 + dy)) * W + x1;
+    for (int dx = dx_lo + lane; dx < dx_hi; dx += 32) {
+      const int sxi = tab ? (int)sxt[dx] : min((int)floor((double)dx * sx), mw - 1);
+      if (mrow[sxi]) atomicMax(crow + dx, roi + 1);
+    }
   }
 }
 
@@ -275,21 +258,6 @@ int his_post_instance_mask(const float* logits, int N, int H, int W, float score
   return HIS_OK;
 }
 
-int his_post_dilate_logits(const float* logits, int N, int H, int W, int dilation_pixels, float* out, void* stream) {
-  if (!logits || !out) return his_set_error(HIS_ERR_INVALID_ARG, "dilate_logits: null pointer");
-  if (dilation_pixels < 0 || dilation_pixels > 16) return his_set_error(HIS_ERR_UNSUPPORTED, "dilate_logits: dilation_pixels must be in [0,16]");
-  const long long total = (long long)N * H * W;
-  if (total == 0) return HIS_OK;
-  if (dilation_pixels == 0) {
-    if (cudaMemcpyAsync(out, logits, (size_t)total * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ST) != cudaSuccess)
-      return his_set_error(HIS_ERR_LAUNCH, "memcpy failed");
-    return HIS_OK;
-  }
-  dilate_logits_kernel<<<grid_for(total), kThreads, 0, ST>>>(logits, N, H, W, dilation_pixels, out);
-  HIS_CHECK_LAUNCH();
-  return HIS_OK;
-}
-
 int his_post_edge_smooth(const float* mask, int N, int H, int W, float threshold, float blur_strength, float* out, void* stream) {
   if (!mask || !out) return his_set_error(HIS_ERR_INVALID_ARG, "edge_smooth: null pointer");
   const long long total = (long long)N * H * W;
@@ -361,7 +329,7 @@ int his_eval_confusion(const float* logits, const void* gt, int gt_is_int64, int
 int his_post_paste(const unsigned char* masks, int N, int mh, int mw, const float* rois, int* canvas, int B, int H, int W, void* stream) {
   if (!masks || !rois || !canvas) return his_set_error(HIS_ERR_INVALID_ARG, "paste: null pointer");
   if (N == 0) return HIS_OK;
-  dim3 grid(N, 32);
+  dim3 grid(N, 8);
   paste_kernel<<<grid, kThreads, 0, ST>>>(masks, N, mh, mw, rois, canvas, B, H, W);
   HIS_CHECK_LAUNCH();
   return HIS_OK;

@@ -593,32 +593,53 @@ __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, 
   }
 }
 
-template <int K>
+// 3 CTAs per SM: 80 registers; 4 (64 registers, spills) measured 9 % slower
+template <int K, int ITS>
 __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
-                                                                        const float* __restrict__ gauss, int iterations, float thr,
-                                                                        float* __restrict__ out) {
+                                                                        const float* __restrict__ gauss, float thr, float* __restrict__ out) {
   __shared__ __align__(16) float pa[kPlane2], pb[kPlane2], pc[kPlane2];
   __shared__ __align__(16) float wk[K * 8];
   __shared__ float tab[64];
   constexpr int R = K / 2;
-  const int halo = 1 + iterations * R;                        // <= kHalo2 (host checks)
+  constexpr int halo = 1 + ITS * R;                           // <= kHalo2 (host checks)
+  constexpr int D = 8 - halo;                                 // plane column of the window's first column
   const int tiles_x = (W + TW2 - 1) / TW2;
   const int x0 = (blockIdx.x % tiles_x) * TW2, y0 = blockIdx.y * TH2;
   const long long plane = (long long)(blockIdx.x / tiles_x) * H * W;
-  const int W0 = TW2 + 2 * halo, H0 = TH2 + 2 * halo;
+  constexpr int W0 = TW2 + 2 * halo, H0 = TH2 + 2 * halo;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // window (zero padded, pad columns of the pitch zeroed too) + is every value 0 or 1?
+  const bool vec_io = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  // window, zero padded; plane column p holds image column x0 - 8 + p (80 columns: the window aligned down to 16 bytes, so a
+  // row is 20 float4 loads when W % 4 == 0 -- a group of four is then entirely inside or outside the image).  Is every
+  // value 0 or 1?
   bool bin = true;
-  for (int r = warp; r < H0; r += kThreads / 32) {
-    const int y = y0 - halo + r;
-    const bool yin = y >= 0 && y < H;
-    const float* grow = in + plane + (long long)y * W;
-    for (int c = lane; c < kPitch2; c += 32) {
-      const int x = x0 - halo + c;
-      float v = 0.0f;
-      if (yin && c < W0 && x >= 0 && x < W) v = grow[x];
-      bin = bin && (v == 0.0f || v == 1.0f);
-      pa[r * kPitch2 + c] = v;
+  if (vec_io) {
+    constexpr int G = 20;                                     // float4 groups per window row
+#pragma unroll
+    for (int u = 0; u < (46 * G + kThreads - 1) / kThreads; ++u) {
+      const int i = threadIdx.x + u * kThreads;
+      const int r = i / G, q = i - r * G;
+      const int y = y0 - halo + r, x = x0 - 8 + 4 * q;
+      if (r < H0) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4*>(in + plane + (long long)y * W + x));
+        bin = bin && (v.x == 0.0f || v.x == 1.0f) && (v.y == 0.0f || v.y == 1.0f) && (v.z == 0.0f || v.z == 1.0f) && (v.w == 0.0f || v.w == 1.0f);
+        *reinterpret_cast<float4*>(pa + r * kPitch2 + 4 * q) = v;
+      }
+    }
+    if (threadIdx.x < H0) *reinterpret_cast<float4*>(pa + threadIdx.x * kPitch2 + 80) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int r = warp; r < H0; r += kThreads / 32) {
+      const int y = y0 - halo + r;
+      const bool yin = y >= 0 && y < H;
+      const float* grow = in + plane + (long long)y * W;
+      for (int c = lane; c < kPitch2; c += 32) {
+        const int x = x0 - 8 + c;
+        float v = 0.0f;
+        if (yin && c < 80 && x >= 0 && x < W) v = grow[x];
+        bin = bin && (v == 0.0f || v == 1.0f);
+        pa[r * kPitch2 + c] = v;
+      }
     }
   }
   for (int i = threadIdx.x; i < K * 8; i += kThreads) wk[i] = (i & 7) < K ? gauss[(i >> 3) * K + (i & 7)] : 0.0f;
@@ -638,10 +659,10 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
       const int S = (rw + 3) >> 2;
       for (int i = threadIdx.x; i < S * rh; i += kThreads) {
         const int sx = i / rh, ry = i - sx * rh, c0 = sx * 4, y = oy + ry;
-        float up[8], mid[8], dn[8];
-        const float* base = pa + ry * kPitch2 + c0;
+        float up[12], mid[12], dn[12];
+        const float* base = pa + ry * kPitch2 + c0 + (D & ~3);
 #pragma unroll
-        for (int l = 0; l < 2; ++l) {
+        for (int l = 0; l < 3; ++l) {
           const float4 a = reinterpret_cast<const float4*>(base)[l], b = reinterpret_cast<const float4*>(base + kPitch2)[l],
                        d = reinterpret_cast<const float4*>(base + 2 * kPitch2)[l];
           up[4 * l] = a.x; up[4 * l + 1] = a.y; up[4 * l + 2] = a.z; up[4 * l + 3] = a.w;
@@ -650,12 +671,12 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
         }
         float cs[6], o[4];
 #pragma unroll
-        for (int l = 0; l < 6; ++l) cs[l] = up[l] + dn[l];
+        for (int l = 0; l < 6; ++l) cs[l] = up[l + (D & 3)] + dn[l + (D & 3)];
         const bool yin = y >= 0 && y < H;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float ne = cs[j + 1] + mid[j] + mid[j + 2], nc = cs[j] + cs[j + 2];
-          const int idx = __float2int_rn(fmaf(mid[j + 1], 25.0f, fmaf(ne, 5.0f, nc)));
+          const float ne = cs[j + 1] + mid[j + (D & 3)] + mid[j + 2 + (D & 3)], nc = cs[j] + cs[j + 2];
+          const int idx = __float2int_rn(fmaf(mid[j + 1 + (D & 3)], 25.0f, fmaf(ne, 5.0f, nc)));
           const int x = ox + c0 + j;
           o[j] = (yin && x >= 0 && x < W) ? tab[idx] : 0.0f;
         }
@@ -665,13 +686,13 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
       for (int i = threadIdx.x; i < rw * rh; i += kThreads) {
         const int ry = i / rw, c = i - ry * rw, y = oy + ry, x = ox + c;
         const bool in_img = y >= 0 && y < H && x >= 0 && x < W;
-        pb[ry * kPitch2 + c] = in_img ? (edge_smooth_at(pa, kPitch2, ry + 1, c + 1, es_strength) > es_thr ? 1.0f : 0.0f) : 0.0f;
+        pb[ry * kPitch2 + c] = in_img ? (edge_smooth_at(pa, kPitch2, ry + 1, c + 1 + D, es_strength) > es_thr ? 1.0f : 0.0f) : 0.0f;
       }
     }
   }
   __syncthreads();
-  const bool vec_store = (W & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  if (iterations == 1) {
+  const bool vec_store = vec_io;
+  if (ITS == 1) {
     const Region g{TW2, TH2, y0, x0};
     bilateral_stage2<K, true, true>(pb, nullptr, nullptr, nullptr, wk, g, H, W, thr, out + plane, vec_store);
   } else {
@@ -680,6 +701,75 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
     __syncthreads();
     const Region g2{TW2, TH2, y0, x0};
     bilateral_stage2<K, false, true>(pa, pc, nullptr, nullptr, wk, g2, H, W, thr, out + plane, vec_store);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- MaskDilationModule, tiled
+// export_hierarchical_instance_peopleseg_onnx.py:85-141: p1 = softmax(logits)[1]; d = max_pool(p1, 2k+1, stride 1, pad k);
+// l1 += 2 where d - p1 > 0.1.  p1 is computed ONCE per pixel into shared memory (the per-pixel form evaluated 3 expf + a
+// division for each of the (2k+1)^2 neighbours: 1.5 G warp instructions per 5 120 ROIs), the window maximum is taken as a
+// row pass then a column pass (max is exact in any order); pixels outside the plane hold -1 and never win, which is
+// max_pool2d's implicit -inf padding.  MASK: the instance mask of the dilated logits (instance_mask_kernel's rule) is
+// written instead of the logits -- the dilated tensor never goes to HBM.
+__device__ __forceinline__ float softmax_p1_of(float l0, float l1, float l2) {
+  const float m = fmaxf(l0, fmaxf(l1, l2));
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+  return e1 / ((e0 + e1) + e2);
+}
+
+constexpr int kDilMax = 16;                                  // largest dilation_pixels (host checks)
+
+template <bool MASK>
+__global__ void __launch_bounds__(kThreads) dilate_logits_tiled_kernel(const float* __restrict__ logits, int H, int W, int k, float score_thr,
+                                                                       float* __restrict__ out, unsigned char* __restrict__ out_u8) {
+  __shared__ float sp[(TH + 2 * kDilMax) * (TW + 2 * kDilMax + 1)];      // p1 window, odd pitch
+  __shared__ float sr[(TH + 2 * kDilMax) * TW];                          // row maxima
+  const Tile t = tile_of(H, W);
+  const long long HW = (long long)H * W, n = plane_of(W);
+  const float* l0p = logits + n * 3 * HW;
+  const int w0 = TW + 2 * k, h0 = TH + 2 * k, pitch = w0 | 1;
+  const float inv_w0 = 1.0f / (float)w0;
+  for (int i = threadIdx.x; i < w0 * h0; i += kThreads) {
+    const int ly = (int)(((float)i + 0.5f) * inv_w0), lx = i - ly * w0;  // exact for i < 2^12
+    const int y = t.y0 - k + ly, x = t.x0 - k + lx;
+    float v = -1.0f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const long long p = (long long)y * W + x;
+      v = softmax_p1_of(l0p[p], l0p[HW + p], l0p[2 * HW + p]);
+    }
+    sp[ly * pitch + lx] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * h0; i += kThreads) {
+    const int ly = i / TW, lx = i % TW;
+    const float* row = sp + ly * pitch + lx;
+    float m = row[0];
+    for (int d = 1; d <= 2 * k; ++d) m = fmaxf(m, row[d]);
+    sr[ly * TW + lx] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TW * TH; i += kThreads) {
+    const int ly = i / TW, lx = i % TW;
+    const int y = t.y0 + ly, x = t.x0 + lx;
+    if (y >= H || x >= W) continue;
+    float d = sr[ly * TW + lx];
+    for (int e = 1; e <= 2 * k; ++e) d = fmaxf(d, sr[(ly + e) * TW + lx]);
+    const float p1 = sp[(ly + k) * pitch + lx + k];
+    const long long p = (long long)y * W + x;
+    const float l0 = l0p[p], l1 = l0p[HW + p], l2 = l0p[2 * HW + p];
+    const float l1d = ((d - p1) > 0.1f) ? l1 + 2.0f : l1;
+    if (!MASK) {
+      float* o = out + n * 3 * HW;
+      o[p] = l0; o[HW + p] = l1d; o[2 * HW + p] = l2;
+    } else {
+      bool on = (l1d > l0) && (l1d >= l2);
+      if (on && score_thr > 0.0f) {
+        const float s = expf(l0 - l1d) + 1.0f + expf(l2 - l1d);
+        on = (1.0f / s) > score_thr;
+      }
+      if (out) out[n * HW + p] = on ? 1.0f : 0.0f;
+      if (out_u8) out_u8[n * HW + p] = on ? 1 : 0;
+    }
   }
 }
 
@@ -788,6 +878,31 @@ int his_post_binary_bilateral_tiled(const float* mask, int N, int H, int W, cons
   return HIS_OK;
 }
 
+int his_post_dilate_logits(const float* logits, int N, int H, int W, int dilation_pixels, float* out, void* stream) {
+  if (!logits || !out) return his_set_error(HIS_ERR_INVALID_ARG, "dilate_logits: null pointer");
+  if (dilation_pixels < 0 || dilation_pixels > kDilMax) return his_set_error(HIS_ERR_UNSUPPORTED, "dilate_logits: dilation_pixels must be in [0,16]");
+  CHECK_PLANES("dilate_logits");
+  if (dilation_pixels == 0) {
+    if (cudaMemcpyAsync(out, logits, (size_t)N * H * W * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ST) != cudaSuccess)
+      return his_set_error(HIS_ERR_LAUNCH, "memcpy failed");
+    return HIS_OK;
+  }
+  dilate_logits_tiled_kernel<false><<<tile_grid(N, H, W), kThreads, 0, ST>>>(logits, H, W, dilation_pixels, 0.0f, out, nullptr);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_dilate_instance_mask(const float* logits, int N, int H, int W, int dilation_pixels, float score_threshold, float* out_f32,
+                                  unsigned char* out_u8, void* stream) {
+  if (!logits || (!out_f32 && !out_u8)) return his_set_error(HIS_ERR_INVALID_ARG, "dilate_instance_mask: null pointer");
+  if (dilation_pixels < 0 || dilation_pixels > kDilMax)
+    return his_set_error(HIS_ERR_UNSUPPORTED, "dilate_instance_mask: dilation_pixels must be in [0,16]");
+  CHECK_PLANES("dilate_instance_mask");
+  dilate_logits_tiled_kernel<true><<<tile_grid(N, H, W), kThreads, 0, ST>>>(logits, H, W, dilation_pixels, score_threshold, out_f32, out_u8);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
 int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es_threshold, float es_strength, const float* gauss, int k,
                                 int iterations, float threshold, float* out, void* stream) {
   if (!mask || !gauss || !out) return his_set_error(HIS_ERR_INVALID_ARG, "mask_cleanup_fused: null pointer");
@@ -798,9 +913,11 @@ int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es
   static const bool wide = [] { const char* e = getenv("HIS_POST_WIDE"); return !e || atoi(e) != 0; }();
   if (wide && iterations <= 2 && (k == 3 || k == 5 || k == 7) && (long long)N * ((W + TW2 - 1) / TW2) < (1LL << 31)) {
     const dim3 grid((unsigned)((long long)N * ((W + TW2 - 1) / TW2)), (H + TH2 - 1) / TH2, 1);
-    if (k == 7) mask_cleanup_wide_kernel<7><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, iterations, threshold, out);
-    else if (k == 5) mask_cleanup_wide_kernel<5><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, iterations, threshold, out);
-    else mask_cleanup_wide_kernel<3><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, iterations, threshold, out);
+#define HIS_WIDE(K_, I_) mask_cleanup_wide_kernel<K_, I_><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out)
+    if (k == 7) { if (iterations == 2) HIS_WIDE(7, 2); else HIS_WIDE(7, 1); }
+    else if (k == 5) { if (iterations == 2) HIS_WIDE(5, 2); else HIS_WIDE(5, 1); }
+    else { if (iterations == 2) HIS_WIDE(3, 2); else HIS_WIDE(3, 1); }
+#undef HIS_WIDE
   } else {
     mask_cleanup_fused_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, k, iterations, threshold, out);
   }

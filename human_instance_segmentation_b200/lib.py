@@ -149,6 +149,7 @@ SIGNATURES = {
     # post-processing (csrc/post.cu)
     "his_post_instance_mask": [_P, c_int, c_int, c_int, c_float, _P, _P, _P],
     "his_post_dilate_logits": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "his_post_dilate_instance_mask": [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P],
     "his_post_edge_smooth": [_P, c_int, c_int, c_int, c_float, c_float, _P, _P],
     "his_post_binary_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P, _P, _P, _P],
     "his_post_morph_bilateral": [_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P],

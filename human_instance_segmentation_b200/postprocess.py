@@ -31,19 +31,21 @@ def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
 
 
 @_lib.on_tensor_device
-def instance_masks(logits: torch.Tensor, score_threshold: float = 0.0, as_uint8: bool = False) -> torch.Tensor:
-    """[N,3,H,W] logits -> [N,1,H,W] fp32 in {0,1} (or [N,H,W] uint8)."""
+def instance_masks(logits: torch.Tensor, score_threshold: float = 0.0, as_uint8: bool = False, dilation_pixels: int = 0) -> torch.Tensor:
+    """[N,3,H,W] logits -> [N,1,H,W] fp32 in {0,1} (or [N,H,W] uint8).  ``dilation_pixels > 0`` applies MaskDilationModule to
+    the logits first, inside the same kernel (== ``instance_masks(MaskDilationModule(d)(logits))`` bit for bit, without the
+    dilated tensor going through HBM)."""
     x = _cuda_f32(logits, "instance_masks")
     n, c, h, w = x.shape
     if c != 3:
         raise ValueError("instance_masks expects 3-class logits [N,3,H,W]")
     L = _lib.load()
-    if as_uint8:
-        out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
-        _lib.check(L.his_post_instance_mask(x.data_ptr(), n, h, w, float(score_threshold), None, out.data_ptr(), _stream(x)))
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device) if as_uint8 else torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+    ptrs = (None, out.data_ptr()) if as_uint8 else (out.data_ptr(), None)
+    if dilation_pixels > 0:
+        _lib.check(L.his_post_dilate_instance_mask(x.data_ptr(), n, h, w, int(dilation_pixels), float(score_threshold), *ptrs, _stream(x)))
     else:
-        out = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
-        _lib.check(L.his_post_instance_mask(x.data_ptr(), n, h, w, float(score_threshold), out.data_ptr(), None, _stream(x)))
+        _lib.check(L.his_post_instance_mask(x.data_ptr(), n, h, w, float(score_threshold), *ptrs, _stream(x)))
     return out
 
 

@@ -240,6 +240,8 @@ int his_memset_async(void* ptr, int value, long long bytes, void* stream);
  *   AND (max softmax prob > score_threshold) (test_hierarchical_instance_peopleseg_onnx.py:250-262; <= 0 disables);
  *   writes fp32 [N,1,H,W] and/or u8 [N,H,W].
  * dilate_logits: MaskDilationModule (export_hierarchical_instance_peopleseg_onnx.py:85-141).
+ * dilate_instance_mask: instance_mask(dilate_logits(logits)) in one pass -- the dilated logits are never written (the exported
+ *   graph ends in the dilation module and the caller takes the argmax: test_hierarchical_instance_peopleseg_onnx.py:250-262).
  * edge_smooth: BinaryMaskEdgeSmoothing (hed/edge_smoothing.py:10-90), N = B*C planes.
  * binary_bilateral: BinaryMaskBilateralFilter (hed/bilateral_filter.py:299-406); gauss = device fp32 [k*k] (normalised).
  * morph_bilateral: MorphologicalBilateralFilter (hed/bilateral_filter.py:409-501); kernel2d = device fp32 [k*k].
@@ -248,6 +250,8 @@ int his_memset_async(void* ptr, int value, long long bytes, void* stream);
 int his_post_instance_mask(const float* logits, int N, int H, int W, float score_threshold, float* out_f32,
                            unsigned char* out_u8, void* stream);
 int his_post_dilate_logits(const float* logits, int N, int H, int W, int dilation_pixels, float* out, void* stream);
+int his_post_dilate_instance_mask(const float* logits, int N, int H, int W, int dilation_pixels, float score_threshold,
+                                  float* out_f32, unsigned char* out_u8, void* stream);
 int his_post_edge_smooth(const float* mask, int N, int H, int W, float threshold, float blur_strength, float* out, void* stream);
 int his_post_binary_bilateral(const float* mask, int N, int H, int W, const float* gauss, int k, int iterations,
                               float threshold, float* ws0, float* ws1, float* out, void* stream);

@@ -85,6 +85,27 @@ def test_mask_dilation_matches_reference_golden():
     assert torch.equal(pp.MaskDilationModule(0)(logits), logits)
 
 
+@pytest.mark.parametrize("d", [1, 2, 5, 16])
+def test_fused_dilation_instance_mask_equals_the_two_steps(d):
+    """instance_masks(..., dilation_pixels=d) == instance_masks(MaskDilationModule(d)(logits)) bit for bit (ROI-sized planes,
+    ragged planes with partial tiles, score threshold on / off, fp32 and u8 outputs), and the tiled dilation equals a
+    max_pool2d restatement of the module on the same softmax values."""
+    g = torch.Generator().manual_seed(7 + d)
+    for shape in ((5, 3, 128, 96), (2, 3, 37, 70), (1, 3, 3, 2)):
+        lg = (torch.randn(shape[0], 3, max(shape[2] // 8, 1), max(shape[3] // 8, 1), generator=g) * 2)
+        lg = torch.nn.functional.interpolate(lg, size=shape[2:], mode="bilinear").contiguous().cuda()
+        dl = pp.MaskDilationModule(d)(lg)
+        for thr in (0.0, 0.5):
+            assert torch.equal(pp.instance_masks(lg, thr, dilation_pixels=d), pp.instance_masks(dl, thr))
+            assert torch.equal(pp.instance_masks(lg, thr, as_uint8=True, dilation_pixels=d), pp.instance_masks(dl, thr, as_uint8=True))
+        # the module restated with torch ops on the GPU's own fp32 softmax: identical up to ties of (dilated - p) with 0.1
+        p1 = torch.softmax(lg, 1)[:, 1:2]
+        grow = (torch.nn.functional.max_pool2d(p1, 2 * d + 1, 1, d) - p1)
+        want = lg.clone(); want[:, 1:2] += 2.0 * (grow > 0.1).float()
+        bad = (dl != want)
+        assert int(bad.sum()) == 0 or float((grow - 0.1).abs()[bad[:, 1:2]].max()) < 1e-6
+
+
 def _frac_bad(got, want):
     return float((got.float().cpu() != want).float().mean())
 
