@@ -97,4 +97,16 @@ __device__ __forceinline__ void his_st1(__half* p, int lo, float v) {
   *p = h;
   if (lo) p[lo] = __float2half_rn(v - __half2float(h));
 }
+// One-time work per (call site, device): function attributes such as the dynamic shared memory opt-in are per device.
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 #endif

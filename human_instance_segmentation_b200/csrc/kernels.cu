@@ -1536,17 +1536,6 @@ int his_set_error(int code, const char* msg) {
 
 #define ST ((cudaStream_t)stream)
 
-// One-time work per (call site, device): function attributes such as the dynamic shared memory opt-in are per device.
-struct PerDeviceOnce {
-  bool done[64] = {false};
-  bool first() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-    if (done[dev]) return false;
-    done[dev] = true;
-    return true;
-  }
-};
 
 extern "C" {
 

@@ -496,109 +496,134 @@ __global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const f
 
 // ---------------------------------------------------------------------------------------------- fused clean-up chain, wide form
 // Same chain and the same arithmetic per pixel as mask_cleanup_fused_kernel (which stays as the general form and as the checker
-// of this one), laid out for instruction issue instead of simplicity -- the first form spends 3/4 of its issue slots on scalar
-// shared-memory loads, weight loads and index arithmetic (ncu: 28 % FMA-pipe active at 59 % issue utilisation):
-//  * 64 x 32 tile: the stage-1 halo overhead drops from 1.41x to 1.30x and 18 x 38 strips fill three rounds of 256 threads;
+// of this one), laid out for the two limits ncu showed on the first form -- instruction issue (3/4 of the slots were scalar
+// shared-memory loads, weight loads and index arithmetic: 28 % FMA-pipe active) and, once those were gone, shared-memory
+// wavefronts (every output row re-read its K window rows):
+//  * 64 x 32 tile: the stage-1 halo overhead drops from 1.41x to 1.30x;
 //  * every stage keeps ITS region at origin (0,0) of its plane, so the strip of 4 outputs at columns [4j, 4j+4) reads input
-//    columns [4j, 4j+K+3) -- 16-byte aligned: 3 LDS.128 per window row (K = 7) instead of 10 scalar loads, weights as two
-//    LDS.128 per row from a [K][8] table instead of K scalar loads; pitch 84 = 20 mod 32 makes the column-major strip order
-//    (8 consecutive rows per quarter warp) and the row-major one (8 consecutive strips) both bank-conflict free;
+//    columns [4j, 4j+K+3) -- 16-byte aligned: 3 LDS.128 per window row (K = 7) instead of 10 scalar loads;
+//  * a thread owns a 4 x 2 block of outputs: the K+1 window rows it loads feed both output rows (8/14 of the wavefronts), and
+//    the two rows share one packed FFMA2 (fma.rn.f32x2, sm_100): (f_row0, f_row1) += v * (w[r][kx], w[r-1][kx]) -- the window
+//    value is the broadcast operand, the weight pair comes from a [K+1][K] table of pairs whose out-of-range halves are 0
+//    (v * 0 added to a non-negative sum changes nothing, so each output still sees exactly its K*K fmaf in ky-major order);
+//  * items are numbered strip-minor: with pitch 84 (two rows = 42 quads = 2 mod 8) any 8 consecutive items of an 18- or
+//    16-strip stage touch 8 different bank quads -> conflict-free LDS.128 / STS.128, and the global stores are row segments;
 //  * squares of the stage-1 output are written once to a third plane (1 FMUL + store per pixel instead of 17.5 FMUL per output);
 //  * edge smoothing of a {0,1} window depends only on (centre, #edge neighbours, #corner neighbours): a 50-entry table per CTA,
 //    computed by edge_smooth_at itself on synthetic 3x3 windows (all its sums are exact on such inputs, so the arrangement of
 //    the neighbours cannot matter), replaces 18 FMA + sigmoid per pixel.  A window holding anything but 0 / 1 (checked while
 //    loading, block-wide vote) takes the general per-pixel path.
-// The accumulation order per output (ky major, kx minor, fmaf) and the epilogue are those of bilateral4: results are
-// bit-identical (tests/test_gpu_post.py compares the two forms on random and soft masks).
+// Results are bit-identical to the general form (tests/test_gpu_post.py compares against the unfused per-pixel kernels on
+// random, blob and soft masks).
 constexpr int TW2 = 64, TH2 = 32, kHalo2 = 7;
 constexpr int kPitch2 = 84;                                   // >= 4 * ceil((TW2 + 2*kHalo2 - 2) / 4) + 8, and = 20 mod 32
 constexpr int kPlane2 = (TH2 + 2 * kHalo2) * kPitch2;         // 46 rows
 
 struct Region {
-  int rw, rh;      // extent of the stage's output region
+  int rw, rh;      // extent of the stage's output region (rh even)
   int oy, ox;      // image coordinates of its (0,0)
 };
 
+// (d0, d1) += a * (b0, b1): one FFMA2, `a` as the broadcast operand
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a, float b0, float b1) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rc));
+}
+
+__device__ __forceinline__ void load_quads(const float* __restrict__ p, float* __restrict__ v, int n) {
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+    if (l < n) { const float4 t = reinterpret_cast<const float4*>(p)[l]; v[4 * l] = t.x; v[4 * l + 1] = t.y; v[4 * l + 2] = t.z; v[4 * l + 3] = t.w; }
+}
+
+// wp: [K+1][8] pairs (w[r][kx], w[r-1][kx]) as float2, rows outside 0..K-1 are 0
 template <int K, bool BIN, bool LAST>
 __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, const float* __restrict__ src2, float* __restrict__ dst,
-                                                 float* __restrict__ dst2, const float* __restrict__ wk, const Region g, int H, int W, float thr,
+                                                 float* __restrict__ dst2, const float* __restrict__ wp, const Region g, int H, int W, float thr,
                                                  float* __restrict__ out_plane, bool vec_store) {
   constexpr int R = K / 2, NL = (K + 3 + 3) / 4;              // float4 loads per window row
   const int S = (g.rw + 3) >> 2;
-  for (int i = threadIdx.x; i < S * g.rh; i += kThreads) {
-    int sx, ry;
-    if (LAST) { ry = i / S; sx = i - ry * S; }                // rows of strips: coalesced global stores
-    else { sx = i / g.rh; ry = i - sx * g.rh; }               // columns of strips: conflict-free for any strip count
-    const int c0 = sx * 4, y = g.oy + ry;
-    if (y < 0 || y >= H) {                                    // outside the image: zero padding of the next stage
+  for (int i = threadIdx.x; i < S * (g.rh >> 1); i += kThreads) {
+    const int rp = i / S, sx = i - rp * S;
+    const int c0 = sx * 4, ry = 2 * rp, y = g.oy + ry;
+    const bool in0 = y >= 0 && y < H, in1 = y + 1 >= 0 && y + 1 < H;
+    if (!in0 && !in1) {                                       // outside the image: zero padding of the next stage
       if (!LAST) {
-        *reinterpret_cast<float4*>(dst + ry * kPitch2 + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(dst2 + ry * kPitch2 + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          *reinterpret_cast<float4*>(dst + (ry + o) * kPitch2 + c0) = z;
+          *reinterpret_cast<float4*>(dst2 + (ry + o) * kPitch2 + c0) = z;
+        }
       }
       continue;
     }
-    float f[4] = {0.0f, 0.0f, 0.0f, 0.0f}, f2[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ctr[4];
+    float f[4][2], f2[4][2];
 #pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      float v[4 * NL], q[4 * NL], wv[8];
-      const float4* row = reinterpret_cast<const float4*>(src + (ry + ky) * kPitch2 + c0);
+    for (int j = 0; j < 4; ++j) { f[j][0] = f[j][1] = 0.0f; f2[j][0] = f2[j][1] = 0.0f; }
+#pragma unroll 1
+    for (int r = 0; r <= K; ++r) {
+      float v[12], q[12], w[16];
+      load_quads(src + (ry + r) * kPitch2 + c0, v, NL);
+      if (!BIN) load_quads(src2 + (ry + r) * kPitch2 + c0, q, NL);
 #pragma unroll
-      for (int l = 0; l < NL; ++l) { const float4 t = row[l]; v[4 * l] = t.x; v[4 * l + 1] = t.y; v[4 * l + 2] = t.z; v[4 * l + 3] = t.w; }
-      if (!BIN) {
-        const float4* row2 = reinterpret_cast<const float4*>(src2 + (ry + ky) * kPitch2 + c0);
-#pragma unroll
-        for (int l = 0; l < NL; ++l) { const float4 t = row2[l]; q[4 * l] = t.x; q[4 * l + 1] = t.y; q[4 * l + 2] = t.z; q[4 * l + 3] = t.w; }
-      }
-      {
-        const float4 a = *reinterpret_cast<const float4*>(wk + ky * 8), b = *reinterpret_cast<const float4*>(wk + ky * 8 + 4);
-        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
+      for (int l = 0; l < (2 * K + 3) / 4; ++l) {
+        const float4 t = reinterpret_cast<const float4*>(wp + r * 16)[l];
+        w[4 * l] = t.x; w[4 * l + 1] = t.y; w[4 * l + 2] = t.z; w[4 * l + 3] = t.w;
       }
 #pragma unroll
       for (int kx = 0; kx < K; ++kx)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[j] = fmaf(v[kx + j], wv[kx], f[j]);
-          if (!BIN) f2[j] = fmaf(q[kx + j], wv[kx], f2[j]);
+          ffma2_bcast(f[j][0], f[j][1], v[kx + j], w[2 * kx], w[2 * kx + 1]);
+          if (!BIN) ffma2_bcast(f2[j][0], f2[j][1], q[kx + j], w[2 * kx], w[2 * kx + 1]);
         }
-      if (ky == R) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ctr[j] = v[R + j];
-      }
-    }
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float qq = BIN ? f[j] : f2[j];
-      const float var = fmaxf(__fsub_rn(qq, __fmul_rn(f[j], f[j])), 0.0f);
-      const float ew = expf(__fmul_rn(-var, 10.0f));
-      o[j] = __fadd_rn(__fmul_rn(ew, f[j]), __fmul_rn(__fsub_rn(1.0f, ew), ctr[j]));
     }
     const int x = g.ox + c0;
-    if (!LAST) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = (x + j >= 0 && x + j < W) ? o[j] : 0.0f;
-      *reinterpret_cast<float4*>(dst + ry * kPitch2 + c0) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(dst2 + ry * kPitch2 + c0) =
-          make_float4(__fmul_rn(o[0], o[0]), __fmul_rn(o[1], o[1]), __fmul_rn(o[2], o[2]), __fmul_rn(o[3], o[3]));
-    } else {
-      float* orow = out_plane + (long long)y * W + x;
+    for (int o = 0; o < 2; ++o) {
+      float res[4], ctr[4];
+      // centre values re-read here (two quads) rather than carried through the window loop in 8 registers
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = o[j] > thr ? 1.0f : 0.0f;
-      if (vec_store && x + 3 < W) *reinterpret_cast<float4*>(orow) = make_float4(o[0], o[1], o[2], o[3]);
-      else {
+      for (int j = 0; j < 4; ++j) ctr[j] = src[(ry + o + R) * kPitch2 + c0 + R + j];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (x + j < W) orow[j] = o[j];
+      for (int j = 0; j < 4; ++j) {
+        const float fj = f[j][o], qq = BIN ? fj : f2[j][o];
+        const float var = fmaxf(__fsub_rn(qq, __fmul_rn(fj, fj)), 0.0f);
+        const float ew = expf(__fmul_rn(-var, 10.0f));
+        res[j] = __fadd_rn(__fmul_rn(ew, fj), __fmul_rn(__fsub_rn(1.0f, ew), ctr[j]));
+      }
+      const bool yin = o == 0 ? in0 : in1;
+      if (!LAST) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = (yin && x + j >= 0 && x + j < W) ? res[j] : 0.0f;
+        *reinterpret_cast<float4*>(dst + (ry + o) * kPitch2 + c0) = make_float4(res[0], res[1], res[2], res[3]);
+        *reinterpret_cast<float4*>(dst2 + (ry + o) * kPitch2 + c0) =
+            make_float4(__fmul_rn(res[0], res[0]), __fmul_rn(res[1], res[1]), __fmul_rn(res[2], res[2]), __fmul_rn(res[3], res[3]));
+      } else if (yin) {
+        float* orow = out_plane + (long long)(y + o) * W + x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = res[j] > thr ? 1.0f : 0.0f;
+        if (vec_store && x + 3 < W) *reinterpret_cast<float4*>(orow) = make_float4(res[0], res[1], res[2], res[3]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (x + j < W) orow[j] = res[j];
+        }
       }
     }
   }
 }
 
-// 3 CTAs per SM: 80 registers; 4 (64 registers, spills) measured 9 % slower
+// 3 CTAs per SM (80 registers); 4 (64 registers, spills) measured 9 % slower on the one-row form
 template <int K, int ITS>
-__global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
+__global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
                                                                         const float* __restrict__ gauss, float thr, float* __restrict__ out) {
   __shared__ __align__(16) float pa[kPlane2], pb[kPlane2], pc[kPlane2];
-  __shared__ __align__(16) float wk[K * 8];
+  __shared__ __align__(16) float wp[(K + 1) * 16];
   __shared__ float tab[64];
   constexpr int R = K / 2;
   constexpr int halo = 1 + ITS * R;                           // <= kHalo2 (host checks)
@@ -642,7 +667,10 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
       }
     }
   }
-  for (int i = threadIdx.x; i < K * 8; i += kThreads) wk[i] = (i & 7) < K ? gauss[(i >> 3) * K + (i & 7)] : 0.0f;
+  for (int i = threadIdx.x; i < (K + 1) * 16; i += kThreads) {                 // pairs (w[r][kx], w[r-1][kx])
+    const int r = i >> 4, kx = (i & 15) >> 1, rr = r - (i & 1);
+    wp[i] = (kx < K && rr >= 0 && rr < K) ? gauss[rr * K + kx] : 0.0f;
+  }
   if (threadIdx.x < 50) {                                     // edge-smoothing table: (centre, #edge, #corner neighbours) -> {0,1}
     const int c = threadIdx.x / 25, ne = (threadIdx.x / 5) % 5, nc = threadIdx.x % 5;
     float* w3 = pc + threadIdx.x * 9;                         // pc is not a plane yet
@@ -654,33 +682,32 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
   const int all_bin = __syncthreads_and(bin ? 1 : 0);
   // stage 0: edge smoothing, region shrunk by 1
   {
-    const int rw = W0 - 2, rh = H0 - 2, oy = y0 - halo + 1, ox = x0 - halo + 1;
+    constexpr int rw = W0 - 2, rh = H0 - 2;
+    const int oy = y0 - halo + 1, ox = x0 - halo + 1;
     if (all_bin) {
-      const int S = (rw + 3) >> 2;
-      for (int i = threadIdx.x; i < S * rh; i += kThreads) {
-        const int sx = i / rh, ry = i - sx * rh, c0 = sx * 4, y = oy + ry;
-        float up[12], mid[12], dn[12];
+      constexpr int S = (rw + 3) >> 2, O = D & 3;
+      for (int i = threadIdx.x; i < S * (rh >> 1); i += kThreads) {
+        const int rp = i / S, sx = i - rp * S, c0 = sx * 4, ry = 2 * rp;
+        float w4[4][12];
         const float* base = pa + ry * kPitch2 + c0 + (D & ~3);
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-          const float4 a = reinterpret_cast<const float4*>(base)[l], b = reinterpret_cast<const float4*>(base + kPitch2)[l],
-                       d = reinterpret_cast<const float4*>(base + 2 * kPitch2)[l];
-          up[4 * l] = a.x; up[4 * l + 1] = a.y; up[4 * l + 2] = a.z; up[4 * l + 3] = a.w;
-          mid[4 * l] = b.x; mid[4 * l + 1] = b.y; mid[4 * l + 2] = b.z; mid[4 * l + 3] = b.w;
-          dn[4 * l] = d.x; dn[4 * l + 1] = d.y; dn[4 * l + 2] = d.z; dn[4 * l + 3] = d.w;
-        }
-        float cs[6], o[4];
+        for (int r = 0; r < 4; ++r) load_quads(base + r * kPitch2, w4[r], 3);
 #pragma unroll
-        for (int l = 0; l < 6; ++l) cs[l] = up[l + (D & 3)] + dn[l + (D & 3)];
-        const bool yin = y >= 0 && y < H;
+        for (int o = 0; o < 2; ++o) {
+          const int y = oy + ry + o;
+          const bool yin = y >= 0 && y < H;
+          float cs[6], res[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float ne = cs[j + 1] + mid[j + (D & 3)] + mid[j + 2 + (D & 3)], nc = cs[j] + cs[j + 2];
-          const int idx = __float2int_rn(fmaf(mid[j + 1 + (D & 3)], 25.0f, fmaf(ne, 5.0f, nc)));
-          const int x = ox + c0 + j;
-          o[j] = (yin && x >= 0 && x < W) ? tab[idx] : 0.0f;
+          for (int l = 0; l < 6; ++l) cs[l] = w4[o][l + O] + w4[o + 2][l + O];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float ne = cs[j + 1] + w4[o + 1][j + O] + w4[o + 1][j + 2 + O], nc = cs[j] + cs[j + 2];
+            const int idx = __float2int_rn(fmaf(w4[o + 1][j + 1 + O], 25.0f, fmaf(ne, 5.0f, nc)));
+            const int x = ox + c0 + j;
+            res[j] = (yin && x >= 0 && x < W) ? tab[idx] : 0.0f;
+          }
+          *reinterpret_cast<float4*>(pb + (ry + o) * kPitch2 + c0) = make_float4(res[0], res[1], res[2], res[3]);
         }
-        *reinterpret_cast<float4*>(pb + ry * kPitch2 + c0) = make_float4(o[0], o[1], o[2], o[3]);
       }
     } else {
       for (int i = threadIdx.x; i < rw * rh; i += kThreads) {
@@ -691,16 +718,15 @@ __global__ void __launch_bounds__(kThreads, 3) mask_cleanup_wide_kernel(const fl
     }
   }
   __syncthreads();
-  const bool vec_store = vec_io;
   if (ITS == 1) {
     const Region g{TW2, TH2, y0, x0};
-    bilateral_stage2<K, true, true>(pb, nullptr, nullptr, nullptr, wk, g, H, W, thr, out + plane, vec_store);
+    bilateral_stage2<K, true, true>(pb, nullptr, nullptr, nullptr, wp, g, H, W, thr, out + plane, vec_io);
   } else {
     const Region g1{TW2 + 2 * R, TH2 + 2 * R, y0 - R, x0 - R};
-    bilateral_stage2<K, true, false>(pb, nullptr, pa, pc, wk, g1, H, W, thr, nullptr, false);
+    bilateral_stage2<K, true, false>(pb, nullptr, pa, pc, wp, g1, H, W, thr, nullptr, false);
     __syncthreads();
     const Region g2{TW2, TH2, y0, x0};
-    bilateral_stage2<K, false, true>(pa, pc, nullptr, nullptr, wk, g2, H, W, thr, out + plane, vec_store);
+    bilateral_stage2<K, false, true>(pa, pc, nullptr, nullptr, wp, g2, H, W, thr, out + plane, vec_io);
   }
 }
 
@@ -913,7 +939,12 @@ int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es
   static const bool wide = [] { const char* e = getenv("HIS_POST_WIDE"); return !e || atoi(e) != 0; }();
   if (wide && iterations <= 2 && (k == 3 || k == 5 || k == 7) && (long long)N * ((W + TW2 - 1) / TW2) < (1LL << 31)) {
     const dim3 grid((unsigned)((long long)N * ((W + TW2 - 1) / TW2)), (H + TH2 - 1) / TH2, 1);
-#define HIS_WIDE(K_, I_) mask_cleanup_wide_kernel<K_, I_><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out)
+#define HIS_WIDE(K_, I_)                                                                                                        \
+  do {                                                                                                                          \
+    static PerDeviceOnce carve;                                                                                                 \
+    if (carve.first()) cudaFuncSetAttribute(mask_cleanup_wide_kernel<K_, I_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+    mask_cleanup_wide_kernel<K_, I_><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out);  \
+  } while (0)
     if (k == 7) { if (iterations == 2) HIS_WIDE(7, 2); else HIS_WIDE(7, 1); }
     else if (k == 5) { if (iterations == 2) HIS_WIDE(5, 2); else HIS_WIDE(5, 1); }
     else { if (iterations == 2) HIS_WIDE(3, 2); else HIS_WIDE(3, 1); }
