@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(kThreads) binary_bilateral_smem_kernel(const f
 // Results are bit-identical to the general form (tests/test_gpu_post.py compares against the unfused per-pixel kernels on
 // random, blob and soft masks).
 constexpr int TW2 = 64, TH2 = 32, kHalo2 = 7;
+constexpr int kWideThreads = 256;   // 352 (stage 1's 18 x 19 blocks in one round, 3 CTAs/SM) measured 6 % slower
 constexpr int kPitch2 = 84;                                   // >= 4 * ceil((TW2 + 2*kHalo2 - 2) / 4) + 8, and = 20 mod 32
 constexpr int kPlane2 = (TH2 + 2 * kHalo2) * kPitch2;         // 46 rows
 
@@ -547,7 +548,7 @@ __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, 
                                                  float* __restrict__ out_plane, bool vec_store) {
   constexpr int R = K / 2, NL = (K + 3 + 3) / 4;              // float4 loads per window row
   const int S = (g.rw + 3) >> 2;
-  for (int i = threadIdx.x; i < S * (g.rh >> 1); i += kThreads) {
+  for (int i = threadIdx.x; i < S * (g.rh >> 1); i += kWideThreads) {
     const int rp = i / S, sx = i - rp * S;
     const int c0 = sx * 4, ry = 2 * rp, y = g.oy + ry;
     const bool in0 = y >= 0 && y < H, in1 = y + 1 >= 0 && y + 1 < H;
@@ -618,9 +619,9 @@ __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, 
   }
 }
 
-// 3 CTAs per SM (80 registers); 4 (64 registers, spills) measured 9 % slower on the one-row form
+// 4 CTAs per SM: the window-row loop stays rolled (55 registers; unrolled it wants 128 and spills at 80)
 template <int K, int ITS>
-__global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
+__global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
                                                                         const float* __restrict__ gauss, float thr, float* __restrict__ out) {
   __shared__ __align__(16) float pa[kPlane2], pb[kPlane2], pc[kPlane2];
   __shared__ __align__(16) float wp[(K + 1) * 16];
@@ -641,8 +642,8 @@ __global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const fl
   if (vec_io) {
     constexpr int G = 20;                                     // float4 groups per window row
 #pragma unroll
-    for (int u = 0; u < (46 * G + kThreads - 1) / kThreads; ++u) {
-      const int i = threadIdx.x + u * kThreads;
+    for (int u = 0; u < (46 * G + kWideThreads - 1) / kWideThreads; ++u) {
+      const int i = threadIdx.x + u * kWideThreads;
       const int r = i / G, q = i - r * G;
       const int y = y0 - halo + r, x = x0 - 8 + 4 * q;
       if (r < H0) {
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const fl
     }
     if (threadIdx.x < H0) *reinterpret_cast<float4*>(pa + threadIdx.x * kPitch2 + 80) = make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
-    for (int r = warp; r < H0; r += kThreads / 32) {
+    for (int r = warp; r < H0; r += kWideThreads / 32) {
       const int y = y0 - halo + r;
       const bool yin = y >= 0 && y < H;
       const float* grow = in + plane + (long long)y * W;
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const fl
       }
     }
   }
-  for (int i = threadIdx.x; i < (K + 1) * 16; i += kThreads) {                 // pairs (w[r][kx], w[r-1][kx])
+  for (int i = threadIdx.x; i < (K + 1) * 16; i += kWideThreads) {                 // pairs (w[r][kx], w[r-1][kx])
     const int r = i >> 4, kx = (i & 15) >> 1, rr = r - (i & 1);
     wp[i] = (kx < K && rr >= 0 && rr < K) ? gauss[rr * K + kx] : 0.0f;
   }
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const fl
     const int oy = y0 - halo + 1, ox = x0 - halo + 1;
     if (all_bin) {
       constexpr int S = (rw + 3) >> 2, O = D & 3;
-      for (int i = threadIdx.x; i < S * (rh >> 1); i += kThreads) {
+      for (int i = threadIdx.x; i < S * (rh >> 1); i += kWideThreads) {
         const int rp = i / S, sx = i - rp * S, c0 = sx * 4, ry = 2 * rp;
         float w4[4][12];
         const float* base = pa + ry * kPitch2 + c0 + (D & ~3);
@@ -710,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 4) mask_cleanup_wide_kernel(const fl
         }
       }
     } else {
-      for (int i = threadIdx.x; i < rw * rh; i += kThreads) {
+      for (int i = threadIdx.x; i < rw * rh; i += kWideThreads) {
         const int ry = i / rw, c = i - ry * rw, y = oy + ry, x = ox + c;
         const bool in_img = y >= 0 && y < H && x >= 0 && x < W;
         pb[ry * kPitch2 + c] = in_img ? (edge_smooth_at(pa, kPitch2, ry + 1, c + 1 + D, es_strength) > es_thr ? 1.0f : 0.0f) : 0.0f;
@@ -943,7 +944,7 @@ int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es
   do {                                                                                                                          \
     static PerDeviceOnce carve;                                                                                                 \
     if (carve.first()) cudaFuncSetAttribute(mask_cleanup_wide_kernel<K_, I_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-    mask_cleanup_wide_kernel<K_, I_><<<grid, kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out);  \
+    mask_cleanup_wide_kernel<K_, I_><<<grid, kWideThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out);  \
   } while (0)
     if (k == 7) { if (iterations == 2) HIS_WIDE(7, 2); else HIS_WIDE(7, 1); }
     else if (k == 5) { if (iterations == 2) HIS_WIDE(5, 2); else HIS_WIDE(5, 1); }
