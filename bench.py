@@ -262,10 +262,10 @@ def run_post(ctx, steps, warmup, cpu_baseline=True):
     cleanup = pp.MaskCleanup().to(dev)
     out_full = torch.empty_like(full)
 
-    def step(f, r, lg):
+    def step(f, r, lg, out=out_full):
         masks = pp.instance_masks(lg, as_uint8=True, dilation_pixels=1)       # MaskDilationModule(1) + argmax, one pass
         canvas = pp.paste_masks(masks, r, B, H, W)
-        return cleanup(f, out=out_full), canvas
+        return cleanup(f, out=out), canvas
 
     warmup = max(warmup, 3)
     sampler = ClockSampler(ctx.local)
@@ -306,7 +306,23 @@ def run_post(ctx, steps, warmup, cpu_baseline=True):
     e1.record()
     ctx.barrier()
     ms_e2e = e0.elapsed_time(e1) / steps
-    ms, ms_e2e, ms_fused = ctx.max_over_ranks([ms, ms_e2e, ms_fused])
+    # the same step with the full-image masks as bytes on both sides (MaskCleanup's uint8 variant: a quarter of the mask bytes over PCIe)
+    full8_h = full_h.to(torch.uint8).pin_memory()
+    res8_h = torch.empty_like(full8_h).pin_memory()
+
+    def e2e_step_u8():
+        o, c = step(full8_h.to(dev, non_blocking=True), rois_h.to(dev, non_blocking=True), logits_h.to(dev, non_blocking=True), out=None)
+        res8_h.copy_(o, non_blocking=True); canvas_h.copy_(c, non_blocking=True)
+
+    e2e_step_u8(); ctx.barrier()
+    same_u8 = bool(torch.equal(res8_h, res_h.to(torch.uint8)))
+    e0.record()
+    for _ in range(steps):
+        e2e_step_u8()
+    e1.record()
+    ctx.barrier()
+    ms_e2e_u8 = e0.elapsed_time(e1) / steps
+    ms, ms_e2e, ms_fused, ms_e2e_u8 = ctx.max_over_ranks([ms, ms_e2e, ms_fused, ms_e2e_u8])
     if rank != 0:
         return None
     pk = peaks()
@@ -323,7 +339,11 @@ def run_post(ctx, steps, warmup, cpu_baseline=True):
            "e2e": {"value": world * units / (ms_e2e * 1e-3), "unit": "masks/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": full_h.numel() * 4 + logits_h.numel() * 4 + rois_h.numel() * 4,
                    "d2h_bytes_per_step": res_h.numel() * 4 + canvas_h.numel() * 4,
-                   "api": "postprocess.instance_masks(dilation_pixels=1) / paste_masks / MaskCleanup on pinned host tensors"},
+                   "api": "postprocess.instance_masks(dilation_pixels=1) / paste_masks / MaskCleanup on pinned host tensors",
+                   "u8_masks": {"value": world * units / (ms_e2e_u8 * 1e-3), "ms_per_step": ms_e2e_u8,
+                                "h2d_bytes_per_step": full8_h.numel() + logits_h.numel() * 4 + rois_h.numel() * 4,
+                                "d2h_bytes_per_step": res8_h.numel() + canvas_h.numel() * 4, "equal_to_fp32_result": same_u8,
+                                "what": "the same step with the full-image masks as uint8 on the host and on the device (MaskCleanup's byte variant)"}},
            "gpu_launches": 5 * steps, "launches_per_step": 5,
            "roofline": {"bound": "hbm", "kernel": "mask_cleanup_fused_kernel", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / pk["hbm_gbs"], "traffic": measured_traffic("mask_cleanup_fused_kernel:post"), "peak_source": pk["source"],

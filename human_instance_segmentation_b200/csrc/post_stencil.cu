@@ -542,10 +542,10 @@ __device__ __forceinline__ void load_quads(const float* __restrict__ p, float* _
 }
 
 // wp: [K+1][8] pairs (w[r][kx], w[r-1][kx]) as float2, rows outside 0..K-1 are 0
-template <int K, bool BIN, bool LAST>
+template <int K, bool BIN, bool LAST, typename T>
 __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, const float* __restrict__ src2, float* __restrict__ dst,
                                                  float* __restrict__ dst2, const float* __restrict__ wp, const Region g, int H, int W, float thr,
-                                                 float* __restrict__ out_plane, bool vec_store) {
+                                                 T* __restrict__ out_plane, bool vec_store) {
   constexpr int R = K / 2, NL = (K + 3 + 3) / 4;              // float4 loads per window row
   const int S = (g.rw + 3) >> 2;
   for (int i = threadIdx.x; i < S * (g.rh >> 1); i += kWideThreads) {
@@ -606,13 +606,15 @@ __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, 
         *reinterpret_cast<float4*>(dst2 + (ry + o) * kPitch2 + c0) =
             make_float4(__fmul_rn(res[0], res[0]), __fmul_rn(res[1], res[1]), __fmul_rn(res[2], res[2]), __fmul_rn(res[3], res[3]));
       } else if (yin) {
-        float* orow = out_plane + (long long)(y + o) * W + x;
+        T* orow = out_plane + (long long)(y + o) * W + x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) res[j] = res[j] > thr ? 1.0f : 0.0f;
-        if (vec_store && x + 3 < W) *reinterpret_cast<float4*>(orow) = make_float4(res[0], res[1], res[2], res[3]);
-        else {
+        if (vec_store && x + 3 < W) {
+          if (sizeof(T) == 4) *reinterpret_cast<float4*>(orow) = make_float4(res[0], res[1], res[2], res[3]);
+          else *reinterpret_cast<uchar4*>(orow) = make_uchar4((unsigned char)res[0], (unsigned char)res[1], (unsigned char)res[2], (unsigned char)res[3]);
+        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (x + j < W) orow[j] = res[j];
+          for (int j = 0; j < 4; ++j) if (x + j < W) orow[j] = (T)res[j];
         }
       }
     }
@@ -620,9 +622,11 @@ __device__ __forceinline__ void bilateral_stage2(const float* __restrict__ src, 
 }
 
 // 4 CTAs per SM: the window-row loop stays rolled (55 registers; unrolled it wants 128 and spills at 80)
-template <int K, int ITS>
-__global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(const float* __restrict__ in, int H, int W, float es_thr, float es_strength,
-                                                                        const float* __restrict__ gauss, float thr, float* __restrict__ out) {
+// T = float (the reference's mask tensors) or unsigned char (0 / 1 masks: a quarter of the bytes over PCIe and HBM; the values are
+// converted to float while loading, so any other byte value behaves as float(mask) would)
+template <int K, int ITS, typename T>
+__global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(const T* __restrict__ in, int H, int W, float es_thr, float es_strength,
+                                                                        const float* __restrict__ gauss, float thr, T* __restrict__ out) {
   __shared__ __align__(16) float pa[kPlane2], pb[kPlane2], pc[kPlane2];
   __shared__ __align__(16) float wp[(K + 1) * 16];
   __shared__ float tab[64];
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(cons
   const long long plane = (long long)(blockIdx.x / tiles_x) * H * W;
   constexpr int W0 = TW2 + 2 * halo, H0 = TH2 + 2 * halo;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool vec_io = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const bool vec_io = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & (4 * sizeof(T) - 1)) == 0;
   // window, zero padded; plane column p holds image column x0 - 8 + p (80 columns: the window aligned down to 16 bytes, so a
   // row is 20 float4 loads when W % 4 == 0 -- a group of four is then entirely inside or outside the image).  Is every
   // value 0 or 1?
@@ -648,7 +652,13 @@ __global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(cons
       const int y = y0 - halo + r, x = x0 - 8 + 4 * q;
       if (r < H0) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4*>(in + plane + (long long)y * W + x));
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          if (sizeof(T) == 4) v = __ldg(reinterpret_cast<const float4*>(in + plane + (long long)y * W + x));
+          else {
+            const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(in + plane + (long long)y * W + x));
+            v = make_float4((float)t.x, (float)t.y, (float)t.z, (float)t.w);
+          }
+        }
         bin = bin && (v.x == 0.0f || v.x == 1.0f) && (v.y == 0.0f || v.y == 1.0f) && (v.z == 0.0f || v.z == 1.0f) && (v.w == 0.0f || v.w == 1.0f);
         *reinterpret_cast<float4*>(pa + r * kPitch2 + 4 * q) = v;
       }
@@ -658,11 +668,11 @@ __global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(cons
     for (int r = warp; r < H0; r += kWideThreads / 32) {
       const int y = y0 - halo + r;
       const bool yin = y >= 0 && y < H;
-      const float* grow = in + plane + (long long)y * W;
+      const T* grow = in + plane + (long long)y * W;
       for (int c = lane; c < kPitch2; c += 32) {
         const int x = x0 - 8 + c;
         float v = 0.0f;
-        if (yin && c < 80 && x >= 0 && x < W) v = grow[x];
+        if (yin && c < 80 && x >= 0 && x < W) v = (float)grow[x];
         bin = bin && (v == 0.0f || v == 1.0f);
         pa[r * kPitch2 + c] = v;
       }
@@ -721,13 +731,13 @@ __global__ void __launch_bounds__(kWideThreads, 4) mask_cleanup_wide_kernel(cons
   __syncthreads();
   if (ITS == 1) {
     const Region g{TW2, TH2, y0, x0};
-    bilateral_stage2<K, true, true>(pb, nullptr, nullptr, nullptr, wp, g, H, W, thr, out + plane, vec_io);
+    bilateral_stage2<K, true, true, T>(pb, nullptr, nullptr, nullptr, wp, g, H, W, thr, out + plane, vec_io);
   } else {
     const Region g1{TW2 + 2 * R, TH2 + 2 * R, y0 - R, x0 - R};
-    bilateral_stage2<K, true, false>(pb, nullptr, pa, pc, wp, g1, H, W, thr, nullptr, false);
+    bilateral_stage2<K, true, false, T>(pb, nullptr, pa, pc, wp, g1, H, W, thr, nullptr, false);
     __syncthreads();
     const Region g2{TW2, TH2, y0, x0};
-    bilateral_stage2<K, false, true>(pa, pc, nullptr, nullptr, wp, g2, H, W, thr, out + plane, vec_io);
+    bilateral_stage2<K, false, true, T>(pa, pc, nullptr, nullptr, wp, g2, H, W, thr, out + plane, vec_io);
   }
 }
 
@@ -808,6 +818,26 @@ inline dim3 tile_grid(int N, int H, int W) { return dim3((unsigned)((long long)N
 #define CHECK_PLANES(name)                                                                                              \
   if (N == 0 || H == 0 || W == 0) return HIS_OK;                                                                        \
   if ((long long)N * ((W + TW - 1) / TW) >= (1LL << 31)) return his_set_error(HIS_ERR_UNSUPPORTED, name ": too many planes per call")
+
+namespace {
+template <typename T>
+bool launch_cleanup_wide(const T* mask, int N, int H, int W, float es_threshold, float es_strength, const float* gauss, int k, int iterations,
+                         float threshold, T* out, cudaStream_t st) {
+  if (iterations < 1 || iterations > 2 || !(k == 3 || k == 5 || k == 7) || (long long)N * ((W + TW2 - 1) / TW2) >= (1LL << 31)) return false;
+  const dim3 grid((unsigned)((long long)N * ((W + TW2 - 1) / TW2)), (H + TH2 - 1) / TH2, 1);
+#define HIS_WIDE(K_, I_)                                                                                                            \
+  do {                                                                                                                              \
+    static PerDeviceOnce carve;                                                                                                     \
+    if (carve.first()) cudaFuncSetAttribute(mask_cleanup_wide_kernel<K_, I_, T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+    mask_cleanup_wide_kernel<K_, I_, T><<<grid, kWideThreads, 0, st>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out); \
+  } while (0)
+  if (k == 7) { if (iterations == 2) HIS_WIDE(7, 2); else HIS_WIDE(7, 1); }
+  else if (k == 5) { if (iterations == 2) HIS_WIDE(5, 2); else HIS_WIDE(5, 1); }
+  else { if (iterations == 2) HIS_WIDE(3, 2); else HIS_WIDE(3, 1); }
+#undef HIS_WIDE
+  return true;
+}
+}  // namespace
 
 extern "C" {
 
@@ -936,23 +966,20 @@ int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es
   if (k < 1 || !(k & 1) || k > 9 || iterations < 1 || 1 + iterations * (k / 2) > kMaxR)
     return his_set_error(HIS_ERR_UNSUPPORTED, "mask_cleanup_fused: odd kernel size <= 9 and 1 + iterations*(k/2) <= 8");
   CHECK_PLANES("mask_cleanup_fused");
-  // wide form for the shapes it covers (HIS_POST_WIDE=0 keeps the general form: A/B runs and the bit-identity test)
+  // wide form for the shapes it covers (HIS_POST_WIDE=0 keeps the general form: A/B runs)
   static const bool wide = [] { const char* e = getenv("HIS_POST_WIDE"); return !e || atoi(e) != 0; }();
-  if (wide && iterations <= 2 && (k == 3 || k == 5 || k == 7) && (long long)N * ((W + TW2 - 1) / TW2) < (1LL << 31)) {
-    const dim3 grid((unsigned)((long long)N * ((W + TW2 - 1) / TW2)), (H + TH2 - 1) / TH2, 1);
-#define HIS_WIDE(K_, I_)                                                                                                        \
-  do {                                                                                                                          \
-    static PerDeviceOnce carve;                                                                                                 \
-    if (carve.first()) cudaFuncSetAttribute(mask_cleanup_wide_kernel<K_, I_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-    mask_cleanup_wide_kernel<K_, I_><<<grid, kWideThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, threshold, out);  \
-  } while (0)
-    if (k == 7) { if (iterations == 2) HIS_WIDE(7, 2); else HIS_WIDE(7, 1); }
-    else if (k == 5) { if (iterations == 2) HIS_WIDE(5, 2); else HIS_WIDE(5, 1); }
-    else { if (iterations == 2) HIS_WIDE(3, 2); else HIS_WIDE(3, 1); }
-#undef HIS_WIDE
-  } else {
+  if (!wide || !launch_cleanup_wide<float>(mask, N, H, W, es_threshold, es_strength, gauss, k, iterations, threshold, out, ST))
     mask_cleanup_fused_kernel<<<tile_grid(N, H, W), kThreads, 0, ST>>>(mask, H, W, es_threshold, es_strength, gauss, k, iterations, threshold, out);
-  }
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_post_mask_cleanup_fused_u8(const unsigned char* mask, int N, int H, int W, float es_threshold, float es_strength, const float* gauss,
+                                   int k, int iterations, float threshold, unsigned char* out, void* stream) {
+  if (!mask || !gauss || !out) return his_set_error(HIS_ERR_INVALID_ARG, "mask_cleanup_fused_u8: null pointer");
+  CHECK_PLANES("mask_cleanup_fused_u8");
+  if (!launch_cleanup_wide<unsigned char>(mask, N, H, W, es_threshold, es_strength, gauss, k, iterations, threshold, out, ST))
+    return his_set_error(HIS_ERR_UNSUPPORTED, "mask_cleanup_fused_u8: kernel size 3 / 5 / 7 and 1 or 2 iterations");
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

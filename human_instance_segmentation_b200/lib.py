@@ -167,6 +167,7 @@ SIGNATURES = {
     "his_post_guided_filter": [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
     "his_post_binary_bilateral_tiled": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_float, _P, _P],
     "his_post_mask_cleanup_fused": [_P, c_int, c_int, c_int, c_float, c_float, _P, c_int, c_int, c_float, _P, _P],
+    "his_post_mask_cleanup_fused_u8": [_P, c_int, c_int, c_int, c_float, c_float, _P, c_int, c_int, c_float, _P, _P],
 }
 _RESTYPES = {"his_last_error": c_char_p, "his_conv_gemm_issued_macs": _LL}
 

@@ -319,11 +319,23 @@ class MaskCleanup(nn.Module):
 
     @_lib.on_tensor_device
     def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-        x = _cuda_f32(x, "MaskCleanup")
-        out = torch.empty_like(x) if out is None else out
+        """fp32 masks [B,C,H,W] -> fp32 {0,1}; uint8 masks (0 / 1) -> uint8 through the byte variant of the same kernel (the result
+        is that of the fp32 call on ``x.float()``, with a quarter of the bytes moved)."""
         g = self.gaussian_kernel.to(x.device).contiguous()
-        _run_planes(_lib.load().his_post_mask_cleanup_fused, x, out, float(self.es_threshold), float(self.blur_strength), g.data_ptr(),
-                    self.kernel_size, int(self.num_iterations), float(self.threshold))
+        if x.dtype == torch.uint8:
+            if not x.is_cuda:
+                raise _lib.HisError("MaskCleanup: CUDA tensor required (no CPU fallback)")
+            x = x.contiguous()
+            out = torch.empty_like(x) if out is None else out
+            fn = _lib.load().his_post_mask_cleanup_fused_u8
+        else:
+            x = _cuda_f32(x, "MaskCleanup")
+            out = torch.empty_like(x) if out is None else out
+            fn = _lib.load().his_post_mask_cleanup_fused
+        if out.dtype != x.dtype or out.shape != x.shape or not out.is_contiguous():
+            raise ValueError("MaskCleanup: out must be a contiguous tensor of the input's shape and dtype")
+        _run_planes(fn, x, out, float(self.es_threshold), float(self.blur_strength), g.data_ptr(), self.kernel_size, int(self.num_iterations),
+                    float(self.threshold))
         return out
 
 

@@ -302,6 +302,10 @@ int his_post_binary_bilateral_tiled(const float* mask, int N, int H, int W, cons
                                     float* out, void* stream);
 int his_post_mask_cleanup_fused(const float* mask, int N, int H, int W, float es_threshold, float es_strength, const float* gauss, int k,
                                 int iterations, float threshold, float* out, void* stream);
+/* The same chain on unsigned char masks (0 / 1 in, 0 / 1 out; a byte is converted to float while loading, so the result is that of
+ * the fp32 call on float(mask)): a quarter of the bytes over PCIe and HBM.  kernel size 3 / 5 / 7, 1 or 2 iterations. */
+int his_post_mask_cleanup_fused_u8(const unsigned char* mask, int N, int H, int W, float es_threshold, float es_strength,
+                                   const float* gauss, int k, int iterations, float threshold, unsigned char* out, void* stream);
 
 #ifdef __cplusplus
 }

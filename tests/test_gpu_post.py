@@ -200,6 +200,13 @@ def test_wide_mask_cleanup_is_bit_identical_to_the_unfused_chain(k, its):
     buf = torch.empty(m.numel() + 1, device="cuda")
     out = buf[1:].view_as(m)
     assert torch.equal(fused(m, out=out), bf(es(m)))
+    # byte masks: same kernel, 0 / 1 in and out (aligned and odd widths, a view at an odd byte offset)
+    for shape in ((3, 1, 96, 128), (2, 1, 67, 131)):
+        m = (torch.rand(*shape, generator=g) > 0.5)
+        assert torch.equal(fused(m.to(torch.uint8).cuda()), bf(es(m.float().cuda())).to(torch.uint8))
+    m = (torch.rand(2, 1, 64, 128, generator=g) > 0.5)
+    buf8 = torch.empty(m.numel() + 1, dtype=torch.uint8, device="cuda")
+    assert torch.equal(fused(m.to(torch.uint8).cuda(), out=buf8[1:].view(2, 1, 64, 128)), bf(es(m.float().cuda())).to(torch.uint8))
     # other thresholds / strength
     f2 = pp.MaskCleanup(0.4, 2.0, k, 1.2, 0.45, its).cuda()
     m = blob_masks(4, 2, 90, 150).cuda()
