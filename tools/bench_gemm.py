@@ -20,6 +20,9 @@ SHAPES = [
     ("unet dec4 conv1 32->16 k3 480x640", 16, 480, 640, 32, 16, 3, RES_NONE, False),
     ("unet dec3 conv1 96->32 k3 240x320", 32, 240, 320, 96, 32, 3, RES_NONE, False),
     ("unet dec3 conv2 32->32 k3 240x320", 32, 240, 320, 32, 32, 3, RES_NONE, False),
+    ("unet tail1 packed 32->64 k3 240x320", 64, 240, 320, 32, 64, 3, RES_NONE, False),
+    ("unet tail2 packed 64->64 k3 240x320", 64, 240, 320, 64, 64, 3, RES_NONE, False),
+    ("unet probe 32->32 k3 240x320 n64", 64, 240, 320, 32, 32, 3, RES_NONE, False),
     ("unet dec2 conv1 152->64 k3 120x160", 64, 120, 160, 152, 64, 3, RES_NONE, False),
     ("unet expand 16->96 k1 240x320", 32, 240, 320, 16, 96, 1, RES_NONE, False),
     ("unet expand 24->144 k1 120x160", 64, 120, 160, 24, 144, 1, RES_NONE, False),

@@ -39,6 +39,6 @@ if os.path.exists(lp):
     out["depthwise:b0"] = traffic(lp, "depthwise")
     out["roi_align_rows_kernel:b0"] = traffic(lp, "roi_align")
 if os.path.exists(pp):
-    out["mask_cleanup_fused_kernel:post"] = traffic(pp, "mask_cleanup")
+    out["mask_cleanup_wide_kernel:post"] = traffic(pp, "mask_cleanup")
 json.dump(out, open(os.path.join(DST, "r2_traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))

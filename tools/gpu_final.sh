@@ -15,9 +15,9 @@ L=$(python -c "import json; print(json.load(open('gpurun_out/${P}_bench_b0.json'
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s $((3*L)) -c $L --csv --log-file gpurun_out/${P}_launches.csv python bench.py --steps 1 --warmup 3 --quick --no-cpu-baseline --no-graph --no-pipeline > gpurun_out/${P}_ncu_launches.log 2>&1
 tail -1 gpurun_out/${P}_ncu_launches.log | cut -c1-200
 timeout 300 python bench.py --workload post --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:mask_cleanup -s 3 -c 2 --csv --log-file gpurun_out/${P}_post_launches.csv python bench.py --workload post --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${P}_ncu_post.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 12 -c 8 --csv --log-file gpurun_out/${P}_post_launches.csv python bench.py --workload post --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${P}_ncu_post.log 2>&1
 timeout 300 python tools/prof_set.py > gpurun_out/${P}_prof_set_plain.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"depthwise|conv_gemm|mask_cleanup|roi_align" -c 20 -o gpurun_out/${P}_prof_set python tools/prof_set.py > gpurun_out/${P}_prof_set_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"depthwise|conv_gemm|mask_cleanup|roi_align|dilate_logits|paste_kernel" -c 24 -o gpurun_out/${P}_prof_set python tools/prof_set.py > gpurun_out/${P}_prof_set_ncu.log 2>&1
 tail -2 gpurun_out/${P}_prof_set_ncu.log
 # the report itself can exceed what gpurun copies back (64 MiB for the whole directory): keep its raw page as CSV, drop the file when large
 ncu -i gpurun_out/${P}_prof_set.ncu-rep --page raw --csv > gpurun_out/${P}_prof_set_raw.csv 2> /dev/null

@@ -77,5 +77,8 @@ L.check(lib.his_roi_align_fused(two.data_ptr(), 2, 480.0, 640.0, 1, msk.ptr, msk
 from human_instance_segmentation_b200 import postprocess as pp  # noqa: E402
 masks = (torch.rand(64, 1, 480, 640, device=dev) > 0.5).float()
 pp.MaskCleanup().to(dev)(masks)
+# ROI chain of config 5: dilation + argmax in one pass, paste-back (640 ROIs of 64 images)
+lg = torch.nn.functional.interpolate(torch.randn(640, 3, 16, 12, device=dev) * 2, size=(128, 96), mode="bilinear").contiguous()
+pp.paste_masks(pp.instance_masks(lg, as_uint8=True, dilation_pixels=1), rois, 64, 480, 640)
 torch.cuda.synchronize()
 print("ok")
