@@ -693,48 +693,119 @@ __global__ void __launch_bounds__(kDw2Threads) depthwise_tiled_kernel(const DwPa
   }
 }
 
-// Split-fp16 ("strict" precision) depthwise conv: same CTA geometry and pooling-partial layout as the tiled kernel above, operands read
-// straight from global memory as hi + lo pairs, fp32 filter taps, fp32 pooling of the exact (unrounded) outputs.  Precision first:
-// this path is 2-3x slower than the staged kernel and only runs when the model is in strict mode.
+// Split-fp16 ("strict" precision) depthwise conv: the tiled kernel's CTA geometry, pooling-partial layout and FFMA2 inner loop, with
+// the window staged as fp32 (hi + lo summed once per element while staging: 144-byte pixel pitch = the low halves of the four
+// 8-channel vectors, their high halves, 16 B of padding), fp32 filter taps and fp32 pooling of the exact (unrounded) outputs.
+// Zero padding is staged as 0: fmaf(0, w, acc) == acc, so the result equals the tap-skipping form bit for bit.
+constexpr int kDwsPitch = 144;
+template <int K, int S, int XPT>
+struct DwsCfg {
+  using B = Dw2Cfg<K, S, XPT>;
+  static constexpr int kInBytes = B::IW * B::IH * kDwsPitch;
+  static constexpr int kWBytes = K * K * kDw2Cb * 4;
+  static constexpr int kSmem = kInBytes + kWBytes + kDw2Threads * 8 * 4;
+};
+
 template <int K, int S, int XPT, int ACT>
 __global__ void __launch_bounds__(kDw2Threads) depthwise_split_kernel(const DwParams p, int tiles_x, const float* __restrict__ w32, int in_lo, int out_lo) {
   using Cfg = Dw2Cfg<K, S, XPT>;
-  __shared__ float s_pool[kDw2Threads * 8];
+  extern __shared__ __align__(16) unsigned char dw_smem[];
+  unsigned char* s_in = dw_smem;
+  float* s_w = reinterpret_cast<float*>(dw_smem + DwsCfg<K, S, XPT>::kInBytes);
+  float* s_pool = reinterpret_cast<float*>(dw_smem + DwsCfg<K, S, XPT>::kInBytes + DwsCfg<K, S, XPT>::kWBytes);
   const int n = blockIdx.z, cb0 = blockIdx.y * kDw2Cb;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
   const int oy0 = ty * Cfg::TOH, ox0 = tx * Cfg::TOW;
+  const int iy0 = oy0 * S - p.pad, ix0 = ox0 * S - p.pad;
   const int nvec = min(4, (p.C - cb0) >> 3);
+  const __half* inb = p.in + (long long)n * p.H * p.W * p.in_cs + cb0;
+  // ---- stage the window as fp32: four (pixel, vector) elements per thread and pass, their eight 16-byte loads issued together
+  constexpr int kElems = Cfg::IW * Cfg::IH * 4;
+  for (int base = threadIdx.x; base < kElems; base += 4 * kDw2Threads) {
+    uint4 hi[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * kDw2Threads;
+      const int v = i & 3, px = i >> 2;
+      const int ly = px / Cfg::IW, lx = px - ly * Cfg::IW;
+      const int iy = iy0 + ly, ix = ix0 + lx;
+      hi[u] = make_uint4(0u, 0u, 0u, 0u); lo[u] = hi[u];
+      if (i < kElems && v < nvec && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+        const __half* src = inb + ((long long)iy * p.W + ix) * p.in_cs + v * 8;
+        hi[u] = __ldg(reinterpret_cast<const uint4*>(src));
+        lo[u] = __ldg(reinterpret_cast<const uint4*>(src + in_lo));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * kDw2Threads;
+      if (i >= kElems) continue;
+      const int v = i & 3, px = i >> 2;
+      const __half2* hh = reinterpret_cast<const __half2*>(&hi[u]);
+      const __half2* lh = reinterpret_cast<const __half2*>(&lo[u]);
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(hh[e]), b = __half22float2(lh[e]);
+        f[2 * e] = a.x + b.x; f[2 * e + 1] = a.y + b.y;
+      }
+      *reinterpret_cast<float4*>(s_in + px * kDwsPitch + v * 16) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(s_in + px * kDwsPitch + 64 + v * 16) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+  for (int i = threadIdx.x; i < K * K * kDw2Cb; i += kDw2Threads) {
+    const int t = i / kDw2Cb, c = i - t * kDw2Cb;
+    s_w[i] = (cb0 + c < p.C) ? __ldg(w32 + (long long)t * p.C + cb0 + c) : 0.0f;
+  }
+  __syncthreads();
   const int v = threadIdx.x & 3, strip = (threadIdx.x >> 2) & 7, row = threadIdx.x >> 5;
   const int c0 = cb0 + v * 8;
-  const int oy = oy0 + row;
+  float2 acc2[XPT][4];
+#pragma unroll
+  for (int j = 0; j < XPT; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc2[j][e] = make_float2(0.0f, 0.0f);
+  const unsigned char* base = s_in + ((row * S) * Cfg::IW + strip * XPT * S) * kDwsPitch + v * 16;
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+    float2 xf[Cfg::NX][4];
+#pragma unroll
+    for (int i = 0; i < Cfg::NX; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(base + (ky * Cfg::IW + i) * kDwsPitch);
+      const float4 b = *reinterpret_cast<const float4*>(base + (ky * Cfg::IW + i) * kDwsPitch + 64);
+      xf[i][0] = make_float2(a.x, a.y); xf[i][1] = make_float2(a.z, a.w); xf[i][2] = make_float2(b.x, b.y); xf[i][3] = make_float2(b.z, b.w);
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * kDw2Cb + v * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ky * K + kx) * kDw2Cb + v * 8 + 4);
+      const float2 wf[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+#pragma unroll
+      for (int j = 0; j < XPT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc2[j][e] = his_ffma2(xf[j * S + kx][e], wf[e], acc2[j][e]);
+    }
+  }
   float psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int oy = oy0 + row;
   if (v < nvec && oy < p.Ho) {
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
-    const __half* inb = p.in + (long long)n * p.H * p.W * p.in_cs + c0;
+#pragma unroll
     for (int j = 0; j < XPT; ++j) {
       const int ox = ox0 + strip * XPT + j;
-      if (ox >= p.Wo) continue;
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int ky = 0; ky < K; ++ky) {
-        const int iy = oy * S - p.pad + ky;
-        if (iy < 0 || iy >= p.H) continue;
-        for (int kx = 0; kx < K; ++kx) {
-          const int ix = ox * S - p.pad + kx;
-          if (ix < 0 || ix >= p.W) continue;
-          float xf[8];
-          his_ld8(inb + ((long long)iy * p.W + ix) * p.in_cs, in_lo, xf);
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w32 + (long long)(ky * K + kx) * p.C + c0));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(w32 + (long long)(ky * K + kx) * p.C + c0 + 4));
-          acc[0] = fmaf(xf[0], w0.x, acc[0]); acc[1] = fmaf(xf[1], w0.y, acc[1]); acc[2] = fmaf(xf[2], w0.z, acc[2]); acc[3] = fmaf(xf[3], w0.w, acc[3]);
-          acc[4] = fmaf(xf[4], w1.x, acc[4]); acc[5] = fmaf(xf[5], w1.y, acc[5]); acc[6] = fmaf(xf[6], w1.z, acc[6]); acc[7] = fmaf(xf[7], w1.w, acc[7]);
-        }
-      }
-      float y[8];
+      if (ox < p.Wo) {
+        float y[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { y[e] = act_ct<ACT>(acc[e] * sc[e] + sh[e]); psum[e] += y[e]; }
-      his_st8(p.out + ((long long)(n * p.Ho + oy) * p.Wo + ox) * p.out_cs + c0, out_lo, y);
+        for (int e = 0; e < 4; ++e) {
+          y[2 * e] = act_ct<ACT>(acc2[j][e].x * sc[2 * e] + sh[2 * e]);
+          y[2 * e + 1] = act_ct<ACT>(acc2[j][e].y * sc[2 * e + 1] + sh[2 * e + 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) psum[e] += y[e];
+        his_st8(p.out + ((long long)(n * p.Ho + oy) * p.Wo + ox) * p.out_cs + c0, out_lo, y);
+      }
     }
   }
   if (p.pool) {
@@ -1696,8 +1767,16 @@ int his_depthwise_conv(const void* in, int N, int H, int W, int C, int in_cs, co
     const int il = in_cs / 2, ol = out_cs / 2;
 #define DWS_LAUNCH(K_, S_, X_)                                                                                            \
   do {                                                                                                                    \
-    if (act == HIS_ACT_SILU) depthwise_split_kernel<K_, S_, X_, HIS_ACT_SILU><<<g2, kDw2Threads, 0, ST>>>(p, tiles_x, w32, il, ol); \
-    else depthwise_split_kernel<K_, S_, X_, HIS_ACT_NONE><<<g2, kDw2Threads, 0, ST>>>(p, tiles_x, w32, il, ol);             \
+    constexpr int smem = DwsCfg<K_, S_, X_>::kSmem;                                                                       \
+    if (act == HIS_ACT_SILU) {                                                                                            \
+      static PerDeviceOnce attr_a;                                                                                        \
+      if (attr_a.first()) cudaFuncSetAttribute(depthwise_split_kernel<K_, S_, X_, HIS_ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+      depthwise_split_kernel<K_, S_, X_, HIS_ACT_SILU><<<g2, kDw2Threads, smem, ST>>>(p, tiles_x, w32, il, ol);           \
+    } else {                                                                                                              \
+      static PerDeviceOnce attr_b;                                                                                        \
+      if (attr_b.first()) cudaFuncSetAttribute(depthwise_split_kernel<K_, S_, X_, HIS_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+      depthwise_split_kernel<K_, S_, X_, HIS_ACT_NONE><<<g2, kDw2Threads, smem, ST>>>(p, tiles_x, w32, il, ol);           \
+    }                                                                                                                     \
   } while (0)
     if (k == 3 && stride == 1 && xpt == 4) DWS_LAUNCH(3, 1, 4);
     else if (k == 3 && stride == 1) DWS_LAUNCH(3, 1, 2);
