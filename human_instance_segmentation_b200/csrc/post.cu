@@ -177,9 +177,12 @@ __global__ void __launch_bounds__(kThreads) paste_kernel(const unsigned char* __
     const int syi = min((int)floor((double)dy * sy), mh - 1);
     const unsigned char* mrow = masks + ((long long)roi * mh + syi) * mw;
     int* crow = canvas + ((long long)b * H + (y1 + dy)) * W + x1;
-    for (int dx = dx_lo + lane; dx < dx_hi; dx += 32) {
-      const int sxi = tab ? (int)sxt[dx] : min((int)floor((double)dx * sx), mw - 1);
-      if (mrow[sxi]) atomicMax(crow + dx, roi + 1);
+    if (tab) {                                              // two loops: a select would keep the double-precision product in the hot one
+      for (int dx = dx_lo + lane; dx < dx_hi; dx += 32)
+        if (mrow[sxt[dx]]) atomicMax(crow + dx, roi + 1);
+    } else {
+      for (int dx = dx_lo + lane; dx < dx_hi; dx += 32)
+        if (mrow[min((int)floor((double)dx * sx), mw - 1)]) atomicMax(crow + dx, roi + 1);
     }
   }
 }

@@ -756,32 +756,33 @@ __device__ __forceinline__ float softmax_p1_of(float l0, float l1, float l2) {
 
 constexpr int kDilMax = 16;                                  // largest dilation_pixels (host checks)
 
-template <bool MASK>
-__global__ void __launch_bounds__(kThreads) dilate_logits_tiled_kernel(const float* __restrict__ logits, int H, int W, int k, float score_thr,
+// KD = dilation_pixels as a compile-time constant (1 and 2: window extents, divisions and the max loops unroll), 0 = run time
+template <bool MASK, int KD>
+__global__ void __launch_bounds__(kThreads) dilate_logits_tiled_kernel(const float* __restrict__ logits, int H, int W, int k_rt, float score_thr,
                                                                        float* __restrict__ out, unsigned char* __restrict__ out_u8) {
   __shared__ float sp[(TH + 2 * kDilMax) * (TW + 2 * kDilMax + 1)];      // p1 window, odd pitch
   __shared__ float sr[(TH + 2 * kDilMax) * TW];                          // row maxima
+  const int k = KD ? KD : k_rt;
   const Tile t = tile_of(H, W);
   const long long HW = (long long)H * W, n = plane_of(W);
   const float* l0p = logits + n * 3 * HW;
   const int w0 = TW + 2 * k, h0 = TH + 2 * k, pitch = w0 | 1;
   const float inv_w0 = 1.0f / (float)w0;
-  // four window pixels per thread and pass: the twelve loads are issued before the first softmax (the one-pixel loop waited for
-  // DRAM once per pixel: the kernel ran at a third of its issue rate)
+  // four window pixels per thread and pass: the twelve loads are issued before the first softmax
   for (int base = threadIdx.x; base < w0 * h0; base += 4 * kThreads) {
     float l[4][3];
     int at[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int i = base + u * kThreads;
-      const int ly = (int)(((float)i + 0.5f) * inv_w0), lx = i - ly * w0;   // exact for i < 2^13
+      const int ly = KD ? i / w0 : (int)(((float)i + 0.5f) * inv_w0), lx = i - ly * w0;   // float form exact for i < 2^13
       const int y = t.y0 - k + ly, x = t.x0 - k + lx;
       at[u] = -1;
       if (i < w0 * h0) {
         at[u] = ly * pitch + lx;
         if (y >= 0 && y < H && x >= 0 && x < W) {
-          const long long p = (long long)y * W + x;
-          l[u][0] = __ldg(l0p + p); l[u][1] = __ldg(l0p + HW + p); l[u][2] = __ldg(l0p + 2 * HW + p);
+          const float* q = l0p + ((long long)y * W + x);
+          l[u][0] = __ldg(q); l[u][1] = __ldg(q + HW); l[u][2] = __ldg(q + 2 * HW);
         } else {
           at[u] = -2 - at[u];                                  // outside the plane: -1 (never the maximum)
         }
@@ -798,7 +799,12 @@ __global__ void __launch_bounds__(kThreads) dilate_logits_tiled_kernel(const flo
     const int ly = i / TW, lx = i % TW;
     const float* row = sp + ly * pitch + lx;
     float m = row[0];
-    for (int d = 1; d <= 2 * k; ++d) m = fmaxf(m, row[d]);
+    if (KD) {
+#pragma unroll
+      for (int d = 1; d <= 2 * KD; ++d) m = fmaxf(m, row[d]);
+    } else {
+      for (int d = 1; d <= 2 * k; ++d) m = fmaxf(m, row[d]);
+    }
     sr[ly * TW + lx] = m;
   }
   __syncthreads();
@@ -809,14 +815,20 @@ __global__ void __launch_bounds__(kThreads) dilate_logits_tiled_kernel(const flo
     const int y = t.y0 + ly, x = t.x0 + lx;
     if (y >= H || x >= W) continue;
     float d = sr[ly * TW + lx];
-    for (int e = 1; e <= 2 * k; ++e) d = fmaxf(d, sr[(ly + e) * TW + lx]);
+    if (KD) {
+#pragma unroll
+      for (int e = 1; e <= 2 * KD; ++e) d = fmaxf(d, sr[(ly + e) * TW + lx]);
+    } else {
+      for (int e = 1; e <= 2 * k; ++e) d = fmaxf(d, sr[(ly + e) * TW + lx]);
+    }
     const float p1 = sp[(ly + k) * pitch + lx + k];
+    const float* q = l0p + ((long long)y * W + x);
     const long long p = (long long)y * W + x;
-    const float l0 = __ldg(l0p + p), l1 = __ldg(l0p + HW + p), l2 = __ldg(l0p + 2 * HW + p);
+    const float l0 = __ldg(q), l1 = __ldg(q + HW), l2 = __ldg(q + 2 * HW);
     const float l1d = ((d - p1) > 0.1f) ? l1 + 2.0f : l1;
     if (!MASK) {
-      float* o = out + n * 3 * HW;
-      o[p] = l0; o[HW + p] = l1d; o[2 * HW + p] = l2;
+      float* o = out + n * 3 * HW + p;
+      o[0] = l0; o[HW] = l1d; o[2 * HW] = l2;
     } else {
       bool on = (l1d > l0) && (l1d >= l2);
       if (on && score_thr > 0.0f) {
@@ -829,7 +841,18 @@ __global__ void __launch_bounds__(kThreads) dilate_logits_tiled_kernel(const flo
   }
 }
 
+template <bool MASK>
+void launch_dilate(const float* logits, int N, int H, int W, int k, float thr, float* out, unsigned char* out_u8, cudaStream_t st);
+
 inline dim3 tile_grid(int N, int H, int W) { return dim3((unsigned)((long long)N * ((W + TW - 1) / TW)), (H + TH - 1) / TH, 1); }
+
+template <bool MASK>
+void launch_dilate(const float* logits, int N, int H, int W, int k, float thr, float* out, unsigned char* out_u8, cudaStream_t st) {
+  const dim3 g = tile_grid(N, H, W);
+  if (k == 1) dilate_logits_tiled_kernel<MASK, 1><<<g, kThreads, 0, st>>>(logits, H, W, k, thr, out, out_u8);
+  else if (k == 2) dilate_logits_tiled_kernel<MASK, 2><<<g, kThreads, 0, st>>>(logits, H, W, k, thr, out, out_u8);
+  else dilate_logits_tiled_kernel<MASK, 0><<<g, kThreads, 0, st>>>(logits, H, W, k, thr, out, out_u8);
+}
 
 }  // namespace
 
@@ -963,7 +986,7 @@ int his_post_dilate_logits(const float* logits, int N, int H, int W, int dilatio
       return his_set_error(HIS_ERR_LAUNCH, "memcpy failed");
     return HIS_OK;
   }
-  dilate_logits_tiled_kernel<false><<<tile_grid(N, H, W), kThreads, 0, ST>>>(logits, H, W, dilation_pixels, 0.0f, out, nullptr);
+  launch_dilate<false>(logits, N, H, W, dilation_pixels, 0.0f, out, nullptr, ST);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
@@ -974,7 +997,7 @@ int his_post_dilate_instance_mask(const float* logits, int N, int H, int W, int 
   if (dilation_pixels < 0 || dilation_pixels > kDilMax)
     return his_set_error(HIS_ERR_UNSUPPORTED, "dilate_instance_mask: dilation_pixels must be in [0,16]");
   CHECK_PLANES("dilate_instance_mask");
-  dilate_logits_tiled_kernel<true><<<tile_grid(N, H, W), kThreads, 0, ST>>>(logits, H, W, dilation_pixels, score_threshold, out_f32, out_u8);
+  launch_dilate<true>(logits, N, H, W, dilation_pixels, score_threshold, out_f32, out_u8, ST);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }
