@@ -32,7 +32,7 @@ SPLIT = pytest.mark.parametrize("split", [False, True], ids=["fp16", "split"])
 
 
 @SPLIT
-@pytest.mark.parametrize("k,s,c", [(3, 1, 32), (3, 2, 96), (5, 2, 144), (5, 1, 672), (3, 1, 1152)])
+@pytest.mark.parametrize("k,s,c", [(3, 1, 32), (3, 2, 96), (5, 2, 144), (5, 1, 672), (3, 1, 1152), (3, 1, 16), (5, 1, 240), (3, 2, 40)])
 def test_depthwise_se_matches_torch(k, s, c, split):
     p = _plan(split)
     lib = p.lib
@@ -237,3 +237,4 @@ def test_fused_roi_align_matches_reference_golden_and_plain_kernel(split):
                               b.data_ptr(), 0, st))
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
