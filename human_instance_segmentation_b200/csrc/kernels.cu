@@ -1136,6 +1136,45 @@ __global__ void gn_apply_kernel(const __half* __restrict__ in, int HW, int C, in
   }
 }
 
+// ForegroundAwareNorm (normalization_comparison.py:113-132): y = IN(x) * (p*fs + (1-p)*bs) + (p*fb + (1-p)*bb) with the per-pixel
+// foreground probability p (fp32 [N*HW], from the detector convs) and the instance statistics of gn_stats / gn_finalize (G = C).
+__global__ void fgaware_apply_kernel(const __half* __restrict__ in, int HW, int C, int cs, const float* __restrict__ ws, int nparts,
+                                     const float* __restrict__ fg_scale, const float* __restrict__ fg_bias, const float* __restrict__ bg_scale,
+                                     const float* __restrict__ bg_bias, const float* __restrict__ prob, int act, float act_beta, int res_mode,
+                                     const __half* __restrict__ res, int res_cs, __half* __restrict__ out, int out_cs, int in_lo, int res_lo,
+                                     int out_lo) {
+  extern __shared__ float s_fg[];                       // per channel: mean, rstd, fs, fb, bs, bb
+  const int n = blockIdx.y, cgs = C / 8;
+  const float* st = ws + ((long long)n * (nparts + 1) + nparts) * C * 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_fg[6 * c] = st[2 * c]; s_fg[6 * c + 1] = st[2 * c + 1];
+    s_fg[6 * c + 2] = __ldg(fg_scale + c); s_fg[6 * c + 3] = __ldg(fg_bias + c);
+    s_fg[6 * c + 4] = __ldg(bg_scale + c); s_fg[6 * c + 5] = __ldg(bg_bias + c);
+  }
+  __syncthreads();
+  const long long per_img_vec = (long long)HW * cgs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(idx % cgs);
+    const long long pix = (long long)n * HW + idx / cgs;
+    const float pf = __ldg(prob + pix), pb = 1.0f - pf;
+    float f[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    his_ld8(in + pix * cs + cg * 8, in_lo, f);
+    if (res_mode) his_ld8(res + pix * res_cs + cg * 8, res_lo, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float* q = s_fg + 6 * (cg * 8 + e);
+      const float xn = (f[e] - q[0]) * q[1];
+      const float scale = pf * q[2] + pb * q[4], bias = pf * q[3] + pb * q[5];
+      float y = xn * scale + bias;
+      if (res_mode == HIS_RES_ADD) y += r[e];
+      y = his_act(y, act, act_beta);
+      if (res_mode == HIS_RES_MUL) y *= r[e];
+      f[e] = y;
+    }
+    his_st8(out + pix * out_cs + cg * 8, out_lo, f);
+  }
+}
+
 // ConvTranspose2d(k2,s2) for tiny Cin (upsample_bg_fg.0 in LayerNorm mode: 2 -> 32): NCHW fp32 in, NHWC fp16 out (+bias)
 __global__ void convT2x2_small_kernel(const float* __restrict__ in, int N, int Cin, int h, int w, const float* __restrict__ wt,
                                       const float* __restrict__ bias, int Cout, __half* __restrict__ out, int out_cs, int out_lo) {
@@ -1949,6 +1988,35 @@ int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int group
   gn_apply_kernel<<<dim3((int)(gx < 1 ? 1 : gx), N), kThreads, (size_t)C * 3 * sizeof(float), ST>>>(
       (const __half*)in, HW, C, in_cs, ws, parts, gamma, beta, act, act_beta, res_mode, (const __half*)res, res_cs, (__half*)out, out_cs,
       split ? in_cs / 2 : 0, split ? res_cs / 2 : 0, split ? out_cs / 2 : 0);
+  HIS_CHECK_LAUNCH();
+  return HIS_OK;
+}
+
+int his_fgaware_norm_act(const void* in, int N, int HW, int C, int in_cs, const float* fg_scale, const float* fg_bias, const float* bg_scale,
+                         const float* bg_bias, const float* prob, float eps, int act, float act_beta, int res_mode, const void* res, int res_cs,
+                         float* ws, void* out, int out_cs, int split, void* stream) {
+  if (!in || !fg_scale || !fg_bias || !bg_scale || !bg_bias || !prob || !ws || !out) return his_set_error(HIS_ERR_INVALID_ARG, "fgaware_norm: null pointer");
+  if (res_mode && !res) return his_set_error(HIS_ERR_INVALID_ARG, "fgaware_norm: res_mode without residual");
+  if (C % 8 || in_cs % 8 || out_cs % 8 || (res_mode && res_cs % 8)) return his_set_error(HIS_ERR_UNSUPPORTED, "fgaware_norm: channels must be multiples of 8");
+  if (C > kGnMaxC) return his_set_error(HIS_ERR_UNSUPPORTED, "fgaware_norm: more than 2048 channels");
+  if (N == 0) return HIS_OK;
+  const int parts = his_groupnorm_parts(N, HW, C);
+  const int ppp = (HW + parts - 1) / parts;
+  const int cgs = C / 8, PL = kThreads / cgs;
+  static PerDeviceOnce attr_done;
+  if (attr_done.first()) cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const size_t sm1 = (size_t)PL * C * 2 * sizeof(float);
+  gn_stats_kernel<<<dim3(parts, N), kThreads, sm1, ST>>>((const __half*)in, HW, C, in_cs, split ? in_cs / 2 : 0, ppp, parts + 1, ws);
+  gn_finalize_kernel<<<dim3((C + 127) / 128, N), 128, 0, ST>>>(ws, (const __half*)in, in_cs, split ? in_cs / 2 : 0, HW, C, C, parts, eps);
+  const long long per_img_vec = (long long)HW * cgs;
+  long long gx = (per_img_vec + kThreads - 1) / kThreads;
+  const long long cap = (148LL * 16 + N - 1) / N;
+  if (gx > cap) gx = cap;
+  static PerDeviceOnce attr2;
+  if (attr2.first()) cudaFuncSetAttribute(fgaware_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  fgaware_apply_kernel<<<dim3((int)(gx < 1 ? 1 : gx), N), kThreads, (size_t)C * 6 * sizeof(float), ST>>>(
+      (const __half*)in, HW, C, in_cs, ws, parts, fg_scale, fg_bias, bg_scale, bg_bias, prob, act, act_beta, res_mode, (const __half*)res, res_cs,
+      (__half*)out, out_cs, split ? in_cs / 2 : 0, split ? res_cs / 2 : 0, split ? out_cs / 2 : 0);
   HIS_CHECK_LAUNCH();
   return HIS_OK;
 }

@@ -124,6 +124,8 @@ SIGNATURES = {
     "his_layernorm2d_act": [_P, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P],
     "his_groupnorm_parts": [c_int, c_int, c_int],
     "his_groupnorm_act": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
+    "his_fgaware_norm_act": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_float, c_int, c_float, c_int, _P, c_int, _P, _P, c_int,
+                             c_int, _P],
     "his_convT2x2_small": [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, c_int, _P],
     "his_spatial_attention": [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, c_int, _P],
     "his_spatial_gate": [_P, c_int, c_int, c_int, _P, c_int, _P, _P],

@@ -742,7 +742,7 @@ class _BuiltPlan:
             assert tail is None and out_f32 is None and aux_f32 is None and stats_out is None
             # LayerNorm2d: the statistics of the conv output come from the GEMM epilogue (no separate pass over the tensor)
             raw = self.conv(x, conv, None, ACT["none"], in_gate=in_gate, row_scale=row_scale,
-                            ln_stats=pt.group_norm_args(norm) is None and os.environ.get("HIS_LN_EPILOGUE", "1") != "0")
+                            ln_stats=isinstance(norm, pt.LayerNorm2dParams) and os.environ.get("HIS_LN_EPILOGUE", "1") != "0")
             return self.layernorm(raw, norm, act, res, res_mode, out)
         transposed = isinstance(conv, nn.ConvTranspose2d)
         w = conv.weight
@@ -799,8 +799,22 @@ class _BuiltPlan:
         if out is None:
             out = p.act(x.N, x.H, x.W, x.C)
         if isinstance(norm, pt.INSTANCE_NORMS) and not self.split:
-            raise NotImplementedError("normalization_type 'instance' / 'adaptive_instance' needs model.precision = 'strict': per-channel statistics "
-                                      "of a single-fp16 pre-normalisation tensor are 1.5e-2 .. 4e-2 off the reference (DESIGN section 4)")
+            raise NotImplementedError("normalization_type 'instance' / 'adaptive_instance' / 'foreground_aware' needs model.precision = 'strict': "
+                                      "per-channel statistics of a single-fp16 pre-normalisation tensor are 1.5e-2 .. 4e-2 off the reference "
+                                      "(DESIGN section 4)")
+        if isinstance(norm, pt.ForegroundAwareNormParams):
+            # fg detector on the un-normalised input: conv1x1 C -> C/4 + ReLU (GEMM / direct kernel), conv1x1 C/4 -> 1 + sigmoid to fp32
+            hid = self.conv(x, norm.fg_detector[0], None, ACT["relu"])
+            prob = p.f32(x.N, 1, x.H, x.W)
+            self.conv(hid, norm.fg_detector[2], None, ACT["sigmoid"], out_f32=prob)
+            parts = L.his_groupnorm_parts(x.N, x.H * x.W, x.C)
+            ws = torch.empty((x.N, parts + 1, x.C, 2), dtype=torch.float32, device=self.dev)
+            p.keep.append(ws)
+            p.add("fgaware_norm", L.his_fgaware_norm_act, x.ptr, x.N, x.H * x.W, x.C, x.cs, p.const(norm.fg_scale).data_ptr(),
+                  p.const(norm.fg_bias).data_ptr(), p.const(norm.bg_scale).data_ptr(), p.const(norm.bg_bias).data_ptr(), prob.data_ptr(),
+                  float(norm.eps), act, self.beta, res_mode, res.ptr if res is not None else None, res.cs if res is not None else 0,
+                  ws.data_ptr(), out.ptr, out.cs, self.S)
+            return out
         gn = pt.group_norm_args(norm)
         if gn is not None:
             groups, gamma, beta, eps = gn

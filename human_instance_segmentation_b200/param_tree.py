@@ -66,6 +66,22 @@ class AdaptiveInstanceNormParams(nn.Module):
         self.register_buffer("running_var", torch.ones(c))
 
 
+class ForegroundAwareNormParams(nn.Module):
+    """ForegroundAwareNorm (normalization_comparison.py:84-132): instance norm (no affine) whose per-channel scale / bias are blended
+    per PIXEL between a foreground and a background set by a learned detector on the un-normalised input:
+    p = sigmoid(conv1x1(relu(conv1x1(x)))),  y = IN(x) * (p*fg_scale + (1-p)*bg_scale) + (p*fg_bias + (1-p)*bg_bias)."""
+
+    def __init__(self, c: int, eps: float = 1e-5):
+        super().__init__()
+        self.num_features, self.eps = c, eps
+        self.norm = nn.InstanceNorm2d(c, eps=eps, affine=False)
+        self.fg_scale = nn.Parameter(torch.ones(c))
+        self.fg_bias = nn.Parameter(torch.zeros(c))
+        self.bg_scale = nn.Parameter(torch.ones(c))
+        self.bg_bias = nn.Parameter(torch.zeros(c))
+        self.fg_detector = nn.Sequential(nn.Conv2d(c, c // 4, 1), nn.ReLU(inplace=True), nn.Conv2d(c // 4, 1, 1), nn.Sigmoid())
+
+
 def norm_spec(kind: str, groups: int = 8) -> str:
     """Internal spelling of (normalization_type, normalization_groups) handed down the parameter tree: 'group:8'."""
     return f"{kind}:{int(groups)}"
@@ -102,8 +118,7 @@ def norm_params(kind: str, c: int, clamp: bool = True) -> nn.Module:
     if k == "mixed":
         return MixedNormParams(c)
     if k == "foreground_aware":
-        raise NotImplementedError("normalization_type='foreground_aware' (instance norm blended by a learned fg detector, experimental "
-                                  "in the reference) is not implemented by the B200 path")
+        return ForegroundAwareNormParams(c)
     raise ValueError(f"Unknown normalization type: {k}")
 
 
@@ -118,7 +133,7 @@ def group_norm_args(norm: nn.Module):
     return None
 
 
-INSTANCE_NORMS = (nn.InstanceNorm2d, AdaptiveInstanceNormParams)
+INSTANCE_NORMS = (nn.InstanceNorm2d, AdaptiveInstanceNormParams, ForegroundAwareNormParams)
 NORM_MODULES = (nn.BatchNorm2d, LayerNorm2dParams, nn.GroupNorm, SpatialGroupNormParams, MixedNormParams) + INSTANCE_NORMS
 
 

@@ -169,6 +169,12 @@ int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const f
 int his_groupnorm_parts(int N, int HW, int C);
 int his_groupnorm_act(const void* in, int N, int HW, int C, int in_cs, int groups, const float* gamma, const float* beta, float eps, int act,
                       float act_beta, int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, int split, void* stream);
+/* ForegroundAwareNorm (normalization_comparison.py:84-132): instance statistics of `in` (ws as for his_groupnorm_act), then
+ * y = IN(x) * (p*fg_scale + (1-p)*bg_scale) + (p*fg_bias + (1-p)*bg_bias) (+ residual) + activation, with p = prob[N*HW] (fp32, the
+ * output of the module's detector convs on the un-normalised input, run by the caller through the conv entry points). */
+int his_fgaware_norm_act(const void* in, int N, int HW, int C, int in_cs, const float* fg_scale, const float* fg_bias,
+                         const float* bg_scale, const float* bg_bias, const float* prob, float eps, int act, float act_beta,
+                         int res_mode, const void* res, int res_cs, float* ws, void* out, int out_cs, int split, void* stream);
 int his_convT2x2_small(const float* in, int N, int cin, int h, int w, const float* wt, const float* bias, int cout,
                        void* out, int out_cs, int split, void* stream);
 

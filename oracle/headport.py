@@ -148,6 +148,15 @@ def norm(sd: SD, p: str, x: Tensor, cfg: PathConfig) -> Tensor:
         var = xr.var(dim=2, keepdim=True, unbiased=False)
         xn = ((xr - mean) / torch.sqrt(var + 1e-5)).view(b, c, h, w)
         return xn * sd[p + "weight"].view(1, c, 1, 1) + sd[p + "bias"].view(1, c, 1, 1)
+    if t == "foreground_aware":
+        # ForegroundAwareNorm.forward (:113-132): instance norm without affine, scale / bias blended per pixel by the fg detector
+        c = x.shape[1]
+        xn = F.instance_norm(x, None, None, None, None, True, 0.0, 1e-5)
+        prob = torch.sigmoid(conv(sd, p + "fg_detector.2.", F.relu(conv(sd, p + "fg_detector.0.", x))))
+        v = lambda k: sd[p + k].view(1, c, 1, 1)
+        scale = prob * v("fg_scale") + (1 - prob) * v("bg_scale")
+        bias = prob * v("fg_bias") + (1 - prob) * v("bg_bias")
+        return xn * scale + bias
     if t in ("group", "groupnorm", "spatial_group"):
         # nn.GroupNorm (:187-194; SpatialGroupNorm :54-74 wraps one under .norm); group count as the factory resolves it for
         # group counts that do not exceed the channel count

@@ -75,6 +75,9 @@ REFINE_CASES = {
                                   use_attention_module=True, use_distance_transform=False), (96, 128)),
     "small_b0_adaptive_instance": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="adaptive_instance",
                                            use_attention_module=False, use_contour_detection=False), (96, 128)),
+    # foreground_aware (:84-132, :200): instance norm blended per pixel by a learned detector; strict precision mode only
+    "small_b0_foreground_aware": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="foreground_aware",
+                                          use_attention_module=False, use_distance_transform=False), (96, 128)),
     "small_b0_mixed": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), normalization_type="mixed",
                                use_progressive_upsampling=True), (96, 128)),
     "small_b0_progressive": (replace(headport.PRESETS["b0"], roi_size=(16, 12), mask_size=(32, 24), use_progressive_upsampling=True,
@@ -161,11 +164,14 @@ def make_model_goldens():
           "argmax", torch.bincount(logits.argmax(1).flatten(), minlength=3).tolist())
 
 
-def make_guided_goldens():
-    """The guided-head variant; adds its key/shape tables to state_dict_keys.json without touching the other entries."""
+def make_guided_goldens(only_case=None):
+    """The guided-head variant; adds its key/shape tables to state_dict_keys.json without touching the other entries.
+    only_case: regenerate that one case (``--only case:NAME``)."""
     path = os.path.join(GOLDEN, "state_dict_keys.json")
     keys_json = json.load(open(path))
     for name, (cfg, (h, w)) in {**GUIDED_CASES, **STANDARD_CASES, **MULTISCALE_CASES, **REFINE_CASES}.items():
+        if only_case is not None and name != only_case:
+            continue
         images = synth_images(11, 2, h, w)
         rois = torch.cat([synth_rois(11, 2, 2), edge_rois(2)], 0)
         model, sd, logits, aux = _run_reference(cfg, images, rois)
@@ -258,6 +264,8 @@ def main():
         make_default_init_golden()
     if args.only in ("all", "guided"):
         make_guided_goldens()
+    if args.only.startswith("case:"):
+        make_guided_goldens(args.only[5:])
     if args.only in ("all", "real"):
         make_real_goldens()
     if args.only in ("all", "post"):
