@@ -315,6 +315,11 @@ int his_conv_gemm_create(void** out_plan,
   if (const char* e = getenv("HIS_GEMM_DIRECT")) p.direct_ok = p.direct_ok ? atoi(e) : 0;   // 0 never, 1 channel-clipped chunks, 2 + clipped tiles, 3 = 1 + residual of clipped tiles
   p.debug = 0;
   if (const char* e = getenv("HIS_GEMM_DEBUG")) p.debug = atoi(e);
+  p.dbg_ts = nullptr;
+  if (p.debug & 16) {
+    if (cudaMalloc(&p.dbg_ts, 64 * 32 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(p.dbg_ts, 0, 64 * 32 * sizeof(unsigned long long));
+    else p.dbg_ts = nullptr;
+  }
   p.up_in = (const __half*)in; p.up_sn = 0; p.up_cs = 8; p.up_split = 0;      // no fused upsample
   // TMEM accumulator ring: as many buffers as the 512 columns hold (even, <= 8) so that short tiles are not paced by
   // the MMA -> epilogue -> MMA hand-shake latency
@@ -579,7 +584,31 @@ int his_conv_gemm_run(void* plan, void* stream) {
 }
 
 int his_conv_gemm_destroy(void* plan) {
-  delete (ConvGemmPlan*)plan;
+  ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  if (pl && pl->p.dbg_ts) {
+    // tuning aid (HIS_GEMM_DEBUG & 16): mean clock deltas between the epilogue's stamps over the tiles thread 128 of CTA 0 drained
+    static unsigned long long ts[64 * 32];
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(ts, pl->p.dbg_ts, sizeof ts, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      int nt = 0;
+      while (nt < 64 && ts[nt * 32 + 24]) ++nt;
+      fprintf(stderr, "[his dbg] N%d %dx%d cin%d cout%d k%d res%d tiles stamped %d", pl->p.n_img, pl->p.H, pl->p.W, pl->p.cin, pl->p.cout, pl->p.ksize,
+              pl->res_mode, nt);
+      if (nt > 4) {
+        fprintf(stderr, " period %.0f clk |", (double)(ts[(nt - 1) * 32] - ts[2 * 32]) / (nt - 3));
+        int prev = 0;
+        for (int k = 1; k <= 24; ++k) {
+          double sum = 0; int cnt = 0;
+          for (int t = 2; t < nt; ++t)
+            if (ts[t * 32 + k] && ts[t * 32 + prev]) { sum += (double)(long long)(ts[t * 32 + k] - ts[t * 32 + prev]); ++cnt; }
+          if (cnt) { fprintf(stderr, " %d:%.0f", k, sum / cnt); prev = k; }
+        }
+      }
+      fprintf(stderr, "\n");
+    }
+    cudaFree(pl->p.dbg_ts);
+  }
+  delete pl;
   return HIS_OK;
 }
 

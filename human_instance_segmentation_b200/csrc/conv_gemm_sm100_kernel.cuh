@@ -103,7 +103,8 @@ struct ConvGemmParams {
   // [0, up_split) are gathered from the low-resolution tensor `up_in` [n, H/2, W/2, up_cs] at (y>>1, x>>1), the rest from `in`
   const __half* up_in; long long up_sn; int up_cs, up_split;
   int pair;             // 1: CTA pairs (cluster of 2) run cta_group::2 MMAs, M = 256 pixels x block_n, each CTA stages half of the weight tile
-  int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs
+  int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs,
+                        // 16 epilogue time stamps, 32 general chunk body everywhere, 64 residual chunks loaded at the top of their own chunk
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
   //   SIGMOID: s = 1/(1+exp(-act_beta*y)); y = act_mul_x ? y*s : s   (sigmoid / silu / swish(beta))
@@ -144,6 +145,8 @@ struct ConvGemmParams {
   // writes (sum, sum of squares) of the values it stores -- the fp16-rounded ones, i.e. what the normalise pass will read -- to
   // ln_partials[work item][2] (double); a sample's work items are contiguous, his_layernorm2d_act adds them in order.
   double* ln_partials;
+  // HIS_GEMM_DEBUG & 16 (tuning only): thread 128 of CTA 0 writes clock64() stamps of its first 64 tiles here, 32 slots per tile
+  unsigned long long* dbg_ts;
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -341,6 +344,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// explicit shared-window 16-byte accesses (the epilogue's pointers are otherwise generic: LD / ST instead of LDS / STS)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 template <int ACTC>
 __device__ __forceinline__ float epi_act(float y, const ConvGemmParams& p) {
@@ -738,8 +751,12 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // the CTA's i-th tile uses accumulator i % n_acc (phase (i / n_acc) & 1) and is drained by group i % epi_groups
     const int G = p.epi_groups;
     int ti = g, acc = g % n_acc; uint32_t acc_phase = (uint32_t)(g / n_acc) & 1u;
+    const bool ts_on = (p.debug & 16) && p.dbg_ts && blockIdx.x == 0 && threadIdx.x == 128;
+    int ts_tile = 0;
+#define HIS_TS(k) do { if (ts_on && ts_tile < 64) p.dbg_ts[ts_tile * 32 + (k)] = (unsigned long long)clock64(); } while (0)
     for (int w = blockIdx.x + g * gridDim.x; w < p.num_work; w += G * gridDim.x) {
       const WorkItem it = decode_work(p, w);
+      HIS_TS(0);
       const uint32_t acc_col = (uint32_t)(acc * p.acc_stride);
       const int chbase = it.n_tile * p.block_n;
       const float* shp = p.n_tiles == 1 ? s_shift : p.shift + chbase;
@@ -769,6 +786,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      HIS_TS(1);
       float tacc0 = 0.0f, tacc1 = 0.0f;
       constexpr bool TAIL = EPI == EPI_TAIL;
       const bool store_main = (!TAIL || p.store_main) && !(p.debug & 1);
@@ -790,8 +808,19 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       float st_sum = 0.0f, st_max = -INFINITY;
       float ln_s = 0.0f, ln_q = 0.0f;
+      // Straight-line chunk body for the common case (plain fp16 store of a full 32-channel chunk through the staging buffer, no
+      // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
+      // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
+      // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
+      const bool fast_tile = EPI == EPI_PLAIN && !SPLIT && p.n_tiles == 1 && !p.stats_out && !p.ln_partials && !has_rsc && !res_glob &&
+                             store_main && !(p.debug & 32);
+      // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
+      const bool res_early = RES && !SPLIT && !res_glob && !(p.debug & 64);
+      HIS_TS(2);
       for (int j = 0; j < nchunks; ++j) {
         const bool direct = j >= ntma;
+        const int tsb = 3 + (j < 3 ? j : 2) * 7;
+        HIS_TS(tsb);
         const int b = SPLIT ? 0 : (cc & 1);     // SPLIT: staging[0] = hi plane, staging[1] = lo plane of the chunk
         const uint32_t stg = stg0 + b * kStagingBytes;
         const int cl0 = j * kChunkC;            // first channel of this chunk within the N tile
@@ -810,7 +839,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 tma_load_5d(stg0 + kStagingBytes, &tmR, res_bar(2 * g), ch0, 1, it.x0, it.y0, it.img);
               }
             }
-          } else if ((!RES || res_glob || j >= 2) && issuer_warp && elect_one()) {
+          } else if ((!RES || res_glob || (j >= 2 && !res_early)) && issuer_warp && elect_one()) {
             tma_wait_read<1>();                    // the store that last read staging[b] has drained
             if (RES && !res_glob) {
               mbar_expect_tx(res_bar(2 * g + b), kStagingBytes);
@@ -819,10 +848,12 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         }
+        HIS_TS(tsb + 1);
         uint32_t v[kChunkC];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)cl0;
         if (ncol > 16) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_ld_wait();
+        HIS_TS(tsb + 2);
         if (j == nchunks - 1) {                  // accumulator fully read -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -832,11 +863,59 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
         if (RES && !direct && !res_glob) { mbar_wait(res_bar(2 * g + b), (res_phase >> b) & 1u); res_phase ^= 1u << b; }
+        if (res_early && j >= 1 && j + 1 < ntma && issuer_warp && elect_one()) {
+          // chunk j+1's residual -> the other staging buffer, whose last reader is the store of chunk j-1 (issued a whole chunk
+          // ago: the wait is short); the load then has this chunk's math and store to land instead of being waited for at once
+          tma_wait_read<0>();
+          mbar_expect_tx(res_bar(2 * g + (b ^ 1)), kStagingBytes);
+          tma_load_4d(stg0 + (b ^ 1) * kStagingBytes, &tmR, res_bar(2 * g + (b ^ 1)), ch0 + kChunkC, it.x0, it.y0, it.img);
+        }
+        HIS_TS(tsb + 3);
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
         float* aux_row = reinterpret_cast<float*>(smem_gen + (aux_base - smem_base) + g * kAuxStagingBytes) + te;
+        const bool fast = fast_tile && !direct && ncol == kChunkC;
+        if (fast) {
+          const uint32_t rowa = stg + (uint32_t)te * (kChunkC * 2), sw = (uint32_t)(te >> 1) & 3u;     // SWIZZLE_64B row of this pixel
+          const uint32_t sha = shift_base + (uint32_t)cl0 * 4u;
+          // two halves of 16 channels: all shared-memory loads of a half first (the volatile accesses keep their program order, so
+          // loads placed after a store would wait for it), then the math, then the stores
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 rv[2], sv[4];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (RES) rv[k] = lds128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4));
+              sv[2 * k] = lds128(sha + (uint32_t)(2 * h + k) * 32u);
+              sv[2 * k + 1] = lds128(sha + (uint32_t)(2 * h + k) * 32u + 16u);
+            }
+            uint4 ov[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int i = 2 * h + k;
+              const float sh[8] = {__uint_as_float(sv[2 * k].x), __uint_as_float(sv[2 * k].y), __uint_as_float(sv[2 * k].z), __uint_as_float(sv[2 * k].w),
+                                   __uint_as_float(sv[2 * k + 1].x), __uint_as_float(sv[2 * k + 1].y), __uint_as_float(sv[2 * k + 1].z),
+                                   __uint_as_float(sv[2 * k + 1].w)};
+              const __half2* rh = reinterpret_cast<const __half2*>(&rv[k]);
+              __half2* o = reinterpret_cast<__half2*>(&ov[k]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t0 = fmaf(__uint_as_float(v[i * 8 + 2 * e]), rs, sh[2 * e]);
+                float t1 = fmaf(__uint_as_float(v[i * 8 + 2 * e + 1]), rs, sh[2 * e + 1]);
+                float2 r = make_float2(0.0f, 0.0f);
+                if (RES) r = __half22float2(rh[e]);
+                if (RES == HIS_RES_ADD) { t0 += r.x; t1 += r.y; }
+                t0 = epi_act<ACTC>(t0, p); t1 = epi_act<ACTC>(t1, p);
+                if (RES == HIS_RES_MUL) { t0 *= r.x; t1 *= r.y; }
+                o[e] = __floats2half2_rn(t0, t1);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) sts128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4), ov[k]);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < kChunkC / 8; ++i) {
-          if (i * 8 < ncol) {
+          if (!fast && i * 8 < ncol) {
             const int cl = cl0 + i * 8, c = ch0 + i * 8;
             uint4* cell = reinterpret_cast<uint4*>(row_ptr + ((i ^ ((te >> 1) & 3)) << 4));   // SWIZZLE_64B
             uint4* cell_lo = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(cell) + kStagingBytes);      // SPLIT: lo plane
@@ -934,9 +1013,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
         }
+        HIS_TS(tsb + 4);
         if ((store_main && !direct) || aux_tma) {
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          HIS_TS(tsb + 5);
           if (issuer_warp && elect_one()) {
             if (store_main && !direct) {
               // merged ConvT phases: the chunk belongs to phase (group * merge + cl0 / phase_slab) and to its output map
@@ -956,8 +1037,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tma_commit();
           }
         }
+        HIS_TS(tsb + 6);
         if (!direct) ++cc;
       }
+      HIS_TS(24);
+      ++ts_tile;
       if (p.stats_out && inb) {
         p.stats_out[pix * 2] = st_sum / (float)p.cout;
         p.stats_out[pix * 2 + 1] = st_max;
@@ -987,6 +1071,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       acc = ti % n_acc; acc_phase = (uint32_t)(ti / n_acc) & 1u;
     }
     if (issuer_warp && elect_one()) tma_wait_all();
+#undef HIS_TS
   }
 
   tc_fence_before();

@@ -36,6 +36,9 @@ SHAPES = [
     ("head 128->256 k1 gate*shared", 640, 64, 48, 128, 256, 1, RES_MUL, False),
     ("head 258->256 k1", 640, 64, 48, 258, 256, 1, RES_NONE, False),
     ("head convT 256->128", 640, 64, 48, 256, 128, 1, RES_NONE, True),
+    ("head 256->256 k1 plain", 640, 64, 48, 256, 256, 1, RES_NONE, False),
+    ("head 128->128 k3 128x96 res", 320, 128, 96, 128, 128, 3, RES_ADD, False),
+    ("head 128->128 k3 64x48 res", 640, 64, 48, 128, 128, 3, RES_ADD, False),
 ]
 
 
