@@ -386,7 +386,7 @@ int his_conv_gemm_create(void** out_plan,
     if (const char* e = getenv("HIS_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }
   }
   pl->actc = actc; pl->res_mode = res_mode; pl->transposed = transposed; pl->cin_pad = cin_pad;
-  p.tail_c = 0; p.store_main = 1; p.aux_out = nullptr; p.cout = cout;
+  p.tail_c = 0; p.store_main = 1; p.aux_out = nullptr; p.aux_bufs = 1; p.cout = cout;
   p.shift = shift;
   int taps = ksize * ksize;
   int rc;
@@ -524,18 +524,26 @@ int his_conv_gemm_set_aux(void* plan, float* aux_out) {
   ConvGemmParams& p = pl->p;
   int want = (p.W % 4) == 0;
   if (const char* e = getenv("HIS_GEMM_AUX_TMA")) want = want && atoi(e) != 0;
-  p.aux_tma = 0;
+  p.aux_tma = 0; p.aux_bufs = 1;
   if (want) {
-    const int need = p.epi_groups * kAuxStagingBytes;
-    bool ok = true;
-    if (!pl->halo) {
-      const int st = (KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes - need) / p.stage_bytes;
-      if (st >= 2) { if (st < p.stages) p.stages = st; } else ok = false;
-    } else {
-      const int budget = KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes - need;
-      while (p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes > budget && p.a_stages > 2) --p.a_stages;
-      while (p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes > budget && p.stages > 2 && !p.b_resident) --p.stages;
-      ok = p.stages * p.stage_bytes + p.a_stages * p.a_stage_bytes <= budget;
+    // two export tiles per group (the store of a chunk drains while the next chunk is written) where the operand ring can spare
+    // the 16 KB per group: the short K loops of the 1x1 layers; a 3x3 layer keeps its ring depth and one tile
+    bool ok = false;
+    int max_bufs = p.ksize == 1 ? 2 : 1;
+    if (const char* e = getenv("HIS_GEMM_AUX_BUFS")) { const int v = atoi(e); if (v == 1 || v == 2) max_bufs = v; }
+    for (int bufs = max_bufs; bufs >= 1 && !ok; --bufs) {
+      const int need = p.epi_groups * bufs * kAuxStagingBytes;
+      if (!pl->halo) {
+        const int st = (KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes - need) / p.stage_bytes;
+        if (st >= 2) { if (st < p.stages) p.stages = st; ok = true; }
+      } else {
+        const int budget = KCfg<64>::kRingBytes - (p.epi_groups - 2) * 2 * kStagingBytes - need;
+        int a_st = p.a_stages, b_st = p.stages;
+        while (b_st * p.stage_bytes + a_st * p.a_stage_bytes > budget && a_st > 2) --a_st;
+        while (b_st * p.stage_bytes + a_st * p.a_stage_bytes > budget && b_st > 2 && !p.b_resident) --b_st;
+        if (b_st * p.stage_bytes + a_st * p.a_stage_bytes <= budget) { p.a_stages = a_st; p.stages = b_st; ok = true; }
+      }
+      if (ok) p.aux_bufs = bufs;
     }
     if (ok) {
       PFN_encodeTiled enc = get_encode();

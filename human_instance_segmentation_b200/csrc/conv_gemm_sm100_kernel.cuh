@@ -119,6 +119,7 @@ struct ConvGemmParams {
   int tail_c, tail_sigmoid, store_main;
   // fp32 NCHW copy of the layer output (EPI_AUX kernels): aux[n][c][y][x] = y, or the gate itself (before the product) for RES_MUL
   float* aux_out;
+  int aux_bufs;         // export staging tiles per epilogue group (2: the TMA store of chunk j drains while chunk j+1 is written)
   int aux_tma;          // 1: the export leaves through a [32 ch][128 px] fp32 staging tile and ONE TMA store per chunk (coalesced
                         // 64-byte rows per channel) instead of 32 strided 4-byte stores per thread; needs W % 4 == 0
   int cout;             // true output channel count
@@ -351,6 +352,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -452,6 +456,11 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   float* s_shift = reinterpret_cast<float*>(smem_gen + (shift_base - smem_base));
   if (p.n_tiles == 1)
     for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) s_shift[i] = __ldg(p.shift + (p.phase_merge > 1 ? i % p.phase_slab : i));
+  // fused 1x1 tail: its weight rows live in the (otherwise unused) residual-scale rows 0 / 1 of the shift block
+  const bool tail_smem = EPI == EPI_TAIL && p.n_tiles == 1 && !p.res_scale && !p.ln_partials;
+  if (tail_smem)
+    for (int i = threadIdx.x; i < p.tail_c * p.cout_slab; i += blockDim.x)
+      s_shift[256 + (i / p.cout_slab) * 256 + (i % p.cout_slab)] = __ldg(p.tail_w + i);
   tc_fence_before();
   __syncthreads();
   if (pair) cluster_sync_all();        // the peer's barriers are initialised and its TMEM is allocated before anything remote happens
@@ -746,7 +755,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool issuer_warp = q == 0;            // first warp of the group issues the group's TMA traffic
     const int nchunks = (p.block_n + kChunkC - 1) / kChunkC;
     const uint32_t stg0 = staging_base + g * 2 * kStagingBytes;
-    uint32_t cc = 0;
+    uint32_t cc = 0, ac = 0;                      // staging / export tile parity counters
     uint32_t res_phase = 0;                       // bit b: parity of the next residual load into staging buffer b
     // the CTA's i-th tile uses accumulator i % n_acc (phase (i / n_acc) & 1) and is drained by group i % epi_groups
     const int G = p.epi_groups;
@@ -812,8 +821,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
       // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
       // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
-      const bool fast_tile = EPI == EPI_PLAIN && !SPLIT && p.n_tiles == 1 && !p.stats_out && !p.ln_partials && !has_rsc && !res_glob &&
-                             store_main && !(p.debug & 32);
+      const bool fast_tile = !SPLIT && p.n_tiles == 1 && !p.stats_out && !p.ln_partials && !has_rsc && !res_glob && !(p.debug & 32) &&
+                             (EPI != EPI_TAIL || tail_smem) && (EPI != EPI_AUX || p.aux_tma);
       // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
       const bool res_early = RES && !SPLIT && !res_glob && !(p.debug & 64);
       HIS_TS(2);
@@ -827,7 +836,9 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int ch0 = chbase + cl0;           // ... and within the layer
         const int ncol = min(kChunkC, p.block_n - cl0);   // valid accumulator columns in this chunk (16 or 32)
         const bool aux_tma = EPI == EPI_AUX && p.aux_tma;
-        if (aux_tma && issuer_warp && elect_one()) tma_wait_read<0>();     // the (single) export tile and staging[b] are free again
+        // the export tile this chunk writes (and staging[b]) are free again: with two tiles the previous chunk's stores may still drain
+        if (aux_tma && issuer_warp && elect_one()) { if (p.aux_bufs > 1) tma_wait_read<1>(); else tma_wait_read<0>(); }
+        const uint32_t aux_tile = aux_base + (uint32_t)(g * p.aux_bufs + (p.aux_bufs > 1 ? (int)(ac & 1u) : 0)) * kAuxStagingBytes;
         if (direct && aux_tma) asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         if (!direct) {
           if (SPLIT) {
@@ -872,7 +883,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         HIS_TS(tsb + 3);
         uint8_t* row_ptr = smem_gen + (stg - smem_base) + te * (kChunkC * 2);
-        float* aux_row = reinterpret_cast<float*>(smem_gen + (aux_base - smem_base) + g * kAuxStagingBytes) + te;
+        float* aux_row = reinterpret_cast<float*>(smem_gen + (aux_tile - smem_base)) + te;
         const bool fast = fast_tile && !direct && ncol == kChunkC;
         if (fast) {
           const uint32_t rowa = stg + (uint32_t)te * (kChunkC * 2), sw = (uint32_t)(te >> 1) & 3u;     // SWIZZLE_64B row of this pixel
@@ -897,6 +908,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                    __uint_as_float(sv[2 * k + 1].w)};
               const __half2* rh = reinterpret_cast<const __half2*>(&rv[k]);
               __half2* o = reinterpret_cast<__half2*>(&ov[k]);
+              float y[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float t0 = fmaf(__uint_as_float(v[i * 8 + 2 * e]), rs, sh[2 * e]);
@@ -905,12 +917,31 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if (RES) r = __half22float2(rh[e]);
                 if (RES == HIS_RES_ADD) { t0 += r.x; t1 += r.y; }
                 t0 = epi_act<ACTC>(t0, p); t1 = epi_act<ACTC>(t1, p);
+                if (EPI == EPI_AUX) {      // [channel][pixel] fp32 tile: lanes write consecutive words
+                  sts32f(aux_tile + (uint32_t)((i * 8 + 2 * e) * kBlockM + te) * 4u, t0);
+                  sts32f(aux_tile + (uint32_t)((i * 8 + 2 * e + 1) * kBlockM + te) * 4u, t1);
+                }
                 if (RES == HIS_RES_MUL) { t0 *= r.x; t1 *= r.y; }
+                y[2 * e] = t0; y[2 * e + 1] = t1;
                 o[e] = __floats2half2_rn(t0, t1);
               }
+              if (TAIL) {
+                const uint4 wa = lds128(sha + 1024u + (uint32_t)i * 32u), wb = lds128(sha + 1024u + (uint32_t)i * 32u + 16u);
+                const float4 w0 = make_float4(__uint_as_float(wa.x), __uint_as_float(wa.y), __uint_as_float(wa.z), __uint_as_float(wa.w));
+                const float4 w1 = make_float4(__uint_as_float(wb.x), __uint_as_float(wb.y), __uint_as_float(wb.z), __uint_as_float(wb.w));
+                tacc0 += y[0] * w0.x + y[1] * w0.y + y[2] * w0.z + y[3] * w0.w + y[4] * w1.x + y[5] * w1.y + y[6] * w1.z + y[7] * w1.w;
+                if (p.tail_c > 1) {
+                  const uint4 ua = lds128(sha + 2048u + (uint32_t)i * 32u), ub = lds128(sha + 2048u + (uint32_t)i * 32u + 16u);
+                  const float4 u0 = make_float4(__uint_as_float(ua.x), __uint_as_float(ua.y), __uint_as_float(ua.z), __uint_as_float(ua.w));
+                  const float4 u1 = make_float4(__uint_as_float(ub.x), __uint_as_float(ub.y), __uint_as_float(ub.z), __uint_as_float(ub.w));
+                  tacc1 += y[0] * u0.x + y[1] * u0.y + y[2] * u0.z + y[3] * u0.w + y[4] * u1.x + y[5] * u1.y + y[6] * u1.z + y[7] * u1.w;
+                }
+              }
             }
+            if (store_main) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) sts128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4), ov[k]);
+              for (int k = 0; k < 2; ++k) sts128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4), ov[k]);
+            }
           }
         }
 #pragma unroll
@@ -1033,12 +1064,13 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               }
             }
             // fp32 NCHW export: box {bw, bh, 32 channels, 1} of the map {W, H, C, N}; the TMA unit clips image edges / channel tail
-            if (aux_tma) tma_store_4d(&tmAux, aux_base + g * kAuxStagingBytes, it.x0, it.y0, ch0, it.img);
+            if (aux_tma) tma_store_4d(&tmAux, aux_tile, it.x0, it.y0, ch0, it.img);
             tma_commit();
           }
         }
         HIS_TS(tsb + 6);
         if (!direct) ++cc;
+        if (aux_tma) ++ac;
       }
       HIS_TS(24);
       ++ts_tile;
