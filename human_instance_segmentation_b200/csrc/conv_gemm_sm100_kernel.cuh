@@ -815,16 +815,26 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int i = te; i < p.block_n; i += 128) s_rsc[i] = (chbase + i < p.cout) ? __ldg(rsrc + i) : 0.0f;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
+      // several N tiles: the tile's slice of the shift vector goes to the group's (free) residual-scale row
+      const bool shift_stage = !SPLIT && p.n_tiles > 1 && !has_rsc && !p.ln_partials && !(p.debug & 32);
+      if (shift_stage) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        for (int i = te; i < p.block_n; i += 128) s_rsc[i] = __ldg(p.shift + chbase + i);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      }
+      const uint32_t sha0 = shift_stage ? shift_base + (uint32_t)(1 + g) * 1024u : shift_base;
       float st_sum = 0.0f, st_max = -INFINITY;
       float ln_s = 0.0f, ln_q = 0.0f;
       // Straight-line chunk body for the common case (plain fp16 store of a full 32-channel chunk through the staging buffer, no
       // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
       // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
       // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
-      const bool fast_tile = !SPLIT && p.n_tiles == 1 && !p.stats_out && !p.ln_partials && !has_rsc && !res_glob && !(p.debug & 32) &&
+      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !p.stats_out && !p.ln_partials && !has_rsc && !res_glob && !(p.debug & 32) &&
                              (EPI != EPI_TAIL || tail_smem) && (EPI != EPI_AUX || p.aux_tma);
       // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
-      const bool res_early = RES && !SPLIT && !res_glob && !(p.debug & 64);
+      // (needs a group barrier inside every staged chunk -- the one before the chunk's store -- so that no warp runs ahead of the
+      // group by more than a chunk: a tail-only layer (store_main == 0) has none and keeps the loads at the top of the chunks)
+      const bool res_early = RES && !SPLIT && !res_glob && !(p.debug & 64) && (store_main || (EPI == EPI_AUX && p.aux_tma));
       HIS_TS(2);
       for (int j = 0; j < nchunks; ++j) {
         const bool direct = j >= ntma;
@@ -840,7 +850,12 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (aux_tma && issuer_warp && elect_one()) { if (p.aux_bufs > 1) tma_wait_read<1>(); else tma_wait_read<0>(); }
         const uint32_t aux_tile = aux_base + (uint32_t)(g * p.aux_bufs + (p.aux_bufs > 1 ? (int)(ac & 1u) : 0)) * kAuxStagingBytes;
         if (direct && aux_tma) asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-        if (!direct) {
+        // Staging hand-over.  lean: every chunk's issuer drains the earlier stores BEFORE the barrier that precedes its own store
+        // (see below; residual chunks: before the next chunk's residual load), so after that barrier the other staging buffer is
+        // known free to the whole group and a chunk starts without a wait and without a barrier.  The split / export kernels
+        // keep the wait + barrier at the top of the chunk.
+        const bool lean_sync = !SPLIT && !aux_tma && store_main && !(p.debug & 64);
+        if (!direct && !lean_sync) {
           if (SPLIT) {
             if ((!RES || res_glob || j >= 1) && issuer_warp && elect_one()) {
               tma_wait_read<0>();                  // both stores of the previous chunk have drained
@@ -887,7 +902,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const bool fast = fast_tile && !direct && ncol == kChunkC;
         if (fast) {
           const uint32_t rowa = stg + (uint32_t)te * (kChunkC * 2), sw = (uint32_t)(te >> 1) & 3u;     // SWIZZLE_64B row of this pixel
-          const uint32_t sha = shift_base + (uint32_t)cl0 * 4u;
+          const uint32_t sha = sha0 + (uint32_t)cl0 * 4u;
           // two halves of 16 channels: all shared-memory loads of a half first (the volatile accesses keep their program order, so
           // loads placed after a store would wait for it), then the math, then the stores
 #pragma unroll
@@ -1045,6 +1060,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
         HIS_TS(tsb + 4);
+        if (lean_sync && store_main && !direct && !(RES && !res_glob) && issuer_warp && elect_one()) tma_wait_read<0>();
         if ((store_main && !direct) || aux_tma) {
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
