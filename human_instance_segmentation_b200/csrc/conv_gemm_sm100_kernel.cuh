@@ -42,7 +42,8 @@ constexpr int kBlockM = 128;
 constexpr int kChunkC = 32;                            // output channels per epilogue chunk
 constexpr int kStagingBytes = kBlockM * kChunkC * 2;   // 8 KB : 128 rows x 32 channels fp16 (SWIZZLE_64B rows)
 constexpr int kMaxEpiGroups = 3;                       // epilogue warpgroups: 2 (384 threads) or 3 (512 threads), see ConvGemmParams::epi_groups
-constexpr int kShiftBytes = (1 + kMaxEpiGroups) * 256 * 4;   // per-channel shift of the (single) N tile + one residual-scale row per epilogue group
+constexpr int kShiftBytes = (1 + kMaxEpiGroups + 2) * 256 * 4;   // per-channel shift of the (single) N tile, one residual-scale row per epilogue
+                                                                 // group, two weight rows of a fused 1x1 tail
 constexpr int kThreadsGemm = 128 + 128 * kMaxEpiGroups;      // launch bound; a plan launches 128 + 128 * epi_groups threads
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 48;
@@ -105,6 +106,7 @@ struct ConvGemmParams {
   int pair;             // 1: CTA pairs (cluster of 2) run cta_group::2 MMAs, M = 256 pixels x block_n, each CTA stages half of the weight tile
   int debug;            // HIS_GEMM_DEBUG bit mask (tuning experiments only): 1 no epilogue stores, 2 no A loads, 4 no B loads, 8 no MMAs,
                         // 16 epilogue time stamps, 32 general chunk body everywhere, 64 residual chunks loaded at the top of their own chunk
+                        // + wait / barrier at the top of every chunk, 128 general body for tiles with a residual scale
   // activation, compile-time class + runtime parameters:
   //   CLAMP:   y = max(y, act_lo)                  (none: -inf, relu: 0)
   //   SIGMOID: s = 1/(1+exp(-act_beta*y)); y = act_mul_x ? y*s : s   (sigmoid / silu / swish(beta))
@@ -456,11 +458,12 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   float* s_shift = reinterpret_cast<float*>(smem_gen + (shift_base - smem_base));
   if (p.n_tiles == 1)
     for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) s_shift[i] = __ldg(p.shift + (p.phase_merge > 1 ? i % p.phase_slab : i));
-  // fused 1x1 tail: its weight rows live in the (otherwise unused) residual-scale rows 0 / 1 of the shift block
-  const bool tail_smem = EPI == EPI_TAIL && p.n_tiles == 1 && !p.res_scale && !p.ln_partials;
+  // fused 1x1 tail: its weight rows live in rows 4 / 5 of the shift block
+  constexpr uint32_t kTailRow = (1 + kMaxEpiGroups) * 1024;       // byte offset of tail row 0 from the shift row
+  const bool tail_smem = EPI == EPI_TAIL && p.n_tiles == 1;
   if (tail_smem)
     for (int i = threadIdx.x; i < p.tail_c * p.cout_slab; i += blockDim.x)
-      s_shift[256 + (i / p.cout_slab) * 256 + (i % p.cout_slab)] = __ldg(p.tail_w + i);
+      s_shift[(1 + kMaxEpiGroups) * 256 + (i / p.cout_slab) * 256 + (i % p.cout_slab)] = __ldg(p.tail_w + i);
   tc_fence_before();
   __syncthreads();
   if (pair) cluster_sync_all();        // the peer's barriers are initialised and its TMEM is allocated before anything remote happens
@@ -829,12 +832,13 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
       // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
       // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
-      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !p.stats_out && !p.ln_partials && !has_rsc && !res_glob && !(p.debug & 32) &&
+      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !p.stats_out && !p.ln_partials && !res_glob && !(p.debug & 32) &&
+                             !(has_rsc && (p.debug & 128)) &&
                              (EPI != EPI_TAIL || tail_smem) && (EPI != EPI_AUX || p.aux_tma);
       // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
-      // (needs a group barrier inside every staged chunk -- the one before the chunk's store -- so that no warp runs ahead of the
-      // group by more than a chunk: a tail-only layer (store_main == 0) has none and keeps the loads at the top of the chunks)
-      const bool res_early = RES && !SPLIT && !res_glob && !(p.debug & 64) && (store_main || (EPI == EPI_AUX && p.aux_tma));
+      // (needs a group barrier inside every staged chunk so that no warp runs ahead of the group by more than a chunk: the one
+      // before the chunk's store, or -- a tail-only layer, store_main == 0, has no store -- the one kept at the top of its chunks)
+      const bool res_early = RES && !SPLIT && !res_glob && !(p.debug & 64);
       HIS_TS(2);
       for (int j = 0; j < nchunks; ++j) {
         const bool direct = j >= ntma;
@@ -903,6 +907,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (fast) {
           const uint32_t rowa = stg + (uint32_t)te * (kChunkC * 2), sw = (uint32_t)(te >> 1) & 3u;     // SWIZZLE_64B row of this pixel
           const uint32_t sha = sha0 + (uint32_t)cl0 * 4u;
+          const uint32_t rsca = shift_base + (uint32_t)(1 + g) * 1024u + (uint32_t)cl0 * 4u;
           // two halves of 16 channels: all shared-memory loads of a half first (the volatile accesses keep their program order, so
           // loads placed after a store would wait for it), then the math, then the stores
 #pragma unroll
@@ -923,6 +928,8 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                    __uint_as_float(sv[2 * k + 1].w)};
               const __half2* rh = reinterpret_cast<const __half2*>(&rv[k]);
               __half2* o = reinterpret_cast<__half2*>(&ov[k]);
+              uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = qa;          // residual scale of the 8 channels (ChannelAttention gate)
+              if (RES && has_rsc) { qa = lds128(rsca + (uint32_t)i * 32u); qb = lds128(rsca + (uint32_t)i * 32u + 16u); }
               float y[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -930,6 +937,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 float t1 = fmaf(__uint_as_float(v[i * 8 + 2 * e + 1]), rs, sh[2 * e + 1]);
                 float2 r = make_float2(0.0f, 0.0f);
                 if (RES) r = __half22float2(rh[e]);
+                if (RES && has_rsc) { r.x *= __uint_as_float(e < 2 ? (e ? qa.z : qa.x) : (e == 2 ? qb.x : qb.z)); r.y *= __uint_as_float(e < 2 ? (e ? qa.w : qa.y) : (e == 2 ? qb.y : qb.w)); }
                 if (RES == HIS_RES_ADD) { t0 += r.x; t1 += r.y; }
                 t0 = epi_act<ACTC>(t0, p); t1 = epi_act<ACTC>(t1, p);
                 if (EPI == EPI_AUX) {      // [channel][pixel] fp32 tile: lanes write consecutive words
@@ -941,12 +949,12 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 o[e] = __floats2half2_rn(t0, t1);
               }
               if (TAIL) {
-                const uint4 wa = lds128(sha + 1024u + (uint32_t)i * 32u), wb = lds128(sha + 1024u + (uint32_t)i * 32u + 16u);
+                const uint4 wa = lds128(sha + kTailRow + (uint32_t)i * 32u), wb = lds128(sha + kTailRow + (uint32_t)i * 32u + 16u);
                 const float4 w0 = make_float4(__uint_as_float(wa.x), __uint_as_float(wa.y), __uint_as_float(wa.z), __uint_as_float(wa.w));
                 const float4 w1 = make_float4(__uint_as_float(wb.x), __uint_as_float(wb.y), __uint_as_float(wb.z), __uint_as_float(wb.w));
                 tacc0 += y[0] * w0.x + y[1] * w0.y + y[2] * w0.z + y[3] * w0.w + y[4] * w1.x + y[5] * w1.y + y[6] * w1.z + y[7] * w1.w;
                 if (p.tail_c > 1) {
-                  const uint4 ua = lds128(sha + 2048u + (uint32_t)i * 32u), ub = lds128(sha + 2048u + (uint32_t)i * 32u + 16u);
+                  const uint4 ua = lds128(sha + kTailRow + 1024u + (uint32_t)i * 32u), ub = lds128(sha + kTailRow + 1024u + (uint32_t)i * 32u + 16u);
                   const float4 u0 = make_float4(__uint_as_float(ua.x), __uint_as_float(ua.y), __uint_as_float(ua.z), __uint_as_float(ua.w));
                   const float4 u1 = make_float4(__uint_as_float(ub.x), __uint_as_float(ub.y), __uint_as_float(ub.z), __uint_as_float(ub.w));
                   tacc1 += y[0] * u0.x + y[1] * u0.y + y[2] * u0.z + y[3] * u0.w + y[4] * u1.x + y[5] * u1.y + y[6] * u1.z + y[7] * u1.w;
