@@ -832,7 +832,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
       // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
       // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
-      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !p.stats_out && !p.ln_partials && !res_glob && !(p.debug & 32) &&
+      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !(p.ln_partials && p.phase_merge > 1) && !res_glob && !(p.debug & 32) &&
                              !(has_rsc && (p.debug & 128)) &&
                              (EPI != EPI_TAIL || tail_smem) && (EPI != EPI_AUX || p.aux_tma);
       // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
@@ -947,6 +947,18 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if (RES == HIS_RES_MUL) { t0 *= r.x; t1 *= r.y; }
                 y[2 * e] = t0; y[2 * e + 1] = t1;
                 o[e] = __floats2half2_rn(t0, t1);
+              }
+              if (p.stats_out) {        // per-pixel channel mean / max (every channel of a full chunk is a real one)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { st_sum += y[e]; st_max = fmaxf(st_max, y[e]); }
+              }
+              if (p.ln_partials && inb) {      // LayerNorm2d sums over the fp16-rounded values the normalise pass will read
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 hh = __half22float2(o[e]);
+                  ln_s += hh.x; ln_q = fmaf(hh.x, hh.x, ln_q);
+                  ln_s += hh.y; ln_q = fmaf(hh.y, hh.y, ln_q);
+                }
               }
               if (TAIL) {
                 const uint4 wa = lds128(sha + kTailRow + (uint32_t)i * 32u), wb = lds128(sha + kTailRow + (uint32_t)i * 32u + 16u);
