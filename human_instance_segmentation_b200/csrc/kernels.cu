@@ -1002,18 +1002,114 @@ __global__ void ln_apply_kernel(const __half* __restrict__ in, int HW, int C, in
                                 int in_lo, int res_lo, int out_lo) {
   __shared__ float s_mu, s_rstd;
   const int n = blockIdx.y, cgs = C / 8;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // fixed order whatever the batch: lane l adds parts l, l + 32, ... in sequence, then a butterfly over the lanes
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < nparts; ++i) { s += partials[((long long)n * nparts + i) * 2]; q += partials[((long long)n * nparts + i) * 2 + 1]; }
-    const double cnt = (double)HW * (double)C;
-    const double mu = s / cnt;
-    double var = q / cnt - mu * mu;
-    if (var < 0.0) var = 0.0;
-    s_mu = (float)mu; s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int i = threadIdx.x; i < nparts; i += 32) { s += partials[((long long)n * nparts + i) * 2]; q += partials[((long long)n * nparts + i) * 2 + 1]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (threadIdx.x == 0) {
+      const double cnt = (double)HW * (double)C;
+      const double mu = s / cnt;
+      double var = q / cnt - mu * mu;
+      if (var < 0.0) var = 0.0;
+      s_mu = (float)mu; s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
   const float mu = s_mu, rstd = s_rstd;
   const long long per_img_vec = (long long)HW * cgs;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  if (nthreads % cgs == 0 && in_lo == 0 && out_lo == 0 && res_lo == 0) {
+    // plain fp16 tensors: four pixels of the thread's channel group in flight as raw 16-byte vectors (the kernel is a pure HBM
+    // stream; with ~70 registers three blocks fit an SM, so the bytes in flight have to come from the unroll)
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int cg = (int)(t % cgs);
+    const int pstep = (int)(nthreads / cgs);
+    float gm[8], bt[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { gm[e] = __ldg(gamma + cg * 8 + e); bt[e] = __ldg(beta + cg * 8 + e); }
+    const __half* inp = in + (long long)n * HW * cs + cg * 8;
+    const __half* resp = res_mode ? res + (long long)n * HW * res_cs + cg * 8 : nullptr;
+    __half* outp = out + (long long)n * HW * out_cs + cg * 8;
+    for (int pix = (int)(t / cgs); pix < HW; pix += 4 * pstep) {
+      uint4 a[4], r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pu = pix + u * pstep;
+        a[u] = make_uint4(0u, 0u, 0u, 0u); r[u] = a[u];
+        if (pu < HW) {
+          a[u] = __ldg(reinterpret_cast<const uint4*>(inp + (long long)pu * cs));
+          if (res_mode) r[u] = __ldg(reinterpret_cast<const uint4*>(resp + (long long)pu * res_cs));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pu = pix + u * pstep;
+        if (pu < HW) {
+          const __half2* ah = reinterpret_cast<const __half2*>(&a[u]);
+          const __half2* rh = reinterpret_cast<const __half2*>(&r[u]);
+          __half2 o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(ah[e]), rr = __half22float2(rh[e]);
+            float y0 = (f.x - mu) * rstd * gm[2 * e] + bt[2 * e], y1 = (f.y - mu) * rstd * gm[2 * e + 1] + bt[2 * e + 1];
+            if (res_mode == HIS_RES_ADD) { y0 += rr.x; y1 += rr.y; }
+            y0 = his_act(y0, act, act_beta); y1 = his_act(y1, act, act_beta);
+            if (res_mode == HIS_RES_MUL) { y0 *= rr.x; y1 *= rr.y; }
+            o[e] = __floats2half2_rn(y0, y1);
+          }
+          *reinterpret_cast<uint4*>(outp + (long long)pu * out_cs) = *reinterpret_cast<const uint4*>(o);
+        }
+      }
+    }
+    return;
+  }
+  if (nthreads % cgs == 0) {
+    // the grid stride is a multiple of the channel-vector count (the host sizes the grid so): a thread keeps ONE 8-channel group for
+    // all its pixels -- gamma / beta live in registers, no 64-bit division per vector, two independent pixels in flight
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int cg = (int)(t % cgs);
+    const int pstep = (int)(nthreads / cgs);
+    float gm[8], bt[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { gm[e] = __ldg(gamma + cg * 8 + e); bt[e] = __ldg(beta + cg * 8 + e); }
+    const __half* inp = in + (long long)n * HW * cs + cg * 8;
+    const __half* resp = res_mode ? res + (long long)n * HW * res_cs + cg * 8 : nullptr;
+    __half* outp = out + (long long)n * HW * out_cs + cg * 8;
+    for (int pix = (int)(t / cgs); pix < HW; pix += 2 * pstep) {
+      const int pix1 = pix + pstep;
+      const bool two = pix1 < HW;
+      float f0[8], f1[8], r0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      his_ld8(inp + (long long)pix * cs, in_lo, f0);
+      if (two) his_ld8(inp + (long long)pix1 * cs, in_lo, f1);
+      if (res_mode) {
+        his_ld8(resp + (long long)pix * res_cs, res_lo, r0);
+        if (two) his_ld8(resp + (long long)pix1 * res_cs, res_lo, r1);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float y = (f0[e] - mu) * rstd * gm[e] + bt[e];
+        if (res_mode == HIS_RES_ADD) y += r0[e];
+        y = his_act(y, act, act_beta);
+        if (res_mode == HIS_RES_MUL) y *= r0[e];
+        f0[e] = y;
+      }
+      his_st8(outp + (long long)pix * out_cs, out_lo, f0);
+      if (two) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float y = (f1[e] - mu) * rstd * gm[e] + bt[e];
+          if (res_mode == HIS_RES_ADD) y += r1[e];
+          y = his_act(y, act, act_beta);
+          if (res_mode == HIS_RES_MUL) y *= r1[e];
+          f1[e] = y;
+        }
+        his_st8(outp + (long long)pix1 * out_cs, out_lo, f1);
+      }
+    }
+    return;
+  }
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img_vec; idx += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(idx % cgs);
     const long long pix = (long long)n * HW + idx / cgs;
@@ -1947,10 +2043,18 @@ int his_layernorm2d_act(const void* in, int N, int HW, int C, int in_cs, const f
   dim3 g1(parts, N);
   if (nparts_given <= 0)
     ln_stats_kernel<<<g1, kThreads, 0, ST>>>((const __half*)in, per_img_vec, HW, C, in_cs, split ? in_cs / 2 : 0, partials_ws);
-  long long gx = (per_img_vec + kThreads - 1) / kThreads;
+  long long gx = (per_img_vec + 4 * kThreads - 1) / (4 * kThreads);      // up to four vectors per thread and pass
   const long long cap = (148LL * 16 + N - 1) / N;
   if (gx > cap) gx = cap;
-  dim3 g2((int)(gx < 1 ? 1 : gx), N);
+  if (gx < 1) gx = 1;
+  {   // grid stride a multiple of the channel-vector count: every thread of ln_apply_kernel keeps one 8-channel group
+    const int cgs = C / 8;
+    int a = cgs, b = kThreads;
+    while (b) { const int t = a % b; a = b; b = t; }
+    const int m = cgs / a;                                  // blocks per period
+    gx = (gx + m - 1) / m * m;
+  }
+  dim3 g2((int)gx, N);
   ln_apply_kernel<<<g2, kThreads, 0, ST>>>((const __half*)in, HW, C, in_cs, partials_ws, parts, gamma, beta, eps, act, act_beta, res_mode,
                                           (const __half*)res, res_cs, (__half*)out, out_cs, split ? in_cs / 2 : 0, split ? res_cs / 2 : 0,
                                           split ? out_cs / 2 : 0);
