@@ -832,7 +832,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
       // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
       // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
-      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !(p.ln_partials && p.phase_merge > 1) && !res_glob && !(p.debug & 32) &&
+      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !(p.ln_partials && ((p.phase_merge > 1 && p.phase_slab != p.cout) || (!p.direct_ok && (p.cout % kChunkC) != 0))) && !res_glob && !(p.debug & 32) &&
                              !(has_rsc && (p.debug & 128)) &&
                              (EPI != EPI_TAIL || tail_smem) && (EPI != EPI_AUX || p.aux_tma);
       // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
