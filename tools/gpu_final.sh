@@ -1,12 +1,12 @@
 #!/bin/bash
 # Measurement pass of round 2: tests, the bench line (all sub-records) + reference arm, per-workload breakdowns, ncu launch list +
 # DRAM traffic of one B0 step, ncu --set full of the kernels under study.  Everything lands in gpurun_out/${P}_* (P = prefix).
-P=${1:-r2f}
+P=${1:-r2g}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${P}_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${P}_tests.log; tail -3 gpurun_out/${P}_tests.log
 timeout 600 python bench.py --steps 5 --warmup 3 --breakdown --top 400 > gpurun_out/${P}_bench_b0.json 2> gpurun_out/${P}_bench_b0_breakdown.txt; cut -c1-160 gpurun_out/${P}_bench_b0.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${P}_bench_ref.json 2> /dev/null; cut -c1-200 gpurun_out/${P}_bench_ref.json
-for w in b1 b7 b0_160x120; do timeout 300 python bench.py --steps 3 --warmup 3 --workload $w --no-cpu-baseline --breakdown > gpurun_out/${P}_bench_$w.json 2> gpurun_out/${P}_bench_${w}_breakdown.txt; cut -c1-160 gpurun_out/${P}_bench_$w.json; done
+for w in b1 b7 b0_160x120 b0_ln; do timeout 300 python bench.py --steps 3 --warmup 3 --workload $w --no-cpu-baseline --breakdown > gpurun_out/${P}_bench_$w.json 2> gpurun_out/${P}_bench_${w}_breakdown.txt; cut -c1-160 gpurun_out/${P}_bench_$w.json; done
 timeout 300 python bench.py --steps 3 --warmup 3 --precision strict --quick --no-cpu-baseline --breakdown > gpurun_out/${P}_bench_strict.json 2> gpurun_out/${P}_bench_strict_breakdown.txt; cut -c1-160 gpurun_out/${P}_bench_strict.json
 timeout 300 python bench.py --workload post --steps 5 --warmup 3 > gpurun_out/${P}_bench_post.json 2> /dev/null; cut -c1-160 gpurun_out/${P}_bench_post.json
 # one step under ncu: launch durations + DRAM bytes (graph replay off so that every kernel is a separate launch record)
