@@ -819,7 +819,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
       }
       // several N tiles: the tile's slice of the shift vector goes to the group's (free) residual-scale row
-      const bool shift_stage = !SPLIT && p.n_tiles > 1 && !has_rsc && !p.ln_partials && !(p.debug & 32);
+      const bool shift_stage = p.n_tiles > 1 && !has_rsc && !p.ln_partials && !(p.debug & 32);
       if (shift_stage) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         for (int i = te; i < p.block_n; i += 128) s_rsc[i] = __ldg(p.shift + chbase + i);
@@ -832,7 +832,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // per-pixel statistics / LayerNorm sums / residual scale): one warp per scheduler runs this code, so what bounds a chunk is
       // the dependent-issue latency of its instruction stream -- the general body below is four branchy 8-channel blocks the
       // compiler cannot interleave (measured 1 150 - 2 000 clk per chunk of a 256-wide layer against ~110 clk for the TMEM load).
-      const bool fast_tile = !SPLIT && (p.n_tiles == 1 || shift_stage) && !(p.ln_partials && ((p.phase_merge > 1 && p.phase_slab != p.cout) || (!p.direct_ok && (p.cout % kChunkC) != 0))) && !res_glob && !(p.debug & 32) &&
+      const bool fast_tile = (p.n_tiles == 1 || shift_stage) && !(p.ln_partials && ((p.phase_merge > 1 && p.phase_slab != p.cout) || (!p.direct_ok && (p.cout % kChunkC) != 0))) && !res_glob && !(p.debug & 32) &&
                              !(has_rsc && (p.debug & 128)) &&
                              (EPI != EPI_TAIL || tail_smem) && (EPI != EPI_AUX || p.aux_tma);
       // residual operand (not SPLIT): the load of chunk j+1 is issued from the middle of chunk j (see below) instead of the top of j+1
@@ -912,14 +912,15 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           // loads placed after a store would wait for it), then the math, then the stores
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint4 rv[2], sv[4];
+            uint4 rv[2], rl[2], sv[4];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               if (RES) rv[k] = lds128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4));
+              if (RES && SPLIT) rl[k] = lds128(rowa + kStagingBytes + (((uint32_t)(2 * h + k) ^ sw) << 4));      // lo plane of the residual
               sv[2 * k] = lds128(sha + (uint32_t)(2 * h + k) * 32u);
               sv[2 * k + 1] = lds128(sha + (uint32_t)(2 * h + k) * 32u + 16u);
             }
-            uint4 ov[2];
+            uint4 ov[2], ol[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const int i = 2 * h + k;
@@ -927,7 +928,9 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                    __uint_as_float(sv[2 * k + 1].x), __uint_as_float(sv[2 * k + 1].y), __uint_as_float(sv[2 * k + 1].z),
                                    __uint_as_float(sv[2 * k + 1].w)};
               const __half2* rh = reinterpret_cast<const __half2*>(&rv[k]);
+              const __half2* rlh = reinterpret_cast<const __half2*>(&rl[k]);
               __half2* o = reinterpret_cast<__half2*>(&ov[k]);
+              __half2* olo = reinterpret_cast<__half2*>(&ol[k]);
               uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = qa;          // residual scale of the 8 channels (ChannelAttention gate)
               if (RES && has_rsc) { qa = lds128(rsca + (uint32_t)i * 32u); qb = lds128(rsca + (uint32_t)i * 32u + 16u); }
               float y[8];
@@ -937,6 +940,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 float t1 = fmaf(__uint_as_float(v[i * 8 + 2 * e + 1]), rs, sh[2 * e + 1]);
                 float2 r = make_float2(0.0f, 0.0f);
                 if (RES) r = __half22float2(rh[e]);
+                if (RES && SPLIT) { const float2 q2 = __half22float2(rlh[e]); r.x += q2.x; r.y += q2.y; }
                 if (RES && has_rsc) { r.x *= __uint_as_float(e < 2 ? (e ? qa.z : qa.x) : (e == 2 ? qb.x : qb.z)); r.y *= __uint_as_float(e < 2 ? (e ? qa.w : qa.y) : (e == 2 ? qb.y : qb.w)); }
                 if (RES == HIS_RES_ADD) { t0 += r.x; t1 += r.y; }
                 t0 = epi_act<ACTC>(t0, p); t1 = epi_act<ACTC>(t1, p);
@@ -947,6 +951,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if (RES == HIS_RES_MUL) { t0 *= r.x; t1 *= r.y; }
                 y[2 * e] = t0; y[2 * e + 1] = t1;
                 o[e] = __floats2half2_rn(t0, t1);
+                if (SPLIT) { const float2 hh = __half22float2(o[e]); olo[e] = __floats2half2_rn(t0 - hh.x, t1 - hh.y); }     // lo = fp16(y - hi)
               }
               if (p.stats_out) {        // per-pixel channel mean / max (every channel of a full chunk is a real one)
 #pragma unroll
@@ -955,7 +960,7 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               if (p.ln_partials && inb) {      // LayerNorm2d sums over the fp16-rounded values the normalise pass will read
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float2 hh = __half22float2(o[e]);
+                  const float2 hh = SPLIT ? make_float2(y[2 * e], y[2 * e + 1]) : __half22float2(o[e]);      // split: hi + lo ~ y itself
                   ln_s += hh.x; ln_q = fmaf(hh.x, hh.x, ln_q);
                   ln_s += hh.y; ln_q = fmaf(hh.y, hh.y, ln_q);
                 }
@@ -975,7 +980,10 @@ conv_gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
             if (store_main) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) sts128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4), ov[k]);
+              for (int k = 0; k < 2; ++k) {
+                sts128(rowa + (((uint32_t)(2 * h + k) ^ sw) << 4), ov[k]);
+                if (SPLIT) sts128(rowa + kStagingBytes + (((uint32_t)(2 * h + k) ^ sw) << 4), ol[k]);
+              }
             }
           }
         }
