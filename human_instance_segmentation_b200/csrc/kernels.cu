@@ -826,24 +826,28 @@ __global__ void __launch_bounds__(kDw2Threads) depthwise_split_kernel(const DwPa
 __global__ void pool_sum_kernel(const __half* __restrict__ in, int HW, int C, int cs, int lo, float* __restrict__ pool) {
   extern __shared__ float s_pool[];
   const int n = blockIdx.y, cgs = C / 8;
-  const long long per_img = (long long)HW * cgs;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long step = (long long)gridDim.x * blockDim.x;
   const __half* img = in + (long long)n * HW * cs;
-  auto addr = [&](long long i) { return reinterpret_cast<const uint4*>(img + (i / cgs) * cs + (int)(i % cgs) * 8); };
+  // blockDim.x is a multiple of cgs (threads_multiple_of), so a thread keeps ONE channel group and walks pixels with a constant
+  // stride: one division up front instead of a 64-bit divide + modulo per 16-byte load (same elements, same order as idx += step)
+  const long long idx0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cg0 = (int)(idx0 % cgs);
+  const long long pix0 = idx0 / cgs, pstep = step / cgs;
+  auto addr = [&](long long p) { return reinterpret_cast<const uint4*>(img + p * cs + cg0 * 8); };
   auto add = [&](const uint4& xv) {
     const __half2* xh = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(xh[e]); acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
   };
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  for (; idx + 3 * step < per_img; idx += 4 * step) {      // four loads in flight; the per-thread summation order is unchanged
-    const uint4 v0 = __ldg(addr(idx)), v1 = __ldg(addr(idx + step)), v2 = __ldg(addr(idx + 2 * step)), v3 = __ldg(addr(idx + 3 * step));
+  long long pix = pix0;
+  for (; pix + 3 * pstep < HW; pix += 4 * pstep) {      // four loads in flight; the per-thread summation order is unchanged
+    const uint4 v0 = __ldg(addr(pix)), v1 = __ldg(addr(pix + pstep)), v2 = __ldg(addr(pix + 2 * pstep)), v3 = __ldg(addr(pix + 3 * pstep));
     add(v0); add(v1); add(v2); add(v3);
   }
-  for (; idx < per_img; idx += step) add(__ldg(addr(idx)));
+  for (; pix < HW; pix += pstep) add(__ldg(addr(pix)));
   if (lo)      // split-fp16 input: the lo planes of the same pixels (their sum is ~2^-11 of the total: order is immaterial)
-    for (idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_img; idx += step) add(__ldg(addr(idx) + (lo >> 3)));
+    for (pix = pix0; pix < HW; pix += pstep) add(__ldg(addr(pix) + (lo >> 3)));
 #pragma unroll
   for (int e = 0; e < 8; ++e) s_pool[threadIdx.x * 8 + e] = acc[e];
   __syncthreads();
