@@ -281,6 +281,14 @@ int his_conv_gemm_create(void** out_plan,
   p.in_lo = split ? in_cs / 2 : 0; p.out_lo = split ? out_cs / 2 : 0; p.res_lo = split ? res_cs / 2 : 0; p.up_lo = 0;
   pl->split = split;
   his_conv_gemm_tile_n(cout, &p.n_tiles, &p.block_n);
+  // A 1x1 layer with a 256-wide N tile runs as two 128-wide N tiles (same packed weights: the slab stays 256 rows), and a
+  // ConvTranspose with 128-wide phases keeps its four phase groups instead of merging two per tile, so that THREE epilogue groups
+  // fit the accumulator ring (3 x 128 columns): these layers are bound by the drain rate of two groups (8 chunks of ~1 350 clk per
+  // 256-wide tile), not by HBM; A is read twice, the second time from L2.  Measured: ConvT 256->128 0.997 -> 0.811 ms, gate layer
+  // 0.644 -> 0.575, 256->256 0.442 -> 0.427.  HIS_GEMM_K1_SPLITN=0 restores the 256-wide tiles.
+  int k1_split = 1;
+  if (const char* e = getenv("HIS_GEMM_K1_SPLITN")) k1_split = atoi(e);
+  if (k1_split && ksize == 1 && !split && p.n_tiles == 1 && p.block_n == 256 && !transposed) { p.n_tiles = 2; p.block_n = 128; }
   p.groups = transposed ? 4 : 1;
   p.cout_slab = p.n_tiles * p.block_n;
   p.phase_merge = 1; p.phase_slab = p.block_n;
@@ -289,6 +297,7 @@ int his_conv_gemm_create(void** out_plan,
     // weight rows of the phases are contiguous, so the slab layout does not change).  HIS_GEMM_CONVT_MERGE=0 keeps four groups.
     int merge = 256 / p.block_n >= 4 ? 4 : 256 / p.block_n >= 2 ? 2 : 1;
     if (const char* e = getenv("HIS_GEMM_CONVT_MERGE")) if (atoi(e) == 0) merge = 1;
+    if (k1_split && !split && p.block_n == 128) merge = 1;
     if (merge > 1) {
       p.phase_merge = merge; p.block_n *= merge; p.groups = 4 / merge; p.cout_slab = p.block_n;
     }
@@ -331,7 +340,7 @@ int his_conv_gemm_create(void** out_plan,
   p.fast_decode = (p.n_tiles == 1 && p.groups == 1 && p.num_work < (1 << 21)) ? 1 : 0;
   // a third epilogue warpgroup for the layers bound by the epilogue's per-tile latency: narrow N tiles and the 1x1 convs
   // (HIS_GEMM_EPI=2|3 forces the count; pair kernels keep two)
-  p.epi_groups = (p.block_n <= 96 || (ksize == 1 && cin <= 112)) ? 3 : 2;
+  p.epi_groups = (p.block_n <= 96 || (ksize == 1 && cin <= 112) || (k1_split && ksize == 1 && !split && p.block_n == 128 && (p.n_tiles > 1 || transposed))) ? 3 : 2;
   if (const char* e = getenv("HIS_GEMM_EPI")) { const int v = atoi(e); if (v == 2 || v == 3) p.epi_groups = v; }
   // every accumulator must always be drained by the SAME group (a group that met an accumulator first at its second use would
   // pass the parity wait of the still untouched barrier): the ring length is a multiple of the group count

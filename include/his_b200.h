@@ -87,6 +87,7 @@ int his_conv_gemm_create(void** plan, const void* in, int n_img, int H, int W, i
  *   window), HIS_GEMM_TAPS=1|3|9 (taps per weight stage), HIS_GEMM_ASTAGES / HIS_GEMM_STAGES (ring depths), HIS_GEMM_BRES=0
  *   (no resident weights), HIS_GEMM_NACC (TMEM accumulator ring), HIS_GEMM_DIRECT=0..3 (register->global epilogue policy),
  *   HIS_GEMM_FUSE_UP=0 (no fused nearest upsample), HIS_GEMM_AUX_BUFS=1|2 (fp32 export tiles per epilogue group),
+ *   HIS_GEMM_K1_SPLITN=0 (256-wide N tiles for 1x1 layers / merged ConvTranspose phases, two epilogue groups),
  *   HIS_GEMM_DEBUG (bit mask: 1 / 2 / 4 / 8 skip stores / A loads / B loads / MMAs, 16 epilogue clock stamps printed to stderr when
  *   the plan is destroyed, 32 general chunk body everywhere, 64 wait + barrier at the top of every chunk and late residual loads),
  *   HIS_DW_TILED=0 (register-resident depthwise kernel). */
