@@ -145,6 +145,8 @@ struct ConvGemmPlan {
   CUtensorMap tmA, tmB, tmO[4], tmR, tmAux;
   ConvGemmParams p;
   int grid, bk, smem, actc, res_mode, transposed, cin_pad, halo, b_box_rows, pair_grid_checked, split;
+  int k1_split, num_sms;        // k1_split: a 256-wide 1x1 layer running as two 128-wide N tiles (see his_conv_gemm_create)
+  const void* w_packed;
   ConvGemmKernel kernel;
 };
 
@@ -288,7 +290,8 @@ int his_conv_gemm_create(void** out_plan,
   // 0.644 -> 0.575, 256->256 0.442 -> 0.427.  HIS_GEMM_K1_SPLITN=0 restores the 256-wide tiles.
   int k1_split = 1;
   if (const char* e = getenv("HIS_GEMM_K1_SPLITN")) k1_split = atoi(e);
-  if (k1_split && ksize == 1 && !split && p.n_tiles == 1 && p.block_n == 256 && !transposed) { p.n_tiles = 2; p.block_n = 128; }
+  pl->k1_split = 0; pl->w_packed = w_packed; pl->num_sms = num_sms;
+  if (k1_split && ksize == 1 && !split && p.n_tiles == 1 && p.block_n == 256 && !transposed) { p.n_tiles = 2; p.block_n = 128; pl->k1_split = 1; }
   p.groups = transposed ? 4 : 1;
   p.cout_slab = p.n_tiles * p.block_n;
   p.phase_merge = 1; p.phase_slab = p.block_n;
@@ -441,11 +444,32 @@ int his_conv_gemm_create(void** out_plan,
   return HIS_OK;
 }
 
+// The fused tail and the per-pixel statistics need the whole channel range in ONE N tile: a 1x1 layer that was split into two
+// 128-wide tiles goes back to its 256-wide tile (two epilogue groups, accumulator ring of two) -- before anything that depends on
+// the work-item count or the ring depth was attached to the plan.
+static int unsplit_k1(ConvGemmPlan* pl, const char* who) {
+  if (!pl->k1_split) return HIS_OK;
+  ConvGemmParams& p = pl->p;
+  if (p.aux_out || p.ln_partials) return his_set_error(HIS_ERR_UNSUPPORTED, who);
+  p.n_tiles = 1; p.block_n = 256; p.cout_slab = 256; p.phase_slab = 256;
+  p.num_work = p.n_img * p.tiles_y * p.tiles_x;
+  p.acc_stride = 256; p.n_acc = 2; p.epi_groups = 2;
+  p.fast_decode = p.num_work < (1 << 21) ? 1 : 0;
+  p.stage_bytes = (kBlockM * pl->bk * 2 + 256 * pl->bk * 2 + 1023) / 1024 * 1024;
+  p.stages = KCfg<64>::kRingBytes / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  pl->b_box_rows = 256;
+  pl->grid = p.num_work < pl->num_sms ? p.num_work : pl->num_sms;
+  pl->k1_split = 0;
+  return encode_weight_map(&pl->tmB, pl->w_packed, pl->cin_pad, (long long)p.cout_slab, pl->b_box_rows, pl->bk);
+}
+
 int his_conv_gemm_set_tail(void* plan, const float* tail_w, float tail_b0, float tail_b1, int tail_c, int tail_sigmoid, float* tail_out,
                            int store_main) {
   if (!plan || !tail_w || !tail_out) return his_set_error(HIS_ERR_INVALID_ARG, "set_tail: null pointer");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
   if (tail_c < 1 || tail_c > 2) return his_set_error(HIS_ERR_INVALID_ARG, "set_tail: tail_c must be 1 or 2");
+  if (int rc = unsplit_k1(pl, "set_tail: attach the tail before the fp32 export / LayerNorm statistics of a 1x1 layer")) return rc;
   if (pl->p.n_tiles != 1 || pl->transposed || pl->actc != ACTC_CLAMP || pl->res_mode == HIS_RES_MUL)
     return his_set_error(HIS_ERR_UNSUPPORTED, "set_tail: needs a single N tile, none/relu activation, no MUL operand, not transposed");
   pl->p.tail_w = tail_w; pl->p.tail_b0 = tail_b0; pl->p.tail_b1 = tail_b1; pl->p.tail_c = tail_c; pl->p.tail_sigmoid = tail_sigmoid;
@@ -479,6 +503,8 @@ int his_conv_gemm_set_res_scale(void* plan, const float* res_scale) {
 int his_conv_gemm_set_row_ops(void* plan, const float* row_scale, float* stats_out) {
   if (!plan) return his_set_error(HIS_ERR_INVALID_ARG, "set_row_ops: null plan");
   ConvGemmPlan* pl = (ConvGemmPlan*)plan;
+  if (stats_out)
+    if (int rc = unsplit_k1(pl, "set_row_ops: attach the statistics before the fp32 export / LayerNorm statistics of a 1x1 layer")) return rc;
   if (stats_out && (pl->p.n_tiles != 1 || pl->transposed)) return his_set_error(HIS_ERR_UNSUPPORTED, "set_row_ops: statistics need a single N tile, not transposed");
   pl->p.row_scale = row_scale; pl->p.stats_out = stats_out;
   return HIS_OK;

@@ -86,6 +86,7 @@ CASES = {
     "tail2-res-n32-halo": dict(n=64, h=64, w=48, cin=64, cout=32, k=3, res_mode=RES_ADD, tail_c=2),
     "tail2-res-rsc-n128-pair": dict(n=48, h=64, w=48, cin=128, cout=128, k=3, res_mode=RES_ADD, tail_c=2, rsc=True),
     "res-rsc-k3-n256": dict(n=24, h=64, w=48, cin=256, cout=256, k=3, res_mode=RES_ADD, rsc=True),
+    "tail1-k1-n256": dict(n=64, h=32, w=24, cin=64, cout=256, k=1, tail_c=1),            # split 1x1 layer goes back to one N tile
     "aux-gate-k1": dict(n=64, h=64, w=48, cin=128, cout=256, k=1, act=3, res_mode=RES_MUL, aux=True),
     "aux-res-k3-pair": dict(n=24, h=64, w=48, cin=256, cout=256, k=3, res_mode=RES_ADD, aux=True),
     "aux-clipped": dict(n=9, h=60, w=44, cin=64, cout=72, k=3, aux=True),
