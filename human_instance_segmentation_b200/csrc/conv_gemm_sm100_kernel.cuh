@@ -18,7 +18,10 @@
 //    TMA store (clips partial tiles / channel tails), 32 channels at a time.  The BatchNorm scale is
 //    folded into the packed weights by the caller; the residual / multiplicand tile arrives through
 //    TMA into the same staging buffer.  Two epilogue warpgroups alternate tiles (one per TMEM
-//    accumulator), so two tiles drain concurrently while the MMAs of later tiles run.
+//    accumulator), so two tiles drain concurrently while the MMAs of later tiles run.  (Narrow layers and the 1x1 layers run three
+//    groups.)  A full chunk takes a straight-line body (ld.shared / math / st.shared per 16-channel half); the residual box of
+//    chunk j+1 is requested from the middle of chunk j; the issuer drains earlier stores before the barrier of its own store, so
+//    a chunk starts without a wait -- see the comments in the epilogue and DESIGN.md for the clock-stamp measurements behind this.
 //  * conv_transpose k2s2 = 4 independent 1x1 GEMMs ("groups"), each scattered through its own
 //    strided output tensor map (pixel (2y+dy, 2x+dx)).
 //
